@@ -1,0 +1,126 @@
+"""Import pieces of the UNMODIFIED reference from /root/reference (oracle; test infrastructure only).
+
+Only usable in the build container: /root/reference does not exist on the GPU box, so nothing in
+``-m gpu`` tests, ``smoke()`` or ``bench.py`` calls into this module.  It exists to (a) generate the
+committed golden vectors (``oracle/make_golden.py``) and (b) cross-check the restatements in the
+``-m "not gpu"`` tests when the reference happens to be present.
+
+Nothing is copied: the reference modules are imported from where they lie, with stub modules standing
+in for packages that are absent here (matplotlib; torch_mimicry).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("SDG_REFERENCE_ROOT", "/root/reference")
+REF_PKG = os.path.join(REF_ROOT, "diagan-pkg")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_PKG, "diagan"))
+
+
+def _stub(name: str, **attrs):
+    if name in sys.modules:
+        mod = sys.modules[name]
+    else:
+        mod = types.ModuleType(name)
+        sys.modules[name] = mod
+    for k, v in attrs.items():
+        setattr(mod, k, v)
+    return mod
+
+
+def _ensure_path():
+    if not available():
+        raise RuntimeError(f"reference not present at {REF_ROOT}")
+    if REF_PKG not in sys.path:
+        sys.path.insert(0, REF_PKG)
+
+
+def _stub_matplotlib():
+    try:
+        import matplotlib  # noqa: F401
+        return
+    except Exception:
+        pass
+    mpl = _stub("matplotlib")
+    plt = _stub("matplotlib.pyplot")
+    mpl.pyplot = plt
+    mpl.use = lambda *a, **k: None
+
+
+def _stub_mimicry():
+    try:
+        import torch_mimicry  # noqa: F401
+        return
+    except Exception:
+        pass
+    import torch.nn as nn
+
+    class BaseDiscriminator(nn.Module):
+        def __init__(self, ndf=None, loss_type=None, **kw):
+            super().__init__()
+            self.ndf, self.loss_type = ndf, loss_type
+
+    class BaseGenerator(nn.Module):
+        def __init__(self, nz=None, ngf=None, bottom_width=None, loss_type=None, **kw):
+            super().__init__()
+            self.nz, self.ngf, self.bottom_width, self.loss_type = nz, ngf, bottom_width, loss_type
+
+    def _loss(*a, **k):
+        raise NotImplementedError("torch_mimicry stub")
+
+    class _Placeholder(nn.Module):
+        pass
+
+    root = _stub("torch_mimicry")
+    nets = _stub("torch_mimicry.nets")
+    gan = _stub("torch_mimicry.nets.gan")
+    gan_gan = _stub("torch_mimicry.nets.gan.gan", BaseDiscriminator=BaseDiscriminator, BaseGenerator=BaseGenerator)
+    modules = _stub("torch_mimicry.modules")
+    losses = _stub("torch_mimicry.modules.losses", hinge_loss_dis=_loss, minimax_loss_dis=_loss,
+                   hinge_loss_gen=_loss, minimax_loss_gen=_loss, ns_loss_gen=_loss)
+    sn = {n: type(n, (_Placeholder,), {}) for n in
+          ("SNGANGenerator32", "SNGANGenerator64", "SNGANDiscriminator32", "SNGANDiscriminator64")}
+    info = {n: type(n, (_Placeholder,), {}) for n in
+            ("InfoMaxGANGenerator32", "InfoMaxGANGenerator64", "InfoMaxGANDiscriminator32", "InfoMaxGANDiscriminator64")}
+    ss = {n: type(n, (_Placeholder,), {}) for n in
+          ("SSGANGenerator32", "SSGANGenerator64", "SSGANDiscriminator32", "SSGANDiscriminator64")}
+    sngan = _stub("torch_mimicry.nets.sngan", **sn)
+    infomax = _stub("torch_mimicry.nets.infomax_gan", **info)
+    ssgan = _stub("torch_mimicry.nets.ssgan", **ss)
+    root.nets, root.modules = nets, modules
+    nets.gan, nets.sngan, nets.infomax_gan, nets.ssgan = gan, sngan, infomax, ssgan
+    gan.gan = gan_gan
+    modules.losses = losses
+
+
+def reference_calculate_scores():
+    """-> the reference's own ``diagan.utils.plot.calculate_scores`` (plot.py:220-249)."""
+    _ensure_path()
+    _stub_matplotlib()
+    from diagan.utils.plot import calculate_scores
+    return calculate_scores
+
+
+def reference_drs_class():
+    """-> the reference's own ``diagan.models.drs.DRS`` (drs.py:10-69)."""
+    _ensure_path()
+    _stub_mimicry()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_drs", os.path.join(REF_PKG, "diagan", "models", "drs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.DRS
+
+
+def reference_dcgan_discriminator():
+    """-> the reference's own ``MNIST_DCGAN_Discriminator`` class (mnist.py:155-223)."""
+    _ensure_path()
+    _stub_matplotlib()
+    _stub_mimicry()
+    from diagan.models.mnist import MNIST_DCGAN_Discriminator
+    return MNIST_DCGAN_Discriminator

@@ -1,0 +1,158 @@
+"""CPU/torch fp32 restatement of torch-mimicry 0.1.16 SNGAN discriminators (oracle; test infrastructure only).
+
+PARITY UNPINNED.  ``torch-mimicry==0.1.16`` (requirements.txt:72, environment.yml:122) is a
+third-party dependency that is neither vendored under /root/reference nor installable here.
+This file restates, from the published sources as recalled:
+
+* ``torch_mimicry/modules/spectral_norm.py``   SpectralNorm._power_iteration / sn_weights
+* ``torch_mimicry/modules/resblocks.py``       DBlock, DBlockOptimized
+* ``torch_mimicry/nets/sngan/sngan_32.py``     SNGANDiscriminator32
+* ``torch_mimicry/nets/sngan/sngan_64.py``     SNGANDiscriminator64
+
+Parity is anchored on the reference's own call sites: ``predefined_models.py:14,36-52,74-90``
+(construction), ``trainer.py:145-154`` (eval mode, no_grad, ``netD(x)`` -> [B,1]).
+
+Parameters are a flat dict with torch-mimicry ``state_dict`` key names
+(``block1.c1.weight``, ``block1.c1.bias``, ``block1.c1.sn_u``, ..., ``l5.weight``), so a phase-1
+checkpoint's ``model_state_dict`` can be fed straight in.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# (name, kind, cin, cout, downsample); kind "opt" = DBlockOptimized, "res" = DBlock
+ARCH = {
+    32: dict(blocks=[("block1", "opt", 3, 128, True), ("block2", "res", 128, 128, True),
+                     ("block3", "res", 128, 128, False), ("block4", "res", 128, 128, False)],
+             head="l5", ndf=128, size=32),
+    64: dict(blocks=[("block1", "opt", 3, 64, True), ("block2", "res", 64, 128, True),
+                     ("block3", "res", 128, 256, True), ("block4", "res", 256, 512, True),
+                     ("block5", "res", 512, 1024, True)],
+             head="l6", ndf=1024, size=64),
+}
+
+
+def has_shortcut_conv(kind, cin, cout, down):
+    """resblocks.py: ``learnable_sc = in != out or downsample`` (DBlockOptimized always has c_sc)."""
+    return kind == "opt" or cin != cout or down
+
+
+def layer_list(arch: int):
+    """[(key_prefix, cout, cin, ksize)] for every spectral-normalised layer, forward order."""
+    out = []
+    for name, kind, cin, cout, down in ARCH[arch]["blocks"]:
+        hidden = cout if kind == "opt" else cin          # DBlock: hidden = in_channels
+        out.append((f"{name}.c1", hidden, cin, 3))
+        out.append((f"{name}.c2", cout, hidden, 3))
+        if has_shortcut_conv(kind, cin, cout, down):
+            out.append((f"{name}.c_sc", cout, cin, 1))
+    out.append((ARCH[arch]["head"], 1, ARCH[arch]["ndf"], 0))
+    return out
+
+
+def init_params(arch: int, seed: int = 1) -> dict:
+    """Random init with mimicry's scheme (xavier-uniform, gain sqrt2 for c1/c2, 1 for c_sc and the
+    linear head; torch default uniform bias; sn_u ~ N(0,1); sn_sigma = 1), drawn from a NumPy
+    RandomState so the values are identical on every platform."""
+    rng = np.random.RandomState(seed)
+    p = {}
+    for key, cout, cin, k in layer_list(arch):
+        if k == 0:
+            shape, fan_in, fan_out, gain = (cout, cin), cin, cout, 1.0
+        else:
+            shape, fan_in, fan_out = (cout, cin, k, k), cin * k * k, cout * k * k
+            gain = 1.0 if key.endswith("c_sc") else math.sqrt(2.0)
+        bound = gain * math.sqrt(6.0 / (fan_in + fan_out))
+        p[f"{key}.weight"] = torch.from_numpy(rng.uniform(-bound, bound, shape).astype(np.float32))
+        bb = 1.0 / math.sqrt(fan_in)
+        p[f"{key}.bias"] = torch.from_numpy(rng.uniform(-bb, bb, (cout,)).astype(np.float32))
+        p[f"{key}.sn_u"] = torch.from_numpy(rng.standard_normal((1, cout)).astype(np.float32))
+        p[f"{key}.sn_sigma"] = torch.ones(1)
+    return p
+
+
+def perturb_params(params: dict, step: int, scale: float = 1e-3) -> dict:
+    """Deterministic stand-in for one stretch of GAN training between two recording passes
+    (SURVEY 8(d) item 2): W += scale * randn with seed = step; biases and sn_u untouched."""
+    rng = np.random.RandomState(step)
+    out = dict(params)
+    for k in sorted(params):
+        if k.endswith(".weight"):
+            w = params[k]
+            out[k] = w + scale * torch.from_numpy(rng.standard_normal(tuple(w.shape)).astype(np.float32))
+    return out
+
+
+def sigma_eval(weight: torch.Tensor, u: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """spectral_norm.py _power_iteration with num_iters=1; in eval mode the buffers are not
+    updated, so sigma is the same for every batch of a recording pass."""
+    W = weight.reshape(weight.shape[0], -1)
+    v = F.normalize(torch.matmul(u, W), eps=eps)
+    u2 = F.normalize(torch.matmul(v, W.t()), eps=eps)
+    return torch.mm(u2, torch.mm(W, v.t()))            # [1,1]
+
+
+def sn_weight(params: dict, key: str) -> torch.Tensor:
+    w = params[f"{key}.weight"]
+    return w / sigma_eval(w, params[f"{key}.sn_u"])
+
+
+def _conv(params, key, x, pad):
+    return F.conv2d(x, sn_weight(params, key), params[f"{key}.bias"], stride=1, padding=pad)
+
+
+def forward(params: dict, x: torch.Tensor, arch: int = 32, inplace_relu: bool = True) -> torch.Tensor:
+    """x float32 NCHW in [-1,1] -> logits [B,1].
+
+    ``inplace_relu=True`` reproduces mimicry's ``nn.ReLU(True)`` aliasing in ``DBlock``: the
+    residual branch runs first and rectifies ``x`` in place, so the shortcut branch (the 1x1 conv,
+    or the identity of blocks 3/4 of SNGAN-32) sees relu(x).  ``False`` gives the textbook block.
+    """
+    h = x
+    for name, kind, cin, cout, down in ARCH[arch]["blocks"]:
+        if kind == "opt":
+            r = _conv(params, f"{name}.c1", h, 1)
+            r = F.relu(r)
+            r = _conv(params, f"{name}.c2", r, 1)
+            r = F.avg_pool2d(r, 2)
+            s = _conv(params, f"{name}.c_sc", F.avg_pool2d(h, 2), 0)
+            h = r + s
+        else:
+            a = F.relu(h)
+            r = _conv(params, f"{name}.c1", a, 1)
+            r = F.relu(r)
+            r = _conv(params, f"{name}.c2", r, 1)
+            if down:
+                r = F.avg_pool2d(r, 2)
+            s = a if inplace_relu else h
+            if has_shortcut_conv(kind, cin, cout, down):
+                s = _conv(params, f"{name}.c_sc", s, 0)
+                if down:
+                    s = F.avg_pool2d(s, 2)
+            h = r + s
+    h = F.relu(h)
+    h = torch.sum(h, dim=(2, 3))
+    head = ARCH[arch]["head"]
+    return F.linear(h, sn_weight(params, head), params[f"{head}.bias"])
+
+
+def normalise_u8(x_u8_nhwc: torch.Tensor) -> torch.Tensor:
+    """ToTensor + Normalize(0.5, 0.5) of transform.py:3-11 on a uint8 NHWC batch -> float32 NCHW."""
+    x = x_u8_nhwc.permute(0, 3, 1, 2).to(torch.float32) / 255.0
+    return (x - 0.5) / 0.5
+
+
+def logits_pass(params, data_u8_nhwc: torch.Tensor, arch=32, batch=64, inplace_relu=True) -> np.ndarray:
+    """The recording pass of trainer.py:142-156 on an in-memory dataset, sequential batches of 64:
+    float64 [N] with fp32 values widened, indexed by dataset index."""
+    n = data_u8_nhwc.shape[0]
+    out = np.zeros(n)
+    with torch.no_grad():
+        for s in range(0, n, batch):
+            x = normalise_u8(data_u8_nhwc[s:s + batch])
+            out[s:s + batch] = forward(params, x, arch, inplace_relu).view(-1).numpy()
+    return out

@@ -1,0 +1,108 @@
+"""The CPU oracle against the golden vectors produced by the reference itself
+(tests/golden/*.npz, made by oracle/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dcgan as dcgan_oracle
+from oracle import drs as drs_oracle
+from oracle import scores as so
+
+CASES = ["scores_cifar_window", "scores_ffhq_window", "scores_ties"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("faithful", [False, True])
+def test_scores_oracle_bit_exact(golden_dir, name, faithful):
+    g = _load(golden_dir, name)
+    logits = {int(s): g["logits"][i] for i, s in enumerate(g["steps"])}
+    out = so.calculate_scores(logits, int(g["start"]), int(g["end"]), faithful=faithful)
+    keys = [str(k) for k in g["keys"]]
+    assert list(out.keys()) == keys
+    for i, k in enumerate(keys):
+        assert np.array_equal(out[k], g["scores"][i]), k
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_moments_loop_matches_numpy_reduction(golden_dir, name):
+    """The explicit row-by-row order (what the CUDA kernel does) == NumPy's axis-0 reduction."""
+    g = _load(golden_dir, name)
+    steps = g["steps"]
+    sel = (steps >= g["start"]) & (steps < g["end"])
+    arr = g["logits"][sel]
+    mean, var = so.moments(arr)
+    keys = [str(k) for k in g["keys"]]
+    assert np.array_equal(mean, g["scores"][keys.index("ldrm")])
+    assert np.array_equal(var, g["scores"][keys.index("ldrv")])
+    for t in (so.conf_values()[2], so.conf_values()[49]):
+        s = so.score_from_moments(mean, var, t)
+        assert np.array_equal(s, g["scores"][keys.index(so.conf_key(t))])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_welford_close(golden_dir, name):
+    g = _load(golden_dir, name)
+    steps = g["steps"]
+    sel = (steps >= g["start"]) & (steps < g["end"])
+    arr = g["logits"][sel]
+    T = arr.shape[0]
+    mean, m2, last, sad = so.welford(arr)
+    keys = [str(k) for k in g["keys"]]
+    np.testing.assert_allclose(mean, g["scores"][keys.index("ldrm")], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(m2 / (T - 1), g["scores"][keys.index("ldrv")], rtol=1e-10, atol=1e-18)
+    assert np.array_equal(last, g["scores"][keys.index("ldr")])
+    np.testing.assert_allclose(sad / (T - 1), g["scores"][keys.index("ldrd")], rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_stream_and_top_indices(golden_dir, name):
+    g = _load(golden_dir, name)
+    keys = [str(k) for k in g["keys"]]
+    w = g["scores"][keys.index("ldr_conf_0.3_ratio_50")]
+    stream = so.resample_stream(so.floor_weights(w), int(g["stream_seed"]))
+    assert np.array_equal(stream, g["stream"])
+    assert np.array_equal(so.top_indices(w, 20, True), g["argsort_stable"][-20:])
+    assert np.array_equal(so.top_indices(w, 20, False), g["argsort_stable"][:20])
+
+
+def test_conf_key_grammar():
+    t = so.conf_values()
+    assert len(t) == 99
+    assert so.conf_key(t[2]) == "ldr_conf_0.3_ratio_50" and t[2] == 0.30000000000000004
+    assert so.conf_from_key("ldr_conf_5.0_ratio_50") == 5.0
+
+
+@pytest.mark.parametrize("name", ["drs_b256", "drs_b128"])
+def test_drs_oracle_matches_reference(golden_dir, name):
+    g = _load(golden_dir, name)
+    o = drs_oracle.DRSOracle(percentile=int(g["percentile"]))
+    o.burn_in(list(g["burn_ldr"]))
+    assert np.float32(o.maximum) == g["max_after_burn"]
+    for b in range(g["ldr"].shape[0]):
+        p, acc = o.accept(g["ldr"][b], g["psi"][b])
+        assert np.array_equal(acc, g["accept"][b])
+        assert np.float32(o.maximum) == g["max_after"][b]
+
+
+def test_percentile_restatement():
+    rng = np.random.RandomState(0)
+    for n in (2, 3, 50, 128, 256, 257, 1000):
+        for q in (80, 50, 99, 1):
+            x = rng.standard_normal(n).astype(np.float32)
+            assert drs_oracle.percentile_f32(x, q) == np.percentile(x.reshape(-1, 1), q)
+
+
+def test_dcgan_oracle_matches_reference(golden_dir):
+    g = _load(golden_dir, "dcgan_eval")
+    params = dcgan_oracle.init_params(int(g["param_seed"]))
+    chk = sum(float(v.double().sum()) for v in params.values())
+    assert chk == float(g["param_checksum"])
+    torch.set_num_threads(1)
+    y = dcgan_oracle.logits_pass(params, torch.from_numpy(g["x_u8"]))
+    np.testing.assert_allclose(y, g["logits"], rtol=1e-5, atol=1e-7)
