@@ -1,0 +1,171 @@
+/* sdg.h -- C ABI of the B200-native per-sample diagnosis path of Self-Diagnosing GAN.
+ *
+ * The reference (grayhong/self-diagnosing-gan) has no FFI layer of its own: its boundary is the
+ * Python surface of `diagan-pkg`.  Each entry point below names the
+ * reference interface whose arithmetic it replaces (paths relative to the reference root); the
+ * ctypes binding a maintainer adds on the reference side is shown in INTEGRATION.md and lives in
+ * `self-diagnosing-gan_b200/diagan_b200/_lib.py`.
+ *
+ * Conventions
+ *   - every pointer is a CALLER-OWNED DEVICE pointer unless the name ends in `_host`;
+ *     the library never frees or retains them past the call (packed weights and scratch live in
+ *     the opaque `sdg_ctx`);
+ *   - `stream` is a `cudaStream_t` passed as `void*` (torch's current stream); all calls are
+ *     asynchronous with respect to the host unless stated otherwise;
+ *   - return value: 0 = ok, < 0 = invalid argument / unsupported shape (SDG_E_*), > 0 = cudaError_t.
+ *     Nothing throws across the ABI.  `sdg_last_error()` returns a thread-local message;
+ *   - one ctx per device/rank; calls on a ctx are not re-entrant;
+ *   - there is NO CPU fallback anywhere behind this ABI.
+ */
+#ifndef SDG_H_
+#define SDG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDG_ABI_VERSION 1
+
+#define SDG_E_INVALID      (-1)   /* bad argument */
+#define SDG_E_UNSUPPORTED  (-2)   /* shape / mode not implemented */
+#define SDG_E_STATE        (-3)   /* call order (e.g. forward before load) */
+#define SDG_E_DEVICE       (-4)   /* not an sm_100 device / driver entry point missing */
+
+/* discriminator architectures */
+#define SDG_ARCH_DCGAN32   1      /* diagan/models/mnist.py:155-223, eval mode, 3x32x32 */
+#define SDG_ARCH_SNGAN32   32     /* torch_mimicry SNGANDiscriminator32 (predefined_models.py:14,38,50) */
+#define SDG_ARCH_SNGAN64   64     /* torch_mimicry SNGANDiscriminator64 (predefined_models.py:76,88) */
+
+/* arithmetic of the conv stack */
+#define SDG_PREC_FP32      0      /* CUDA-core fp32 (IEEE, no TF32): the 1e-5 parity mode */
+#define SDG_PREC_BF16      1      /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulators: the throughput mode */
+
+/* input layouts of sdg_d_forward */
+#define SDG_LAYOUT_U8_NHWC   0    /* uint8 [n,H,W,3]; normalised (x/255-.5)/.5 on load (transform.py:3-11) */
+#define SDG_LAYOUT_F32_NCHW  1    /* float32 [n,3,H,W] already in [-1,1] (what netD(x) receives, trainer.py:150) */
+
+#if defined(__GNUC__)
+#define SDG_API __attribute__((visibility("default")))
+#else
+#define SDG_API
+#endif
+
+typedef struct sdg_ctx sdg_ctx;
+
+SDG_API const char* sdg_last_error(void);
+SDG_API int sdg_abi_version(void);
+
+/* per-device context: packed weights, TMA descriptors, activation scratch */
+SDG_API int sdg_ctx_create(int device, sdg_ctx** out);
+SDG_API int sdg_ctx_destroy(sdg_ctx* ctx);
+/* upper bound on samples processed per internal sweep (bounds scratch memory); 0 = default */
+SDG_API int sdg_ctx_set_chunk(sdg_ctx* ctx, int64_t samples_per_chunk);
+
+/* ---- discriminator weights ------------------------------------------------------------------
+ * Replaces torch_mimicry SNConv2d/SNLinear.sn_weights as called in eval mode under
+ * trainer.py:145-150: one power iteration from the stored `sn_u` (buffers NOT updated), sigma =
+ * u'.W.v, weight used = W / sigma.  sigma is identical for every batch of a recording pass, so it is
+ * computed ONCE here and folded into the packed weights.
+ * W/b/u: host arrays of `n_layers` DEVICE pointers in forward order
+ *   SNGAN32: b1.c1 b1.c2 b1.c_sc b2.c1 b2.c2 b2.c_sc b3.c1 b3.c2 b4.c1 b4.c2 l5        (11)
+ *   SNGAN64: b1.c1 b1.c2 b1.c_sc then (c1 c2 c_sc) for b2..b5, l6                       (16)
+ * weights are torch layout [Cout,Cin,k,k] fp32 contiguous; u is [Cout].
+ * inplace_relu != 0 reproduces mimicry's nn.ReLU(True) aliasing in DBlock (shortcut sees relu(x)). */
+SDG_API int sdg_sngan_load(sdg_ctx* ctx, int arch, int n_layers,
+                   const float* const* W_host, const float* const* b_host, const float* const* u_host,
+                   int precision, int inplace_relu, void* stream);
+/* copies the per-layer sigma computed by the last sdg_sngan_load to a device array [n_layers] */
+SDG_API int sdg_sngan_sigmas(sdg_ctx* ctx, float* sigma_out, void* stream);
+
+/* Replaces MNIST_DCGAN_Discriminator.forward in eval mode (mnist.py:213-223): BatchNorm running
+ * statistics are folded into the conv weights/bias, Dropout is the identity.
+ * conv_w: 6 device pointers [Cout,Cin,3,3]; bn_{gamma,beta,mean,var}: 5 device pointers each
+ * (convs 2..6); fc_w [1,8192] in NCHW flatten order, fc_b [1]. */
+SDG_API int sdg_dcgan_load(sdg_ctx* ctx, const float* const* conv_w_host,
+                   const float* const* bn_gamma_host, const float* const* bn_beta_host,
+                   const float* const* bn_mean_host, const float* const* bn_var_host,
+                   const float* fc_w, const float* fc_b, int precision, void* stream);
+
+/* ---- recording pass --------------------------------------------------------------------------
+ * Replaces the loop body of LogTrainer._get_logit (trainer.py:148-154) and of stylegan2
+ * get_logit (train_ffhq.py:135-141): logits_out[i] = netD(x_i) for i in [0,n), fp32.
+ * The caller passes logits_out already offset to the first sample's dataset index. */
+SDG_API int sdg_d_forward(sdg_ctx* ctx, const void* x, int layout, int64_t n, float* logits_out, void* stream);
+
+/* One spectral-normalised conv layer of the bf16 path on its own (what sdg_d_forward launches per
+ * layer; exposed for kernel-level parity tests and for the roofline measurement in bench.py).
+ * Replaces F.conv2d(x, W/sigma, b, stride=1, padding=ks/2) of mimicry SNConv2d.forward.
+ * in  bf16 [n,H,W,Cin] NHWC (Cin % 64 == 0, H == W a power of two in 4..128)
+ * wb  bf16 [Cout, ks*ks*Cin], K index = (ky*ks+kx)*Cin + c      (Cout % 64 == 0, <= 1024)
+ * out bf16 [n,H,W,Cout]; bias fp32 [Cout] or NULL; relu != 0 applies ReLU after the bias. ks in {1,3}. */
+SDG_API int sdg_conv2d_bf16(const void* in, const void* wb, const float* bias, void* out, int64_t n, int H, int W,
+                    int Cin, int Cout, int ks, int relu, void* stream);
+
+/* ---- running per-sample statistics (new: the reference keeps every snapshot, trainer.py:337-338) --
+ * Welford update with snapshot number t (0-based) plus last value and sum |x_t - x_{t-1}|:
+ * after T updates  ldrm = mean, ldrv = m2/(T-1), ldr = last, ldrd = sad/(T-1)  (plot.py:243-246). */
+SDG_API int sdg_stats_update(const float* snapshot, double* mean, double* m2, double* last, double* sad,
+                     int64_t n, int64_t t, void* stream);
+
+/* ---- scoring ---------------------------------------------------------------------------------
+ * Replaces calculate_scores (plot.py:220-249).
+ * sdg_window_moments_{f32,f64}: snaps [T, ld] row-major (row t = snapshot t of the selected window);
+ * two-pass mean / ddof-1 variance in NumPy's evaluation order (bit-exact vs np.mean/np.var/np.std),
+ * ldrd = mean_t |x_{t+1}-x_t|, ldr = last row.  Any output pointer may be NULL. */
+SDG_API int sdg_window_moments_f32(const float* snaps, int64_t T, int64_t n, int64_t ld,
+                           double* mean, double* var, double* ldrd, double* ldr, void* stream);
+SDG_API int sdg_window_moments_f64(const double* snaps, int64_t T, int64_t n, int64_t ld,
+                           double* mean, double* var, double* ldrd, double* ldr, void* stream);
+/* phase 1: score[j][i] = max(mean[i] + conf[j]*sqrt(var[i]), floor), mins[j] = min_i score[j][i]
+ * (clip_min, plot.py:230-231).  conf_host: host array of n_conf multipliers; score [n_conf, n];
+ * mins [n_conf] device.  var_is_m2_over: if > 0, `var` holds Welford m2 and is divided by it. */
+SDG_API int sdg_score_floor_min(const double* mean, const double* var, int64_t n, const double* conf_host,
+                        int n_conf, double floor, double var_is_m2_over, double* score, double* mins,
+                        void* stream);
+/* phase 2: score[j][i] = max(min(score[j][i], mins[j]*ratio), eps)  (clip_max_ratio plot.py:226-228,
+ * then the sampler floor of train_mimicry_phase2.py:23; pass eps = 0 to skip the floor).
+ * Between the phases a sharded caller all-reduces `mins` with MIN. */
+SDG_API int sdg_score_clip(double* score, int64_t n, int n_conf, const double* mins, double ratio, double eps,
+                   void* stream);
+
+/* ---- top-index selection ---------------------------------------------------------------------
+ * Replaces np.argsort(w)[-k:] / [:k] (eval_gan_drs_with_index.py:97-99, plot.py:100-101) with the
+ * tie-break of a stable sort: idx_out[0..k) in ascending (score, index) order, equal to
+ * np.argsort(w, kind="stable")[-k:] (largest != 0) or [:k].  k <= 4096.
+ * workspace: device scratch of at least sdg_topk_workspace_bytes(n) bytes. */
+SDG_API size_t sdg_topk_workspace_bytes(int64_t n);
+SDG_API int sdg_topk_indices(const double* score, int64_t n, int k, int largest, int64_t* idx_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Discriminator Rejection Sampling ----------------------------------------------------------
+ * Replaces DRS.init_drs / sub_rejection_sampler (models/drs.py:31-57, trainer/evaluate.py:45-68).
+ * running_max: device float, initialised by the caller to -100000.
+ * sdg_drs_update_max: running_max = max(running_max, max_i ldr[i])      (burn-in, drs.py:31-36)
+ * sdg_drs_accept: updates running_max, F = l - log(1 - exp(l - eps)) with l = ldr - max (fp32),
+ *   gamma = `gamma` if use_gamma else the `percentile`-th linear-interpolation percentile of F,
+ *   p = sigmoid(F - gamma), accept[i] = p[i] > psi[i]; accepted indices are compacted in order into
+ *   idx_out and their number written to count_out.  n <= 2048.  Any of p_out/accept_out/idx_out may
+ *   be NULL. */
+SDG_API int sdg_drs_update_max(const float* ldr, int n, float* running_max, void* stream);
+SDG_API int sdg_drs_accept(const float* ldr, int n, float* running_max, float eps, float percentile,
+                   int use_gamma, float gamma, const double* psi,
+                   float* p_out, uint8_t* accept_out, int32_t* idx_out, int32_t* count_out, void* stream);
+
+/* ---- introspection for bench.py ("gpu_launches") ---------------------------------------------- */
+SDG_API int64_t sdg_launch_count(void);       /* kernels launched by this library since load / last reset */
+SDG_API void sdg_launch_count_reset(void);
+
+/* Event timing of the dominant kernel of the bf16 SNGAN forward (block1.c2, the 3x3 128->128 conv at
+ * full resolution) on the launching stream, for the roofline line of bench.py.  _read synchronises on
+ * the recorded events, returns total milliseconds, number of launches and their algorithmic FLOPs
+ * (2*M*N*K of the reference formulation) since the last read, and clears the record. */
+SDG_API int sdg_ctx_profile(sdg_ctx* ctx, int enable);
+SDG_API int sdg_ctx_profile_read(sdg_ctx* ctx, double* ms_total_host, int64_t* launches_host, double* flops_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDG_H_ */

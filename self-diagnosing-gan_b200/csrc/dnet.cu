@@ -1,0 +1,485 @@
+// dnet.cu -- discriminator engines behind the C ABI: context, weight loading, the recording-pass forward.
+//
+// Replaces `netD(real_data)` inside LogTrainer._get_logit (diagan-pkg/diagan/trainer/trainer.py:145-154)
+// and DRS.get_fake_samples_and_ldr (diagan-pkg/diagan/models/drs.py:21-29) for
+//   * torch-mimicry SNGANDiscriminator32 / 64 (constructed at predefined_models.py:14,38,50,76,88)
+//   * MNIST_DCGAN_Discriminator in eval mode (diagan-pkg/diagan/models/mnist.py:155-223)
+// Samples are processed in chunks that bound the activation scratch; within a chunk every layer is one
+// launch over all samples of the chunk.
+#include <cstdarg>
+#include <cstring>
+
+#include "kernels.cuh"
+
+namespace sdg {
+
+static thread_local std::string t_error;
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_error = buf;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+    SDG_CUDA(cudaMalloc(&p, need));
+    bytes = need;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct ConvLayer {
+  int cout = 0, cin = 0, ks = 0, stride = 1;
+  int kpad = 0;              // bf16 K (taps*cin rounded up to 64)
+  DevBuf w32, w16, bias;
+  bool has_bias = false;
+};
+
+struct BlockSpec { int kind, cin, cout, down; };   // kind 0 = DBlockOptimized, 1 = DBlock
+
+}  // namespace sdg
+
+using namespace sdg;
+
+struct sdg_ctx {
+  int device = 0;
+  int arch = 0;
+  int precision = SDG_PREC_FP32;
+  int inplace_relu = 1;
+  int64_t chunk = 0;
+  int size = 0;                          // input H = W
+  std::vector<BlockSpec> blocks;
+  std::vector<ConvLayer> convs;          // forward order (SNGAN: c1,c2,c_sc per block; DCGAN: 6 convs)
+  std::vector<int> block_first_conv;     // index of a block's c1 in `convs`
+  std::vector<int> block_has_sc;
+  DevBuf head_w, head_b;                 // fp32
+  int head_len = 0;
+  DevBuf sigma;                          // [n_layers]
+  int n_layers = 0;
+  DevBuf sn_table, sn_scratch, bn_scratch;
+  DevBuf buf[4], xin, xpool;             // activation scratch
+  bool loaded = false;
+  // optional timing of the dominant kernel (block1.c2) with events on the launching stream
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+  double prof_flops = 0.0;
+};
+
+static int prof_begin(sdg_ctx* c, cudaStream_t s) {
+  if (!c->profile) return 0;
+  if (c->prof_used == c->prof_events.size()) {
+    cudaEvent_t a, b;
+    SDG_CUDA(cudaEventCreate(&a));
+    SDG_CUDA(cudaEventCreate(&b));
+    c->prof_events.push_back({a, b});
+  }
+  SDG_CUDA(cudaEventRecord(c->prof_events[c->prof_used].first, s));
+  return 0;
+}
+
+static int prof_end(sdg_ctx* c, cudaStream_t s, double flops) {
+  if (!c->profile) return 0;
+  SDG_CUDA(cudaEventRecord(c->prof_events[c->prof_used].second, s));
+  c->prof_used++;
+  c->prof_flops += flops;
+  return 0;
+}
+
+static int64_t max_act_elems(const sdg_ctx* c) {
+  // largest per-sample activation tensor (elements)
+  int64_t m = 0;
+  if (c->arch == SDG_ARCH_DCGAN32) return 16 * 16 * 32;
+  int hw = c->size;
+  for (auto& b : c->blocks) {
+    int hidden = b.kind == 0 ? b.cout : b.cin;
+    int64_t a = (int64_t)hw * hw * (hidden > b.cout ? hidden : b.cout);
+    m = a > m ? a : m;
+    if (b.down) hw /= 2;
+  }
+  return m;
+}
+
+extern "C" const char* sdg_last_error(void) { return t_error.c_str(); }
+extern "C" int sdg_abi_version(void) { return SDG_ABI_VERSION; }
+extern "C" int64_t sdg_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" void sdg_launch_count_reset(void) { g_launches.store(0); }
+
+extern "C" int sdg_ctx_create(int device, sdg_ctx** out) {
+  SDG_REQUIRE(out, SDG_E_INVALID, "sdg_ctx_create: null out");
+  int count = 0;
+  SDG_CUDA(cudaGetDeviceCount(&count));
+  SDG_REQUIRE(device >= 0 && device < count, SDG_E_INVALID, "sdg_ctx_create: device %d of %d", device, count);
+  SDG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SDG_CUDA(cudaGetDeviceProperties(&prop, device));
+  SDG_REQUIRE(prop.major == 10, SDG_E_DEVICE, "sdg_ctx_create: device %d is sm_%d%d; this library is sm_100a only",
+              device, prop.major, prop.minor);
+  sdg_ctx* c = new sdg_ctx();
+  c->device = device;
+  *out = c;
+  return 0;
+}
+
+extern "C" int sdg_ctx_destroy(sdg_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); }
+  c->head_w.release(); c->head_b.release(); c->sigma.release();
+  c->sn_table.release(); c->sn_scratch.release(); c->bn_scratch.release();
+  for (auto& b : c->buf) b.release();
+  c->xin.release(); c->xpool.release();
+  delete c;
+  return 0;
+}
+
+extern "C" int sdg_ctx_set_chunk(sdg_ctx* c, int64_t samples_per_chunk) {
+  SDG_REQUIRE(c && samples_per_chunk >= 0, SDG_E_INVALID, "sdg_ctx_set_chunk: bad argument");
+  c->chunk = samples_per_chunk;
+  return 0;
+}
+
+static void sngan_spec(int arch, std::vector<BlockSpec>& blocks, int& size, int& ndf) {
+  blocks.clear();
+  if (arch == SDG_ARCH_SNGAN32) {
+    blocks = {{0, 3, 128, 1}, {1, 128, 128, 1}, {1, 128, 128, 0}, {1, 128, 128, 0}};
+    size = 32; ndf = 128;
+  } else {
+    blocks = {{0, 3, 64, 1}, {1, 64, 128, 1}, {1, 128, 256, 1}, {1, 256, 512, 1}, {1, 512, 1024, 1}};
+    size = 64; ndf = 1024;
+  }
+}
+
+extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* const* W, const float* const* b,
+                              const float* const* u, int precision, int inplace_relu, void* stream) {
+  SDG_REQUIRE(c && W && b && u, SDG_E_INVALID, "sdg_sngan_load: null pointer");
+  SDG_REQUIRE(arch == SDG_ARCH_SNGAN32 || arch == SDG_ARCH_SNGAN64, SDG_E_INVALID, "sdg_sngan_load: arch=%d", arch);
+  SDG_REQUIRE(precision == SDG_PREC_FP32 || precision == SDG_PREC_BF16, SDG_E_INVALID, "sdg_sngan_load: precision=%d",
+              precision);
+  cudaStream_t s = (cudaStream_t)stream;
+  SDG_CUDA(cudaSetDevice(c->device));
+  int ndf = 0;
+  sngan_spec(arch, c->blocks, c->size, ndf);
+
+  // enumerate layers in forward order
+  struct L { int cout, cin, ks; };
+  std::vector<L> ls;
+  c->block_first_conv.clear(); c->block_has_sc.clear();
+  for (auto& bl : c->blocks) {
+    int hidden = bl.kind == 0 ? bl.cout : bl.cin;
+    c->block_first_conv.push_back((int)ls.size());
+    ls.push_back({hidden, bl.cin, 3});
+    ls.push_back({bl.cout, hidden, 3});
+    int sc = (bl.kind == 0) || bl.cin != bl.cout || bl.down;
+    c->block_has_sc.push_back(sc);
+    if (sc) ls.push_back({bl.cout, bl.cin, 1});
+  }
+  const int n_convs = (int)ls.size();
+  SDG_REQUIRE(n_layers == n_convs + 1, SDG_E_INVALID, "sdg_sngan_load: arch %d has %d layers, got %d", arch,
+              n_convs + 1, n_layers);
+  for (int i = 0; i < n_layers; ++i)
+    SDG_REQUIRE(W[i] && b[i] && u[i], SDG_E_INVALID, "sdg_sngan_load: layer %d has a null pointer", i);
+
+  c->arch = arch; c->precision = precision; c->inplace_relu = inplace_relu ? 1 : 0; c->n_layers = n_layers;
+  c->loaded = false;
+  if (precision == SDG_PREC_BF16) { int rc = conv_tc_init(c->device); if (rc) return rc; }
+
+  // ---- sigma for every layer: one batched power iteration ----
+  std::vector<SnLayer> tab(n_layers);
+  size_t scratch_floats = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    int cout = i < n_convs ? ls[i].cout : 1;
+    int K = i < n_convs ? ls[i].cin * ls[i].ks * ls[i].ks : ndf;
+    tab[i].W = W[i]; tab[i].u = u[i]; tab[i].cout = cout; tab[i].K = K;
+    scratch_floats += (size_t)K + cout;
+  }
+  { int rc = c->sn_scratch.ensure(scratch_floats * sizeof(float)); if (rc) return rc; }
+  { int rc = c->sn_table.ensure(sizeof(SnLayer) * n_layers); if (rc) return rc; }
+  { int rc = c->sigma.ensure(sizeof(float) * n_layers); if (rc) return rc; }
+  float* sp = c->sn_scratch.as<float>();
+  for (int i = 0; i < n_layers; ++i) { tab[i].v = sp; sp += tab[i].K; tab[i].t = sp; sp += tab[i].cout; }
+  SDG_CUDA(cudaMemcpyAsync(c->sn_table.p, tab.data(), sizeof(SnLayer) * n_layers, cudaMemcpyHostToDevice, s));
+  { int rc = sn_sigmas(c->sn_table.as<SnLayer>(), tab.data(), n_layers, c->sigma.as<float>(), s); if (rc) return rc; }
+
+  // ---- pack W / sigma ----
+  if ((int)c->convs.size() != n_convs) {
+    for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); }
+    c->convs.assign(n_convs, ConvLayer());
+  }
+  const float* sig = c->sigma.as<float>();
+  for (int i = 0; i < n_convs; ++i) {
+    ConvLayer& l = c->convs[i];
+    l.cout = ls[i].cout; l.cin = ls[i].cin; l.ks = ls[i].ks; l.stride = 1; l.has_bias = true;
+    int K = l.cin * l.ks * l.ks;
+    l.kpad = (K + 63) / 64 * 64;
+    { int rc = l.bias.ensure(sizeof(float) * l.cout); if (rc) return rc; }
+    SDG_CUDA(cudaMemcpyAsync(l.bias.p, b[i], sizeof(float) * l.cout, cudaMemcpyDeviceToDevice, s));
+    if (precision == SDG_PREC_FP32) {
+      { int rc = l.w32.ensure(sizeof(float) * K * l.cout); if (rc) return rc; }
+      int rc = pack_conv_fp32(W[i], sig + i, nullptr, l.w32.as<float>(), l.cout, l.cin, l.ks, s);
+      if (rc) return rc;
+    } else {
+      { int rc = l.w16.ensure(sizeof(__nv_bfloat16) * (size_t)l.kpad * l.cout); if (rc) return rc; }
+      int rc = pack_conv_bf16(W[i], sig + i, nullptr, l.w16.as<__nv_bfloat16>(), l.cout, l.cin, l.kpad, l.ks, s);
+      if (rc) return rc;
+    }
+  }
+  c->head_len = ndf;
+  { int rc = c->head_w.ensure(sizeof(float) * ndf); if (rc) return rc; }
+  { int rc = c->head_b.ensure(sizeof(float)); if (rc) return rc; }
+  { int rc = scale_vec(W[n_convs], sig + n_convs, c->head_w.as<float>(), ndf, s); if (rc) return rc; }
+  SDG_CUDA(cudaMemcpyAsync(c->head_b.p, b[n_convs], sizeof(float), cudaMemcpyDeviceToDevice, s));
+  c->loaded = true;
+  return 0;
+}
+
+extern "C" int sdg_sngan_sigmas(sdg_ctx* c, float* sigma_out, void* stream) {
+  SDG_REQUIRE(c && sigma_out, SDG_E_INVALID, "sdg_sngan_sigmas: null pointer");
+  SDG_REQUIRE(c->loaded && c->arch != SDG_ARCH_DCGAN32, SDG_E_STATE, "sdg_sngan_sigmas: no SNGAN weights loaded");
+  SDG_CUDA(cudaMemcpyAsync(sigma_out, c->sigma.p, sizeof(float) * c->n_layers, cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return 0;
+}
+
+static const int kDcganSpec[6][3] = {{3, 16, 2}, {16, 32, 1}, {32, 64, 2}, {64, 128, 1}, {128, 256, 2}, {256, 512, 1}};
+
+extern "C" int sdg_dcgan_load(sdg_ctx* c, const float* const* conv_w, const float* const* bn_gamma,
+                              const float* const* bn_beta, const float* const* bn_mean, const float* const* bn_var,
+                              const float* fc_w, const float* fc_b, int precision, void* stream) {
+  SDG_REQUIRE(c && conv_w && bn_gamma && bn_beta && bn_mean && bn_var && fc_w && fc_b, SDG_E_INVALID,
+              "sdg_dcgan_load: null pointer");
+  SDG_REQUIRE(precision == SDG_PREC_FP32, SDG_E_UNSUPPORTED,
+              "sdg_dcgan_load: only SDG_PREC_FP32 is implemented for the DCGAN discriminator");
+  cudaStream_t s = (cudaStream_t)stream;
+  SDG_CUDA(cudaSetDevice(c->device));
+  c->loaded = false;
+  c->arch = SDG_ARCH_DCGAN32; c->precision = precision; c->size = 32; c->blocks.clear();
+  if (c->convs.size() != 6) {
+    for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); }
+    c->convs.assign(6, ConvLayer());
+  }
+  { int rc = c->bn_scratch.ensure(sizeof(float) * 512); if (rc) return rc; }
+  for (int i = 0; i < 6; ++i) {
+    ConvLayer& l = c->convs[i];
+    l.cin = kDcganSpec[i][0]; l.cout = kDcganSpec[i][1]; l.stride = kDcganSpec[i][2]; l.ks = 3;
+    SDG_REQUIRE(conv_w[i], SDG_E_INVALID, "sdg_dcgan_load: conv %d null", i);
+    { int rc = l.w32.ensure(sizeof(float) * 9 * l.cin * l.cout); if (rc) return rc; }
+    const float* scale = nullptr;
+    l.has_bias = i > 0;
+    if (i > 0) {
+      SDG_REQUIRE(bn_gamma[i - 1] && bn_beta[i - 1] && bn_mean[i - 1] && bn_var[i - 1], SDG_E_INVALID,
+                  "sdg_dcgan_load: bn %d null", i);
+      { int rc = l.bias.ensure(sizeof(float) * l.cout); if (rc) return rc; }
+      int rc = bn_fold(bn_gamma[i - 1], bn_beta[i - 1], bn_mean[i - 1], bn_var[i - 1], 1e-5f,
+                       c->bn_scratch.as<float>(), l.bias.as<float>(), l.cout, s);
+      if (rc) return rc;
+      scale = c->bn_scratch.as<float>();
+    }
+    int rc = pack_conv_fp32(conv_w[i], nullptr, scale, l.w32.as<float>(), l.cout, l.cin, 3, s);
+    if (rc) return rc;
+  }
+  c->head_len = 8192;
+  { int rc = c->head_w.ensure(sizeof(float) * 8192); if (rc) return rc; }
+  { int rc = c->head_b.ensure(sizeof(float)); if (rc) return rc; }
+  { int rc = permute_fc(fc_w, c->head_w.as<float>(), 512, 16, s); if (rc) return rc; }
+  SDG_CUDA(cudaMemcpyAsync(c->head_b.p, fc_b, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  c->loaded = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int forward_sngan_fp32(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s) {
+  const int S = c->size;
+  float* X = c->xin.as<float>();
+  float* PX = c->xpool.as<float>();
+  float* h = c->buf[0].as<float>();
+  float* f1 = c->buf[1].as<float>();
+  float* f2 = c->buf[2].as<float>();
+  int rc;
+  if ((rc = prep_input_fp32(x, layout, X, nb, S, S, s))) return rc;
+  int hw = S;
+  for (size_t bi = 0; bi < c->blocks.size(); ++bi) {
+    const BlockSpec& bl = c->blocks[bi];
+    const ConvLayer& c1 = c->convs[c->block_first_conv[bi]];
+    const ConvLayer& c2 = c->convs[c->block_first_conv[bi] + 1];
+    const int ho = bl.down ? hw / 2 : hw;
+    if (bl.kind == 0) {
+      const ConvLayer& sc = c->convs[c->block_first_conv[bi] + 2];
+      if ((rc = conv_fp32(X, c1.w32.as<float>(), c1.bias.as<float>(), f1, nb, hw, hw, c1.cin, c1.cout, 3, 1, ACT_NONE, ACT_RELU, s))) return rc;
+      if ((rc = conv_fp32(f1, c2.w32.as<float>(), c2.bias.as<float>(), f2, nb, hw, hw, c2.cin, c2.cout, 3, 1, ACT_NONE, ACT_NONE, s))) return rc;
+      if ((rc = combine_fp32(X, 1, nullptr, 0, 0, PX, nb, ho, ho, 3, s))) return rc;                   // avg_pool2d(x)
+      if ((rc = conv_fp32(PX, sc.w32.as<float>(), sc.bias.as<float>(), f1, nb, ho, ho, sc.cin, sc.cout, 1, 1, ACT_NONE, ACT_NONE, s))) return rc;
+      if ((rc = combine_fp32(f2, 1, f1, 0, 0, h, nb, ho, ho, bl.cout, s))) return rc;
+    } else {
+      if ((rc = conv_fp32(h, c1.w32.as<float>(), c1.bias.as<float>(), f1, nb, hw, hw, c1.cin, c1.cout, 3, 1, ACT_RELU, ACT_RELU, s))) return rc;
+      if ((rc = conv_fp32(f1, c2.w32.as<float>(), c2.bias.as<float>(), f2, nb, hw, hw, c2.cin, c2.cout, 3, 1, ACT_NONE, ACT_NONE, s))) return rc;
+      if (c->block_has_sc[bi]) {
+        const ConvLayer& sc = c->convs[c->block_first_conv[bi] + 2];
+        if ((rc = conv_fp32(h, sc.w32.as<float>(), sc.bias.as<float>(), f1, nb, hw, hw, sc.cin, sc.cout, 1, 1,
+                            c->inplace_relu ? ACT_RELU : ACT_NONE, ACT_NONE, s))) return rc;
+        if ((rc = combine_fp32(f2, bl.down, f1, bl.down, 0, h, nb, ho, ho, bl.cout, s))) return rc;
+      } else {
+        if ((rc = combine_fp32(f2, 0, h, 0, c->inplace_relu, f1, nb, ho, ho, bl.cout, s))) return rc;
+        float* t = h; h = f1; f1 = t;
+      }
+    }
+    hw = ho;
+  }
+  return head_sumpool_fp32(h, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, hw * hw, c->head_len, 1, s);
+}
+
+static int forward_sngan_bf16(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s) {
+  typedef __nv_bfloat16 bf;
+  const int S = c->size;
+  bf* X = c->xin.as<bf>();          // [nb,S,S,64] 3x3x3 patches of the normalised input
+  bf* PX = c->xpool.as<bf>();       // [nb,S/2,S/2,64] pooled input
+  bf* h = c->buf[0].as<bf>();       // relu(h): block output as the next conv / head consumes it
+  bf* f1 = c->buf[1].as<bf>();
+  bf* f2 = c->buf[2].as<bf>();
+  bf* hraw = c->inplace_relu ? nullptr : c->buf[3].as<bf>();   // unrectified h for the textbook shortcut
+  int rc;
+  if ((rc = stage_first_conv(x, layout, X, PX, nb, S, S, s))) return rc;
+  int hw = S;
+  for (size_t bi = 0; bi < c->blocks.size(); ++bi) {
+    const BlockSpec& bl = c->blocks[bi];
+    const ConvLayer& c1 = c->convs[c->block_first_conv[bi]];
+    const ConvLayer& c2 = c->convs[c->block_first_conv[bi] + 1];
+    const int ho = bl.down ? hw / 2 : hw;
+    if (bl.kind == 0) {
+      const ConvLayer& sc = c->convs[c->block_first_conv[bi] + 2];
+      // c1 as a 1x1 GEMM over the staged 27(->64)-wide patches; c_sc over the pooled input
+      if ((rc = conv_tc(X, c1.w16.as<bf>(), c1.bias.as<float>(), f1, nb, hw, hw, 64, c1.cout, 1, 1, s))) return rc;
+      if ((rc = prof_begin(c, s))) return rc;
+      if ((rc = conv_tc(f1, c2.w16.as<bf>(), c2.bias.as<float>(), f2, nb, hw, hw, c2.cin, c2.cout, 9, 0, s))) return rc;
+      if ((rc = prof_end(c, s, 2.0 * (double)nb * hw * hw * c2.cout * 9.0 * c2.cin))) return rc;
+      if ((rc = conv_tc(PX, sc.w16.as<bf>(), sc.bias.as<float>(), f1, nb, ho, ho, 64, sc.cout, 1, 0, s))) return rc;
+      if ((rc = combine_bf16(f2, 1, f1, 0, h, hraw, nb, ho, ho, bl.cout, s))) return rc;
+    } else {
+      if ((rc = conv_tc(h, c1.w16.as<bf>(), c1.bias.as<float>(), f1, nb, hw, hw, c1.cin, c1.cout, 9, 1, s))) return rc;
+      if ((rc = conv_tc(f1, c2.w16.as<bf>(), c2.bias.as<float>(), f2, nb, hw, hw, c2.cin, c2.cout, 9, 0, s))) return rc;
+      const bf* sc_in = c->inplace_relu ? h : hraw;
+      if (c->block_has_sc[bi]) {
+        const ConvLayer& sc = c->convs[c->block_first_conv[bi] + 2];
+        if ((rc = conv_tc(sc_in, sc.w16.as<bf>(), sc.bias.as<float>(), f1, nb, hw, hw, sc.cin, sc.cout, 1, 0, s))) return rc;
+        if ((rc = combine_bf16(f2, bl.down, f1, bl.down, h, hraw, nb, ho, ho, bl.cout, s))) return rc;
+      } else {
+        // identity shortcut: h' = c2(...) + (relu(h) | h); written to f1, then the roles swap
+        if ((rc = combine_bf16(f2, 0, sc_in, 0, f1, hraw, nb, ho, ho, bl.cout, s))) return rc;
+        bf* t = h; h = f1; f1 = t;
+      }
+    }
+    hw = ho;
+  }
+  return head_bf16(h, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, hw * hw, c->head_len, s);
+}
+
+static int forward_dcgan_fp32(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s) {
+  float* X = c->xin.as<float>();
+  float* a = c->buf[0].as<float>();
+  float* b = c->buf[1].as<float>();
+  int rc;
+  if ((rc = prep_input_fp32(x, layout, X, nb, 32, 32, s))) return rc;
+  const float* in = X;
+  int hw = 32;
+  for (int i = 0; i < 6; ++i) {
+    const ConvLayer& l = c->convs[i];
+    if ((rc = conv_fp32(in, l.w32.as<float>(), l.has_bias ? l.bias.as<float>() : nullptr, a, nb, hw, hw, l.cin, l.cout,
+                        3, l.stride, ACT_NONE, ACT_LRELU, s))) return rc;
+    hw = (hw + 2 - 3) / l.stride + 1;
+    in = a;
+    float* t = a; a = b; b = t;
+  }
+  return head_dot_fp32(in, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, c->head_len, s);
+}
+
+extern "C" int sdg_d_forward(sdg_ctx* c, const void* x, int layout, int64_t n, float* logits_out, void* stream) {
+  SDG_REQUIRE(c && x && logits_out, SDG_E_INVALID, "sdg_d_forward: null pointer");
+  SDG_REQUIRE(c->loaded, SDG_E_STATE, "sdg_d_forward: no discriminator weights loaded");
+  SDG_REQUIRE(layout == SDG_LAYOUT_U8_NHWC || layout == SDG_LAYOUT_F32_NCHW, SDG_E_INVALID, "sdg_d_forward: layout=%d", layout);
+  SDG_REQUIRE(n >= 0, SDG_E_INVALID, "sdg_d_forward: n=%lld", (long long)n);
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  SDG_CUDA(cudaSetDevice(c->device));
+  const int S = c->size;
+  const bool bf = c->precision == SDG_PREC_BF16;
+  const int64_t act = max_act_elems(c);
+  int64_t chunk = c->chunk;
+  if (chunk <= 0) {
+    // default: about 1 GiB per activation buffer
+    const int64_t bytes_per = act * (bf ? 2 : 4);
+    chunk = (1LL << 30) / bytes_per;
+    if (chunk < 1) chunk = 1;
+  }
+  if (chunk > n) chunk = n;
+  const size_t esz = bf ? 2 : 4;
+  const int nbuf = c->arch == SDG_ARCH_DCGAN32 ? 2 : ((bf && !c->inplace_relu) ? 4 : 3);
+  for (int i = 0; i < nbuf; ++i) { int rc = c->buf[i].ensure((size_t)chunk * act * esz); if (rc) return rc; }
+  if (bf) {
+    { int rc = c->xin.ensure((size_t)chunk * S * S * 64 * 2); if (rc) return rc; }
+    { int rc = c->xpool.ensure((size_t)chunk * (S / 2) * (S / 2) * 64 * 2); if (rc) return rc; }
+  } else {
+    { int rc = c->xin.ensure((size_t)chunk * S * S * 3 * 4); if (rc) return rc; }
+    { int rc = c->xpool.ensure((size_t)chunk * (S / 2) * (S / 2) * 3 * 4); if (rc) return rc; }
+  }
+  const size_t in_stride = layout == SDG_LAYOUT_U8_NHWC ? (size_t)S * S * 3 : (size_t)S * S * 3 * 4;
+  for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+    const int64_t nb = (n - s0) < chunk ? (n - s0) : chunk;
+    const void* xs = (const char*)x + (size_t)s0 * in_stride;
+    int rc;
+    if (c->arch == SDG_ARCH_DCGAN32) rc = forward_dcgan_fp32(c, xs, layout, nb, logits_out + s0, s);
+    else if (bf) rc = forward_sngan_bf16(c, xs, layout, nb, logits_out + s0, s);
+    else rc = forward_sngan_fp32(c, xs, layout, nb, logits_out + s0, s);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int sdg_conv2d_bf16(const void* in, const void* wb, const float* bias, void* out, int64_t n, int H, int W,
+                               int Cin, int Cout, int ks, int relu, void* stream) {
+  SDG_REQUIRE(in && wb && out, SDG_E_INVALID, "sdg_conv2d_bf16: null pointer");
+  SDG_REQUIRE(ks == 1 || ks == 3, SDG_E_UNSUPPORTED, "sdg_conv2d_bf16: ks=%d", ks);
+  int dev = 0;
+  SDG_CUDA(cudaGetDevice(&dev));
+  { int rc = conv_tc_init(dev); if (rc) return rc; }
+  return conv_tc((const __nv_bfloat16*)in, (const __nv_bfloat16*)wb, bias, (__nv_bfloat16*)out, n, H, W, Cin, Cout,
+                 ks * ks, relu, (cudaStream_t)stream);
+}
+
+extern "C" int sdg_ctx_profile(sdg_ctx* c, int enable) {
+  SDG_REQUIRE(c, SDG_E_INVALID, "sdg_ctx_profile: null ctx");
+  c->profile = enable != 0;
+  c->prof_used = 0;
+  c->prof_flops = 0.0;
+  return 0;
+}
+
+extern "C" int sdg_ctx_profile_read(sdg_ctx* c, double* ms_total_host, int64_t* launches_host, double* flops_host) {
+  SDG_REQUIRE(c && ms_total_host && launches_host && flops_host, SDG_E_INVALID, "sdg_ctx_profile_read: null pointer");
+  double ms = 0.0;
+  for (size_t i = 0; i < c->prof_used; ++i) {
+    SDG_CUDA(cudaEventSynchronize(c->prof_events[i].second));
+    float t = 0.f;
+    SDG_CUDA(cudaEventElapsedTime(&t, c->prof_events[i].first, c->prof_events[i].second));
+    ms += t;
+  }
+  *ms_total_host = ms;
+  *launches_host = (int64_t)c->prof_used;
+  *flops_host = c->prof_flops;
+  c->prof_used = 0;
+  c->prof_flops = 0.0;
+  return 0;
+}

@@ -1,0 +1,64 @@
+// kernels.cuh -- internal launch API between the discriminator engine (dnet.cu) and the kernel files.
+#pragma once
+#include "common.cuh"
+
+namespace sdg {
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };   // LRELU: slope 0.2 (mnist.py:164)
+
+// ---- conv_fp32.cu: IEEE fp32 CUDA-core path (NHWC activations) ---------------------------------
+// wp: packed [ks*ks*Cin][Cout] (k = (ky*ks+kx)*Cin + c), pad = ks/2
+int conv_fp32(const float* in, const float* wp, const float* bias, float* out, int64_t n, int H, int W, int Cin,
+              int Cout, int ks, int stride, int pre_act, int post_act, cudaStream_t s);
+// out = (pool_a ? avgpool2(a) : a) + (pool_b ? avgpool2(relu_b ? relu(b) : b) : ...); b may be null
+int combine_fp32(const float* a, int pool_a, const float* b, int pool_b, int relu_b, float* out, int64_t n,
+                 int Ho, int Wo, int C, cudaStream_t s);
+int prep_input_fp32(const void* x, int layout, float* out_nhwc, int64_t n, int H, int W, cudaStream_t s);
+// logits[i] = bias + sum_c w[c] * sum_hw act(h[i,hw,c])            (SNGAN head: relu, sum-pool, SNLinear)
+int head_sumpool_fp32(const float* h, const float* w, const float* bias, float* logits, int64_t n, int HW, int C,
+                      int relu, cudaStream_t s);
+// logits[i] = bias + sum_j w[j] * h[i,j]                            (DCGAN head: Linear(8192,1))
+int head_dot_fp32(const float* h, const float* w, const float* bias, float* logits, int64_t n, int L,
+                  cudaStream_t s);
+
+// ---- pack.cu: spectral-norm sigma (eval semantics) and weight packing ---------------------------
+struct SnLayer {
+  const float* W;     // [cout, K] torch layout flattened (K = cin*ks*ks)
+  const float* u;     // [cout]
+  int cout, K;
+  float* v;           // scratch [K]
+  float* t;           // scratch [cout]
+};
+int sn_sigmas(const SnLayer* layers_dev, const SnLayer* layers_host, int n_layers, float* sigma_dev,
+              cudaStream_t s);
+// wp[(tap*Cin + c)*Cout + o] = W[o][c][tap] * scale[o] / sigma   (scale may be null; sigma may be null)
+int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float* wp, int Cout, int Cin, int ks,
+                   cudaStream_t s);
+// wb[o][k] = bf16(W[o][c][tap] * scale[o] / sigma) at k = tap*Cin + c, rows zero padded to Kpad (multiple of 64)
+int pack_conv_bf16(const float* W, const float* sigma, const float* scale, __nv_bfloat16* wb, int Cout, int Cin,
+                   int Kpad, int ks, cudaStream_t s);
+int scale_vec(const float* in, const float* sigma, float* out, int n, cudaStream_t s);   // out = in / sigma
+// BatchNorm(eval) folding: scale[o] = gamma/sqrt(var+eps), shift[o] = beta - mean*scale
+int bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+            float* shift, int C, cudaStream_t s);
+// DCGAN fc weight [C*HW] (NCHW flatten) -> NHWC flatten order
+int permute_fc(const float* w, float* out, int C, int HW, cudaStream_t s);
+
+// ---- elem_bf16.cu: streaming helpers of the bf16 path (NHWC bf16, 16-byte accesses) ---------------
+// patches [n,H,W,64]: 3x3x3 neighbourhood of the normalised input at k = tap*3+c (27 real, rest 0);
+// pooled [n,H/2,W/2,64]: avg_pool2d of the normalised input in channels 0..2 (rest 0)
+int stage_first_conv(const void* x, int layout, __nv_bfloat16* patches, __nv_bfloat16* pooled, int64_t n, int H, int W,
+                     cudaStream_t s);
+int combine_bf16(const __nv_bfloat16* a, int pool_a, const __nv_bfloat16* b, int pool_b, __nv_bfloat16* out_relu,
+                 __nv_bfloat16* out_raw, int64_t n, int Ho, int Wo, int C, cudaStream_t s);
+int head_bf16(const __nv_bfloat16* hrelu, const float* w, const float* bias, float* logits, int64_t n, int HW, int C,
+              cudaStream_t s);
+
+// ---- conv_tc.cu: tcgen05 implicit-GEMM convolution (bf16 in, fp32 TMEM accumulate, bf16 out) -----
+// in [n,H,W,Cin] bf16 NHWC (Cin % 64 == 0), wb [Cout][taps*Cin] bf16 K-major, out [n,H,W,Cout] bf16;
+// taps = 9 (3x3, pad 1) or 1 (1x1); stride 1; epilogue: + bias, optional ReLU.
+int conv_tc_init(int device);
+int conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* wb, const float* bias, __nv_bfloat16* out, int64_t n, int H,
+            int W, int Cin, int Cout, int taps, int post_relu, cudaStream_t s);
+
+}  // namespace sdg

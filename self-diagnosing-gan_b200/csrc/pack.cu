@@ -1,0 +1,178 @@
+// pack.cu -- spectral-norm sigma (eval semantics) and weight pre-packing, run once per recording pass.
+//
+// Replaces torch-mimicry SpectralNorm.sn_weights as evaluated in eval mode (spectral_norm.py, SURVEY
+// 8(a) row a5): W2d = W.view(Cout,-1); v = normalize(u W2d); u' = normalize(v W2d^T);
+// sigma = u' W2d v^T; weight used = W / sigma; buffers are NOT updated, so the value is the same for
+// all ceil(N/64) batches of a pass (trainer.py:145-154) and is computed exactly once here.
+// All layers of a discriminator are processed by the same four launches (layer = blockIdx.y / .x).
+#include "kernels.cuh"
+
+namespace sdg {
+
+constexpr float kSnEps = 1e-12f;
+
+// v_raw[k] = sum_o u[o] * W[o][k]     (thread per column k: coalesced across k)
+__global__ void __launch_bounds__(256) sn_uW_kernel(const SnLayer* __restrict__ layers) {
+  const SnLayer L = layers[blockIdx.y];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L.K; k += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int o = 0; o < L.cout; ++o) acc = fmaf(L.u[o], L.W[(int64_t)o * L.K + k], acc);
+    L.v[k] = acc;
+  }
+}
+
+__device__ float block_sum(float v, float* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+  __syncthreads();
+  return t;
+}
+
+// v = v_raw / max(||v_raw||, eps)      (one CTA per layer)
+__global__ void __launch_bounds__(256) sn_normalize_v_kernel(const SnLayer* __restrict__ layers) {
+  __shared__ float red[8];
+  const SnLayer L = layers[blockIdx.x];
+  float s = 0.f;
+  for (int k = threadIdx.x; k < L.K; k += blockDim.x) s = fmaf(L.v[k], L.v[k], s);
+  float nrm = sqrtf(block_sum(s, red));
+  float d = fmaxf(nrm, kSnEps);
+  for (int k = threadIdx.x; k < L.K; k += blockDim.x) L.v[k] = L.v[k] / d;
+}
+
+// t[o] = sum_k W[o][k] * v[k]          (one warp per row)
+__global__ void __launch_bounds__(256) sn_Wv_kernel(const SnLayer* __restrict__ layers) {
+  const SnLayer L = layers[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int o = blockIdx.x * wpb + (threadIdx.x >> 5); o < L.cout; o += gridDim.x * wpb) {
+    const float* row = L.W + (int64_t)o * L.K;
+    float acc = 0.f;
+    for (int k = lane; k < L.K; k += 32) acc = fmaf(row[k], L.v[k], acc);
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) L.t[o] = acc;
+  }
+}
+
+// u' = t / max(||t||, eps); sigma = u' . t     (one CTA per layer)
+__global__ void __launch_bounds__(256) sn_sigma_kernel(const SnLayer* __restrict__ layers, float* __restrict__ sigma) {
+  __shared__ float red[8];
+  const SnLayer L = layers[blockIdx.x];
+  float s = 0.f;
+  for (int o = threadIdx.x; o < L.cout; o += blockDim.x) s = fmaf(L.t[o], L.t[o], s);
+  float nrm = sqrtf(block_sum(s, red));
+  float d = fmaxf(nrm, kSnEps);
+  float dot = 0.f;
+  for (int o = threadIdx.x; o < L.cout; o += blockDim.x) dot = fmaf(L.t[o] / d, L.t[o], dot);
+  dot = block_sum(dot, red);
+  if (threadIdx.x == 0) sigma[blockIdx.x] = dot;
+}
+
+int sn_sigmas(const SnLayer* layers_dev, const SnLayer* layers_host, int n_layers, float* sigma_dev,
+              cudaStream_t s) {
+  int maxK = 1, maxC = 1;
+  for (int i = 0; i < n_layers; ++i) {
+    maxK = layers_host[i].K > maxK ? layers_host[i].K : maxK;
+    maxC = layers_host[i].cout > maxC ? layers_host[i].cout : maxC;
+  }
+  SDG_LAUNCH(sn_uW_kernel, dim3((unsigned)cdiv(maxK, 256), n_layers), 256, 0, s, layers_dev);
+  SDG_LAUNCH(sn_normalize_v_kernel, n_layers, 256, 0, s, layers_dev);
+  SDG_LAUNCH(sn_Wv_kernel, dim3((unsigned)cdiv(maxC, 8), n_layers), 256, 0, s, layers_dev);
+  SDG_LAUNCH(sn_sigma_kernel, n_layers, 256, 0, s, layers_dev, sigma_dev);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_conv_fp32_kernel(const float* __restrict__ W, const float* __restrict__ sigma, const float* __restrict__ scale,
+                      float* __restrict__ wp, int Cout, int Cin, int taps) {
+  const int total = Cout * Cin * taps;
+  const float sg = sigma ? sigma[0] : 1.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int o = i % Cout;
+    int k = i / Cout;
+    int tap = k / Cin, c = k - tap * Cin;
+    float w = W[((int64_t)o * Cin + c) * taps + tap];
+    if (sigma) w = w / sg;                       // self.weight / sigma
+    if (scale) w = w * scale[o];
+    wp[i] = w;
+  }
+}
+
+int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float* wp, int Cout, int Cin, int ks,
+                   cudaStream_t s) {
+  int total = Cout * Cin * ks * ks;
+  SDG_LAUNCH(pack_conv_fp32_kernel, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wp, Cout, Cin, ks * ks);
+  return 0;
+}
+
+__global__ void __launch_bounds__(256)
+pack_conv_bf16_kernel(const float* __restrict__ W, const float* __restrict__ sigma, const float* __restrict__ scale,
+                      __nv_bfloat16* __restrict__ wb, int Cout, int Cin, int Kpad, int taps) {
+  const int total = Cout * Kpad;
+  const float sg = sigma ? sigma[0] : 1.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int k = i % Kpad;
+    int o = i / Kpad;
+    float w = 0.f;
+    if (k < taps * Cin) {
+      int tap = k / Cin, c = k - tap * Cin;
+      w = W[((int64_t)o * Cin + c) * taps + tap];
+      if (sigma) w = w / sg;
+      if (scale) w = w * scale[o];
+    }
+    wb[i] = __float2bfloat16_rn(w);
+  }
+}
+
+int pack_conv_bf16(const float* W, const float* sigma, const float* scale, __nv_bfloat16* wb, int Cout, int Cin,
+                   int Kpad, int ks, cudaStream_t s) {
+  int total = Cout * Kpad;
+  SDG_LAUNCH(pack_conv_bf16_kernel, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wb, Cout, Cin, Kpad,
+             ks * ks);
+  return 0;
+}
+
+__global__ void scale_vec_kernel(const float* __restrict__ in, const float* __restrict__ sigma, float* __restrict__ out,
+                                 int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = sigma ? in[i] / sigma[0] : in[i];
+}
+
+int scale_vec(const float* in, const float* sigma, float* out, int n, cudaStream_t s) {
+  SDG_LAUNCH(scale_vec_kernel, (unsigned)cdiv(n, 256), 256, 0, s, in, sigma, out, n);
+  return 0;
+}
+
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                               float* scale, float* shift, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) {
+    float sc = gamma[i] / sqrtf(var[i] + eps);
+    scale[i] = sc;
+    shift[i] = beta[i] - mean[i] * sc;
+  }
+}
+
+int bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+            float* shift, int C, cudaStream_t s) {
+  SDG_LAUNCH(bn_fold_kernel, (unsigned)cdiv(C, 256), 256, 0, s, gamma, beta, mean, var, eps, scale, shift, C);
+  return 0;
+}
+
+__global__ void permute_fc_kernel(const float* __restrict__ w, float* __restrict__ out, int C, int HW) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;       // NHWC index p*C + c
+  if (i < C * HW) {
+    int c = i % C, p = i / C;
+    out[i] = w[c * HW + p];
+  }
+}
+
+int permute_fc(const float* w, float* out, int C, int HW, cudaStream_t s) {
+  SDG_LAUNCH(permute_fc_kernel, (unsigned)cdiv((int64_t)C * HW, 256), 256, 0, s, w, out, C, HW);
+  return 0;
+}
+
+}  // namespace sdg

@@ -1,0 +1,241 @@
+// stats.cu -- per-sample running statistics and the LDR score stage (fp64, HBM-streaming kernels).
+//
+// Compiled with -fmad=false: the reference evaluates these expressions in NumPy float64 with separate
+// multiplies and adds (diagan-pkg/diagan/utils/plot.py:243-248); contraction into FMA would change the
+// last bit and break the bit-exact comparison against np.mean / np.var / np.std.
+//
+// Rooflines (DESIGN.md "Kernels"): all kernels here are HBM-bound streams.
+//   stats_update        4 B read + 4*8 B read + 4*8 B write = 68 B / sample
+//   window_moments<f32> 4*T B read + 8 B per requested output / sample   (T*N re-read served by L1/L2)
+//   score_floor_min     16 B read + 8 B write / sample / conf
+//   score_clip          8 B read + 8 B write / sample / conf
+#include "common.cuh"
+
+namespace sdg {
+
+// ------------------------------------------------------------------------------------------------
+// Welford + last + sum|delta| update, two samples per thread (16-byte loads/stores on the fp64 state)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void welford_step(double x, double inv_count, bool first,
+                                             double& mean, double& m2, double& last, double& sad) {
+  if (!first) sad = sad + fabs(x - last);
+  double d = x - mean;
+  mean = mean + d * inv_count;
+  m2 = m2 + d * (x - mean);
+  last = x;
+}
+
+__global__ void __launch_bounds__(256)
+stats_update_kernel(const float* __restrict__ snap, double* __restrict__ mean, double* __restrict__ m2,
+                    double* __restrict__ last, double* __restrict__ sad, int64_t n, int64_t t, int vec_ok) {
+  const double inv = 1.0 / (double)(t + 1);
+  const bool first = (t == 0);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t pairs = vec_ok ? n / 2 : 0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += stride) {
+    float2 x = reinterpret_cast<const float2*>(snap)[p];
+    double2 me, q, la, sa;
+    if (first) {
+      me = make_double2(0.0, 0.0); q = me; la = me; sa = me;
+    } else {
+      me = reinterpret_cast<double2*>(mean)[p];
+      q = reinterpret_cast<double2*>(m2)[p];
+      la = reinterpret_cast<double2*>(last)[p];
+      sa = reinterpret_cast<double2*>(sad)[p];
+    }
+    welford_step((double)x.x, inv, first, me.x, q.x, la.x, sa.x);
+    welford_step((double)x.y, inv, first, me.y, q.y, la.y, sa.y);
+    reinterpret_cast<double2*>(mean)[p] = me;
+    reinterpret_cast<double2*>(m2)[p] = q;
+    reinterpret_cast<double2*>(last)[p] = la;
+    reinterpret_cast<double2*>(sad)[p] = sa;
+  }
+  // scalar tail (odd n, or unaligned shard base)
+  for (int64_t i = pairs * 2 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double me = 0.0, q = 0.0, la = 0.0, sa = 0.0;
+    if (!first) { me = mean[i]; q = m2[i]; la = last[i]; sa = sad[i]; }
+    welford_step((double)snap[i], inv, first, me, q, la, sa);
+    mean[i] = me; m2[i] = q; last[i] = la; sad[i] = sa;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// two-pass window moments in NumPy's axis-0 order: thread i owns sample i, warps read rows coalesced
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+window_moments_kernel(const T* __restrict__ snaps, int64_t Tn, int64_t n, int64_t ld,
+                      double* __restrict__ mean_out, double* __restrict__ var_out,
+                      double* __restrict__ ldrd_out, double* __restrict__ ldr_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const T* col = snaps + i;
+    double acc = 0.0, sad = 0.0, prev = 0.0;
+    int64_t t = 0;
+    // unrolled by 4: four independent loads in flight, additions still strictly in row order
+    for (; t + 4 <= Tn; t += 4) {
+      double x0 = (double)col[(t + 0) * ld], x1 = (double)col[(t + 1) * ld];
+      double x2 = (double)col[(t + 2) * ld], x3 = (double)col[(t + 3) * ld];
+      if (t > 0) sad = sad + fabs(x0 - prev);
+      sad = sad + fabs(x1 - x0);
+      sad = sad + fabs(x2 - x1);
+      sad = sad + fabs(x3 - x2);
+      acc = acc + x0; acc = acc + x1; acc = acc + x2; acc = acc + x3;
+      prev = x3;
+    }
+    for (; t < Tn; ++t) {
+      double x = (double)col[t * ld];
+      if (t > 0) sad = sad + fabs(x - prev);
+      acc = acc + x;
+      prev = x;
+    }
+    const double mean = acc / (double)Tn;
+    if (mean_out) mean_out[i] = mean;
+    if (ldr_out) ldr_out[i] = prev;
+    if (ldrd_out) ldrd_out[i] = sad / (double)(Tn - 1);
+    if (var_out) {
+      double sq = 0.0;
+      t = 0;
+      for (; t + 4 <= Tn; t += 4) {   // second pass: this thread's column again (L1/L2 resident)
+        double d0 = (double)col[(t + 0) * ld] - mean, d1 = (double)col[(t + 1) * ld] - mean;
+        double d2 = (double)col[(t + 2) * ld] - mean, d3 = (double)col[(t + 3) * ld] - mean;
+        sq = sq + d0 * d0; sq = sq + d1 * d1; sq = sq + d2 * d2; sq = sq + d3 * d3;
+      }
+      for (; t < Tn; ++t) {
+        double d = (double)col[t * ld] - mean;
+        sq = sq + d * d;
+      }
+      var_out[i] = sq / (double)(Tn - 1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// score phase 1: floor + per-conf global min
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_double(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a;
+  while (v < __longlong_as_double((long long)old)) {
+    unsigned long long assumed = old;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    if (old == assumed) break;
+  }
+}
+
+__global__ void fill_double_kernel(double* p, int n, double v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+struct ConfTable { double c[128]; };
+
+__global__ void __launch_bounds__(256)
+score_floor_min_kernel(const double* __restrict__ mean, const double* __restrict__ var, int64_t n,
+                       ConfTable conf, double floor, double m2_over, double* __restrict__ score,
+                       double* __restrict__ mins) {
+  const int j = blockIdx.y;
+  const double c = conf.c[j];
+  double* out = score + (int64_t)j * n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double lmin = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double v = var[i];
+    if (m2_over > 0.0) v = v / m2_over;
+    double s = mean[i] + c * sqrt(v);
+    s = s < floor ? floor : s;            // np.clip(a_min=floor): NaN propagates like NumPy
+    out[i] = s;
+    lmin = s < lmin ? s : lmin;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    double other = __shfl_xor_sync(0xffffffffu, lmin, o);
+    lmin = other < lmin ? other : lmin;
+  }
+  __shared__ double wmin[8];
+  if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = lmin;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = wmin[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = wmin[w] < m ? wmin[w] : m;
+    atomic_min_double(&mins[j], m);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+score_clip_kernel(double* __restrict__ score, int64_t n, const double* __restrict__ mins, double ratio,
+                  double eps) {
+  const int j = blockIdx.y;
+  const double upper = mins[j] * ratio;
+  double* s = score + (int64_t)j * n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double v = s[i];
+    v = v > upper ? upper : v;
+    if (eps > 0.0) v = v < eps ? eps : v;
+    s[i] = v;
+  }
+}
+
+}  // namespace sdg
+
+using namespace sdg;
+
+extern "C" int sdg_stats_update(const float* snapshot, double* mean, double* m2, double* last, double* sad,
+                                int64_t n, int64_t t, void* stream) {
+  SDG_REQUIRE(snapshot && mean && m2 && last && sad, SDG_E_INVALID, "sdg_stats_update: null pointer");
+  SDG_REQUIRE(n >= 0 && t >= 0, SDG_E_INVALID, "sdg_stats_update: n=%lld t=%lld", (long long)n, (long long)t);
+  if (n == 0) return 0;
+  auto al = [](const void* p, size_t a) { return ((uintptr_t)p % a) == 0; };
+  int vec_ok = al(snapshot, 8) && al(mean, 16) && al(m2, 16) && al(last, 16) && al(sad, 16);
+  int grid = stream_grid(cdiv(n, 2), 256);
+  SDG_LAUNCH(stats_update_kernel, grid, 256, 0, stream, snapshot, mean, m2, last, sad, n, t, vec_ok);
+  return 0;
+}
+
+template <typename T>
+static int window_moments(const T* snaps, int64_t Tn, int64_t n, int64_t ld, double* mean, double* var,
+                          double* ldrd, double* ldr, void* stream) {
+  SDG_REQUIRE(snaps, SDG_E_INVALID, "sdg_window_moments: null snapshots");
+  SDG_REQUIRE(Tn >= 1 && n >= 0 && ld >= n, SDG_E_INVALID, "sdg_window_moments: T=%lld n=%lld ld=%lld",
+              (long long)Tn, (long long)n, (long long)ld);
+  if (n == 0) return 0;
+  int grid = stream_grid(n, 256);
+  SDG_LAUNCH(window_moments_kernel<T>, grid, 256, 0, stream, snaps, Tn, n, ld, mean, var, ldrd, ldr);
+  return 0;
+}
+
+extern "C" int sdg_window_moments_f32(const float* snaps, int64_t T, int64_t n, int64_t ld, double* mean,
+                                      double* var, double* ldrd, double* ldr, void* stream) {
+  return window_moments<float>(snaps, T, n, ld, mean, var, ldrd, ldr, stream);
+}
+
+extern "C" int sdg_window_moments_f64(const double* snaps, int64_t T, int64_t n, int64_t ld, double* mean,
+                                      double* var, double* ldrd, double* ldr, void* stream) {
+  return window_moments<double>(snaps, T, n, ld, mean, var, ldrd, ldr, stream);
+}
+
+extern "C" int sdg_score_floor_min(const double* mean, const double* var, int64_t n, const double* conf_host,
+                                   int n_conf, double floor, double var_is_m2_over, double* score, double* mins,
+                                   void* stream) {
+  SDG_REQUIRE(mean && var && conf_host && score && mins, SDG_E_INVALID, "sdg_score_floor_min: null pointer");
+  SDG_REQUIRE(n_conf >= 1 && n_conf <= 128, SDG_E_INVALID, "sdg_score_floor_min: n_conf=%d (1..128)", n_conf);
+  SDG_REQUIRE(n >= 0, SDG_E_INVALID, "sdg_score_floor_min: n=%lld", (long long)n);
+  ConfTable tab;
+  for (int j = 0; j < n_conf; ++j) tab.c[j] = conf_host[j];
+  SDG_LAUNCH(fill_double_kernel, 1, 128, 0, stream, mins, n_conf, __builtin_inf());
+  if (n == 0) return 0;
+  int gx = stream_grid(n, 256, n_conf >= 8 ? 1 : 8);
+  SDG_LAUNCH(score_floor_min_kernel, dim3(gx, n_conf), 256, 0, stream, mean, var, n, tab, floor,
+             var_is_m2_over, score, mins);
+  return 0;
+}
+
+extern "C" int sdg_score_clip(double* score, int64_t n, int n_conf, const double* mins, double ratio, double eps,
+                              void* stream) {
+  SDG_REQUIRE(score && mins, SDG_E_INVALID, "sdg_score_clip: null pointer");
+  SDG_REQUIRE(n_conf >= 1 && n >= 0, SDG_E_INVALID, "sdg_score_clip: n_conf=%d n=%lld", n_conf, (long long)n);
+  if (n == 0) return 0;
+  int gx = stream_grid(n, 256, n_conf >= 8 ? 1 : 8);
+  SDG_LAUNCH(score_clip_kernel, dim3(gx, n_conf), 256, 0, stream, score, n, mins, ratio, eps);
+  return 0;
+}

@@ -1,0 +1,116 @@
+"""Multi-GPU side of the diagnosis path: shard by sample index, exchange only finished vectors.
+
+Mirrors the module-level functions of ``stylegan2/train_ffhq.py`` that the reference uses for its
+distributed logit pass -- ``get_logit`` (:128-143), ``concat_all_gather`` (:150-161), ``save_logit``
+(:145-147) -- and the helpers of ``stylegan2/distributed.py`` it relies on (``get_rank``,
+``get_world_size``, :7-16,34-41).
+
+Design: rank r owns the contiguous index range ``[r*ceil(N/W), min(N,(r+1)*ceil(N/W)))``,
+keeps that slice of the dataset resident, and scores it with replicated weights.  The reference
+all-gathers ``(idx, logit)`` twice per batch of 4; here each pass does ONE all-gather of the finished
+shard, and the score stage adds ONE MIN all-reduce of the per-key clip bounds (``score.min()`` in
+``clip_max_ratio``, plot.py:226-228, is the only cross-sample coupling).  Both are latency-bound NCCL
+calls over NVLink (tens of KB); there is no data-path collective inside the discriminator forward.
+
+The collectives work on whatever device the tensors live on, so the index arithmetic is testable with
+the ``gloo`` backend on CPU (tests/test_distributed_gloo.py).
+"""
+from __future__ import annotations
+
+import pickle
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+
+def get_rank() -> int:
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def get_world_size() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def shard_size(n: int, world: int) -> int:
+    return (n + world - 1) // world
+
+
+def shard_range(n: int, rank: int = None, world: int = None):
+    """Contiguous dataset-index range owned by ``rank``; trailing ranks may be short or empty."""
+    rank = get_rank() if rank is None else rank
+    world = get_world_size() if world is None else world
+    s = shard_size(n, world)
+    lo = min(n, rank * s)
+    return lo, min(n, lo + s)
+
+
+def all_gather_shards(local: torch.Tensor, n: int) -> torch.Tensor:
+    """local: this rank's finished slice ``[hi-lo, ...]`` -> the full ``[n, ...]`` vector on every rank.
+    One collective; ragged tails are handled by padding each shard to ``ceil(n/W)``."""
+    world = get_world_size()
+    if world == 1:
+        return local[:n]
+    s = shard_size(n, world)
+    tail = local.shape[1:]
+    padded = local
+    if local.shape[0] != s:
+        padded = local.new_zeros((s,) + tuple(tail))
+        padded[:local.shape[0]] = local
+    out = local.new_empty((world * s,) + tuple(tail))
+    dist.all_gather_into_tensor(out, padded.contiguous())
+    return out[:n]
+
+
+def all_reduce_min_(t: torch.Tensor) -> torch.Tensor:
+    """In-place MIN all-reduce (the clip bound of clip_max_ratio across shards)."""
+    if get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return t
+
+
+def all_reduce_max_(t: torch.Tensor) -> torch.Tensor:
+    """In-place MAX all-reduce (the DRS running maximum when burn-in batches are spread over ranks)."""
+    if get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t
+
+
+@torch.no_grad()
+def concat_all_gather(tensor: torch.Tensor) -> torch.Tensor:
+    """Same contract as train_ffhq.py:150-161: equal-shaped per-rank tensors concatenated on dim 0."""
+    world = get_world_size()
+    if world == 1:
+        return tensor
+    out = tensor.new_empty((world * tensor.shape[0],) + tuple(tensor.shape[1:]))
+    dist.all_gather_into_tensor(out, tensor.contiguous())
+    return out
+
+
+def get_logit(recorder, netD, step=None) -> torch.Tensor:
+    """Distributed recording pass (train_ffhq.py:128-143 semantics: every rank ends up with the full
+    vector).  ``recorder`` is a :class:`diagan_b200.trainer.trainer.LogitRecorder` whose ``shard`` is this
+    rank's range; returns float32 [N] on the device."""
+    n = recorder.n
+    lo, hi = shard_range(n)
+    recorder.shard = (lo, hi)
+    snap = recorder.record(netD)
+    full = all_gather_shards(snap[lo:hi], n)
+    if step is not None:
+        recorder.observe(step, full)
+    return full
+
+
+def sharded_score(recorder, conf: float, eps: float = 0.0) -> torch.Tensor:
+    """ldr_conf score of the whole dataset from per-rank running statistics: local floor+min, MIN
+    all-reduce of the bound, local clip, one all-gather of the float64 shard -> float64 [N]."""
+    local = recorder.stats.score(conf, eps=eps, min_reduce=all_reduce_min_)
+    return all_gather_shards(local, recorder.n)
+
+
+def save_logit(logits_dict, output_path):
+    """train_ffhq.py:145-147 (rank 0 calls it, :321-323)."""
+    for name, logits in logits_dict.items():
+        host = {k: (v.double().cpu().numpy() if torch.is_tensor(v) else v) for k, v in logits.items()}
+        with open(Path(output_path) / f'logits_{name}.pkl', 'wb') as f:
+            pickle.dump(host, f)

@@ -1,0 +1,71 @@
+"""Synthetic stand-ins for datasets and checkpoints (no network on the GPU box): random-init
+discriminator ``state_dict``s with the reference's key names and shapes, and uniform uint8 images of
+CIFAR-10 / CelebA / Colour-MNIST shape.  Used by ``bench.py`` and ``__graft_entry__.smoke``."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .engine import sngan_layer_keys
+
+_SNGAN_BLOCKS = {
+    32: [("block1", "opt", 3, 128, True), ("block2", "res", 128, 128, True),
+         ("block3", "res", 128, 128, False), ("block4", "res", 128, 128, False)],
+    64: [("block1", "opt", 3, 64, True), ("block2", "res", 64, 128, True), ("block3", "res", 128, 256, True),
+         ("block4", "res", 256, 512, True), ("block5", "res", 512, 1024, True)],
+}
+
+
+def sngan_shapes(arch: int) -> dict:
+    """{layer key: weight shape} of torch-mimicry SNGANDiscriminator32/64."""
+    shapes = {}
+    for name, kind, cin, cout, down in _SNGAN_BLOCKS[arch]:
+        hidden = cout if kind == "opt" else cin
+        shapes[f"{name}.c1"] = (hidden, cin, 3, 3)
+        shapes[f"{name}.c2"] = (cout, hidden, 3, 3)
+        if kind == "opt" or cin != cout or down:
+            shapes[f"{name}.c_sc"] = (cout, cin, 1, 1)
+    head = "l5" if arch == 32 else "l6"
+    shapes[head] = (1, 128 if arch == 32 else 1024)
+    assert list(shapes.keys()) == sngan_layer_keys(arch)
+    return shapes
+
+
+def sngan_state_dict(arch: int, seed: int = 1) -> dict:
+    """Xavier-uniform weights (gain sqrt2 for 3x3, 1 for 1x1 / linear), uniform bias, sn_u ~ N(0,1)."""
+    rng = np.random.RandomState(seed)
+    sd = {}
+    for key, shape in sngan_shapes(arch).items():
+        fan_in = int(np.prod(shape[1:]))
+        fan_out = shape[0] * (int(np.prod(shape[2:])) if len(shape) == 4 else 1)
+        gain = math.sqrt(2.0) if (len(shape) == 4 and shape[2] == 3) else 1.0
+        bound = gain * math.sqrt(6.0 / (fan_in + fan_out))
+        sd[f"{key}.weight"] = torch.from_numpy(rng.uniform(-bound, bound, shape).astype(np.float32))
+        bb = 1.0 / math.sqrt(fan_in)
+        sd[f"{key}.bias"] = torch.from_numpy(rng.uniform(-bb, bb, (shape[0],)).astype(np.float32))
+        sd[f"{key}.sn_u"] = torch.from_numpy(rng.standard_normal((1, shape[0])).astype(np.float32))
+        sd[f"{key}.sn_sigma"] = torch.ones(1)
+    return sd
+
+
+def perturb_(state_dict: dict, step: int, scale: float = 1e-3, device=None) -> dict:
+    """W += scale * randn(seed = step): a deterministic stand-in for the training between two recording
+    passes, so that per-sample logits move and std > 0."""
+    gen = torch.Generator(device=device or "cpu").manual_seed(int(step))
+    out = dict(state_dict)
+    for k in sorted(state_dict):
+        if k.endswith(".weight"):
+            w = state_dict[k]
+            out[k] = w + scale * torch.randn(w.shape, generator=gen, device=w.device, dtype=w.dtype)
+    return out
+
+
+def uniform_images_u8(n: int, size: int, seed: int = 1, device="cpu", pin: bool = False) -> torch.Tensor:
+    """uint8 [n,size,size,3] ~ U{0..255} (CIFAR-10 shape for size 32, CelebA for 64)."""
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randint(0, 256, (n, size, size, 3), dtype=torch.uint8, generator=gen)
+    if pin:
+        x = x.pin_memory()
+    return x.to(device) if device != "cpu" else x

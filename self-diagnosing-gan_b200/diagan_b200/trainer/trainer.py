@@ -1,0 +1,239 @@
+"""The recording side of ``diagan.trainer.trainer.LogTrainer`` (diagan-pkg/diagan/trainer/trainer.py).
+
+What is mirrored (same names, argument meaning, return types):
+
+* ``_get_logit(netD, eval_mode=False) -> np.float64 [len(dataset)]`` indexed by dataset index, leaves
+  ``netD`` in train mode on exit                                              (trainer.py:142-156)
+* ``_save_logit(logits_dict)`` -> ``output_path / 'logits_<name>.pkl'``, ``{step: float64[N]}``
+                                                                              (trainer.py:138-140)
+* the recording trigger and the ``logit_results`` bookkeeping                 (trainer.py:222,328-351)
+
+What is NOT here: the GAN optimisation loop of ``LogTrainer.train()`` (trainer.py:208-327), which is
+outside the diagnosis path.  ``diagan_b200.patch.install()`` grafts ``_get_logit`` / ``_save_logit`` onto
+the reference's own ``LogTrainer`` so its ``train()`` runs unchanged.
+
+The B200-native difference: the whole training set is resident in HBM (uint8 NHWC, 154 MB for
+CIFAR-10), the discriminator weights are re-packed once per pass (sigma is constant in eval mode) and
+the pass is a handful of launches per chunk of samples instead of 782 DataLoader batches with a
+device->host sync each.
+"""
+from __future__ import annotations
+
+import pickle
+from collections import defaultdict
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .. import _lib, engine
+
+
+class ResidentDataset:
+    """The training set as the recording pass wants it: one device tensor in dataset-index order,
+    either raw uint8 NHWC (normalised on load, transform.py:3-11) or float32 NCHW in [-1,1]."""
+
+    def __init__(self, data: torch.Tensor):
+        if not data.is_cuda:
+            raise _lib.SdgError("ResidentDataset needs a CUDA tensor")
+        if data.dtype == torch.uint8:
+            assert data.dim() == 4 and data.shape[3] == 3, "uint8 data must be [N,H,W,3]"
+        elif data.dtype == torch.float32:
+            assert data.dim() == 4 and data.shape[1] == 3, "float32 data must be [N,3,H,W]"
+        else:
+            raise _lib.SdgError(f"unsupported dataset dtype {data.dtype}")
+        self.data = data.contiguous()
+
+    def __len__(self):
+        return self.data.shape[0]
+
+    @classmethod
+    def from_numpy_u8(cls, arr: np.ndarray, device):
+        """e.g. ``torchvision.datasets.CIFAR10(...).data`` ([N,32,32,3] uint8)."""
+        return cls(torch.from_numpy(np.ascontiguousarray(arr)).to(device))
+
+    @classmethod
+    def from_dataset(cls, dataset, device, batch_size=1024):
+        """Materialise any ``WeightedDataset``-style dataset (``(data, target, weight, index)`` items,
+        predefined.py:17-27, or ``(img, idx)``, stylegan2/dataset.py:63) once, as float32 NCHW."""
+        n = len(dataset)
+        first = dataset[0]
+        shape = tuple(first[0].shape)
+        out = torch.empty((n,) + shape, dtype=torch.float32, device=device)
+        loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=False, num_workers=0)
+        for item in loader:
+            data, idx = item[0], item[-1]
+            out[idx.to(device)] = data.to(device=device, dtype=torch.float32)
+        return cls(out)
+
+
+class LogitRecorder:
+    """Full-dataset discriminator logit recording + running statistics for one rank's shard.
+
+    ``shard = (lo, hi)`` restricts the pass to dataset indices [lo, hi) (multi-GPU); the
+    snapshot vector is always full length N so that ``diagan_b200.distributed`` can all-gather in place.
+    """
+
+    def __init__(self, dataset: ResidentDataset = None, device=None, precision="bf16", inplace_relu=True,
+                 shard=None, keep_snapshots=True, stats_window=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dataset = dataset
+        self.precision = precision
+        self.inplace_relu = inplace_relu
+        self.engine = engine.DiscriminatorEngine(self.device)
+        self.n = len(dataset) if dataset is not None else None
+        self.shard = shard
+        self.keep_snapshots = keep_snapshots
+        self.stats_window = stats_window          # (start, end): only steps in [start, end) feed the stats
+        self.snapshots = {}                       # step -> float32 [N] device tensor
+        self.stats = None
+
+    def _range(self):
+        return (0, self.n) if self.shard is None else self.shard
+
+    def load_weights(self, netD):
+        sd = netD.state_dict() if hasattr(netD, "state_dict") else netD
+        self.engine.load(sd, self.precision if engine.detect_arch(sd) != "dcgan32" else "fp32", self.inplace_relu)
+
+    def record(self, netD, step=None, out: torch.Tensor = None) -> torch.Tensor:
+        """One recording pass over the resident dataset (this rank's shard) -> float32 [N] on the device."""
+        if self.dataset is None:
+            raise _lib.SdgError("LogitRecorder.record needs a ResidentDataset")
+        self.load_weights(netD)
+        lo, hi = self._range()
+        snap = torch.zeros(self.n, dtype=torch.float32, device=self.device) if out is None else out
+        self.engine.forward(self.dataset.data[lo:hi], out=snap[lo:hi])
+        if step is not None:
+            self.observe(step, snap)
+        return snap
+
+    def observe(self, step, snap: torch.Tensor):
+        """Book-keep one finished snapshot: keep it (for the pickle) and fold it into the running stats."""
+        if self.keep_snapshots:
+            self.snapshots[step] = snap
+        w = self.stats_window
+        if w is None or (w[0] <= step < w[1]):
+            lo, hi = self._range()
+            if self.stats is None:
+                self.stats = engine.RunningStats(hi - lo, self.device)
+            self.stats.update(snap[lo:hi])
+
+    def record_from_host(self, netD, host_u8: torch.Tensor, step=None, chunk: int = 8192) -> torch.Tensor:
+        """Recording pass over a dataset that lives in (pinned) HOST memory: uint8 NHWC chunks are
+        copied on a side stream into two staging buffers while the previous chunk is in the engine, so
+        the H2D traffic (3 KB/sample for CIFAR shape) overlaps the forward."""
+        self.load_weights(netD)
+        n = host_u8.shape[0]
+        self.n = n
+        snap = torch.zeros(n, dtype=torch.float32, device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._stage = None
+        shape = (min(chunk, n),) + tuple(host_u8.shape[1:])
+        if self._stage is None or self._stage[0].shape != shape:
+            self._stage = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self._ev_copied = [torch.cuda.Event() for _ in range(2)]
+            self._ev_used = [torch.cuda.Event() for _ in range(2)]
+            for e in self._ev_used:
+                e.record(main)
+        starts = list(range(0, n, chunk))
+        for i, s0 in enumerate(starts):
+            b = i & 1
+            nb = min(chunk, n - s0)
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._ev_used[b])          # staging buffer free again
+                self._stage[b][:nb].copy_(host_u8[s0:s0 + nb], non_blocking=True)
+                self._ev_copied[b].record(self._copy_stream)
+            main.wait_event(self._ev_copied[b])
+            self.engine.forward(self._stage[b][:nb], out=snap[s0:s0 + nb])
+            self._ev_used[b].record(main)
+        if step is not None:
+            self.observe(step, snap)
+        return snap
+
+    def record_from_loader(self, netD, dataloader, n=None) -> torch.Tensor:
+        """Generic feeding path with the reference's item contract: batches ``(data, target, weight,
+        index)`` (predefined.py:22-24) or ``(img, idx)`` come from a DataLoader, the forward still runs in
+        the CUDA engine, logits are scattered by dataset index (trainer.py:148-154)."""
+        self.load_weights(netD)
+        n = len(dataloader.dataset) if n is None else n
+        snap = torch.zeros(n, dtype=torch.float32, device=self.device)
+        for item in dataloader:
+            data, idx = item[0], item[-1]
+            x = data.to(device=self.device, dtype=torch.float32).contiguous()
+            snap[idx.to(self.device)] = self.engine.forward(x)
+        return snap
+
+
+# ---- reference-named methods (usable standalone or grafted onto the reference class) -------------
+
+def _get_logit(self, netD, eval_mode=False):
+    """``LogTrainer._get_logit`` (trainer.py:142-156): float64 [N] by dataset index.
+
+    Uses ``self.recorder`` (a :class:`LogitRecorder` with a resident dataset) when present, otherwise
+    feeds the CUDA engine from ``self.dataloader``.  Only eval-mode logits have a per-sample definition
+    for discriminators with BatchNorm/Dropout; SNGAN is mode-independent apart from
+    the spectral-norm buffers, which this pass never updates."""
+    rec = getattr(self, "recorder", None)
+    if rec is None:
+        rec = LogitRecorder(None, getattr(self, "device", None))
+        self.recorder = rec
+    sd = netD.state_dict()
+    if not eval_mode and engine.detect_arch(sd) == "dcgan32":
+        raise _lib.SdgError("train-mode logits of the DCGAN discriminator (Dropout + batch-stat BatchNorm) are "
+                            "stochastic and batch dependent; only eval_mode=True is reproducible")
+    if rec.dataset is not None:
+        snap = rec.record(netD)
+    else:
+        snap = rec.record_from_loader(netD, self.dataloader)
+    if hasattr(netD, "train"):
+        netD.train()                                        # trainer.py:155
+    return snap.double().cpu().numpy()                      # fp32 values widened, like trainer.py:144,154
+
+
+def _save_logit(self, logits_dict):
+    """``LogTrainer._save_logit`` (trainer.py:138-140): one pickle per name, ``{step: float64[N]}``."""
+    for name, logits in logits_dict.items():
+        host = {k: (v.double().cpu().numpy() if torch.is_tensor(v) else v) for k, v in logits.items()}
+        with open(Path(self.output_path) / f'logits_{name}.pkl', 'wb') as f:
+            pickle.dump(host, f)
+
+
+class LogTrainer:
+    """Recording-side stand-in for the reference ``LogTrainer``: same constructor keywords for everything
+    that concerns logit recording (trainer.py:16-49) and the same trigger (trainer.py:328-351), driven by
+    ``on_step(global_step)`` from whatever loop trains the GAN."""
+
+    _get_logit = _get_logit
+    _save_logit = _save_logit
+
+    def __init__(self, output_path, netD, dataloader=None, netD_drs=None, device=None, save_steps=5000,
+                 logit_save_steps=500, save_logits=True, save_logit_after=0, stop_save_logit_after=100000,
+                 save_eval_logits=True, recorder: LogitRecorder = None, **unused):
+        self.output_path = Path(output_path)
+        self.netD, self.netD_drs = netD, netD_drs
+        self.train_drs = netD_drs is not None               # trainer.py:86
+        self.dataloader = dataloader
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.save_steps = save_steps
+        self.logit_save_steps = logit_save_steps
+        self.save_logits = save_logits
+        self.save_logit_after = save_logit_after
+        self.stop_save_logit_after = stop_save_logit_after
+        self.save_eval_logits = save_eval_logits
+        self.recorder = recorder
+        self.logit_results = defaultdict(dict)              # trainer.py:222
+
+    def should_record(self, global_step) -> bool:
+        return bool(self.save_logits and global_step % self.logit_save_steps == 0
+                    and self.save_logit_after <= global_step <= self.stop_save_logit_after)
+
+    def on_step(self, global_step):
+        """Body of trainer.py:328-346 for one finished optimisation step."""
+        if self.should_record(global_step):
+            netD, name = (self.netD_drs, 'netD_drs') if self.train_drs else (self.netD, 'netD')
+            mode = 'eval' if self.save_eval_logits else 'train'
+            self.logit_results[f'{name}_{mode}'][global_step] = self._get_logit(netD=netD, eval_mode=mode == 'eval')
+        if global_step % self.save_steps == 0 and self.save_logits and global_step >= self.save_logit_after:
+            self._save_logit(self.logit_results)

@@ -1,0 +1,429 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle and the golden vectors the
+reference itself produced.  Run on the B200 box: ``python -m pytest tests -m gpu``.
+
+Tolerances (BASELINE.json north_star / BASELINE.md section 4):
+  * score stage fed identical logits: BIT-EXACT float64 against the reference (snapshot-window path);
+    <= 1e-12 relative for the streaming Welford accumulator; resampled index stream and selected index
+    sets bit-exact;
+  * discriminator logits: fp32 engine <= 1e-5, bf16 engine <= 1e-3, relative to the logit scale
+    (|a-b| <= tol * max(|b|, mean|b|)), against the fp32 CPU oracle;
+  * DRS: acceptance decisions identical under the same psi except where |p - psi| < 1e-5 (fp32
+    exp/log differ from NumPy's in the last ulp), running maximum identical.
+"""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dcgan as dcgan_oracle      # noqa: E402
+from oracle import drs as drs_oracle          # noqa: E402
+from oracle import scores as so               # noqa: E402
+from oracle import sngan as sngan_oracle      # noqa: E402
+
+SCORE_CASES = ["scores_cifar_window", "scores_ffhq_window", "scores_ties"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def _logit_close(a, b, tol):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    scale = np.maximum(np.abs(b), np.abs(b).mean())
+    err = np.abs(a - b) / scale
+    return err.max(), err.mean()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# scoring stage
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SCORE_CASES)
+def test_calculate_scores_bit_exact_vs_reference(golden_dir, name):
+    from diagan_b200.utils.plot import calculate_scores
+    g = _load(golden_dir, name)
+    logits = {int(s): g["logits"][i] for i, s in enumerate(g["steps"])}
+    out = calculate_scores(logits, start_epoch=int(g["start"]), end_epoch=int(g["end"]))
+    keys = [str(k) for k in g["keys"]]
+    assert list(out.keys()) == keys
+    for i, k in enumerate(keys):
+        assert out[k].dtype == np.float64
+        assert np.array_equal(out[k], g["scores"][i]), f"{name}:{k} differs from the reference"
+
+
+@pytest.mark.parametrize("name", SCORE_CASES)
+def test_fp32_snapshots_give_same_scores(golden_dir, name, dev):
+    """The recorder keeps fp32 snapshots on the device; widening inside the kernel == the float64 pickle."""
+    from diagan_b200.utils.plot import calculate_scores_device
+    g = _load(golden_dir, name)
+    logits = {int(s): torch.from_numpy(g["logits"][i].astype(np.float32)).to(dev) for i, s in enumerate(g["steps"])}
+    out = calculate_scores_device(logits, int(g["start"]), int(g["end"]), keys=["ldr_conf_0.3_ratio_50"])
+    keys = [str(k) for k in g["keys"]]
+    for k in ("ldrm", "ldrv", "ldrd", "ldr", "ldr_conf_0.3_ratio_50"):
+        assert np.array_equal(out[k].cpu().numpy(), g["scores"][keys.index(k)]), k
+
+
+@pytest.mark.parametrize("name", SCORE_CASES)
+def test_running_stats_and_resample_stream(golden_dir, name, dev):
+    from diagan_b200 import engine
+    g = _load(golden_dir, name)
+    steps = g["steps"]
+    sel = (steps >= g["start"]) & (steps < g["end"])
+    arr = g["logits"][sel]
+    T, n = arr.shape
+    st = engine.RunningStats(n, dev)
+    for t in range(T):
+        st.update(torch.from_numpy(arr[t].astype(np.float32)).to(dev))
+    keys = [str(k) for k in g["keys"]]
+    ref = lambda k: g["scores"][keys.index(k)]
+    np.testing.assert_allclose(st.mean.cpu().numpy(), ref("ldrm"), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(st.ldrv().cpu().numpy(), ref("ldrv"), rtol=1e-10, atol=1e-18)
+    np.testing.assert_allclose(st.ldrd().cpu().numpy(), ref("ldrd"), rtol=1e-12, atol=1e-15)
+    assert np.array_equal(st.ldr().cpu().numpy(), ref("ldr"))
+    # same update as the oracle's streaming restatement, bit for bit
+    om, oq, ol, osad = so.welford(arr)
+    assert np.array_equal(st.mean.cpu().numpy(), om) and np.array_equal(st.m2.cpu().numpy(), oq)
+    # weights -> WeightedRandomSampler stream identical to the reference's (train_mimicry_phase2.py:21-24)
+    w = st.score(engine.conf_from_key("ldr_conf_0.3_ratio_50"), eps=1e-6).cpu().numpy()
+    np.testing.assert_allclose(w, ref("ldr_conf_0.3_ratio_50"), rtol=1e-11)
+    assert np.array_equal(so.resample_stream(w, int(g["stream_seed"])), g["stream"])
+
+
+def test_odd_sizes_and_unaligned_shards(dev):
+    """ragged / tiny inputs: N = 1, 2, 3, odd N, shard views starting at odd offsets."""
+    from diagan_b200 import engine
+    rng = np.random.RandomState(0)
+    for n in (1, 2, 3, 255, 1001):
+        arr = rng.normal(0.3, 1.0, (6, n)).astype(np.float32)
+        st = engine.RunningStats(n, dev)
+        for t in range(6):
+            st.update(torch.from_numpy(arr[t]).to(dev))
+        om, oq, ol, osad = so.welford(arr.astype(np.float64))
+        assert np.array_equal(st.mean.cpu().numpy(), om)
+        assert np.array_equal(st.state[3].cpu().numpy(), osad)
+        mom = engine.window_moments(torch.from_numpy(arr).to(dev))
+        mean, var = so.moments(arr.astype(np.float64))
+        assert np.array_equal(mom["mean"].cpu().numpy(), mean) and np.array_equal(mom["var"].cpu().numpy(), var)
+    # unaligned: statistics over a slice [3:] of a bigger buffer
+    full = torch.from_numpy(rng.normal(size=(4, 40)).astype(np.float32)).to(dev)
+    st = engine.RunningStats(37, dev)
+    for t in range(4):
+        st.update(full[t, 3:].contiguous()[0:37])
+    om, _, _, _ = so.welford(full[:, 3:].cpu().numpy().astype(np.float64))
+    assert np.array_equal(st.mean.cpu().numpy(), om)
+    mom = engine.window_moments(full[:, 3:])       # strided rows (ld = 40)
+    assert np.array_equal(mom["mean"].cpu().numpy(), so.moments(full[:, 3:].cpu().numpy().astype(np.float64))[0])
+
+
+@pytest.mark.parametrize("name", SCORE_CASES)
+def test_top_indices_match_stable_argsort(golden_dir, name, dev):
+    from diagan_b200 import engine
+    g = _load(golden_dir, name)
+    keys = [str(k) for k in g["keys"]]
+    w = g["scores"][keys.index("ldr_conf_0.3_ratio_50")]
+    wd = torch.from_numpy(w).to(dev)
+    order = g["argsort_stable"]
+    for k in (1, 20, 100, len(w)):
+        assert np.array_equal(engine.top_indices(wd, k, True).cpu().numpy(), order[-k:])
+        assert np.array_equal(engine.top_indices(wd, k, False).cpu().numpy(), order[:k])
+
+
+def test_top_indices_heavy_ties_large(dev):
+    """After clipping most samples tie at a bound ('Ties'); tie-break = ascending index."""
+    from diagan_b200 import engine
+    rng = np.random.RandomState(1)
+    n = 200_000
+    w = np.clip(rng.normal(1.0, 1.0, n), 0.01, 0.5)
+    w[rng.randint(0, n, 50)] *= -1.0          # a few negatives: sign handling of the key transform
+    wd = torch.from_numpy(w).to(dev)
+    order = np.argsort(w, kind="stable")
+    for k in (100, 4096):
+        assert np.array_equal(engine.top_indices(wd, k, True).cpu().numpy(), order[-k:])
+        assert np.array_equal(engine.top_indices(wd, k, False).cpu().numpy(), order[:k])
+
+
+# ---------------------------------------------------------------------------------------------------
+# DRS
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["drs_b256", "drs_b128"])
+def test_drs_accept_vs_reference(golden_dir, name, dev):
+    from diagan_b200 import _lib
+    from diagan_b200._lib import check, ptr, stream_ptr
+    lib = _lib.load()
+    g = _load(golden_dir, name)
+    mx = torch.full((1,), -100000.0, dtype=torch.float32, device=dev)
+    for b in range(g["burn_ldr"].shape[0]):
+        l = torch.from_numpy(g["burn_ldr"][b].reshape(-1)).to(dev)
+        check(lib.sdg_drs_update_max(ptr(l), l.numel(), ptr(mx), stream_ptr(dev)))
+    assert np.float32(mx.item()) == g["max_after_burn"]
+    oracle = drs_oracle.DRSOracle(int(g["percentile"]))
+    oracle.maximum = g["max_after_burn"]
+    for b in range(g["ldr"].shape[0]):
+        l = torch.from_numpy(g["ldr"][b].reshape(-1)).to(dev)
+        n = l.numel()
+        psi = torch.from_numpy(g["psi"][b]).to(dev)
+        p = torch.empty(n, dtype=torch.float32, device=dev)
+        acc = torch.empty(n, dtype=torch.uint8, device=dev)
+        idx = torch.empty(n, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(lib.sdg_drs_accept(ptr(l), n, ptr(mx), 1e-6, float(g["percentile"]), 0, 0.0, ptr(psi), ptr(p), ptr(acc),
+                                 ptr(idx), ptr(cnt), stream_ptr(dev)))
+        assert np.float32(mx.item()) == g["max_after"][b]
+        p_ref, acc_ref = oracle.accept(g["ldr"][b], g["psi"][b])
+        assert np.array_equal(acc_ref, g["accept"][b])
+        p_gpu, acc_gpu = p.cpu().numpy(), acc.cpu().numpy().astype(bool)
+        np.testing.assert_allclose(p_gpu, p_ref, rtol=0, atol=2e-6)
+        diff = acc_gpu != g["accept"][b]
+        assert np.all(np.abs(p_ref[diff] - g["psi"][b][diff]) < 1e-5), "acceptance differs away from the boundary"
+        k = int(cnt.item())
+        assert k == int(acc_gpu.sum())
+        assert np.array_equal(idx[:k].cpu().numpy(), np.nonzero(acc_gpu)[0])
+
+
+def test_drs_module_contract(dev):
+    """diagan_b200.models.drs.DRS with stand-in G/D: reference method contracts (drs.py:21-69)."""
+    from diagan_b200.models.drs import DRS
+    from diagan_b200.trainer.evaluate import DRS as EvalDRS
+
+    class G:
+        def __init__(self):
+            self.gen = torch.Generator(device="cuda").manual_seed(5)
+
+        def generate_images(self, n, device=None):
+            return torch.randn(n, 3, 4, 4, generator=self.gen, device=device)
+
+    class D(torch.nn.Module):
+        def forward(self, x):
+            return x.mean(dim=(1, 2, 3)).view(-1, 1) * 9.0 + 0.25
+
+    drs = DRS(G(), D(), dev)
+    assert isinstance(drs.maximum, np.float32) and drs.maximum > -100000
+    imgs, ldr = drs.get_fake_samples_and_ldr(256)
+    assert imgs.is_cuda and ldr.dtype == np.float32 and ldr.shape == (256, 1)
+    np.random.seed(1)
+    acc = drs.sub_rejection_sampler(imgs, ldr)
+    assert acc.device.type == "cpu" and acc.dtype == torch.float32 and acc.shape[1:] == (3, 4, 4)
+    # same decisions as the oracle under the same psi
+    o = drs_oracle.DRSOracle(80)
+    o.maximum = drs.maximum
+    np.random.seed(1)
+    p_ref, acc_ref = o.accept(ldr, np.random.rand(256))
+    assert abs(int(acc_ref.sum()) - acc.shape[0]) <= 1
+    out = drs.generate_images(300)
+    assert out.shape == (300, 3, 4, 4)
+    e = EvalDRS(G(), D(), dev, batch_size=128)
+    assert e.generate_images(50).is_cuda and e.batch_size == 128
+
+
+# ---------------------------------------------------------------------------------------------------
+# discriminator forward
+# ---------------------------------------------------------------------------------------------------
+def _u8(n, size, seed):
+    return torch.from_numpy(np.random.RandomState(seed).randint(0, 256, (n, size, size, 3)).astype(np.uint8))
+
+
+def test_dcgan_fp32_vs_reference_golden(golden_dir, dev):
+    from diagan_b200 import engine
+    g = _load(golden_dir, "dcgan_eval")
+    params = dcgan_oracle.init_params(int(g["param_seed"]))
+    eng = engine.DiscriminatorEngine(dev).load(params)
+    assert eng.arch == "dcgan32"
+    x = torch.from_numpy(g["x_u8"]).to(dev)
+    y = eng.forward(x).cpu().numpy()
+    emax, _ = _logit_close(y, g["logits"], 1e-5)
+    assert emax <= 1e-5, emax
+    # float32 NCHW entry (what netD(x) receives in trainer.py:150)
+    xf = sngan_oracle.normalise_u8(torch.from_numpy(g["x_u8"])).contiguous().to(dev)
+    y2 = eng.forward(xf).cpu().numpy()
+    assert np.array_equal(y, y2)
+
+
+@pytest.mark.parametrize("arch,n", [(32, 70), (64, 20)])
+@pytest.mark.parametrize("inplace", [True, False])
+def test_sngan_fp32_vs_oracle(arch, n, inplace, dev):
+    from diagan_b200 import engine
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    params = sngan_oracle.init_params(arch, seed=1)
+    x = _u8(n, arch, 2)
+    want = sngan_oracle.logits_pass(params, x, arch, inplace_relu=inplace)
+    eng = engine.DiscriminatorEngine(dev).load_sngan(params, arch, "fp32", inplace)
+    got = eng.forward(x.to(dev)).cpu().numpy()
+    emax, emean = _logit_close(got, want, 1e-5)
+    print(f"sngan{arch} fp32 inplace={inplace}: max rel err {emax:.2e} mean {emean:.2e}")
+    assert emax <= 1e-5
+    # sigma of every layer against the oracle's power iteration
+    sig = eng.sigmas().cpu().numpy()
+    ref = np.array([float(sngan_oracle.sigma_eval(params[f"{k}.weight"], params[f"{k}.sn_u"]))
+                    for k in engine.sngan_layer_keys(arch)])
+    np.testing.assert_allclose(sig, ref, rtol=2e-6)
+    # chunking must not change results
+    eng.set_chunk(7)
+    assert np.array_equal(eng.forward(x.to(dev)).cpu().numpy(), got)
+
+
+def _conv_case(dev, n, hw, cin, cout, ks, relu, seed):
+    from diagan_b200 import _lib
+    from diagan_b200._lib import check, ptr, stream_ptr
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, cin, hw, hw, generator=gen)
+    w = torch.randn(cout, cin, ks, ks, generator=gen) / np.sqrt(cin * ks * ks)
+    b = torch.randn(cout, generator=gen)
+    xb, wb = x.bfloat16(), w.bfloat16()
+    want = torch.nn.functional.conv2d(xb.float(), wb.float(), b, padding=ks // 2)
+    if relu:
+        want = want.relu()
+    x_nhwc = xb.permute(0, 2, 3, 1).contiguous().to(dev)
+    w_pack = wb.permute(0, 2, 3, 1).reshape(cout, ks * ks * cin).contiguous().to(dev)
+    out = torch.full((n, hw, hw, cout), float("nan"), dtype=torch.bfloat16, device=dev)
+    check(lib.sdg_conv2d_bf16(ptr(x_nhwc), ptr(w_pack), ptr(b.to(dev)), ptr(out), n, hw, hw, cin, cout, ks,
+                              1 if relu else 0, stream_ptr(dev)), "sdg_conv2d_bf16")
+    torch.cuda.synchronize()
+    got = out.float().cpu().permute(0, 3, 1, 2)
+    err = (got - want).abs().max().item()
+    scale = want.abs().max().item()
+    return err, scale
+
+
+@pytest.mark.parametrize("n,hw,cin,cout,ks,relu", [
+    (3, 32, 128, 128, 3, 0),      # SNGAN-32 block1.c2 shape (55% of the FLOPs)
+    (5, 16, 128, 128, 3, 1),      # block2 convs
+    (7, 8, 128, 128, 3, 1),       # blocks 3/4: two images per 128-pixel tile, ragged last tile
+    (2, 32, 64, 128, 1, 1),       # first conv as a 1x1 GEMM over staged patches
+    (3, 16, 128, 128, 1, 0),      # block2 shortcut
+    (2, 64, 64, 64, 3, 0),        # SNGAN-64 block1.c2 (N tile 64, two rows per tile)
+    (9, 4, 512, 1024, 3, 0),      # SNGAN-64 block5.c2: 8 images per tile, 8 N tiles, 8 K chunks
+    (3, 8, 256, 512, 1, 0),       # SNGAN-64 block4 shortcut
+    (300, 32, 128, 128, 3, 1),    # more tiles than SMs: persistent loop + TMEM double buffering
+])
+def test_conv2d_bf16_tcgen05_vs_torch(n, hw, cin, cout, ks, relu, dev):
+    """The tcgen05 implicit-GEMM kernel alone against F.conv2d on the same bf16-rounded operands
+    (fp32 accumulate both sides; output rounded to bf16 -> tolerance 2^-8 of the output scale)."""
+    err, scale = _conv_case(dev, n, hw, cin, cout, ks, relu, seed=n * 1000 + hw)
+    print(f"conv n={n} hw={hw} {cin}->{cout} k{ks}: max abs err {err:.3e} (scale {scale:.2f})")
+    assert err <= scale * 2.0 ** -7
+
+
+@pytest.mark.parametrize("arch,n", [(32, 300), (64, 40)])
+@pytest.mark.parametrize("inplace", [True, False])
+def test_sngan_bf16_vs_oracle(arch, n, inplace, dev):
+    from diagan_b200 import engine
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    params = sngan_oracle.init_params(arch, seed=1)
+    x = _u8(n, arch, 3)
+    want = sngan_oracle.logits_pass(params, x, arch, inplace_relu=inplace)
+    eng = engine.DiscriminatorEngine(dev).load_sngan(params, arch, "bf16", inplace)
+    got = eng.forward(x.to(dev)).cpu().numpy()
+    emax, emean = _logit_close(got, want, 1e-3)
+    print(f"sngan{arch} bf16 inplace={inplace}: max rel err {emax:.2e} mean {emean:.2e} "
+          f"(logit mean {want.mean():.4f} std {want.std():.4f})")
+    assert emax <= 1e-3
+    eng.set_chunk(64)
+    assert np.array_equal(eng.forward(x.to(dev)).cpu().numpy(), got)
+    # float32 NCHW input path gives the same logits as the uint8 path
+    xf = sngan_oracle.normalise_u8(x).contiguous().to(dev)
+    assert np.array_equal(eng.forward(xf).cpu().numpy(), got)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the recorder end to end: pass -> snapshots -> pickle -> calculate_scores -> weights
+# ---------------------------------------------------------------------------------------------------
+def test_recorder_end_to_end(tmp_path, dev):
+    from diagan_b200.trainer.trainer import LogitRecorder, LogTrainer, ResidentDataset
+    from diagan_b200.utils.plot import calculate_scores
+
+    class Net:                                   # stands in for the mimicry module: state_dict + train()
+        def __init__(self, p): self.p, self.mode = p, "eval"
+        def state_dict(self): return self.p
+        def train(self): self.mode = "train"
+        def eval(self): self.mode = "eval"
+
+    n = 257
+    data = _u8(n, 32, 9)
+    ds = ResidentDataset(data.to(dev))
+    base = sngan_oracle.init_params(32, seed=1)
+    rec = LogitRecorder(ds, dev, precision="fp32")
+    tr = LogTrainer(tmp_path, Net(base), recorder=rec, device=dev, logit_save_steps=100, save_logit_after=300,
+                    stop_save_logit_after=800, save_steps=400)
+    oracle_logits = {}
+    for step in range(0, 1001, 100):
+        tr.netD.p = sngan_oracle.perturb_params(base, step, 2e-2)
+        tr.on_step(step)
+        if tr.should_record(step):
+            oracle_logits[step] = sngan_oracle.logits_pass(tr.netD.p, data, 32)
+    assert tr.netD.mode == "train"                                   # trainer.py:155
+    got = tr.logit_results["netD_eval"]
+    assert list(got.keys()) == [300, 400, 500, 600, 700, 800]
+    for s in got:
+        assert got[s].dtype == np.float64 and got[s].shape == (n,)
+        assert _logit_close(got[s], oracle_logits[s], 1e-5)[0] <= 1e-5
+    saved = pickle.load(open(tmp_path / "logits_netD_eval.pkl", "rb"))   # written at step 400 and 800
+    assert list(saved.keys()) == [300, 400, 500, 600, 700, 800]
+    sc = calculate_scores(saved, start_epoch=300, end_epoch=800)          # 5 snapshots, 800 excluded
+    want = so.calculate_scores(saved, 300, 800)
+    for k in want:
+        assert np.array_equal(sc[k], want[k]), k
+
+
+def test_get_logit_from_dataloader_contract(dev):
+    """The generic path: (data, target, weight, index) batches from a shuffled DataLoader, scattered by index."""
+    from diagan_b200.trainer.trainer import LogTrainer
+
+    class DS(torch.utils.data.Dataset):
+        def __init__(self, x): self.x = x
+        def __len__(self): return self.x.shape[0]
+        def __getitem__(self, i): return sngan_oracle.normalise_u8(self.x[i:i + 1])[0], 0, 1.0, i
+
+    class Net:
+        def __init__(self, p): self.p = p
+        def state_dict(self): return self.p
+        def train(self): pass
+
+    data = _u8(100, 32, 4)
+    params = sngan_oracle.init_params(32, seed=2)
+    loader = torch.utils.data.DataLoader(DS(data), batch_size=64, shuffle=True)
+    tr = LogTrainer("/tmp", Net(params), dataloader=loader, device=dev)
+    tr.recorder = None
+    from diagan_b200.trainer.trainer import LogitRecorder
+    tr.recorder = LogitRecorder(None, dev, precision="fp32")
+    got = tr._get_logit(tr.netD, eval_mode=True)
+    want = sngan_oracle.logits_pass(params, data, 32)
+    assert got.dtype == np.float64 and _logit_close(got, want, 1e-5)[0] <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE-size properties (no oracle at this size: invariants instead)
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_properties(dev):
+    """50k samples x 50 snapshots (configs[1] score stage): window path == Welford path to 1e-12,
+    clip bounds hold, idempotent clip, top-k sorted and consistent with the score vector."""
+    from diagan_b200 import engine
+    n, T = 50_000, 50
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    snaps = (1.0 + 1.5 * torch.randn(T, n, generator=gen, device=dev)).float()
+    mom = engine.window_moments(snaps)
+    st = engine.RunningStats(n, dev)
+    for t in range(T):
+        st.update(snaps[t])
+    torch.testing.assert_close(st.mean, mom["mean"], rtol=1e-12, atol=1e-14)
+    torch.testing.assert_close(st.ldrv(), mom["var"], rtol=1e-10, atol=1e-14)
+    ref_mean = snaps.double().mean(0)
+    torch.testing.assert_close(mom["mean"], ref_mean, rtol=1e-12, atol=1e-14)
+    t03 = engine.conf_from_key("ldr_conf_0.3_ratio_50")
+    s = engine.scores_from_moments(mom["mean"], mom["var"], [t03, 5.0])
+    for row in s:
+        assert row.min().item() >= engine.FLOOR and row.max().item() <= row.min().item() * engine.RATIO * (1 + 1e-15)
+    top = engine.top_indices(s[0], 100, True)
+    vals = s[0][top]
+    assert torch.all(vals[1:] >= vals[:-1])
+    assert vals[0].item() >= torch.kthvalue(s[0], n - 99).values.item()
+    bot = engine.top_indices(s[0], 100, False)
+    assert s[0][bot].max().item() <= torch.kthvalue(s[0], 100).values.item()
