@@ -41,7 +41,9 @@ extern "C" {
 
 /* arithmetic of the conv stack */
 #define SDG_PREC_FP32      0      /* CUDA-core fp32 (IEEE, no TF32): the 1e-5 parity mode */
-#define SDG_PREC_BF16      1      /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulators: the throughput mode */
+#define SDG_PREC_BF16      1      /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulators */
+#define SDG_PREC_FP16      2      /* tcgen05 kind::f16, fp16 operands, fp32 TMEM accumulators: same speed as bf16,
+                                     8x smaller rounding error -- the throughput mode that meets the 1e-3 parity bar */
 
 /* input layouts of sdg_d_forward */
 #define SDG_LAYOUT_U8_NHWC   0    /* uint8 [n,H,W,3]; normalised (x/255-.5)/.5 on load (transform.py:3-11) */
@@ -95,14 +97,15 @@ SDG_API int sdg_dcgan_load(sdg_ctx* ctx, const float* const* conv_w_host,
  * The caller passes logits_out already offset to the first sample's dataset index. */
 SDG_API int sdg_d_forward(sdg_ctx* ctx, const void* x, int layout, int64_t n, float* logits_out, void* stream);
 
-/* One spectral-normalised conv layer of the bf16 path on its own (what sdg_d_forward launches per
+/* One spectral-normalised conv layer of the 16-bit tensor-core path on its own (what sdg_d_forward launches per
  * layer; exposed for kernel-level parity tests and for the roofline measurement in bench.py).
  * Replaces F.conv2d(x, W/sigma, b, stride=1, padding=ks/2) of mimicry SNConv2d.forward.
- * in  bf16 [n,H,W,Cin] NHWC (Cin % 64 == 0, H == W a power of two in 4..128)
- * wb  bf16 [Cout, ks*ks*Cin], K index = (ky*ks+kx)*Cin + c      (Cout % 64 == 0, <= 1024)
- * out bf16 [n,H,W,Cout]; bias fp32 [Cout] or NULL; relu != 0 applies ReLU after the bias. ks in {1,3}. */
-SDG_API int sdg_conv2d_bf16(const void* in, const void* wb, const float* bias, void* out, int64_t n, int H, int W,
-                    int Cin, int Cout, int ks, int relu, void* stream);
+ * in  [n,H,W,Cin] NHWC 16-bit (Cin % 64 == 0, H == W a power of two in 4..128)
+ * wb  [Cout, ks*ks*Cin] 16-bit, K index = (ky*ks+kx)*Cin + c      (Cout % 64 == 0, <= 1024)
+ * out [n,H,W,Cout] 16-bit; bias fp32 [Cout] or NULL; relu != 0 applies ReLU after the bias. ks in {1,3}.
+ * precision: SDG_PREC_BF16 or SDG_PREC_FP16 (the element type of in / wb / out). */
+SDG_API int sdg_conv2d_h16(const void* in, const void* wb, const float* bias, void* out, int64_t n, int H, int W,
+                   int Cin, int Cout, int ks, int relu, int precision, void* stream);
 
 /* ---- running per-sample statistics (new: the reference keeps every snapshot, trainer.py:337-338) --
  * Welford update with snapshot number t (0-based) plus last value and sum |x_t - x_{t-1}|:

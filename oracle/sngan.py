@@ -146,13 +146,18 @@ def normalise_u8(x_u8_nhwc: torch.Tensor) -> torch.Tensor:
     return (x - 0.5) / 0.5
 
 
-def logits_pass(params, data_u8_nhwc: torch.Tensor, arch=32, batch=64, inplace_relu=True) -> np.ndarray:
+def logits_pass(params, data_u8_nhwc: torch.Tensor, arch=32, batch=64, inplace_relu=True,
+                dtype=torch.float32) -> np.ndarray:
     """The recording pass of trainer.py:142-156 on an in-memory dataset, sequential batches of 64:
-    float64 [N] with fp32 values widened, indexed by dataset index."""
+    float64 [N] with fp32 values widened, indexed by dataset index.  ``dtype=torch.float64`` evaluates
+    the same network in double precision (the exact-arithmetic yardstick the parity tests use to
+    separate the GPU's rounding error from the fp32 CPU path's own)."""
     n = data_u8_nhwc.shape[0]
     out = np.zeros(n)
+    if dtype != torch.float32:
+        params = {k: v.to(dtype) for k, v in params.items()}
     with torch.no_grad():
         for s in range(0, n, batch):
-            x = normalise_u8(data_u8_nhwc[s:s + batch])
+            x = normalise_u8(data_u8_nhwc[s:s + batch]).to(dtype)
             out[s:s + batch] = forward(params, x, arch, inplace_relu).view(-1).numpy()
     return out

@@ -155,16 +155,18 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-// instruction descriptor: D fp32, A/B bf16, both K-major, M x N
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor: D fp32 (bits 4-5 = 1), A/B format (bits 7-9 / 10-12: 0 = fp16, 1 = bf16),
+// both operands K-major, N >> 3 at bits 17-22, M >> 4 at bits 24-28
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool f16) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, const TcParams p) {
+               const float* __restrict__ bias, h16* __restrict__ out, const TcParams p) {
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -237,7 +239,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(TC_BM, BN);
+      constexpr uint32_t idesc = make_idesc(TC_BM, BN, F16);
       int stage = 0;
       uint32_t phase = 0;
       long long local = 0;
@@ -277,7 +279,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const long long pix = mt * TC_BM + q * 32 + lane;      // tile rows are 128 consecutive NHW pixels
       const bool valid = pix < p.total_pixels;
-      __nv_bfloat16* orow = out + pix * p.Cout + nt * BN;
+      h16* orow = out + pix * p.Cout + nt * BN;
       const float* brow = s_bias + nt * BN;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -287,15 +289,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (valid) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            __align__(16) __nv_bfloat162 h[4];
+            uint4 pk;
+            uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float x = __uint_as_float(r[g * 8 + 2 * j]) + brow[c0 + g * 8 + 2 * j];
               float y = __uint_as_float(r[g * 8 + 2 * j + 1]) + brow[c0 + g * 8 + 2 * j + 1];
               if (p.post_relu) { x = fmaxf(x, 0.f); y = fmaxf(y, 0.f); }
-              h[j] = __floats2bfloat162_rn(x, y);
+              h[j] = pack_h2<F16>(x, y);
             }
-            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = *reinterpret_cast<const uint4*>(h);
+            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = pk;
           }
         }
       }
@@ -337,14 +340,16 @@ int conv_tc_init(int device) {
   cudaDriverEntryPointQueryResult qres;
   SDG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   SDG_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, SDG_E_DEVICE, "conv_tc: cuTensorMapEncodeTiled unavailable");
-  SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>()));
-  SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>()));
+  SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>()));
+  SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>()));
+  SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>()));
+  SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>()));
   g_encode = (EncodeTiledFn)fn;
   return 0;
 }
 
-int conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* wb, const float* bias, __nv_bfloat16* out, int64_t n, int H,
-            int W, int Cin, int Cout, int taps, int post_relu, cudaStream_t s) {
+int conv_tc(const h16* in, const h16* wb, const float* bias, h16* out, int64_t n, int H, int W, int Cin, int Cout,
+            int taps, int post_relu, int f16, cudaStream_t s) {
   SDG_REQUIRE(g_encode, SDG_E_STATE, "conv_tc: conv_tc_init not called");
   SDG_REQUIRE(taps == 9 || taps == 1, SDG_E_UNSUPPORTED, "conv_tc: taps=%d", taps);
   SDG_REQUIRE(Cin % TC_BK == 0 && Cout % 64 == 0 && Cout <= TC_MAX_COUT, SDG_E_UNSUPPORTED, "conv_tc: Cin=%d Cout=%d", Cin, Cout);
@@ -364,12 +369,13 @@ int conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* wb, const float* bias,
   p.total_pixels = n * H * W;
 
   CUtensorMap map_a, map_b;
+  const CUtensorMapDataType dtype = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
     cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)W, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)in, dims, strides, box, estr,
+    CUresult r = g_encode(&map_a, dtype, 4, (void*)in, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SDG_REQUIRE(r == CUDA_SUCCESS, SDG_E_INVALID, "conv_tc: cuTensorMapEncodeTiled(A) failed: %d", (int)r);
@@ -379,17 +385,21 @@ int conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* wb, const float* bias,
     cuuint64_t strides[1] = {(cuuint64_t)taps * Cin * 2};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)wb, dims, strides, box, estr,
+    CUresult r = g_encode(&map_b, dtype, 2, (void*)wb, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SDG_REQUIRE(r == CUDA_SUCCESS, SDG_E_INVALID, "conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
   const long long total_tiles = p.m_tiles * p.n_tiles;
   const int grid = (int)(total_tiles < g_num_sms ? total_tiles : g_num_sms);
-  if (BN == 128) {
-    SDG_LAUNCH(conv_tc_kernel<128>, grid, TC_THREADS, tc_smem_bytes<128>(), s, map_a, map_b, bias, out, p);
+  if (BN == 128 && f16) {
+    SDG_LAUNCH((conv_tc_kernel<128, true>), grid, TC_THREADS, tc_smem_bytes<128>(), s, map_a, map_b, bias, out, p);
+  } else if (BN == 128) {
+    SDG_LAUNCH((conv_tc_kernel<128, false>), grid, TC_THREADS, tc_smem_bytes<128>(), s, map_a, map_b, bias, out, p);
+  } else if (f16) {
+    SDG_LAUNCH((conv_tc_kernel<64, true>), grid, TC_THREADS, tc_smem_bytes<64>(), s, map_a, map_b, bias, out, p);
   } else {
-    SDG_LAUNCH(conv_tc_kernel<64>, grid, TC_THREADS, tc_smem_bytes<64>(), s, map_a, map_b, bias, out, p);
+    SDG_LAUNCH((conv_tc_kernel<64, false>), grid, TC_THREADS, tc_smem_bytes<64>(), s, map_a, map_b, bias, out, p);
   }
   return 0;
 }

@@ -168,8 +168,8 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
                               const float* const* u, int precision, int inplace_relu, void* stream) {
   SDG_REQUIRE(c && W && b && u, SDG_E_INVALID, "sdg_sngan_load: null pointer");
   SDG_REQUIRE(arch == SDG_ARCH_SNGAN32 || arch == SDG_ARCH_SNGAN64, SDG_E_INVALID, "sdg_sngan_load: arch=%d", arch);
-  SDG_REQUIRE(precision == SDG_PREC_FP32 || precision == SDG_PREC_BF16, SDG_E_INVALID, "sdg_sngan_load: precision=%d",
-              precision);
+  SDG_REQUIRE(precision == SDG_PREC_FP32 || precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID,
+              "sdg_sngan_load: precision=%d", precision);
   cudaStream_t s = (cudaStream_t)stream;
   SDG_CUDA(cudaSetDevice(c->device));
   int ndf = 0;
@@ -196,7 +196,7 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
 
   c->arch = arch; c->precision = precision; c->inplace_relu = inplace_relu ? 1 : 0; c->n_layers = n_layers;
   c->loaded = false;
-  if (precision == SDG_PREC_BF16) { int rc = conv_tc_init(c->device); if (rc) return rc; }
+  if (precision != SDG_PREC_FP32) { int rc = conv_tc_init(c->device); if (rc) return rc; }
 
   // ---- sigma for every layer: one batched power iteration ----
   std::vector<SnLayer> tab(n_layers);
@@ -233,8 +233,9 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
       int rc = pack_conv_fp32(W[i], sig + i, nullptr, l.w32.as<float>(), l.cout, l.cin, l.ks, s);
       if (rc) return rc;
     } else {
-      { int rc = l.w16.ensure(sizeof(__nv_bfloat16) * (size_t)l.kpad * l.cout); if (rc) return rc; }
-      int rc = pack_conv_bf16(W[i], sig + i, nullptr, l.w16.as<__nv_bfloat16>(), l.cout, l.cin, l.kpad, l.ks, s);
+      { int rc = l.w16.ensure(sizeof(h16) * (size_t)l.kpad * l.cout); if (rc) return rc; }
+      int rc = pack_conv_h16(W[i], sig + i, nullptr, l.w16.as<h16>(), l.cout, l.cin, l.kpad, l.ks,
+                             precision == SDG_PREC_FP16, s);
       if (rc) return rc;
     }
   }
@@ -342,8 +343,9 @@ static int forward_sngan_fp32(sdg_ctx* c, const void* x, int layout, int64_t nb,
   return head_sumpool_fp32(h, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, hw * hw, c->head_len, 1, s);
 }
 
-static int forward_sngan_bf16(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s) {
-  typedef __nv_bfloat16 bf;
+static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s) {
+  typedef h16 bf;
+  const int f16 = c->precision == SDG_PREC_FP16;
   const int S = c->size;
   bf* X = c->xin.as<bf>();          // [nb,S,S,64] 3x3x3 patches of the normalised input
   bf* PX = c->xpool.as<bf>();       // [nb,S/2,S/2,64] pooled input
@@ -352,7 +354,7 @@ static int forward_sngan_bf16(sdg_ctx* c, const void* x, int layout, int64_t nb,
   bf* f2 = c->buf[2].as<bf>();
   bf* hraw = c->inplace_relu ? nullptr : c->buf[3].as<bf>();   // unrectified h for the textbook shortcut
   int rc;
-  if ((rc = stage_first_conv(x, layout, X, PX, nb, S, S, s))) return rc;
+  if ((rc = stage_first_conv(x, layout, X, PX, nb, S, S, f16, s))) return rc;
   int hw = S;
   for (size_t bi = 0; bi < c->blocks.size(); ++bi) {
     const BlockSpec& bl = c->blocks[bi];
@@ -362,29 +364,29 @@ static int forward_sngan_bf16(sdg_ctx* c, const void* x, int layout, int64_t nb,
     if (bl.kind == 0) {
       const ConvLayer& sc = c->convs[c->block_first_conv[bi] + 2];
       // c1 as a 1x1 GEMM over the staged 27(->64)-wide patches; c_sc over the pooled input
-      if ((rc = conv_tc(X, c1.w16.as<bf>(), c1.bias.as<float>(), f1, nb, hw, hw, 64, c1.cout, 1, 1, s))) return rc;
+      if ((rc = conv_tc(X, c1.w16.as<bf>(), c1.bias.as<float>(), f1, nb, hw, hw, 64, c1.cout, 1, 1, f16, s))) return rc;
       if ((rc = prof_begin(c, s))) return rc;
-      if ((rc = conv_tc(f1, c2.w16.as<bf>(), c2.bias.as<float>(), f2, nb, hw, hw, c2.cin, c2.cout, 9, 0, s))) return rc;
+      if ((rc = conv_tc(f1, c2.w16.as<bf>(), c2.bias.as<float>(), f2, nb, hw, hw, c2.cin, c2.cout, 9, 0, f16, s))) return rc;
       if ((rc = prof_end(c, s, 2.0 * (double)nb * hw * hw * c2.cout * 9.0 * c2.cin))) return rc;
-      if ((rc = conv_tc(PX, sc.w16.as<bf>(), sc.bias.as<float>(), f1, nb, ho, ho, 64, sc.cout, 1, 0, s))) return rc;
-      if ((rc = combine_bf16(f2, 1, f1, 0, h, hraw, nb, ho, ho, bl.cout, s))) return rc;
+      if ((rc = conv_tc(PX, sc.w16.as<bf>(), sc.bias.as<float>(), f1, nb, ho, ho, 64, sc.cout, 1, 0, f16, s))) return rc;
+      if ((rc = combine_h16(f2, 1, f1, 0, h, hraw, nb, ho, ho, bl.cout, f16, s))) return rc;
     } else {
-      if ((rc = conv_tc(h, c1.w16.as<bf>(), c1.bias.as<float>(), f1, nb, hw, hw, c1.cin, c1.cout, 9, 1, s))) return rc;
-      if ((rc = conv_tc(f1, c2.w16.as<bf>(), c2.bias.as<float>(), f2, nb, hw, hw, c2.cin, c2.cout, 9, 0, s))) return rc;
+      if ((rc = conv_tc(h, c1.w16.as<bf>(), c1.bias.as<float>(), f1, nb, hw, hw, c1.cin, c1.cout, 9, 1, f16, s))) return rc;
+      if ((rc = conv_tc(f1, c2.w16.as<bf>(), c2.bias.as<float>(), f2, nb, hw, hw, c2.cin, c2.cout, 9, 0, f16, s))) return rc;
       const bf* sc_in = c->inplace_relu ? h : hraw;
       if (c->block_has_sc[bi]) {
         const ConvLayer& sc = c->convs[c->block_first_conv[bi] + 2];
-        if ((rc = conv_tc(sc_in, sc.w16.as<bf>(), sc.bias.as<float>(), f1, nb, hw, hw, sc.cin, sc.cout, 1, 0, s))) return rc;
-        if ((rc = combine_bf16(f2, bl.down, f1, bl.down, h, hraw, nb, ho, ho, bl.cout, s))) return rc;
+        if ((rc = conv_tc(sc_in, sc.w16.as<bf>(), sc.bias.as<float>(), f1, nb, hw, hw, sc.cin, sc.cout, 1, 0, f16, s))) return rc;
+        if ((rc = combine_h16(f2, bl.down, f1, bl.down, h, hraw, nb, ho, ho, bl.cout, f16, s))) return rc;
       } else {
         // identity shortcut: h' = c2(...) + (relu(h) | h); written to f1, then the roles swap
-        if ((rc = combine_bf16(f2, 0, sc_in, 0, f1, hraw, nb, ho, ho, bl.cout, s))) return rc;
+        if ((rc = combine_h16(f2, 0, sc_in, 0, f1, hraw, nb, ho, ho, bl.cout, f16, s))) return rc;
         bf* t = h; h = f1; f1 = t;
       }
     }
     hw = ho;
   }
-  return head_bf16(h, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, hw * hw, c->head_len, s);
+  return head_h16(h, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, hw * hw, c->head_len, f16, s);
 }
 
 static int forward_dcgan_fp32(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s) {
@@ -415,7 +417,7 @@ extern "C" int sdg_d_forward(sdg_ctx* c, const void* x, int layout, int64_t n, f
   cudaStream_t s = (cudaStream_t)stream;
   SDG_CUDA(cudaSetDevice(c->device));
   const int S = c->size;
-  const bool bf = c->precision == SDG_PREC_BF16;
+  const bool bf = c->precision != SDG_PREC_FP32;
   const int64_t act = max_act_elems(c);
   int64_t chunk = c->chunk;
   if (chunk <= 0) {
@@ -441,22 +443,24 @@ extern "C" int sdg_d_forward(sdg_ctx* c, const void* x, int layout, int64_t n, f
     const void* xs = (const char*)x + (size_t)s0 * in_stride;
     int rc;
     if (c->arch == SDG_ARCH_DCGAN32) rc = forward_dcgan_fp32(c, xs, layout, nb, logits_out + s0, s);
-    else if (bf) rc = forward_sngan_bf16(c, xs, layout, nb, logits_out + s0, s);
+    else if (bf) rc = forward_sngan_h16(c, xs, layout, nb, logits_out + s0, s);
     else rc = forward_sngan_fp32(c, xs, layout, nb, logits_out + s0, s);
     if (rc) return rc;
   }
   return 0;
 }
 
-extern "C" int sdg_conv2d_bf16(const void* in, const void* wb, const float* bias, void* out, int64_t n, int H, int W,
-                               int Cin, int Cout, int ks, int relu, void* stream) {
-  SDG_REQUIRE(in && wb && out, SDG_E_INVALID, "sdg_conv2d_bf16: null pointer");
-  SDG_REQUIRE(ks == 1 || ks == 3, SDG_E_UNSUPPORTED, "sdg_conv2d_bf16: ks=%d", ks);
+extern "C" int sdg_conv2d_h16(const void* in, const void* wb, const float* bias, void* out, int64_t n, int H, int W,
+                              int Cin, int Cout, int ks, int relu, int precision, void* stream) {
+  SDG_REQUIRE(in && wb && out, SDG_E_INVALID, "sdg_conv2d_h16: null pointer");
+  SDG_REQUIRE(ks == 1 || ks == 3, SDG_E_UNSUPPORTED, "sdg_conv2d_h16: ks=%d", ks);
+  SDG_REQUIRE(precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID, "sdg_conv2d_h16: precision=%d",
+              precision);
   int dev = 0;
   SDG_CUDA(cudaGetDevice(&dev));
   { int rc = conv_tc_init(dev); if (rc) return rc; }
-  return conv_tc((const __nv_bfloat16*)in, (const __nv_bfloat16*)wb, bias, (__nv_bfloat16*)out, n, H, W, Cin, Cout,
-                 ks * ks, relu, (cudaStream_t)stream);
+  return conv_tc((const h16*)in, (const h16*)wb, bias, (h16*)out, n, H, W, Cin, Cout, ks * ks, relu,
+                 precision == SDG_PREC_FP16, (cudaStream_t)stream);
 }
 
 extern "C" int sdg_ctx_profile(sdg_ctx* c, int enable) {

@@ -1,10 +1,32 @@
 // kernels.cuh -- internal launch API between the discriminator engine (dnet.cu) and the kernel files.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sdg {
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };   // LRELU: slope 0.2 (mnist.py:164)
+
+// 16-bit storage of the tensor-core path: IEEE fp16 (F16 = true) or bfloat16; arithmetic is fp32.
+typedef uint16_t h16;
+
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
+  if (F16) {
+    __half2 h = __floats2half2_rn(x, y);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
+template <bool F16>
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
+  if (F16) return __half22float2(*reinterpret_cast<__half2*>(&v));
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+}
 
 // ---- conv_fp32.cu: IEEE fp32 CUDA-core path (NHWC activations) ---------------------------------
 // wp: packed [ks*ks*Cin][Cout] (k = (ky*ks+kx)*Cin + c), pad = ks/2
@@ -34,9 +56,9 @@ int sn_sigmas(const SnLayer* layers_dev, const SnLayer* layers_host, int n_layer
 // wp[(tap*Cin + c)*Cout + o] = W[o][c][tap] * scale[o] / sigma   (scale may be null; sigma may be null)
 int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float* wp, int Cout, int Cin, int ks,
                    cudaStream_t s);
-// wb[o][k] = bf16(W[o][c][tap] * scale[o] / sigma) at k = tap*Cin + c, rows zero padded to Kpad (multiple of 64)
-int pack_conv_bf16(const float* W, const float* sigma, const float* scale, __nv_bfloat16* wb, int Cout, int Cin,
-                   int Kpad, int ks, cudaStream_t s);
+// wb[o][k] = h16(W[o][c][tap] * scale[o] / sigma) at k = tap*Cin + c, rows zero padded to Kpad (multiple of 64)
+int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* wb, int Cout, int Cin, int Kpad,
+                  int ks, int f16, cudaStream_t s);
 int scale_vec(const float* in, const float* sigma, float* out, int n, cudaStream_t s);   // out = in / sigma
 // BatchNorm(eval) folding: scale[o] = gamma/sqrt(var+eps), shift[o] = beta - mean*scale
 int bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
@@ -44,21 +66,21 @@ int bn_fold(const float* gamma, const float* beta, const float* mean, const floa
 // DCGAN fc weight [C*HW] (NCHW flatten) -> NHWC flatten order
 int permute_fc(const float* w, float* out, int C, int HW, cudaStream_t s);
 
-// ---- elem_bf16.cu: streaming helpers of the bf16 path (NHWC bf16, 16-byte accesses) ---------------
+// ---- elem_h16.cu: streaming helpers of the 16-bit path (NHWC, 16-byte accesses) -------------------
 // patches [n,H,W,64]: 3x3x3 neighbourhood of the normalised input at k = tap*3+c (27 real, rest 0);
 // pooled [n,H/2,W/2,64]: avg_pool2d of the normalised input in channels 0..2 (rest 0)
-int stage_first_conv(const void* x, int layout, __nv_bfloat16* patches, __nv_bfloat16* pooled, int64_t n, int H, int W,
+int stage_first_conv(const void* x, int layout, h16* patches, h16* pooled, int64_t n, int H, int W, int f16,
                      cudaStream_t s);
-int combine_bf16(const __nv_bfloat16* a, int pool_a, const __nv_bfloat16* b, int pool_b, __nv_bfloat16* out_relu,
-                 __nv_bfloat16* out_raw, int64_t n, int Ho, int Wo, int C, cudaStream_t s);
-int head_bf16(const __nv_bfloat16* hrelu, const float* w, const float* bias, float* logits, int64_t n, int HW, int C,
-              cudaStream_t s);
+int combine_h16(const h16* a, int pool_a, const h16* b, int pool_b, h16* out_relu, h16* out_raw, int64_t n, int Ho,
+                int Wo, int C, int f16, cudaStream_t s);
+int head_h16(const h16* hrelu, const float* w, const float* bias, float* logits, int64_t n, int HW, int C, int f16,
+             cudaStream_t s);
 
-// ---- conv_tc.cu: tcgen05 implicit-GEMM convolution (bf16 in, fp32 TMEM accumulate, bf16 out) -----
-// in [n,H,W,Cin] bf16 NHWC (Cin % 64 == 0), wb [Cout][taps*Cin] bf16 K-major, out [n,H,W,Cout] bf16;
+// ---- conv_tc.cu: tcgen05 implicit-GEMM convolution (16-bit in, fp32 TMEM accumulate, 16-bit out) ----
+// in [n,H,W,Cin] NHWC (Cin % 64 == 0), wb [Cout][taps*Cin] K-major, out [n,H,W,Cout];
 // taps = 9 (3x3, pad 1) or 1 (1x1); stride 1; epilogue: + bias, optional ReLU.
 int conv_tc_init(int device);
-int conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* wb, const float* bias, __nv_bfloat16* out, int64_t n, int H,
-            int W, int Cin, int Cout, int taps, int post_relu, cudaStream_t s);
+int conv_tc(const h16* in, const h16* wb, const float* bias, h16* out, int64_t n, int H, int W, int Cin, int Cout,
+            int taps, int post_relu, int f16, cudaStream_t s);
 
 }  // namespace sdg

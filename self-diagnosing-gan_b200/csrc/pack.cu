@@ -108,9 +108,10 @@ int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float
   return 0;
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(256)
-pack_conv_bf16_kernel(const float* __restrict__ W, const float* __restrict__ sigma, const float* __restrict__ scale,
-                      __nv_bfloat16* __restrict__ wb, int Cout, int Cin, int Kpad, int taps) {
+pack_conv_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigma, const float* __restrict__ scale,
+                     h16* __restrict__ wb, int Cout, int Cin, int Kpad, int taps) {
   const int total = Cout * Kpad;
   const float sg = sigma ? sigma[0] : 1.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -123,15 +124,20 @@ pack_conv_bf16_kernel(const float* __restrict__ W, const float* __restrict__ sig
       if (sigma) w = w / sg;
       if (scale) w = w * scale[o];
     }
-    wb[i] = __float2bfloat16_rn(w);
+    wb[i] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
   }
 }
 
-int pack_conv_bf16(const float* W, const float* sigma, const float* scale, __nv_bfloat16* wb, int Cout, int Cin,
-                   int Kpad, int ks, cudaStream_t s) {
+int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* wb, int Cout, int Cin, int Kpad,
+                  int ks, int f16, cudaStream_t s) {
   int total = Cout * Kpad;
-  SDG_LAUNCH(pack_conv_bf16_kernel, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wb, Cout, Cin, Kpad,
-             ks * ks);
+  if (f16) {
+    SDG_LAUNCH(pack_conv_h16_kernel<true>, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wb, Cout, Cin, Kpad,
+               ks * ks);
+  } else {
+    SDG_LAUNCH(pack_conv_h16_kernel<false>, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wb, Cout, Cin, Kpad,
+               ks * ks);
+  }
   return 0;
 }
 

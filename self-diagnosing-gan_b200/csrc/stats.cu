@@ -16,11 +16,11 @@ namespace sdg {
 // ------------------------------------------------------------------------------------------------
 // Welford + last + sum|delta| update, two samples per thread (16-byte loads/stores on the fp64 state)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void welford_step(double x, double inv_count, bool first,
+__device__ __forceinline__ void welford_step(double x, double count, bool first,
                                              double& mean, double& m2, double& last, double& sad) {
   if (!first) sad = sad + fabs(x - last);
   double d = x - mean;
-  mean = mean + d * inv_count;
+  mean = mean + d / count;               // a true division, like the oracle's NumPy restatement
   m2 = m2 + d * (x - mean);
   last = x;
 }
@@ -28,7 +28,7 @@ __device__ __forceinline__ void welford_step(double x, double inv_count, bool fi
 __global__ void __launch_bounds__(256)
 stats_update_kernel(const float* __restrict__ snap, double* __restrict__ mean, double* __restrict__ m2,
                     double* __restrict__ last, double* __restrict__ sad, int64_t n, int64_t t, int vec_ok) {
-  const double inv = 1.0 / (double)(t + 1);
+  const double inv = (double)(t + 1);
   const bool first = (t == 0);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t pairs = vec_ok ? n / 2 : 0;

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsdg.so")
 # constants mirrored from include/sdg.h
 ABI_VERSION = 1
 ARCH_DCGAN32, ARCH_SNGAN32, ARCH_SNGAN64 = 1, 32, 64
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 LAYOUT_U8_NHWC, LAYOUT_F32_NCHW = 0, 1
 
 _vp, _i, _i64, _d, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float, C.c_size_t
@@ -32,7 +32,7 @@ SIGNATURES = {
     "sdg_sngan_sigmas": (_i, [_vp, _vp, _vp]),
     "sdg_dcgan_load": (_i, [_vp, _pp, _pp, _pp, _pp, _pp, _vp, _vp, _i, _vp]),
     "sdg_d_forward": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
-    "sdg_conv2d_bf16": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "sdg_conv2d_h16": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "sdg_stats_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "sdg_window_moments_f32": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "sdg_window_moments_f64": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),

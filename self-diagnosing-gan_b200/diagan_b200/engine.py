@@ -110,12 +110,12 @@ class DiscriminatorEngine:
     def _dev(self, t):
         return t.detach().to(device=self.device, dtype=torch.float32).contiguous()
 
-    def load_sngan(self, state_dict, arch: int, precision: str = "bf16", inplace_relu: bool = True):
+    def load_sngan(self, state_dict, arch: int, precision: str = "fp16", inplace_relu: bool = True):
         keys = sngan_layer_keys(arch)
         W = [self._dev(state_dict[f"{k}.weight"]) for k in keys]
         b = [self._dev(state_dict[f"{k}.bias"]) for k in keys]
         u = [self._dev(state_dict[f"{k}.sn_u"]).view(-1) for k in keys]
-        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision]
+        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}[precision]
         with torch.cuda.device(self.device):
             check(self.lib.sdg_sngan_load(self._h, arch, len(keys), ptr_array(W), ptr_array(b), ptr_array(u), prec,
                                           1 if inplace_relu else 0, stream_ptr(self.device)), "sdg_sngan_load")
@@ -134,7 +134,7 @@ class DiscriminatorEngine:
         mu = [self._dev(state_dict[f"conv.{i}.running_mean"]) for i in bn_idx]
         var = [self._dev(state_dict[f"conv.{i}.running_var"]) for i in bn_idx]
         fw, fb = self._dev(state_dict["out_d.weight"]), self._dev(state_dict["out_d.bias"])
-        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision]
+        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}[precision]
         with torch.cuda.device(self.device):
             check(self.lib.sdg_dcgan_load(self._h, ptr_array(W), ptr_array(g), ptr_array(be), ptr_array(mu),
                                           ptr_array(var), ptr(fw), ptr(fb), prec, stream_ptr(self.device)),
@@ -147,7 +147,7 @@ class DiscriminatorEngine:
         kind = detect_arch(state_dict)
         if kind == "dcgan32":
             return self.load_dcgan(state_dict, precision or "fp32")
-        return self.load_sngan(state_dict, int(kind[5:]), precision or "bf16", inplace_relu)
+        return self.load_sngan(state_dict, int(kind[5:]), precision or "fp16", inplace_relu)
 
     def sigmas(self) -> torch.Tensor:
         out = torch.empty(self.n_layers, dtype=torch.float32, device=self.device)

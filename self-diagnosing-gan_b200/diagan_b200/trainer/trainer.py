@@ -74,7 +74,7 @@ class LogitRecorder:
     snapshot vector is always full length N so that ``diagan_b200.distributed`` can all-gather in place.
     """
 
-    def __init__(self, dataset: ResidentDataset = None, device=None, precision="bf16", inplace_relu=True,
+    def __init__(self, dataset: ResidentDataset = None, device=None, precision="fp16", inplace_relu=True,
                  shard=None, keep_snapshots=True, stats_window=None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dataset = dataset
