@@ -97,15 +97,28 @@ SDG_API int sdg_dcgan_load(sdg_ctx* ctx, const float* const* conv_w_host,
  * The caller passes logits_out already offset to the first sample's dataset index. */
 SDG_API int sdg_d_forward(sdg_ctx* ctx, const void* x, int layout, int64_t n, float* logits_out, void* stream);
 
-/* One spectral-normalised conv layer of the 16-bit tensor-core path on its own (what sdg_d_forward launches per
- * layer; exposed for kernel-level parity tests and for the roofline measurement in bench.py).
- * Replaces F.conv2d(x, W/sigma, b, stride=1, padding=ks/2) of mimicry SNConv2d.forward.
- * in  [n,H,W,Cin] NHWC 16-bit (Cin % 64 == 0, H == W a power of two in 4..128)
- * wb  [Cout, ks*ks*Cin] 16-bit, K index = (ky*ks+kx)*Cin + c      (Cout % 64 == 0, <= 1024)
- * out [n,H,W,Cout] 16-bit; bias fp32 [Cout] or NULL; relu != 0 applies ReLU after the bias. ks in {1,3}.
- * precision: SDG_PREC_BF16 or SDG_PREC_FP16 (the element type of in / wb / out). */
-SDG_API int sdg_conv2d_h16(const void* in, const void* wb, const float* bias, void* out, int64_t n, int H, int W,
-                   int Cin, int Cout, int ks, int relu, int precision, void* stream);
+/* One fused residual-block stage of the 16-bit tensor-core path on its own (what sdg_d_forward launches per
+ * conv layer; exposed for kernel-level parity tests and the roofline measurement in bench.py).
+ * Replaces, from torch-mimicry DBlock / DBlockOptimized (resblocks.py):
+ *   v = F.conv2d(in, W/sigma, b, stride 1, padding ks/2)
+ *       [+ F.conv2d(sc_in, Wsc/sigma)      the block's 1x1 shortcut conv: sc_C extra K columns of wb]
+ *   [v = F.avg_pool2d(v, 2)                 pool != 0]
+ *   [v += sc_w3 . avg_pool2d(normalise(img), 2)   DBlockOptimized shortcut, img = the network input]
+ *   [v += res_f32 (rectified if res_relu)   identity shortcut]
+ *   out_relu = relu(v) 16-bit, out_raw = v 16-bit, out_f32 = v fp32        (each optional, >= 1 required)
+ * in  [n,H,W,Cin] NHWC 16-bit (Cin % 64 == 0, H == W a power of two in 4..128; pooled: <= 64)
+ * wb  [Cout, ks*ks*Cin + sc_C] 16-bit, K index = (ky*ks+kx)*Cin + c, then the shortcut columns
+ * bias fp32 [Cout] (all biases summed) or NULL; Cout % 64 == 0, <= 1024; ks in {1,3}
+ * precision: SDG_PREC_BF16 or SDG_PREC_FP16 = the 16-bit element type of in / wb / sc_in / out_relu / out_raw. */
+SDG_API int sdg_conv2d_h16(const void* in, const void* wb, const float* bias, int64_t n, int H, int W, int Cin, int Cout,
+                   int ks, const void* sc_in, int sc_C, int pool, const float* res_f32, int res_relu,
+                   const void* img, int img_layout, const float* sc_w3, void* out_relu, void* out_raw,
+                   float* out_f32, int precision, void* stream);
+/* First conv of the SNGAN discriminators straight from the dataset bytes: out = relu(conv3x3(normalise(x)) + b).
+ * Replaces transform.py:3-11 + DBlockOptimized.c1 + ReLU.  x: uint8 [n,S,S,3] or fp32 [n,3,S,S] (layout);
+ * wb 16-bit [Cout][64] with K index (ky*3+kx)*3 + c (27 real columns, rest zero); S in {32,64}; Cout in {64,128}. */
+SDG_API int sdg_first_conv_h16(const void* x, int layout, const void* wb, const float* bias, void* out, int64_t n, int S,
+                       int Cout, int precision, void* stream);
 
 /* ---- running per-sample statistics (new: the reference keeps every snapshot, trainer.py:337-338) --
  * Welford update with snapshot number t (0-based) plus last value and sum |x_t - x_{t-1}|:

@@ -1,0 +1,242 @@
+// conv_first.cu -- first convolution of the SNGAN discriminators straight from the dataset bytes.
+//
+// Replaces transform.py:3-11 (ToTensor + Normalize) + DBlockOptimized.c1 (SNConv2d 3->C, 3x3, pad 1) + ReLU
+// (torch-mimicry resblocks.py; SURVEY 8(a) "b1.c1"): out = relu(conv3x3(norm(x)) + b), written as the 16-bit
+// NHWC operand of the next conv.  K = 27 is too thin to stream through TMA, so builder warps assemble the
+// im2col tile (128 pixels x 32, 128B-swizzled K-major) in shared memory from a small raw patch of the
+// uint8 (or fp32 NCHW) image -- uint8 goes through a 256-entry lookup table of normalised 16-bit values
+// -- and one thread issues two tcgen05.mma (K = 2 x 16) per tile.  HBM-write-bound: 3 KB in, 256 KB out
+// per CIFAR-shaped sample.
+// Warp roles: warps 0-3 epilogue (TMEM lane quadrant = warp), warps 4-7 builders, warp 8 TMA / MMA / TMEM.
+#include "tc_ptx.cuh"
+
+namespace sdg {
+
+constexpr int FC_THREADS = 288;
+constexpr int FC_A_BYTES = 128 * 128;
+
+struct FcParams {
+  const void* x;
+  int layout, S, Cout;
+  long long n_images, tiles;
+  const float* bias;
+  h16* out;
+};
+
+template <int BN, bool F16>
+__global__ void __launch_bounds__(FC_THREADS, 1)
+first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const FcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t b_addr = smem_base + 2 * FC_A_BYTES;
+
+  __shared__ __align__(8) uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_bias[BN];
+  __shared__ __align__(16) float s_rawf[2][768];      // raw patch: (R+2) x S x 3 bytes (u8) or floats (fp32)
+  __shared__ uint16_t s_lut[256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.S;
+  const int R = 128 / S;                  // image rows per tile
+  const int tiles_y = S / R;
+
+  for (int i = threadIdx.x; i < BN; i += FC_THREADS) s_bias[i] = p.bias[i];
+  if (threadIdx.x < 256) {
+    float v = __fdiv_rn((float)threadIdx.x, 255.0f);
+    v = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
+    s_lut[threadIdx.x] = (uint16_t)(pack_h2<F16>(v, 0.f) & 0xffffu);
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(smem_u32(&a_full[s]), 128);
+        mbar_init(smem_u32(&a_empty[s]), 1);
+        mbar_init(smem_u32(&acc_full[s]), 1);
+        mbar_init(smem_u32(&acc_empty[s]), 4);
+      }
+      mbar_init(smem_u32(&b_full), 1);
+      fence_barrier_init();
+      tma_prefetch_desc(&map_b);
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&tmem_base_slot), 2 * BN);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 8) {
+    // ================= weights (once) + MMA issuer =================
+    if (elect_one()) {
+      mbar_expect_tx(smem_u32(&b_full), BN * 128);
+      tma_load_2d(b_addr, &map_b, smem_u32(&b_full), 0, 0);
+      mbar_wait(smem_u32(&b_full), 0);
+      constexpr uint32_t idesc = make_idesc(128, BN, F16);
+      const uint64_t bdesc = make_sw128_desc(b_addr);
+      long long local = 0;
+      for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++local) {
+        const int buf = (int)(local & 1);
+        const uint32_t ph = (uint32_t)((local >> 1) & 1);
+        mbar_wait(smem_u32(&acc_empty[buf]), ph ^ 1u);
+        mbar_wait(smem_u32(&a_full[buf]), ph);
+        tc_fence_after();
+        const uint64_t adesc = make_sw128_desc(smem_base + buf * FC_A_BYTES);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        umma_bf16(d_tmem, adesc, bdesc, idesc, 0u);                 // k = 0..15
+        umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);         // k = 16..31 (27..31 are zero)
+        umma_commit(smem_u32(&a_empty[buf]));
+        umma_commit(smem_u32(&acc_full[buf]));
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= builders: raw patch -> swizzled im2col tile =================
+    const int bt = threadIdx.x - 128;           // 0..127 = pixel of the tile
+    const int ly = bt / S, lx = bt - ly * S;
+    const bool u8 = p.layout == SDG_LAYOUT_U8_NHWC;
+    long long local = 0;
+    for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++local) {
+      const int buf = (int)(local & 1);
+      const uint32_t ph = (uint32_t)((local >> 1) & 1);
+      const long long n = tile / tiles_y;
+      const int y0 = (int)(tile % tiles_y) * R;
+      float* rawf = s_rawf[buf];
+      uint8_t* rawb = reinterpret_cast<uint8_t*>(rawf);
+      // ---- raw patch rows y0-1 .. y0+R (rows outside the image are never read back) ----
+      if (u8) {
+        const int words_per_row = S * 3 / 4;
+        const int words = (R + 2) * words_per_row;
+        for (int w = bt; w < words; w += 128) {
+          const int pr = w / words_per_row, wi = w - pr * words_per_row;
+          const int iy = y0 - 1 + pr;
+          if (iy >= 0 && iy < S)
+            reinterpret_cast<uint32_t*>(rawb)[w] =
+                reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(p.x) + ((n * S + iy) * (long long)S) * 3)[wi];
+        }
+      } else {
+        const int per_c = (R + 2) * S;
+        for (int w = bt; w < 3 * per_c; w += 128) {
+          const int c = w / per_c, r = w - c * per_c;
+          const int pr = r / S, ix = r - pr * S;
+          const int iy = y0 - 1 + pr;
+          if (iy >= 0 && iy < S) rawf[w] = reinterpret_cast<const float*>(p.x)[((n * 3 + c) * S + iy) * (long long)S + ix];
+        }
+      }
+      named_bar_sync(1, 128);
+      // ---- gather this pixel's 3x3x3 neighbourhood: k = (ky*3+kx)*3 + c ----
+      uint32_t packed[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) packed[j] = 0u;
+      uint16_t vals[28];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        const int iy = y0 + ly + ky - 1, ix = lx + kx - 1;
+        const bool ok = iy >= 0 && iy < S && ix >= 0 && ix < S;
+        const int pr = ly + ky;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint16_t h = 0;
+          if (ok) {
+            if (u8) h = s_lut[rawb[(pr * S + ix) * 3 + c]];
+            else h = (uint16_t)(pack_h2<F16>(rawf[(c * (R + 2) + pr) * S + ix], 0.f) & 0xffffu);
+          }
+          vals[tap * 3 + c] = h;
+        }
+      }
+      vals[27] = 0;
+#pragma unroll
+      for (int j = 0; j < 14; ++j) packed[j] = (uint32_t)vals[2 * j] | ((uint32_t)vals[2 * j + 1] << 16);
+      mbar_wait(smem_u32(&a_empty[buf]), ph ^ 1u);          // the MMAs that read this buffer have retired
+      uint8_t* row = smem_gen + buf * FC_A_BYTES + bt * 128;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(row + ((ch ^ (bt & 7)) << 4)) =
+            make_uint4(packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
+      fence_proxy_async_smem();                             // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(smem_u32(&a_full[buf]));
+    }
+  } else {
+    // ================= epilogue: TMEM -> bias + ReLU -> 16-bit NHWC =================
+    const int q = warp;
+    long long local = 0;
+    for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++local) {
+      const int buf = (int)(local & 1);
+      const uint32_t ph = (uint32_t)((local >> 1) & 1);
+      mbar_wait(smem_u32(&acc_full[buf]), ph);
+      tc_fence_after();
+      h16* orow = p.out + (tile * 128 + q * 32 + lane) * (long long)BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float a = fmaxf(__uint_as_float(r[g * 8 + 2 * j]) + s_bias[c0 + g * 8 + 2 * j], 0.f);
+            float b = fmaxf(__uint_as_float(r[g * 8 + 2 * j + 1]) + s_bias[c0 + g * 8 + 2 * j + 1], 0.f);
+            h[j] = pack_h2<F16>(a, b);
+          }
+          *reinterpret_cast<uint4*>(orow + c0 + g * 8) = pk;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+template <int BN>
+constexpr int fc_smem_bytes() { return 2 * FC_A_BYTES + BN * 128 + 1024; }
+
+int first_conv_init() {
+  SDG_CUDA(cudaFuncSetAttribute(first_conv_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<128>()));
+  SDG_CUDA(cudaFuncSetAttribute(first_conv_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<128>()));
+  SDG_CUDA(cudaFuncSetAttribute(first_conv_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<64>()));
+  SDG_CUDA(cudaFuncSetAttribute(first_conv_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<64>()));
+  return 0;
+}
+
+int first_conv(const void* x, int layout, const h16* wb, const float* bias, h16* out, int64_t n, int S, int Cout,
+               int f16, cudaStream_t s) {
+  SDG_REQUIRE(S == 32 || S == 64, SDG_E_UNSUPPORTED, "first_conv: image size %d", S);
+  SDG_REQUIRE(Cout == 64 || Cout == 128, SDG_E_UNSUPPORTED, "first_conv: Cout=%d", Cout);
+  SDG_REQUIRE(bias, SDG_E_INVALID, "first_conv: bias required");
+  SDG_REQUIRE(((uintptr_t)x % 4) == 0 && ((uintptr_t)out % 16) == 0, SDG_E_INVALID, "first_conv: misaligned pointer");
+  if (n == 0) return 0;
+  CUtensorMap map_b;
+  { int rc = tc_encode_2d(&map_b, wb, f16, 64, Cout, 64, Cout); if (rc) return rc; }
+  FcParams p;
+  p.x = x; p.layout = layout; p.S = S; p.Cout = Cout; p.n_images = n;
+  p.tiles = n * (S * S / 128);
+  p.bias = bias; p.out = out;
+  const int sms = tc_num_sms();
+  const int grid = (int)(p.tiles < sms ? p.tiles : sms);
+  if (Cout == 128 && f16) {
+    SDG_LAUNCH((first_conv_kernel<128, true>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, p);
+  } else if (Cout == 128) {
+    SDG_LAUNCH((first_conv_kernel<128, false>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, p);
+  } else if (f16) {
+    SDG_LAUNCH((first_conv_kernel<64, true>), grid, FC_THREADS, fc_smem_bytes<64>(), s, map_b, p);
+  } else {
+    SDG_LAUNCH((first_conv_kernel<64, false>), grid, FC_THREADS, fc_smem_bytes<64>(), s, map_b, p);
+  }
+  return 0;
+}
+
+}  // namespace sdg

@@ -1,28 +1,32 @@
-// conv_tc.cu -- tcgen05 implicit-GEMM convolution for the discriminator forward (the throughput path).
+// conv_tc.cu -- tcgen05 implicit-GEMM convolution with fused block epilogues (the throughput path).
 //
-// Replaces F.conv2d(x, W/sigma, b, stride 1, pad ks/2) of torch-mimicry SNConv2d as called by the
-// SNGAN discriminator blocks (call site trainer.py:150) for 3x3 and 1x1 kernels.
+// Replaces, for one spectral-normalised residual-block stage of the SNGAN discriminators (torch-mimicry
+// DBlock / DBlockOptimized; call site trainer.py:150):
+//     F.conv2d(x, W/sigma, b, stride 1, pad ks/2)                       (3x3 or 1x1)
+//   [ + F.conv2d(s, Wsc/sigma_sc, bsc)   the block's 1x1 shortcut conv, folded in as extra K columns ]
+//   [ + Wsc3 . avg_pool2d(x_img)         DBlockOptimized's 3-channel shortcut, 3 FMAs in the epilogue ]
+//   [ avg_pool2d(., 2) ]  [ + identity shortcut ]  [ ReLU for the next conv ]
 //
-// GEMM view: D[M = pixels, N = Cout] = A[M, K = taps*Cin] * B[N, K]^T, bf16 operands, fp32 accumulate.
-//   * A is never materialised: NHWC activations are read by 4-D TMA boxes {64 channels, bw, bh, bn}
-//     (bw*bh*bn = 128 consecutive pixels of full-width rows), one box per (tap, 64-channel chunk),
-//     shifted by the tap offset; the halo of the 3x3 window is the TMA out-of-bounds zero fill.
-//     A box lands in shared memory as 128 rows x 128 B, 128B-swizzled = the canonical K-major UMMA
-//     operand layout.
-//   * B (weights, [Cout][taps*Cin] bf16, sigma folded in) is read by 2-D TMA boxes {64, BN}.
-//   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM
-//     accumulator; stages are recycled with tcgen05.commit -> mbarrier.
-//   * epilogue warps read TMEM with tcgen05.ld, add bias, optional ReLU, pack bf16, store NHWC.
-// Persistent CTAs (one per SM), static tile schedule, warp-specialised: warp 0 TMA producer, warp 1
-// MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
-#include <cuda.h>
-
-#include "kernels.cuh"
+// GEMM view: D[M = pixels, N = Cout] = A[M, K] * B[N, K]^T, 16-bit operands (fp16 or bf16), fp32 accumulate.
+//   * A is never materialised: NHWC activations are read by 4-D TMA boxes of 64 channels x 128 pixels, one
+//     box set per (tap, 64-channel chunk), shifted by the tap offset; the halo of the 3x3 window is the
+//     TMA out-of-bounds zero fill.  A box lands in shared memory as rows of 128 B, 128B-swizzled = the
+//     canonical K-major UMMA operand layout.
+//     Tile geometry: "linear" = 128 consecutive pixels (full-width rows, W <= 16 or no pooling);
+//     "quarter" = four 2-row x 16-column boxes so that every epilogue warp owns whole 2x2 pooling quads.
+//   * B (weights [Cout][K] K-major, sigma folded in, shortcut columns appended) by 2-D TMA boxes {64, BN}.
+//   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM accumulator;
+//     smem stages are recycled with tcgen05.commit -> mbarrier.
+//   * epilogue warps: tcgen05.ld, 2x2 average pooling by warp shuffles, + bias, + shortcut, then up to
+//     three stores: ReLU'd 16-bit (operand of the next conv), raw 16-bit, raw fp32 (residual stream / head).
+// Persistent CTAs (one per SM), static tile schedule, warp-specialised: warp 0 TMA producer, warp 1 MMA
+// issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
+#include "tc_ptx.cuh"
 
 namespace sdg {
 
 constexpr int TC_BM = 128;            // pixels per tile (UMMA M)
-constexpr int TC_BK = 64;             // channels per stage (128 B of bf16 = one swizzle row)
+constexpr int TC_BK = 64;             // channels per stage (128 B of 16-bit = one swizzle row)
 constexpr int TC_STAGES = 6;
 constexpr int TC_THREADS = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;     // 16 KB
@@ -31,148 +35,44 @@ constexpr int TC_MAX_COUT = 1024;
 
 struct TcParams {
   int H, W, Cin, Cout, taps;
-  int bh, tiles_y, bn;       // tile = bn images x bh rows x W columns
-  int n_tiles;               // Cout / BN
   int kchunks;               // Cin / 64
-  int post_relu;
+  int sc_chunks;             // extra shortcut K chunks read through map_s (0 = none)
+  int quarter;               // tile geometry: 0 linear, 1 quarter boxes (W >= 32 with pooling)
+  int bh, tiles_y, bn;       // linear: tile = bn images x bh rows x W columns; quarter: tiles_y row groups per image
+  int n_tiles;               // Cout / BN
+  int pool;                  // 2x2 average pooling in the epilogue
+  int res_relu;              // ReLU the identity residual before adding (mimicry's in-place aliasing)
+  int img_layout;            // layout of `img` for the 3-FMA shortcut
+  long long n_images;
   long long m_tiles;
   long long total_pixels;
+  const float* bias;         // [Cout] (shortcut bias already added)
+  const float* res_f32;      // identity shortcut, fp32 [out pixels][Cout] or null
+  const void* img;           // network input for the 3-FMA shortcut (DBlockOptimized) or null
+  const float* sc_w3;        // [Cout][3] fp32, W_sc / sigma
+  h16* out_relu;             // relu(v) 16-bit or null
+  h16* out_raw;              // v 16-bit or null
+  float* out_f32;            // v fp32 or null
 };
 
-// ---------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug must fail the launch (trap), never hang the GPU box
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 6000000000LL) {      // ~3 s at 2 GHz
-      printf("sdg conv_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+__device__ __forceinline__ float norm_px(const void* img, int layout, long long n, int y, int x, int c, int H, int W) {
+  if (layout == SDG_LAYOUT_U8_NHWC) {
+    float v = __fdiv_rn((float)reinterpret_cast<const uint8_t*>(img)[((n * H + y) * W + x) * 3 + c], 255.0f);
+    return __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
   }
-}
-
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16 (bf16 inputs, fp32 accumulate)
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, 16-byte units        bits [0,14)
-  d |= (uint64_t)1 << 16;                             // leading byte offset (ignored)       bits [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset                  bits [32,46)
-  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)      bits [46,48)
-  d |= (uint64_t)2 << 61;                             // layout type SWIZZLE_128B            bits [61,64)
-  return d;
-}
-
-// instruction descriptor: D fp32 (bits 4-5 = 1), A/B format (bits 7-9 / 10-12: 0 = fp16, 1 = bf16),
-// both operands K-major, N >> 3 at bits 17-22, M >> 4 at bits 24-28
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool f16) {
-  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
+  return reinterpret_cast<const float*>(img)[((n * 3 + c) * H + y) * (long long)W + x];
 }
 
 // ---------------------------------------------------------------------------------------------------
 template <int BN, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const float* __restrict__ bias, h16* __restrict__ out, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_s, const TcParams p) {
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: required by the 128B swizzle atom (TMA and UMMA must agree on address bits)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   __shared__ __align__(8) uint64_t bar_full[TC_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[TC_STAGES];
@@ -180,15 +80,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_bias[TC_MAX_COUT];
+  __shared__ float s_w3[TC_MAX_COUT * 3];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) s_bias[i] = bias ? bias[i] : 0.f;
+  for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  if (p.img)
+    for (int i = threadIdx.x; i < p.Cout * 3; i += TC_THREADS) s_w3[i] = p.sc_w3[i];
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (p.sc_chunks) tma_prefetch_desc(&map_s);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -208,7 +112,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = tmem_base_slot;
 
   const long long total_tiles = p.m_tiles * p.n_tiles;
-  const int k_iters = p.taps * p.kchunks;
+  const int main_iters = p.taps * p.kchunks;
+  const int k_iters = main_iters + p.sc_chunks;
+  const int QR = p.W >> 4;                           // quarter mode: 16-column boxes per image row (2 or 4)
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -219,20 +125,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int nt = (int)(tile % p.n_tiles);
         const long long mt = tile / p.n_tiles;
         const int ty = (int)(mt % p.tiles_y);
-        const int n0 = (int)(mt / p.tiles_y) * p.bn;
-        const int y0 = ty * p.bh;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
-          const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-            const uint32_t full = smem_u32(&bar_full[stage]);
-            mbar_expect_tx(full, STAGE_BYTES);
-            const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-            tma_load_4d(a_dst, &map_a, full, kc * TC_BK, dx, y0 + dy, n0);
-            tma_load_2d(a_dst + TC_A_BYTES, &map_b, full, tap * p.Cin + kc * TC_BK, nt * BN);
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+        const int n0 = p.quarter ? (int)(mt / p.tiles_y) : (int)(mt / p.tiles_y) * p.bn;
+        const int y0 = p.quarter ? ty * (8 / QR) : ty * p.bh;
+        for (int it = 0; it < k_iters; ++it) {
+          const bool is_sc = it >= main_iters;
+          const int tap = is_sc ? 0 : it / p.kchunks;
+          const int kc = is_sc ? it - main_iters : it - tap * p.kchunks;
+          const int dy = (!is_sc && p.taps == 9) ? tap / 3 - 1 : 0;
+          const int dx = (!is_sc && p.taps == 9) ? tap % 3 - 1 : 0;
+          const CUtensorMap* am = is_sc ? &map_s : &map_a;
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          mbar_expect_tx(full, STAGE_BYTES);
+          const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
+          if (p.quarter) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              tma_load_4d(a_dst + q * 4096, am, full, kc * TC_BK, 16 * (q % QR) + dx, y0 + 2 * (q / QR) + dy, n0);
+          } else {
+            tma_load_4d(a_dst, am, full, kc * TC_BK, dx, y0 + dy, n0);
           }
+          tma_load_2d(a_dst + TC_A_BYTES, &map_b, full, it * TC_BK, nt * BN);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -257,7 +171,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint64_t bdesc = make_sw128_desc(a_addr + TC_A_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the swizzle row: +2 in the 16-byte-unit address field
+            // advance 16 elements = 32 B inside the swizzle row: +2 in the 16-byte-unit address field
             umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit(smem_u32(&bar_empty[stage]));       // frees the smem stage when these MMAs retire
@@ -267,38 +181,110 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue: TMEM -> registers -> bias/ReLU -> bf16 -> global (NHWC) =================
+    // ================= epilogue =================
     const int q = warp - 4;                       // TMEM lane quadrant this warp may access
+    const int wc = p.quarter ? 16 : (p.W < 16 ? p.W : 16);   // columns per warp-row (pooling partner stride)
+    const int HW = p.H * p.W;
+    const int Ho = p.pool ? p.H >> 1 : p.H, Wo = p.pool ? p.W >> 1 : p.W;
     long long local = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int nt = (int)(tile % p.n_tiles);
       const long long mt = tile / p.n_tiles;
       const int acc = (int)(local & 1);
       const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
+      // this thread's pixel (n, y, x)
+      long long n;
+      int y, x;
+      bool valid;
+      if (p.quarter) {
+        n = mt / p.tiles_y;
+        const int ty = (int)(mt % p.tiles_y);
+        x = 16 * (q % QR) + (lane & 15);
+        y = ty * (8 / QR) + 2 * (q / QR) + (lane >> 4);
+        valid = n < p.n_images;
+      } else {
+        const long long pix = mt * TC_BM + q * 32 + lane;    // 128 consecutive NHW pixels
+        n = pix / HW;
+        const int r = (int)(pix - n * HW);
+        y = r / p.W;
+        x = r - y * p.W;
+        valid = pix < p.total_pixels;
+      }
+      bool active = valid;
+      if (p.pool) active = valid && ((x & 1) == 0) && ((y & 1) == 0);
+      const long long opix = (n * Ho + (p.pool ? (y >> 1) : y)) * Wo + (p.pool ? (x >> 1) : x);
+      float px[3] = {0.f, 0.f, 0.f};
+      if (p.img && active) {
+        // avg_pool2d of the normalised network input at this pooled pixel (DBlockOptimized shortcut input)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          px[c] = (norm_px(p.img, p.img_layout, n, y, x, c, p.H, p.W) + norm_px(p.img, p.img_layout, n, y, x + 1, c, p.H, p.W) +
+                   norm_px(p.img, p.img_layout, n, y + 1, x, c, p.H, p.W) + norm_px(p.img, p.img_layout, n, y + 1, x + 1, c, p.H, p.W)) * 0.25f;
+      }
       mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
       tc_fence_after();
-      const long long pix = mt * TC_BM + q * 32 + lane;      // tile rows are 128 consecutive NHW pixels
-      const bool valid = pix < p.total_pixels;
-      h16* orow = out + pix * p.Cout + nt * BN;
-      const float* brow = s_bias + nt * BN;
+      const long long obase = opix * p.Cout + nt * BN;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
         tmem_ld_wait();
-        if (valid) {
+        float v[32];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 pk;
-            uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.pool) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float x = __uint_as_float(r[g * 8 + 2 * j]) + brow[c0 + g * 8 + 2 * j];
-              float y = __uint_as_float(r[g * 8 + 2 * j + 1]) + brow[c0 + g * 8 + 2 * j + 1];
-              if (p.post_relu) { x = fmaxf(x, 0.f); y = fmaxf(y, 0.f); }
-              h[j] = pack_h2<F16>(x, y);
+          for (int j = 0; j < 32; ++j) {
+            v[j] += __shfl_down_sync(0xffffffffu, v[j], 1);
+            v[j] += __shfl_down_sync(0xffffffffu, v[j], wc);
+            v[j] *= 0.25f;
+          }
+        }
+        if (active) {
+          const int cb = nt * BN + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += s_bias[cb + j];
+          if (p.img) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float* w3 = s_w3 + (cb + j) * 3;
+              v[j] = fmaf(w3[0], px[0], fmaf(w3[1], px[1], fmaf(w3[2], px[2], v[j])));
             }
-            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = pk;
+          }
+          if (p.res_f32) {
+            const float4* rp = reinterpret_cast<const float4*>(p.res_f32 + obase + c0);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              float4 t = rp[g];
+              if (p.res_relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+              v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+            }
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) op[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          }
+          if (p.out_raw) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 pk;
+              uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) h[j] = pack_h2<F16>(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+              *reinterpret_cast<uint4*>(p.out_raw + obase + c0 + g * 8) = pk;
+            }
+          }
+          if (p.out_relu) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 pk;
+              uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                h[j] = pack_h2<F16>(fmaxf(v[g * 8 + 2 * j], 0.f), fmaxf(v[g * 8 + 2 * j + 1], 0.f));
+              *reinterpret_cast<uint4*>(p.out_relu + obase + c0 + g * 8) = pk;
+            }
           }
         }
       }
@@ -314,7 +300,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
-  (void)smem_gen;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -328,6 +313,34 @@ static int g_num_sms = kNumSMs;
 
 template <int BN>
 constexpr int tc_smem_bytes() { return TC_STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024; }
+
+int tc_num_sms() { return g_num_sms; }
+
+int tc_encode_2d(CUtensorMap* map, const void* ptr, int f16, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                 uint32_t box_outer) {
+  SDG_REQUIRE(g_encode, SDG_E_STATE, "conv_tc: conv_tc_init not called");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SDG_REQUIRE(r == CUDA_SUCCESS, SDG_E_INVALID, "conv_tc: cuTensorMapEncodeTiled(2d) failed: %d", (int)r);
+  return 0;
+}
+
+static int encode_act(CUtensorMap* map, const void* ptr, int f16, int64_t n, int H, int W, int C, int bw, int bh, int bn) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SDG_REQUIRE(r == CUDA_SUCCESS, SDG_E_INVALID, "conv_tc: cuTensorMapEncodeTiled(act) failed: %d", (int)r);
+  return 0;
+}
 
 int conv_tc_init(int device) {
   if (g_encode) return 0;
@@ -345,61 +358,69 @@ int conv_tc_init(int device) {
   SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>()));
   SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>()));
   g_encode = (EncodeTiledFn)fn;
+  int rc = first_conv_init();
+  if (rc) { g_encode = nullptr; return rc; }
   return 0;
 }
 
-int conv_tc(const h16* in, const h16* wb, const float* bias, h16* out, int64_t n, int H, int W, int Cin, int Cout,
-            int taps, int post_relu, int f16, cudaStream_t s) {
+int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   SDG_REQUIRE(g_encode, SDG_E_STATE, "conv_tc: conv_tc_init not called");
+  const int H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout, taps = a.taps;
   SDG_REQUIRE(taps == 9 || taps == 1, SDG_E_UNSUPPORTED, "conv_tc: taps=%d", taps);
   SDG_REQUIRE(Cin % TC_BK == 0 && Cout % 64 == 0 && Cout <= TC_MAX_COUT, SDG_E_UNSUPPORTED, "conv_tc: Cin=%d Cout=%d", Cin, Cout);
   SDG_REQUIRE(W >= 4 && W <= 128 && (W & (W - 1)) == 0 && H == W, SDG_E_UNSUPPORTED, "conv_tc: H=%d W=%d", H, W);
-  SDG_REQUIRE(((uintptr_t)in % 16) == 0 && ((uintptr_t)wb % 16) == 0 && ((uintptr_t)out % 16) == 0, SDG_E_INVALID,
-              "conv_tc: pointers must be 16-byte aligned");
-  if (n == 0) return 0;
+  SDG_REQUIRE(a.sc_C % TC_BK == 0, SDG_E_UNSUPPORTED, "conv_tc: shortcut channels %d", a.sc_C);
+  SDG_REQUIRE((a.sc_C == 0) == (a.sc_in == nullptr), SDG_E_INVALID, "conv_tc: shortcut tensor / channels mismatch");
+  SDG_REQUIRE(!a.img || (a.pool && a.sc_w3), SDG_E_INVALID, "conv_tc: image shortcut needs pooling and weights");
+  SDG_REQUIRE(a.out_relu || a.out_raw || a.out_f32, SDG_E_INVALID, "conv_tc: no output");
+  auto al16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
+  SDG_REQUIRE(al16(a.in) && al16(a.wb) && al16(a.sc_in) && al16(a.res_f32) && al16(a.out_relu) && al16(a.out_raw) &&
+                  al16(a.out_f32), SDG_E_INVALID, "conv_tc: pointers must be 16-byte aligned");
+  if (a.n == 0) return 0;
   TcParams p;
-  p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.post_relu = post_relu;
-  int rows = TC_BM / W;                       // image rows per tile if one image is big enough
-  if (rows >= H) { p.bh = H; p.bn = TC_BM / (H * W); } else { p.bh = rows; p.bn = 1; }
-  p.tiles_y = H / p.bh;
+  p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps;
+  p.kchunks = Cin / TC_BK;
+  p.sc_chunks = a.sc_C / TC_BK;
+  p.pool = a.pool ? 1 : 0;
+  p.quarter = (a.pool && W >= 32) ? 1 : 0;
+  SDG_REQUIRE(!p.quarter || W <= 64, SDG_E_UNSUPPORTED, "conv_tc: pooled conv with W=%d", W);
   const int BN = (Cout % 128 == 0) ? 128 : 64;
   p.n_tiles = Cout / BN;
-  p.kchunks = Cin / TC_BK;
-  p.m_tiles = cdiv(n, p.bn) * p.tiles_y;
-  p.total_pixels = n * H * W;
+  int bw = W, bh, bn;
+  if (p.quarter) {
+    bw = 16; bh = 2; bn = 1;
+    p.bh = 8 / (W / 16); p.bn = 1;
+    p.tiles_y = H / p.bh;
+    p.m_tiles = a.n * p.tiles_y;
+  } else {
+    int rows = TC_BM / W;                       // image rows per tile if one image is big enough
+    if (rows >= H) { p.bh = H; p.bn = TC_BM / (H * W); } else { p.bh = rows; p.bn = 1; }
+    bh = p.bh; bn = p.bn;
+    p.tiles_y = H / p.bh;
+    p.m_tiles = cdiv(a.n, p.bn) * p.tiles_y;
+  }
+  p.res_relu = a.res_relu; p.img_layout = a.img_layout;
+  p.n_images = a.n;
+  p.total_pixels = a.n * H * W;
+  p.bias = a.bias; p.res_f32 = a.res_f32; p.img = a.img; p.sc_w3 = a.sc_w3;
+  p.out_relu = a.out_relu; p.out_raw = a.out_raw; p.out_f32 = a.out_f32;
 
-  CUtensorMap map_a, map_b;
-  const CUtensorMapDataType dtype = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
-    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)W, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode(&map_a, dtype, 4, (void*)in, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SDG_REQUIRE(r == CUDA_SUCCESS, SDG_E_INVALID, "conv_tc: cuTensorMapEncodeTiled(A) failed: %d", (int)r);
-  }
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)taps * Cin, (cuuint64_t)Cout};
-    cuuint64_t strides[1] = {(cuuint64_t)taps * Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(&map_b, dtype, 2, (void*)wb, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SDG_REQUIRE(r == CUDA_SUCCESS, SDG_E_INVALID, "conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r);
-  }
+  CUtensorMap map_a, map_b, map_s;
+  { int rc = encode_act(&map_a, a.in, f16, a.n, H, W, Cin, bw, bh, bn); if (rc) return rc; }
+  if (a.sc_in) { int rc = encode_act(&map_s, a.sc_in, f16, a.n, H, W, a.sc_C, bw, bh, bn); if (rc) return rc; }
+  else map_s = map_a;
+  { int rc = tc_encode_2d(&map_b, a.wb, f16, (uint64_t)taps * Cin + a.sc_C, Cout, TC_BK, BN); if (rc) return rc; }
+
   const long long total_tiles = p.m_tiles * p.n_tiles;
   const int grid = (int)(total_tiles < g_num_sms ? total_tiles : g_num_sms);
   if (BN == 128 && f16) {
-    SDG_LAUNCH((conv_tc_kernel<128, true>), grid, TC_THREADS, tc_smem_bytes<128>(), s, map_a, map_b, bias, out, p);
+    SDG_LAUNCH((conv_tc_kernel<128, true>), grid, TC_THREADS, tc_smem_bytes<128>(), s, map_a, map_b, map_s, p);
   } else if (BN == 128) {
-    SDG_LAUNCH((conv_tc_kernel<128, false>), grid, TC_THREADS, tc_smem_bytes<128>(), s, map_a, map_b, bias, out, p);
+    SDG_LAUNCH((conv_tc_kernel<128, false>), grid, TC_THREADS, tc_smem_bytes<128>(), s, map_a, map_b, map_s, p);
   } else if (f16) {
-    SDG_LAUNCH((conv_tc_kernel<64, true>), grid, TC_THREADS, tc_smem_bytes<64>(), s, map_a, map_b, bias, out, p);
+    SDG_LAUNCH((conv_tc_kernel<64, true>), grid, TC_THREADS, tc_smem_bytes<64>(), s, map_a, map_b, map_s, p);
   } else {
-    SDG_LAUNCH((conv_tc_kernel<64, false>), grid, TC_THREADS, tc_smem_bytes<64>(), s, map_a, map_b, bias, out, p);
+    SDG_LAUNCH((conv_tc_kernel<64, false>), grid, TC_THREADS, tc_smem_bytes<64>(), s, map_a, map_b, map_s, p);
   }
   return 0;
 }

@@ -6,6 +6,7 @@
 //   * MNIST_DCGAN_Discriminator in eval mode (diagan-pkg/diagan/models/mnist.py:155-223)
 // Samples are processed in chunks that bound the activation scratch; within a chunk every layer is one
 // launch over all samples of the chunk.
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 
@@ -46,6 +47,8 @@ struct ConvLayer {
   int cout = 0, cin = 0, ks = 0, stride = 1;
   int kpad = 0;              // bf16 K (taps*cin rounded up to 64)
   DevBuf w32, w16, bias;
+  DevBuf w3, bias_sum;       // 16-bit path: fp32 [Cout][3] shortcut weights (DBlockOptimized), conv + shortcut bias
+  int ktot = 0;              // 16-bit path: K columns of w16 (conv taps + folded shortcut columns)
   bool has_bias = false;
 };
 
@@ -71,7 +74,7 @@ struct sdg_ctx {
   DevBuf sigma;                          // [n_layers]
   int n_layers = 0;
   DevBuf sn_table, sn_scratch, bn_scratch;
-  DevBuf buf[4], xin, xpool;             // activation scratch
+  DevBuf buf[7], xin, xpool;             // activation scratch
   bool loaded = false;
   // optional timing of the dominant kernel (block1.c2) with events on the launching stream
   bool profile = false;
@@ -138,7 +141,7 @@ extern "C" int sdg_ctx_create(int device, sdg_ctx** out) {
 extern "C" int sdg_ctx_destroy(sdg_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); }
+  for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); l.w3.release(); l.bias_sum.release(); }
   c->head_w.release(); c->head_b.release(); c->sigma.release();
   c->sn_table.release(); c->sn_scratch.release(); c->bn_scratch.release();
   for (auto& b : c->buf) b.release();
@@ -232,11 +235,44 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
       { int rc = l.w32.ensure(sizeof(float) * K * l.cout); if (rc) return rc; }
       int rc = pack_conv_fp32(W[i], sig + i, nullptr, l.w32.as<float>(), l.cout, l.cin, l.ks, s);
       if (rc) return rc;
-    } else {
-      { int rc = l.w16.ensure(sizeof(h16) * (size_t)l.kpad * l.cout); if (rc) return rc; }
-      int rc = pack_conv_h16(W[i], sig + i, nullptr, l.w16.as<h16>(), l.cout, l.cin, l.kpad, l.ks,
-                             precision == SDG_PREC_FP16, s);
-      if (rc) return rc;
+    }
+  }
+  if (precision != SDG_PREC_FP32) {
+    // 16-bit path: c1 as is; c2 with the block's 1x1 shortcut conv folded in as extra K columns (res blocks) or
+    // kept as fp32 [Cout][3] for the 3-FMA epilogue (DBlockOptimized); biases of c2 and c_sc summed.
+    const int f16 = precision == SDG_PREC_FP16;
+    for (size_t bi = 0; bi < c->blocks.size(); ++bi) {
+      const int i1 = c->block_first_conv[bi], i2 = i1 + 1, isc = i1 + 2;
+      const bool has_sc = c->block_has_sc[bi] != 0;
+      ConvLayer& l1 = c->convs[i1];
+      ConvLayer& l2 = c->convs[i2];
+      l1.ktot = l1.kpad;
+      { int rc = l1.w16.ensure(sizeof(h16) * (size_t)l1.ktot * l1.cout); if (rc) return rc; }
+      { int rc = pack_conv_h16(W[i1], sig + i1, nullptr, l1.w16.as<h16>(), l1.cout, l1.cin, l1.kpad, l1.ks, f16, l1.ktot, 0, s);
+        if (rc) return rc; }
+      const bool fold = has_sc && c->blocks[bi].kind == 1;
+      const int sc_cols = fold ? c->convs[isc].kpad : 0;
+      l2.ktot = l2.kpad + sc_cols;
+      { int rc = l2.w16.ensure(sizeof(h16) * (size_t)l2.ktot * l2.cout); if (rc) return rc; }
+      { int rc = pack_conv_h16(W[i2], sig + i2, nullptr, l2.w16.as<h16>(), l2.cout, l2.cin, l2.kpad, l2.ks, f16, l2.ktot, 0, s);
+        if (rc) return rc; }
+      { int rc = l2.bias_sum.ensure(sizeof(float) * l2.cout); if (rc) return rc; }
+      if (has_sc) {
+        ConvLayer& lsc = c->convs[isc];
+        if (fold) {
+          int rc = pack_conv_h16(W[isc], sig + isc, nullptr, l2.w16.as<h16>(), lsc.cout, lsc.cin, lsc.kpad, 1, f16, l2.ktot,
+                                 l2.kpad, s);
+          if (rc) return rc;
+        } else {
+          { int rc = lsc.w3.ensure(sizeof(float) * 3 * lsc.cout); if (rc) return rc; }
+          int rc = scale_vec(W[isc], sig + isc, lsc.w3.as<float>(), 3 * lsc.cout, s);
+          if (rc) return rc;
+        }
+        int rc = add_vec(l2.bias.as<float>(), lsc.bias.as<float>(), l2.bias_sum.as<float>(), l2.cout, s);
+        if (rc) return rc;
+      } else {
+        SDG_CUDA(cudaMemcpyAsync(l2.bias_sum.p, l2.bias.p, sizeof(float) * l2.cout, cudaMemcpyDeviceToDevice, s));
+      }
     }
   }
   c->head_len = ndf;
@@ -344,49 +380,57 @@ static int forward_sngan_fp32(sdg_ctx* c, const void* x, int layout, int64_t nb,
 }
 
 static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s) {
-  typedef h16 bf;
   const int f16 = c->precision == SDG_PREC_FP16;
   const int S = c->size;
-  bf* X = c->xin.as<bf>();          // [nb,S,S,64] 3x3x3 patches of the normalised input
-  bf* PX = c->xpool.as<bf>();       // [nb,S/2,S/2,64] pooled input
-  bf* h = c->buf[0].as<bf>();       // relu(h): block output as the next conv / head consumes it
-  bf* f1 = c->buf[1].as<bf>();
-  bf* f2 = c->buf[2].as<bf>();
-  bf* hraw = c->inplace_relu ? nullptr : c->buf[3].as<bf>();   // unrectified h for the textbook shortcut
+  const int nblk = (int)c->blocks.size();
+  h16* T = c->buf[0].as<h16>();                                   // relu(c1(.)) of the current block, full resolution
+  h16* hR[2] = {c->buf[1].as<h16>(), c->buf[2].as<h16>()};        // relu(h): operand of the next conv
+  h16* hW[2] = {c->buf[3].as<h16>(), c->buf[4].as<h16>()};        // raw h, 16-bit: operand of a 1x1 shortcut (textbook mode)
+  float* hF[2] = {c->buf[5].as<float>(), c->buf[6].as<float>()};  // raw h, fp32: residual stream / head input
   int rc;
-  if ((rc = stage_first_conv(x, layout, X, PX, nb, S, S, f16, s))) return rc;
-  int hw = S;
-  for (size_t bi = 0; bi < c->blocks.size(); ++bi) {
+  int hw = S, cur = 0;
+  for (int bi = 0; bi < nblk; ++bi) {
     const BlockSpec& bl = c->blocks[bi];
-    const ConvLayer& c1 = c->convs[c->block_first_conv[bi]];
-    const ConvLayer& c2 = c->convs[c->block_first_conv[bi] + 1];
+    const int i1 = c->block_first_conv[bi];
+    const ConvLayer& c1 = c->convs[i1];
+    const ConvLayer& c2 = c->convs[i1 + 1];
+    const bool has_sc = c->block_has_sc[bi] != 0;
     const int ho = bl.down ? hw / 2 : hw;
+    const bool last = bi + 1 == nblk;
+    const bool next_sc = !last && c->block_has_sc[bi + 1];
+    const int o = bi == 0 ? 0 : cur ^ 1;
+    TcConv a2;
+    a2.n = nb; a2.H = hw; a2.W = hw; a2.Cin = c2.cin; a2.Cout = c2.cout; a2.taps = 9;
+    a2.in = T; a2.wb = c2.w16.as<h16>(); a2.bias = c2.bias_sum.as<float>();
+    a2.pool = bl.down;
+    a2.out_relu = last ? nullptr : hR[o];
+    a2.out_raw = (next_sc && !c->inplace_relu) ? hW[o] : nullptr;
+    a2.out_f32 = (last || !next_sc) ? hF[o] : nullptr;
     if (bl.kind == 0) {
-      const ConvLayer& sc = c->convs[c->block_first_conv[bi] + 2];
-      // c1 as a 1x1 GEMM over the staged 27(->64)-wide patches; c_sc over the pooled input
-      if ((rc = conv_tc(X, c1.w16.as<bf>(), c1.bias.as<float>(), f1, nb, hw, hw, 64, c1.cout, 1, 1, f16, s))) return rc;
+      // DBlockOptimized: c1 straight from the image bytes; shortcut c_sc(avg_pool2d(x)) as 3 FMAs in c2's epilogue
+      if ((rc = first_conv(x, layout, c1.w16.as<h16>(), c1.bias.as<float>(), T, nb, S, c1.cout, f16, s))) return rc;
+      a2.img = x; a2.img_layout = layout; a2.sc_w3 = c->convs[i1 + 2].w3.as<float>();
       if ((rc = prof_begin(c, s))) return rc;
-      if ((rc = conv_tc(f1, c2.w16.as<bf>(), c2.bias.as<float>(), f2, nb, hw, hw, c2.cin, c2.cout, 9, 0, f16, s))) return rc;
+      if ((rc = conv_tc(a2, f16, s))) return rc;
       if ((rc = prof_end(c, s, 2.0 * (double)nb * hw * hw * c2.cout * 9.0 * c2.cin))) return rc;
-      if ((rc = conv_tc(PX, sc.w16.as<bf>(), sc.bias.as<float>(), f1, nb, ho, ho, 64, sc.cout, 1, 0, f16, s))) return rc;
-      if ((rc = combine_h16(f2, 1, f1, 0, h, hraw, nb, ho, ho, bl.cout, f16, s))) return rc;
     } else {
-      if ((rc = conv_tc(h, c1.w16.as<bf>(), c1.bias.as<float>(), f1, nb, hw, hw, c1.cin, c1.cout, 9, 1, f16, s))) return rc;
-      if ((rc = conv_tc(f1, c2.w16.as<bf>(), c2.bias.as<float>(), f2, nb, hw, hw, c2.cin, c2.cout, 9, 0, f16, s))) return rc;
-      const bf* sc_in = c->inplace_relu ? h : hraw;
-      if (c->block_has_sc[bi]) {
-        const ConvLayer& sc = c->convs[c->block_first_conv[bi] + 2];
-        if ((rc = conv_tc(sc_in, sc.w16.as<bf>(), sc.bias.as<float>(), f1, nb, hw, hw, sc.cin, sc.cout, 1, 0, f16, s))) return rc;
-        if ((rc = combine_h16(f2, bl.down, f1, bl.down, h, hraw, nb, ho, ho, bl.cout, f16, s))) return rc;
-      } else {
-        // identity shortcut: h' = c2(...) + (relu(h) | h); written to f1, then the roles swap
-        if ((rc = combine_h16(f2, 0, sc_in, 0, f1, hraw, nb, ho, ho, bl.cout, f16, s))) return rc;
-        bf* t = h; h = f1; f1 = t;
+      TcConv a1;
+      a1.n = nb; a1.H = hw; a1.W = hw; a1.Cin = c1.cin; a1.Cout = c1.cout; a1.taps = 9;
+      a1.in = hR[cur]; a1.wb = c1.w16.as<h16>(); a1.bias = c1.bias.as<float>(); a1.out_relu = T;
+      if ((rc = conv_tc(a1, f16, s))) return rc;
+      if (has_sc) {                      // 1x1 shortcut conv folded into c2's K loop (input: relu(h) or h)
+        a2.sc_in = c->inplace_relu ? hR[cur] : hW[cur];
+        a2.sc_C = c->convs[i1 + 2].kpad;
+      } else {                           // identity shortcut from the fp32 residual stream
+        a2.res_f32 = hF[cur];
+        a2.res_relu = c->inplace_relu;
       }
+      if ((rc = conv_tc(a2, f16, s))) return rc;
     }
+    cur = o;
     hw = ho;
   }
-  return head_h16(h, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, hw * hw, c->head_len, f16, s);
+  return head_sumpool_fp32(hF[cur], c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, hw * hw, c->head_len, 1, s);
 }
 
 static int forward_dcgan_fp32(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s) {
@@ -427,13 +471,24 @@ extern "C" int sdg_d_forward(sdg_ctx* c, const void* x, int layout, int64_t n, f
     if (chunk < 1) chunk = 1;
   }
   if (chunk > n) chunk = n;
-  const size_t esz = bf ? 2 : 4;
-  const int nbuf = c->arch == SDG_ARCH_DCGAN32 ? 2 : ((bf && !c->inplace_relu) ? 4 : 3);
-  for (int i = 0; i < nbuf; ++i) { int rc = c->buf[i].ensure((size_t)chunk * act * esz); if (rc) return rc; }
   if (bf) {
-    { int rc = c->xin.ensure((size_t)chunk * S * S * 64 * 2); if (rc) return rc; }
-    { int rc = c->xpool.ensure((size_t)chunk * (S / 2) * (S / 2) * 64 * 2); if (rc) return rc; }
+    // T: full-resolution relu(c1) of any block; hR/hW: block outputs 16-bit; hF: block outputs fp32
+    int64_t t_el = 0, h_el = 0;
+    int hw = S;
+    for (auto& b : c->blocks) {
+      const int hidden = b.kind == 0 ? b.cout : b.cin;
+      const int ho = b.down ? hw / 2 : hw;
+      t_el = std::max<int64_t>(t_el, (int64_t)hw * hw * hidden);
+      h_el = std::max<int64_t>(h_el, (int64_t)ho * ho * b.cout);
+      hw = ho;
+    }
+    { int rc = c->buf[0].ensure((size_t)chunk * t_el * 2); if (rc) return rc; }
+    for (int i = 1; i <= 2; ++i) { int rc = c->buf[i].ensure((size_t)chunk * h_el * 2); if (rc) return rc; }
+    if (!c->inplace_relu) for (int i = 3; i <= 4; ++i) { int rc = c->buf[i].ensure((size_t)chunk * h_el * 2); if (rc) return rc; }
+    for (int i = 5; i <= 6; ++i) { int rc = c->buf[i].ensure((size_t)chunk * h_el * 4); if (rc) return rc; }
   } else {
+    const int nbuf = c->arch == SDG_ARCH_DCGAN32 ? 2 : 3;
+    for (int i = 0; i < nbuf; ++i) { int rc = c->buf[i].ensure((size_t)chunk * act * 4); if (rc) return rc; }
     { int rc = c->xin.ensure((size_t)chunk * S * S * 3 * 4); if (rc) return rc; }
     { int rc = c->xpool.ensure((size_t)chunk * (S / 2) * (S / 2) * 3 * 4); if (rc) return rc; }
   }
@@ -450,17 +505,36 @@ extern "C" int sdg_d_forward(sdg_ctx* c, const void* x, int layout, int64_t n, f
   return 0;
 }
 
-extern "C" int sdg_conv2d_h16(const void* in, const void* wb, const float* bias, void* out, int64_t n, int H, int W,
-                              int Cin, int Cout, int ks, int relu, int precision, void* stream) {
-  SDG_REQUIRE(in && wb && out, SDG_E_INVALID, "sdg_conv2d_h16: null pointer");
+extern "C" int sdg_conv2d_h16(const void* in, const void* wb, const float* bias, int64_t n, int H, int W, int Cin,
+                              int Cout, int ks, const void* sc_in, int sc_C, int pool, const float* res_f32, int res_relu,
+                              const void* img, int img_layout, const float* sc_w3, void* out_relu, void* out_raw,
+                              float* out_f32, int precision, void* stream) {
+  SDG_REQUIRE(in && wb, SDG_E_INVALID, "sdg_conv2d_h16: null pointer");
   SDG_REQUIRE(ks == 1 || ks == 3, SDG_E_UNSUPPORTED, "sdg_conv2d_h16: ks=%d", ks);
   SDG_REQUIRE(precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID, "sdg_conv2d_h16: precision=%d",
               precision);
   int dev = 0;
   SDG_CUDA(cudaGetDevice(&dev));
   { int rc = conv_tc_init(dev); if (rc) return rc; }
-  return conv_tc((const h16*)in, (const h16*)wb, bias, (h16*)out, n, H, W, Cin, Cout, ks * ks, relu,
-                 precision == SDG_PREC_FP16, (cudaStream_t)stream);
+  TcConv a;
+  a.in = (const h16*)in; a.wb = (const h16*)wb; a.bias = bias; a.n = n; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
+  a.taps = ks * ks; a.sc_in = (const h16*)sc_in; a.sc_C = sc_C; a.pool = pool; a.res_f32 = res_f32; a.res_relu = res_relu;
+  a.img = img; a.img_layout = img_layout; a.sc_w3 = sc_w3;
+  a.out_relu = (h16*)out_relu; a.out_raw = (h16*)out_raw; a.out_f32 = out_f32;
+  return conv_tc(a, precision == SDG_PREC_FP16, (cudaStream_t)stream);
+}
+
+extern "C" int sdg_first_conv_h16(const void* x, int layout, const void* wb, const float* bias, void* out, int64_t n,
+                                  int S, int Cout, int precision, void* stream) {
+  SDG_REQUIRE(x && wb && bias && out, SDG_E_INVALID, "sdg_first_conv_h16: null pointer");
+  SDG_REQUIRE(precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID, "sdg_first_conv_h16: precision=%d",
+              precision);
+  SDG_REQUIRE(layout == SDG_LAYOUT_U8_NHWC || layout == SDG_LAYOUT_F32_NCHW, SDG_E_INVALID, "sdg_first_conv_h16: layout=%d",
+              layout);
+  int dev = 0;
+  SDG_CUDA(cudaGetDevice(&dev));
+  { int rc = conv_tc_init(dev); if (rc) return rc; }
+  return first_conv(x, layout, (const h16*)wb, bias, (h16*)out, n, S, Cout, precision == SDG_PREC_FP16, (cudaStream_t)stream);
 }
 
 extern "C" int sdg_ctx_profile(sdg_ctx* c, int enable) {

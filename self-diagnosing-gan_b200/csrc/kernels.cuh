@@ -56,9 +56,10 @@ int sn_sigmas(const SnLayer* layers_dev, const SnLayer* layers_host, int n_layer
 // wp[(tap*Cin + c)*Cout + o] = W[o][c][tap] * scale[o] / sigma   (scale may be null; sigma may be null)
 int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float* wp, int Cout, int Cin, int ks,
                    cudaStream_t s);
-// wb[o][k] = h16(W[o][c][tap] * scale[o] / sigma) at k = tap*Cin + c, rows zero padded to Kpad (multiple of 64)
+// wb[o*ld + col0 + k] = h16(W[o][c][tap] * scale[o] / sigma) at k = tap*Cin + c, zero padded up to Kpad columns
 int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* wb, int Cout, int Cin, int Kpad,
-                  int ks, int f16, cudaStream_t s);
+                  int ks, int f16, int ld, int col0, cudaStream_t s);
+int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);          // out = a + b
 int scale_vec(const float* in, const float* sigma, float* out, int n, cudaStream_t s);   // out = in / sigma
 // BatchNorm(eval) folding: scale[o] = gamma/sqrt(var+eps), shift[o] = beta - mean*scale
 int bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
@@ -76,11 +77,32 @@ int combine_h16(const h16* a, int pool_a, const h16* b, int pool_b, h16* out_rel
 int head_h16(const h16* hrelu, const float* w, const float* bias, float* logits, int64_t n, int HW, int C, int f16,
              cudaStream_t s);
 
-// ---- conv_tc.cu: tcgen05 implicit-GEMM convolution (16-bit in, fp32 TMEM accumulate, 16-bit out) ----
-// in [n,H,W,Cin] NHWC (Cin % 64 == 0), wb [Cout][taps*Cin] K-major, out [n,H,W,Cout];
-// taps = 9 (3x3, pad 1) or 1 (1x1); stride 1; epilogue: + bias, optional ReLU.
+// ---- conv_tc.cu / conv_first.cu: tcgen05 implicit-GEMM convolutions (16-bit in, fp32 TMEM accumulate) ----
+// One fused residual-block stage: conv (3x3 pad 1 or 1x1, stride 1) [+ the block's 1x1 shortcut conv as extra K
+// columns] [+ 3-FMA shortcut from the network input] [2x2 avg-pool] [+ identity residual] -> up to three outputs.
+struct TcConv {
+  const h16* in = nullptr;        // [n,H,W,Cin] NHWC, Cin % 64 == 0
+  const h16* wb = nullptr;        // [Cout][taps*Cin + sc_C] K-major, k = tap*Cin + c, then the shortcut columns
+  const float* bias = nullptr;    // [Cout] (conv bias + shortcut bias) or null
+  int64_t n = 0;
+  int H = 0, W = 0, Cin = 0, Cout = 0, taps = 9;
+  const h16* sc_in = nullptr;     // [n,H,W,sc_C]: input of the block's 1x1 shortcut conv (same resolution as `in`)
+  int sc_C = 0;
+  int pool = 0;                   // avg_pool2d(., 2) of conv (+ shortcut conv) before the adds below
+  const float* res_f32 = nullptr; // identity shortcut [n,Ho,Wo,Cout] fp32
+  int res_relu = 0;               // rectify the identity shortcut (mimicry's in-place ReLU aliasing)
+  const void* img = nullptr;      // network input (DBlockOptimized: shortcut = Wsc3 . avg_pool2d(img) at pooled res)
+  int img_layout = 0;
+  const float* sc_w3 = nullptr;   // [Cout][3] fp32
+  h16* out_relu = nullptr;        // relu(v) [n,Ho,Wo,Cout] 16-bit
+  h16* out_raw = nullptr;         // v 16-bit
+  float* out_f32 = nullptr;       // v fp32
+};
 int conv_tc_init(int device);
-int conv_tc(const h16* in, const h16* wb, const float* bias, h16* out, int64_t n, int H, int W, int Cin, int Cout,
-            int taps, int post_relu, int f16, cudaStream_t s);
+int conv_tc(const TcConv& args, int f16, cudaStream_t s);
+// out = relu(conv3x3(normalise(x)) + bias): x uint8 NHWC or fp32 NCHW [n,3,S,S]; wb [Cout][64] (k = tap*3+c, 27 real)
+int first_conv_init();
+int first_conv(const void* x, int layout, const h16* wb, const float* bias, h16* out, int64_t n, int S, int Cout,
+               int f16, cudaStream_t s);
 
 }  // namespace sdg

@@ -111,7 +111,7 @@ int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float
 template <bool F16>
 __global__ void __launch_bounds__(256)
 pack_conv_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigma, const float* __restrict__ scale,
-                     h16* __restrict__ wb, int Cout, int Cin, int Kpad, int taps) {
+                     h16* __restrict__ wb, int Cout, int Cin, int Kpad, int taps, int ld, int col0) {
   const int total = Cout * Kpad;
   const float sg = sigma ? sigma[0] : 1.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -124,19 +124,19 @@ pack_conv_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigm
       if (sigma) w = w / sg;
       if (scale) w = w * scale[o];
     }
-    wb[i] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
+    wb[(int64_t)o * ld + col0 + k] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
   }
 }
 
 int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* wb, int Cout, int Cin, int Kpad,
-                  int ks, int f16, cudaStream_t s) {
+                  int ks, int f16, int ld, int col0, cudaStream_t s) {
   int total = Cout * Kpad;
   if (f16) {
     SDG_LAUNCH(pack_conv_h16_kernel<true>, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wb, Cout, Cin, Kpad,
-               ks * ks);
+               ks * ks, ld, col0);
   } else {
     SDG_LAUNCH(pack_conv_h16_kernel<false>, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wb, Cout, Cin, Kpad,
-               ks * ks);
+               ks * ks, ld, col0);
   }
   return 0;
 }
@@ -145,6 +145,16 @@ __global__ void scale_vec_kernel(const float* __restrict__ in, const float* __re
                                  int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = sigma ? in[i] / sigma[0] : in[i];
+}
+
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s) {
+  SDG_LAUNCH(add_vec_kernel, (unsigned)cdiv(n, 256), 256, 0, s, a, b, out, n);
+  return 0;
 }
 
 int scale_vec(const float* in, const float* sigma, float* out, int n, cudaStream_t s) {

@@ -219,7 +219,10 @@ class RunningStats:
 def window_moments(snaps: torch.Tensor, want=("mean", "var", "ldrd", "ldr")):
     """snaps [T,N] float32 or float64 (rows = selected window, in order) -> dict of float64 [N]."""
     lib = _lib.load()
-    _require_cuda(snaps, "snaps")
+    if not snaps.is_cuda:
+        raise _lib.SdgError("snaps must be a CUDA tensor (diagan_b200 has no CPU path)")
+    if snaps.dim() != 2 or (snaps.shape[1] > 1 and snaps.stride(1) != 1):
+        raise _lib.SdgError("snaps must be [T, N] with unit stride along N (rows may be strided)")
     T, n = snaps.shape
     out = {k: torch.empty(n, dtype=torch.float64, device=snaps.device) for k in want}
     fn = {torch.float32: lib.sdg_window_moments_f32, torch.float64: lib.sdg_window_moments_f64}[snaps.dtype]
