@@ -34,7 +34,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const FcParams p) {
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_bias[BN];
-  __shared__ __align__(16) float s_rawf[2][768];      // raw patch: (R+2) x S x 3 bytes (u8) or floats (fp32)
+  __shared__ __align__(16) float s_rawf[3][768];      // raw patch: (R+2) x S x 3 bytes (u8) or floats (fp32)
   __shared__ uint16_t s_lut[256];
 
   const int warp = threadIdx.x >> 5;
@@ -97,34 +97,46 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const FcParams p) {
     const int bt = threadIdx.x - 128;           // 0..127 = pixel of the tile
     const int ly = bt / S, lx = bt - ly * S;
     const bool u8 = p.layout == SDG_LAYOUT_U8_NHWC;
+    // raw patch rows y0-1 .. y0+R of a tile, fetched two tiles ahead with cp.async (rows outside the image are
+    // skipped: the gather below never reads them)
+    auto prefetch_raw = [&](long long tile, int rb) {
+      if (tile < p.tiles) {
+        const long long n = tile / tiles_y;
+        const int y0 = (int)(tile % tiles_y) * R;
+        float* rawf = s_rawf[rb];
+        if (u8) {
+          const int words_per_row = S * 3 / 4;
+          const int words = (R + 2) * words_per_row;
+          for (int w = bt; w < words; w += 128) {
+            const int pr = w / words_per_row, wi = w - pr * words_per_row;
+            const int iy = y0 - 1 + pr;
+            if (iy >= 0 && iy < S)
+              cp_async_4(smem_u32(reinterpret_cast<uint32_t*>(rawf) + w),
+                         reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(p.x) + ((n * S + iy) * (long long)S) * 3) + wi);
+          }
+        } else {
+          const int per_c = (R + 2) * S;
+          for (int w = bt; w < 3 * per_c; w += 128) {
+            const int c = w / per_c, r = w - c * per_c;
+            const int pr = r / S, ix = r - pr * S;
+            const int iy = y0 - 1 + pr;
+            if (iy >= 0 && iy < S)
+              cp_async_4(smem_u32(rawf + w), reinterpret_cast<const float*>(p.x) + ((n * 3 + c) * S + iy) * (long long)S + ix);
+          }
+        }
+      }
+      cp_async_commit();          // one group per call, empty or not: keeps the wait_group arithmetic uniform
+    };
+    prefetch_raw(blockIdx.x, 0);
+    prefetch_raw((long long)blockIdx.x + gridDim.x, 1);
     long long local = 0;
     for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++local) {
       const int buf = (int)(local & 1);
       const uint32_t ph = (uint32_t)((local >> 1) & 1);
-      const long long n = tile / tiles_y;
       const int y0 = (int)(tile % tiles_y) * R;
-      float* rawf = s_rawf[buf];
-      uint8_t* rawb = reinterpret_cast<uint8_t*>(rawf);
-      // ---- raw patch rows y0-1 .. y0+R (rows outside the image are never read back) ----
-      if (u8) {
-        const int words_per_row = S * 3 / 4;
-        const int words = (R + 2) * words_per_row;
-        for (int w = bt; w < words; w += 128) {
-          const int pr = w / words_per_row, wi = w - pr * words_per_row;
-          const int iy = y0 - 1 + pr;
-          if (iy >= 0 && iy < S)
-            reinterpret_cast<uint32_t*>(rawb)[w] =
-                reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(p.x) + ((n * S + iy) * (long long)S) * 3)[wi];
-        }
-      } else {
-        const int per_c = (R + 2) * S;
-        for (int w = bt; w < 3 * per_c; w += 128) {
-          const int c = w / per_c, r = w - c * per_c;
-          const int pr = r / S, ix = r - pr * S;
-          const int iy = y0 - 1 + pr;
-          if (iy >= 0 && iy < S) rawf[w] = reinterpret_cast<const float*>(p.x)[((n * 3 + c) * S + iy) * (long long)S + ix];
-        }
-      }
+      const float* rawf = s_rawf[local % 3];
+      const uint8_t* rawb = reinterpret_cast<const uint8_t*>(rawf);
+      cp_async_wait_1();          // everything but the newest group has landed -> this tile's patch is in smem
       named_bar_sync(1, 128);
       // ---- gather this pixel's 3x3x3 neighbourhood: k = (ky*3+kx)*3 + c ----
       uint32_t packed[16];
@@ -158,6 +170,8 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const FcParams p) {
             make_uint4(packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
       fence_proxy_async_smem();                             // generic-proxy writes -> visible to the tensor core
       mbar_arrive(smem_u32(&a_full[buf]));
+      // the buffer of tile local-1 is free: every builder passed this tile's barrier after gathering from it
+      prefetch_raw(tile + 2 * (long long)gridDim.x, (int)((local + 2) % 3));
     }
   } else {
     // ================= epilogue: TMEM -> bias + ReLU -> 16-bit NHWC =================

@@ -13,7 +13,8 @@
 //     TMA out-of-bounds zero fill.  A box lands in shared memory as rows of 128 B, 128B-swizzled = the
 //     canonical K-major UMMA operand layout.
 //     Tile geometry: "linear" = 128 consecutive pixels (full-width rows, W <= 16 or no pooling);
-//     "quarter" = four 2-row x 16-column boxes so that every epilogue warp owns whole 2x2 pooling quads.
+//     "box16" = 8 rows x 16 columns (pooled layers with W >= 32) so that every epilogue warp owns two
+//     rows x 16 columns = whole 2x2 pooling quads.  Either way one TMA box per operand per stage.
 //   * B (weights [Cout][K] K-major, sigma folded in, shortcut columns appended) by 2-D TMA boxes {64, BN}.
 //   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM accumulator;
 //     smem stages are recycled with tcgen05.commit -> mbarrier.
@@ -37,8 +38,9 @@ struct TcParams {
   int H, W, Cin, Cout, taps;
   int kchunks;               // Cin / 64
   int sc_chunks;             // extra shortcut K chunks read through map_s (0 = none)
-  int quarter;               // tile geometry: 0 linear, 1 quarter boxes (W >= 32 with pooling)
-  int bh, tiles_y, bn;       // linear: tile = bn images x bh rows x W columns; quarter: tiles_y row groups per image
+  int box16;                 // tile geometry: 0 linear, 1 = 8 rows x 16 columns (W >= 32 with pooling)
+  int bh, tiles_y, bn;       // linear: tile = bn images x bh rows x W columns; box16: tiles_y x tiles_x tiles per image
+  int tiles_x;
   int n_tiles;               // Cout / BN
   int pool;                  // 2x2 average pooling in the epilogue
   int res_relu;              // ReLU the identity residual before adding (mimicry's in-place aliasing)
@@ -114,7 +116,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const long long total_tiles = p.m_tiles * p.n_tiles;
   const int main_iters = p.taps * p.kchunks;
   const int k_iters = main_iters + p.sc_chunks;
-  const int QR = p.W >> 4;                           // quarter mode: 16-column boxes per image row (2 or 4)
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -124,9 +125,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = (int)(tile % p.n_tiles);
         const long long mt = tile / p.n_tiles;
-        const int ty = (int)(mt % p.tiles_y);
-        const int n0 = p.quarter ? (int)(mt / p.tiles_y) : (int)(mt / p.tiles_y) * p.bn;
-        const int y0 = p.quarter ? ty * (8 / QR) : ty * p.bh;
+        int n0, y0, x0;
+        if (p.box16) {
+          const int per_img = p.tiles_x * p.tiles_y;
+          n0 = (int)(mt / per_img);
+          const int r = (int)(mt - (long long)n0 * per_img);
+          y0 = (r / p.tiles_x) * 8;
+          x0 = (r % p.tiles_x) * 16;
+        } else {
+          n0 = (int)(mt / p.tiles_y) * p.bn;
+          y0 = (int)(mt % p.tiles_y) * p.bh;
+          x0 = 0;
+        }
         for (int it = 0; it < k_iters; ++it) {
           const bool is_sc = it >= main_iters;
           const int tap = is_sc ? 0 : it / p.kchunks;
@@ -138,13 +148,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t full = smem_u32(&bar_full[stage]);
           mbar_expect_tx(full, STAGE_BYTES);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-          if (p.quarter) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              tma_load_4d(a_dst + q * 4096, am, full, kc * TC_BK, 16 * (q % QR) + dx, y0 + 2 * (q / QR) + dy, n0);
-          } else {
-            tma_load_4d(a_dst, am, full, kc * TC_BK, dx, y0 + dy, n0);
-          }
+          tma_load_4d(a_dst, am, full, kc * TC_BK, x0 + dx, y0 + dy, n0);
           tma_load_2d(a_dst + TC_A_BYTES, &map_b, full, it * TC_BK, nt * BN);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -183,7 +187,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp >= 4) {
     // ================= epilogue =================
     const int q = warp - 4;                       // TMEM lane quadrant this warp may access
-    const int wc = p.quarter ? 16 : (p.W < 16 ? p.W : 16);   // columns per warp-row (pooling partner stride)
+    const int wc = p.W < 16 ? p.W : 16;             // columns per warp-row (pooling partner stride)
     const int HW = p.H * p.W;
     const int Ho = p.pool ? p.H >> 1 : p.H, Wo = p.pool ? p.W >> 1 : p.W;
     long long local = 0;
@@ -196,11 +200,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       long long n;
       int y, x;
       bool valid;
-      if (p.quarter) {
-        n = mt / p.tiles_y;
-        const int ty = (int)(mt % p.tiles_y);
-        x = 16 * (q % QR) + (lane & 15);
-        y = ty * (8 / QR) + 2 * (q / QR) + (lane >> 4);
+      if (p.box16) {
+        const int per_img = p.tiles_x * p.tiles_y;
+        n = mt / per_img;
+        const int r = (int)(mt - n * per_img);
+        x = (r % p.tiles_x) * 16 + (lane & 15);
+        y = (r / p.tiles_x) * 8 + 2 * q + (lane >> 4);
         valid = n < p.n_images;
       } else {
         const long long pix = mt * TC_BM + q * 32 + lane;    // 128 consecutive NHW pixels
@@ -221,9 +226,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           px[c] = (norm_px(p.img, p.img_layout, n, y, x, c, p.H, p.W) + norm_px(p.img, p.img_layout, n, y, x + 1, c, p.H, p.W) +
                    norm_px(p.img, p.img_layout, n, y + 1, x, c, p.H, p.W) + norm_px(p.img, p.img_layout, n, y + 1, x + 1, c, p.H, p.W)) * 0.25f;
       }
+      const long long obase = opix * p.Cout + nt * BN;
+      if (p.res_f32 && active) {
+        // pull this thread's residual row (BN fp32 = BN*4 bytes) towards L2 while the MMAs of the tile still run
+#pragma unroll
+        for (int b = 0; b < BN * 4; b += 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.res_f32 + obase) + b));
+      }
       mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
       tc_fence_after();
-      const long long obase = opix * p.Cout + nt * BN;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -382,16 +393,17 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   p.kchunks = Cin / TC_BK;
   p.sc_chunks = a.sc_C / TC_BK;
   p.pool = a.pool ? 1 : 0;
-  p.quarter = (a.pool && W >= 32) ? 1 : 0;
-  SDG_REQUIRE(!p.quarter || W <= 64, SDG_E_UNSUPPORTED, "conv_tc: pooled conv with W=%d", W);
+  p.box16 = (a.pool && W >= 32) ? 1 : 0;
+  p.tiles_x = 1;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
   p.n_tiles = Cout / BN;
   int bw = W, bh, bn;
-  if (p.quarter) {
-    bw = 16; bh = 2; bn = 1;
-    p.bh = 8 / (W / 16); p.bn = 1;
-    p.tiles_y = H / p.bh;
-    p.m_tiles = a.n * p.tiles_y;
+  if (p.box16) {
+    bw = 16; bh = 8; bn = 1;
+    p.bh = 8; p.bn = 1;
+    p.tiles_x = W / 16;
+    p.tiles_y = H / 8;
+    p.m_tiles = a.n * p.tiles_x * p.tiles_y;
   } else {
     int rows = TC_BM / W;                       // image rows per tile if one image is big enough
     if (rows >= H) { p.bh = H; p.bn = TC_BM / (H * W); } else { p.bh = rows; p.bn = 1; }
