@@ -25,11 +25,15 @@ struct FcParams {
 
 template <int BN, bool F16>
 __global__ void __launch_bounds__(FC_THREADS, 1)
-first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const FcParams p) {
+first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const FcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t b_addr = smem_base + 2 * FC_A_BYTES;
+  // output staging: 2 buffers x (BN/64) boxes of 128 rows x 128 B, 128B-swizzled, drained by TMA stores
+  constexpr int OUT_BOX = 128 * 128;
+  constexpr int OUT_BYTES = (BN / 64) * OUT_BOX;
+  const uint32_t out_off = 2 * FC_A_BYTES + BN * 128;
 
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_slot;
@@ -60,6 +64,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const FcParams p) {
       mbar_init(smem_u32(&b_full), 1);
       fence_barrier_init();
       tma_prefetch_desc(&map_b);
+      tma_prefetch_desc(&map_out);
     }
     __syncwarp();
     tmem_alloc(smem_u32(&tmem_base_slot), 2 * BN);
@@ -174,20 +179,25 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const FcParams p) {
       prefetch_raw(tile + 2 * (long long)gridDim.x, (int)((local + 2) % 3));
     }
   } else {
-    // ================= epilogue: TMEM -> bias + ReLU -> 16-bit NHWC =================
+    // ================= epilogue: TMEM -> bias + ReLU -> 16-bit -> swizzled smem -> TMA store =================
     const int q = warp;
+    const int row = q * 32 + lane;
     long long local = 0;
     for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++local) {
       const int buf = (int)(local & 1);
       const uint32_t ph = (uint32_t)((local >> 1) & 1);
       mbar_wait(smem_u32(&acc_full[buf]), ph);
       tc_fence_after();
-      h16* orow = p.out + (tile * 128 + q * 32 + lane) * (long long)BN;
+      // the store that read this staging buffer two tiles ago must have finished reading it
+      if (threadIdx.x == 0) bulk_wait_read_1();
+      named_bar_sync(2, 128);
+      uint8_t* stage = smem_gen + out_off + buf * OUT_BYTES;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
         tmem_ld_wait();
+        uint8_t* srow = stage + (c0 >> 6) * OUT_BOX + row * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 pk;
@@ -198,13 +208,23 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const FcParams p) {
             float b = fmaxf(__uint_as_float(r[g * 8 + 2 * j + 1]) + s_bias[c0 + g * 8 + 2 * j + 1], 0.f);
             h[j] = pack_h2<F16>(a, b);
           }
-          *reinterpret_cast<uint4*>(orow + c0 + g * 8) = pk;
+          const int chunk = ((c0 & 63) >> 3) + g;                 // 16-byte chunk within the 128-byte row
+          *reinterpret_cast<uint4*>(srow + ((chunk ^ (row & 7)) << 4)) = pk;
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));       // TMEM stage drained
+      fence_proxy_async_smem();                                    // staging writes -> visible to the TMA engine
+      named_bar_sync(2, 128);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int bx = 0; bx < BN / 64; ++bx)
+          tma_store_2d(&map_out, smem_base + out_off + buf * OUT_BYTES + bx * OUT_BOX, bx * 64, (int)(tile * 128));
+        bulk_commit();
+      }
     }
+    if (threadIdx.x == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -216,7 +236,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const FcParams p) {
 }
 
 template <int BN>
-constexpr int fc_smem_bytes() { return 2 * FC_A_BYTES + BN * 128 + 1024; }
+constexpr int fc_smem_bytes() { return 2 * FC_A_BYTES + BN * 128 + 2 * (BN / 64) * 128 * 128 + 1024; }
 
 int first_conv_init() {
   SDG_CUDA(cudaFuncSetAttribute(first_conv_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<128>()));
@@ -233,8 +253,9 @@ int first_conv(const void* x, int layout, const h16* wb, const float* bias, h16*
   SDG_REQUIRE(bias, SDG_E_INVALID, "first_conv: bias required");
   SDG_REQUIRE(((uintptr_t)x % 4) == 0 && ((uintptr_t)out % 16) == 0, SDG_E_INVALID, "first_conv: misaligned pointer");
   if (n == 0) return 0;
-  CUtensorMap map_b;
+  CUtensorMap map_b, map_out;
   { int rc = tc_encode_2d(&map_b, wb, f16, 64, Cout, 64, Cout); if (rc) return rc; }
+  { int rc = tc_encode_2d(&map_out, out, f16, Cout, (uint64_t)n * S * S, 64, 128); if (rc) return rc; }
   FcParams p;
   p.x = x; p.layout = layout; p.S = S; p.Cout = Cout; p.n_images = n;
   p.tiles = n * (S * S / 128);
@@ -242,13 +263,13 @@ int first_conv(const void* x, int layout, const h16* wb, const float* bias, h16*
   const int sms = tc_num_sms();
   const int grid = (int)(p.tiles < sms ? p.tiles : sms);
   if (Cout == 128 && f16) {
-    SDG_LAUNCH((first_conv_kernel<128, true>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, p);
+    SDG_LAUNCH((first_conv_kernel<128, true>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, map_out, p);
   } else if (Cout == 128) {
-    SDG_LAUNCH((first_conv_kernel<128, false>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, p);
+    SDG_LAUNCH((first_conv_kernel<128, false>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, map_out, p);
   } else if (f16) {
-    SDG_LAUNCH((first_conv_kernel<64, true>), grid, FC_THREADS, fc_smem_bytes<64>(), s, map_b, p);
+    SDG_LAUNCH((first_conv_kernel<64, true>), grid, FC_THREADS, fc_smem_bytes<64>(), s, map_b, map_out, p);
   } else {
-    SDG_LAUNCH((first_conv_kernel<64, false>), grid, FC_THREADS, fc_smem_bytes<64>(), s, map_b, p);
+    SDG_LAUNCH((first_conv_kernel<64, false>), grid, FC_THREADS, fc_smem_bytes<64>(), s, map_b, map_out, p);
   }
   return 0;
 }

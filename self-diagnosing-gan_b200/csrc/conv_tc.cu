@@ -137,19 +137,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           y0 = (int)(mt % p.tiles_y) * p.bh;
           x0 = 0;
         }
+        // k iterations: (tap, 64-channel chunk) of the main operand, then the folded shortcut's chunks
+        int tap = 0, kc = 0;
         for (int it = 0; it < k_iters; ++it) {
           const bool is_sc = it >= main_iters;
-          const int tap = is_sc ? 0 : it / p.kchunks;
-          const int kc = is_sc ? it - main_iters : it - tap * p.kchunks;
-          const int dy = (!is_sc && p.taps == 9) ? tap / 3 - 1 : 0;
-          const int dx = (!is_sc && p.taps == 9) ? tap % 3 - 1 : 0;
+          int dy = 0, dx = 0, ch = kc;
+          if (is_sc) {
+            ch = it - main_iters;
+          } else if (p.taps == 9) {
+            const int ty3 = (tap * 11) >> 5;            // tap / 3 for tap in 0..8
+            dy = ty3 - 1;
+            dx = tap - 3 * ty3 - 1;
+          }
           const CUtensorMap* am = is_sc ? &map_s : &map_a;
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&bar_full[stage]);
           mbar_expect_tx(full, STAGE_BYTES);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-          tma_load_4d(a_dst, am, full, kc * TC_BK, x0 + dx, y0 + dy, n0);
+          tma_load_4d(a_dst, am, full, ch * TC_BK, x0 + dx, y0 + dy, n0);
           tma_load_2d(a_dst + TC_A_BYTES, &map_b, full, it * TC_BK, nt * BN);
+          if (++kc == p.kchunks) { kc = 0; ++tap; }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
         }
       }

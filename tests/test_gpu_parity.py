@@ -411,8 +411,9 @@ def test_first_conv_from_bytes_vs_torch(S, cout, n, layout, prec, dev):
     wb[:, :27] = w.permute(0, 2, 3, 1).reshape(cout, 27)
     out = torch.full((n, S, S, cout), float("nan"), dtype=tdt, device=dev)
     xd = img.to(dev) if layout == "u8" else xn.to(dev)
-    check(lib.sdg_first_conv_h16(ptr(xd), _lib.LAYOUT_U8_NHWC if layout == "u8" else _lib.LAYOUT_F32_NCHW, ptr(wb.to(dev)),
-                                 ptr(b.to(dev)), ptr(out), n, S, cout, _lib.PREC_FP16 if prec == "fp16" else _lib.PREC_BF16,
+    wbd, bd = wb.to(dev), b.to(dev)          # keep the device copies alive until the kernel has run
+    check(lib.sdg_first_conv_h16(ptr(xd), _lib.LAYOUT_U8_NHWC if layout == "u8" else _lib.LAYOUT_F32_NCHW, ptr(wbd),
+                                 ptr(bd), ptr(out), n, S, cout, _lib.PREC_FP16 if prec == "fp16" else _lib.PREC_BF16,
                                  stream_ptr(dev)), "sdg_first_conv_h16")
     torch.cuda.synchronize()
     got = out.float().cpu().permute(0, 3, 1, 2)
