@@ -37,7 +37,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
 
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_bias[BN];
+  __shared__ __align__(16) float s_bias[BN];
   __shared__ __align__(16) float s_rawf[3][768];      // raw patch: (R+2) x S x 3 bytes (u8) or floats (fp32)
   __shared__ uint16_t s_lut[256];
 
@@ -202,10 +202,13 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
         for (int g = 0; g < 4; ++g) {
           uint4 pk;
           uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float a = fmaxf(__uint_as_float(r[g * 8 + 2 * j]) + s_bias[c0 + g * 8 + 2 * j], 0.f);
-            float b = fmaxf(__uint_as_float(r[g * 8 + 2 * j + 1]) + s_bias[c0 + g * 8 + 2 * j + 1], 0.f);
+            float a = fmaxf(__uint_as_float(r[g * 8 + 2 * j]) + bb[2 * j], 0.f);
+            float b = fmaxf(__uint_as_float(r[g * 8 + 2 * j + 1]) + bb[2 * j + 1], 0.f);
             h[j] = pack_h2<F16>(a, b);
           }
           const int chunk = ((c0 & 63) >> 3) + g;                 // 16-byte chunk within the 128-byte row

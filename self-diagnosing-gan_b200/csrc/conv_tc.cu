@@ -81,8 +81,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __shared__ __align__(8) uint64_t bar_acc_full[2];
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_bias[TC_MAX_COUT];
-  __shared__ float s_w3[TC_MAX_COUT * 3];
+  __shared__ __align__(16) float s_bias[TC_MAX_COUT];
+  __shared__ __align__(16) float s_w3[TC_MAX_COUT * 3];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -260,14 +260,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (active) {
           const int cb = nt * BN + c0;
+          // shared memory bandwidth is what bounds the MMA mainloop (operand fetch + TMA fill), so the epilogue
+          // reads its constants with as few wavefronts as possible: 128-bit broadcast loads
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += s_bias[cb + j];
+          for (int g = 0; g < 8; ++g) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cb + 4 * g);
+            v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+          }
           if (p.img) {
+            float w3[96];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float* w3 = s_w3 + (cb + j) * 3;
-              v[j] = fmaf(w3[0], px[0], fmaf(w3[1], px[1], fmaf(w3[2], px[2], v[j])));
+            for (int g = 0; g < 24; ++g) {
+              const float4 t = *reinterpret_cast<const float4*>(s_w3 + cb * 3 + 4 * g);
+              w3[4 * g] = t.x; w3[4 * g + 1] = t.y; w3[4 * g + 2] = t.z; w3[4 * g + 3] = t.w;
             }
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = fmaf(w3[3 * j], px[0], fmaf(w3[3 * j + 1], px[1], fmaf(w3[3 * j + 2], px[2], v[j])));
           }
           if (p.res_f32) {
             const float4* rp = reinterpret_cast<const float4*>(p.res_f32 + obase + c0);
