@@ -114,6 +114,9 @@ SDG_API int sdg_conv2d_h16(const void* in, const void* wb, const float* bias, in
                    int ks, const void* sc_in, int sc_C, int pool, const float* res_f32, int res_relu,
                    const void* img, int img_layout, const float* sc_w3, void* out_relu, void* out_raw,
                    float* out_f32, int precision, void* stream);
+/* Kernel selection for Cout = 128 3x3 stages: on != 0 (default) uses the CTA-pair kernel (tcgen05.mma.cta_group::2,
+ * weights resident in shared memory), 0 forces the single-CTA kernel.  Process-wide; for tests and A/B timing. */
+SDG_API int sdg_set_conv_pair(int on);
 /* First conv of the SNGAN discriminators straight from the dataset bytes: out = relu(conv3x3(normalise(x)) + b).
  * Replaces transform.py:3-11 + DBlockOptimized.c1 + ReLU.  x: uint8 [n,S,S,3] or fp32 [n,3,S,S] (layout);
  * wb 16-bit [Cout][64] with K index (ky*3+kx)*3 + c (27 real columns, rest zero); S in {32,64}; Cout in {64,128}. */

@@ -66,6 +66,148 @@ __device__ __forceinline__ float norm_px(const void* img, int layout, long long 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// tile geometry: origin (image, row, column) of M tile `mt`
+__device__ __forceinline__ void tc_tile_origin(const TcParams& p, long long mt, int& n0, int& y0, int& x0) {
+  if (p.box16) {
+    const int per_img = p.tiles_x * p.tiles_y;
+    n0 = (int)(mt / per_img);
+    const int r = (int)(mt - (long long)n0 * per_img);
+    y0 = (r / p.tiles_x) * 8;
+    x0 = (r % p.tiles_x) * 16;
+  } else {
+    n0 = (int)(mt / p.tiles_y) * p.bn;
+    y0 = (int)(mt % p.tiles_y) * p.bh;
+    x0 = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// epilogue of one 128-pixel x BN tile for one warp (TMEM lane quadrant q): waits for the accumulator, then
+// pooling / bias / shortcuts / stores.  tmem_acc = TMEM address of column 0 of this accumulator stage.
+template <int BN, bool F16>
+__device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float* s_bias, const float* s_w3,
+                                                 uint32_t tmem_acc, long long mt, int nt, int q, int lane,
+                                                 uint32_t acc_full_bar, uint32_t acc_phase) {
+  const int wc = p.W < 16 ? p.W : 16;             // columns per warp-row (pooling partner stride)
+  const int HW = p.H * p.W;
+  const int Ho = p.pool ? p.H >> 1 : p.H, Wo = p.pool ? p.W >> 1 : p.W;
+  {
+    // this thread's pixel (n, y, x)
+    long long n;
+    int y, x;
+    bool valid;
+    if (p.box16) {
+      const int per_img = p.tiles_x * p.tiles_y;
+      n = mt / per_img;
+      const int r = (int)(mt - n * per_img);
+      x = (r % p.tiles_x) * 16 + (lane & 15);
+      y = (r / p.tiles_x) * 8 + 2 * q + (lane >> 4);
+      valid = n < p.n_images;
+    } else {
+      const long long pix = mt * TC_BM + q * 32 + lane;    // 128 consecutive NHW pixels
+      n = pix / HW;
+      const int r = (int)(pix - n * HW);
+      y = r / p.W;
+      x = r - y * p.W;
+      valid = pix < p.total_pixels;
+    }
+    bool active = valid;
+    if (p.pool) active = valid && ((x & 1) == 0) && ((y & 1) == 0);
+    const long long opix = (n * Ho + (p.pool ? (y >> 1) : y)) * Wo + (p.pool ? (x >> 1) : x);
+    float px[3] = {0.f, 0.f, 0.f};
+    if (p.img && active) {
+      // avg_pool2d of the normalised network input at this pooled pixel (DBlockOptimized shortcut input)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        px[c] = (norm_px(p.img, p.img_layout, n, y, x, c, p.H, p.W) + norm_px(p.img, p.img_layout, n, y, x + 1, c, p.H, p.W) +
+                 norm_px(p.img, p.img_layout, n, y + 1, x, c, p.H, p.W) + norm_px(p.img, p.img_layout, n, y + 1, x + 1, c, p.H, p.W)) * 0.25f;
+    }
+    const long long obase = opix * p.Cout + nt * BN;
+    if (p.res_f32 && active) {
+      // pull this thread's residual row (BN fp32 = BN*4 bytes) towards L2 while the MMAs of the tile still run
+#pragma unroll
+      for (int b = 0; b < BN * 4; b += 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.res_f32 + obase) + b));
+    }
+    mbar_wait(acc_full_bar, acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.pool) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] += __shfl_down_sync(0xffffffffu, v[j], 1);
+          v[j] += __shfl_down_sync(0xffffffffu, v[j], wc);
+          v[j] *= 0.25f;
+        }
+      }
+      if (active) {
+        const int cb = nt * BN + c0;
+        // shared memory bandwidth is what bounds the MMA mainloop (operand fetch + TMA fill), so the epilogue
+        // reads its constants with as few wavefronts as possible: 128-bit broadcast loads
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cb + 4 * g);
+          v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+        }
+        if (p.img) {
+          float w3[96];
+#pragma unroll
+          for (int g = 0; g < 24; ++g) {
+            const float4 t = *reinterpret_cast<const float4*>(s_w3 + cb * 3 + 4 * g);
+            w3[4 * g] = t.x; w3[4 * g + 1] = t.y; w3[4 * g + 2] = t.z; w3[4 * g + 3] = t.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = fmaf(w3[3 * j], px[0], fmaf(w3[3 * j + 1], px[1], fmaf(w3[3 * j + 2], px[2], v[j])));
+        }
+        if (p.res_f32) {
+          const float4* rp = reinterpret_cast<const float4*>(p.res_f32 + obase + c0);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 t = rp[g];
+            if (p.res_relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+            v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+          }
+        }
+        if (p.out_f32) {
+          float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) op[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
+        if (p.out_raw) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk;
+            uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = pack_h2<F16>(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+            *reinterpret_cast<uint4*>(p.out_raw + obase + c0 + g * 8) = pk;
+          }
+        }
+        if (p.out_relu) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk;
+            uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              h[j] = pack_h2<F16>(fmaxf(v[g * 8 + 2 * j], 0.f), fmaxf(v[g * 8 + 2 * j + 1], 0.f));
+            *reinterpret_cast<uint4*>(p.out_relu + obase + c0 + g * 8) = pk;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 template <int BN, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -126,17 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int nt = (int)(tile % p.n_tiles);
         const long long mt = tile / p.n_tiles;
         int n0, y0, x0;
-        if (p.box16) {
-          const int per_img = p.tiles_x * p.tiles_y;
-          n0 = (int)(mt / per_img);
-          const int r = (int)(mt - (long long)n0 * per_img);
-          y0 = (r / p.tiles_x) * 8;
-          x0 = (r % p.tiles_x) * 16;
-        } else {
-          n0 = (int)(mt / p.tiles_y) * p.bn;
-          y0 = (int)(mt % p.tiles_y) * p.bh;
-          x0 = 0;
-        }
+        tc_tile_origin(p, mt, n0, y0, x0);
         // k iterations: (tap, 64-channel chunk) of the main operand, then the folded shortcut's chunks
         int tap = 0, kc = 0;
         for (int it = 0; it < k_iters; ++it) {
@@ -194,127 +326,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp >= 4) {
     // ================= epilogue =================
     const int q = warp - 4;                       // TMEM lane quadrant this warp may access
-    const int wc = p.W < 16 ? p.W : 16;             // columns per warp-row (pooling partner stride)
-    const int HW = p.H * p.W;
-    const int Ho = p.pool ? p.H >> 1 : p.H, Wo = p.pool ? p.W >> 1 : p.W;
     long long local = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int nt = (int)(tile % p.n_tiles);
       const long long mt = tile / p.n_tiles;
       const int acc = (int)(local & 1);
       const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
-      // this thread's pixel (n, y, x)
-      long long n;
-      int y, x;
-      bool valid;
-      if (p.box16) {
-        const int per_img = p.tiles_x * p.tiles_y;
-        n = mt / per_img;
-        const int r = (int)(mt - n * per_img);
-        x = (r % p.tiles_x) * 16 + (lane & 15);
-        y = (r / p.tiles_x) * 8 + 2 * q + (lane >> 4);
-        valid = n < p.n_images;
-      } else {
-        const long long pix = mt * TC_BM + q * 32 + lane;    // 128 consecutive NHW pixels
-        n = pix / HW;
-        const int r = (int)(pix - n * HW);
-        y = r / p.W;
-        x = r - y * p.W;
-        valid = pix < p.total_pixels;
-      }
-      bool active = valid;
-      if (p.pool) active = valid && ((x & 1) == 0) && ((y & 1) == 0);
-      const long long opix = (n * Ho + (p.pool ? (y >> 1) : y)) * Wo + (p.pool ? (x >> 1) : x);
-      float px[3] = {0.f, 0.f, 0.f};
-      if (p.img && active) {
-        // avg_pool2d of the normalised network input at this pooled pixel (DBlockOptimized shortcut input)
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          px[c] = (norm_px(p.img, p.img_layout, n, y, x, c, p.H, p.W) + norm_px(p.img, p.img_layout, n, y, x + 1, c, p.H, p.W) +
-                   norm_px(p.img, p.img_layout, n, y + 1, x, c, p.H, p.W) + norm_px(p.img, p.img_layout, n, y + 1, x + 1, c, p.H, p.W)) * 0.25f;
-      }
-      const long long obase = opix * p.Cout + nt * BN;
-      if (p.res_f32 && active) {
-        // pull this thread's residual row (BN fp32 = BN*4 bytes) towards L2 while the MMAs of the tile still run
-#pragma unroll
-        for (int b = 0; b < BN * 4; b += 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.res_f32 + obase) + b));
-      }
-      mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.pool) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] += __shfl_down_sync(0xffffffffu, v[j], 1);
-            v[j] += __shfl_down_sync(0xffffffffu, v[j], wc);
-            v[j] *= 0.25f;
-          }
-        }
-        if (active) {
-          const int cb = nt * BN + c0;
-          // shared memory bandwidth is what bounds the MMA mainloop (operand fetch + TMA fill), so the epilogue
-          // reads its constants with as few wavefronts as possible: 128-bit broadcast loads
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cb + 4 * g);
-            v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
-          }
-          if (p.img) {
-            float w3[96];
-#pragma unroll
-            for (int g = 0; g < 24; ++g) {
-              const float4 t = *reinterpret_cast<const float4*>(s_w3 + cb * 3 + 4 * g);
-              w3[4 * g] = t.x; w3[4 * g + 1] = t.y; w3[4 * g + 2] = t.z; w3[4 * g + 3] = t.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = fmaf(w3[3 * j], px[0], fmaf(w3[3 * j + 1], px[1], fmaf(w3[3 * j + 2], px[2], v[j])));
-          }
-          if (p.res_f32) {
-            const float4* rp = reinterpret_cast<const float4*>(p.res_f32 + obase + c0);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float4 t = rp[g];
-              if (p.res_relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-              v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
-            }
-          }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) op[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-          }
-          if (p.out_raw) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 pk;
-              uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) h[j] = pack_h2<F16>(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-              *reinterpret_cast<uint4*>(p.out_raw + obase + c0 + g * 8) = pk;
-            }
-          }
-          if (p.out_relu) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 pk;
-              uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                h[j] = pack_h2<F16>(fmaxf(v[g * 8 + 2 * j], 0.f), fmaxf(v[g * 8 + 2 * j + 1], 0.f));
-              *reinterpret_cast<uint4*>(p.out_relu + obase + c0 + g * 8) = pk;
-            }
-          }
-        }
-      }
+      tc_epilogue_tile<BN, F16>(p, s_bias, s_w3, tmem_base + (uint32_t)(acc * BN), mt, nt, q, lane,
+                                smem_u32(&bar_acc_full[acc]), acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
@@ -326,6 +345,166 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CTA-pair variant for Cout = 128 layers (all 3x3 convs of SNGAN-32): two CTAs of a cluster run ONE
+// tcgen05.mma.cta_group::2 of M = 256 (128 pixels each) x N = 128, each CTA supplying 64 rows of B.
+// Why: the 1-CTA kernel above is bounded by shared-memory bandwidth -- per 64-cycle MMA it reads 4 KB of A and
+// 4 KB of B from smem while TMA writes the same amount -- which caps it near 50 % of the tensor peak.  In the pair
+// every CTA reads 4 KB + 2 KB per MMA, and its half of the weights (<= 20 k-chunks x 8 KB) stays RESIDENT in shared
+// memory for the whole kernel, so the only streaming traffic is the A tile: 160 B/clk -> 96 B/clk of smem traffic
+// at full tensor rate.
+// Synchronisation: "full" and "accumulator-empty" barriers live in the leader CTA (rank 0) and are signalled by both
+// CTAs (TMA complete_tx through .cta_group::2 loads, remote mbarrier arrives); "stage-empty" and "accumulator-full"
+// are signalled in both CTAs at once by the leader's multicast tcgen05.commit.
+constexpr int PAIR_MAX_KI = 20;
+constexpr int PAIR_B_TILE = 64 * TC_BK * 2;        // 8 KB: 64 weight rows x 64 k
+
+template <bool F16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_s, const TcParams p, const int n_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  __shared__ __align__(8) uint64_t bar_full[8];
+  __shared__ __align__(8) uint64_t bar_empty[8];
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ __align__(8) uint64_t bar_b;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[128];
+  __shared__ __align__(16) float s_w3[128 * 3];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int main_iters = p.taps * p.kchunks;
+  const int k_iters = main_iters + p.sc_chunks;
+  const uint32_t a_base = smem_base + (uint32_t)k_iters * PAIR_B_TILE;      // A stages follow the resident weights
+
+  for (int i = threadIdx.x; i < 128; i += TC_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  if (p.img)
+    for (int i = threadIdx.x; i < 128 * 3; i += TC_THREADS) s_w3[i] = p.sc_w3[i];
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (p.sc_chunks) tma_prefetch_desc(&map_s);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_acc_full[s]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[s]), 8);       // 4 epilogue warps x 2 CTAs
+    }
+    mbar_init(smem_u32(&bar_b), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_slot), TC_TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();                                   // barriers of both CTAs initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const long long cluster_id = blockIdx.x >> 1;
+  const long long n_clusters = gridDim.x >> 1;
+  const long long pair_tiles = (p.m_tiles + 1) >> 1;    // M = 256 tiles; CTA `rank` owns m tile 2*ct + rank
+
+  if (warp == 0) {
+    // ================= TMA producer: this CTA's 128-pixel A tile per k iteration =================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long ct = cluster_id; ct < pair_tiles; ct += n_clusters) {
+        const long long mt = 2 * ct + rank;
+        int n0, y0, x0;
+        tc_tile_origin(p, mt, n0, y0, x0);
+        int tap = 0, kc = 0;
+        for (int it = 0; it < k_iters; ++it) {
+          const bool is_sc = it >= main_iters;
+          int dy = 0, dx = 0, ch = kc;
+          if (is_sc) {
+            ch = it - main_iters;
+          } else if (p.taps == 9) {
+            const int ty3 = (tap * 11) >> 5;
+            dy = ty3 - 1;
+            dx = tap - 3 * ty3 - 1;
+          }
+          const CUtensorMap* am = is_sc ? &map_s : &map_a;
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[stage]), 0);
+          if (leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * TC_A_BYTES);     // both CTAs' A tiles
+          tma_load_4d_pair(a_base + stage * TC_A_BYTES, am, full_leader, ch * TC_BK, x0 + dx, y0 + dy, n0);
+          if (++kc == p.kchunks) { kc = 0; ++tap; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc(256, 128, F16);
+      mbar_wait(smem_u32(&bar_b), 0);                  // both halves of the weights are resident
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      long long local = 0;
+      for (long long ct = cluster_id; ct < pair_tiles; ct += n_clusters, ++local) {
+        const int acc = (int)(local & 1);
+        const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
+        mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_desc(a_base + stage * TC_A_BYTES);
+          const uint64_t bdesc = make_sw128_desc(smem_base + (uint32_t)it * PAIR_B_TILE);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit_pair(smem_u32(&bar_empty[stage]), 3);      // frees the stage in both CTAs
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(smem_u32(&bar_acc_full[acc]), 3);       // accumulator complete -> both epilogues
+      }
+    }
+  } else if (warp == 2) {
+    // ================= resident weights: this CTA's 64 output channels of every k chunk, loaded once =================
+    if (elect_one()) {
+      const uint32_t b_leader = mapa_u32(smem_u32(&bar_b), 0);
+      if (leader) mbar_expect_tx(smem_u32(&bar_b), 2u * (uint32_t)k_iters * PAIR_B_TILE);
+      for (int it = 0; it < k_iters; ++it)
+        tma_load_2d_pair(smem_base + (uint32_t)it * PAIR_B_TILE, &map_b, b_leader, it * TC_BK, (int)rank * 64);
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: this CTA's 128 TMEM lanes =================
+    const int q = warp - 4;
+    long long local = 0;
+    for (long long ct = cluster_id; ct < pair_tiles; ct += n_clusters, ++local) {
+      const long long mt = 2 * ct + rank;
+      const int acc = (int)(local & 1);
+      const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
+      tc_epilogue_tile<128, F16>(p, s_bias, s_w3, tmem_base + (uint32_t)(acc * 128), mt, 0, q, lane,
+                                 smem_u32(&bar_acc_full[acc]), acc_phase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_acc_empty[acc]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                   // every MMA retired, every epilogue done, in both CTAs
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TC_TMEM_COLS);
   }
 }
 
@@ -342,6 +521,10 @@ template <int BN>
 constexpr int tc_smem_bytes() { return TC_STAGES * (TC_A_BYTES + BN * TC_BK * 2) + 1024; }
 
 int tc_num_sms() { return g_num_sms; }
+
+constexpr int kPairSmemMax = 227 * 1024 - 3072;       // dynamic shared memory budget of the pair kernel (static: ~2.5 KB)
+static int g_pair_mode = 1;                          // 0 = never use the CTA-pair kernel, 1 = use it where it applies
+void conv_tc_set_pair(int on) { g_pair_mode = on; }
 
 int tc_encode_2d(CUtensorMap* map, const void* ptr, int f16, uint64_t inner, uint64_t outer, uint32_t box_inner,
                  uint32_t box_outer) {
@@ -384,6 +567,8 @@ int conv_tc_init(int device) {
   SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>()));
   SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>()));
   SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>()));
+  SDG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemMax));
+  SDG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemMax));
   g_encode = (EncodeTiledFn)fn;
   int rc = first_conv_init();
   if (rc) { g_encode = nullptr; return rc; }
@@ -439,6 +624,32 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   else map_s = map_a;
   { int rc = tc_encode_2d(&map_b, a.wb, f16, (uint64_t)taps * Cin + a.sc_C, Cout, TC_BK, BN); if (rc) return rc; }
 
+  const int k_iters = taps * p.kchunks + p.sc_chunks;
+  if (g_pair_mode && Cout == 128 && taps == 9 && k_iters <= PAIR_MAX_KI && p.m_tiles >= 2) {
+    // CTA-pair kernel: weights resident (64 rows per CTA), A streamed through as many 16 KB stages as fit
+    CUtensorMap map_bh;
+    { int rc = tc_encode_2d(&map_bh, a.wb, f16, (uint64_t)taps * Cin + a.sc_C, Cout, TC_BK, 64); if (rc) return rc; }
+    int n_stages = (kPairSmemMax - 1024 - k_iters * PAIR_B_TILE) / TC_A_BYTES;
+    if (n_stages > 8) n_stages = 8;
+    SDG_REQUIRE(n_stages >= 3, SDG_E_UNSUPPORTED, "conv_tc: pair kernel needs >= 3 stages, K chunks = %d", k_iters);
+    const size_t smem = 1024 + (size_t)k_iters * PAIR_B_TILE + (size_t)n_stages * TC_A_BYTES;
+    const long long pair_tiles = (p.m_tiles + 1) / 2;
+    long long clusters = g_num_sms / 2;
+    if (pair_tiles < clusters) clusters = pair_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (f16) { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<true>, map_a, map_bh, map_s, p, n_stages)); }
+    else { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<false>, map_a, map_bh, map_s, p, n_stages)); }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
   const long long total_tiles = p.m_tiles * p.n_tiles;
   const int grid = (int)(total_tiles < g_num_sms ? total_tiles : g_num_sms);
   if (BN == 128 && f16) {

@@ -537,6 +537,11 @@ extern "C" int sdg_first_conv_h16(const void* x, int layout, const void* wb, con
   return first_conv(x, layout, (const h16*)wb, bias, (h16*)out, n, S, Cout, precision == SDG_PREC_FP16, (cudaStream_t)stream);
 }
 
+extern "C" int sdg_set_conv_pair(int on) {
+  conv_tc_set_pair(on ? 1 : 0);
+  return 0;
+}
+
 extern "C" int sdg_ctx_profile(sdg_ctx* c, int enable) {
   SDG_REQUIRE(c, SDG_E_INVALID, "sdg_ctx_profile: null ctx");
   c->profile = enable != 0;

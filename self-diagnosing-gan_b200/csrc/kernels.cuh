@@ -100,6 +100,7 @@ struct TcConv {
 };
 int conv_tc_init(int device);
 int conv_tc(const TcConv& args, int f16, cudaStream_t s);
+void conv_tc_set_pair(int on);   // 1 (default): Cout = 128 3x3 layers run on the CTA-pair (cta_group::2) kernel
 // out = relu(conv3x3(normalise(x)) + bias): x uint8 NHWC or fp32 NCHW [n,3,S,S]; wb [Cout][64] (k = tap*3+c, 27 real)
 int first_conv_init();
 int first_conv(const void* x, int layout, const h16* wb, const float* bias, h16* out, int64_t n, int S, int Cout,

@@ -293,7 +293,7 @@ def _tdt(prec):
     return torch.float16 if prec == "fp16" else torch.bfloat16
 
 
-def _conv_fused(dev, n, hw, cin, cout, ks, prec, seed, sc_c=0, pool=0, res=False, res_relu=0, img=False):
+def _conv_fused(dev, n, hw, cin, cout, ks, prec, seed, sc_c=0, pool=0, res=False, res_relu=0, img=False, pair=1):
     """Run one fused conv stage through the C ABI and return {name: (max abs err, scale)} per output against
     torch fp32 on the same 16-bit-rounded operands."""
     import torch.nn.functional as F
@@ -335,10 +335,14 @@ def _conv_fused(dev, n, hw, cin, cout, ks, prec, seed, sc_c=0, pool=0, res=False
     resd = nhwc(res_t) if res else None
     imgd = img_t.to(dev) if img else None
     w3d = w3.contiguous().to(dev) if img else None
-    check(lib.sdg_conv2d_h16(ptr(xd), ptr(wb), ptr(bd), n, hw, hw, cin, cout, ks, ptr(scd), sc_c, pool, ptr(resd), res_relu,
-                             ptr(imgd), _lib.LAYOUT_U8_NHWC, ptr(w3d), ptr(o_relu), ptr(o_raw), ptr(o_f32),
-                             _lib.PREC_FP16 if prec == "fp16" else _lib.PREC_BF16, stream_ptr(dev)), "sdg_conv2d_h16")
-    torch.cuda.synchronize()
+    lib.sdg_set_conv_pair(pair)
+    try:
+        check(lib.sdg_conv2d_h16(ptr(xd), ptr(wb), ptr(bd), n, hw, hw, cin, cout, ks, ptr(scd), sc_c, pool, ptr(resd),
+                                 res_relu, ptr(imgd), _lib.LAYOUT_U8_NHWC, ptr(w3d), ptr(o_relu), ptr(o_raw), ptr(o_f32),
+                                 _lib.PREC_FP16 if prec == "fp16" else _lib.PREC_BF16, stream_ptr(dev)), "sdg_conv2d_h16")
+        torch.cuda.synchronize()
+    finally:
+        lib.sdg_set_conv_pair(1)
     back = lambda t: t.float().cpu().permute(0, 3, 1, 2)
     scale = v.abs().max().item()
     return {"f32": ((back(o_f32) - v).abs().max().item(), scale),
@@ -362,13 +366,16 @@ def _check_conv(errs, prec, tag):
     (2, 64, 64, 64, 3),        # SNGAN-64 block1.c2 (N tile 64, two rows per tile)
     (9, 4, 512, 1024, 3),      # SNGAN-64 block5.c2: 8 images per tile, 8 N tiles, 8 K chunks
     (300, 32, 128, 128, 3),    # more tiles than SMs: persistent loop + TMEM double buffering
+    (37, 8, 128, 128, 3),      # odd number of M tiles (19): the pair kernel's last M=256 tile is half empty
 ])
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
-def test_conv2d_h16_tcgen05_vs_torch(n, hw, cin, cout, ks, prec, dev):
-    """The tcgen05 implicit-GEMM kernel alone (no fusion) against F.conv2d on the same 16-bit-rounded operands
-    (fp32 accumulate both sides; 16-bit outputs within one output ulp of the scale, fp32 output within 2e-5)."""
-    errs = _conv_fused(dev, n, hw, cin, cout, ks, prec, seed=n * 1000 + hw)
-    _check_conv(errs, prec, f"conv {prec} n={n} hw={hw} {cin}->{cout} k{ks}")
+@pytest.mark.parametrize("pair", [0, 1])
+def test_conv2d_h16_tcgen05_vs_torch(n, hw, cin, cout, ks, prec, pair, dev):
+    """The tcgen05 implicit-GEMM kernels alone (no fusion) against F.conv2d on the same 16-bit-rounded operands
+    (fp32 accumulate both sides; 16-bit outputs within one output ulp of the scale, fp32 output within 2e-5).
+    pair=1: Cout = 128 3x3 cases run on the CTA-pair (cta_group::2, resident weights) kernel; 0: single-CTA kernel."""
+    errs = _conv_fused(dev, n, hw, cin, cout, ks, prec, seed=n * 1000 + hw, pair=pair)
+    _check_conv(errs, prec, f"conv {prec} pair={pair} n={n} hw={hw} {cin}->{cout} k{ks}")
 
 
 @pytest.mark.parametrize("tag,n,hw,cin,cout,kw", [
@@ -384,11 +391,12 @@ def test_conv2d_h16_tcgen05_vs_torch(n, hw, cin, cout, ks, prec, dev):
     ("many tiles, pooled", 200, 32, 128, 128, dict(pool=1, img=True)),
 ])
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
-def test_conv2d_fused_block_stage_vs_torch(tag, n, hw, cin, cout, kw, prec, dev):
+@pytest.mark.parametrize("pair", [0, 1])
+def test_conv2d_fused_block_stage_vs_torch(tag, n, hw, cin, cout, kw, prec, pair, dev):
     """Fused epilogues: pooling by warp shuffles, shortcut conv as extra K columns, image shortcut FMAs, identity
-    residual from the fp32 stream, the three output forms."""
-    errs = _conv_fused(dev, n, hw, cin, cout, 3, prec, seed=hw * 7 + n, **kw)
-    _check_conv(errs, prec, f"{prec} {tag}")
+    residual from the fp32 stream, the three output forms -- on both kernel variants."""
+    errs = _conv_fused(dev, n, hw, cin, cout, 3, prec, seed=hw * 7 + n, pair=pair, **kw)
+    _check_conv(errs, prec, f"{prec} pair={pair} {tag}")
 
 
 @pytest.mark.parametrize("S,cout,n", [(32, 128, 5), (64, 64, 3), (32, 128, 333)])
