@@ -22,6 +22,8 @@
 //     three stores: ReLU'd 16-bit (operand of the next conv), raw 16-bit, raw fp32 (residual stream / head).
 // Persistent CTAs (one per SM), static tile schedule, warp-specialised: warp 0 TMA producer, warp 1 MMA
 // issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
+#include <cstdlib>
+
 #include "tc_ptx.cuh"
 
 namespace sdg {
@@ -45,6 +47,7 @@ struct TcParams {
   int pool;                  // 2x2 average pooling in the epilogue
   int res_relu;              // ReLU the identity residual before adding (mimicry's in-place aliasing)
   int img_layout;            // layout of `img` for the 3-FMA shortcut
+  int debug_skip_a;          // SDG_DEBUG_SKIP_A=1: pair kernel issues no A loads (timing experiment only, wrong results)
   long long n_images;
   long long m_tiles;
   long long total_pixels;
@@ -440,8 +443,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const CUtensorMap* am = is_sc ? &map_s : &map_a;
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[stage]), 0);
-          if (leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * TC_A_BYTES);     // both CTAs' A tiles
-          tma_load_4d_pair(a_base + stage * TC_A_BYTES, am, full_leader, ch * TC_BK, x0 + dx, y0 + dy, n0);
+          if (p.debug_skip_a) {
+            if (leader) mbar_arrive(smem_u32(&bar_full[stage]));
+          } else {
+            if (leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * TC_A_BYTES);     // both CTAs' A tiles
+            tma_load_4d_pair(a_base + stage * TC_A_BYTES, am, full_leader, ch * TC_BK, x0 + dx, y0 + dy, n0);
+          }
           if (++kc == p.kchunks) { kc = 0; ++tap; }
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
@@ -613,6 +620,9 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
     p.m_tiles = cdiv(a.n, p.bn) * p.tiles_y;
   }
   p.res_relu = a.res_relu; p.img_layout = a.img_layout;
+  static const int dbg_skip_a = getenv("SDG_DEBUG_SKIP_A") ? atoi(getenv("SDG_DEBUG_SKIP_A")) : 0;
+  static const int dbg_stages = getenv("SDG_PAIR_STAGES") ? atoi(getenv("SDG_PAIR_STAGES")) : 0;
+  p.debug_skip_a = dbg_skip_a;
   p.n_images = a.n;
   p.total_pixels = a.n * H * W;
   p.bias = a.bias; p.res_f32 = a.res_f32; p.img = a.img; p.sc_w3 = a.sc_w3;
@@ -631,6 +641,7 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
     { int rc = tc_encode_2d(&map_bh, a.wb, f16, (uint64_t)taps * Cin + a.sc_C, Cout, TC_BK, 64); if (rc) return rc; }
     int n_stages = (kPairSmemMax - 1024 - k_iters * PAIR_B_TILE) / TC_A_BYTES;
     if (n_stages > 8) n_stages = 8;
+    if (dbg_stages > 0 && dbg_stages < n_stages) n_stages = dbg_stages;
     SDG_REQUIRE(n_stages >= 3, SDG_E_UNSUPPORTED, "conv_tc: pair kernel needs >= 3 stages, K chunks = %d", k_iters);
     const size_t smem = 1024 + (size_t)k_iters * PAIR_B_TILE + (size_t)n_stages * TC_A_BYTES;
     const long long pair_tiles = (p.m_tiles + 1) / 2;
