@@ -48,6 +48,7 @@ struct TcParams {
   int res_relu;              // ReLU the identity residual before adding (mimicry's in-place aliasing)
   int img_layout;            // layout of `img` for the 3-FMA shortcut
   int debug_skip_a;          // SDG_DEBUG_SKIP_A=1: pair kernel issues no A loads (timing experiment only, wrong results)
+  int debug_skip_epi;        // SDG_DEBUG_SKIP_EPI=1: epilogues only drain the barrier protocol (timing experiment only)
   long long n_images;
   long long m_tiles;
   long long total_pixels;
@@ -91,6 +92,11 @@ template <int BN, bool F16>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float* s_bias, const float* s_w3,
                                                  uint32_t tmem_acc, long long mt, int nt, int q, int lane,
                                                  uint32_t acc_full_bar, uint32_t acc_phase) {
+  if (p.debug_skip_epi) {
+    mbar_wait(acc_full_bar, acc_phase);
+    tc_fence_after();
+    return;
+  }
   const int wc = p.W < 16 ? p.W : 16;             // columns per warp-row (pooling partner stride)
   const int HW = p.H * p.W;
   const int Ho = p.pool ? p.H >> 1 : p.H, Wo = p.pool ? p.W >> 1 : p.W;
@@ -622,7 +628,9 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   p.res_relu = a.res_relu; p.img_layout = a.img_layout;
   static const int dbg_skip_a = getenv("SDG_DEBUG_SKIP_A") ? atoi(getenv("SDG_DEBUG_SKIP_A")) : 0;
   static const int dbg_stages = getenv("SDG_PAIR_STAGES") ? atoi(getenv("SDG_PAIR_STAGES")) : 0;
+  static const int dbg_skip_epi = getenv("SDG_DEBUG_SKIP_EPI") ? atoi(getenv("SDG_DEBUG_SKIP_EPI")) : 0;
   p.debug_skip_a = dbg_skip_a;
+  p.debug_skip_epi = dbg_skip_epi;
   p.n_images = a.n;
   p.total_pixels = a.n * H * W;
   p.bias = a.bias; p.res_f32 = a.res_f32; p.img = a.img; p.sc_w3 = a.sc_w3;

@@ -1,0 +1,54 @@
+"""Kernel-level timing of one fused conv stage through the C ABI (CUDA events on the launching stream).
+    python tools/conv_microbench.py [--n 4096] [--hw 32] [--cin 128] [--cout 128] [--pool 0] [--pair 1] [--iters 20]
+Debug environment switches of libsdg (SDG_DEBUG_SKIP_A, SDG_DEBUG_SKIP_EPI, SDG_PAIR_STAGES) apply."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "self-diagnosing-gan_b200"))
+import torch  # noqa: E402
+
+from diagan_b200 import _lib  # noqa: E402
+from diagan_b200._lib import check, ptr, stream_ptr  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--hw", type=int, default=32)
+    ap.add_argument("--cin", type=int, default=128)
+    ap.add_argument("--cout", type=int, default=128)
+    ap.add_argument("--pool", type=int, default=0)
+    ap.add_argument("--pair", type=int, default=1)
+    ap.add_argument("--iters", type=int, default=20)
+    a = ap.parse_args()
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    x = torch.randn(a.n, a.hw, a.hw, a.cin, device=dev).half()
+    w = (torch.randn(a.cout, 9 * a.cin, device=dev) / (9 * a.cin) ** 0.5).half()
+    b = torch.zeros(a.cout, device=dev)
+    ho = a.hw // 2 if a.pool else a.hw
+    out = torch.empty(a.n, ho, ho, a.cout, device=dev, dtype=torch.float16)
+    lib.sdg_set_conv_pair(a.pair)
+
+    def run():
+        check(lib.sdg_conv2d_h16(ptr(x), ptr(w), ptr(b), a.n, a.hw, a.hw, a.cin, a.cout, 3, None, 0, a.pool, None, 0, None, 0,
+                                 None, ptr(out), None, None, _lib.PREC_FP16, stream_ptr(dev)), "conv")
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.iters
+    flops = 2.0 * a.n * a.hw * a.hw * a.cout * 9 * a.cin
+    env = {k: v for k, v in os.environ.items() if k.startswith("SDG_")}
+    print(f"n={a.n} hw={a.hw} {a.cin}->{a.cout} pool={a.pool} pair={a.pair} {env}: {ms * 1e3:.1f} us  {flops / ms / 1e9:.1f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    main()
