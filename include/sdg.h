@@ -102,7 +102,10 @@ SDG_API int sdg_d_forward(sdg_ctx* ctx, const void* x, int layout, int64_t n, fl
  * Replaces, from torch-mimicry DBlock / DBlockOptimized (resblocks.py):
  *   v = F.conv2d(in, W/sigma, b, stride 1, padding ks/2)
  *       [+ F.conv2d(sc_in, Wsc/sigma)      the block's 1x1 shortcut conv: sc_C extra K columns of wb]
- *   [v = F.avg_pool2d(v, 2)                 pool != 0]
+ *   [v = F.avg_pool2d(v, 2)                 pool != 0; pool == 2 evaluates conv + pool as the algebraically equal
+ *                                           4x4 stride-2 conv (16/36 of the MACs): wb is then [Cout, 16*Cin + 4*sc_C] with
+ *                                           wb[o][(a*4+b)*Cin + c] = 0.25 * sum_{ky in {a-1,a}, kx in {b-1,b}} W[o][c][ky][kx]
+ *                                           and the shortcut block 0.25 * Wsc[o][c] repeated for its 4 taps]
  *   [v += sc_w3 . avg_pool2d(normalise(img), 2)   DBlockOptimized shortcut, img = the network input]
  *   [v += res_f32 (rectified if res_relu)   identity shortcut]
  *   out_relu = relu(v) 16-bit, out_raw = v 16-bit, out_f32 = v fp32        (each optional, >= 1 required)

@@ -39,7 +39,11 @@ constexpr int TC_MAX_COUT = 1024;
 struct TcParams {
   int H, W, Cin, Cout, taps;
   int kchunks;               // Cin / 64
-  int sc_chunks;             // extra shortcut K chunks read through map_s (0 = none)
+  int sc_chunks;             // extra shortcut K iterations read through map_s (0 = none) = sc_taps * sc_kchunks
+  int sc_kchunks;            // shortcut channels / 64
+  int tw;                    // taps per kernel row (3: 3x3, 4: pooled-3x3-as-4x4, 1: 1x1)
+  int cs;                    // input coordinate scale: 2 for the 4x4 stride-2 form, else 1
+  int img_up;                // epilogue pixels are at pooled resolution of `img` (stride-2 form)
   int box16;                 // tile geometry: 0 linear, 1 = 8 rows x 16 columns (W >= 32 with pooling)
   int bh, tiles_y, bn;       // linear: tile = bn images x bh rows x W columns; box16: tiles_y x tiles_x tiles per image
   int tiles_x;
@@ -67,6 +71,29 @@ __device__ __forceinline__ float norm_px(const void* img, int layout, long long 
     return __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
   }
   return reinterpret_cast<const float*>(img)[((n * 3 + c) * H + y) * (long long)W + x];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k iteration -> which tensor map, which 64-channel chunk, which tap offset (in input pixels)
+//   main iterations: (tap, chunk) of the conv operand; 3x3: offsets -1..1; pooled-3x3-as-4x4-stride-2: -1..2
+//   then the folded 1x1 shortcut conv: offset 0 (same resolution) or the four taps of a 2x2 stride-2 average
+__device__ __forceinline__ void tc_k_iter(const TcParams& p, int it, int main_iters, int tap, int kc, bool& is_sc, int& ch,
+                                          int& dy, int& dx) {
+  is_sc = it >= main_iters;
+  dy = 0; dx = 0; ch = kc;
+  if (is_sc) {
+    const int j = it - main_iters;
+    const int st = j / p.sc_kchunks;
+    ch = j - st * p.sc_kchunks;
+    if (p.cs == 2) { dy = st >> 1; dx = st & 1; }
+  } else if (p.tw == 3) {
+    const int ty3 = (tap * 11) >> 5;            // tap / 3 for tap in 0..8
+    dy = ty3 - 1;
+    dx = tap - 3 * ty3 - 1;
+  } else if (p.tw == 4) {
+    dy = (tap >> 2) - 1;
+    dx = (tap & 3) - 1;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -126,10 +153,12 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
     float px[3] = {0.f, 0.f, 0.f};
     if (p.img && active) {
       // avg_pool2d of the normalised network input at this pooled pixel (DBlockOptimized shortcut input)
+      const int iy = p.img_up ? 2 * y : y, ix = p.img_up ? 2 * x : x;
+      const int iH = p.img_up ? 2 * p.H : p.H, iW = p.img_up ? 2 * p.W : p.W;
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        px[c] = (norm_px(p.img, p.img_layout, n, y, x, c, p.H, p.W) + norm_px(p.img, p.img_layout, n, y, x + 1, c, p.H, p.W) +
-                 norm_px(p.img, p.img_layout, n, y + 1, x, c, p.H, p.W) + norm_px(p.img, p.img_layout, n, y + 1, x + 1, c, p.H, p.W)) * 0.25f;
+        px[c] = (norm_px(p.img, p.img_layout, n, iy, ix, c, iH, iW) + norm_px(p.img, p.img_layout, n, iy, ix + 1, c, iH, iW) +
+                 norm_px(p.img, p.img_layout, n, iy + 1, ix, c, iH, iW) + norm_px(p.img, p.img_layout, n, iy + 1, ix + 1, c, iH, iW)) * 0.25f;
     }
     const long long obase = opix * p.Cout + nt * BN;
     if (p.res_f32 && active) {
@@ -278,24 +307,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const long long mt = tile / p.n_tiles;
         int n0, y0, x0;
         tc_tile_origin(p, mt, n0, y0, x0);
-        // k iterations: (tap, 64-channel chunk) of the main operand, then the folded shortcut's chunks
         int tap = 0, kc = 0;
         for (int it = 0; it < k_iters; ++it) {
-          const bool is_sc = it >= main_iters;
-          int dy = 0, dx = 0, ch = kc;
-          if (is_sc) {
-            ch = it - main_iters;
-          } else if (p.taps == 9) {
-            const int ty3 = (tap * 11) >> 5;            // tap / 3 for tap in 0..8
-            dy = ty3 - 1;
-            dx = tap - 3 * ty3 - 1;
-          }
+          bool is_sc;
+          int dy, dx, ch;
+          tc_k_iter(p, it, main_iters, tap, kc, is_sc, ch, dy, dx);
           const CUtensorMap* am = is_sc ? &map_s : &map_a;
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&bar_full[stage]);
           mbar_expect_tx(full, STAGE_BYTES);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-          tma_load_4d(a_dst, am, full, ch * TC_BK, x0 + dx, y0 + dy, n0);
+          tma_load_4d(a_dst, am, full, ch * TC_BK, p.cs * x0 + dx, p.cs * y0 + dy, n0);
           tma_load_2d(a_dst + TC_A_BYTES, &map_b, full, it * TC_BK, nt * BN);
           if (++kc == p.kchunks) { kc = 0; ++tap; }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
@@ -437,15 +459,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tc_tile_origin(p, mt, n0, y0, x0);
         int tap = 0, kc = 0;
         for (int it = 0; it < k_iters; ++it) {
-          const bool is_sc = it >= main_iters;
-          int dy = 0, dx = 0, ch = kc;
-          if (is_sc) {
-            ch = it - main_iters;
-          } else if (p.taps == 9) {
-            const int ty3 = (tap * 11) >> 5;
-            dy = ty3 - 1;
-            dx = tap - 3 * ty3 - 1;
-          }
+          bool is_sc;
+          int dy, dx, ch;
+          tc_k_iter(p, it, main_iters, tap, kc, is_sc, ch, dy, dx);
           const CUtensorMap* am = is_sc ? &map_s : &map_a;
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[stage]), 0);
@@ -553,11 +569,14 @@ int tc_encode_2d(CUtensorMap* map, const void* ptr, int f16, uint64_t inner, uin
   return 0;
 }
 
-static int encode_act(CUtensorMap* map, const void* ptr, int f16, int64_t n, int H, int W, int C, int bw, int bh, int bn) {
+// 4-D map over NHWC activations; box = 64 channels x bw x bh x bn pixels; es = traversal stride over pixels (2 for the
+// stride-2 form: the box then spans es*bw x es*bh input pixels and every es-th one is loaded)
+static int encode_act(CUtensorMap* map, const void* ptr, int f16, int64_t n, int H, int W, int C, int bw, int bh, int bn,
+                      int es) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   CUresult r = g_encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -591,7 +610,9 @@ int conv_tc_init(int device) {
 int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   SDG_REQUIRE(g_encode, SDG_E_STATE, "conv_tc: conv_tc_init not called");
   const int H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout, taps = a.taps;
+  const bool s2 = a.pool4 != 0;          // conv3x3 + avg_pool2d(2) evaluated as the equivalent 4x4 stride-2 conv
   SDG_REQUIRE(taps == 9 || taps == 1, SDG_E_UNSUPPORTED, "conv_tc: taps=%d", taps);
+  SDG_REQUIRE(!s2 || (taps == 9 && a.pool), SDG_E_INVALID, "conv_tc: pool4 needs a pooled 3x3 stage");
   SDG_REQUIRE(Cin % TC_BK == 0 && Cout % 64 == 0 && Cout <= TC_MAX_COUT, SDG_E_UNSUPPORTED, "conv_tc: Cin=%d Cout=%d", Cin, Cout);
   SDG_REQUIRE(W >= 4 && W <= 128 && (W & (W - 1)) == 0 && H == W, SDG_E_UNSUPPORTED, "conv_tc: H=%d W=%d", H, W);
   SDG_REQUIRE(a.sc_C % TC_BK == 0, SDG_E_UNSUPPORTED, "conv_tc: shortcut channels %d", a.sc_C);
@@ -602,27 +623,34 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   SDG_REQUIRE(al16(a.in) && al16(a.wb) && al16(a.sc_in) && al16(a.res_f32) && al16(a.out_relu) && al16(a.out_raw) &&
                   al16(a.out_f32), SDG_E_INVALID, "conv_tc: pointers must be 16-byte aligned");
   if (a.n == 0) return 0;
+  // resolution of the GEMM's M space: the pooled output grid in the stride-2 form, else the conv's own grid
+  const int Hc = s2 ? H / 2 : H, Wc = s2 ? W / 2 : W;
   TcParams p;
-  p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps;
+  p.H = Hc; p.W = Wc; p.Cin = Cin; p.Cout = Cout;
+  p.taps = s2 ? 16 : taps;
+  p.tw = s2 ? 4 : (taps == 9 ? 3 : 1);
+  p.cs = s2 ? 2 : 1;
+  p.img_up = s2 ? 1 : 0;
   p.kchunks = Cin / TC_BK;
-  p.sc_chunks = a.sc_C / TC_BK;
-  p.pool = a.pool ? 1 : 0;
-  p.box16 = (a.pool && W >= 32) ? 1 : 0;
+  p.sc_kchunks = a.sc_C / TC_BK;
+  p.sc_chunks = (s2 ? 4 : 1) * p.sc_kchunks;
+  p.pool = (a.pool && !s2) ? 1 : 0;
+  p.box16 = (p.pool && W >= 32) ? 1 : 0;
   p.tiles_x = 1;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
   p.n_tiles = Cout / BN;
-  int bw = W, bh, bn;
+  int bw = Wc, bh, bn;
   if (p.box16) {
     bw = 16; bh = 8; bn = 1;
     p.bh = 8; p.bn = 1;
-    p.tiles_x = W / 16;
-    p.tiles_y = H / 8;
+    p.tiles_x = Wc / 16;
+    p.tiles_y = Hc / 8;
     p.m_tiles = a.n * p.tiles_x * p.tiles_y;
   } else {
-    int rows = TC_BM / W;                       // image rows per tile if one image is big enough
-    if (rows >= H) { p.bh = H; p.bn = TC_BM / (H * W); } else { p.bh = rows; p.bn = 1; }
+    int rows = TC_BM / Wc;                      // grid rows per tile if one image is big enough
+    if (rows >= Hc) { p.bh = Hc; p.bn = TC_BM / (Hc * Wc); } else { p.bh = rows; p.bn = 1; }
     bh = p.bh; bn = p.bn;
-    p.tiles_y = H / p.bh;
+    p.tiles_y = Hc / p.bh;
     p.m_tiles = cdiv(a.n, p.bn) * p.tiles_y;
   }
   p.res_relu = a.res_relu; p.img_layout = a.img_layout;
@@ -632,21 +660,23 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   p.debug_skip_a = dbg_skip_a;
   p.debug_skip_epi = dbg_skip_epi;
   p.n_images = a.n;
-  p.total_pixels = a.n * H * W;
+  p.total_pixels = a.n * Hc * Wc;
   p.bias = a.bias; p.res_f32 = a.res_f32; p.img = a.img; p.sc_w3 = a.sc_w3;
   p.out_relu = a.out_relu; p.out_raw = a.out_raw; p.out_f32 = a.out_f32;
+  const int es = s2 ? 2 : 1;                    // TMA traversal stride over input pixels
 
   CUtensorMap map_a, map_b, map_s;
-  { int rc = encode_act(&map_a, a.in, f16, a.n, H, W, Cin, bw, bh, bn); if (rc) return rc; }
-  if (a.sc_in) { int rc = encode_act(&map_s, a.sc_in, f16, a.n, H, W, a.sc_C, bw, bh, bn); if (rc) return rc; }
+  const uint64_t k_cols = (uint64_t)p.taps * Cin + (uint64_t)p.sc_chunks * TC_BK;
+  { int rc = encode_act(&map_a, a.in, f16, a.n, H, W, Cin, bw, bh, bn, es); if (rc) return rc; }
+  if (a.sc_in) { int rc = encode_act(&map_s, a.sc_in, f16, a.n, H, W, a.sc_C, bw, bh, bn, es); if (rc) return rc; }
   else map_s = map_a;
-  { int rc = tc_encode_2d(&map_b, a.wb, f16, (uint64_t)taps * Cin + a.sc_C, Cout, TC_BK, BN); if (rc) return rc; }
+  { int rc = tc_encode_2d(&map_b, a.wb, f16, k_cols, Cout, TC_BK, BN); if (rc) return rc; }
 
-  const int k_iters = taps * p.kchunks + p.sc_chunks;
+  const int k_iters = p.taps * p.kchunks + p.sc_chunks;
   if (g_pair_mode && Cout == 128 && taps == 9 && k_iters <= PAIR_MAX_KI && p.m_tiles >= 2) {
     // CTA-pair kernel: weights resident (64 rows per CTA), A streamed through as many 16 KB stages as fit
     CUtensorMap map_bh;
-    { int rc = tc_encode_2d(&map_bh, a.wb, f16, (uint64_t)taps * Cin + a.sc_C, Cout, TC_BK, 64); if (rc) return rc; }
+    { int rc = tc_encode_2d(&map_bh, a.wb, f16, k_cols, Cout, TC_BK, 64); if (rc) return rc; }
     int n_stages = (kPairSmemMax - 1024 - k_iters * PAIR_B_TILE) / TC_A_BYTES;
     if (n_stages > 8) n_stages = 8;
     if (dbg_stages > 0 && dbg_stages < n_stages) n_stages = dbg_stages;

@@ -8,6 +8,7 @@
 // launch over all samples of the chunk.
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.cuh"
@@ -49,6 +50,7 @@ struct ConvLayer {
   DevBuf w32, w16, bias;
   DevBuf w3, bias_sum;       // 16-bit path: fp32 [Cout][3] shortcut weights (DBlockOptimized), conv + shortcut bias
   int ktot = 0;              // 16-bit path: K columns of w16 (conv taps + folded shortcut columns)
+  int pool4 = 0;             // 16-bit path: packed for the 4x4 stride-2 form of conv3x3 + avg_pool2d
   bool has_bias = false;
 };
 
@@ -251,15 +253,27 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
       { int rc = pack_conv_h16(W[i1], sig + i1, nullptr, l1.w16.as<h16>(), l1.cout, l1.cin, l1.kpad, l1.ks, f16, l1.ktot, 0, s);
         if (rc) return rc; }
       const bool fold = has_sc && c->blocks[bi].kind == 1;
-      const int sc_cols = fold ? c->convs[isc].kpad : 0;
-      l2.ktot = l2.kpad + sc_cols;
+      // pooled blocks: conv3x3 + avg_pool2d(2) == a 4x4 stride-2 conv with summed weights (16/36 of the MACs)
+      static const int use_pool4 = getenv("SDG_POOL4") ? atoi(getenv("SDG_POOL4")) : 1;
+      l2.pool4 = (use_pool4 && c->blocks[bi].down) ? 1 : 0;
+      const int sc_cols = fold ? (l2.pool4 ? 4 : 1) * c->convs[isc].kpad : 0;
+      const int main_cols = l2.pool4 ? 16 * l2.cin : l2.kpad;
+      l2.ktot = main_cols + sc_cols;
       { int rc = l2.w16.ensure(sizeof(h16) * (size_t)l2.ktot * l2.cout); if (rc) return rc; }
-      { int rc = pack_conv_h16(W[i2], sig + i2, nullptr, l2.w16.as<h16>(), l2.cout, l2.cin, l2.kpad, l2.ks, f16, l2.ktot, 0, s);
-        if (rc) return rc; }
+      if (l2.pool4) {
+        int rc = pack_pool4_h16(W[i2], sig + i2, l2.w16.as<h16>(), l2.cout, l2.cin, f16, l2.ktot, s);
+        if (rc) return rc;
+      } else {
+        int rc = pack_conv_h16(W[i2], sig + i2, nullptr, l2.w16.as<h16>(), l2.cout, l2.cin, l2.kpad, l2.ks, f16, l2.ktot, 0, s);
+        if (rc) return rc;
+      }
       { int rc = l2.bias_sum.ensure(sizeof(float) * l2.cout); if (rc) return rc; }
       if (has_sc) {
         ConvLayer& lsc = c->convs[isc];
-        if (fold) {
+        if (fold && l2.pool4) {
+          int rc = pack_pool4_sc_h16(W[isc], sig + isc, l2.w16.as<h16>(), lsc.cout, lsc.cin, lsc.kpad, f16, l2.ktot, main_cols, s);
+          if (rc) return rc;
+        } else if (fold) {
           int rc = pack_conv_h16(W[isc], sig + isc, nullptr, l2.w16.as<h16>(), lsc.cout, lsc.cin, lsc.kpad, 1, f16, l2.ktot,
                                  l2.kpad, s);
           if (rc) return rc;
@@ -403,6 +417,7 @@ static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, 
     a2.n = nb; a2.H = hw; a2.W = hw; a2.Cin = c2.cin; a2.Cout = c2.cout; a2.taps = 9;
     a2.in = T; a2.wb = c2.w16.as<h16>(); a2.bias = c2.bias_sum.as<float>();
     a2.pool = bl.down;
+    a2.pool4 = c2.pool4;
     a2.out_relu = last ? nullptr : hR[o];
     a2.out_raw = (next_sc && !c->inplace_relu) ? hW[o] : nullptr;
     a2.out_f32 = (last || !next_sc) ? hF[o] : nullptr;
@@ -518,7 +533,8 @@ extern "C" int sdg_conv2d_h16(const void* in, const void* wb, const float* bias,
   { int rc = conv_tc_init(dev); if (rc) return rc; }
   TcConv a;
   a.in = (const h16*)in; a.wb = (const h16*)wb; a.bias = bias; a.n = n; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
-  a.taps = ks * ks; a.sc_in = (const h16*)sc_in; a.sc_C = sc_C; a.pool = pool; a.res_f32 = res_f32; a.res_relu = res_relu;
+  a.taps = ks * ks; a.sc_in = (const h16*)sc_in; a.sc_C = sc_C; a.pool = pool != 0; a.pool4 = pool == 2;
+  a.res_f32 = res_f32; a.res_relu = res_relu;
   a.img = img; a.img_layout = img_layout; a.sc_w3 = sc_w3;
   a.out_relu = (h16*)out_relu; a.out_raw = (h16*)out_raw; a.out_f32 = out_f32;
   return conv_tc(a, precision == SDG_PREC_FP16, (cudaStream_t)stream);

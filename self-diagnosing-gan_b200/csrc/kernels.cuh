@@ -59,6 +59,11 @@ int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float
 // wb[o*ld + col0 + k] = h16(W[o][c][tap] * scale[o] / sigma) at k = tap*Cin + c, zero padded up to Kpad columns
 int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* wb, int Cout, int Cin, int Kpad,
                   int ks, int f16, int ld, int col0, cudaStream_t s);
+// pooled-3x3 weights for the 4x4 stride-2 form: wb[o*ld + (a*4+b)*Cin + c] = 0.25 * sum of W[o][c][ky][kx] / sigma over
+// ky in {a-1,a}, kx in {b-1,b} (valid taps); shortcut: wb[o*ld + col0 + t*sc_pad + c] = 0.25 * Wsc[o][c] / sigma_sc, t = 0..3
+int pack_pool4_h16(const float* W, const float* sigma, h16* wb, int Cout, int Cin, int f16, int ld, cudaStream_t s);
+int pack_pool4_sc_h16(const float* Wsc, const float* sigma, h16* wb, int Cout, int Csc, int sc_pad, int f16, int ld, int col0,
+                      cudaStream_t s);
 int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);          // out = a + b
 int scale_vec(const float* in, const float* sigma, float* out, int n, cudaStream_t s);   // out = in / sigma
 // BatchNorm(eval) folding: scale[o] = gamma/sqrt(var+eps), shift[o] = beta - mean*scale
@@ -89,6 +94,8 @@ struct TcConv {
   const h16* sc_in = nullptr;     // [n,H,W,sc_C]: input of the block's 1x1 shortcut conv (same resolution as `in`)
   int sc_C = 0;
   int pool = 0;                   // avg_pool2d(., 2) of conv (+ shortcut conv) before the adds below
+  int pool4 = 0;                  // with pool: run conv3x3 + avg_pool2d as the algebraically equal 4x4 stride-2 conv
+                                  // (16/36 of the MACs); wb then holds 16 taps x Cin (+ 4 taps x sc_C), see pack_pool4_h16
   const float* res_f32 = nullptr; // identity shortcut [n,Ho,Wo,Cout] fp32
   int res_relu = 0;               // rectify the identity shortcut (mimicry's in-place ReLU aliasing)
   const void* img = nullptr;      // network input (DBlockOptimized: shortcut = Wsc3 . avg_pool2d(img) at pooled res)

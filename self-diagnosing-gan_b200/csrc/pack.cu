@@ -141,6 +141,59 @@ int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* w
   return 0;
 }
 
+template <bool F16>
+__global__ void __launch_bounds__(256)
+pack_pool4_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigma, h16* __restrict__ wb, int Cout, int Cin,
+                      int ld) {
+  const int total = Cout * 16 * Cin;
+  const float sg = sigma[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % Cin;
+    const int r = i / Cin;
+    const int t = r & 15, o = r >> 4;
+    const int a = t >> 2, b = t & 3;
+    float acc = 0.f;
+    for (int ky = a - 1; ky <= a; ++ky) {
+      if (ky < 0 || ky > 2) continue;
+      for (int kx = b - 1; kx <= b; ++kx) {
+        if (kx < 0 || kx > 2) continue;
+        acc += W[((int64_t)o * Cin + c) * 9 + ky * 3 + kx] / sg;       // (W / sigma) as the reference forms it
+      }
+    }
+    wb[(int64_t)o * ld + t * Cin + c] = (h16)(pack_h2<F16>(0.25f * acc, 0.f) & 0xffffu);
+  }
+}
+
+int pack_pool4_h16(const float* W, const float* sigma, h16* wb, int Cout, int Cin, int f16, int ld, cudaStream_t s) {
+  int total = Cout * 16 * Cin;
+  if (f16) { SDG_LAUNCH(pack_pool4_h16_kernel<true>, stream_grid(total, 256), 256, 0, s, W, sigma, wb, Cout, Cin, ld); }
+  else { SDG_LAUNCH(pack_pool4_h16_kernel<false>, stream_grid(total, 256), 256, 0, s, W, sigma, wb, Cout, Cin, ld); }
+  return 0;
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(256)
+pack_pool4_sc_h16_kernel(const float* __restrict__ Wsc, const float* __restrict__ sigma, h16* __restrict__ wb, int Cout,
+                         int Csc, int sc_pad, int ld, int col0) {
+  const int total = Cout * 4 * sc_pad;
+  const float sg = sigma[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % sc_pad;
+    const int r = i / sc_pad;
+    const int t = r & 3, o = r >> 2;
+    const float w = c < Csc ? 0.25f * (Wsc[(int64_t)o * Csc + c] / sg) : 0.f;
+    wb[(int64_t)o * ld + col0 + t * sc_pad + c] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
+  }
+}
+
+int pack_pool4_sc_h16(const float* Wsc, const float* sigma, h16* wb, int Cout, int Csc, int sc_pad, int f16, int ld, int col0,
+                      cudaStream_t s) {
+  int total = Cout * 4 * sc_pad;
+  if (f16) { SDG_LAUNCH(pack_pool4_sc_h16_kernel<true>, stream_grid(total, 256), 256, 0, s, Wsc, sigma, wb, Cout, Csc, sc_pad, ld, col0); }
+  else { SDG_LAUNCH(pack_pool4_sc_h16_kernel<false>, stream_grid(total, 256), 256, 0, s, Wsc, sigma, wb, Cout, Csc, sc_pad, ld, col0); }
+  return 0;
+}
+
 __global__ void scale_vec_kernel(const float* __restrict__ in, const float* __restrict__ sigma, float* __restrict__ out,
                                  int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
