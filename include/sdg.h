@@ -182,8 +182,9 @@ SDG_API void sdg_launch_count_reset(void);
 
 /* Event timing of the dominant kernel of the bf16 SNGAN forward (block1.c2, the 3x3 128->128 conv at
  * full resolution) on the launching stream, for the roofline line of bench.py.  _read synchronises on
- * the recorded events, returns total milliseconds, number of launches and their algorithmic FLOPs
- * (2*M*N*K of the reference formulation) since the last read, and clears the record. */
+ * the recorded events, returns total milliseconds, number of launches and the FLOPs those launches EXECUTED
+ * (2*M*N*K of the GEMM actually run: with the 4x4 stride-2 form of conv3x3 + avg_pool2d that is 16/36 of the
+ * reference formulation's count) since the last read, and clears the record. */
 SDG_API int sdg_ctx_profile(sdg_ctx* ctx, int enable);
 SDG_API int sdg_ctx_profile_read(sdg_ctx* ctx, double* ms_total_host, int64_t* launches_host, double* flops_host);
 

@@ -469,7 +469,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (leader) mbar_arrive(smem_u32(&bar_full[stage]));
           } else {
             if (leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * TC_A_BYTES);     // both CTAs' A tiles
-            tma_load_4d_pair(a_base + stage * TC_A_BYTES, am, full_leader, ch * TC_BK, x0 + dx, y0 + dy, n0);
+            tma_load_4d_pair(a_base + stage * TC_A_BYTES, am, full_leader, ch * TC_BK, p.cs * x0 + dx, p.cs * y0 + dy, n0);
           }
           if (++kc == p.kchunks) { kc = 0; ++tap; }
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }

@@ -427,7 +427,9 @@ static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, 
       a2.img = x; a2.img_layout = layout; a2.sc_w3 = c->convs[i1 + 2].w3.as<float>();
       if ((rc = prof_begin(c, s))) return rc;
       if ((rc = conv_tc(a2, f16, s))) return rc;
-      if ((rc = prof_end(c, s, 2.0 * (double)nb * hw * hw * c2.cout * 9.0 * c2.cin))) return rc;
+      // executed FLOPs of this launch: the 4x4 stride-2 form does 16 taps per pooled pixel instead of 9 per input pixel
+      const double macs_per_out = c2.pool4 ? 16.0 * c2.cin * 0.25 : 9.0 * c2.cin;
+      if ((rc = prof_end(c, s, 2.0 * (double)nb * hw * hw * c2.cout * macs_per_out))) return rc;
     } else {
       TcConv a1;
       a1.n = nb; a1.H = hw; a1.W = hw; a1.Cin = c1.cin; a1.Cout = c1.cout; a1.taps = 9;
