@@ -14,6 +14,8 @@ namespace sdg {
 
 constexpr int FC_THREADS = 288;
 constexpr int FC_A_BYTES = 128 * 128;
+constexpr int FC_OUT_BUFS = 5;       // output staging tiles in flight: the kernel is HBM-write-bound, TMA stores drain
+                                     // shared memory only as fast as DRAM accepts them, so keep several tiles queued
 
 struct FcParams {
   const void* x;
@@ -30,7 +32,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t b_addr = smem_base + 2 * FC_A_BYTES;
-  // output staging: 2 buffers x (BN/64) boxes of 128 rows x 128 B, 128B-swizzled, drained by TMA stores
+  // output staging: FC_OUT_BUFS buffers x (BN/64) boxes of 128 rows x 128 B, 128B-swizzled, drained by TMA stores
   constexpr int OUT_BOX = 128 * 128;
   constexpr int OUT_BYTES = (BN / 64) * OUT_BOX;
   const uint32_t out_off = 2 * FC_A_BYTES + BN * 128;
@@ -188,10 +190,11 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
       const uint32_t ph = (uint32_t)((local >> 1) & 1);
       mbar_wait(smem_u32(&acc_full[buf]), ph);
       tc_fence_after();
-      // the store that read this staging buffer two tiles ago must have finished reading it
-      if (threadIdx.x == 0) bulk_wait_read_1();
+      // the store that read this staging buffer FC_OUT_BUFS tiles ago must have finished reading it
+      const int ob = (int)(local % FC_OUT_BUFS);
+      if (threadIdx.x == 0) bulk_wait_read<FC_OUT_BUFS - 1>();
       named_bar_sync(2, 128);
-      uint8_t* stage = smem_gen + out_off + buf * OUT_BYTES;
+      uint8_t* stage = smem_gen + out_off + ob * OUT_BYTES;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -223,7 +226,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
       if (threadIdx.x == 0) {
 #pragma unroll
         for (int bx = 0; bx < BN / 64; ++bx)
-          tma_store_2d(&map_out, smem_base + out_off + buf * OUT_BYTES + bx * OUT_BOX, bx * 64, (int)(tile * 128));
+          tma_store_2d(&map_out, smem_base + out_off + ob * OUT_BYTES + bx * OUT_BOX, bx * 64, (int)(tile * 128));
         bulk_commit();
       }
     }
@@ -239,7 +242,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
 }
 
 template <int BN>
-constexpr int fc_smem_bytes() { return 2 * FC_A_BYTES + BN * 128 + 2 * (BN / 64) * 128 * 128 + 1024; }
+constexpr int fc_smem_bytes() { return 2 * FC_A_BYTES + BN * 128 + FC_OUT_BUFS * (BN / 64) * 128 * 128 + 1024; }
 
 int first_conv_init() {
   SDG_CUDA(cudaFuncSetAttribute(first_conv_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<128>()));

@@ -22,9 +22,30 @@ def main():
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--pair", type=int, default=1)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--first", type=int, default=0, help="time the first conv (from uint8 bytes) instead")
     a = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda", 0)
+    if a.first:
+        img = torch.randint(0, 256, (a.n, a.hw, a.hw, 3), dtype=torch.uint8, device=dev)
+        wb = (torch.randn(a.cout, 64, device=dev) / 5).half()
+        bias = torch.zeros(a.cout, device=dev)
+        out = torch.empty(a.n, a.hw, a.hw, a.cout, device=dev, dtype=torch.float16)
+        run = lambda: check(lib.sdg_first_conv_h16(ptr(img), _lib.LAYOUT_U8_NHWC, ptr(wb), ptr(bias), ptr(out), a.n, a.hw,
+                                                   a.cout, _lib.PREC_FP16, stream_ptr(dev)), "first")
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.iters):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.iters
+        gb = out.numel() * 2 / 1e9
+        print(f"first conv n={a.n} S={a.hw} ->{a.cout}: {ms * 1e3:.1f} us  {gb / ms * 1e3:.0f} GB/s written")
+        return
     x = torch.randn(a.n, a.hw, a.hw, a.cin, device=dev).half()
     w = (torch.randn(a.cout, 9 * a.cin, device=dev) / (9 * a.cin) ** 0.5).half()
     b = torch.zeros(a.cout, device=dev)
