@@ -3,19 +3,23 @@
 // Replaces transform.py:3-11 (ToTensor + Normalize) + DBlockOptimized.c1 (SNConv2d 3->C, 3x3, pad 1) + ReLU
 // (torch-mimicry resblocks.py; SURVEY 8(a) "b1.c1"): out = relu(conv3x3(norm(x)) + b), written as the 16-bit
 // NHWC operand of the next conv.  K = 27 is too thin to stream through TMA, so builder warps assemble the
-// im2col tile (128 pixels x 32, 128B-swizzled K-major) in shared memory from a small raw patch of the
-// uint8 (or fp32 NCHW) image -- uint8 goes through a 256-entry lookup table of normalised 16-bit values
-// -- and one thread issues two tcgen05.mma (K = 2 x 16) per tile.  HBM-write-bound: 3 KB in, 256 KB out
-// per CIFAR-shaped sample.
-// Warp roles: warps 0-3 epilogue (TMEM lane quadrant = warp), warps 4-7 builders, warp 8 TMA / MMA / TMEM.
+// im2col tile (128 pixels x 32, 128B-swizzled K-major) in shared memory:
+//   1. the raw rows of the tile (+1 halo row each side) are prefetched two tiles ahead with cp.async;
+//   2. they are converted ONCE to normalised 16-bit values (uint8 through a 256-entry lookup table holding
+//      (v/255 - 0.5)/0.5 rounded to the operand type) into a patch with a zero border, so that
+//   3. each builder thread gathers its pixel's 3 x 9 contiguous values without any bounds test.
+// One thread issues two tcgen05.mma (K = 2 x 16) per tile; eight epilogue warps (two per TMEM lane quadrant, half
+// of the channels each) add bias + ReLU, stage the 128 x Cout tile in swizzled shared memory and drain it with TMA
+// stores, several tiles in flight.  HBM-write-bound by design: 3 KB in, 256 KB out per CIFAR-shaped sample.
+// Warp roles: 0-3 and 9-12 epilogue (TMEM lane quadrant = warp % 4), 4-7 builders, 8 weights TMA / MMA / TMEM.
 #include "tc_ptx.cuh"
 
 namespace sdg {
 
-constexpr int FC_THREADS = 288;
+constexpr int FC_THREADS = 13 * 32;
 constexpr int FC_A_BYTES = 128 * 128;
-constexpr int FC_OUT_BUFS = 5;       // output staging tiles in flight: the kernel is HBM-write-bound, TMA stores drain
-                                     // shared memory only as fast as DRAM accepts them, so keep several tiles queued
+constexpr int FC_OUT_BUFS = 4;       // output staging tiles in flight
+constexpr int FC_PATCH_MAX = 4 * 66 * 3;     // normalised patch, 16-bit elements: (R+2) x (S+2) x 3; S=32: 612, S=64: 792
 
 struct FcParams {
   const void* x;
@@ -40,7 +44,8 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[BN];
-  __shared__ __align__(16) float s_rawf[3][768];      // raw patch: (R+2) x S x 3 bytes (u8) or floats (fp32)
+  __shared__ __align__(16) float s_rawf[3][768];      // raw rows: (R+2) x S x 3 bytes (u8) or floats (fp32 NCHW)
+  __shared__ __align__(16) uint16_t s_patch[2][FC_PATCH_MAX];
   __shared__ uint16_t s_lut[256];
 
   const int warp = threadIdx.x >> 5;
@@ -61,7 +66,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
         mbar_init(smem_u32(&a_full[s]), 128);
         mbar_init(smem_u32(&a_empty[s]), 1);
         mbar_init(smem_u32(&acc_full[s]), 1);
-        mbar_init(smem_u32(&acc_empty[s]), 4);
+        mbar_init(smem_u32(&acc_empty[s]), 8);
       }
       mbar_init(smem_u32(&b_full), 1);
       fence_barrier_init();
@@ -99,13 +104,12 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
         umma_commit(smem_u32(&acc_full[buf]));
       }
     }
-  } else if (warp >= 4) {
-    // ================= builders: raw patch -> swizzled im2col tile =================
+  } else if (warp >= 4 && warp < 8) {
+    // ================= builders: raw rows -> normalised patch -> swizzled im2col tile =================
     const int bt = threadIdx.x - 128;           // 0..127 = pixel of the tile
     const int ly = bt / S, lx = bt - ly * S;
     const bool u8 = p.layout == SDG_LAYOUT_U8_NHWC;
-    // raw patch rows y0-1 .. y0+R of a tile, fetched two tiles ahead with cp.async (rows outside the image are
-    // skipped: the gather below never reads them)
+    const int prow = (S + 2) * 3;               // patch row pitch in 16-bit elements (zero column each side)
     auto prefetch_raw = [&](long long tile, int rb) {
       if (tile < p.tiles) {
         const long long n = tile / tiles_y;
@@ -143,33 +147,42 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
       const int y0 = (int)(tile % tiles_y) * R;
       const float* rawf = s_rawf[local % 3];
       const uint8_t* rawb = reinterpret_cast<const uint8_t*>(rawf);
-      cp_async_wait_1();          // everything but the newest group has landed -> this tile's patch is in smem
-      named_bar_sync(1, 128);
-      // ---- gather this pixel's 3x3x3 neighbourhood: k = (ky*3+kx)*3 + c ----
-      uint32_t packed[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) packed[j] = 0u;
-      uint16_t vals[28];
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int ky = tap / 3, kx = tap % 3;
-        const int iy = y0 + ly + ky - 1, ix = lx + kx - 1;
-        const bool ok = iy >= 0 && iy < S && ix >= 0 && ix < S;
-        const int pr = ly + ky;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
+      uint16_t* patch = s_patch[buf];
+      cp_async_wait_1();          // everything but the newest group has landed -> this tile's rows are in smem
+      named_bar_sync(1, 128);     // ... for every builder thread; also: everyone is done gathering from patch[buf]
+      // ---- 1. convert once: patch[pr][pc][c] = normalised value of image (y0-1+pr, pc-1, c), zero outside ----
+      for (int pr = 0; pr < R + 2; ++pr) {
+        const int iy = y0 - 1 + pr;
+        const bool row_ok = iy >= 0 && iy < S;
+        for (int e = bt; e < prow; e += 128) {
+          const int pc = (e * 171) >> 9;        // e / 3 for e < 512
+          const int c = e - 3 * pc;
+          const int ix = pc - 1;
           uint16_t h = 0;
-          if (ok) {
+          if (row_ok && ix >= 0 && ix < S) {
             if (u8) h = s_lut[rawb[(pr * S + ix) * 3 + c]];
             else h = (uint16_t)(pack_h2<F16>(rawf[(c * (R + 2) + pr) * S + ix], 0.f) & 0xffffu);
           }
-          vals[tap * 3 + c] = h;
+          patch[pr * prow + e] = h;
         }
       }
+      named_bar_sync(1, 128);
+      // the raw buffer of tile local-1 is free now (everyone passed the first barrier of this tile after converting it)
+      prefetch_raw(tile + 2 * (long long)gridDim.x, (int)((local + 2) % 3));
+      // ---- 2. gather this pixel's 3 x (3 pixels x 3 channels) contiguous values: k = (ky*3+kx)*3 + c ----
+      uint16_t vals[28];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const uint16_t* src = patch + (ly + ky) * prow + lx * 3;     // patch column lx = image column lx-1
+#pragma unroll
+        for (int j = 0; j < 9; ++j) vals[ky * 9 + j] = src[j];
+      }
       vals[27] = 0;
+      uint32_t packed[16];
 #pragma unroll
       for (int j = 0; j < 14; ++j) packed[j] = (uint32_t)vals[2 * j] | ((uint32_t)vals[2 * j + 1] << 16);
-      mbar_wait(smem_u32(&a_empty[buf]), ph ^ 1u);          // the MMAs that read this buffer have retired
+      packed[14] = 0u; packed[15] = 0u;
+      mbar_wait(smem_u32(&a_empty[buf]), ph ^ 1u);          // the MMAs that read this A buffer have retired
       uint8_t* row = smem_gen + buf * FC_A_BYTES + bt * 128;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch)
@@ -177,12 +190,13 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
             make_uint4(packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
       fence_proxy_async_smem();                             // generic-proxy writes -> visible to the tensor core
       mbar_arrive(smem_u32(&a_full[buf]));
-      // the buffer of tile local-1 is free: every builder passed this tile's barrier after gathering from it
-      prefetch_raw(tile + 2 * (long long)gridDim.x, (int)((local + 2) % 3));
     }
   } else {
     // ================= epilogue: TMEM -> bias + ReLU -> 16-bit -> swizzled smem -> TMA store =================
-    const int q = warp;
+    // two warps per TMEM lane quadrant; the second group (warps 9-12) takes the upper half of the channels
+    const int q = warp & 3;
+    const int half = warp >= 9 ? 1 : 0;
+    const int et = half * 128 + (warp < 4 ? threadIdx.x : threadIdx.x - 9 * 32);   // 0..255 among epilogue threads
     const int row = q * 32 + lane;
     long long local = 0;
     for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++local) {
@@ -192,11 +206,11 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
       tc_fence_after();
       // the store that read this staging buffer FC_OUT_BUFS tiles ago must have finished reading it
       const int ob = (int)(local % FC_OUT_BUFS);
-      if (threadIdx.x == 0) bulk_wait_read<FC_OUT_BUFS - 1>();
-      named_bar_sync(2, 128);
+      if (et == 0) bulk_wait_read<FC_OUT_BUFS - 1>();
+      named_bar_sync(2, 256);
       uint8_t* stage = smem_gen + out_off + ob * OUT_BYTES;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
         tmem_ld_wait();
@@ -220,17 +234,17 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));       // TMEM stage drained
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));       // this warp's part of the TMEM stage is drained
       fence_proxy_async_smem();                                    // staging writes -> visible to the TMA engine
-      named_bar_sync(2, 128);
-      if (threadIdx.x == 0) {
+      named_bar_sync(2, 256);
+      if (et == 0) {
 #pragma unroll
         for (int bx = 0; bx < BN / 64; ++bx)
           tma_store_2d(&map_out, smem_base + out_off + ob * OUT_BYTES + bx * OUT_BOX, bx * 64, (int)(tile * 128));
         bulk_commit();
       }
     }
-    if (threadIdx.x == 0) bulk_wait_all();
+    if (et == 0) bulk_wait_all();
   }
 
   tc_fence_before();
