@@ -8,15 +8,17 @@
 //   2. they are converted ONCE to normalised 16-bit values (uint8 through a 256-entry lookup table holding
 //      (v/255 - 0.5)/0.5 rounded to the operand type) into a patch with a zero border, so that
 //   3. each builder thread gathers its pixel's 3 x 9 contiguous values without any bounds test.
-// One thread issues two tcgen05.mma (K = 2 x 16) per tile; eight epilogue warps (two per TMEM lane quadrant, half
-// of the channels each) add bias + ReLU, stage the 128 x Cout tile in swizzled shared memory and drain it with TMA
-// stores, several tiles in flight.  HBM-write-bound by design: 3 KB in, 256 KB out per CIFAR-shaped sample.
-// Warp roles: 0-3 and 9-12 epilogue (TMEM lane quadrant = warp % 4), 4-7 builders, 8 weights TMA / MMA / TMEM.
+// One thread issues two tcgen05.mma (K = 2 x 16) per tile.  The bias rides in the GEMM: operand columns 27 and 28 of
+// every pixel are 1.0 and the matching weight columns hold bias_hi and bias_lo (bias = hi + lo to ~22 bits), so the
+// epilogue is only TMEM load -> convert-with-ReLU (cvt.rn.relu) -> swizzled shared memory -> TMA store, several tiles
+// in flight.  The kernel is instruction-issue-bound per SM sub-partition (one builder + one epilogue warp each), so
+// every instruction removed from the two loops counts.  3 KB in, 256 KB out per CIFAR-shaped sample.
+// Warp roles: 0-3 epilogue (TMEM lane quadrant = warp), 4-7 builders, 8 weights TMA / MMA / TMEM.
 #include "tc_ptx.cuh"
 
 namespace sdg {
 
-constexpr int FC_THREADS = 13 * 32;
+constexpr int FC_THREADS = 9 * 32;
 constexpr int FC_A_BYTES = 128 * 128;
 constexpr int FC_OUT_BUFS = 4;       // output staging tiles in flight
 constexpr int FC_PATCH_MAX = 4 * 66 * 3;     // normalised patch, 16-bit elements: (R+2) x (S+2) x 3; S=32: 612, S=64: 792
@@ -43,7 +45,6 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
 
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float s_bias[BN];
   __shared__ __align__(16) float s_rawf[3][768];      // raw rows: (R+2) x S x 3 bytes (u8) or floats (fp32 NCHW)
   __shared__ __align__(16) uint16_t s_patch[2][FC_PATCH_MAX];
   __shared__ uint16_t s_lut[256];
@@ -54,7 +55,6 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
   const int R = 128 / S;                  // image rows per tile
   const int tiles_y = S / R;
 
-  for (int i = threadIdx.x; i < BN; i += FC_THREADS) s_bias[i] = p.bias[i];
   if (threadIdx.x < 256) {
     float v = __fdiv_rn((float)threadIdx.x, 255.0f);
     v = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
@@ -66,7 +66,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
         mbar_init(smem_u32(&a_full[s]), 128);
         mbar_init(smem_u32(&a_empty[s]), 1);
         mbar_init(smem_u32(&acc_full[s]), 1);
-        mbar_init(smem_u32(&acc_empty[s]), 8);
+        mbar_init(smem_u32(&acc_empty[s]), 4);
       }
       mbar_init(smem_u32(&b_full), 1);
       fence_barrier_init();
@@ -86,7 +86,23 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
     if (elect_one()) {
       mbar_expect_tx(smem_u32(&b_full), BN * 128);
       tma_load_2d(b_addr, &map_b, smem_u32(&b_full), 0, 0);
-      mbar_wait(smem_u32(&b_full), 0);
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&b_full), 0);
+    // bias as two extra K columns (k = 27: hi, k = 28: lo) of the resident weight tile; A carries 1.0 there.
+    // row o of the swizzled tile: 16-byte chunk 3 (k = 24..31) sits at chunk position 3 ^ (o & 7)
+    for (int o = lane; o < BN; o += 32) {
+      const float b = p.bias[o];
+      const uint32_t hi = pack_h2<F16>(b, 0.f) & 0xffffu;
+      const float bhi = unpack_h2<F16>(hi).x;
+      const uint32_t lo = pack_h2<F16>(b - bhi, 0.f) & 0xffffu;
+      uint16_t* chunk = reinterpret_cast<uint16_t*>(smem_gen + 2 * FC_A_BYTES + o * 128 + ((3 ^ (o & 7)) << 4));
+      chunk[3] = (uint16_t)hi;
+      chunk[4] = (uint16_t)lo;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(128, BN, F16);
       const uint64_t bdesc = make_sw128_desc(b_addr);
       long long local = 0;
@@ -99,12 +115,12 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
         const uint64_t adesc = make_sw128_desc(smem_base + buf * FC_A_BYTES);
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
         umma_bf16(d_tmem, adesc, bdesc, idesc, 0u);                 // k = 0..15
-        umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);         // k = 16..31 (27..31 are zero)
+        umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);         // k = 16..31 (27, 28: the bias columns; 29..31 zero)
         umma_commit(smem_u32(&a_empty[buf]));
         umma_commit(smem_u32(&acc_full[buf]));
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4) {
     // ================= builders: raw rows -> normalised patch -> swizzled im2col tile =================
     const int bt = threadIdx.x - 128;           // 0..127 = pixel of the tile
     const int ly = bt / S, lx = bt - ly * S;
@@ -177,11 +193,12 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 9; ++j) vals[ky * 9 + j] = src[j];
       }
-      vals[27] = 0;
+      constexpr uint32_t kOne = F16 ? 0x3C00u : 0x3F80u;      // 1.0 in the operand type: the bias columns
+      vals[27] = (uint16_t)kOne;
       uint32_t packed[16];
 #pragma unroll
       for (int j = 0; j < 14; ++j) packed[j] = (uint32_t)vals[2 * j] | ((uint32_t)vals[2 * j + 1] << 16);
-      packed[14] = 0u; packed[15] = 0u;
+      packed[14] = kOne; packed[15] = 0u;
       mbar_wait(smem_u32(&a_empty[buf]), ph ^ 1u);          // the MMAs that read this A buffer have retired
       uint8_t* row = smem_gen + buf * FC_A_BYTES + bt * 128;
 #pragma unroll
@@ -192,11 +209,8 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
       mbar_arrive(smem_u32(&a_full[buf]));
     }
   } else {
-    // ================= epilogue: TMEM -> bias + ReLU -> 16-bit -> swizzled smem -> TMA store =================
-    // two warps per TMEM lane quadrant; the second group (warps 9-12) takes the upper half of the channels
-    const int q = warp & 3;
-    const int half = warp >= 9 ? 1 : 0;
-    const int et = half * 128 + (warp < 4 ? threadIdx.x : threadIdx.x - 9 * 32);   // 0..255 among epilogue threads
+    // ================= epilogue: TMEM -> ReLU + 16-bit convert -> swizzled smem -> TMA store =================
+    const int q = warp;
     const int row = q * 32 + lane;
     long long local = 0;
     for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++local) {
@@ -206,11 +220,11 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
       tc_fence_after();
       // the store that read this staging buffer FC_OUT_BUFS tiles ago must have finished reading it
       const int ob = (int)(local % FC_OUT_BUFS);
-      if (et == 0) bulk_wait_read<FC_OUT_BUFS - 1>();
-      named_bar_sync(2, 256);
+      if (threadIdx.x == 0) bulk_wait_read<FC_OUT_BUFS - 1>();
+      named_bar_sync(2, 128);
       uint8_t* stage = smem_gen + out_off + ob * OUT_BYTES;
-#pragma unroll 1
-      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
         tmem_ld_wait();
@@ -218,33 +232,27 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 pk;
-          uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
-          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8 + 4);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float a = fmaxf(__uint_as_float(r[g * 8 + 2 * j]) + bb[2 * j], 0.f);
-            float b = fmaxf(__uint_as_float(r[g * 8 + 2 * j + 1]) + bb[2 * j + 1], 0.f);
-            h[j] = pack_h2<F16>(a, b);
-          }
+          pk.x = pack_relu_h2<F16>(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]));
+          pk.y = pack_relu_h2<F16>(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
+          pk.z = pack_relu_h2<F16>(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
+          pk.w = pack_relu_h2<F16>(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
           const int chunk = ((c0 & 63) >> 3) + g;                 // 16-byte chunk within the 128-byte row
           *reinterpret_cast<uint4*>(srow + ((chunk ^ (row & 7)) << 4)) = pk;
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));       // this warp's part of the TMEM stage is drained
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));       // TMEM stage drained
       fence_proxy_async_smem();                                    // staging writes -> visible to the TMA engine
-      named_bar_sync(2, 256);
-      if (et == 0) {
+      named_bar_sync(2, 128);
+      if (threadIdx.x == 0) {
 #pragma unroll
         for (int bx = 0; bx < BN / 64; ++bx)
           tma_store_2d(&map_out, smem_base + out_off + ob * OUT_BYTES + bx * OUT_BOX, bx * 64, (int)(tile * 128));
         bulk_commit();
       }
     }
-    if (et == 0) bulk_wait_all();
+    if (threadIdx.x == 0) bulk_wait_all();
   }
 
   tc_fence_before();

@@ -22,6 +22,15 @@ __device__ __forceinline__ uint32_t pack_h2(float x, float y) {
   }
 }
 
+// pack with ReLU in the conversion itself (cvt.rn.relu.{f16x2,bf16x2}.f32: negative inputs become +0)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_relu_h2(float x, float y) {
+  uint32_t r;
+  if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+  return r;
+}
+
 template <bool F16>
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) {
   if (F16) return __half22float2(*reinterpret_cast<__half2*>(&v));
