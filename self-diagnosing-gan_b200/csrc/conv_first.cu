@@ -4,15 +4,14 @@
 // (torch-mimicry resblocks.py; SURVEY 8(a) "b1.c1"): out = relu(conv3x3(norm(x)) + b), written as the 16-bit
 // NHWC operand of the next conv.  K = 27 is too thin to stream through TMA, so builder warps assemble the
 // im2col tile (128 pixels x 32, 128B-swizzled K-major) in shared memory:
-//   1. the raw rows of the tile (+1 halo row each side) are prefetched two tiles ahead with cp.async;
-//   2. they are converted ONCE to normalised 16-bit values (uint8 through a 256-entry lookup table holding
-//      (v/255 - 0.5)/0.5 rounded to the operand type) into a patch with a zero border, so that
-//   3. each builder thread gathers its pixel's 3 x 9 contiguous values without any bounds test.
+//   the raw rows of the tile (+1 halo row each side) are prefetched two tiles ahead with cp.async; each builder thread
+//   gathers its pixel's 27 values, uint8 through a 256-entry lookup table holding (v/255 - 0.5)/0.5 rounded to the
+//   operand type (27 independent load chains).
 // One thread issues two tcgen05.mma (K = 2 x 16) per tile.  The bias rides in the GEMM: operand columns 27 and 28 of
 // every pixel are 1.0 and the matching weight columns hold bias_hi and bias_lo (bias = hi + lo to ~22 bits), so the
 // epilogue is only TMEM load -> convert-with-ReLU (cvt.rn.relu) -> swizzled shared memory -> TMA store, several tiles
-// in flight.  The kernel is instruction-issue-bound per SM sub-partition (one builder + one epilogue warp each), so
-// every instruction removed from the two loops counts.  3 KB in, 256 KB out per CIFAR-shaped sample.
+// in flight.  Profiled, the kernel is latency-bound (warps issue 17 % of the time), so TWO CTAs share each SM
+// (<= 112 registers, ~94 KB of shared memory, 2 x 256 TMEM columns).  3 KB in, 256 KB out per CIFAR-shaped sample.
 // Warp roles: 0-3 epilogue (TMEM lane quadrant = warp), 4-7 builders, 8 weights TMA / MMA / TMEM.
 #include "tc_ptx.cuh"
 
@@ -20,8 +19,7 @@ namespace sdg {
 
 constexpr int FC_THREADS = 9 * 32;
 constexpr int FC_A_BYTES = 128 * 128;
-constexpr int FC_OUT_BUFS = 4;       // output staging tiles in flight
-constexpr int FC_PATCH_MAX = 4 * 66 * 3;     // normalised patch, 16-bit elements: (R+2) x (S+2) x 3; S=32: 612, S=64: 792
+constexpr int FC_OUT_BUFS = 1;       // output staging tiles per CTA (two CTAs share an SM and overlap each other)
 
 struct FcParams {
   const void* x;
@@ -32,7 +30,7 @@ struct FcParams {
 };
 
 template <int BN, bool F16>
-__global__ void __launch_bounds__(FC_THREADS, 1)
+__global__ void __launch_bounds__(FC_THREADS, 2)
 first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const FcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -46,7 +44,6 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_rawf[3][768];      // raw rows: (R+2) x S x 3 bytes (u8) or floats (fp32 NCHW)
-  __shared__ __align__(16) uint16_t s_patch[2][FC_PATCH_MAX];
   __shared__ uint16_t s_lut[256];
 
   const int warp = threadIdx.x >> 5;
@@ -125,7 +122,6 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
     const int bt = threadIdx.x - 128;           // 0..127 = pixel of the tile
     const int ly = bt / S, lx = bt - ly * S;
     const bool u8 = p.layout == SDG_LAYOUT_U8_NHWC;
-    const int prow = (S + 2) * 3;               // patch row pitch in 16-bit elements (zero column each side)
     auto prefetch_raw = [&](long long tile, int rb) {
       if (tile < p.tiles) {
         const long long n = tile / tiles_y;
@@ -163,35 +159,27 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
       const int y0 = (int)(tile % tiles_y) * R;
       const float* rawf = s_rawf[local % 3];
       const uint8_t* rawb = reinterpret_cast<const uint8_t*>(rawf);
-      uint16_t* patch = s_patch[buf];
       cp_async_wait_1();          // everything but the newest group has landed -> this tile's rows are in smem
-      named_bar_sync(1, 128);     // ... for every builder thread; also: everyone is done gathering from patch[buf]
-      // ---- 1. convert once: patch[pr][pc][c] = normalised value of image (y0-1+pr, pc-1, c), zero outside ----
-      for (int pr = 0; pr < R + 2; ++pr) {
-        const int iy = y0 - 1 + pr;
-        const bool row_ok = iy >= 0 && iy < S;
-        for (int e = bt; e < prow; e += 128) {
-          const int pc = (e * 171) >> 9;        // e / 3 for e < 512
-          const int c = e - 3 * pc;
-          const int ix = pc - 1;
+      named_bar_sync(1, 128);     // ... for every builder thread
+      // the raw buffer of tile local-1 is free now: prefetch two tiles ahead
+      prefetch_raw(tile + 2 * (long long)gridDim.x, (int)((local + 2) % 3));
+      // ---- gather this pixel's 3x3x3 neighbourhood: k = (ky*3+kx)*3 + c (27 independent byte -> LUT chains) ----
+      uint16_t vals[28];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        const int iy = y0 + ly + ky - 1, ix = lx + kx - 1;
+        const bool ok = iy >= 0 && iy < S && ix >= 0 && ix < S;
+        const int pr = ly + ky;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
           uint16_t h = 0;
-          if (row_ok && ix >= 0 && ix < S) {
+          if (ok) {
             if (u8) h = s_lut[rawb[(pr * S + ix) * 3 + c]];
             else h = (uint16_t)(pack_h2<F16>(rawf[(c * (R + 2) + pr) * S + ix], 0.f) & 0xffffu);
           }
-          patch[pr * prow + e] = h;
+          vals[tap * 3 + c] = h;
         }
-      }
-      named_bar_sync(1, 128);
-      // the raw buffer of tile local-1 is free now (everyone passed the first barrier of this tile after converting it)
-      prefetch_raw(tile + 2 * (long long)gridDim.x, (int)((local + 2) % 3));
-      // ---- 2. gather this pixel's 3 x (3 pixels x 3 channels) contiguous values: k = (ky*3+kx)*3 + c ----
-      uint16_t vals[28];
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const uint16_t* src = patch + (ly + ky) * prow + lx * 3;     // patch column lx = image column lx-1
-#pragma unroll
-        for (int j = 0; j < 9; ++j) vals[ky * 9 + j] = src[j];
       }
       constexpr uint32_t kOne = F16 ? 0x3C00u : 0x3F80u;      // 1.0 in the operand type: the bias columns
       vals[27] = (uint16_t)kOne;
@@ -289,7 +277,7 @@ int first_conv(const void* x, int layout, const h16* wb, const float* bias, h16*
   p.tiles = n * (S * S / 128);
   p.bias = bias; p.out = out;
   const int sms = tc_num_sms();
-  const int grid = (int)(p.tiles < sms ? p.tiles : sms);
+  const int grid = (int)(p.tiles < 2 * sms ? p.tiles : 2 * sms);     // two persistent CTAs per SM
   if (Cout == 128 && f16) {
     SDG_LAUNCH((first_conv_kernel<128, true>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, map_out, p);
   } else if (Cout == 128) {
