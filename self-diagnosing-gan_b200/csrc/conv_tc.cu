@@ -113,6 +113,31 @@ __device__ __forceinline__ void tc_tile_origin(const TcParams& p, long long mt, 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// In-register transpose of an 8 x 8 matrix of float4 held by each group of 8 consecutive lanes (lane i of the group
+// holds Q[i][0..7] in t[4j..4j+3]); afterwards lane i holds Q[0..7][i].  Three xor-butterfly stages, 48 shuffles.
+// The epilogue uses it so that its fp32 global accesses are coalesced: 8 lanes x 16 B = one full 128-byte line of
+// ONE pixel row per group, instead of 32 lanes touching 32 different lines (the LSU wavefront count, not the DRAM
+// bandwidth, is what made the residual-stream epilogues slow).
+__device__ __forceinline__ void warp_transpose8_f4(float (&t)[32], int lane) {
+#pragma unroll
+  for (int s = 4; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if ((j & s) == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = t[4 * j + e], b = t[4 * (j + s) + e];
+          const float recv = __shfl_xor_sync(0xffffffffu, up ? a : b, s);
+          t[4 * j + e] = up ? recv : a;
+          t[4 * (j + s) + e] = up ? b : recv;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // epilogue of one 128-pixel x BN tile for one warp (TMEM lane quadrant q): waits for the accumulator, then
 // pooling / bias / shortcuts / stores.  tmem_acc = TMEM address of column 0 of this accumulator stage.
 template <int BN, bool F16>
@@ -125,6 +150,9 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
     return;
   }
   const int wc = p.W < 16 ? p.W : 16;             // columns per warp-row (pooling partner stride)
+  const bool lin = !p.pool && !p.box16;           // this warp's 32 rows are 32 consecutive output pixels
+  const long long wpix = mt * TC_BM + q * 32;     // ... starting here
+  const int g8 = lane >> 3, i8 = lane & 7;
   const int HW = p.H * p.W;
   const int Ho = p.pool ? p.H >> 1 : p.H, Wo = p.pool ? p.W >> 1 : p.W;
   {
@@ -185,6 +213,21 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
           v[j] *= 0.25f;
         }
       }
+      if (lin && p.res_f32) {
+        // identity residual, coalesced: lane (g8, i8) loads float4 #i8 of rows g8*8 + m, then an in-register transpose
+        // brings every row's 32 values to the lane that owns the row
+        float t[32];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const long long rp = wpix + g8 * 8 + m;
+          float4 ld = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rp < p.total_pixels) ld = *reinterpret_cast<const float4*>(p.res_f32 + rp * p.Cout + nt * BN + c0 + i8 * 4);
+          t[4 * m] = ld.x; t[4 * m + 1] = ld.y; t[4 * m + 2] = ld.z; t[4 * m + 3] = ld.w;
+        }
+        warp_transpose8_f4(t, lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += p.res_relu ? fmaxf(t[j], 0.f) : t[j];
+      }
       if (active) {
         const int cb = nt * BN + c0;
         // shared memory bandwidth is what bounds the MMA mainloop (operand fetch + TMA fill), so the epilogue
@@ -205,7 +248,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
           for (int j = 0; j < 32; ++j)
             v[j] = fmaf(w3[3 * j], px[0], fmaf(w3[3 * j + 1], px[1], fmaf(w3[3 * j + 2], px[2], v[j])));
         }
-        if (p.res_f32) {
+        if (p.res_f32 && !lin) {
           const float4* rp = reinterpret_cast<const float4*>(p.res_f32 + obase + c0);
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -214,7 +257,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
             v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
           }
         }
-        if (p.out_f32) {
+        if (p.out_f32 && !lin) {
           float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
 #pragma unroll
           for (int g = 0; g < 8; ++g) op[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
@@ -239,6 +282,21 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
               h[j] = pack_h2<F16>(fmaxf(v[g * 8 + 2 * j], 0.f), fmaxf(v[g * 8 + 2 * j + 1], 0.f));
             *reinterpret_cast<uint4*>(p.out_relu + obase + c0 + g * 8) = pk;
           }
+        }
+      }
+      if (lin && p.out_f32) {
+        // fp32 output, coalesced the same way (rows of invalid pixels are skipped).  Bias and shortcuts were added
+        // under `active`, which in linear mode is simply `valid`, so every stored row is complete.
+        float t[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] = v[j];
+        warp_transpose8_f4(t, lane);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const long long rp = wpix + g8 * 8 + m;
+          if (rp < p.total_pixels)
+            *reinterpret_cast<float4*>(p.out_f32 + rp * p.Cout + nt * BN + c0 + i8 * 4) =
+                make_float4(t[4 * m], t[4 * m + 1], t[4 * m + 2], t[4 * m + 3]);
         }
       }
     }
