@@ -240,6 +240,37 @@ def test_drs_module_contract(dev):
     assert e.generate_images(50).is_cuda and e.batch_size == 128
 
 
+def test_drs_with_engine_discriminator_sngan64(dev):
+    """BASELINE config 4: DRS acceptance pass with the SNGAN-64 discriminator running in the CUDA engine
+    (EngineNetD keeps the netD(x) -> [B,1] contract of drs.py:24-28); logits checked against the oracle."""
+    from diagan_b200.models.drs import DRS
+    from diagan_b200.models.engine_netd import EngineNetD
+    params = sngan_oracle.init_params(64, seed=1)
+
+    class G:
+        def __init__(self):
+            self.gen = torch.Generator(device="cuda").manual_seed(11)
+
+        def generate_images(self, n, device=None):
+            return torch.randn(n, 3, 64, 64, generator=self.gen, device=device).tanh()
+
+    netD = EngineNetD(params, dev, precision="fp32")
+    drs = DRS(G(), netD, dev, batch_size=64)
+    imgs, ldr = drs.get_fake_samples_and_ldr(64)
+    with torch.no_grad():
+        want = sngan_oracle.forward(params, imgs.cpu(), 64).numpy()
+        exact = sngan_oracle.forward({k: v.double() for k, v in params.items()}, imgs.cpu().double(), 64).numpy()
+    assert ldr.shape == (64, 1) and ldr.dtype == np.float32
+    assert _fp32_ok(ldr.reshape(-1), want.reshape(-1), exact.reshape(-1))[0]
+    np.random.seed(3)
+    out = drs.generate_images(40)
+    assert out.shape == (40, 3, 64, 64)
+    # tensor-core engine through the same wrapper
+    tc = EngineNetD(params, dev)          # fp16 operands by default
+    y = tc(imgs).cpu().numpy().reshape(-1)
+    assert _logit_close(y, exact.reshape(-1))[0] <= 2e-3
+
+
 # ---------------------------------------------------------------------------------------------------
 # discriminator forward
 # ---------------------------------------------------------------------------------------------------
