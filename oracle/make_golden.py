@@ -23,6 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import dcgan as dcgan_oracle   # noqa: E402
+from oracle import stylegan2 as sg2_oracle # noqa: E402
 from oracle import ref_loader              # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -162,9 +163,34 @@ def make_dcgan():
     print("dcgan_eval logits[:4]", y[:4])
 
 
+def make_stylegan2():
+    """StyleGANDiscriminator (diagan/models/stylegan2.py:619-677) on the CPU fall-back ops: weights from
+    oracle.stylegan2.init_params(seed) (regenerated by the tests), whole reference batches (minibatch-stddev)."""
+    D = ref_loader.reference_stylegan2_discriminator()
+    for size, n, batch in ((32, 16, 8), (128, 4, 4)):
+        net = D(size=size)
+        params = sg2_oracle.init_params(size, seed=1)
+        sd = net.state_dict()
+        for k, v in params.items():
+            assert sd[k].shape == v.shape, (k, sd[k].shape, v.shape)
+            sd[k] = v.clone()
+        net.load_state_dict(sd)
+        net.eval()
+        rng = np.random.RandomState(5)
+        x_u8 = rng.randint(0, 256, (n, size, size, 3)).astype(np.uint8)
+        x = ((torch.from_numpy(x_u8).permute(0, 3, 1, 2).float() / 255.0 - 0.5) / 0.5).contiguous()
+        with torch.no_grad():
+            y = torch.cat([net(x[s:s + batch]) for s in range(0, n, batch)]).view(-1).numpy()
+        chk = np.float64(sum(float(np.sum(v.numpy().astype(np.float64))) for v in params.values()))   # NumPy: thread-independent
+        np.savez_compressed(os.path.join(OUT, f"stylegan2_d{size}.npz"), size=np.int64(size), batch=np.int64(batch),
+                            param_seed=np.int64(1), param_checksum=chk, x_u8=x_u8, logits=y.astype(np.float32))
+        print(f"stylegan2_d{size} logits[:4]", y[:4])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)      # single-thread convs: deterministic accumulation order
     make_scores()
     make_drs()
     make_dcgan()
+    make_stylegan2()

@@ -124,3 +124,22 @@ def reference_dcgan_discriminator():
     _stub_mimicry()
     from diagan.models.mnist import MNIST_DCGAN_Discriminator
     return MNIST_DCGAN_Discriminator
+
+
+def reference_stylegan2_discriminator():
+    """-> the reference's own ``StyleGANDiscriminator`` class (diagan/models/stylegan2.py:619-677).
+
+    Importing ``diagan.models.op`` JIT-compiles two CUDA extensions at import time (op/fused_act.py:11-17,
+    op/upfirdn2d.py:10-16).  The oracle only needs the CPU fall-backs of those ops (fused_act.py:104-116,
+    upfirdn2d.py:145-200), so the JIT loader is stubbed out for the duration of the import."""
+    _ensure_path()
+    _stub_matplotlib()
+    _stub_mimicry()
+    import torch.utils.cpp_extension as ext
+    real = ext.load
+    ext.load = lambda *a, **k: None
+    try:
+        from diagan.models.stylegan2 import StyleGANDiscriminator
+    finally:
+        ext.load = real
+    return StyleGANDiscriminator

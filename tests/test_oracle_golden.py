@@ -9,6 +9,7 @@ import torch
 from oracle import dcgan as dcgan_oracle
 from oracle import drs as drs_oracle
 from oracle import scores as so
+from oracle import stylegan2 as sg2_oracle
 
 CASES = ["scores_cifar_window", "scores_ffhq_window", "scores_ties"]
 
@@ -106,3 +107,15 @@ def test_dcgan_oracle_matches_reference(golden_dir):
     torch.set_num_threads(1)
     y = dcgan_oracle.logits_pass(params, torch.from_numpy(g["x_u8"]))
     np.testing.assert_allclose(y, g["logits"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("size", [32, 128])
+def test_stylegan2_oracle_matches_reference(golden_dir, size):
+    g = _load(golden_dir, f"stylegan2_d{size}")
+    params = sg2_oracle.init_params(size, int(g["param_seed"]))
+    chk = sum(float(np.sum(v.numpy().astype(np.float64))) for v in params.values())
+    assert chk == float(g["param_checksum"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    y = sg2_oracle.logits_pass(params, torch.from_numpy(g["x_u8"]), size, int(g["batch"]))
+    np.testing.assert_allclose(y, g["logits"], rtol=2e-5, atol=1e-6)
+    assert sg2_oracle.block_channels(256) == [(128, 256), (256, 512), (512, 512), (512, 512), (512, 512), (512, 512)]
