@@ -36,6 +36,7 @@ extern "C" {
 
 /* discriminator architectures */
 #define SDG_ARCH_DCGAN32   1      /* diagan/models/mnist.py:155-223, eval mode, 3x32x32 */
+#define SDG_ARCH_STYLEGAN2 2      /* diagan/models/stylegan2.py:619-677 (= stylegan2/model.py:603-660), any power-of-two size */
 #define SDG_ARCH_SNGAN32   32     /* torch_mimicry SNGANDiscriminator32 (predefined_models.py:14,38,50) */
 #define SDG_ARCH_SNGAN64   64     /* torch_mimicry SNGANDiscriminator64 (predefined_models.py:76,88) */
 
@@ -90,6 +91,19 @@ SDG_API int sdg_dcgan_load(sdg_ctx* ctx, const float* const* conv_w_host,
                    const float* const* bn_gamma_host, const float* const* bn_beta_host,
                    const float* const* bn_mean_host, const float* const* bn_var_host,
                    const float* fc_w, const float* fc_b, int precision, void* stream);
+
+/* Replaces StyleGANDiscriminator.forward (diagan/models/stylegan2.py:659-677; twin stylegan2/model.py:642-660) for an
+ * input of `size` x `size`, channel_multiplier 2, blur kernel [1,3,3,1]: equalised-lr scales folded into the packed
+ * weights, FusedLeakyReLU (op/fused_act.py), Blur = upfirdn2d (op/upfirdn2d.py) and minibatch-stddev reproduced.
+ * tensors_host: device pointers in this order
+ *   convs.0.0.weight, convs.0.1.bias, then per ResBlock i = 1..: conv1.0.weight, conv1.1.bias, conv2.1.weight, conv2.2.bias,
+ *   skip.1.weight, then final_conv.0.weight, final_conv.1.bias, final_linear.0.weight, .0.bias, final_linear.1.weight, .1.bias
+ * Only SDG_PREC_FP32 (CUDA-core path) this round.
+ * Minibatch-stddev couples the samples of a reference batch: sdg_ctx_set_batch gives the batch size B
+ * the reference loader used (default 4); sdg_d_forward then needs n % B == 0 and treats samples [kB, (k+1)B) as one batch. */
+SDG_API int sdg_stylegan2_load(sdg_ctx* ctx, int size, int n_tensors, const float* const* tensors_host, int precision,
+                       void* stream);
+SDG_API int sdg_ctx_set_batch(sdg_ctx* ctx, int batch);
 
 /* ---- recording pass --------------------------------------------------------------------------
  * Replaces the loop body of LogTrainer._get_logit (trainer.py:148-154) and of stylegan2

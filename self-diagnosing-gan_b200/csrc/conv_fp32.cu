@@ -11,6 +11,7 @@ namespace sdg {
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return v > 0.f ? v : 0.f;
   if (act == ACT_LRELU) return v > 0.f ? v : 0.2f * v;
+  if (act == ACT_LRELU_SQRT2) return (v > 0.f ? v : 0.2f * v) * 1.4142135623730951f;   // fused_leaky_relu (op/fused_act.py:104-116)
   return v;
 }
 
@@ -20,11 +21,10 @@ constexpr int BM = 64, BN = 64, BK = 16, APAD = 2;
 __global__ void __launch_bounds__(256)
 conv_fp32_kernel(const float* __restrict__ in, const float* __restrict__ wp, const float* __restrict__ bias,
                  float* __restrict__ out, int64_t M, int H, int W, int Cin, int Cout, int Ho, int Wo, int ks,
-                 int stride, int pre_act, int post_act) {
+                 int stride, int pad, int pre_act, int post_act) {
   __shared__ float As[BK][BM + APAD];
   __shared__ __align__(16) float Bs[BK][BN];
   const int K = ks * ks * Cin;
-  const int pad = ks / 2;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int tid = threadIdx.x;
@@ -106,15 +106,15 @@ conv_fp32_kernel(const float* __restrict__ in, const float* __restrict__ wp, con
 }
 
 int conv_fp32(const float* in, const float* wp, const float* bias, float* out, int64_t n, int H, int W, int Cin,
-              int Cout, int ks, int stride, int pre_act, int post_act, cudaStream_t s) {
+              int Cout, int ks, int stride, int pre_act, int post_act, cudaStream_t s, int pad) {
   SDG_REQUIRE(Cout % 4 == 0, SDG_E_UNSUPPORTED, "conv_fp32: Cout=%d not a multiple of 4", Cout);
-  int pad = ks / 2;
+  if (pad < 0) pad = ks / 2;
   int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
   int64_t M = n * Ho * Wo;
   if (M == 0) return 0;
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(Cout, BN));
   SDG_LAUNCH(conv_fp32_kernel, grid, 256, 0, s, in, wp, bias, out, M, H, W, Cin, Cout, Ho, Wo, ks, stride,
-             pre_act, post_act);
+             pad, pre_act, post_act);
   return 0;
 }
 

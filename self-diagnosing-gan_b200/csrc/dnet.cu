@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 
 #include "kernels.cuh"
@@ -78,12 +79,19 @@ struct sdg_ctx {
   DevBuf sn_table, sn_scratch, bn_scratch;
   DevBuf buf[7], xin, xpool;             // activation scratch
   bool loaded = false;
+  // StyleGAN2 discriminator (fp32): ResBlock channel pairs, reference batch size for minibatch-stddev
+  std::vector<std::pair<int, int>> sg2_blocks;
+  int sg2_batch = 4;
+  DevBuf sg2_sd;
   // optional timing of the dominant kernel (block1.c2) with events on the launching stream
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
   double prof_flops = 0.0;
 };
+
+static int64_t sg2_buf_elems(const sdg_ctx* c);
+static int forward_stylegan2_fp32(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s);
 
 static int prof_begin(sdg_ctx* c, cudaStream_t s) {
   if (!c->profile) return 0;
@@ -147,7 +155,7 @@ extern "C" int sdg_ctx_destroy(sdg_ctx* c) {
   c->head_w.release(); c->head_b.release(); c->sigma.release();
   c->sn_table.release(); c->sn_scratch.release(); c->bn_scratch.release();
   for (auto& b : c->buf) b.release();
-  c->xin.release(); c->xpool.release();
+  c->xin.release(); c->xpool.release(); c->sg2_sd.release();
   delete c;
   return 0;
 }
@@ -479,6 +487,26 @@ extern "C" int sdg_d_forward(sdg_ctx* c, const void* x, int layout, int64_t n, f
   SDG_CUDA(cudaSetDevice(c->device));
   const int S = c->size;
   const bool bf = c->precision != SDG_PREC_FP32;
+  if (c->arch == SDG_ARCH_STYLEGAN2) {
+    const int B = c->sg2_batch;
+    SDG_REQUIRE(n % B == 0, SDG_E_INVALID, "sdg_d_forward: StyleGAN2 needs whole reference batches (minibatch-stddev): n=%lld "
+                "is not a multiple of batch %d; drop the ragged tail like the reference's drop_last=True", (long long)n, B);
+    const int64_t el = sg2_buf_elems(c);
+    int64_t chunk = c->chunk;
+    if (chunk <= 0) chunk = (3LL << 30) / (4 * el * 4 + (int64_t)S * S * 12);
+    chunk = std::max<int64_t>(B, chunk / B * B);
+    if (chunk > n) chunk = n;
+    for (int i = 0; i < 4; ++i) { int rc = c->buf[i].ensure((size_t)chunk * el * 4); if (rc) return rc; }
+    { int rc = c->xin.ensure((size_t)chunk * S * S * 3 * 4); if (rc) return rc; }
+    { int rc = c->sg2_sd.ensure(sizeof(float) * (size_t)chunk); if (rc) return rc; }
+    const size_t in_stride = layout == SDG_LAYOUT_U8_NHWC ? (size_t)S * S * 3 : (size_t)S * S * 3 * 4;
+    for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+      const int64_t nb = (n - s0) < chunk ? (n - s0) : chunk;
+      int rc = forward_stylegan2_fp32(c, (const char*)x + (size_t)s0 * in_stride, layout, nb, logits_out + s0, s);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   const int64_t act = max_act_elems(c);
   int64_t chunk = c->chunk;
   if (chunk <= 0) {
@@ -553,6 +581,140 @@ extern "C" int sdg_first_conv_h16(const void* x, int layout, const void* wb, con
   SDG_CUDA(cudaGetDevice(&dev));
   { int rc = conv_tc_init(dev); if (rc) return rc; }
   return first_conv(x, layout, (const h16*)wb, bias, (h16*)out, n, S, Cout, precision == SDG_PREC_FP16, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// StyleGAN2 discriminator (diagan-pkg/diagan/models/stylegan2.py:619-677), fp32 CUDA-core path
+// ------------------------------------------------------------------------------------------------
+static int sg2_channels(int res) {
+  switch (res) {
+    case 4: case 8: case 16: case 32: case 64: return 512;
+    case 128: return 256;
+    case 256: return 128;
+    case 512: return 64;
+    case 1024: return 32;
+  }
+  return 0;
+}
+
+extern "C" int sdg_ctx_set_batch(sdg_ctx* c, int batch) {
+  SDG_REQUIRE(c && batch >= 1, SDG_E_INVALID, "sdg_ctx_set_batch: bad argument");
+  const int group = batch < 4 ? batch : 4;
+  SDG_REQUIRE(batch % group == 0, SDG_E_INVALID, "sdg_ctx_set_batch: batch %d is not divisible by the stddev group %d (the "
+              "reference's view() fails for it too)", batch, group);
+  c->sg2_batch = batch;
+  return 0;
+}
+
+extern "C" int sdg_stylegan2_load(sdg_ctx* c, int size, int n_tensors, const float* const* t, int precision, void* stream) {
+  SDG_REQUIRE(c && t, SDG_E_INVALID, "sdg_stylegan2_load: null pointer");
+  SDG_REQUIRE(precision == SDG_PREC_FP32, SDG_E_UNSUPPORTED, "sdg_stylegan2_load: only SDG_PREC_FP32 is implemented");
+  SDG_REQUIRE(size >= 8 && size <= 1024 && (size & (size - 1)) == 0, SDG_E_INVALID, "sdg_stylegan2_load: size=%d", size);
+  cudaStream_t s = (cudaStream_t)stream;
+  SDG_CUDA(cudaSetDevice(c->device));
+  c->loaded = false;
+  c->sg2_blocks.clear();
+  int cin = sg2_channels(size);
+  for (int res = size; res > 4; res >>= 1) {
+    const int cout = sg2_channels(res >> 1);
+    c->sg2_blocks.push_back({cin, cout});
+    cin = cout;
+  }
+  const int nblk = (int)c->sg2_blocks.size();
+  const int want = 2 + 5 * nblk + 6;
+  SDG_REQUIRE(n_tensors == want, SDG_E_INVALID, "sdg_stylegan2_load: size %d needs %d tensors, got %d", size, want, n_tensors);
+  for (int i = 0; i < n_tensors; ++i) SDG_REQUIRE(t[i], SDG_E_INVALID, "sdg_stylegan2_load: tensor %d is null", i);
+  c->arch = SDG_ARCH_STYLEGAN2; c->precision = precision; c->size = size; c->blocks.clear();
+  const int n_convs = 1 + 3 * nblk + 2;                  // first, (conv1, conv2, skip) per block, final conv, linear 0
+  if ((int)c->convs.size() != n_convs) {
+    for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); l.w3.release(); l.bias_sum.release(); }
+    c->convs.assign(n_convs, ConvLayer());
+  }
+  auto pack = [&](ConvLayer& l, const float* W, const float* b, int cout, int cin_, int ks) -> int {
+    l.cout = cout; l.cin = cin_; l.ks = ks; l.has_bias = b != nullptr;
+    { int rc = l.w32.ensure(sizeof(float) * (size_t)ks * ks * cin_ * cout); if (rc) return rc; }
+    { int rc = pack_conv_fp32(W, nullptr, nullptr, l.w32.as<float>(), cout, cin_, ks, s, 1.0f / sqrtf((float)cin_ * ks * ks));
+      if (rc) return rc; }
+    if (b) {
+      { int rc = l.bias.ensure(sizeof(float) * cout); if (rc) return rc; }
+      SDG_CUDA(cudaMemcpyAsync(l.bias.p, b, sizeof(float) * cout, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+  };
+  int ti = 0, li = 0;
+  const int c0 = sg2_channels(size);
+  { int rc = pack(c->convs[li++], t[ti], t[ti + 1], c0, 3, 1); if (rc) return rc; ti += 2; }
+  for (auto& b : c->sg2_blocks) {
+    { int rc = pack(c->convs[li++], t[ti], t[ti + 1], b.first, b.first, 3); if (rc) return rc; }
+    { int rc = pack(c->convs[li++], t[ti + 2], t[ti + 3], b.second, b.first, 3); if (rc) return rc; }
+    { int rc = pack(c->convs[li++], t[ti + 4], nullptr, b.second, b.first, 1); if (rc) return rc; }
+    ti += 5;
+  }
+  { int rc = pack(c->convs[li++], t[ti], t[ti + 1], 512, 513, 3); if (rc) return rc; ti += 2; }
+  {
+    ConvLayer& l = c->convs[li++];           // EqualLinear(8192, 512, fused_lrelu) as a 1x1 conv over the NHWC-flattened map
+    l.cout = 512; l.cin = 8192; l.ks = 1; l.has_bias = true;
+    { int rc = l.w32.ensure(sizeof(float) * 8192 * 512); if (rc) return rc; }
+    { int rc = pack_linear_nchw_fp32(t[ti], 1.0f / sqrtf(8192.f), l.w32.as<float>(), 512, 512, 16, s); if (rc) return rc; }
+    { int rc = l.bias.ensure(sizeof(float) * 512); if (rc) return rc; }
+    SDG_CUDA(cudaMemcpyAsync(l.bias.p, t[ti + 1], sizeof(float) * 512, cudaMemcpyDeviceToDevice, s));
+    ti += 2;
+  }
+  c->head_len = 512;
+  { int rc = c->head_w.ensure(sizeof(float) * 512); if (rc) return rc; }
+  { int rc = c->head_b.ensure(sizeof(float)); if (rc) return rc; }
+  { int rc = pack_conv_fp32(t[ti], nullptr, nullptr, c->head_w.as<float>(), 1, 512, 1, s, 1.0f / sqrtf(512.f)); if (rc) return rc; }
+  SDG_CUDA(cudaMemcpyAsync(c->head_b.p, t[ti + 1], sizeof(float), cudaMemcpyDeviceToDevice, s));
+  c->loaded = true;
+  return 0;
+}
+
+static int64_t sg2_buf_elems(const sdg_ctx* c) {
+  int64_t m = (int64_t)c->size * c->size * sg2_channels(c->size);
+  int hw = c->size;
+  for (auto& b : c->sg2_blocks) {
+    const int cm = b.first > b.second ? b.first : b.second;
+    m = std::max<int64_t>(m, (int64_t)(hw + 1) * (hw + 1) * cm);
+    hw >>= 1;
+  }
+  return std::max<int64_t>(m, 16 * 513);
+}
+
+static int forward_stylegan2_fp32(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s) {
+  const int S = c->size;
+  float* X = c->xin.as<float>();
+  float* A = c->buf[0].as<float>();
+  float* B = c->buf[1].as<float>();
+  float* C = c->buf[2].as<float>();
+  float* D = c->buf[3].as<float>();
+  int rc, li = 0;
+  if ((rc = prep_input_fp32(x, layout, X, nb, S, S, s))) return rc;
+  {
+    const ConvLayer& l = c->convs[li++];
+    if ((rc = conv_fp32(X, l.w32.as<float>(), l.bias.as<float>(), A, nb, S, S, 3, l.cout, 1, 1, ACT_NONE, ACT_LRELU_SQRT2, s, 0))) return rc;
+  }
+  int hw = S;
+  for (auto& b : c->sg2_blocks) {
+    const ConvLayer& c1 = c->convs[li++];
+    const ConvLayer& c2 = c->convs[li++];
+    const ConvLayer& sk = c->convs[li++];
+    const int ho = hw / 2;
+    // conv1: 3x3 + FusedLeakyReLU;  conv2: Blur(pad 2) + 3x3 stride 2 + FusedLeakyReLU;  skip: Blur(pad 1) + 1x1 stride 2
+    if ((rc = conv_fp32(A, c1.w32.as<float>(), c1.bias.as<float>(), B, nb, hw, hw, b.first, b.first, 3, 1, ACT_NONE, ACT_LRELU_SQRT2, s, 1))) return rc;
+    if ((rc = blur_fp32(B, C, nb, hw, hw, b.first, 2, s))) return rc;
+    if ((rc = conv_fp32(C, c2.w32.as<float>(), c2.bias.as<float>(), D, nb, hw + 1, hw + 1, b.first, b.second, 3, 2, ACT_NONE, ACT_LRELU_SQRT2, s, 0))) return rc;
+    if ((rc = blur_fp32(A, C, nb, hw, hw, b.first, 1, s))) return rc;
+    if ((rc = conv_fp32(C, sk.w32.as<float>(), nullptr, B, nb, hw - 1, hw - 1, b.first, b.second, 1, 2, ACT_NONE, ACT_NONE, s, 0))) return rc;
+    if ((rc = add_div_sqrt2_fp32(D, B, A, nb * ho * ho * (int64_t)b.second, s))) return rc;
+    hw = ho;
+  }
+  // minibatch-stddev channel, final conv, the two EqualLinear layers
+  if ((rc = minibatch_stddev_cat_fp32(A, B, c->sg2_sd.as<float>(), nb, c->sg2_batch, 16, 512, s))) return rc;
+  const ConvLayer& fc = c->convs[li++];
+  if ((rc = conv_fp32(B, fc.w32.as<float>(), fc.bias.as<float>(), D, nb, 4, 4, 513, 512, 3, 1, ACT_NONE, ACT_LRELU_SQRT2, s, 1))) return rc;
+  const ConvLayer& l0 = c->convs[li++];
+  if ((rc = conv_fp32(D, l0.w32.as<float>(), l0.bias.as<float>(), C, nb, 1, 1, 8192, 512, 1, 1, ACT_NONE, ACT_LRELU_SQRT2, s, 0))) return rc;
+  return head_dot_fp32(C, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, 512, s);
 }
 
 extern "C" int sdg_set_conv_pair(int on) {

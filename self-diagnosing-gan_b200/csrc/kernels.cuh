@@ -6,7 +6,7 @@
 
 namespace sdg {
 
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };   // LRELU: slope 0.2 (mnist.py:164)
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_LRELU_SQRT2 = 3 };   // LRELU: slope 0.2 (mnist.py:164)
 
 // 16-bit storage of the tensor-core path: IEEE fp16 (F16 = true) or bfloat16; arithmetic is fp32.
 typedef uint16_t h16;
@@ -38,9 +38,20 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t v) {
 }
 
 // ---- conv_fp32.cu: IEEE fp32 CUDA-core path (NHWC activations) ---------------------------------
-// wp: packed [ks*ks*Cin][Cout] (k = (ky*ks+kx)*Cin + c), pad = ks/2
+// wp: packed [ks*ks*Cin][Cout] (k = (ky*ks+kx)*Cin + c); pad < 0 means ks/2
 int conv_fp32(const float* in, const float* wp, const float* bias, float* out, int64_t n, int H, int W, int Cin,
-              int Cout, int ks, int stride, int pre_act, int post_act, cudaStream_t s);
+              int Cout, int ks, int stride, int pre_act, int post_act, cudaStream_t s, int pad = -1);
+
+// ---- sg2_fp32.cu: StyleGAN2 discriminator pieces (fp32) ------------------------------------------------------------
+// out[n,H+2*pad-3,...] = upfirdn2d(in, outer([1,3,3,1])/64, pad=(pad,pad))      (Blur, stylegan2.py:75-90)
+int blur_fp32(const float* in, float* out, int64_t n, int H, int W, int C, int pad, cudaStream_t s);
+int add_div_sqrt2_fp32(const float* a, const float* b, float* out, int64_t total, cudaStream_t s);   // (a + b) / sqrt(2)
+// minibatch-stddev (stylegan2.py:662-670) over consecutive reference batches of `batch` samples, appended as channel C:
+// in [n,HW,C] -> out [n,HW,C+1]
+int minibatch_stddev_cat_fp32(const float* in, float* out, float* sd_scratch, int64_t n, int batch, int HW, int C,
+                              cudaStream_t s);
+// wp[(p*C + c)*O + o] = W[o][c*HW + p] * mul    (EqualLinear on an NCHW-flattened feature map, activations kept NHWC)
+int pack_linear_nchw_fp32(const float* W, float mul, float* wp, int O, int C, int HW, cudaStream_t s);
 // out = (pool_a ? avgpool2(a) : a) + (pool_b ? avgpool2(relu_b ? relu(b) : b) : ...); b may be null
 int combine_fp32(const float* a, int pool_a, const float* b, int pool_b, int relu_b, float* out, int64_t n,
                  int Ho, int Wo, int C, cudaStream_t s);
@@ -64,7 +75,7 @@ int sn_sigmas(const SnLayer* layers_dev, const SnLayer* layers_host, int n_layer
               cudaStream_t s);
 // wp[(tap*Cin + c)*Cout + o] = W[o][c][tap] * scale[o] / sigma   (scale may be null; sigma may be null)
 int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float* wp, int Cout, int Cin, int ks,
-                   cudaStream_t s);
+                   cudaStream_t s, float mul = 1.0f);
 // wb[o*ld + col0 + k] = h16(W[o][c][tap] * scale[o] / sigma) at k = tap*Cin + c, zero padded up to Kpad columns
 int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* wb, int Cout, int Cin, int Kpad,
                   int ks, int f16, int ld, int col0, cudaStream_t s);

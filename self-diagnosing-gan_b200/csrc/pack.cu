@@ -87,7 +87,7 @@ int sn_sigmas(const SnLayer* layers_dev, const SnLayer* layers_host, int n_layer
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pack_conv_fp32_kernel(const float* __restrict__ W, const float* __restrict__ sigma, const float* __restrict__ scale,
-                      float* __restrict__ wp, int Cout, int Cin, int taps) {
+                      float* __restrict__ wp, int Cout, int Cin, int taps, float mul) {
   const int total = Cout * Cin * taps;
   const float sg = sigma ? sigma[0] : 1.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -97,14 +97,15 @@ pack_conv_fp32_kernel(const float* __restrict__ W, const float* __restrict__ sig
     float w = W[((int64_t)o * Cin + c) * taps + tap];
     if (sigma) w = w / sg;                       // self.weight / sigma
     if (scale) w = w * scale[o];
+    if (mul != 1.0f) w = w * mul;                // EqualConv2d: weight * (1/sqrt(Cin k^2))
     wp[i] = w;
   }
 }
 
 int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float* wp, int Cout, int Cin, int ks,
-                   cudaStream_t s) {
+                   cudaStream_t s, float mul) {
   int total = Cout * Cin * ks * ks;
-  SDG_LAUNCH(pack_conv_fp32_kernel, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wp, Cout, Cin, ks * ks);
+  SDG_LAUNCH(pack_conv_fp32_kernel, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wp, Cout, Cin, ks * ks, mul);
   return 0;
 }
 

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsdg.so")
 
 # constants mirrored from include/sdg.h
 ABI_VERSION = 1
-ARCH_DCGAN32, ARCH_SNGAN32, ARCH_SNGAN64 = 1, 32, 64
+ARCH_DCGAN32, ARCH_STYLEGAN2, ARCH_SNGAN32, ARCH_SNGAN64 = 1, 2, 32, 64
 PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 LAYOUT_U8_NHWC, LAYOUT_F32_NCHW = 0, 1
 
@@ -31,6 +31,8 @@ SIGNATURES = {
     "sdg_sngan_load": (_i, [_vp, _i, _i, _pp, _pp, _pp, _i, _i, _vp]),
     "sdg_sngan_sigmas": (_i, [_vp, _vp, _vp]),
     "sdg_dcgan_load": (_i, [_vp, _pp, _pp, _pp, _pp, _pp, _vp, _vp, _i, _vp]),
+    "sdg_stylegan2_load": (_i, [_vp, _i, _i, _pp, _i, _vp]),
+    "sdg_ctx_set_batch": (_i, [_vp, _i]),
     "sdg_d_forward": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "sdg_conv2d_h16": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i,
                              _vp]),

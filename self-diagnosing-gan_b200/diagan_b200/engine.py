@@ -66,12 +66,28 @@ def detect_arch(state_dict) -> str:
     keys = set(state_dict.keys())
     if "conv.0.weight" in keys and "out_d.weight" in keys:
         return "dcgan32"
+    if "final_conv.0.weight" in keys and "convs.0.0.weight" in keys:
+        return "stylegan2"
     if "l6.weight" in keys and "block5.c1.weight" in keys:
         return "sngan64"
     if "l5.weight" in keys and "block4.c1.weight" in keys and "block1.c_sc.weight" in keys:
         return "sngan32"
-    raise _lib.SdgError("unsupported discriminator: expected torch-mimicry SNGANDiscriminator32/64 or the "
-                        "reference's MNIST_DCGAN_Discriminator state_dict")
+    raise _lib.SdgError("unsupported discriminator: expected torch-mimicry SNGANDiscriminator32/64, the reference's "
+                        "MNIST_DCGAN_Discriminator or its StyleGANDiscriminator state_dict")
+
+
+def stylegan2_tensor_keys(state_dict):
+    """(size, ordered key list) of the reference StyleGANDiscriminator state_dict (include/sdg.h, sdg_stylegan2_load)."""
+    nblk = 0
+    while f"convs.{nblk + 1}.conv1.0.weight" in state_dict:
+        nblk += 1
+    keys = ["convs.0.0.weight", "convs.0.1.bias"]
+    for i in range(1, nblk + 1):
+        keys += [f"convs.{i}.conv1.0.weight", f"convs.{i}.conv1.1.bias", f"convs.{i}.conv2.1.weight",
+                 f"convs.{i}.conv2.2.bias", f"convs.{i}.skip.1.weight"]
+    keys += ["final_conv.0.weight", "final_conv.1.bias", "final_linear.0.weight", "final_linear.0.bias",
+             "final_linear.1.weight", "final_linear.1.bias"]
+    return 4 << nblk, keys
 
 
 class DiscriminatorEngine:
@@ -143,10 +159,29 @@ class DiscriminatorEngine:
         self.arch, self.size, self.n_layers = "dcgan32", 32, 7
         return self
 
+    def load_stylegan2(self, state_dict, precision: str = "fp32", batch: int = 4):
+        """The reference's StyleGANDiscriminator (any power-of-two size).  ``batch`` = the loader batch size the
+        reference would use: minibatch-stddev groups are formed inside consecutive batches of that size."""
+        size, keys = stylegan2_tensor_keys(state_dict)
+        T = [self._dev(state_dict[k]) for k in keys]
+        prec = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}[precision]
+        with torch.cuda.device(self.device):
+            check(self.lib.sdg_stylegan2_load(self._h, size, len(T), ptr_array(T), prec, stream_ptr(self.device)),
+                  "sdg_stylegan2_load")
+            check(self.lib.sdg_ctx_set_batch(self._h, int(batch)), "sdg_ctx_set_batch")
+        self._keep = T
+        self.arch, self.size, self.n_layers = "stylegan2", size, len(T)
+        return self
+
+    def set_batch(self, batch: int):
+        check(self.lib.sdg_ctx_set_batch(self._h, int(batch)), "sdg_ctx_set_batch")
+
     def load(self, state_dict, precision: str = None, inplace_relu: bool = True):
         kind = detect_arch(state_dict)
         if kind == "dcgan32":
             return self.load_dcgan(state_dict, precision or "fp32")
+        if kind == "stylegan2":
+            return self.load_stylegan2(state_dict, "fp32")
         return self.load_sngan(state_dict, int(kind[5:]), precision or "fp16", inplace_relu)
 
     def sigmas(self) -> torch.Tensor:

@@ -320,6 +320,35 @@ def test_sngan_fp32_vs_oracle(arch, n, inplace, dev):
     assert np.array_equal(eng.forward(x.to(dev)).cpu().numpy(), got)
 
 
+@pytest.mark.parametrize("size", [32, 128])
+def test_stylegan2_fp32_vs_reference_golden(golden_dir, size, dev):
+    """StyleGANDiscriminator (BASELINE config 5 architecture) in the fp32 engine against logits produced by the
+    reference module itself; whole reference batches (minibatch-stddev), both input layouts, chunking invariance."""
+    from diagan_b200 import engine
+    from oracle import stylegan2 as sg2_oracle
+    g = _load(golden_dir, f"stylegan2_d{size}")
+    batch = int(g["batch"])
+    params = sg2_oracle.init_params(size, int(g["param_seed"]))
+    eng = engine.DiscriminatorEngine(dev).load_stylegan2(params, batch=batch)
+    assert eng.arch == "stylegan2" and eng.size == size
+    x = torch.from_numpy(g["x_u8"]).to(dev)
+    y = eng.forward(x).cpu().numpy()
+    emax, _ = _logit_close(y, g["logits"])
+    print(f"stylegan2 D{size} fp32 vs reference golden: max rel err {emax:.2e}")
+    assert emax <= 1e-5
+    xf = sngan_oracle.normalise_u8(torch.from_numpy(g["x_u8"])).contiguous().to(dev)
+    assert np.array_equal(eng.forward(xf).cpu().numpy(), y)
+    if x.shape[0] > batch:            # one reference batch per internal sweep gives the same logits
+        eng.set_chunk(batch)
+        assert np.array_equal(eng.forward(x).cpu().numpy(), y)
+        # a different batch composition changes the stddev channel, hence the logits (SURVEY 0.1 item 9)
+        eng.set_chunk(0); eng.set_batch(batch // 2)
+        assert not np.array_equal(eng.forward(x).cpu().numpy(), y)
+    with pytest.raises(Exception):
+        eng.set_batch(batch)
+        eng.forward(x[:batch - 1].contiguous())
+
+
 def _tdt(prec):
     return torch.float16 if prec == "fp16" else torch.bfloat16
 
