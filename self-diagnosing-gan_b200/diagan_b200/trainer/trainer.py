@@ -75,7 +75,7 @@ class LogitRecorder:
     """
 
     def __init__(self, dataset: ResidentDataset = None, device=None, precision="fp16", inplace_relu=True,
-                 shard=None, keep_snapshots=True, stats_window=None):
+                 shard=None, keep_snapshots=True, stats_window=None, batch=4):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dataset = dataset
         self.precision = precision
@@ -87,13 +87,20 @@ class LogitRecorder:
         self.stats_window = stats_window          # (start, end): only steps in [start, end) feed the stats
         self.snapshots = {}                       # step -> float32 [N] device tensor
         self.stats = None
+        # StyleGAN2 only: the loader batch size of the reference pass (stylegan2/train_ffhq.py:596-602); minibatch-stddev
+        # groups live inside consecutive batches of this size and the ragged tail is dropped (drop_last=True)
+        self.batch = batch
 
     def _range(self):
         return (0, self.n) if self.shard is None else self.shard
 
     def load_weights(self, netD):
         sd = netD.state_dict() if hasattr(netD, "state_dict") else netD
-        self.engine.load(sd, self.precision if engine.detect_arch(sd) != "dcgan32" else "fp32", self.inplace_relu)
+        kind = engine.detect_arch(sd)
+        if kind == "stylegan2":
+            self.engine.load_stylegan2(sd, "fp32", batch=self.batch)
+        else:
+            self.engine.load(sd, self.precision if kind != "dcgan32" else "fp32", self.inplace_relu)
 
     def record(self, netD, step=None, out: torch.Tensor = None) -> torch.Tensor:
         """One recording pass over the resident dataset (this rank's shard) -> float32 [N] on the device."""
@@ -102,6 +109,8 @@ class LogitRecorder:
         self.load_weights(netD)
         lo, hi = self._range()
         snap = torch.zeros(self.n, dtype=torch.float32, device=self.device) if out is None else out
+        if self.engine.arch == "stylegan2":
+            hi = lo + (hi - lo) // self.batch * self.batch      # drop_last: the tail keeps its 0.0 like the reference
         self.engine.forward(self.dataset.data[lo:hi], out=snap[lo:hi])
         if step is not None:
             self.observe(step, snap)
