@@ -137,6 +137,40 @@ __device__ __forceinline__ void warp_transpose8_f4(float (&t)[32], int lane) {
   }
 }
 
+// Same idea for the 16-bit outputs: a row's 32 columns are 4 x 16 B; a 4 x 4 transpose inside each group of 4 lanes
+// lets 4 lanes write the 64 contiguous bytes of ONE row (8 rows per instruction) instead of 32 lanes x 16 B on 32 rows.
+__device__ __forceinline__ void warp_transpose4_u4(uint32_t (&t)[16], int lane) {
+#pragma unroll
+  for (int s = 2; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if ((j & s) == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t a = t[4 * j + e], b = t[4 * (j + s) + e];
+          const uint32_t recv = __shfl_xor_sync(0xffffffffu, up ? a : b, s);
+          t[4 * j + e] = up ? recv : a;
+          t[4 * (j + s) + e] = up ? b : recv;
+        }
+      }
+    }
+  }
+}
+
+// store this warp's 32 rows x 32 columns of 16-bit values (pk = the lane's own row, 16 packed words) coalesced
+__device__ __forceinline__ void store_rows16_coalesced(h16* base, long long wpix, long long total_pixels, int Cout, int col0,
+                                                       uint32_t (&pk)[16], int lane) {
+  warp_transpose4_u4(pk, lane);
+  const int g4 = lane >> 2, i4 = lane & 3;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const long long rp = wpix + g4 * 4 + m;
+    if (rp < total_pixels)
+      *reinterpret_cast<uint4*>(base + rp * Cout + col0 + i4 * 8) = make_uint4(pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // epilogue of one 128-pixel x BN tile for one warp (TMEM lane quadrant q): waits for the accumulator, then
 // pooling / bias / shortcuts / stores.  tmem_acc = TMEM address of column 0 of this accumulator stage.
@@ -262,7 +296,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
 #pragma unroll
           for (int g = 0; g < 8; ++g) op[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
         }
-        if (p.out_raw) {
+        if (p.out_raw && !lin) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 pk;
@@ -272,7 +306,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
             *reinterpret_cast<uint4*>(p.out_raw + obase + c0 + g * 8) = pk;
           }
         }
-        if (p.out_relu) {
+        if (p.out_relu && !lin) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 pk;
@@ -283,6 +317,18 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
             *reinterpret_cast<uint4*>(p.out_relu + obase + c0 + g * 8) = pk;
           }
         }
+      }
+      if (lin && p.out_raw) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_h2<F16>(v[2 * j], v[2 * j + 1]);
+        store_rows16_coalesced(p.out_raw, wpix, p.total_pixels, p.Cout, nt * BN + c0, pk, lane);
+      }
+      if (lin && p.out_relu) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_relu_h2<F16>(v[2 * j], v[2 * j + 1]);
+        store_rows16_coalesced(p.out_relu, wpix, p.total_pixels, p.Cout, nt * BN + c0, pk, lane);
       }
       if (lin && p.out_f32) {
         // fp32 output, coalesced the same way (rows of invalid pixels are skipped).  Bias and shortcuts were added
