@@ -610,9 +610,52 @@ def test_get_logit_from_dataloader_contract(dev):
     assert got.dtype == np.float64 and ok
 
 
+def test_recorder_stylegan2_drop_last(golden_dir, dev):
+    """StyleGAN2 recording pass through LogitRecorder: whole batches only, the ragged tail keeps 0.0 like the
+    reference's drop_last=True loader (stylegan2/train_ffhq.py:596-602)."""
+    from diagan_b200.trainer.trainer import LogitRecorder, ResidentDataset
+    from oracle import stylegan2 as sg2_oracle
+    g = _load(golden_dir, "stylegan2_d32")
+    params = sg2_oracle.init_params(32, int(g["param_seed"]))
+    x = torch.from_numpy(g["x_u8"][:13])                        # 13 samples, batch 8 -> one batch + 5 dropped
+    rec = LogitRecorder(ResidentDataset(x.to(dev)), dev, batch=8)
+    snap = rec.record(params).cpu().numpy()
+    assert _logit_close(snap[:8], g["logits"][:8])[0] <= 1e-5
+    assert np.all(snap[8:] == 0.0)
+
+
 # ---------------------------------------------------------------------------------------------------
 # BASELINE-size properties (no oracle at this size: invariants instead)
 # ---------------------------------------------------------------------------------------------------
+def test_full_size_recording_pass_properties(dev):
+    """configs[1] at full size (50 000 x 3x32x32, SNGAN-32, tensor-core engine): the pass is deterministic, every
+    sample's logit is independent of where it sits in the pass (shards / permutations give bit-identical values:
+    this is what makes index sharding across GPUs exact), and a random subset agrees with the oracle."""
+    from diagan_b200 import engine, synthetic
+    n = 50_000
+    x = synthetic.uniform_images_u8(n, 32, seed=1).to(dev)
+    sd = synthetic.sngan_state_dict(32, seed=1)
+    eng = engine.DiscriminatorEngine(dev).load_sngan(sd, 32, "fp16", True)
+    full = eng.forward(x)
+    assert torch.equal(full, eng.forward(x))                                   # deterministic
+    lo, hi = 12_345, 31_111                                                    # an arbitrary shard
+    assert torch.equal(eng.forward(x[lo:hi].contiguous()), full[lo:hi])
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(0)).to(dev)
+    assert torch.equal(eng.forward(x[perm].contiguous()), full[perm])          # permutation equivariance
+    eng.set_chunk(1000)
+    assert torch.equal(eng.forward(x), full)                                   # chunking invariance
+    sub = torch.randperm(n, generator=torch.Generator().manual_seed(1))[:192]
+    want = sngan_oracle.logits_pass(sd, x[sub.to(dev)].cpu(), 32, dtype=torch.float64)
+    torch.backends.cudnn.allow_tf32 = True
+    with torch.no_grad():
+        ytf = sngan_oracle.forward({k: v.to(dev) for k, v in sd.items()}, sngan_oracle.normalise_u8(x[sub.to(dev)].cpu()).to(dev),
+                                   32, True).view(-1).cpu().numpy()
+    e, etf = _logit_close(full[sub.to(dev)].cpu().numpy(), want)[0], _logit_close(ytf, want)[0]
+    print(f"full-size pass, 192-sample subset vs float64 oracle: {e:.2e} (torch-eager TF32: {etf:.2e})")
+    assert e <= 1e-3 or e <= 1.5 * etf
+
+
+
 def test_full_size_properties(dev):
     """50k samples x 50 snapshots (configs[1] score stage): window path == Welford path to 1e-12,
     clip bounds hold, idempotent clip, top-k sorted and consistent with the score vector."""
