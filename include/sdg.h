@@ -98,7 +98,8 @@ SDG_API int sdg_dcgan_load(sdg_ctx* ctx, const float* const* conv_w_host,
  * tensors_host: device pointers in this order
  *   convs.0.0.weight, convs.0.1.bias, then per ResBlock i = 1..: conv1.0.weight, conv1.1.bias, conv2.1.weight, conv2.2.bias,
  *   skip.1.weight, then final_conv.0.weight, final_conv.1.bias, final_linear.0.weight, .0.bias, final_linear.1.weight, .1.bias
- * Only SDG_PREC_FP32 (CUDA-core path) this round.
+ * precision: SDG_PREC_FP32 = exact CUDA-core path; SDG_PREC_FP16 / SDG_PREC_BF16 = ResBlock convolutions on tcgen05
+ * (16-bit NHWC activations, fp32 accumulation; the 3-channel first conv and the 4x4 tail stay fp32).
  * Minibatch-stddev couples the samples of a reference batch: sdg_ctx_set_batch gives the batch size B
  * the reference loader used (default 4); sdg_d_forward then needs n % B == 0 and treats samples [kB, (k+1)B) as one batch. */
 SDG_API int sdg_stylegan2_load(sdg_ctx* ctx, int size, int n_tensors, const float* const* tensors_host, int precision,
@@ -131,6 +132,20 @@ SDG_API int sdg_conv2d_h16(const void* in, const void* wb, const float* bias, in
                    int ks, const void* sc_in, int sc_C, int pool, const float* res_f32, int res_relu,
                    const void* img, int img_layout, const float* sc_w3, void* out_relu, void* out_raw,
                    float* out_f32, int precision, void* stream);
+/* StyleGAN2 ConvLayer stages of the tensor-core path on their own (what sdg_d_forward launches per ResBlock conv; exposed
+ * for kernel-level parity tests).  Replaces ConvLayer / ResBlock.forward pieces (stylegan2.py:553-616):
+ *   v = F.conv2d(in, W * scale, stride = stride, padding = pad ? ks/2 : 0)          ks in {1,3}, stride in {1,2}
+ *   [v = leaky_relu(v + bias, 0.2) * sqrt(2)     act != 0: FusedLeakyReLU (op/fused_act.py:104-116); else v += bias]
+ *   [v += res_f32]  v *= out_scale               ResBlock: (out + skip) / sqrt(2)
+ * in [n,in_H,in_W,Cin] NHWC 16-bit; outputs [n,Hout,Wout,Cout] (Hout == Wout a power of two in 4..512); wb [Cout, ks*ks*Cin]
+ * 16-bit with the equalised-lr scale folded in; out_raw 16-bit and/or out_f32. */
+SDG_API int sdg_conv2d_sg2_h16(const void* in, const void* wb, const float* bias, int64_t n, int Hout, int Wout, int in_H,
+                       int in_W, int Cin, int Cout, int ks, int stride, int pad, int act, const float* res_f32,
+                       float out_scale, void* out_raw, float* out_f32, int precision, void* stream);
+/* Blur (stylegan2.py:75-90 = upfirdn2d with outer([1,3,3,1])/64, zero padding `pad` on every side) on 16-bit NHWC;
+ * out extent (H + 2*pad - 4) / stride + 1: stride 2 evaluates only the outputs a following stride-2 1x1 conv reads. */
+SDG_API int sdg_blur_h16(const void* in, void* out, int64_t n, int H, int W, int C, int pad, int stride, int precision,
+                 void* stream);
 /* Kernel selection for Cout = 128 3x3 stages: on != 0 (default) uses the CTA-pair kernel (tcgen05.mma.cta_group::2,
  * weights resident in shared memory), 0 forces the single-CTA kernel.  Process-wide; for tests and A/B timing. */
 SDG_API int sdg_set_conv_pair(int on);

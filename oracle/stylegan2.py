@@ -68,7 +68,7 @@ def fir_kernel() -> torch.Tensor:
 def blur(x: torch.Tensor, pad0: int, pad1: int) -> torch.Tensor:
     """upfirdn2d(x, k, up=1, down=1, pad=(pad0, pad1)): zero-pad, correlate with the flipped 4x4 FIR."""
     c = x.shape[1]
-    w = torch.flip(fir_kernel(), [0, 1]).to(x.dtype).view(1, 1, 4, 4).repeat(c, 1, 1, 1)
+    w = torch.flip(fir_kernel(), [0, 1]).to(device=x.device, dtype=x.dtype).view(1, 1, 4, 4).repeat(c, 1, 1, 1)
     return F.conv2d(F.pad(x, [pad0, pad1, pad0, pad1]), w, groups=c)
 
 

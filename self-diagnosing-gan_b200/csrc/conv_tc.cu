@@ -44,6 +44,10 @@ struct TcParams {
   int tw;                    // taps per kernel row (3: 3x3, 4: pooled-3x3-as-4x4, 1: 1x1)
   int cs;                    // input coordinate scale: 2 for the 4x4 stride-2 form, else 1
   int img_up;                // epilogue pixels are at pooled resolution of `img` (stride-2 form)
+  int toff;                  // offset of tap 0 relative to the output pixel (times cs): -1 for "same" padding, 0 for none
+  int act;                   // 1: FusedLeakyReLU on (acc + bias) before the residual
+  float out_scale;           // final multiplier (StyleGAN2 ResBlock: 1/sqrt(2))
+  int wide;                  // W > 128: a tile is 128 consecutive pixels of one row (tiles_x per row)
   int box16;                 // tile geometry: 0 linear, 1 = 8 rows x 16 columns (W >= 32 with pooling)
   int bh, tiles_y, bn;       // linear: tile = bn images x bh rows x W columns; box16: tiles_y x tiles_x tiles per image
   int tiles_x;
@@ -88,11 +92,11 @@ __device__ __forceinline__ void tc_k_iter(const TcParams& p, int it, int main_it
     if (p.cs == 2) { dy = st >> 1; dx = st & 1; }
   } else if (p.tw == 3) {
     const int ty3 = (tap * 11) >> 5;            // tap / 3 for tap in 0..8
-    dy = ty3 - 1;
-    dx = tap - 3 * ty3 - 1;
+    dy = ty3 + p.toff;
+    dx = tap - 3 * ty3 + p.toff;
   } else if (p.tw == 4) {
-    dy = (tap >> 2) - 1;
-    dx = (tap & 3) - 1;
+    dy = (tap >> 2) + p.toff;
+    dx = (tap & 3) + p.toff;
   }
 }
 
@@ -105,6 +109,11 @@ __device__ __forceinline__ void tc_tile_origin(const TcParams& p, long long mt, 
     const int r = (int)(mt - (long long)n0 * per_img);
     y0 = (r / p.tiles_x) * 8;
     x0 = (r % p.tiles_x) * 16;
+  } else if (p.wide) {
+    const long long row = mt / p.tiles_x;
+    x0 = (int)(mt - row * p.tiles_x) * TC_BM;
+    y0 = (int)(row % p.H);
+    n0 = (int)(row / p.H);
   } else {
     n0 = (int)(mt / p.tiles_y) * p.bn;
     y0 = (int)(mt % p.tiles_y) * p.bh;
@@ -247,21 +256,6 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
           v[j] *= 0.25f;
         }
       }
-      if (lin && p.res_f32) {
-        // identity residual, coalesced: lane (g8, i8) loads float4 #i8 of rows g8*8 + m, then an in-register transpose
-        // brings every row's 32 values to the lane that owns the row
-        float t[32];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          const long long rp = wpix + g8 * 8 + m;
-          float4 ld = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rp < p.total_pixels) ld = *reinterpret_cast<const float4*>(p.res_f32 + rp * p.Cout + nt * BN + c0 + i8 * 4);
-          t[4 * m] = ld.x; t[4 * m + 1] = ld.y; t[4 * m + 2] = ld.z; t[4 * m + 3] = ld.w;
-        }
-        warp_transpose8_f4(t, lane);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += p.res_relu ? fmaxf(t[j], 0.f) : t[j];
-      }
       if (active) {
         const int cb = nt * BN + c0;
         // shared memory bandwidth is what bounds the MMA mainloop (operand fetch + TMA fill), so the epilogue
@@ -282,6 +276,31 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
           for (int j = 0; j < 32; ++j)
             v[j] = fmaf(w3[3 * j], px[0], fmaf(w3[3 * j + 1], px[1], fmaf(w3[3 * j + 2], px[2], v[j])));
         }
+        if (p.act) {                       // FusedLeakyReLU: leaky_relu(x + b, 0.2) * sqrt(2)  (op/fused_act.py:104-116)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (v[j] > 0.f ? v[j] : 0.2f * v[j]) * 1.4142135623730951f;
+        }
+      }
+      if (lin && p.res_f32) {
+        // residual (identity shortcut / StyleGAN2 skip branch), coalesced: lane (g8, i8) loads float4 #i8 of rows g8*8 + m, then an in-register transpose
+        // brings every row's 32 values to the lane that owns the row
+        float t[32];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const long long rp = wpix + g8 * 8 + m;
+          float4 ld = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rp < p.total_pixels) ld = *reinterpret_cast<const float4*>(p.res_f32 + rp * p.Cout + nt * BN + c0 + i8 * 4);
+          t[4 * m] = ld.x; t[4 * m + 1] = ld.y; t[4 * m + 2] = ld.z; t[4 * m + 3] = ld.w;
+        }
+        warp_transpose8_f4(t, lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += p.res_relu ? fmaxf(t[j], 0.f) : t[j];
+      }
+      if (p.out_scale != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+      }
+      if (active) {
         if (p.res_f32 && !lin) {
           const float4* rp = reinterpret_cast<const float4*>(p.res_f32 + obase + c0);
 #pragma unroll
@@ -715,10 +734,13 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   SDG_REQUIRE(g_encode, SDG_E_STATE, "conv_tc: conv_tc_init not called");
   const int H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout, taps = a.taps;
   const bool s2 = a.pool4 != 0;          // conv3x3 + avg_pool2d(2) evaluated as the equivalent 4x4 stride-2 conv
+  const bool strided = s2 || a.stride == 2;
   SDG_REQUIRE(taps == 9 || taps == 1, SDG_E_UNSUPPORTED, "conv_tc: taps=%d", taps);
   SDG_REQUIRE(!s2 || (taps == 9 && a.pool), SDG_E_INVALID, "conv_tc: pool4 needs a pooled 3x3 stage");
+  SDG_REQUIRE(a.stride == 1 || a.stride == 2, SDG_E_UNSUPPORTED, "conv_tc: stride=%d", a.stride);
+  SDG_REQUIRE(!(a.stride == 2 && a.pool), SDG_E_UNSUPPORTED, "conv_tc: strided conv with pooling");
   SDG_REQUIRE(Cin % TC_BK == 0 && Cout % 64 == 0 && Cout <= TC_MAX_COUT, SDG_E_UNSUPPORTED, "conv_tc: Cin=%d Cout=%d", Cin, Cout);
-  SDG_REQUIRE(W >= 4 && W <= 128 && (W & (W - 1)) == 0 && H == W, SDG_E_UNSUPPORTED, "conv_tc: H=%d W=%d", H, W);
+  SDG_REQUIRE(W >= 4 && W <= 512 && (W & (W - 1)) == 0 && H == W, SDG_E_UNSUPPORTED, "conv_tc: H=%d W=%d", H, W);
   SDG_REQUIRE(a.sc_C % TC_BK == 0, SDG_E_UNSUPPORTED, "conv_tc: shortcut channels %d", a.sc_C);
   SDG_REQUIRE((a.sc_C == 0) == (a.sc_in == nullptr), SDG_E_INVALID, "conv_tc: shortcut tensor / channels mismatch");
   SDG_REQUIRE(!a.img || (a.pool && a.sc_w3), SDG_E_INVALID, "conv_tc: image shortcut needs pooling and weights");
@@ -727,29 +749,43 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   SDG_REQUIRE(al16(a.in) && al16(a.wb) && al16(a.sc_in) && al16(a.res_f32) && al16(a.out_relu) && al16(a.out_raw) &&
                   al16(a.out_f32), SDG_E_INVALID, "conv_tc: pointers must be 16-byte aligned");
   if (a.n == 0) return 0;
-  // resolution of the GEMM's M space: the pooled output grid in the stride-2 form, else the conv's own grid
+  // H, W describe the GEMM's M grid for a stride-1 conv and for pool4 (where the grid is H/2 x W/2); for an explicit
+  // stride-2 conv they are the OUTPUT grid and in_H / in_W give the input tensor's extent
   const int Hc = s2 ? H / 2 : H, Wc = s2 ? W / 2 : W;
+  const int Hin = a.in_H ? a.in_H : H, Win = a.in_W ? a.in_W : W;
   TcParams p;
   p.H = Hc; p.W = Wc; p.Cin = Cin; p.Cout = Cout;
   p.taps = s2 ? 16 : taps;
   p.tw = s2 ? 4 : (taps == 9 ? 3 : 1);
-  p.cs = s2 ? 2 : 1;
+  p.cs = strided ? 2 : 1;
+  p.toff = a.no_pad ? 0 : -1;
+  p.act = a.act;
+  p.out_scale = a.out_scale;
   p.img_up = s2 ? 1 : 0;
   p.kchunks = Cin / TC_BK;
   p.sc_kchunks = a.sc_C / TC_BK;
   p.sc_chunks = (s2 ? 4 : 1) * p.sc_kchunks;
   p.pool = (a.pool && !s2) ? 1 : 0;
   p.box16 = (p.pool && W >= 32) ? 1 : 0;
+  p.wide = 0;
   p.tiles_x = 1;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
   p.n_tiles = Cout / BN;
   int bw = Wc, bh, bn;
   if (p.box16) {
+    SDG_REQUIRE(Wc <= 128, SDG_E_UNSUPPORTED, "conv_tc: pooled epilogue with W=%d", Wc);
     bw = 16; bh = 8; bn = 1;
     p.bh = 8; p.bn = 1;
     p.tiles_x = Wc / 16;
     p.tiles_y = Hc / 8;
     p.m_tiles = a.n * p.tiles_x * p.tiles_y;
+  } else if (Wc > TC_BM) {
+    p.wide = 1;
+    bw = TC_BM; bh = 1; bn = 1;
+    p.bh = 1; p.bn = 1;
+    p.tiles_x = Wc / TC_BM;
+    p.tiles_y = Hc;
+    p.m_tiles = a.n * (long long)Hc * p.tiles_x;
   } else {
     int rows = TC_BM / Wc;                      // grid rows per tile if one image is big enough
     if (rows >= Hc) { p.bh = Hc; p.bn = TC_BM / (Hc * Wc); } else { p.bh = rows; p.bn = 1; }
@@ -767,12 +803,12 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   p.total_pixels = a.n * Hc * Wc;
   p.bias = a.bias; p.res_f32 = a.res_f32; p.img = a.img; p.sc_w3 = a.sc_w3;
   p.out_relu = a.out_relu; p.out_raw = a.out_raw; p.out_f32 = a.out_f32;
-  const int es = s2 ? 2 : 1;                    // TMA traversal stride over input pixels
+  const int es = strided ? 2 : 1;               // TMA traversal stride over input pixels
 
   CUtensorMap map_a, map_b, map_s;
   const uint64_t k_cols = (uint64_t)p.taps * Cin + (uint64_t)p.sc_chunks * TC_BK;
-  { int rc = encode_act(&map_a, a.in, f16, a.n, H, W, Cin, bw, bh, bn, es); if (rc) return rc; }
-  if (a.sc_in) { int rc = encode_act(&map_s, a.sc_in, f16, a.n, H, W, a.sc_C, bw, bh, bn, es); if (rc) return rc; }
+  { int rc = encode_act(&map_a, a.in, f16, a.n, Hin, Win, Cin, bw, bh, bn, es); if (rc) return rc; }
+  if (a.sc_in) { int rc = encode_act(&map_s, a.sc_in, f16, a.n, Hin, Win, a.sc_C, bw, bh, bn, es); if (rc) return rc; }
   else map_s = map_a;
   { int rc = tc_encode_2d(&map_b, a.wb, f16, k_cols, Cout, TC_BK, BN); if (rc) return rc; }
 

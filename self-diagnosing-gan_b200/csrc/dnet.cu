@@ -92,6 +92,9 @@ struct sdg_ctx {
 
 static int64_t sg2_buf_elems(const sdg_ctx* c);
 static int forward_stylegan2_fp32(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s);
+static int forward_stylegan2_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s);
+static int sg2_ensure_h16(sdg_ctx* c, int64_t chunk);
+static int64_t sg2_h16_bytes_per_sample(const sdg_ctx* c);
 
 static int prof_begin(sdg_ctx* c, cudaStream_t s) {
   if (!c->profile) return 0;
@@ -491,18 +494,26 @@ extern "C" int sdg_d_forward(sdg_ctx* c, const void* x, int layout, int64_t n, f
     const int B = c->sg2_batch;
     SDG_REQUIRE(n % B == 0, SDG_E_INVALID, "sdg_d_forward: StyleGAN2 needs whole reference batches (minibatch-stddev): n=%lld "
                 "is not a multiple of batch %d; drop the ragged tail like the reference's drop_last=True", (long long)n, B);
+    const bool tc = c->precision != SDG_PREC_FP32;
     const int64_t el = sg2_buf_elems(c);
     int64_t chunk = c->chunk;
-    if (chunk <= 0) chunk = (3LL << 30) / (4 * el * 4 + (int64_t)S * S * 12);
+    if (chunk <= 0) chunk = tc ? (8LL << 30) / sg2_h16_bytes_per_sample(c) : (3LL << 30) / (4 * el * 4 + (int64_t)S * S * 12);
     chunk = std::max<int64_t>(B, chunk / B * B);
     if (chunk > n) chunk = n;
-    for (int i = 0; i < 4; ++i) { int rc = c->buf[i].ensure((size_t)chunk * el * 4); if (rc) return rc; }
-    { int rc = c->xin.ensure((size_t)chunk * S * S * 3 * 4); if (rc) return rc; }
+    if (tc) {
+      int rc = sg2_ensure_h16(c, chunk);
+      if (rc) return rc;
+    } else {
+      for (int i = 0; i < 4; ++i) { int rc = c->buf[i].ensure((size_t)chunk * el * 4); if (rc) return rc; }
+      { int rc = c->xin.ensure((size_t)chunk * S * S * 3 * 4); if (rc) return rc; }
+    }
     { int rc = c->sg2_sd.ensure(sizeof(float) * (size_t)chunk); if (rc) return rc; }
     const size_t in_stride = layout == SDG_LAYOUT_U8_NHWC ? (size_t)S * S * 3 : (size_t)S * S * 3 * 4;
     for (int64_t s0 = 0; s0 < n; s0 += chunk) {
       const int64_t nb = (n - s0) < chunk ? (n - s0) : chunk;
-      int rc = forward_stylegan2_fp32(c, (const char*)x + (size_t)s0 * in_stride, layout, nb, logits_out + s0, s);
+      const void* xs = (const char*)x + (size_t)s0 * in_stride;
+      int rc = tc ? forward_stylegan2_h16(c, xs, layout, nb, logits_out + s0, s)
+                  : forward_stylegan2_fp32(c, xs, layout, nb, logits_out + s0, s);
       if (rc) return rc;
     }
     return 0;
@@ -570,6 +581,32 @@ extern "C" int sdg_conv2d_h16(const void* in, const void* wb, const float* bias,
   return conv_tc(a, precision == SDG_PREC_FP16, (cudaStream_t)stream);
 }
 
+extern "C" int sdg_conv2d_sg2_h16(const void* in, const void* wb, const float* bias, int64_t n, int Hout, int Wout, int in_H,
+                                  int in_W, int Cin, int Cout, int ks, int stride, int pad, int act, const float* res_f32,
+                                  float out_scale, void* out_raw, float* out_f32, int precision, void* stream) {
+  SDG_REQUIRE(in && wb, SDG_E_INVALID, "sdg_conv2d_sg2_h16: null pointer");
+  SDG_REQUIRE(ks == 1 || ks == 3, SDG_E_UNSUPPORTED, "sdg_conv2d_sg2_h16: ks=%d", ks);
+  SDG_REQUIRE(precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID, "sdg_conv2d_sg2_h16: precision=%d",
+              precision);
+  int dev = 0;
+  SDG_CUDA(cudaGetDevice(&dev));
+  { int rc = conv_tc_init(dev); if (rc) return rc; }
+  TcConv a;
+  a.in = (const h16*)in; a.wb = (const h16*)wb; a.bias = bias; a.n = n; a.H = Hout; a.W = Wout; a.in_H = in_H; a.in_W = in_W;
+  a.Cin = Cin; a.Cout = Cout; a.taps = ks * ks; a.stride = stride; a.no_pad = pad ? 0 : 1; a.act = act;
+  a.res_f32 = res_f32; a.out_scale = out_scale; a.out_raw = (h16*)out_raw; a.out_f32 = out_f32;
+  return conv_tc(a, precision == SDG_PREC_FP16, (cudaStream_t)stream);
+}
+
+extern "C" int sdg_blur_h16(const void* in, void* out, int64_t n, int H, int W, int C, int pad, int stride, int precision,
+                            void* stream) {
+  SDG_REQUIRE(in && out, SDG_E_INVALID, "sdg_blur_h16: null pointer");
+  SDG_REQUIRE(precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID, "sdg_blur_h16: precision=%d", precision);
+  SDG_REQUIRE(C % 8 == 0 && (stride == 1 || stride == 2) && pad >= 0 && pad <= 3 && H + 2 * pad >= 4 && W + 2 * pad >= 4,
+              SDG_E_INVALID, "sdg_blur_h16: C=%d pad=%d stride=%d H=%d W=%d", C, pad, stride, H, W);
+  return blur_h16((const h16*)in, (h16*)out, n, H, W, C, pad, stride, precision == SDG_PREC_FP16, (cudaStream_t)stream);
+}
+
 extern "C" int sdg_first_conv_h16(const void* x, int layout, const void* wb, const float* bias, void* out, int64_t n,
                                   int S, int Cout, int precision, void* stream) {
   SDG_REQUIRE(x && wb && bias && out, SDG_E_INVALID, "sdg_first_conv_h16: null pointer");
@@ -608,7 +645,8 @@ extern "C" int sdg_ctx_set_batch(sdg_ctx* c, int batch) {
 
 extern "C" int sdg_stylegan2_load(sdg_ctx* c, int size, int n_tensors, const float* const* t, int precision, void* stream) {
   SDG_REQUIRE(c && t, SDG_E_INVALID, "sdg_stylegan2_load: null pointer");
-  SDG_REQUIRE(precision == SDG_PREC_FP32, SDG_E_UNSUPPORTED, "sdg_stylegan2_load: only SDG_PREC_FP32 is implemented");
+  SDG_REQUIRE(precision == SDG_PREC_FP32 || precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID,
+              "sdg_stylegan2_load: precision=%d", precision);
   SDG_REQUIRE(size >= 8 && size <= 1024 && (size & (size - 1)) == 0, SDG_E_INVALID, "sdg_stylegan2_load: size=%d", size);
   cudaStream_t s = (cudaStream_t)stream;
   SDG_CUDA(cudaSetDevice(c->device));
@@ -630,11 +668,24 @@ extern "C" int sdg_stylegan2_load(sdg_ctx* c, int size, int n_tensors, const flo
     for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); l.w3.release(); l.bias_sum.release(); }
     c->convs.assign(n_convs, ConvLayer());
   }
-  auto pack = [&](ConvLayer& l, const float* W, const float* b, int cout, int cin_, int ks) -> int {
+  const bool tc = precision != SDG_PREC_FP32;
+  if (tc) { int rc = conv_tc_init(c->device); if (rc) return rc; }
+  // equalised learning rate: the run-time scale 1/sqrt(Cin*k*k) (stylegan2.py:103,117) is folded into the packed weights.
+  // Tensor-core mode packs the ResBlock convs as 16-bit [Cout][tap*Cin + c]; the 3-channel first conv and the tail
+  // (513-channel conv on 4x4, the two EqualLinear: 0.1 % of the FLOPs) stay fp32.
+  auto pack = [&](ConvLayer& l, const float* W, const float* b, int cout, int cin_, int ks, bool h) -> int {
     l.cout = cout; l.cin = cin_; l.ks = ks; l.has_bias = b != nullptr;
-    { int rc = l.w32.ensure(sizeof(float) * (size_t)ks * ks * cin_ * cout); if (rc) return rc; }
-    { int rc = pack_conv_fp32(W, nullptr, nullptr, l.w32.as<float>(), cout, cin_, ks, s, 1.0f / sqrtf((float)cin_ * ks * ks));
-      if (rc) return rc; }
+    const float mul = 1.0f / sqrtf((float)cin_ * ks * ks);
+    if (h) {
+      l.kpad = l.ktot = ks * ks * cin_;
+      { int rc = l.w16.ensure(sizeof(h16) * (size_t)l.ktot * cout); if (rc) return rc; }
+      { int rc = pack_conv_h16(W, nullptr, nullptr, l.w16.as<h16>(), cout, cin_, l.kpad, ks, precision == SDG_PREC_FP16, l.ktot, 0,
+                               s, mul);
+        if (rc) return rc; }
+    } else {
+      { int rc = l.w32.ensure(sizeof(float) * (size_t)ks * ks * cin_ * cout); if (rc) return rc; }
+      { int rc = pack_conv_fp32(W, nullptr, nullptr, l.w32.as<float>(), cout, cin_, ks, s, mul); if (rc) return rc; }
+    }
     if (b) {
       { int rc = l.bias.ensure(sizeof(float) * cout); if (rc) return rc; }
       SDG_CUDA(cudaMemcpyAsync(l.bias.p, b, sizeof(float) * cout, cudaMemcpyDeviceToDevice, s));
@@ -643,14 +694,14 @@ extern "C" int sdg_stylegan2_load(sdg_ctx* c, int size, int n_tensors, const flo
   };
   int ti = 0, li = 0;
   const int c0 = sg2_channels(size);
-  { int rc = pack(c->convs[li++], t[ti], t[ti + 1], c0, 3, 1); if (rc) return rc; ti += 2; }
+  { int rc = pack(c->convs[li++], t[ti], t[ti + 1], c0, 3, 1, false); if (rc) return rc; ti += 2; }
   for (auto& b : c->sg2_blocks) {
-    { int rc = pack(c->convs[li++], t[ti], t[ti + 1], b.first, b.first, 3); if (rc) return rc; }
-    { int rc = pack(c->convs[li++], t[ti + 2], t[ti + 3], b.second, b.first, 3); if (rc) return rc; }
-    { int rc = pack(c->convs[li++], t[ti + 4], nullptr, b.second, b.first, 1); if (rc) return rc; }
+    { int rc = pack(c->convs[li++], t[ti], t[ti + 1], b.first, b.first, 3, tc); if (rc) return rc; }
+    { int rc = pack(c->convs[li++], t[ti + 2], t[ti + 3], b.second, b.first, 3, tc); if (rc) return rc; }
+    { int rc = pack(c->convs[li++], t[ti + 4], nullptr, b.second, b.first, 1, tc); if (rc) return rc; }
     ti += 5;
   }
-  { int rc = pack(c->convs[li++], t[ti], t[ti + 1], 512, 513, 3); if (rc) return rc; ti += 2; }
+  { int rc = pack(c->convs[li++], t[ti], t[ti + 1], 512, 513, 3, false); if (rc) return rc; ti += 2; }
   {
     ConvLayer& l = c->convs[li++];           // EqualLinear(8192, 512, fused_lrelu) as a 1x1 conv over the NHWC-flattened map
     l.cout = 512; l.cin = 8192; l.ks = 1; l.has_bias = true;
@@ -715,6 +766,106 @@ static int forward_stylegan2_fp32(sdg_ctx* c, const void* x, int layout, int64_t
   const ConvLayer& l0 = c->convs[li++];
   if ((rc = conv_fp32(D, l0.w32.as<float>(), l0.bias.as<float>(), C, nb, 1, 1, 8192, 512, 1, 1, ACT_NONE, ACT_LRELU_SQRT2, s, 0))) return rc;
   return head_dot_fp32(C, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, 512, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// StyleGAN2 discriminator, tensor-core path: ResBlock convs on tcgen05 (conv_tc.cu), activations NHWC 16-bit.
+//   conv1  = conv3x3 + FusedLeakyReLU                       -> one conv_tc launch (act in the epilogue)
+//   skip   = Blur(pad 1) + conv1x1 stride 2                 -> blur evaluated only at the even outputs, then a 1x1 conv (fp32 out)
+//   conv2  = Blur(pad 2) + conv3x3 stride 2 + FusedLeakyReLU -> blur, then ONE strided conv_tc launch whose epilogue also does
+//            (out + skip) / sqrt(2)  (stylegan2.py:611-614)
+// Per-sample scratch (elements): A, B = max hw^2*Cin; C = max (hw+1)^2*Cin; S = max (hw/2)^2*Cin; F = max (hw/2)^2*Cout fp32.
+struct Sg2Sizes { int64_t a, c, sd, f; };
+
+static Sg2Sizes sg2_h16_sizes(const sdg_ctx* c) {
+  Sg2Sizes z = {0, 0, 0, 0};
+  int hw = c->size;
+  for (auto& b : c->sg2_blocks) {
+    const int ho = hw / 2;
+    z.a = std::max<int64_t>(z.a, (int64_t)hw * hw * b.first);
+    z.a = std::max<int64_t>(z.a, (int64_t)ho * ho * b.second);
+    z.c = std::max<int64_t>(z.c, (int64_t)(hw + 1) * (hw + 1) * b.first);
+    z.sd = std::max<int64_t>(z.sd, (int64_t)ho * ho * b.first);
+    z.f = std::max<int64_t>(z.f, (int64_t)ho * ho * b.second);
+    hw = ho;
+  }
+  return z;
+}
+
+static constexpr int64_t kSg2TailFloats = 16 * 513 + 16 * 512 + 16 * 512 + 512;   // stddev-cat, block out, final conv, linear
+
+static int64_t sg2_h16_bytes_per_sample(const sdg_ctx* c) {
+  const Sg2Sizes z = sg2_h16_sizes(c);
+  return 2 * (2 * z.a + z.c + z.sd) + 4 * z.f + 4 * kSg2TailFloats;
+}
+
+static int sg2_ensure_h16(sdg_ctx* c, int64_t chunk) {
+  const Sg2Sizes z = sg2_h16_sizes(c);
+  int rc;
+  if ((rc = c->buf[0].ensure((size_t)chunk * z.a * 2))) return rc;
+  if ((rc = c->buf[1].ensure((size_t)chunk * z.a * 2))) return rc;
+  if ((rc = c->buf[2].ensure((size_t)chunk * z.c * 2))) return rc;
+  if ((rc = c->buf[3].ensure((size_t)chunk * z.sd * 2))) return rc;
+  if ((rc = c->buf[4].ensure((size_t)chunk * z.f * 4))) return rc;
+  if ((rc = c->buf[5].ensure((size_t)chunk * kSg2TailFloats * 4))) return rc;
+  return 0;
+}
+
+static int forward_stylegan2_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s) {
+  const int f16 = c->precision == SDG_PREC_FP16;
+  const int S = c->size;
+  h16* A = c->buf[0].as<h16>();
+  h16* B = c->buf[1].as<h16>();
+  h16* Cb = c->buf[2].as<h16>();
+  h16* Sd = c->buf[3].as<h16>();
+  float* F = c->buf[4].as<float>();
+  float* tail = c->buf[5].as<float>();
+  float* t_cat = tail;                               // [nb,16,513]
+  float* t_blk = t_cat + nb * 16 * 513;              // [nb,16,512] last ResBlock output, fp32
+  float* t_fc = t_blk + nb * 16 * 512;               // [nb,16,512]
+  float* t_lin = t_fc + nb * 16 * 512;               // [nb,512]
+  int rc, li = 0;
+  {
+    const ConvLayer& l = c->convs[li++];
+    if ((rc = sg2_first_conv_h16(x, layout, l.w32.as<float>(), l.bias.as<float>(), A, nb, S, l.cout, f16, s))) return rc;
+  }
+  int hw = S;
+  const size_t nblk = c->sg2_blocks.size();
+  for (size_t bi = 0; bi < nblk; ++bi) {
+    const auto& b = c->sg2_blocks[bi];
+    const ConvLayer& c1 = c->convs[li++];
+    const ConvLayer& c2 = c->convs[li++];
+    const ConvLayer& sk = c->convs[li++];
+    const int ho = hw / 2;
+    const bool last = bi + 1 == nblk;
+    TcConv a1;
+    a1.n = nb; a1.H = hw; a1.W = hw; a1.Cin = b.first; a1.Cout = b.first; a1.taps = 9;
+    a1.in = A; a1.wb = c1.w16.as<h16>(); a1.bias = c1.bias.as<float>(); a1.act = 1; a1.out_raw = B;
+    if (bi == 0 && (rc = prof_begin(c, s))) return rc;
+    if ((rc = conv_tc(a1, f16, s))) return rc;
+    if (bi == 0 && (rc = prof_end(c, s, 2.0 * (double)nb * hw * hw * b.first * 9.0 * b.first))) return rc;
+    if ((rc = blur_h16(A, Sd, nb, hw, hw, b.first, 1, 2, f16, s))) return rc;
+    TcConv as;
+    as.n = nb; as.H = ho; as.W = ho; as.Cin = b.first; as.Cout = b.second; as.taps = 1;
+    as.in = Sd; as.wb = sk.w16.as<h16>(); as.out_f32 = F;
+    if ((rc = conv_tc(as, f16, s))) return rc;
+    if ((rc = blur_h16(B, Cb, nb, hw, hw, b.first, 2, 1, f16, s))) return rc;
+    TcConv a2;
+    a2.n = nb; a2.H = ho; a2.W = ho; a2.in_H = hw + 1; a2.in_W = hw + 1; a2.stride = 2; a2.no_pad = 1;
+    a2.Cin = b.first; a2.Cout = b.second; a2.taps = 9;
+    a2.in = Cb; a2.wb = c2.w16.as<h16>(); a2.bias = c2.bias.as<float>(); a2.act = 1;
+    a2.res_f32 = F; a2.out_scale = 0.70710678118654752f;
+    if (last) a2.out_f32 = t_blk; else a2.out_raw = A;
+    if ((rc = conv_tc(a2, f16, s))) return rc;
+    hw = ho;
+  }
+  // tail in fp32: minibatch-stddev channel, final conv (513 -> 512 on 4x4), the two EqualLinear layers
+  if ((rc = minibatch_stddev_cat_fp32(t_blk, t_cat, c->sg2_sd.as<float>(), nb, c->sg2_batch, 16, 512, s))) return rc;
+  const ConvLayer& fc = c->convs[li++];
+  if ((rc = conv_fp32(t_cat, fc.w32.as<float>(), fc.bias.as<float>(), t_fc, nb, 4, 4, 513, 512, 3, 1, ACT_NONE, ACT_LRELU_SQRT2, s, 1))) return rc;
+  const ConvLayer& l0 = c->convs[li++];
+  if ((rc = conv_fp32(t_fc, l0.w32.as<float>(), l0.bias.as<float>(), t_lin, nb, 1, 1, 8192, 512, 1, 1, ACT_NONE, ACT_LRELU_SQRT2, s, 0))) return rc;
+  return head_dot_fp32(t_lin, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, 512, s);
 }
 
 extern "C" int sdg_set_conv_pair(int on) {

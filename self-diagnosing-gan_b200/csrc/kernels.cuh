@@ -50,6 +50,12 @@ int add_div_sqrt2_fp32(const float* a, const float* b, float* out, int64_t total
 // in [n,HW,C] -> out [n,HW,C+1]
 int minibatch_stddev_cat_fp32(const float* in, float* out, float* sd_scratch, int64_t n, int batch, int HW, int C,
                               cudaStream_t s);
+// 16-bit (tensor-core path) pieces: first 1x1 conv + FusedLeakyReLU from the image (w3 [3][C] fp32, scaled), Blur, widening
+int sg2_first_conv_h16(const void* x, int layout, const float* w3, const float* bias, h16* out, int64_t n, int S, int C, int f16,
+                       cudaStream_t s);
+// blur_h16: out extent = (H + 2*pad - 4) / stride + 1 (stride 2 = only the blur outputs a stride-2 1x1 conv reads)
+int blur_h16(const h16* in, h16* out, int64_t n, int H, int W, int C, int pad, int stride, int f16, cudaStream_t s);
+int widen_h16(const h16* in, float* out, int64_t total, int f16, cudaStream_t s);
 // wp[(p*C + c)*O + o] = W[o][c*HW + p] * mul    (EqualLinear on an NCHW-flattened feature map, activations kept NHWC)
 int pack_linear_nchw_fp32(const float* W, float mul, float* wp, int O, int C, int HW, cudaStream_t s);
 // out = (pool_a ? avgpool2(a) : a) + (pool_b ? avgpool2(relu_b ? relu(b) : b) : ...); b may be null
@@ -78,7 +84,7 @@ int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float
                    cudaStream_t s, float mul = 1.0f);
 // wb[o*ld + col0 + k] = h16(W[o][c][tap] * scale[o] / sigma) at k = tap*Cin + c, zero padded up to Kpad columns
 int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* wb, int Cout, int Cin, int Kpad,
-                  int ks, int f16, int ld, int col0, cudaStream_t s);
+                  int ks, int f16, int ld, int col0, cudaStream_t s, float mul = 1.0f);
 // pooled-3x3 weights for the 4x4 stride-2 form: wb[o*ld + (a*4+b)*Cin + c] = 0.25 * sum of W[o][c][ky][kx] / sigma over
 // ky in {a-1,a}, kx in {b-1,b} (valid taps); shortcut: wb[o*ld + col0 + t*sc_pad + c] = 0.25 * Wsc[o][c] / sigma_sc, t = 0..3
 int pack_pool4_h16(const float* W, const float* sigma, h16* wb, int Cout, int Cin, int f16, int ld, cudaStream_t s);
@@ -116,6 +122,11 @@ struct TcConv {
   int pool = 0;                   // avg_pool2d(., 2) of conv (+ shortcut conv) before the adds below
   int pool4 = 0;                  // with pool: run conv3x3 + avg_pool2d as the algebraically equal 4x4 stride-2 conv
                                   // (16/36 of the MACs); wb then holds 16 taps x Cin (+ 4 taps x sc_C), see pack_pool4_h16
+  int stride = 1;                 // 2: explicit stride-2 conv; H, W are then the OUTPUT grid and in_H, in_W the input extent
+  int in_H = 0, in_W = 0;
+  int no_pad = 0;                 // 1: taps start at the output pixel (padding 0) instead of one pixel before ("same")
+  int act = 0;                    // 1: FusedLeakyReLU on (acc + bias): leaky_relu(., 0.2) * sqrt(2), before the residual
+  float out_scale = 1.0f;         // final multiplier after the residual (StyleGAN2 ResBlock: 1/sqrt(2))
   const float* res_f32 = nullptr; // identity shortcut [n,Ho,Wo,Cout] fp32
   int res_relu = 0;               // rectify the identity shortcut (mimicry's in-place ReLU aliasing)
   const void* img = nullptr;      // network input (DBlockOptimized: shortcut = Wsc3 . avg_pool2d(img) at pooled res)

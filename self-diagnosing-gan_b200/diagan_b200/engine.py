@@ -159,7 +159,7 @@ class DiscriminatorEngine:
         self.arch, self.size, self.n_layers = "dcgan32", 32, 7
         return self
 
-    def load_stylegan2(self, state_dict, precision: str = "fp32", batch: int = 4):
+    def load_stylegan2(self, state_dict, precision: str = "fp16", batch: int = 4):
         """The reference's StyleGANDiscriminator (any power-of-two size).  ``batch`` = the loader batch size the
         reference would use: minibatch-stddev groups are formed inside consecutive batches of that size."""
         size, keys = stylegan2_tensor_keys(state_dict)
@@ -181,7 +181,7 @@ class DiscriminatorEngine:
         if kind == "dcgan32":
             return self.load_dcgan(state_dict, precision or "fp32")
         if kind == "stylegan2":
-            return self.load_stylegan2(state_dict, "fp32")
+            return self.load_stylegan2(state_dict, precision or "fp16")
         return self.load_sngan(state_dict, int(kind[5:]), precision or "fp16", inplace_relu)
 
     def sigmas(self) -> torch.Tensor:

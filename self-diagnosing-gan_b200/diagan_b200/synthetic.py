@@ -50,6 +50,46 @@ def sngan_state_dict(arch: int, seed: int = 1) -> dict:
     return sd
 
 
+_SG2_CHANNELS = {4: 512, 8: 512, 16: 512, 32: 512, 64: 512, 128: 256, 256: 128, 512: 64, 1024: 32}
+
+
+def stylegan2_state_dict(size: int, seed: int = 1) -> dict:
+    """Random-init StyleGANDiscriminator(size) state_dict with the reference's key names (diagan/models/stylegan2.py:
+    619-657): N(0,1) weights (equalised learning rate scales them at run time), small non-zero biases."""
+    rng = np.random.RandomState(seed)
+    r = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32))
+    sd = {"convs.0.0.weight": r(_SG2_CHANNELS[size], 3, 1, 1), "convs.0.1.bias": 0.1 * r(_SG2_CHANNELS[size])}
+    cin, res, i = _SG2_CHANNELS[size], size, 1
+    while res > 4:
+        cout = _SG2_CHANNELS[res // 2]
+        sd[f"convs.{i}.conv1.0.weight"] = r(cin, cin, 3, 3)
+        sd[f"convs.{i}.conv1.1.bias"] = 0.1 * r(cin)
+        sd[f"convs.{i}.conv2.1.weight"] = r(cout, cin, 3, 3)
+        sd[f"convs.{i}.conv2.2.bias"] = 0.1 * r(cout)
+        sd[f"convs.{i}.skip.1.weight"] = r(cout, cin, 1, 1)
+        cin, res, i = cout, res // 2, i + 1
+    sd["final_conv.0.weight"] = r(512, 513, 3, 3)
+    sd["final_conv.1.bias"] = 0.1 * r(512)
+    sd["final_linear.0.weight"] = r(512, 8192)
+    sd["final_linear.0.bias"] = 0.1 * r(512)
+    sd["final_linear.1.weight"] = r(1, 512)
+    sd["final_linear.1.bias"] = 0.1 * r(1)
+    return sd
+
+
+def stylegan2_flops(size: int) -> float:
+    """2 x MAC per sample of StyleGANDiscriminator(size) in the reference formulation (convs + linears; the blur FIRs,
+    ~0.6 % more, are not counted: SURVEY 8(a) appendix)."""
+    mac = size * size * 3 * _SG2_CHANNELS[size]
+    cin, res = _SG2_CHANNELS[size], size
+    while res > 4:
+        cout = _SG2_CHANNELS[res // 2]
+        mac += res * res * cin * cin * 9 + (res // 2) ** 2 * cout * cin * 10
+        cin, res = cout, res // 2
+    mac += 16 * 512 * 513 * 9 + 8192 * 512 + 512
+    return 2.0 * mac
+
+
 def perturb_(state_dict: dict, step: int, scale: float = 1e-3, device=None) -> dict:
     """W += scale * randn(seed = step): a deterministic stand-in for the training between two recording
     passes, so that per-sample logits move and std > 0."""

@@ -98,7 +98,7 @@ class LogitRecorder:
         sd = netD.state_dict() if hasattr(netD, "state_dict") else netD
         kind = engine.detect_arch(sd)
         if kind == "stylegan2":
-            self.engine.load_stylegan2(sd, "fp32", batch=self.batch)
+            self.engine.load_stylegan2(sd, self.precision, batch=self.batch)
         else:
             self.engine.load(sd, self.precision if kind != "dcgan32" else "fp32", self.inplace_relu)
 

@@ -20,12 +20,14 @@ Tolerances (BASELINE.json north_star / BASELINE.md section 4):
   * DRS: acceptance decisions identical under the same psi except where |p - psi| < 1e-5 (fp32
     exp/log differ from NumPy's in the last ulp), running maximum identical.
 """
+import math
 import os
 import pickle
 
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
@@ -329,7 +331,7 @@ def test_stylegan2_fp32_vs_reference_golden(golden_dir, size, dev):
     g = _load(golden_dir, f"stylegan2_d{size}")
     batch = int(g["batch"])
     params = sg2_oracle.init_params(size, int(g["param_seed"]))
-    eng = engine.DiscriminatorEngine(dev).load_stylegan2(params, batch=batch)
+    eng = engine.DiscriminatorEngine(dev).load_stylegan2(params, "fp32", batch=batch)
     assert eng.arch == "stylegan2" and eng.size == size
     x = torch.from_numpy(g["x_u8"]).to(dev)
     y = eng.forward(x).cpu().numpy()
@@ -541,6 +543,118 @@ def test_sngan_tensorcore_vs_oracle(arch, n, seed, inplace, prec, tol, dev):
 
 
 # ---------------------------------------------------------------------------------------------------
+# StyleGAN2 discriminator on the tensor-core path (BASELINE config 5)
+# ---------------------------------------------------------------------------------------------------
+def _sg2_conv(dev, n, hin, cin, cout, ks, stride, pad, act, res, prec, seed):
+    """One ConvLayer stage through sdg_conv2d_sg2_h16 vs torch fp32 on the same 16-bit-rounded operands."""
+    import ctypes as C
+    from diagan_b200 import _lib
+    from diagan_b200._lib import check, ptr, stream_ptr
+    lib = _lib.load()
+    dt = _tdt(prec)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, cin, hin, hin, generator=g).to(dt)
+    w = (torch.randn(cout, cin, ks, ks, generator=g) / math.sqrt(cin * ks * ks)).to(dt)
+    b = 0.1 * torch.randn(cout, generator=g)
+    y = F.conv2d(x.float(), w.float(), stride=stride, padding=(ks // 2 if pad else 0))
+    ho = y.shape[-1]
+    r = torch.randn(n, cout, ho, ho, generator=g) if res else None
+    y = y + b.view(1, -1, 1, 1)
+    if act:
+        y = F.leaky_relu(y, 0.2) * math.sqrt(2.0)
+    scale = 1.0 / math.sqrt(2.0) if res else 1.0
+    if res:
+        y = (y + r) * scale
+    xd = x.permute(0, 2, 3, 1).contiguous().to(dev)
+    wd = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(dev)
+    bd = b.to(dev)
+    rd = r.permute(0, 2, 3, 1).contiguous().to(dev) if res else None
+    o16 = torch.empty(n, ho, ho, cout, dtype=dt, device=dev)
+    o32 = torch.empty(n, ho, ho, cout, dtype=torch.float32, device=dev)
+    pc = {"fp16": _lib.PREC_FP16, "bf16": _lib.PREC_BF16}[prec]
+    check(lib.sdg_conv2d_sg2_h16(ptr(xd), ptr(wd), ptr(bd), n, ho, ho, hin, hin, cin, cout, ks, stride, 1 if pad else 0,
+                                 1 if act else 0, ptr(rd), C.c_float(scale), ptr(o16), ptr(o32), pc, stream_ptr(dev)),
+          "sdg_conv2d_sg2_h16")
+    torch.cuda.synchronize()
+    want = y.permute(0, 2, 3, 1)
+    e32 = (o32.cpu() - want).abs().max().item()
+    e16 = (o16.float().cpu() - want).abs().max().item()
+    return e32, e16, want.abs().max().item()
+
+
+@pytest.mark.parametrize("tag,n,hin,cin,cout,ks,stride,pad,act,res", [
+    ("conv1_256_wide_pair", 1, 256, 128, 128, 3, 1, 1, 1, False),     # 256-pixel rows: two tiles per row, CTA-pair kernel
+    ("conv1_64", 2, 64, 256, 256, 3, 1, 1, 1, False),
+    ("conv1_4", 9, 4, 512, 512, 3, 1, 1, 1, False),
+    ("conv2_s2_from_257", 1, 257, 128, 256, 3, 2, 0, 1, True),        # blurred (hw+1)^2 input, stride 2, no padding, + skip
+    ("conv2_s2_from_33", 3, 33, 512, 512, 3, 2, 0, 1, True),
+    ("conv2_s2_from_9", 5, 9, 512, 512, 3, 2, 0, 1, True),
+    ("skip_1x1", 3, 16, 256, 512, 1, 1, 0, 0, False),
+])
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_stylegan2_conv_stage_vs_torch(tag, n, hin, cin, cout, ks, stride, pad, act, res, prec, dev):
+    e32, e16, mag = _sg2_conv(dev, n, hin, cin, cout, ks, stride, pad, act, res, prec, seed=len(tag))
+    print(f"{tag} {prec}: fp32-out err {e32:.2e}, 16-bit-out err {e16:.2e}, |y|max {mag:.2f}")
+    # operands are identical 16-bit values on both sides: only the accumulation order (fp32) and the output rounding differ
+    assert e32 <= 2e-4 * max(1.0, mag)
+    assert e16 <= mag * (2.0 ** -10 if prec == "fp16" else 2.0 ** -7) + 2e-4
+
+
+@pytest.mark.parametrize("H,C,pad,stride,n", [(16, 64, 2, 1, 3), (16, 64, 1, 2, 3), (8, 512, 2, 1, 2), (256, 128, 1, 2, 1),
+                                              (4, 512, 2, 1, 5)])
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_blur_h16_vs_upfirdn2d_oracle(H, C, pad, stride, n, prec, dev):
+    from diagan_b200 import _lib
+    from diagan_b200._lib import check, ptr, stream_ptr
+    from oracle import stylegan2 as sg2_oracle
+    lib = _lib.load()
+    dt = _tdt(prec)
+    x = torch.randn(n, C, H, H, generator=torch.Generator().manual_seed(H + C)).to(dt)
+    want = sg2_oracle.blur(x.float(), pad, pad)[:, :, ::stride, ::stride].permute(0, 2, 3, 1)
+    ho = want.shape[1]
+    out = torch.empty(n, ho, ho, C, dtype=dt, device=dev)
+    pc = {"fp16": _lib.PREC_FP16, "bf16": _lib.PREC_BF16}[prec]
+    check(lib.sdg_blur_h16(ptr(x.permute(0, 2, 3, 1).contiguous().to(dev)), ptr(out), n, H, H, C, pad, stride, pc,
+                           stream_ptr(dev)), "sdg_blur_h16")
+    err = (out.float().cpu() - want).abs().max().item()
+    assert err <= want.abs().max().item() * (2.0 ** -10 if prec == "fp16" else 2.0 ** -7)
+
+
+@pytest.mark.parametrize("size", [32, 128])
+@pytest.mark.parametrize("prec,tol", [("fp16", 1e-3), ("bf16", 1.5e-2)])
+def test_stylegan2_tensorcore_vs_reference_golden(golden_dir, size, prec, tol, dev):
+    """The tcgen05 StyleGAN2 discriminator against logits of the reference module itself (golden fixture) and the
+    float64 oracle; yardstick = the fp32 oracle network in torch eager with TF32 convolutions on this GPU."""
+    from diagan_b200 import engine
+    from oracle import stylegan2 as sg2_oracle
+    g = _load(golden_dir, f"stylegan2_d{size}")
+    batch = int(g["batch"])
+    params = sg2_oracle.init_params(size, int(g["param_seed"]))
+    x = torch.from_numpy(g["x_u8"])
+    eng = engine.DiscriminatorEngine(dev).load_stylegan2(params, prec, batch=batch)
+    got = eng.forward(x.to(dev)).cpu().numpy()
+    want = sg2_oracle.logits_pass(params, x, size, batch, dtype=torch.float64)
+    emax, emean = _logit_close(got, want)
+    egold = _logit_close(got, g["logits"])[0]
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    pd = {k: v.to(dev) for k, v in params.items()}
+    ytf = np.zeros(x.shape[0])
+    with torch.no_grad():
+        for s0 in range(0, x.shape[0], batch):
+            ytf[s0:s0 + batch] = sg2_oracle.forward(pd, sngan_oracle.normalise_u8(x[s0:s0 + batch]).to(dev), size).view(-1).cpu().numpy()
+    etf = _logit_close(ytf, want)[0]
+    print(f"stylegan2 D{size} {prec}: vs float64 oracle max rel {emax:.2e} mean {emean:.2e}; vs reference golden {egold:.2e} | "
+          f"torch-eager TF32 on this GPU: {etf:.2e} (logit mean {want.mean():.4f} std {want.std():.4f})")
+    assert emax <= tol or emax <= (1.5 if prec == "fp16" else 24.0) * etf
+    xf = sngan_oracle.normalise_u8(x).contiguous().to(dev)
+    assert np.array_equal(eng.forward(xf).cpu().numpy(), got)
+    if x.shape[0] > batch:
+        eng.set_chunk(batch)
+        assert np.array_equal(eng.forward(x.to(dev)).cpu().numpy(), got)
+
+
+# ---------------------------------------------------------------------------------------------------
 # the recorder end to end: pass -> snapshots -> pickle -> calculate_scores -> weights
 # ---------------------------------------------------------------------------------------------------
 def test_recorder_end_to_end(tmp_path, dev):
@@ -618,7 +732,7 @@ def test_recorder_stylegan2_drop_last(golden_dir, dev):
     g = _load(golden_dir, "stylegan2_d32")
     params = sg2_oracle.init_params(32, int(g["param_seed"]))
     x = torch.from_numpy(g["x_u8"][:13])                        # 13 samples, batch 8 -> one batch + 5 dropped
-    rec = LogitRecorder(ResidentDataset(x.to(dev)), dev, batch=8)
+    rec = LogitRecorder(ResidentDataset(x.to(dev)), dev, precision="fp32", batch=8)
     snap = rec.record(params).cpu().numpy()
     assert _logit_close(snap[:8], g["logits"][:8])[0] <= 1e-5
     assert np.all(snap[8:] == 0.0)

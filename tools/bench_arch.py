@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--chunk", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     eng = engine.DiscriminatorEngine(dev)
@@ -32,15 +33,16 @@ def main():
         eng.load_sngan(synthetic.sngan_state_dict(size, 1), size, a.precision, True)
         flop = FLOP[a.arch]
     elif a.arch == "dcgan32":
-        from oracle import dcgan
+        from oracle import dcgan          # tool only: random-init parameters with the reference's key names
         size = 32
         eng.load_dcgan(dcgan.init_params(1))
         flop = FLOP[a.arch]
     else:
-        from oracle import stylegan2
         size = a.size
-        eng.load_stylegan2(stylegan2.init_params(size, 1), batch=a.batch)
-        flop = None
+        eng.load_stylegan2(synthetic.stylegan2_state_dict(size, 1), a.precision, batch=a.batch)
+        flop = synthetic.stylegan2_flops(size)
+    if a.chunk:
+        eng.set_chunk(a.chunk)
     x = synthetic.uniform_images_u8(a.n, size, seed=1).to(dev)
     out = torch.empty(a.n, dtype=torch.float32, device=dev)
     for _ in range(2):
@@ -55,7 +57,7 @@ def main():
     ms = e0.elapsed_time(e1) / a.iters
     rate = a.n / ms * 1e3
     extra = f", {rate * flop / 1e12:.1f} TFLOP/s (reference-formulation FLOPs)" if flop else ""
-    print(f"{a.arch} size={size} n={a.n} {a.precision if a.arch.startswith('sngan') else 'fp32'}: {ms:.2f} ms/pass, "
+    print(f"{a.arch} size={size} n={a.n} {a.precision if a.arch != 'dcgan32' else 'fp32'}: {ms:.2f} ms/pass, "
           f"{rate:,.0f} samples/s{extra}")
 
 
