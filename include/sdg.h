@@ -136,12 +136,15 @@ SDG_API int sdg_conv2d_h16(const void* in, const void* wb, const float* bias, in
  * for kernel-level parity tests).  Replaces ConvLayer / ResBlock.forward pieces (stylegan2.py:553-616):
  *   v = F.conv2d(in, W * scale, stride = stride, padding = pad ? ks/2 : 0)          ks in {1,3}, stride in {1,2}
  *   [v = leaky_relu(v + bias, 0.2) * sqrt(2)     act != 0: FusedLeakyReLU (op/fused_act.py:104-116); else v += bias]
+ *   [v += F.conv2d(skip_in, Wskip)               skip_in [n,Hout,Wout,skip_C] 16-bit at OUTPUT resolution (the blurred,
+ *                                                decimated block input); Wskip = the last skip_C columns of wb; runs as extra
+ *                                                K iterations into a second TMEM accumulator, added after the activation]
  *   [v += res_f32]  v *= out_scale               ResBlock: (out + skip) / sqrt(2)
- * in [n,in_H,in_W,Cin] NHWC 16-bit; outputs [n,Hout,Wout,Cout] (Hout == Wout a power of two in 4..512); wb [Cout, ks*ks*Cin]
- * 16-bit with the equalised-lr scale folded in; out_raw 16-bit and/or out_f32. */
+ * in [n,in_H,in_W,Cin] NHWC 16-bit; outputs [n,Hout,Wout,Cout] (Hout == Wout a power of two in 4..512); wb
+ * [Cout, ks*ks*Cin + skip_C] 16-bit with the equalised-lr scales folded in; out_raw 16-bit and/or out_f32. */
 SDG_API int sdg_conv2d_sg2_h16(const void* in, const void* wb, const float* bias, int64_t n, int Hout, int Wout, int in_H,
-                       int in_W, int Cin, int Cout, int ks, int stride, int pad, int act, const float* res_f32,
-                       float out_scale, void* out_raw, float* out_f32, int precision, void* stream);
+                       int in_W, int Cin, int Cout, int ks, int stride, int pad, int act, const void* skip_in, int skip_C,
+                       const float* res_f32, float out_scale, void* out_raw, float* out_f32, int precision, void* stream);
 /* Blur (stylegan2.py:75-90 = upfirdn2d with outer([1,3,3,1])/64, zero padding `pad` on every side) on 16-bit NHWC;
  * out extent (H + 2*pad - 4) / stride + 1: stride 2 evaluates only the outputs a following stride-2 1x1 conv reads. */
 SDG_API int sdg_blur_h16(const void* in, void* out, int64_t n, int H, int W, int C, int pad, int stride, int precision,

@@ -48,6 +48,8 @@ struct TcParams {
   int act;                   // 1: FusedLeakyReLU on (acc + bias) before the residual
   float out_scale;           // final multiplier (StyleGAN2 ResBlock: 1/sqrt(2))
   int wide;                  // W > 128: a tile is 128 consecutive pixels of one row (tiles_x per row)
+  int sc_sep;                // the shortcut K iterations read an OUTPUT-resolution tensor and accumulate into a second TMEM
+                             // accumulator that is added AFTER the activation (StyleGAN2 ResBlock skip branch)
   int box16;                 // tile geometry: 0 linear, 1 = 8 rows x 16 columns (W >= 32 with pooling)
   int bh, tiles_y, bn;       // linear: tile = bn images x bh rows x W columns; box16: tiles_y x tiles_x tiles per image
   int tiles_x;
@@ -61,6 +63,8 @@ struct TcParams {
   long long m_tiles;
   long long total_pixels;
   const float* bias;         // [Cout] (shortcut bias already added)
+  const float* sd;           // per-sample scalar of a spatially constant extra input channel (minibatch-stddev) or null
+  const float* sd_w;         // its summed weights [H*W][Cout]
   const float* res_f32;      // identity shortcut, fp32 [out pixels][Cout] or null
   const void* img;           // network input for the 3-FMA shortcut (DBlockOptimized) or null
   const float* sc_w3;        // [Cout][3] fp32, W_sc / sigma
@@ -89,7 +93,7 @@ __device__ __forceinline__ void tc_k_iter(const TcParams& p, int it, int main_it
     const int j = it - main_iters;
     const int st = j / p.sc_kchunks;
     ch = j - st * p.sc_kchunks;
-    if (p.cs == 2) { dy = st >> 1; dx = st & 1; }
+    if (p.cs == 2 && !p.sc_sep) { dy = st >> 1; dx = st & 1; }
   } else if (p.tw == 3) {
     const int ty3 = (tap * 11) >> 5;            // tap / 3 for tap in 0..8
     dy = ty3 + p.toff;
@@ -201,7 +205,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
   {
     // this thread's pixel (n, y, x)
     long long n;
-    int y, x;
+    int y, x, r_img = 0;
     bool valid;
     if (p.box16) {
       const int per_img = p.tiles_x * p.tiles_y;
@@ -214,6 +218,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
       const long long pix = mt * TC_BM + q * 32 + lane;    // 128 consecutive NHW pixels
       n = pix / HW;
       const int r = (int)(pix - n * HW);
+      r_img = r;
       y = r / p.W;
       x = r - y * p.W;
       valid = pix < p.total_pixels;
@@ -276,10 +281,27 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
           for (int j = 0; j < 32; ++j)
             v[j] = fmaf(w3[3 * j], px[0], fmaf(w3[3 * j + 1], px[1], fmaf(w3[3 * j + 2], px[2], v[j])));
         }
+        if (p.sd) {                        // spatially constant extra channel: sd[n] * (sum of its in-bounds tap weights)
+          const float sdv = p.sd[n];
+          const float4* ws = reinterpret_cast<const float4*>(p.sd_w + (long long)r_img * p.Cout + cb);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t = ws[g];
+            v[4 * g] = fmaf(sdv, t.x, v[4 * g]); v[4 * g + 1] = fmaf(sdv, t.y, v[4 * g + 1]);
+            v[4 * g + 2] = fmaf(sdv, t.z, v[4 * g + 2]); v[4 * g + 3] = fmaf(sdv, t.w, v[4 * g + 3]);
+          }
+        }
         if (p.act) {                       // FusedLeakyReLU: leaky_relu(x + b, 0.2) * sqrt(2)  (op/fused_act.py:104-116)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = (v[j] > 0.f ? v[j] : 0.2f * v[j]) * 1.4142135623730951f;
         }
+      }
+      if (p.sc_sep) {                      // skip branch accumulated beside the main conv (warp-collective TMEM load)
+        uint32_t r2[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r2[j]);
       }
       if (lin && p.res_f32) {
         // residual (identity shortcut / StyleGAN2 skip branch), coalesced: lane (g8, i8) loads float4 #i8 of rows g8*8 + m, then an in-register transpose
@@ -410,7 +432,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(&tmem_base_slot), TC_TMEM_COLS);
+  const uint32_t tmem_cols = p.sc_sep ? 2 * TC_TMEM_COLS : TC_TMEM_COLS;
+  const uint32_t acc_stride = p.sc_sep ? 2 * BN : BN;      // TMEM columns per accumulator stage
+  if (warp == 2) tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -440,7 +464,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t full = smem_u32(&bar_full[stage]);
           mbar_expect_tx(full, STAGE_BYTES);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-          tma_load_4d(a_dst, am, full, ch * TC_BK, p.cs * x0 + dx, p.cs * y0 + dy, n0);
+          const int cs = (is_sc && p.sc_sep) ? 1 : p.cs;
+          tma_load_4d(a_dst, am, full, ch * TC_BK, cs * x0 + dx, cs * y0 + dy, n0);
           tma_load_2d(a_dst + TC_A_BYTES, &map_b, full, it * TC_BK, nt * BN);
           if (++kc == p.kchunks) { kc = 0; ++tap; }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
@@ -459,17 +484,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
         mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_main = tmem_base + (uint32_t)acc * acc_stride;
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
           const uint64_t adesc = make_sw128_desc(a_addr);
           const uint64_t bdesc = make_sw128_desc(a_addr + TC_A_BYTES);
+          // separate-accumulator shortcut: its K iterations start a fresh accumulation BN columns further
+          const bool sep = p.sc_sep && it >= main_iters;
+          const uint32_t d_tmem = sep ? d_main + BN : d_main;
+          const int it0 = sep ? it - main_iters : it;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 elements = 32 B inside the swizzle row: +2 in the 16-byte-unit address field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it0 | k) != 0 ? 1u : 0u);
           }
           umma_commit(smem_u32(&bar_empty[stage]));       // frees the smem stage when these MMAs retire
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
@@ -486,7 +515,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const long long mt = tile / p.n_tiles;
       const int acc = (int)(local & 1);
       const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
-      tc_epilogue_tile<BN, F16>(p, s_bias, s_w3, tmem_base + (uint32_t)(acc * BN), mt, nt, q, lane,
+      tc_epilogue_tile<BN, F16>(p, s_bias, s_w3, tmem_base + (uint32_t)acc * acc_stride, mt, nt, q, lane,
                                 smem_u32(&bar_acc_full[acc]), acc_phase);
       tc_fence_before();
       __syncwarp();
@@ -498,7 +527,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -740,7 +769,15 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   SDG_REQUIRE(a.stride == 1 || a.stride == 2, SDG_E_UNSUPPORTED, "conv_tc: stride=%d", a.stride);
   SDG_REQUIRE(!(a.stride == 2 && a.pool), SDG_E_UNSUPPORTED, "conv_tc: strided conv with pooling");
   SDG_REQUIRE(Cin % TC_BK == 0 && Cout % 64 == 0 && Cout <= TC_MAX_COUT, SDG_E_UNSUPPORTED, "conv_tc: Cin=%d Cout=%d", Cin, Cout);
-  SDG_REQUIRE(W >= 4 && W <= 512 && (W & (W - 1)) == 0 && H == W, SDG_E_UNSUPPORTED, "conv_tc: H=%d W=%d", H, W);
+  if (a.gemm) {
+    SDG_REQUIRE(taps == 1 && H == 1 && W >= 1 && a.n == 1 && !a.pool && a.stride == 1 && !a.sc_in && !a.img && !a.sd, SDG_E_INVALID,
+                "conv_tc: gemm mode takes a [W rows][Cin] matrix (n = 1, H = 1, taps = 1) and no conv extras");
+  } else {
+    SDG_REQUIRE(W >= 4 && W <= 512 && (W & (W - 1)) == 0 && H == W, SDG_E_UNSUPPORTED, "conv_tc: H=%d W=%d", H, W);
+  }
+  SDG_REQUIRE(!a.sc_sep || (a.sc_in && !a.pool && !a.pool4 && Cout % 128 == 0), SDG_E_INVALID,
+              "conv_tc: separate-accumulator shortcut needs a shortcut tensor, no pooling and Cout %% 128 == 0");
+  SDG_REQUIRE((a.sd == nullptr) == (a.sd_w == nullptr) && (!a.sd || !a.pool), SDG_E_INVALID, "conv_tc: sd / sd_w mismatch");
   SDG_REQUIRE(a.sc_C % TC_BK == 0, SDG_E_UNSUPPORTED, "conv_tc: shortcut channels %d", a.sc_C);
   SDG_REQUIRE((a.sc_C == 0) == (a.sc_in == nullptr), SDG_E_INVALID, "conv_tc: shortcut tensor / channels mismatch");
   SDG_REQUIRE(!a.img || (a.pool && a.sc_w3), SDG_E_INVALID, "conv_tc: image shortcut needs pooling and weights");
@@ -768,6 +805,7 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   p.pool = (a.pool && !s2) ? 1 : 0;
   p.box16 = (p.pool && W >= 32) ? 1 : 0;
   p.wide = 0;
+  p.sc_sep = a.sc_sep;
   p.tiles_x = 1;
   const int BN = (Cout % 128 == 0) ? 128 : 64;
   p.n_tiles = Cout / BN;
@@ -779,11 +817,11 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
     p.tiles_x = Wc / 16;
     p.tiles_y = Hc / 8;
     p.m_tiles = a.n * p.tiles_x * p.tiles_y;
-  } else if (Wc > TC_BM) {
+  } else if (Wc > TC_BM || a.gemm) {
     p.wide = 1;
     bw = TC_BM; bh = 1; bn = 1;
     p.bh = 1; p.bn = 1;
-    p.tiles_x = Wc / TC_BM;
+    p.tiles_x = (int)cdiv(Wc, TC_BM);
     p.tiles_y = Hc;
     p.m_tiles = a.n * (long long)Hc * p.tiles_x;
   } else {
@@ -801,19 +839,20 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   p.debug_skip_epi = dbg_skip_epi;
   p.n_images = a.n;
   p.total_pixels = a.n * Hc * Wc;
-  p.bias = a.bias; p.res_f32 = a.res_f32; p.img = a.img; p.sc_w3 = a.sc_w3;
+  p.bias = a.bias; p.sd = a.sd; p.sd_w = a.sd_w; p.res_f32 = a.res_f32; p.img = a.img; p.sc_w3 = a.sc_w3;
   p.out_relu = a.out_relu; p.out_raw = a.out_raw; p.out_f32 = a.out_f32;
   const int es = strided ? 2 : 1;               // TMA traversal stride over input pixels
 
   CUtensorMap map_a, map_b, map_s;
   const uint64_t k_cols = (uint64_t)p.taps * Cin + (uint64_t)p.sc_chunks * TC_BK;
   { int rc = encode_act(&map_a, a.in, f16, a.n, Hin, Win, Cin, bw, bh, bn, es); if (rc) return rc; }
-  if (a.sc_in) { int rc = encode_act(&map_s, a.sc_in, f16, a.n, Hin, Win, a.sc_C, bw, bh, bn, es); if (rc) return rc; }
+  if (a.sc_in && a.sc_sep) { int rc = encode_act(&map_s, a.sc_in, f16, a.n, Hc, Wc, a.sc_C, bw, bh, bn, 1); if (rc) return rc; }
+  else if (a.sc_in) { int rc = encode_act(&map_s, a.sc_in, f16, a.n, Hin, Win, a.sc_C, bw, bh, bn, es); if (rc) return rc; }
   else map_s = map_a;
   { int rc = tc_encode_2d(&map_b, a.wb, f16, k_cols, Cout, TC_BK, BN); if (rc) return rc; }
 
   const int k_iters = p.taps * p.kchunks + p.sc_chunks;
-  if (g_pair_mode && Cout == 128 && taps == 9 && k_iters <= PAIR_MAX_KI && p.m_tiles >= 2) {
+  if (g_pair_mode && Cout == 128 && taps == 9 && k_iters <= PAIR_MAX_KI && p.m_tiles >= 2 && !p.sc_sep) {
     // CTA-pair kernel: weights resident (64 rows per CTA), A streamed through as many 16 KB stages as fit
     CUtensorMap map_bh;
     { int rc = tc_encode_2d(&map_bh, a.wb, f16, k_cols, Cout, TC_BK, 64); if (rc) return rc; }

@@ -582,8 +582,9 @@ extern "C" int sdg_conv2d_h16(const void* in, const void* wb, const float* bias,
 }
 
 extern "C" int sdg_conv2d_sg2_h16(const void* in, const void* wb, const float* bias, int64_t n, int Hout, int Wout, int in_H,
-                                  int in_W, int Cin, int Cout, int ks, int stride, int pad, int act, const float* res_f32,
-                                  float out_scale, void* out_raw, float* out_f32, int precision, void* stream) {
+                                  int in_W, int Cin, int Cout, int ks, int stride, int pad, int act, const void* skip_in,
+                                  int skip_C, const float* res_f32, float out_scale, void* out_raw, float* out_f32,
+                                  int precision, void* stream) {
   SDG_REQUIRE(in && wb, SDG_E_INVALID, "sdg_conv2d_sg2_h16: null pointer");
   SDG_REQUIRE(ks == 1 || ks == 3, SDG_E_UNSUPPORTED, "sdg_conv2d_sg2_h16: ks=%d", ks);
   SDG_REQUIRE(precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID, "sdg_conv2d_sg2_h16: precision=%d",
@@ -594,6 +595,7 @@ extern "C" int sdg_conv2d_sg2_h16(const void* in, const void* wb, const float* b
   TcConv a;
   a.in = (const h16*)in; a.wb = (const h16*)wb; a.bias = bias; a.n = n; a.H = Hout; a.W = Wout; a.in_H = in_H; a.in_W = in_W;
   a.Cin = Cin; a.Cout = Cout; a.taps = ks * ks; a.stride = stride; a.no_pad = pad ? 0 : 1; a.act = act;
+  a.sc_in = (const h16*)skip_in; a.sc_C = skip_C; a.sc_sep = skip_in ? 1 : 0;
   a.res_f32 = res_f32; a.out_scale = out_scale; a.out_raw = (h16*)out_raw; a.out_f32 = out_f32;
   return conv_tc(a, precision == SDG_PREC_FP16, (cudaStream_t)stream);
 }
@@ -697,12 +699,51 @@ extern "C" int sdg_stylegan2_load(sdg_ctx* c, int size, int n_tensors, const flo
   { int rc = pack(c->convs[li++], t[ti], t[ti + 1], c0, 3, 1, false); if (rc) return rc; ti += 2; }
   for (auto& b : c->sg2_blocks) {
     { int rc = pack(c->convs[li++], t[ti], t[ti + 1], b.first, b.first, 3, tc); if (rc) return rc; }
-    { int rc = pack(c->convs[li++], t[ti + 2], t[ti + 3], b.second, b.first, 3, tc); if (rc) return rc; }
-    { int rc = pack(c->convs[li++], t[ti + 4], nullptr, b.second, b.first, 1, tc); if (rc) return rc; }
+    if (tc) {
+      // conv2 and the skip conv share one launch: wb = [Cout][9*Cin (conv2 taps) | Cin (skip 1x1)], two accumulators
+      ConvLayer& l2 = c->convs[li++];
+      l2.cout = b.second; l2.cin = b.first; l2.ks = 3; l2.has_bias = true;
+      l2.kpad = 9 * b.first; l2.ktot = 10 * b.first;
+      const int f16 = precision == SDG_PREC_FP16;
+      { int rc = l2.w16.ensure(sizeof(h16) * (size_t)l2.ktot * l2.cout); if (rc) return rc; }
+      { int rc = pack_conv_h16(t[ti + 2], nullptr, nullptr, l2.w16.as<h16>(), l2.cout, l2.cin, l2.kpad, 3, f16, l2.ktot, 0, s,
+                               1.0f / sqrtf(9.f * b.first)); if (rc) return rc; }
+      { int rc = pack_conv_h16(t[ti + 4], nullptr, nullptr, l2.w16.as<h16>(), l2.cout, l2.cin, l2.cin, 1, f16, l2.ktot, l2.kpad, s,
+                               1.0f / sqrtf((float)b.first)); if (rc) return rc; }
+      { int rc = l2.bias.ensure(sizeof(float) * l2.cout); if (rc) return rc; }
+      SDG_CUDA(cudaMemcpyAsync(l2.bias.p, t[ti + 3], sizeof(float) * l2.cout, cudaMemcpyDeviceToDevice, s));
+      ConvLayer& lk = c->convs[li++];
+      lk.cout = b.second; lk.cin = b.first; lk.ks = 1; lk.has_bias = false;
+    } else {
+      { int rc = pack(c->convs[li++], t[ti + 2], t[ti + 3], b.second, b.first, 3, tc); if (rc) return rc; }
+      { int rc = pack(c->convs[li++], t[ti + 4], nullptr, b.second, b.first, 1, tc); if (rc) return rc; }
+    }
     ti += 5;
   }
-  { int rc = pack(c->convs[li++], t[ti], t[ti + 1], 512, 513, 3, false); if (rc) return rc; ti += 2; }
-  {
+  if (tc) {
+    // final_conv: the 512 feature channels on the tensor cores; the minibatch-stddev channel (input channel 512) is constant
+    // over the 4x4 map, so its contribution is sd[n] * (sum of its in-bounds tap weights): w3 holds that [16][512] table
+    ConvLayer& l = c->convs[li++];
+    const float mul = 1.0f / sqrtf(513.f * 9.f);
+    l.cout = 512; l.cin = 512; l.ks = 3; l.has_bias = true; l.kpad = l.ktot = 9 * 512;
+    { int rc = l.w16.ensure(sizeof(h16) * (size_t)l.ktot * 512); if (rc) return rc; }
+    { int rc = pack_conv_h16(t[ti], nullptr, nullptr, l.w16.as<h16>(), 512, 512, l.kpad, 3, precision == SDG_PREC_FP16, l.ktot, 0, s,
+                             mul, 513); if (rc) return rc; }
+    { int rc = l.w3.ensure(sizeof(float) * 16 * 512); if (rc) return rc; }
+    { int rc = pack_const_channel_fp32(t[ti], mul, l.w3.as<float>(), 512, 513, 512, 4, s); if (rc) return rc; }
+    { int rc = l.bias.ensure(sizeof(float) * 512); if (rc) return rc; }
+    SDG_CUDA(cudaMemcpyAsync(l.bias.p, t[ti + 1], sizeof(float) * 512, cudaMemcpyDeviceToDevice, s));
+    ti += 2;
+    ConvLayer& l0 = c->convs[li++];          // EqualLinear(8192, 512, fused_lrelu): a [n][8192] x [512][8192]^T GEMM
+    l0.cout = 512; l0.cin = 8192; l0.ks = 1; l0.has_bias = true; l0.kpad = l0.ktot = 8192;
+    { int rc = l0.w16.ensure(sizeof(h16) * 8192 * 512); if (rc) return rc; }
+    { int rc = pack_linear_nchw_h16(t[ti], 1.0f / sqrtf(8192.f), l0.w16.as<h16>(), 512, 512, 16, precision == SDG_PREC_FP16, s);
+      if (rc) return rc; }
+    { int rc = l0.bias.ensure(sizeof(float) * 512); if (rc) return rc; }
+    SDG_CUDA(cudaMemcpyAsync(l0.bias.p, t[ti + 1], sizeof(float) * 512, cudaMemcpyDeviceToDevice, s));
+    ti += 2;
+  } else {
+    { int rc = pack(c->convs[li++], t[ti], t[ti + 1], 512, 513, 3, false); if (rc) return rc; ti += 2; }
     ConvLayer& l = c->convs[li++];           // EqualLinear(8192, 512, fused_lrelu) as a 1x1 conv over the NHWC-flattened map
     l.cout = 512; l.cin = 8192; l.ks = 1; l.has_bias = true;
     { int rc = l.w32.ensure(sizeof(float) * 8192 * 512); if (rc) return rc; }
@@ -771,10 +812,11 @@ static int forward_stylegan2_fp32(sdg_ctx* c, const void* x, int layout, int64_t
 // ------------------------------------------------------------------------------------------------
 // StyleGAN2 discriminator, tensor-core path: ResBlock convs on tcgen05 (conv_tc.cu), activations NHWC 16-bit.
 //   conv1  = conv3x3 + FusedLeakyReLU                       -> one conv_tc launch (act in the epilogue)
-//   skip   = Blur(pad 1) + conv1x1 stride 2                 -> blur evaluated only at the even outputs, then a 1x1 conv (fp32 out)
-//   conv2  = Blur(pad 2) + conv3x3 stride 2 + FusedLeakyReLU -> blur, then ONE strided conv_tc launch whose epilogue also does
-//            (out + skip) / sqrt(2)  (stylegan2.py:611-614)
-// Per-sample scratch (elements): A, B = max hw^2*Cin; C = max (hw+1)^2*Cin; S = max (hw/2)^2*Cin; F = max (hw/2)^2*Cout fp32.
+//   skip   = Blur(pad 1) + conv1x1 stride 2                 -> blur evaluated only at the even outputs (16-bit, output resolution)
+//   conv2  = Blur(pad 2) + conv3x3 stride 2 + FusedLeakyReLU -> blur, then ONE strided conv_tc launch that also runs the skip's 1x1
+//            conv as extra K iterations into a second TMEM accumulator; epilogue: (flrelu(acc0 + b) + acc1) / sqrt(2)
+//            (stylegan2.py:611-614)
+// Per-sample scratch (elements): A, B = max hw^2*Cin; C = max (hw+1)^2*Cin; S = max (hw/2)^2*Cin.
 struct Sg2Sizes { int64_t a, c, sd, f; };
 
 static Sg2Sizes sg2_h16_sizes(const sdg_ctx* c) {
@@ -792,11 +834,11 @@ static Sg2Sizes sg2_h16_sizes(const sdg_ctx* c) {
   return z;
 }
 
-static constexpr int64_t kSg2TailFloats = 16 * 513 + 16 * 512 + 16 * 512 + 512;   // stddev-cat, block out, final conv, linear
+static constexpr int64_t kSg2TailFloats = 16 * 512 + 512;   // last block output (fp32), linear output
 
 static int64_t sg2_h16_bytes_per_sample(const sdg_ctx* c) {
   const Sg2Sizes z = sg2_h16_sizes(c);
-  return 2 * (2 * z.a + z.c + z.sd) + 4 * z.f + 4 * kSg2TailFloats;
+  return 2 * (2 * z.a + z.c + z.sd) + 4 * kSg2TailFloats;
 }
 
 static int sg2_ensure_h16(sdg_ctx* c, int64_t chunk) {
@@ -806,7 +848,6 @@ static int sg2_ensure_h16(sdg_ctx* c, int64_t chunk) {
   if ((rc = c->buf[1].ensure((size_t)chunk * z.a * 2))) return rc;
   if ((rc = c->buf[2].ensure((size_t)chunk * z.c * 2))) return rc;
   if ((rc = c->buf[3].ensure((size_t)chunk * z.sd * 2))) return rc;
-  if ((rc = c->buf[4].ensure((size_t)chunk * z.f * 4))) return rc;
   if ((rc = c->buf[5].ensure((size_t)chunk * kSg2TailFloats * 4))) return rc;
   return 0;
 }
@@ -818,12 +859,9 @@ static int forward_stylegan2_h16(sdg_ctx* c, const void* x, int layout, int64_t 
   h16* B = c->buf[1].as<h16>();
   h16* Cb = c->buf[2].as<h16>();
   h16* Sd = c->buf[3].as<h16>();
-  float* F = c->buf[4].as<float>();
   float* tail = c->buf[5].as<float>();
-  float* t_cat = tail;                               // [nb,16,513]
-  float* t_blk = t_cat + nb * 16 * 513;              // [nb,16,512] last ResBlock output, fp32
-  float* t_fc = t_blk + nb * 16 * 512;               // [nb,16,512]
-  float* t_lin = t_fc + nb * 16 * 512;               // [nb,512]
+  float* t_blk = tail;                               // [nb,16,512] last ResBlock output, fp32
+  float* t_lin = t_blk + nb * 16 * 512;              // [nb,512]
   int rc, li = 0;
   {
     const ConvLayer& l = c->convs[li++];
@@ -835,7 +873,7 @@ static int forward_stylegan2_h16(sdg_ctx* c, const void* x, int layout, int64_t 
     const auto& b = c->sg2_blocks[bi];
     const ConvLayer& c1 = c->convs[li++];
     const ConvLayer& c2 = c->convs[li++];
-    const ConvLayer& sk = c->convs[li++];
+    li++;                                   // the skip conv's weights live in conv2's K extension
     const int ho = hw / 2;
     const bool last = bi + 1 == nblk;
     TcConv a1;
@@ -845,26 +883,32 @@ static int forward_stylegan2_h16(sdg_ctx* c, const void* x, int layout, int64_t 
     if ((rc = conv_tc(a1, f16, s))) return rc;
     if (bi == 0 && (rc = prof_end(c, s, 2.0 * (double)nb * hw * hw * b.first * 9.0 * b.first))) return rc;
     if ((rc = blur_h16(A, Sd, nb, hw, hw, b.first, 1, 2, f16, s))) return rc;
-    TcConv as;
-    as.n = nb; as.H = ho; as.W = ho; as.Cin = b.first; as.Cout = b.second; as.taps = 1;
-    as.in = Sd; as.wb = sk.w16.as<h16>(); as.out_f32 = F;
-    if ((rc = conv_tc(as, f16, s))) return rc;
     if ((rc = blur_h16(B, Cb, nb, hw, hw, b.first, 2, 1, f16, s))) return rc;
     TcConv a2;
     a2.n = nb; a2.H = ho; a2.W = ho; a2.in_H = hw + 1; a2.in_W = hw + 1; a2.stride = 2; a2.no_pad = 1;
     a2.Cin = b.first; a2.Cout = b.second; a2.taps = 9;
     a2.in = Cb; a2.wb = c2.w16.as<h16>(); a2.bias = c2.bias.as<float>(); a2.act = 1;
-    a2.res_f32 = F; a2.out_scale = 0.70710678118654752f;
-    if (last) a2.out_f32 = t_blk; else a2.out_raw = A;
+    a2.sc_in = Sd; a2.sc_C = b.first; a2.sc_sep = 1; a2.out_scale = 0.70710678118654752f;
+    a2.out_raw = A;
+    if (last) a2.out_f32 = t_blk;          // fp32 copy of the last feature map for the minibatch-stddev statistic
     if ((rc = conv_tc(a2, f16, s))) return rc;
     hw = ho;
   }
-  // tail in fp32: minibatch-stddev channel, final conv (513 -> 512 on 4x4), the two EqualLinear layers
-  if ((rc = minibatch_stddev_cat_fp32(t_blk, t_cat, c->sg2_sd.as<float>(), nb, c->sg2_batch, 16, 512, s))) return rc;
+  // tail: minibatch-stddev statistic (fp32), final conv (512 -> 512 on 4x4 + the stddev channel as a rank-1 term in the
+  // epilogue), EqualLinear(8192, 512) as a plain GEMM, EqualLinear(512, 1) as a dot product
+  float* sd = c->sg2_sd.as<float>();
+  if ((rc = minibatch_stddev_fp32(t_blk, sd, nb, c->sg2_batch, 16, 512, s))) return rc;
   const ConvLayer& fc = c->convs[li++];
-  if ((rc = conv_fp32(t_cat, fc.w32.as<float>(), fc.bias.as<float>(), t_fc, nb, 4, 4, 513, 512, 3, 1, ACT_NONE, ACT_LRELU_SQRT2, s, 1))) return rc;
+  TcConv af;
+  af.n = nb; af.H = 4; af.W = 4; af.Cin = 512; af.Cout = 512; af.taps = 9;
+  af.in = A; af.wb = fc.w16.as<h16>(); af.bias = fc.bias.as<float>(); af.act = 1;
+  af.sd = sd; af.sd_w = fc.w3.as<float>(); af.out_raw = B;
+  if ((rc = conv_tc(af, f16, s))) return rc;
   const ConvLayer& l0 = c->convs[li++];
-  if ((rc = conv_fp32(t_fc, l0.w32.as<float>(), l0.bias.as<float>(), t_lin, nb, 1, 1, 8192, 512, 1, 1, ACT_NONE, ACT_LRELU_SQRT2, s, 0))) return rc;
+  TcConv al;
+  al.gemm = 1; al.n = 1; al.H = 1; al.W = (int)nb; al.Cin = 8192; al.Cout = 512; al.taps = 1;
+  al.in = B; al.wb = l0.w16.as<h16>(); al.bias = l0.bias.as<float>(); al.act = 1; al.out_f32 = t_lin;
+  if ((rc = conv_tc(al, f16, s))) return rc;
   return head_dot_fp32(t_lin, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, 512, s);
 }
 

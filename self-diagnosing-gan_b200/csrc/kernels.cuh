@@ -50,6 +50,13 @@ int add_div_sqrt2_fp32(const float* a, const float* b, float* out, int64_t total
 // in [n,HW,C] -> out [n,HW,C+1]
 int minibatch_stddev_cat_fp32(const float* in, float* out, float* sd_scratch, int64_t n, int batch, int HW, int C,
                               cudaStream_t s);
+// the same statistic without the concat: sd_sample[b] = the stddev-channel value sample b would see
+int minibatch_stddev_fp32(const float* in, float* sd_sample, int64_t n, int batch, int HW, int C, cudaStream_t s);
+// wb[o*K + p*C + c] = h16(W[o][c*HW + p] * mul)      (EqualLinear on the NCHW-flattened map; activations NHWC, K = C*HW)
+int pack_linear_nchw_h16(const float* W, float mul, h16* wb, int O, int C, int HW, int f16, cudaStream_t s);
+// contribution of ONE extra input channel (index c_extra of cin_w) of a 3x3 pad-1 conv on an S x S map whose value is constant
+// over the map: wsum[p*Cout + o] = mul * sum over the taps that stay inside the map at pixel p of W[o][c_extra][tap]
+int pack_const_channel_fp32(const float* W, float mul, float* wsum, int Cout, int cin_w, int c_extra, int S, cudaStream_t s);
 // 16-bit (tensor-core path) pieces: first 1x1 conv + FusedLeakyReLU from the image (w3 [3][C] fp32, scaled), Blur, widening
 int sg2_first_conv_h16(const void* x, int layout, const float* w3, const float* bias, h16* out, int64_t n, int S, int C, int f16,
                        cudaStream_t s);
@@ -83,8 +90,9 @@ int sn_sigmas(const SnLayer* layers_dev, const SnLayer* layers_host, int n_layer
 int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float* wp, int Cout, int Cin, int ks,
                    cudaStream_t s, float mul = 1.0f);
 // wb[o*ld + col0 + k] = h16(W[o][c][tap] * scale[o] / sigma) at k = tap*Cin + c, zero padded up to Kpad columns
+// cin_w > 0: the weight tensor has cin_w >= Cin input channels and only the first Cin are packed
 int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* wb, int Cout, int Cin, int Kpad,
-                  int ks, int f16, int ld, int col0, cudaStream_t s, float mul = 1.0f);
+                  int ks, int f16, int ld, int col0, cudaStream_t s, float mul = 1.0f, int cin_w = 0);
 // pooled-3x3 weights for the 4x4 stride-2 form: wb[o*ld + (a*4+b)*Cin + c] = 0.25 * sum of W[o][c][ky][kx] / sigma over
 // ky in {a-1,a}, kx in {b-1,b} (valid taps); shortcut: wb[o*ld + col0 + t*sc_pad + c] = 0.25 * Wsc[o][c] / sigma_sc, t = 0..3
 int pack_pool4_h16(const float* W, const float* sigma, h16* wb, int Cout, int Cin, int f16, int ld, cudaStream_t s);
@@ -119,6 +127,8 @@ struct TcConv {
   int H = 0, W = 0, Cin = 0, Cout = 0, taps = 9;
   const h16* sc_in = nullptr;     // [n,H,W,sc_C]: input of the block's 1x1 shortcut conv (same resolution as `in`)
   int sc_C = 0;
+  int sc_sep = 0;                 // 1: sc_in is at the OUTPUT resolution [n,Ho,Wo,sc_C] and its 1x1 conv (the last sc_C columns of
+                                  // wb) goes to a second accumulator added AFTER the activation (StyleGAN2 ResBlock skip)
   int pool = 0;                   // avg_pool2d(., 2) of conv (+ shortcut conv) before the adds below
   int pool4 = 0;                  // with pool: run conv3x3 + avg_pool2d as the algebraically equal 4x4 stride-2 conv
                                   // (16/36 of the MACs); wb then holds 16 taps x Cin (+ 4 taps x sc_C), see pack_pool4_h16
@@ -127,6 +137,9 @@ struct TcConv {
   int no_pad = 0;                 // 1: taps start at the output pixel (padding 0) instead of one pixel before ("same")
   int act = 0;                    // 1: FusedLeakyReLU on (acc + bias): leaky_relu(., 0.2) * sqrt(2), before the residual
   float out_scale = 1.0f;         // final multiplier after the residual (StyleGAN2 ResBlock: 1/sqrt(2))
+  int gemm = 0;                   // 1: plain GEMM rows: in = [W rows][Cin] (H = 1, any W >= 1), taps = 1  (EqualLinear)
+  const float* sd = nullptr;      // [n] per-sample scalar of a spatially constant extra input channel (minibatch-stddev) ...
+  const float* sd_w = nullptr;    // ... and its summed weights [H*W][Cout]: v += sd[n] * sd_w[pixel][o] before the activation
   const float* res_f32 = nullptr; // identity shortcut [n,Ho,Wo,Cout] fp32
   int res_relu = 0;               // rectify the identity shortcut (mimicry's in-place ReLU aliasing)
   const void* img = nullptr;      // network input (DBlockOptimized: shortcut = Wsc3 . avg_pool2d(img) at pooled res)

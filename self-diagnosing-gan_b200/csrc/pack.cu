@@ -112,7 +112,7 @@ int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float
 template <bool F16>
 __global__ void __launch_bounds__(256)
 pack_conv_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigma, const float* __restrict__ scale,
-                     h16* __restrict__ wb, int Cout, int Cin, int Kpad, int taps, int ld, int col0, float mul) {
+                     h16* __restrict__ wb, int Cout, int Cin, int Kpad, int taps, int ld, int col0, float mul, int cin_w) {
   const int total = Cout * Kpad;
   const float sg = sigma ? sigma[0] : 1.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -121,7 +121,7 @@ pack_conv_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigm
     float w = 0.f;
     if (k < taps * Cin) {
       int tap = k / Cin, c = k - tap * Cin;
-      w = W[((int64_t)o * Cin + c) * taps + tap];
+      w = W[((int64_t)o * cin_w + c) * taps + tap];
       if (sigma) w = w / sg;
       if (scale) w = w * scale[o];
       if (mul != 1.0f) w = w * mul;
@@ -131,14 +131,15 @@ pack_conv_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigm
 }
 
 int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* wb, int Cout, int Cin, int Kpad,
-                  int ks, int f16, int ld, int col0, cudaStream_t s, float mul) {
+                  int ks, int f16, int ld, int col0, cudaStream_t s, float mul, int cin_w) {
   int total = Cout * Kpad;
+  if (cin_w <= 0) cin_w = Cin;
   if (f16) {
     SDG_LAUNCH(pack_conv_h16_kernel<true>, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wb, Cout, Cin, Kpad,
-               ks * ks, ld, col0, mul);
+               ks * ks, ld, col0, mul, cin_w);
   } else {
     SDG_LAUNCH(pack_conv_h16_kernel<false>, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wb, Cout, Cin, Kpad,
-               ks * ks, ld, col0, mul);
+               ks * ks, ld, col0, mul, cin_w);
   }
   return 0;
 }

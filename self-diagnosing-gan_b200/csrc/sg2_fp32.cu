@@ -62,7 +62,8 @@ int add_div_sqrt2_fp32(const float* a, const float* b, float* out, int64_t total
 
 // one CTA per (column m of the group view, batch): sd = mean_{p,c} sqrt(var_g(h[g*M+m][p][c]) + 1e-8), group = min(B,4)
 __global__ void __launch_bounds__(256)
-stddev_kernel(const float* __restrict__ in, float* __restrict__ sd, int batch, int group, int HW, int C) {
+stddev_kernel(const float* __restrict__ in, float* __restrict__ sd, float* __restrict__ sd_sample, int batch, int group, int HW,
+              int C) {
   const int M = batch / group;
   const int m = blockIdx.x;
   const int64_t b0 = (int64_t)blockIdx.y * batch;
@@ -86,7 +87,11 @@ stddev_kernel(const float* __restrict__ in, float* __restrict__ sd, int batch, i
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int k = 0; k < 8; ++k) t += red[k];
-    sd[blockIdx.y * M + m] = t / (float)per;
+    const float v = t / (float)per;
+    if (sd) sd[blockIdx.y * M + m] = v;
+    // stddev.repeat(group, 1, H, W): every sample b of this batch with b % M == m sees this value
+    if (sd_sample)
+      for (int g = 0; g < group; ++g) sd_sample[b0 + (int64_t)g * M + m] = v;
   }
 }
 
@@ -111,9 +116,60 @@ int minibatch_stddev_cat_fp32(const float* in, float* out, float* sd_scratch, in
   const int group = batch < 4 ? batch : 4;
   SDG_REQUIRE(batch % group == 0, SDG_E_INVALID, "minibatch_stddev: batch %d not divisible by the group %d", batch, group);
   if (n == 0) return 0;
-  SDG_LAUNCH(stddev_kernel, dim3(batch / group, (unsigned)(n / batch)), 256, 0, s, in, sd_scratch, batch, group, HW, C);
+  SDG_LAUNCH(stddev_kernel, dim3(batch / group, (unsigned)(n / batch)), 256, 0, s, in, sd_scratch, (float*)nullptr, batch, group, HW, C);
   const int64_t total = n * HW * (C + 1);
   SDG_LAUNCH(cat_stddev_kernel, stream_grid(total, 256), 256, 0, s, in, sd_scratch, out, total, batch, group, HW, C);
+  return 0;
+}
+
+int minibatch_stddev_fp32(const float* in, float* sd_sample, int64_t n, int batch, int HW, int C, cudaStream_t s) {
+  SDG_REQUIRE(batch >= 1 && n % batch == 0, SDG_E_INVALID, "minibatch_stddev: n=%lld is not a multiple of the batch %d",
+              (long long)n, batch);
+  const int group = batch < 4 ? batch : 4;
+  SDG_REQUIRE(batch % group == 0, SDG_E_INVALID, "minibatch_stddev: batch %d not divisible by the group %d", batch, group);
+  if (n == 0) return 0;
+  SDG_LAUNCH(stddev_kernel, dim3(batch / group, (unsigned)(n / batch)), 256, 0, s, in, (float*)nullptr, sd_sample, batch, group, HW, C);
+  return 0;
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(256)
+pack_linear_nchw_h16_kernel(const float* __restrict__ W, float mul, h16* __restrict__ wb, int O, int C, int HW) {
+  const int64_t K = (int64_t)C * HW, total = (int64_t)O * K;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int o = (int)(i / K);
+    const int k = (int)(i - (int64_t)o * K);           // p*C + c
+    const int c = k % C, p = k / C;
+    wb[i] = (h16)(pack_h2<F16>(W[(int64_t)o * K + (int64_t)c * HW + p] * mul, 0.f) & 0xffffu);
+  }
+}
+
+int pack_linear_nchw_h16(const float* W, float mul, h16* wb, int O, int C, int HW, int f16, cudaStream_t s) {
+  const int64_t total = (int64_t)O * C * HW;
+  if (f16) { SDG_LAUNCH(pack_linear_nchw_h16_kernel<true>, stream_grid(total, 256), 256, 0, s, W, mul, wb, O, C, HW); }
+  else { SDG_LAUNCH(pack_linear_nchw_h16_kernel<false>, stream_grid(total, 256), 256, 0, s, W, mul, wb, O, C, HW); }
+  return 0;
+}
+
+__global__ void __launch_bounds__(256)
+pack_const_channel_kernel(const float* __restrict__ W, float mul, float* __restrict__ wsum, int Cout, int cin_w, int c_extra, int S) {
+  const int total = S * S * Cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int o = i % Cout, p = i / Cout;
+    const int y = p / S, x = p % S;
+    float acc = 0.f;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = y + ky - 1, ix = x + kx - 1;
+        if (iy >= 0 && iy < S && ix >= 0 && ix < S) acc += W[((int64_t)o * cin_w + c_extra) * 9 + ky * 3 + kx] * mul;
+      }
+    wsum[i] = acc;
+  }
+}
+
+int pack_const_channel_fp32(const float* W, float mul, float* wsum, int Cout, int cin_w, int c_extra, int S, cudaStream_t s) {
+  SDG_LAUNCH(pack_const_channel_kernel, stream_grid((int64_t)S * S * Cout, 256), 256, 0, s, W, mul, wsum, Cout, cin_w, c_extra, S);
   return 0;
 }
 
@@ -137,107 +193,175 @@ int pack_linear_nchw_fp32(const float* W, float mul, float* wp, int O, int C, in
 // ---------------------------------------------------------------------------------------------------
 // 16-bit (tensor-core path) helpers: first 1x1 conv from the image, blur, widening of the last feature map
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sg2_norm_px(const void* x, int layout, int64_t pix, int c, int64_t HW) {
-  if (layout == SDG_LAYOUT_U8_NHWC) {
-    float v = __fdiv_rn((float)reinterpret_cast<const uint8_t*>(x)[pix * 3 + c], 255.0f);
-    return __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
-  }
-  const int64_t n = pix / HW, r = pix - n * HW;
-  return reinterpret_cast<const float*>(x)[(n * 3 + c) * HW + r];
-}
-
 // ConvLayer(3, C, 1): out[pix][o] = flrelu(sum_c w[c][o] * x[pix][c] + b[o]); w3 = [3][C] (pack_conv_fp32 layout), already
-// carrying 1/sqrt(3).
-// one thread per (pixel, 8 output channels): HBM-write-bound (2*C bytes per pixel)
+// carrying 1/sqrt(3).  HBM-write-bound (2*C bytes per pixel).  A thread owns ONE group of 8 output channels for the whole
+// kernel (its 24 weights + 8 biases stay in registers) and strides over pixels; consecutive lanes write consecutive 16 B.
+// C and S are powers of two, so all index arithmetic is shifts (64-bit division is what made the first version slow).
 template <bool F16>
 __global__ void __launch_bounds__(256)
 sg2_first_conv_kernel(const void* __restrict__ x, int layout, const float* __restrict__ w3, const float* __restrict__ bias,
-                      h16* __restrict__ out, int64_t n_pix, int64_t HW, int C) {
-  const int C8 = C / 8;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix * C8; i += stride) {
-    const int g = (int)(i % C8);
-    const int64_t pix = i / C8;
-    const float x0 = sg2_norm_px(x, layout, pix, 0, HW), x1 = sg2_norm_px(x, layout, pix, 1, HW),
-                x2 = sg2_norm_px(x, layout, pix, 2, HW);
-    uint4 pk;
-    uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
+                      h16* __restrict__ out, int64_t n_pix, int hw_shift, int c8_shift, int C) {
+  const int C8 = 1 << c8_shift;
+  const int g = threadIdx.x & (C8 - 1);
+  float w[3][8], b[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float v[2];
+  for (int j = 0; j < 8; ++j) {
+    b[j] = bias[g * 8 + j];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int o = g * 8 + 2 * j + e;
-        float a = fmaf(w3[2 * C + o], x2, fmaf(w3[C + o], x1, fmaf(w3[o], x0, bias[o])));
-        v[e] = (a > 0.f ? a : 0.2f * a) * 1.4142135623730951f;
+    for (int c = 0; c < 3; ++c) w[c][j] = w3[c * C + g * 8 + j];
+  }
+  const int ppb = 256 >> c8_shift;                                   // pixels per block sub-iteration
+  const int64_t HWm = ((int64_t)1 << hw_shift) - 1;
+  constexpr int U = 4;                                               // pixels in flight per thread (loads batched)
+  for (int64_t p0 = ((int64_t)blockIdx.x * U) * ppb + (threadIdx.x >> c8_shift); p0 < n_pix; p0 += (int64_t)gridDim.x * U * ppb) {
+    float xv[U][3];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t pix = p0 + (int64_t)u * ppb;
+      if (pix >= n_pix) { xv[u][0] = xv[u][1] = xv[u][2] = 0.f; continue; }
+      if (layout == SDG_LAYOUT_U8_NHWC) {
+        const uint8_t* px = reinterpret_cast<const uint8_t*>(x) + pix * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xv[u][c] = (float)__ldg(px + c);
+      } else {
+        const int64_t n = pix >> hw_shift, r = pix & HWm;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xv[u][c] = __ldg(reinterpret_cast<const float*>(x) + (((n * 3 + c)) << hw_shift) + r);
       }
-      h[j] = pack_h2<F16>(v[0], v[1]);
     }
-    *reinterpret_cast<uint4*>(out + pix * C + g * 8) = pk;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t pix = p0 + (int64_t)u * ppb;
+      if (pix >= n_pix) break;
+      if (layout == SDG_LAYOUT_U8_NHWC) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xv[u][c] = __fdiv_rn(__fsub_rn(__fdiv_rn(xv[u][c], 255.0f), 0.5f), 0.5f);
+      }
+      uint4 pk;
+      uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int o = 2 * j + e;
+          const float a = fmaf(w[2][o], xv[u][2], fmaf(w[1][o], xv[u][1], fmaf(w[0][o], xv[u][0], b[o])));
+          v[e] = (a > 0.f ? a : 0.2f * a) * 1.4142135623730951f;
+        }
+        h[j] = pack_h2<F16>(v[0], v[1]);
+      }
+      *reinterpret_cast<uint4*>(out + pix * C + g * 8) = pk;
+    }
   }
 }
+
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 int sg2_first_conv_h16(const void* x, int layout, const float* w3, const float* bias, h16* out, int64_t n, int S, int C, int f16,
                        cudaStream_t s) {
   const int64_t n_pix = n * S * S;
   if (n_pix == 0) return 0;
-  if (f16) { SDG_LAUNCH(sg2_first_conv_kernel<true>, stream_grid(n_pix * (C / 8), 256), 256, 0, s, x, layout, w3, bias, out, n_pix, (int64_t)S * S, C); }
-  else { SDG_LAUNCH(sg2_first_conv_kernel<false>, stream_grid(n_pix * (C / 8), 256), 256, 0, s, x, layout, w3, bias, out, n_pix, (int64_t)S * S, C); }
+  SDG_REQUIRE((S & (S - 1)) == 0 && (C & (C - 1)) == 0 && C >= 8 && C <= 2048, SDG_E_UNSUPPORTED, "sg2_first_conv: S=%d C=%d", S, C);
+  const int c8s = ilog2(C / 8), hws = 2 * ilog2(S);
+  const int grid = stream_grid(n_pix * (C / 8), 256);
+  if (f16) { SDG_LAUNCH(sg2_first_conv_kernel<true>, grid, 256, 0, s, x, layout, w3, bias, out, n_pix, hws, c8s, C); }
+  else { SDG_LAUNCH(sg2_first_conv_kernel<false>, grid, 256, 0, s, x, layout, w3, bias, out, n_pix, hws, c8s, C); }
   return 0;
 }
 
-// Blur on 16-bit NHWC: one thread per (output pixel, 8 channels), fp32 accumulation of the 16 taps.  `st` = 2 keeps only
-// the even blur outputs (all that the stride-2 1x1 skip conv reads, stylegan2.py:575-590)
+// Blur on 16-bit NHWC (Blur.forward, stylegan2.py:75-90: upfirdn2d with outer([1,3,3,1])/64, zero padding `pad`), separable
+// and register-sliding: a thread owns (output column x, 8 channels) and marches down `rows` output rows; per input row it
+// filters horizontally (4 loads of 16 B, neighbours hit L1) and keeps the last four filtered rows in registers, so every
+// input pixel leaves DRAM once and every output costs 4 (ST = 1) or 8 (ST = 2) L1 loads instead of 16.
+// ST = 2 evaluates only the even blur outputs: all that the stride-2 1x1 skip conv reads (stylegan2.py:575-590).
 template <bool F16>
-__global__ void __launch_bounds__(256)
-blur_h16_kernel(const h16* __restrict__ in, h16* __restrict__ out, int64_t total8, int H, int W, int C, int Ho, int Wo, int pad,
-                int st) {
-  const float k1[4] = {1.f, 3.f, 3.f, 1.f};
-  const int C8 = C / 8;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += stride) {
-    const int c = (int)(i % C8) * 8;
-    int64_t r = i / C8;
-    const int x = (int)(r % Wo);
-    r /= Wo;
-    const int y = (int)(r % Ho);
-    const int64_t n = r / Ho;
-    float acc[8];
+__device__ __forceinline__ void blur_hrow(const h16* __restrict__ img, int iy, int ix0, int H, int W, int C, float (&o)[8]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 8; ++j) o[j] = 0.f;
+  if (iy < 0 || iy >= H) return;
+  const h16* row = img + (int64_t)iy * W * C;
+  // the four loads are issued unconditionally (clamped address, zero weight outside the image) so they overlap
+  uint4 raw[4];
+  float kw[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int iy = y * st + a - pad;
-      if (iy < 0 || iy >= H) continue;
+  for (int b = 0; b < 4; ++b) {
+    const int ix = ix0 + b;
+    const bool ok = ix >= 0 && ix < W;
+    kw[b] = ok ? ((b == 0 || b == 3) ? 0.125f : 0.375f) : 0.f;
+    raw[b] = __ldg(reinterpret_cast<const uint4*>(row + (int64_t)(ok ? ix : 0) * C));
+  }
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int ix = x * st + b - pad;
-        if (ix < 0 || ix >= W) continue;
-        const uint4 raw = *reinterpret_cast<const uint4*>(in + ((n * H + iy) * W + ix) * (int64_t)C + c);
-        const uint32_t* wv = reinterpret_cast<const uint32_t*>(&raw);
-        const float kw = k1[a] * k1[b] * (1.f / 64.f);
+  for (int b = 0; b < 4; ++b) {
+    const uint32_t* wv = reinterpret_cast<const uint32_t*>(&raw[b]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 t = unpack_h2<F16>(wv[j]);
-          acc[2 * j] = fmaf(kw, t.x, acc[2 * j]);
-          acc[2 * j + 1] = fmaf(kw, t.y, acc[2 * j + 1]);
-        }
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = unpack_h2<F16>(wv[j]);
+      o[2 * j] = fmaf(kw[b], t.x, o[2 * j]);
+      o[2 * j + 1] = fmaf(kw[b], t.y, o[2 * j + 1]);
     }
+  }
+}
+
+template <bool F16, int ST>
+__global__ void __launch_bounds__(256)
+blur_h16_kernel(const h16* __restrict__ in, h16* __restrict__ out, int H, int W, int C, int Ho, int Wo, int pad, int c8_shift,
+                int x_tiles, int y_segs, int rows) {
+  const int C8 = 1 << c8_shift;
+  const int cg = threadIdx.x & (C8 - 1);
+  int b = blockIdx.x;
+  const int xt = b % x_tiles; b /= x_tiles;
+  const int ys = b % y_segs;
+  const int64_t n = b / y_segs;
+  const int x = xt * (256 >> c8_shift) + (threadIdx.x >> c8_shift);
+  if (x >= Wo) return;
+  const h16* img = in + n * H * W * (int64_t)C + cg * 8;
+  h16* dst = out + n * Ho * Wo * (int64_t)C + cg * 8;
+  const int y0 = ys * rows, y1 = min(Ho, y0 + rows);
+  const int ix0 = x * ST - pad;
+  float h0[8], h1[8], h2[8], h3[8];
+  // filtered input rows y*ST - pad + {0,1,2,3} feed output row y
+  blur_hrow<F16>(img, y0 * ST - pad, ix0, H, W, C, h0);
+  blur_hrow<F16>(img, y0 * ST - pad + 1, ix0, H, W, C, h1);
+  if (ST == 1) blur_hrow<F16>(img, y0 - pad + 2, ix0, H, W, C, h2);
+#pragma unroll 2
+  for (int y = y0; y < y1; ++y) {
+    if (ST == 2) blur_hrow<F16>(img, y * 2 - pad + 2, ix0, H, W, C, h2);
+    blur_hrow<F16>(img, y * ST - pad + 3, ix0, H, W, C, h3);
     uint4 pk;
-    uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
+    uint32_t* hp = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = pack_h2<F16>(acc[2 * j], acc[2 * j + 1]);
-    *reinterpret_cast<uint4*>(out + i * 8) = pk;
+    for (int j = 0; j < 4; ++j) {
+      const float a = 0.125f * (h0[2 * j] + h3[2 * j]) + 0.375f * (h1[2 * j] + h2[2 * j]);
+      const float c = 0.125f * (h0[2 * j + 1] + h3[2 * j + 1]) + 0.375f * (h1[2 * j + 1] + h2[2 * j + 1]);
+      hp[j] = pack_h2<F16>(a, c);
+    }
+    *reinterpret_cast<uint4*>(dst + ((int64_t)y * Wo + x) * C) = pk;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (ST == 1) { h0[j] = h1[j]; h1[j] = h2[j]; h2[j] = h3[j]; }
+      else { h0[j] = h2[j]; h1[j] = h3[j]; }
+    }
   }
 }
 
 int blur_h16(const h16* in, h16* out, int64_t n, int H, int W, int C, int pad, int stride, int f16, cudaStream_t s) {
   const int Ho = (H + 2 * pad - 4) / stride + 1, Wo = (W + 2 * pad - 4) / stride + 1;
-  const int64_t total8 = n * Ho * Wo * (C / 8);
-  if (total8 == 0) return 0;
-  if (f16) { SDG_LAUNCH(blur_h16_kernel<true>, stream_grid(total8, 256), 256, 0, s, in, out, total8, H, W, C, Ho, Wo, pad, stride); }
-  else { SDG_LAUNCH(blur_h16_kernel<false>, stream_grid(total8, 256), 256, 0, s, in, out, total8, H, W, C, Ho, Wo, pad, stride); }
+  if (n == 0 || Ho <= 0 || Wo <= 0) return 0;
+  SDG_REQUIRE((C & (C - 1)) == 0 && C >= 8 && C <= 2048, SDG_E_UNSUPPORTED, "blur_h16: C=%d must be a power of two in 8..2048", C);
+  SDG_REQUIRE(stride == 1 || stride == 2, SDG_E_UNSUPPORTED, "blur_h16: stride=%d", stride);
+  const int c8s = ilog2(C / 8);
+  const int xpb = 256 >> c8s;
+  const int x_tiles = (int)cdiv(Wo, xpb);
+  const int rows = Ho >= 64 ? 32 : (Ho >= 16 ? 8 : Ho);
+  const int y_segs = (int)cdiv(Ho, rows);
+  const int64_t blocks = (int64_t)x_tiles * y_segs * n;
+  SDG_REQUIRE(blocks < (1LL << 31), SDG_E_UNSUPPORTED, "blur_h16: grid too large");
+#define SDG_BLUR(F, ST) SDG_LAUNCH((blur_h16_kernel<F, ST>), (unsigned)blocks, 256, 0, s, in, out, H, W, C, Ho, Wo, pad, c8s, x_tiles, y_segs, rows)
+  if (f16 && stride == 1) { SDG_BLUR(true, 1); }
+  else if (f16) { SDG_BLUR(true, 2); }
+  else if (stride == 1) { SDG_BLUR(false, 1); }
+  else { SDG_BLUR(false, 2); }
+#undef SDG_BLUR
   return 0;
 }
 

@@ -36,7 +36,8 @@ SIGNATURES = {
     "sdg_d_forward": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "sdg_conv2d_h16": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i,
                              _vp]),
-    "sdg_conv2d_sg2_h16": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _vp, _vp, _i, _vp]),
+    "sdg_conv2d_sg2_h16": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _f, _vp, _vp, _i,
+                                 _vp]),
     "sdg_blur_h16": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "sdg_set_conv_pair": (_i, [_i]),
     "sdg_first_conv_h16": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _i, _vp]),

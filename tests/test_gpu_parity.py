@@ -545,7 +545,7 @@ def test_sngan_tensorcore_vs_oracle(arch, n, seed, inplace, prec, tol, dev):
 # ---------------------------------------------------------------------------------------------------
 # StyleGAN2 discriminator on the tensor-core path (BASELINE config 5)
 # ---------------------------------------------------------------------------------------------------
-def _sg2_conv(dev, n, hin, cin, cout, ks, stride, pad, act, res, prec, seed):
+def _sg2_conv(dev, n, hin, cin, cout, ks, stride, pad, act, res, prec, seed, skip=False):
     """One ConvLayer stage through sdg_conv2d_sg2_h16 vs torch fp32 on the same 16-bit-rounded operands."""
     import ctypes as C
     from diagan_b200 import _lib
@@ -562,18 +562,29 @@ def _sg2_conv(dev, n, hin, cin, cout, ks, stride, pad, act, res, prec, seed):
     y = y + b.view(1, -1, 1, 1)
     if act:
         y = F.leaky_relu(y, 0.2) * math.sqrt(2.0)
-    scale = 1.0 / math.sqrt(2.0) if res else 1.0
+    scale = 1.0 / math.sqrt(2.0) if (res or skip) else 1.0
+    sk = wk = None
+    if skip:                                  # the ResBlock skip: a 1x1 conv of an output-resolution tensor, second accumulator
+        sk = torch.randn(n, cin, ho, ho, generator=g).to(dt)
+        wk = (torch.randn(cout, cin, 1, 1, generator=g) / math.sqrt(cin)).to(dt)
+        y = y + F.conv2d(sk.float(), wk.float())
     if res:
-        y = (y + r) * scale
+        y = y + r
+    y = y * scale
     xd = x.permute(0, 2, 3, 1).contiguous().to(dev)
-    wd = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to(dev)
+    wd = w.permute(0, 2, 3, 1).reshape(cout, -1)
+    if skip:
+        wd = torch.cat([wd, wk.view(cout, cin)], 1)
+    wd = wd.contiguous().to(dev)
+    skd = sk.permute(0, 2, 3, 1).contiguous().to(dev) if skip else None
     bd = b.to(dev)
     rd = r.permute(0, 2, 3, 1).contiguous().to(dev) if res else None
     o16 = torch.empty(n, ho, ho, cout, dtype=dt, device=dev)
     o32 = torch.empty(n, ho, ho, cout, dtype=torch.float32, device=dev)
     pc = {"fp16": _lib.PREC_FP16, "bf16": _lib.PREC_BF16}[prec]
     check(lib.sdg_conv2d_sg2_h16(ptr(xd), ptr(wd), ptr(bd), n, ho, ho, hin, hin, cin, cout, ks, stride, 1 if pad else 0,
-                                 1 if act else 0, ptr(rd), C.c_float(scale), ptr(o16), ptr(o32), pc, stream_ptr(dev)),
+                                 1 if act else 0, ptr(skd), cin if skip else 0, ptr(rd), C.c_float(scale), ptr(o16), ptr(o32), pc,
+                                 stream_ptr(dev)),
           "sdg_conv2d_sg2_h16")
     torch.cuda.synchronize()
     want = y.permute(0, 2, 3, 1)
@@ -590,10 +601,14 @@ def _sg2_conv(dev, n, hin, cin, cout, ks, stride, pad, act, res, prec, seed):
     ("conv2_s2_from_33", 3, 33, 512, 512, 3, 2, 0, 1, True),
     ("conv2_s2_from_9", 5, 9, 512, 512, 3, 2, 0, 1, True),
     ("skip_1x1", 3, 16, 256, 512, 1, 1, 0, 0, False),
+    ("conv2_s2_skipfold_257", 1, 257, 128, 256, 3, 2, 0, 1, "skip"),  # skip conv folded in: second TMEM accumulator
+    ("conv2_s2_skipfold_17", 6, 17, 512, 512, 3, 2, 0, 1, "skip"),
+    ("conv2_s2_skipfold_9", 7, 9, 512, 512, 3, 2, 0, 1, "skip"),
 ])
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 def test_stylegan2_conv_stage_vs_torch(tag, n, hin, cin, cout, ks, stride, pad, act, res, prec, dev):
-    e32, e16, mag = _sg2_conv(dev, n, hin, cin, cout, ks, stride, pad, act, res, prec, seed=len(tag))
+    e32, e16, mag = _sg2_conv(dev, n, hin, cin, cout, ks, stride, pad, act, res is True, prec, seed=len(tag),
+                              skip=res == "skip")
     print(f"{tag} {prec}: fp32-out err {e32:.2e}, 16-bit-out err {e16:.2e}, |y|max {mag:.2f}")
     # operands are identical 16-bit values on both sides: only the accumulation order (fp32) and the output rounding differ
     assert e32 <= 2e-4 * max(1.0, mag)
