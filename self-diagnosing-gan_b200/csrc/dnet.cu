@@ -725,19 +725,19 @@ extern "C" int sdg_stylegan2_load(sdg_ctx* c, int size, int n_tensors, const flo
     // over the 4x4 map, so its contribution is sd[n] * (sum of its in-bounds tap weights): w3 holds that [16][512] table
     ConvLayer& l = c->convs[li++];
     const float mul = 1.0f / sqrtf(513.f * 9.f);
-    l.cout = 512; l.cin = 512; l.ks = 3; l.has_bias = true; l.kpad = l.ktot = 9 * 512;
+    // split-precision operands (sg2_fp32.cu): K = 9 taps x [hi | lo | hi] of 512 channels
+    l.cout = 512; l.cin = 3 * 512; l.ks = 3; l.has_bias = true; l.kpad = l.ktot = 9 * 3 * 512;
     { int rc = l.w16.ensure(sizeof(h16) * (size_t)l.ktot * 512); if (rc) return rc; }
-    { int rc = pack_conv_h16(t[ti], nullptr, nullptr, l.w16.as<h16>(), 512, 512, l.kpad, 3, precision == SDG_PREC_FP16, l.ktot, 0, s,
-                             mul, 513); if (rc) return rc; }
+    { int rc = pack_split3_h16(t[ti], mul, l.w16.as<h16>(), 512, 512, 9, 513, 0, precision == SDG_PREC_FP16, s); if (rc) return rc; }
     { int rc = l.w3.ensure(sizeof(float) * 16 * 512); if (rc) return rc; }
     { int rc = pack_const_channel_fp32(t[ti], mul, l.w3.as<float>(), 512, 513, 512, 4, s); if (rc) return rc; }
     { int rc = l.bias.ensure(sizeof(float) * 512); if (rc) return rc; }
     SDG_CUDA(cudaMemcpyAsync(l.bias.p, t[ti + 1], sizeof(float) * 512, cudaMemcpyDeviceToDevice, s));
     ti += 2;
     ConvLayer& l0 = c->convs[li++];          // EqualLinear(8192, 512, fused_lrelu): a [n][8192] x [512][8192]^T GEMM
-    l0.cout = 512; l0.cin = 8192; l0.ks = 1; l0.has_bias = true; l0.kpad = l0.ktot = 8192;
-    { int rc = l0.w16.ensure(sizeof(h16) * 8192 * 512); if (rc) return rc; }
-    { int rc = pack_linear_nchw_h16(t[ti], 1.0f / sqrtf(8192.f), l0.w16.as<h16>(), 512, 512, 16, precision == SDG_PREC_FP16, s);
+    l0.cout = 512; l0.cin = 3 * 8192; l0.ks = 1; l0.has_bias = true; l0.kpad = l0.ktot = 3 * 8192;
+    { int rc = l0.w16.ensure(sizeof(h16) * (size_t)l0.ktot * 512); if (rc) return rc; }
+    { int rc = pack_split3_h16(t[ti], 1.0f / sqrtf(8192.f), l0.w16.as<h16>(), 512, 512, 16, 0, 1, precision == SDG_PREC_FP16, s);
       if (rc) return rc; }
     { int rc = l0.bias.ensure(sizeof(float) * 512); if (rc) return rc; }
     SDG_CUDA(cudaMemcpyAsync(l0.bias.p, t[ti + 1], sizeof(float) * 512, cudaMemcpyDeviceToDevice, s));
@@ -834,7 +834,7 @@ static Sg2Sizes sg2_h16_sizes(const sdg_ctx* c) {
   return z;
 }
 
-static constexpr int64_t kSg2TailFloats = 16 * 512 + 512;   // last block output (fp32), linear output
+static constexpr int64_t kSg2TailFloats = 2 * 16 * 512 + 512;   // last block output, final conv output, linear output (fp32)
 
 static int64_t sg2_h16_bytes_per_sample(const sdg_ctx* c) {
   const Sg2Sizes z = sg2_h16_sizes(c);
@@ -861,7 +861,8 @@ static int forward_stylegan2_h16(sdg_ctx* c, const void* x, int layout, int64_t 
   h16* Sd = c->buf[3].as<h16>();
   float* tail = c->buf[5].as<float>();
   float* t_blk = tail;                               // [nb,16,512] last ResBlock output, fp32
-  float* t_lin = t_blk + nb * 16 * 512;              // [nb,512]
+  float* t_fc = t_blk + nb * 16 * 512;               // [nb,16,512] final conv output, fp32
+  float* t_lin = t_fc + nb * 16 * 512;               // [nb,512]
   int rc, li = 0;
   {
     const ConvLayer& l = c->convs[li++];
@@ -889,8 +890,8 @@ static int forward_stylegan2_h16(sdg_ctx* c, const void* x, int layout, int64_t 
     a2.Cin = b.first; a2.Cout = b.second; a2.taps = 9;
     a2.in = Cb; a2.wb = c2.w16.as<h16>(); a2.bias = c2.bias.as<float>(); a2.act = 1;
     a2.sc_in = Sd; a2.sc_C = b.first; a2.sc_sep = 1; a2.out_scale = 0.70710678118654752f;
-    a2.out_raw = A;
-    if (last) a2.out_f32 = t_blk;          // fp32 copy of the last feature map for the minibatch-stddev statistic
+    if (last) a2.out_f32 = t_blk;          // fp32: the minibatch-stddev statistic and the split-precision tail read it
+    else a2.out_raw = A;
     if ((rc = conv_tc(a2, f16, s))) return rc;
     hw = ho;
   }
@@ -898,16 +899,19 @@ static int forward_stylegan2_h16(sdg_ctx* c, const void* x, int layout, int64_t 
   // epilogue), EqualLinear(8192, 512) as a plain GEMM, EqualLinear(512, 1) as a dot product
   float* sd = c->sg2_sd.as<float>();
   if ((rc = minibatch_stddev_fp32(t_blk, sd, nb, c->sg2_batch, 16, 512, s))) return rc;
+  // split-precision tail: fp32 activations enter the GEMMs as [hi | lo | hi] 16-bit triples (B and Cb are free here)
+  if ((rc = split3_rows_h16(t_blk, B, nb * 16, 512, f16, s))) return rc;
   const ConvLayer& fc = c->convs[li++];
   TcConv af;
-  af.n = nb; af.H = 4; af.W = 4; af.Cin = 512; af.Cout = 512; af.taps = 9;
-  af.in = A; af.wb = fc.w16.as<h16>(); af.bias = fc.bias.as<float>(); af.act = 1;
-  af.sd = sd; af.sd_w = fc.w3.as<float>(); af.out_raw = B;
+  af.n = nb; af.H = 4; af.W = 4; af.Cin = 3 * 512; af.Cout = 512; af.taps = 9;
+  af.in = B; af.wb = fc.w16.as<h16>(); af.bias = fc.bias.as<float>(); af.act = 1;
+  af.sd = sd; af.sd_w = fc.w3.as<float>(); af.out_f32 = t_fc;
   if ((rc = conv_tc(af, f16, s))) return rc;
+  if ((rc = split3_rows_h16(t_fc, Cb, nb * 16, 512, f16, s))) return rc;
   const ConvLayer& l0 = c->convs[li++];
   TcConv al;
-  al.gemm = 1; al.n = 1; al.H = 1; al.W = (int)nb; al.Cin = 8192; al.Cout = 512; al.taps = 1;
-  al.in = B; al.wb = l0.w16.as<h16>(); al.bias = l0.bias.as<float>(); al.act = 1; al.out_f32 = t_lin;
+  al.gemm = 1; al.n = 1; al.H = 1; al.W = (int)nb; al.Cin = 3 * 8192; al.Cout = 512; al.taps = 1;
+  al.in = Cb; al.wb = l0.w16.as<h16>(); al.bias = l0.bias.as<float>(); al.act = 1; al.out_f32 = t_lin;
   if ((rc = conv_tc(al, f16, s))) return rc;
   return head_dot_fp32(t_lin, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, 512, s);
 }

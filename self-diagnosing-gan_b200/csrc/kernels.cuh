@@ -63,6 +63,10 @@ int sg2_first_conv_h16(const void* x, int layout, const float* w3, const float* 
 // blur_h16: out extent = (H + 2*pad - 4) / stride + 1 (stride 2 = only the blur outputs a stride-2 1x1 conv reads)
 int blur_h16(const h16* in, h16* out, int64_t n, int H, int W, int C, int pad, int stride, int f16, cudaStream_t s);
 int widen_h16(const h16* in, float* out, int64_t total, int f16, cudaStream_t s);
+// split-precision tail operands (see sg2_fp32.cu): activations fp32 [rows][C] -> [rows][hi | lo | hi]; weights -> per K group
+// of C channels [Wh | Wh | Wl] (conv: G = 9 taps of W[O][cin_w][3][3]; linear: G = HW pixels of W[O][C*HW], NCHW flatten)
+int split3_rows_h16(const float* in, h16* out, int64_t rows, int C, int f16, cudaStream_t s);
+int pack_split3_h16(const float* W, float mul, h16* wb, int O, int C, int G, int cin_w, int linear, int f16, cudaStream_t s);
 // wp[(p*C + c)*O + o] = W[o][c*HW + p] * mul    (EqualLinear on an NCHW-flattened feature map, activations kept NHWC)
 int pack_linear_nchw_fp32(const float* W, float mul, float* wp, int O, int C, int HW, cudaStream_t s);
 // out = (pool_a ? avgpool2(a) : a) + (pool_b ? avgpool2(relu_b ? relu(b) : b) : ...); b may be null

@@ -203,12 +203,18 @@ sg2_first_conv_kernel(const void* __restrict__ x, int layout, const float* __res
                       h16* __restrict__ out, int64_t n_pix, int hw_shift, int c8_shift, int C) {
   const int C8 = 1 << c8_shift;
   const int g = threadIdx.x & (C8 - 1);
+  // normalisation (x/255 - 0.5)/0.5 with IEEE divisions (transform.py:3-11) through a 256-entry table: the divisions were
+  // most of the instruction stream of this otherwise store-bound kernel
+  __shared__ float lut[256];
+  lut[threadIdx.x] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)threadIdx.x, 255.0f), 0.5f), 0.5f);
+  __syncthreads();
+  // leaky_relu is positively homogeneous: lrelu(a) * sqrt(2) = lrelu(sqrt(2) * a), so sqrt(2) rides on the weights and the bias
   float w[3][8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    b[j] = bias[g * 8 + j];
+    b[j] = bias[g * 8 + j] * 1.4142135623730951f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) w[c][j] = w3[c * C + g * 8 + j];
+    for (int c = 0; c < 3; ++c) w[c][j] = w3[c * C + g * 8 + j] * 1.4142135623730951f;
   }
   const int ppb = 256 >> c8_shift;                                   // pixels per block sub-iteration
   const int64_t HWm = ((int64_t)1 << hw_shift) - 1;
@@ -222,7 +228,7 @@ sg2_first_conv_kernel(const void* __restrict__ x, int layout, const float* __res
       if (layout == SDG_LAYOUT_U8_NHWC) {
         const uint8_t* px = reinterpret_cast<const uint8_t*>(x) + pix * 3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) xv[u][c] = (float)__ldg(px + c);
+        for (int c = 0; c < 3; ++c) xv[u][c] = lut[__ldg(px + c)];
       } else {
         const int64_t n = pix >> hw_shift, r = pix & HWm;
 #pragma unroll
@@ -233,10 +239,6 @@ sg2_first_conv_kernel(const void* __restrict__ x, int layout, const float* __res
     for (int u = 0; u < U; ++u) {
       const int64_t pix = p0 + (int64_t)u * ppb;
       if (pix >= n_pix) break;
-      if (layout == SDG_LAYOUT_U8_NHWC) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) xv[u][c] = __fdiv_rn(__fsub_rn(__fdiv_rn(xv[u][c], 255.0f), 0.5f), 0.5f);
-      }
       uint4 pk;
       uint32_t* h = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
@@ -246,7 +248,7 @@ sg2_first_conv_kernel(const void* __restrict__ x, int layout, const float* __res
         for (int e = 0; e < 2; ++e) {
           const int o = 2 * j + e;
           const float a = fmaf(w[2][o], xv[u][2], fmaf(w[1][o], xv[u][1], fmaf(w[0][o], xv[u][0], b[o])));
-          v[e] = (a > 0.f ? a : 0.2f * a) * 1.4142135623730951f;
+          v[e] = fmaxf(a, 0.2f * a);
         }
         h[j] = pack_h2<F16>(v[0], v[1]);
       }
@@ -362,6 +364,71 @@ int blur_h16(const h16* in, h16* out, int64_t n, int H, int W, int C, int pad, i
   else if (stride == 1) { SDG_BLUR(false, 1); }
   else { SDG_BLUR(false, 2); }
 #undef SDG_BLUR
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Split-precision operands for the 4x4 tail (final conv, EqualLinear 8192 -> 512).  The last stages feed a 512-term dot
+// product that cancels to a small logit, so their 16-bit roundings would dominate the network's error; instead x = hi + lo
+// (two 16-bit values, exact to ~2^-22) and W = Wh + Wl, and the GEMM runs over K' = 3K as
+//   [xh | xl | xh] . [Wh | Wh | Wl]^T  =  xh.Wh + xl.Wh + xh.Wl      (the dropped xl.Wl term is ~2^-22 relative)
+// on the same tcgen05 kernel (fp32 accumulation in TMEM).  3x the MACs of 0.1 % of the network.
+// ---------------------------------------------------------------------------------------------------
+template <bool F16>
+__device__ __forceinline__ void split_hilo(float v, h16& hi, h16& lo) {
+  const uint32_t ph = pack_h2<F16>(v, 0.f);
+  const float vh = unpack_h2<F16>(ph).x;
+  hi = (h16)(ph & 0xffffu);
+  lo = (h16)(pack_h2<F16>(v - vh, 0.f) & 0xffffu);
+}
+
+// in fp32 [rows][C] -> out 16-bit [rows][3C] = [hi | lo | hi]
+template <bool F16>
+__global__ void __launch_bounds__(256)
+split3_rows_kernel(const float* __restrict__ in, h16* __restrict__ out, int64_t total, int C) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    h16 hi, lo;
+    split_hilo<F16>(in[i], hi, lo);
+    h16* o = out + r * 3 * C;
+    o[c] = hi; o[C + c] = lo; o[2 * C + c] = hi;
+  }
+}
+
+int split3_rows_h16(const float* in, h16* out, int64_t rows, int C, int f16, cudaStream_t s) {
+  const int64_t total = rows * C;
+  if (total == 0) return 0;
+  if (f16) { SDG_LAUNCH(split3_rows_kernel<true>, stream_grid(total, 256), 256, 0, s, in, out, total, C); }
+  else { SDG_LAUNCH(split3_rows_kernel<false>, stream_grid(total, 256), 256, 0, s, in, out, total, C); }
+  return 0;
+}
+
+// wb[o][(g*C + c) * 3 -> g*3C + {0, C, 2C} + c] = {Wh, Wh, Wl} of w(o, g, c) * mul, where (g, c) index the K axis as groups
+// of C channels: conv mode (linear = 0): g = tap, w = W[o][c][tap] with cin_w input channels and G = 9 taps;
+// linear mode: g = pixel p, w = W[o][c*G + p] (EqualLinear on an NCHW-flattened map, activations NHWC)
+template <bool F16>
+__global__ void __launch_bounds__(256)
+pack_split3_kernel(const float* __restrict__ W, float mul, h16* __restrict__ wb, int O, int C, int G, int cin_w, int linear) {
+  const int64_t K = (int64_t)G * C, total = (int64_t)O * K;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int o = (int)(i / K);
+    const int k = (int)(i - (int64_t)o * K);
+    const int g = k / C, c = k - g * C;
+    const float w = (linear ? W[(int64_t)o * K + (int64_t)c * G + g] : W[((int64_t)o * cin_w + c) * G + g]) * mul;
+    h16 hi, lo;
+    split_hilo<F16>(w, hi, lo);
+    h16* d = wb + (int64_t)o * 3 * K + (int64_t)g * 3 * C;
+    d[c] = hi; d[C + c] = hi; d[2 * C + c] = lo;
+  }
+}
+
+int pack_split3_h16(const float* W, float mul, h16* wb, int O, int C, int G, int cin_w, int linear, int f16, cudaStream_t s) {
+  const int64_t total = (int64_t)O * C * G;
+  if (f16) { SDG_LAUNCH(pack_split3_kernel<true>, stream_grid(total, 256), 256, 0, s, W, mul, wb, O, C, G, cin_w, linear); }
+  else { SDG_LAUNCH(pack_split3_kernel<false>, stream_grid(total, 256), 256, 0, s, W, mul, wb, O, C, G, cin_w, linear); }
   return 0;
 }
 

@@ -25,9 +25,11 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--pair", type=int, default=1, help="0: force the single-CTA conv kernel for Cout = 128 layers")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     eng = engine.DiscriminatorEngine(dev)
+    eng.lib.sdg_set_conv_pair(a.pair)
     if a.arch.startswith("sngan"):
         size = int(a.arch[5:])
         eng.load_sngan(synthetic.sngan_state_dict(size, 1), size, a.precision, True)
