@@ -39,6 +39,7 @@ def install(verbose: bool = True) -> dict:
     def _trainer(m):
         m.LogTrainer._get_logit = b_trainer._get_logit
         m.LogTrainer._save_logit = b_trainer._save_logit
+        m.LogTrainer._restore_logits = b_trainer._restore_logits      # opt-in resume (call after construction)
     _try("diagan.trainer.trainer", _trainer)
     _try("diagan.models.drs", lambda m: setattr(m, "DRS", b_drs.DRS))
     _try("diagan.trainer.evaluate", lambda m: setattr(m, "DRS", b_eval.DRS))

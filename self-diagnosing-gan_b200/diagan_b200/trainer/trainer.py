@@ -19,6 +19,7 @@ device->host sync each.
 """
 from __future__ import annotations
 
+import os
 import pickle
 from collections import defaultdict
 from pathlib import Path
@@ -201,12 +202,65 @@ def _get_logit(self, netD, eval_mode=False):
     return snap.double().cpu().numpy()                      # fp32 values widened, like trainer.py:144,154
 
 
+def _host_f64(v):
+    return v.double().cpu().numpy() if torch.is_tensor(v) else np.asarray(v, dtype=np.float64)
+
+
+def _atomic_write(path: Path, write_fn):
+    """Write to ``<path>.tmp`` then rename: a job killed mid-save never leaves a truncated pickle behind (the
+    reference overwrites in place, trainer.py:138-140)."""
+    tmp = Path(str(path) + ".tmp")
+    with open(tmp, "wb") as f:
+        write_fn(f)
+        f.flush()
+        os.fsync(f.fileno())
+    os.replace(tmp, path)
+
+
 def _save_logit(self, logits_dict):
-    """``LogTrainer._save_logit`` (trainer.py:138-140): one pickle per name, ``{step: float64[N]}``."""
+    """``LogTrainer._save_logit`` (trainer.py:138-140): one pickle per name, ``{step: float64[N]}`` -- byte-for-byte what
+    ``pickle.dump`` of the reference's dict of float64 arrays produces, so train_mimicry_phase2.py:87-92 loads it unchanged.
+    With ``self.save_f32_sidecar`` a compact ``logits_<name>_f32.npz`` (steps int64 [T], logits float32 [T,N]: the values
+    ARE fp32, trainer.py:154 only widens them) is written beside it; :func:`load_logits` reads either."""
     for name, logits in logits_dict.items():
-        host = {k: (v.double().cpu().numpy() if torch.is_tensor(v) else v) for k, v in logits.items()}
-        with open(Path(self.output_path) / f'logits_{name}.pkl', 'wb') as f:
-            pickle.dump(host, f)
+        host = {k: _host_f64(v) for k, v in logits.items()}
+        _atomic_write(Path(self.output_path) / f'logits_{name}.pkl', lambda f: pickle.dump(host, f))
+        if getattr(self, "save_f32_sidecar", False) and len(host):
+            steps = np.array(list(host.keys()), dtype=np.int64)
+            arr = np.stack([host[k].astype(np.float32) for k in host])
+            _atomic_write(Path(self.output_path) / f'logits_{name}_f32.npz', lambda f: np.savez(f, steps=steps, logits=arr))
+
+
+def load_logits(path) -> dict:
+    """``{step: array [N]}`` from ``logits_<name>.pkl`` (float64, the reference's format) or the ``_f32.npz`` side-file
+    (float32 rows; insertion order = recording order either way, which is what calculate_scores' window filter walks)."""
+    path = Path(path)
+    if path.suffix == ".npz":
+        z = np.load(path)
+        return {int(k): z["logits"][i] for i, k in enumerate(z["steps"])}
+    with open(path, "rb") as f:
+        return pickle.load(f)
+
+
+def _restore_logits(self):
+    """Resume: merge the snapshots already on disk into ``logit_results`` so that the next ``_save_logit`` extends the
+    pickle instead of replacing it.  (The reference starts every run with an empty ``logit_results``, trainer.py:222, and
+    overwrites the file: a phase-1 job restarted inside the recording window silently loses the earlier snapshots.)
+    Steps recorded again after the restart replace their old rows; order stays ascending in step."""
+    out = Path(self.output_path)
+    restored = 0
+    for f in sorted(out.glob("logits_*.pkl")):
+        name = f.stem[len("logits_"):]
+        try:
+            old = load_logits(f)
+        except Exception as e:                              # unreadable pickle: keep going, the new run rewrites it
+            print(f"WARNING: could not restore {f}: {e}")
+            continue
+        merged = dict(old)
+        merged.update(self.logit_results.get(name, {}))
+        self.logit_results[name] = dict(sorted(merged.items()))
+        restored += len(old)
+    return restored
 
 
 class LogTrainer:
@@ -216,10 +270,12 @@ class LogTrainer:
 
     _get_logit = _get_logit
     _save_logit = _save_logit
+    _restore_logits = _restore_logits
 
     def __init__(self, output_path, netD, dataloader=None, netD_drs=None, device=None, save_steps=5000,
                  logit_save_steps=500, save_logits=True, save_logit_after=0, stop_save_logit_after=100000,
-                 save_eval_logits=True, recorder: LogitRecorder = None, **unused):
+                 save_eval_logits=True, recorder: LogitRecorder = None, resume_logits=True, save_f32_sidecar=False,
+                 **unused):
         self.output_path = Path(output_path)
         self.netD, self.netD_drs = netD, netD_drs
         self.train_drs = netD_drs is not None               # trainer.py:86
@@ -233,6 +289,9 @@ class LogTrainer:
         self.save_eval_logits = save_eval_logits
         self.recorder = recorder
         self.logit_results = defaultdict(dict)              # trainer.py:222
+        self.save_f32_sidecar = save_f32_sidecar
+        if resume_logits and self.save_logits and self.output_path.is_dir():
+            self._restore_logits()
 
     def should_record(self, global_step) -> bool:
         return bool(self.save_logits and global_step % self.logit_save_steps == 0

@@ -112,3 +112,33 @@ def test_save_logit_pickle_schema(tmp_path):
     got = pickle.load(open(tmp_path / "logits_netD_eval.pkl", "rb"))
     assert list(got.keys()) == [35000, 35100]
     assert all(v.dtype == np.float64 and v.shape == (5,) for v in got.values())
+
+
+def test_save_logit_is_atomic_and_resume_merges_history(tmp_path):
+    """the pickle keeps the reference's schema, is replaced atomically, and a restarted run extends
+    the history instead of overwriting it (the reference loses it: trainer.py:222 starts empty, :138-140 overwrites)."""
+    import pickle
+    from collections import defaultdict
+    from diagan_b200.trainer import trainer as T
+    tr = T.LogTrainer.__new__(T.LogTrainer)
+    tr.output_path, tr.save_f32_sidecar = tmp_path, True
+    first = {"netD_eval": {35000: np.arange(6, dtype=np.float64), 35100: np.arange(6, dtype=np.float64) + 1}}
+    tr._save_logit(first)
+    assert not list(tmp_path.glob("*.tmp"))
+    # "restart": a fresh trainer records two more steps, one of them again (35100 is overwritten by the new row)
+    tr2 = T.LogTrainer.__new__(T.LogTrainer)
+    tr2.output_path, tr2.save_f32_sidecar = tmp_path, True
+    tr2.logit_results = defaultdict(dict)
+    tr2.logit_results["netD_eval"][35100] = np.full(6, 7.0)
+    tr2.logit_results["netD_eval"][35200] = np.full(6, 9.0)
+    assert tr2._restore_logits() == 2
+    tr2._save_logit(tr2.logit_results)
+    got = pickle.load(open(tmp_path / "logits_netD_eval.pkl", "rb"))
+    assert list(got.keys()) == [35000, 35100, 35200]
+    assert np.array_equal(got[35000], first["netD_eval"][35000]) and np.all(got[35100] == 7.0) and np.all(got[35200] == 9.0)
+    assert type(got) is dict and all(v.dtype == np.float64 for v in got.values())
+    # compact side-file: same steps in the same order, float32 rows
+    side = T.load_logits(tmp_path / "logits_netD_eval_f32.npz")
+    assert list(side.keys()) == [35000, 35100, 35200] and all(v.dtype == np.float32 for v in side.values())
+    assert all(np.array_equal(side[k].astype(np.float64), got[k]) for k in got)
+    assert list(T.load_logits(tmp_path / "logits_netD_eval.pkl").keys()) == [35000, 35100, 35200]
