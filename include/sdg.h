@@ -158,6 +158,14 @@ SDG_API int sdg_set_conv_pair(int on);
 SDG_API int sdg_first_conv_h16(const void* x, int layout, const void* wb, const float* bias, void* out, int64_t n, int S,
                        int Cout, int precision, void* stream);
 
+/* ---- dataset transform (the input pipeline of the pass) ----------------------
+ * Replaces transforms.Resize(size) + transforms.CenterCrop(size) of datasets/transform.py:3-41 as applied to every item of
+ * every recording pass by the reference's DataLoader workers: one pass over the raw uint8 dataset in [n,H,W,C] (C = 3 or 1)
+ * -> out [n,size,size,C] uint8, BIT-EXACT with Pillow's 8-bit bilinear ImagingResample (horizontal pass first, 22-bit
+ * fixed point) and torchvision's Resize(int) / CenterCrop geometry.  ToTensor + Normalize(0.5, 0.5) are not materialised:
+ * sdg_d_forward normalises uint8 input on load.  in/out are device pointers. */
+SDG_API int sdg_resize_center_crop_u8(const uint8_t* in, int64_t n, int H, int W, int C, int size, uint8_t* out, void* stream);
+
 /* ---- running per-sample statistics (new: the reference keeps every snapshot, trainer.py:337-338) --
  * Welford update with snapshot number t (0-based) plus last value and sum |x_t - x_{t-1}|:
  * after T updates  ldrm = mean, ldrv = m2/(T-1), ldr = last, ldrd = sad/(T-1)  (plot.py:243-246). */

@@ -187,6 +187,28 @@ def make_stylegan2():
         print(f"stylegan2_d{size} logits[:4]", y[:4])
 
 
+def make_resize():
+    """The reference's own transform (datasets/transform.py: Resize, CenterCrop, ToTensor, Normalize) applied to PIL images
+    built like color_mnist.py:92 does; the uint8 image is recovered exactly from the normalised tensor."""
+    from PIL import Image
+    get_transform = ref_loader.reference_get_transform()
+    rng = np.random.RandomState(11)
+    out = {}
+    for tag, name, n, h, w in (("mnist28", "color_mnist", 6, 28, 28), ("celeba", "celeba", 3, 218, 178)):
+        tf = get_transform(name)
+        imgs = rng.randint(0, 256, (n, h, w, 3)).astype(np.uint8)
+        res = []
+        for im in imgs:
+            t = tf(Image.fromarray(im, mode="RGB"))                     # float [3,s,s] in [-1,1]
+            u8 = torch.round((t * 0.5 + 0.5) * 255.0).to(torch.uint8).permute(1, 2, 0).numpy()
+            res.append(u8)
+        out[f"{tag}_in"] = imgs
+        out[f"{tag}_out"] = np.stack(res)
+        out[f"{tag}_size"] = np.int64(res[0].shape[0])
+    np.savez_compressed(os.path.join(OUT, "resize_pil.npz"), **out)
+    print("resize_pil", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)      # single-thread convs: deterministic accumulation order
@@ -194,3 +216,4 @@ if __name__ == "__main__":
     make_drs()
     make_dcgan()
     make_stylegan2()
+    make_resize()

@@ -117,6 +117,16 @@ def reference_drs_class():
     return mod.DRS
 
 
+def reference_get_transform():
+    """``diagan.datasets.transform.get_transform`` (transform.py:35-41); needs torchvision + Pillow (installed here)."""
+    _ensure_path()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_transform", os.path.join(REF_PKG, "diagan", "datasets", "transform.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.get_transform
+
+
 def reference_dcgan_discriminator():
     """-> the reference's own ``MNIST_DCGAN_Discriminator`` class (mnist.py:155-223)."""
     _ensure_path()

@@ -32,26 +32,29 @@ def get_world_size() -> int:
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
-def shard_size(n: int, world: int) -> int:
-    return (n + world - 1) // world
+def shard_size(n: int, world: int, multiple: int = 1) -> int:
+    """ceil(n / world), rounded up to a multiple of ``multiple`` (StyleGAN2: the loader batch size, so that the
+    minibatch-stddev groups of consecutive batches never straddle two ranks)."""
+    s = (n + world - 1) // world
+    return (s + multiple - 1) // multiple * multiple
 
 
-def shard_range(n: int, rank: int = None, world: int = None):
+def shard_range(n: int, rank: int = None, world: int = None, multiple: int = 1):
     """Contiguous dataset-index range owned by ``rank``; trailing ranks may be short or empty."""
     rank = get_rank() if rank is None else rank
     world = get_world_size() if world is None else world
-    s = shard_size(n, world)
+    s = shard_size(n, world, multiple)
     lo = min(n, rank * s)
     return lo, min(n, lo + s)
 
 
-def all_gather_shards(local: torch.Tensor, n: int) -> torch.Tensor:
+def all_gather_shards(local: torch.Tensor, n: int, multiple: int = 1) -> torch.Tensor:
     """local: this rank's finished slice ``[hi-lo, ...]`` -> the full ``[n, ...]`` vector on every rank.
-    One collective; ragged tails are handled by padding each shard to ``ceil(n/W)``."""
+    One collective; ragged tails are handled by padding each shard to the common shard size."""
     world = get_world_size()
     if world == 1:
         return local[:n]
-    s = shard_size(n, world)
+    s = shard_size(n, world, multiple)
     tail = local.shape[1:]
     padded = local
     if local.shape[0] != s:
@@ -87,15 +90,22 @@ def concat_all_gather(tensor: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def engine_is_stylegan2(netD) -> bool:
+    sd = netD.state_dict() if hasattr(netD, "state_dict") else netD
+    return "final_conv.0.weight" in sd and "convs.0.0.weight" in sd
+
+
 def get_logit(recorder, netD, step=None) -> torch.Tensor:
     """Distributed recording pass (train_ffhq.py:128-143 semantics: every rank ends up with the full
     vector).  ``recorder`` is a :class:`diagan_b200.trainer.trainer.LogitRecorder` whose ``shard`` is this
     rank's range; returns float32 [N] on the device."""
     n = recorder.n
-    lo, hi = shard_range(n)
+    # StyleGAN2: shard boundaries on whole loader batches (the recorder drops the ragged tail of the LAST shard only)
+    mult = recorder.batch if engine_is_stylegan2(netD) else 1
+    lo, hi = shard_range(n, multiple=mult)
     recorder.shard = (lo, hi)
     snap = recorder.record(netD)
-    full = all_gather_shards(snap[lo:hi], n)
+    full = all_gather_shards(snap[lo:hi], n, multiple=mult)
     if step is not None:
         recorder.observe(step, full)
     return full

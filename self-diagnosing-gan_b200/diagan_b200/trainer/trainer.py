@@ -54,6 +54,13 @@ class ResidentDataset:
         return cls(torch.from_numpy(np.ascontiguousarray(arr)).to(device))
 
     @classmethod
+    def from_raw_images(cls, images_u8: np.ndarray, dataset_name: str, device):
+        """Raw uint8 images [N,H,W,3] at their stored size (CelebA 218x178, Colour-MNIST 28x28 ...) -> the reference's
+        Resize + CenterCrop (datasets/transform.py) done once on the GPU, bit-exact with the PIL pipeline."""
+        from ..datasets.transform import get_transform
+        return cls(get_transform(dataset_name).from_host(images_u8, device))
+
+    @classmethod
     def from_dataset(cls, dataset, device, batch_size=1024):
         """Materialise any ``WeightedDataset``-style dataset (``(data, target, weight, index)`` items,
         predefined.py:17-27, or ``(img, idx)``, stylegan2/dataset.py:63) once, as float32 NCHW."""

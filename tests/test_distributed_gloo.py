@@ -51,6 +51,14 @@ def _worker(rank, world, port, n, out_dir):
     want = so.score_from_moments(mean, var, t)
     assert np.array_equal(got, want)
 
+    # (2b) batch-aligned shards (StyleGAN2 minibatch-stddev groups stay inside one rank): boundaries are multiples of 8,
+    # the ranges still tile [0, n) and the same single all-gather reassembles the vector
+    blo, bhi = D.shard_range(n, multiple=8)
+    assert (blo % 8 == 0 or blo == n) and (bhi % 8 == 0 or bhi == n)
+    spans = [D.shard_range(n, r, world, 8) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    assert np.array_equal(D.all_gather_shards(torch.from_numpy(mean[blo:bhi].copy()), n, multiple=8).numpy(), mean)
+
     # (3) reference-contract concat_all_gather (train_ffhq.py:150-161)
     idx = torch.arange(rank * 4, rank * 4 + 4)
     assert D.concat_all_gather(idx).tolist() == list(range(world * 4))

@@ -670,6 +670,41 @@ def test_stylegan2_tensorcore_vs_reference_golden(golden_dir, size, prec, tol, d
 
 
 # ---------------------------------------------------------------------------------------------------
+# input pipeline: Resize + CenterCrop on the GPU, bit-exact with the reference's PIL transform
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("h,w,size,n", [(28, 28, 32, 37), (218, 178, 64, 9), (45, 37, 32, 5), (37, 45, 32, 5), (100, 300, 64, 3),
+                                         (32, 32, 32, 4), (64, 48, 64, 3), (20, 20, 64, 2), (500, 333, 64, 2)])
+def test_resize_center_crop_bit_exact_vs_pil_and_oracle(h, w, size, n, dev):
+    from diagan_b200.datasets.transform import DeviceTransform
+    from oracle import resize as resize_oracle
+    rng = np.random.RandomState(h * 1000 + w)
+    imgs = rng.randint(0, 256, (n, h, w, 3)).astype(np.uint8)
+    got = DeviceTransform(size)(torch.from_numpy(imgs).to(dev)).cpu().numpy()
+    assert got.shape == (n, size, size, 3)
+    assert np.array_equal(got, resize_oracle.resize_center_crop_u8(imgs, size))
+    try:                                                      # the real thing, when the box has it (same image: it does)
+        from PIL import Image
+        import torchvision.transforms as T
+        tf = T.Compose([T.Resize(size), T.CenterCrop(size)])
+        want = np.stack([np.asarray(tf(Image.fromarray(im, mode="RGB"))) for im in imgs])
+        assert np.array_equal(got, want)
+    except ImportError:
+        pass
+
+
+def test_resident_dataset_from_raw_colour_mnist_shape(dev):
+    """Colour-MNIST items are 28x28 uint8 RGB, resized to 32 (color_mnist.py:90-100 + transform.py:23-31): the resident
+    dataset built on the GPU equals the per-item PIL path, normalisation included (first-conv LUT == ToTensor + Normalize)."""
+    from diagan_b200.trainer.trainer import ResidentDataset
+    from oracle import resize as resize_oracle
+    rng = np.random.RandomState(5)
+    raw = (rng.rand(64, 28, 28, 1) < 0.19).astype(np.uint8) * np.array([255, 0, 0], np.uint8)      # red digits-like masks
+    ds = ResidentDataset.from_raw_images(raw, "color_mnist", dev)
+    assert ds.data.shape == (64, 32, 32, 3) and ds.data.dtype == torch.uint8
+    assert np.array_equal(ds.data.cpu().numpy(), resize_oracle.resize_center_crop_u8(raw, 32))
+
+
+# ---------------------------------------------------------------------------------------------------
 # the recorder end to end: pass -> snapshots -> pickle -> calculate_scores -> weights
 # ---------------------------------------------------------------------------------------------------
 def test_recorder_end_to_end(tmp_path, dev):

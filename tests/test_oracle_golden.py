@@ -119,3 +119,26 @@ def test_stylegan2_oracle_matches_reference(golden_dir, size):
     y = sg2_oracle.logits_pass(params, torch.from_numpy(g["x_u8"]), size, int(g["batch"]))
     np.testing.assert_allclose(y, g["logits"], rtol=2e-5, atol=1e-6)
     assert sg2_oracle.block_channels(256) == [(128, 256), (256, 512), (512, 512), (512, 512), (512, 512), (512, 512)]
+
+
+@pytest.mark.parametrize("h,w,size", [(28, 28, 32), (218, 178, 64), (45, 37, 32), (37, 45, 32), (100, 300, 64), (32, 32, 32),
+                                      (64, 48, 64), (20, 20, 64)])
+def test_resize_oracle_bit_exact_vs_pillow(h, w, size):
+    """oracle/resize.py (restatement of Pillow's 8-bit bilinear resample + torchvision geometry) against the real
+    libraries, which ARE installed in this image: every dataset shape of the reference plus odd ones."""
+    Image = pytest.importorskip("PIL.Image")
+    T = pytest.importorskip("torchvision.transforms")
+    from oracle import resize as R
+    rng = np.random.RandomState(h + 7 * w)
+    img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    want = np.asarray(T.Compose([T.Resize(size), T.CenterCrop(size)])(Image.fromarray(img, mode="RGB")))
+    assert np.array_equal(R.resize_center_crop_u8(img, size), want)
+
+
+def test_resize_oracle_golden(golden_dir):
+    """Committed fixture generated from Pillow/torchvision by oracle/make_golden.py (travels to boxes without them)."""
+    from oracle import resize as R
+    g = np.load(os.path.join(golden_dir, "resize_pil.npz"))
+    for tag in ("mnist28", "celeba"):
+        size = int(g[f"{tag}_size"])
+        assert np.array_equal(R.resize_center_crop_u8(g[f"{tag}_in"], size), g[f"{tag}_out"])
