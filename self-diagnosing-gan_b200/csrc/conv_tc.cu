@@ -690,6 +690,156 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------
+// CTA-pair kernel with STREAMED weights: one tcgen05.mma.cta_group::2 of M = 256 x N = BN per K step, for layers whose
+// weights do not fit in shared memory.  BN = 256 (Cout % 256 == 0: StyleGAN2 and SNGAN-64 bodies): every CTA stages its own
+// 128-pixel A tile (16 KB) and HALF of the 256-row B tile (16 KB) per stage, i.e. the same shared-memory traffic as the
+// single-CTA N = 128 kernel for twice the MMA work -- half the operand bytes per FLOP, which is what the power-capped
+// tensor pipe rewards (cuBLAS runs 256-wide tiles for the same reason).  The accumulator is 2 stages x 256 TMEM columns.
+// BN = 128 serves the separate-accumulator skip form (main 128 + skip 128 columns per stage).
+// Barrier protocol = conv_pair_kernel: full / accumulator-empty live in the leader, stage-empty / accumulator-full are
+// multicast by the leader's tcgen05.commit.
+template <int BN, bool F16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_pair_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        const __grid_constant__ CUtensorMap map_s, const TcParams p, const int n_stages) {
+  constexpr int B_HALF = (BN / 2) * TC_BK * 2;
+  constexpr int STAGE = TC_A_BYTES + B_HALF;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  __shared__ __align__(8) uint64_t bar_full[8];
+  __shared__ __align__(8) uint64_t bar_empty[8];
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[TC_MAX_COUT];
+  __shared__ __align__(16) float s_w3[128 * 3];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int main_iters = p.taps * p.kchunks;
+  const int k_iters = main_iters + p.sc_chunks;
+  const uint32_t tmem_cols = (BN == 256 || p.sc_sep) ? 512u : 256u;
+  const uint32_t acc_stride = p.sc_sep ? 2 * BN : BN;
+
+  for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+  if (p.img)
+    for (int i = threadIdx.x; i < 128 * 3; i += TC_THREADS) s_w3[i] = p.sc_w3[i];
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (p.sc_chunks) tma_prefetch_desc(&map_s);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_acc_full[s]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[s]), 8);       // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_slot), tmem_cols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const long long cluster_id = blockIdx.x >> 1;
+  const long long n_clusters = gridDim.x >> 1;
+  const long long pair_tiles = (p.m_tiles + 1) >> 1;
+  const long long total = pair_tiles * p.n_tiles;       // n tile fastest: consecutive work items share the A tiles (L2)
+
+  if (warp == 0) {
+    // ================= TMA producer: own A tile + own half of the B tile per k iteration =================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = cluster_id; t < total; t += n_clusters) {
+        const int nt = (int)(t % p.n_tiles);
+        const long long mt = 2 * (t / p.n_tiles) + rank;
+        int n0, y0, x0;
+        tc_tile_origin(p, mt, n0, y0, x0);
+        int tap = 0, kc = 0;
+        for (int it = 0; it < k_iters; ++it) {
+          bool is_sc;
+          int dy, dx, ch;
+          tc_k_iter(p, it, main_iters, tap, kc, is_sc, ch, dy, dx);
+          const CUtensorMap* am = is_sc ? &map_s : &map_a;
+          const int cs = (is_sc && p.sc_sep) ? 1 : p.cs;
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[stage]), 0);
+          if (leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * STAGE);
+          const uint32_t dst = smem_base + stage * STAGE;
+          tma_load_4d_pair(dst, am, full_leader, ch * TC_BK, cs * x0 + dx, cs * y0 + dy, n0);
+          tma_load_2d_pair(dst + TC_A_BYTES, &map_b, full_leader, it * TC_BK, nt * BN + (int)rank * (BN / 2));
+          if (++kc == p.kchunks) { kc = 0; ++tap; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc(256, BN, F16);
+      int stage = 0;
+      uint32_t phase = 0;
+      long long local = 0;
+      for (long long t = cluster_id; t < total; t += n_clusters, ++local) {
+        const int acc = (int)(local & 1);
+        const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
+        mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + (uint32_t)acc * acc_stride;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * STAGE;
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + TC_A_BYTES);
+          const bool sep = p.sc_sep && it >= main_iters;
+          const uint32_t d_tmem = sep ? d_main + BN : d_main;
+          const int it0 = sep ? it - main_iters : it;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it0 | k) != 0 ? 1u : 0u);
+          umma_commit_pair(smem_u32(&bar_empty[stage]), 3);
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(smem_u32(&bar_acc_full[acc]), 3);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: this CTA's 128 TMEM lanes x BN columns =================
+    const int q = warp - 4;
+    long long local = 0;
+    for (long long t = cluster_id; t < total; t += n_clusters, ++local) {
+      const int nt = (int)(t % p.n_tiles);
+      const long long mt = 2 * (t / p.n_tiles) + rank;
+      const int acc = (int)(local & 1);
+      const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
+      tc_epilogue_tile<BN, F16>(p, s_bias, s_w3, tmem_base + (uint32_t)acc * acc_stride, mt, nt, q, lane,
+                                smem_u32(&bar_acc_full[acc]), acc_phase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_acc_empty[acc]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -704,7 +854,8 @@ constexpr int tc_smem_bytes() { return TC_STAGES * (TC_A_BYTES + BN * TC_BK * 2)
 int tc_num_sms() { return g_num_sms; }
 
 constexpr int kPairSmemMax = 227 * 1024 - 3072;       // dynamic shared memory budget of the pair kernel (static: ~2.5 KB)
-static int g_pair_mode = 1;                          // 0 = never use the CTA-pair kernel, 1 = use it where it applies
+constexpr int kStreamSmem = 1024 + 6 * (TC_A_BYTES + 128 * TC_BK * 2);   // 6 x 32 KB (BN 256) = 8 x 24 KB (BN 128) stages
+static int g_pair_mode = 1;                          // 0 = never use the CTA-pair kernels, 1 = use them where they apply
 void conv_tc_set_pair(int on) { g_pair_mode = on; }
 
 int tc_encode_2d(CUtensorMap* map, const void* ptr, int f16, uint64_t inner, uint64_t outer, uint32_t box_inner,
@@ -753,6 +904,10 @@ int conv_tc_init(int device) {
   SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>()));
   SDG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemMax));
   SDG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemMax));
+  SDG_CUDA(cudaFuncSetAttribute((conv_pair_stream_kernel<256, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
+  SDG_CUDA(cudaFuncSetAttribute((conv_pair_stream_kernel<256, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
+  SDG_CUDA(cudaFuncSetAttribute((conv_pair_stream_kernel<128, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
+  SDG_CUDA(cudaFuncSetAttribute((conv_pair_stream_kernel<128, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
   g_encode = (EncodeTiledFn)fn;
   int rc = first_conv_init();
   if (rc) { g_encode = nullptr; return rc; }
@@ -852,7 +1007,8 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   { int rc = tc_encode_2d(&map_b, a.wb, f16, k_cols, Cout, TC_BK, BN); if (rc) return rc; }
 
   const int k_iters = p.taps * p.kchunks + p.sc_chunks;
-  if (g_pair_mode && Cout == 128 && taps == 9 && k_iters <= PAIR_MAX_KI && p.m_tiles >= 2 && !p.sc_sep) {
+  static const int stream_all = getenv("SDG_PAIR_STREAM128") ? atoi(getenv("SDG_PAIR_STREAM128")) == 2 : 0;
+  if (g_pair_mode && Cout == 128 && taps == 9 && k_iters <= PAIR_MAX_KI && p.m_tiles >= 2 && !p.sc_sep && !stream_all) {
     // CTA-pair kernel: weights resident (64 rows per CTA), A streamed through as many 16 KB stages as fit
     CUtensorMap map_bh;
     { int rc = tc_encode_2d(&map_bh, a.wb, f16, k_cols, Cout, TC_BK, 64); if (rc) return rc; }
@@ -875,6 +1031,36 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (f16) { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<true>, map_a, map_bh, map_s, p, n_stages)); }
     else { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<false>, map_a, map_bh, map_s, p, n_stages)); }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
+  // Cout = 128 layers whose weights are too large to stay resident (SNGAN-32 block1.c2 / block2.c2 in the 4x4 stride-2 form)
+  // also run as CTA pairs, N = 128, weights streamed (measured +1.9 % on the whole SNGAN-32 pass); 0 disables, 2 = experiment:
+  // streamed weights for EVERY Cout = 128 3x3 layer instead of the resident-weight kernel
+  static const int stream128 = getenv("SDG_PAIR_STREAM128") ? atoi(getenv("SDG_PAIR_STREAM128")) : 1;
+  const int sbn = (!p.sc_sep && Cout % 256 == 0) ? 256 : ((p.sc_sep || (stream128 && Cout == 128)) && Cout % 128 == 0 ? 128 : 0);
+  if (g_pair_mode && sbn && p.m_tiles >= 2 && !p.pool && (!p.img || Cout == 128)) {
+    // CTA-pair kernel with streamed weights: M = 256 x N = sbn per MMA
+    p.n_tiles = Cout / sbn;
+    CUtensorMap map_bh;
+    { int rc = tc_encode_2d(&map_bh, a.wb, f16, k_cols, Cout, TC_BK, sbn / 2); if (rc) return rc; }
+    const int n_stages = sbn == 256 ? 6 : 8;
+    const long long total = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    long long clusters = g_num_sms / 2;
+    if (total < clusters) clusters = total;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = kStreamSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (sbn == 256 && f16) { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_stream_kernel<256, true>, map_a, map_bh, map_s, p, n_stages)); }
+    else if (sbn == 256) { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_stream_kernel<256, false>, map_a, map_bh, map_s, p, n_stages)); }
+    else if (f16) { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_stream_kernel<128, true>, map_a, map_bh, map_s, p, n_stages)); }
+    else { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_stream_kernel<128, false>, map_a, map_bh, map_s, p, n_stages)); }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
   }

@@ -276,30 +276,30 @@ int sg2_first_conv_h16(const void* x, int layout, const float* w3, const float* 
 // filters horizontally (4 loads of 16 B, neighbours hit L1) and keeps the last four filtered rows in registers, so every
 // input pixel leaves DRAM once and every output costs 4 (ST = 1) or 8 (ST = 2) L1 loads instead of 16.
 // ST = 2 evaluates only the even blur outputs: all that the stride-2 1x1 skip conv reads (stylegan2.py:575-590).
+// column taps of one thread: loop-invariant pointers (clamped inside the image) and weights (zero outside)
+struct BlurCols {
+  const h16* p[4];
+  float w[4];
+};
+
 template <bool F16>
-__device__ __forceinline__ void blur_hrow(const h16* __restrict__ img, int iy, int ix0, int H, int W, int C, float (&o)[8]) {
+__device__ __forceinline__ void blur_hrow(const BlurCols& bc, int iy, int H, int64_t row_stride, float (&o)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) o[j] = 0.f;
   if (iy < 0 || iy >= H) return;
-  const h16* row = img + (int64_t)iy * W * C;
+  const int64_t ro = (int64_t)iy * row_stride;
   // the four loads are issued unconditionally (clamped address, zero weight outside the image) so they overlap
   uint4 raw[4];
-  float kw[4];
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const int ix = ix0 + b;
-    const bool ok = ix >= 0 && ix < W;
-    kw[b] = ok ? ((b == 0 || b == 3) ? 0.125f : 0.375f) : 0.f;
-    raw[b] = __ldg(reinterpret_cast<const uint4*>(row + (int64_t)(ok ? ix : 0) * C));
-  }
+  for (int b = 0; b < 4; ++b) raw[b] = __ldg(reinterpret_cast<const uint4*>(bc.p[b] + ro));
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
     const uint32_t* wv = reinterpret_cast<const uint32_t*>(&raw[b]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 t = unpack_h2<F16>(wv[j]);
-      o[2 * j] = fmaf(kw[b], t.x, o[2 * j]);
-      o[2 * j + 1] = fmaf(kw[b], t.y, o[2 * j + 1]);
+      o[2 * j] = fmaf(bc.w[b], t.x, o[2 * j]);
+      o[2 * j + 1] = fmaf(bc.w[b], t.y, o[2 * j + 1]);
     }
   }
 }
@@ -317,31 +317,53 @@ blur_h16_kernel(const h16* __restrict__ in, h16* __restrict__ out, int H, int W,
   const int x = xt * (256 >> c8_shift) + (threadIdx.x >> c8_shift);
   if (x >= Wo) return;
   const h16* img = in + n * H * W * (int64_t)C + cg * 8;
-  h16* dst = out + n * Ho * Wo * (int64_t)C + cg * 8;
+  const int64_t row_stride = (int64_t)W * C;
   const int y0 = ys * rows, y1 = min(Ho, y0 + rows);
-  const int ix0 = x * ST - pad;
+  h16* dst = out + ((n * Ho + y0) * Wo + x) * (int64_t)C + cg * 8;
+  const int64_t dst_stride = (int64_t)Wo * C;
+  BlurCols bc;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int ix = x * ST - pad + t;
+    const bool ok = ix >= 0 && ix < W;
+    bc.w[t] = ok ? ((t == 0 || t == 3) ? 0.125f : 0.375f) : 0.f;
+    bc.p[t] = img + (int64_t)(ok ? ix : 0) * C;
+  }
   float h0[8], h1[8], h2[8], h3[8];
-  // filtered input rows y*ST - pad + {0,1,2,3} feed output row y
-  blur_hrow<F16>(img, y0 * ST - pad, ix0, H, W, C, h0);
-  blur_hrow<F16>(img, y0 * ST - pad + 1, ix0, H, W, C, h1);
-  if (ST == 1) blur_hrow<F16>(img, y0 - pad + 2, ix0, H, W, C, h2);
-#pragma unroll 2
-  for (int y = y0; y < y1; ++y) {
-    if (ST == 2) blur_hrow<F16>(img, y * 2 - pad + 2, ix0, H, W, C, h2);
-    blur_hrow<F16>(img, y * ST - pad + 3, ix0, H, W, C, h3);
+  // filtered input rows y*ST - pad + {0,1,2,3} feed output row y.  The four row buffers rotate roles by NAME (the loop body is
+  // written out for one full rotation) so no register is ever copied.
+  auto emit = [&](const float (&a)[8], const float (&b2)[8], const float (&c)[8], const float (&d)[8]) {
     uint4 pk;
     uint32_t* hp = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float a = 0.125f * (h0[2 * j] + h3[2 * j]) + 0.375f * (h1[2 * j] + h2[2 * j]);
-      const float c = 0.125f * (h0[2 * j + 1] + h3[2 * j + 1]) + 0.375f * (h1[2 * j + 1] + h2[2 * j + 1]);
-      hp[j] = pack_h2<F16>(a, c);
+      const float e = 0.125f * (a[2 * j] + d[2 * j]) + 0.375f * (b2[2 * j] + c[2 * j]);
+      const float f = 0.125f * (a[2 * j + 1] + d[2 * j + 1]) + 0.375f * (b2[2 * j + 1] + c[2 * j + 1]);
+      hp[j] = pack_h2<F16>(e, f);
     }
-    *reinterpret_cast<uint4*>(dst + ((int64_t)y * Wo + x) * C) = pk;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (ST == 1) { h0[j] = h1[j]; h1[j] = h2[j]; h2[j] = h3[j]; }
-      else { h0[j] = h2[j]; h1[j] = h3[j]; }
+    *reinterpret_cast<uint4*>(dst) = pk;
+    dst += dst_stride;
+  };
+  blur_hrow<F16>(bc, y0 * ST - pad, H, row_stride, h0);
+  blur_hrow<F16>(bc, y0 * ST - pad + 1, H, row_stride, h1);
+  if (ST == 1) {
+    blur_hrow<F16>(bc, y0 - pad + 2, H, row_stride, h2);
+    int iy = y0 - pad + 3;                       // next input row to filter
+    for (int y = y0; y < y1; y += 4, iy += 4) {
+      blur_hrow<F16>(bc, iy, H, row_stride, h3); emit(h0, h1, h2, h3);
+      if (y + 1 >= y1) break;
+      blur_hrow<F16>(bc, iy + 1, H, row_stride, h0); emit(h1, h2, h3, h0);
+      if (y + 2 >= y1) break;
+      blur_hrow<F16>(bc, iy + 2, H, row_stride, h1); emit(h2, h3, h0, h1);
+      if (y + 3 >= y1) break;
+      blur_hrow<F16>(bc, iy + 3, H, row_stride, h2); emit(h3, h0, h1, h2);
+    }
+  } else {
+    int iy = y0 * 2 - pad + 2;
+    for (int y = y0; y < y1; y += 2, iy += 4) {
+      blur_hrow<F16>(bc, iy, H, row_stride, h2); blur_hrow<F16>(bc, iy + 1, H, row_stride, h3); emit(h0, h1, h2, h3);
+      if (y + 1 >= y1) break;
+      blur_hrow<F16>(bc, iy + 2, H, row_stride, h0); blur_hrow<F16>(bc, iy + 3, H, row_stride, h1); emit(h2, h3, h0, h1);
     }
   }
 }
