@@ -65,6 +65,9 @@ struct TcParams {
   const float* bias;         // [Cout] (shortcut bias already added)
   const float* sd;           // per-sample scalar of a spatially constant extra input channel (minibatch-stddev) or null
   const float* sd_w;         // its summed weights [H*W][Cout]
+  const float* head_w;       // fused SNGAN head (last block): logit[n] += sum_c head_w[c] * sum_px relu(v[px][c]) (+ head_b once)
+  const float* head_b;
+  float* head_out;           // [n_images] zero-initialised by the caller; at most two warps contribute per image
   const float* res_f32;      // identity shortcut, fp32 [out pixels][Cout] or null
   const void* img;           // network input for the 3-FMA shortcut (DBlockOptimized) or null
   const float* sc_w3;        // [Cout][3] fp32, W_sc / sigma
@@ -245,6 +248,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
     }
     mbar_wait(acc_full_bar, acc_phase);
     tc_fence_after();
+    float head_part = 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -322,6 +326,10 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
       }
+      if (p.head_out && active) {          // s_w3 holds the head weights in this mode
+#pragma unroll
+        for (int j = 0; j < 32; ++j) head_part = fmaf(s_w3[nt * BN + c0 + j], fmaxf(v[j], 0.f), head_part);
+      }
       if (active) {
         if (p.res_f32 && !lin) {
           const float4* rp = reinterpret_cast<const float4*>(p.res_f32 + obase + c0);
@@ -387,6 +395,17 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
         }
       }
     }
+    if (p.head_out) {
+      // fused head: this warp's 32 pixels belong to ONE image (H*W is 32 or 64); fixed shuffle tree, then one atomic per
+      // warp.  With at most two addends into a zeroed slot the fp32 sum does not depend on their order: deterministic.
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) head_part += __shfl_xor_sync(0xffffffffu, head_part, o);
+      if (lane == 0 && wpix < p.total_pixels) {
+        const long long img = wpix / HW;
+        if (wpix - img * HW == 0) head_part += p.head_b[0];
+        atomicAdd(p.head_out + img, head_part);
+      }
+    }
   }
 }
 
@@ -415,6 +434,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   if (p.img)
     for (int i = threadIdx.x; i < p.Cout * 3; i += TC_THREADS) s_w3[i] = p.sc_w3[i];
+  if (p.head_out)
+    for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) s_w3[i] = p.head_w[i];
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -572,6 +593,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   for (int i = threadIdx.x; i < 128; i += TC_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   if (p.img)
     for (int i = threadIdx.x; i < 128 * 3; i += TC_THREADS) s_w3[i] = p.sc_w3[i];
+  if (p.head_out)
+    for (int i = threadIdx.x; i < 128; i += TC_THREADS) s_w3[i] = p.head_w[i];
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -727,6 +750,8 @@ conv_pair_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   if (p.img)
     for (int i = threadIdx.x; i < 128 * 3; i += TC_THREADS) s_w3[i] = p.sc_w3[i];
+  if (p.head_out)
+    for (int i = threadIdx.x; i < 128; i += TC_THREADS) s_w3[i] = p.head_w[i];
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -936,7 +961,9 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   SDG_REQUIRE(a.sc_C % TC_BK == 0, SDG_E_UNSUPPORTED, "conv_tc: shortcut channels %d", a.sc_C);
   SDG_REQUIRE((a.sc_C == 0) == (a.sc_in == nullptr), SDG_E_INVALID, "conv_tc: shortcut tensor / channels mismatch");
   SDG_REQUIRE(!a.img || (a.pool && a.sc_w3), SDG_E_INVALID, "conv_tc: image shortcut needs pooling and weights");
-  SDG_REQUIRE(a.out_relu || a.out_raw || a.out_f32, SDG_E_INVALID, "conv_tc: no output");
+  SDG_REQUIRE(a.out_relu || a.out_raw || a.out_f32 || a.head_out, SDG_E_INVALID, "conv_tc: no output");
+  SDG_REQUIRE(!a.head_out || (a.head_w && a.head_b && Cout == 128 && !a.pool && !a.img && (H * W == 32 || H * W == 64) && !a.gemm),
+              SDG_E_UNSUPPORTED, "conv_tc: fused head needs Cout = 128, an un-pooled stage and 32 or 64 pixels per image");
   auto al16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
   SDG_REQUIRE(al16(a.in) && al16(a.wb) && al16(a.sc_in) && al16(a.res_f32) && al16(a.out_relu) && al16(a.out_raw) &&
                   al16(a.out_f32), SDG_E_INVALID, "conv_tc: pointers must be 16-byte aligned");
@@ -994,7 +1021,8 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   p.debug_skip_epi = dbg_skip_epi;
   p.n_images = a.n;
   p.total_pixels = a.n * Hc * Wc;
-  p.bias = a.bias; p.sd = a.sd; p.sd_w = a.sd_w; p.res_f32 = a.res_f32; p.img = a.img; p.sc_w3 = a.sc_w3;
+  p.bias = a.bias; p.sd = a.sd; p.sd_w = a.sd_w; p.res_f32 = a.res_f32;
+  p.head_w = a.head_w; p.head_b = a.head_b; p.head_out = a.head_out; p.img = a.img; p.sc_w3 = a.sc_w3;
   p.out_relu = a.out_relu; p.out_raw = a.out_raw; p.out_f32 = a.out_f32;
   const int es = strided ? 2 : 1;               // TMA traversal stride over input pixels
 

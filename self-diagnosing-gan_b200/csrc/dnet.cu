@@ -414,6 +414,7 @@ static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, 
   float* hF[2] = {c->buf[5].as<float>(), c->buf[6].as<float>()};  // raw h, fp32: residual stream / head input
   int rc;
   int hw = S, cur = 0;
+  bool fused_head_done = false;
   for (int bi = 0; bi < nblk; ++bi) {
     const BlockSpec& bl = c->blocks[bi];
     const int i1 = c->block_first_conv[bi];
@@ -432,6 +433,15 @@ static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, 
     a2.out_relu = last ? nullptr : hR[o];
     a2.out_raw = (next_sc && !c->inplace_relu) ? hW[o] : nullptr;
     a2.out_f32 = (last || !next_sc) ? hF[o] : nullptr;
+    // last block of SNGAN-32 (8x8, 128 channels, identity shortcut): ReLU -> sum-pool -> SNLinear fused into the epilogue
+    static const int fuse_head_env = getenv("SDG_FUSE_HEAD") ? atoi(getenv("SDG_FUSE_HEAD")) : 1;
+    const bool fuse_head = fuse_head_env && last && !bl.down && c2.cout == 128 && (ho * ho == 64 || ho * ho == 32) && bl.kind == 1;
+    if (fuse_head) {
+      SDG_CUDA(cudaMemsetAsync(logits, 0, sizeof(float) * (size_t)nb, s));
+      a2.out_f32 = nullptr;
+      a2.head_w = c->head_w.as<float>(); a2.head_b = c->head_b.as<float>(); a2.head_out = logits;
+      fused_head_done = true;
+    }
     if (bl.kind == 0) {
       // DBlockOptimized: c1 straight from the image bytes; shortcut c_sc(avg_pool2d(x)) as 3 FMAs in c2's epilogue
       if ((rc = first_conv(x, layout, c1.w16.as<h16>(), c1.bias.as<float>(), T, nb, S, c1.cout, f16, s))) return rc;
@@ -458,6 +468,7 @@ static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, 
     cur = o;
     hw = ho;
   }
+  if (fused_head_done) return 0;
   return head_sumpool_fp32(hF[cur], c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, hw * hw, c->head_len, 1, s);
 }
 

@@ -144,6 +144,12 @@ struct TcConv {
   int gemm = 0;                   // 1: plain GEMM rows: in = [W rows][Cin] (H = 1, any W >= 1), taps = 1  (EqualLinear)
   const float* sd = nullptr;      // [n] per-sample scalar of a spatially constant extra input channel (minibatch-stddev) ...
   const float* sd_w = nullptr;    // ... and its summed weights [H*W][Cout]: v += sd[n] * sd_w[pixel][o] before the activation
+  // fused SNGAN head (ReLU -> sum over H,W -> SNLinear) for the LAST block: head_out[n] += head_b + sum_c head_w[c] * sum_px
+  // relu(v); head_out must be zeroed by the caller; Cout = 128 and H*W in {32, 64} (at most two warps add per image, so the
+  // fp32 result is order-independent).  No other output is required in this mode.
+  const float* head_w = nullptr;
+  const float* head_b = nullptr;
+  float* head_out = nullptr;
   const float* res_f32 = nullptr; // identity shortcut [n,Ho,Wo,Cout] fp32
   int res_relu = 0;               // rectify the identity shortcut (mimicry's in-place ReLU aliasing)
   const void* img = nullptr;      // network input (DBlockOptimized: shortcut = Wsc3 . avg_pool2d(img) at pooled res)
