@@ -236,8 +236,9 @@ def run_ours(args, rank, world, local_rank):
         "whole_path_tflops": value / world * FLOP_PER_SAMPLE / 1e12,
         "roofline": {
             "bound": "tensor",
-            "kernel": "conv_tc_kernel<128> block1.c2 (3x3 128->128 @32x32 + avg-pool + shortcut; 55.5% of the reference FLOPs), "
-                      "run as the algebraically equal 4x4 stride-2 conv",
+            "kernel": "conv_swap_kernel block1.c2 (3x3 128->128 @32x32 + avg-pool + shortcut; 55.5% of the reference FLOPs), "
+                      "run as the algebraically equal 4x4 stride-2 conv with role-swapped operands (M = 128 channels, "
+                      "N = 256 pixels per tcgen05.mma)",
             "achieved": dom_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
             "frac": (dom_tflops / peaks["bf16_sustained"]) if dom_tflops else None,
             "flops_counted": "EXECUTED by the tensor pipe (2*M*N*K of the GEMM run: 16 taps per pooled pixel)",

@@ -865,6 +865,251 @@ conv_pair_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Role-swapped kernel for Cout = 128 layers (every 3x3 conv of SNGAN-32, StyleGAN2's 256x256 conv1):
+//     D^T[128 channels, 256 pixels] = W[128, K] * A[256 pixels, K]^T
+// i.e. the WEIGHTS are the UMMA "A" operand (M = 128) and the pixel tile is the "B" operand with N = 256, so that one
+// tcgen05.mma covers 128 x 256 x 16 -- twice the work per instruction of the pixel-major kernels, whose N is capped at
+// Cout = 128.  Measured (profiles/r1e_ncu_full_pair_stream_summary.txt): N = 128 instructions keep the tensor pipe 55-58 %
+// busy, N = 256 instructions 95 %; the instruction, not shared-memory bandwidth, is the unit that has to be large.
+// The accumulator comes out transposed: TMEM lane = output channel, column = pixel.  That suits NHWC: for a fixed pixel the
+// 32 lanes of an epilogue warp hold 32 consecutive channels, so every global access of the epilogue (16-bit / fp32 stores,
+// fp32 residual loads) is a contiguous 64 / 128-byte segment with no shuffle transposes at all.
+// Per stage: weights 16 KB + two 128-pixel boxes 32 KB; 4 stages; accumulator 2 x 256 TMEM columns.
+constexpr int SW_STAGE = 3 * TC_A_BYTES;      // 48 KB
+constexpr int SW_STAGES = 4;
+constexpr int kSwapSmem = 1024 + SW_STAGES * SW_STAGE;
+
+template <bool F16>
+__device__ __forceinline__ uint16_t to_h16(float v) { return (uint16_t)(pack_h2<F16>(v, 0.f) & 0xffffu); }
+
+template <bool F16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_s, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  __shared__ __align__(8) uint64_t bar_full[SW_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[SW_STAGES];
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_px[256 * 3];              // pooled normalised image pixels of the current tile (image shortcut)
+  __shared__ float s_head[4 * 8];              // per-warp partial logits of the (up to 8) images of the current tile
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (p.sc_chunks) tma_prefetch_desc(&map_s);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SW_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_acc_full[s]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[s]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const long long tiles = (p.m_tiles + 1) >> 1;          // 256-pixel tiles = pairs of 128-pixel boxes
+  const int main_iters = p.taps * p.kchunks;
+  const int k_iters = main_iters + p.sc_chunks;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        int n0[2], y0[2], x0[2];
+        tc_tile_origin(p, 2 * t, n0[0], y0[0], x0[0]);
+        tc_tile_origin(p, 2 * t + 1, n0[1], y0[1], x0[1]);      // beyond the last box: image index >= n, zero filled
+        int tap = 0, kc = 0;
+        for (int it = 0; it < k_iters; ++it) {
+          bool is_sc;
+          int dy, dx, ch;
+          tc_k_iter(p, it, main_iters, tap, kc, is_sc, ch, dy, dx);
+          const CUtensorMap* am = is_sc ? &map_s : &map_a;
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          mbar_expect_tx(full, SW_STAGE);
+          const uint32_t dst = smem_base + stage * SW_STAGE;
+          tma_load_2d(dst, &map_b, full, it * TC_BK, 0);
+          tma_load_4d(dst + TC_A_BYTES, am, full, ch * TC_BK, p.cs * x0[0] + dx, p.cs * y0[0] + dy, n0[0]);
+          tma_load_4d(dst + 2 * TC_A_BYTES, am, full, ch * TC_BK, p.cs * x0[1] + dx, p.cs * y0[1] + dy, n0[1]);
+          if (++kc == p.kchunks) { kc = 0; ++tap; }
+          if (++stage == SW_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: M = 128 channels, N = 256 pixels =================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(128, 256, F16);
+      int stage = 0;
+      uint32_t phase = 0;
+      long long local = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
+        const int acc = (int)(local & 1);
+        const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
+        mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          const uint32_t w_addr = smem_base + stage * SW_STAGE;
+          const uint64_t wdesc = make_sw128_desc(w_addr);
+          const uint64_t pdesc = make_sw128_desc(w_addr + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(d_tmem, wdesc + (uint64_t)(2 * k), pdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&bar_empty[stage]));
+          if (++stage == SW_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&bar_acc_full[acc]));
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: thread = output channel, TMEM columns = the tile's 256 pixels =================
+    const int q = warp - 4;
+    const int c = q * 32 + lane;
+    const int et = threadIdx.x - 128;                     // 0..127 among the epilogue threads
+    const float bias = p.bias ? p.bias[c] : 0.f;
+    float w3[3] = {0.f, 0.f, 0.f};
+    if (p.img) { w3[0] = p.sc_w3[c * 3]; w3[1] = p.sc_w3[c * 3 + 1]; w3[2] = p.sc_w3[c * 3 + 2]; }
+    const float hw_c = p.head_out ? p.head_w[c] : 0.f;
+    const int HW = p.H * p.W;
+    long long local = 0;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
+      const int acc = (int)(local & 1);
+      const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
+      const long long P0 = t * 256;
+      if (p.img) {
+        // avg_pool2d of the normalised network input at the tile's (pooled) pixels: two pixels per epilogue thread
+        named_bar_sync(1, 128);                           // previous tile's readers are done with s_px
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const long long pix = P0 + h * 128 + et;
+          float px[3] = {0.f, 0.f, 0.f};
+          if (pix < p.total_pixels) {
+            const long long n = pix / HW;
+            const int r = (int)(pix - n * HW);
+            const int y = r / p.W, x = r - y * p.W;
+            const int iy = p.img_up ? 2 * y : y, ix = p.img_up ? 2 * x : x;
+            const int iH = p.img_up ? 2 * p.H : p.H, iW = p.img_up ? 2 * p.W : p.W;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+              px[ch] = (norm_px(p.img, p.img_layout, n, iy, ix, ch, iH, iW) + norm_px(p.img, p.img_layout, n, iy, ix + 1, ch, iH, iW) +
+                        norm_px(p.img, p.img_layout, n, iy + 1, ix, ch, iH, iW) + norm_px(p.img, p.img_layout, n, iy + 1, ix + 1, ch, iH, iW)) * 0.25f;
+          }
+          s_px[(h * 128 + et) * 3] = px[0]; s_px[(h * 128 + et) * 3 + 1] = px[1]; s_px[(h * 128 + et) * 3 + 2] = px[2];
+        }
+        named_bar_sync(1, 128);
+      }
+      mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
+      float head_sum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_acc + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const long long pb = P0 + c0;                     // first pixel of this chunk
+        if (pb < p.total_pixels) {                        // warp-uniform; chunks never straddle total_pixels (multiple of 32)
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
+          if (p.img) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float* px = s_px + (c0 + j) * 3;      // same address in every lane: broadcast
+              v[j] = fmaf(w3[0], px[0], fmaf(w3[1], px[1], fmaf(w3[2], px[2], v[j])));
+            }
+          }
+          if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]) * 1.4142135623730951f;
+          }
+          if (p.res_f32) {
+            const float* rp = p.res_f32 + pb * 128 + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float rv = rp[j * 128];
+              v[j] += p.res_relu ? fmaxf(rv, 0.f) : rv;
+            }
+          }
+          if (p.out_scale != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+          }
+          if (p.out_f32) {
+            float* op = p.out_f32 + pb * 128 + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) op[j * 128] = v[j];
+          }
+          if (p.out_raw) {
+            uint16_t* op = p.out_raw + pb * 128 + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) op[j * 128] = to_h16<F16>(v[j]);
+          }
+          if (p.out_relu) {
+            uint16_t* op = p.out_relu + pb * 128 + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) op[j * 128] = to_h16<F16>(fmaxf(v[j], 0.f));
+          }
+          if (p.head_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) head_sum += fmaxf(v[j], 0.f);
+          }
+        }
+        if (p.head_out && ((c0 + 32) % HW) == 0) {
+          // an image is complete: sum over this warp's 32 channels (fixed shuffle tree), park the partial for the tile's reduction
+          float part = head_sum * hw_c;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          if (lane == 0) s_head[q * 8 + c0 / HW] = part;
+          head_sum = 0.f;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
+      if (p.head_out) {
+        // deterministic cross-warp reduction: one thread per image adds the four warp partials in a fixed order
+        named_bar_sync(2, 128);
+        const int imgs = 256 / HW;
+        if (et < imgs) {
+          const long long img = P0 / HW + et;
+          if (img < p.n_images)
+            p.head_out[img] = p.head_b[0] + ((s_head[et] + s_head[8 + et]) + (s_head[16 + et] + s_head[24 + et]));
+        }
+        named_bar_sync(2, 128);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -929,6 +1174,8 @@ int conv_tc_init(int device) {
   SDG_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>()));
   SDG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemMax));
   SDG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemMax));
+  SDG_CUDA(cudaFuncSetAttribute(conv_swap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwapSmem));
+  SDG_CUDA(cudaFuncSetAttribute(conv_swap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwapSmem));
   SDG_CUDA(cudaFuncSetAttribute((conv_pair_stream_kernel<256, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
   SDG_CUDA(cudaFuncSetAttribute((conv_pair_stream_kernel<256, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
   SDG_CUDA(cudaFuncSetAttribute((conv_pair_stream_kernel<128, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
@@ -1035,6 +1282,16 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   { int rc = tc_encode_2d(&map_b, a.wb, f16, k_cols, Cout, TC_BK, BN); if (rc) return rc; }
 
   const int k_iters = p.taps * p.kchunks + p.sc_chunks;
+  // role-swapped kernel (N = 256 pixels per MMA) for Cout = 128 layers with a "linear" epilogue
+  static const int swap_mode = getenv("SDG_SWAP") ? atoi(getenv("SDG_SWAP")) : 1;     // SDG_SWAP=0: A/B against the pixel-major kernels
+  if (swap_mode && g_pair_mode && Cout == 128 && !p.pool && !p.box16 && !p.sc_sep && !a.sd && !a.gemm && p.m_tiles >= 2 &&
+      p.total_pixels % 32 == 0 && (!a.head_out || (256 % (Hc * Wc) == 0 && Hc * Wc >= 32))) {
+    const long long tiles = (p.m_tiles + 1) / 2;
+    const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+    if (f16) { SDG_LAUNCH(conv_swap_kernel<true>, grid, TC_THREADS, kSwapSmem, s, map_a, map_b, map_s, p); }
+    else { SDG_LAUNCH(conv_swap_kernel<false>, grid, TC_THREADS, kSwapSmem, s, map_a, map_b, map_s, p); }
+    return 0;
+  }
   static const int stream_all = getenv("SDG_PAIR_STREAM128") ? atoi(getenv("SDG_PAIR_STREAM128")) == 2 : 0;
   if (g_pair_mode && Cout == 128 && taps == 9 && k_iters <= PAIR_MAX_KI && p.m_tiles >= 2 && !p.sc_sep && !stream_all) {
     // CTA-pair kernel: weights resident (64 rows per CTA), A streamed through as many 16 KB stages as fit
