@@ -746,6 +746,9 @@ conv_pair_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   const int k_iters = main_iters + p.sc_chunks;
   const uint32_t tmem_cols = (BN == 256 || p.sc_sep) ? 512u : 256u;
   const uint32_t acc_stride = p.sc_sep ? 2 * BN : BN;
+  // accumulator stages: two, except N = 256 with the skip accumulator (256 + 256 columns fill TMEM: single-buffered, the
+  // epilogue of a tile is then exposed, ~10 % of a K = 5120 mainloop, in exchange for N = 256 instructions)
+  const int n_acc = (BN == 256 && p.sc_sep) ? 1 : 2;
 
   for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
   if (p.img)
@@ -816,8 +819,8 @@ conv_pair_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       uint32_t phase = 0;
       long long local = 0;
       for (long long t = cluster_id; t < total; t += n_clusters, ++local) {
-        const int acc = (int)(local & 1);
-        const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
+        const int acc = (int)(local % n_acc);
+        const uint32_t acc_phase = (uint32_t)((local / n_acc) & 1);
         mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)acc * acc_stride;
@@ -846,8 +849,8 @@ conv_pair_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     for (long long t = cluster_id; t < total; t += n_clusters, ++local) {
       const int nt = (int)(t % p.n_tiles);
       const long long mt = 2 * (t / p.n_tiles) + rank;
-      const int acc = (int)(local & 1);
-      const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
+      const int acc = (int)(local % n_acc);
+      const uint32_t acc_phase = (uint32_t)((local / n_acc) & 1);
       tc_epilogue_tile<BN, F16>(p, s_bias, s_w3, tmem_base + (uint32_t)acc * acc_stride, mt, nt, q, lane,
                                 smem_u32(&bar_acc_full[acc]), acc_phase);
       tc_fence_before();
@@ -1018,17 +1021,36 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         named_bar_sync(1, 128);
       }
-      mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
-      tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
       float head_sum = 0.f;
+      // The residual does not depend on the accumulator: the 32 loads of a chunk are issued one chunk AHEAD (chunk 0 before
+      // the accumulator wait), so their latency hides behind the previous chunk's arithmetic and stores.  (The epilogue,
+      // not the MMA, paced the residual layers: 34 % tensor-pipe activity in profiles/r1f_ncu_full_swap_summary.txt.)
+      float rnext[32];
+      auto load_res = [&](int c0n) {
+        if (p.res_f32 && P0 + c0n < p.total_pixels) {
+          const float* rp = p.res_f32 + (P0 + c0n) * 128 + c;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rnext[j] = __ldg(rp + j * 128);
+        }
+      };
+      load_res(0);
 #pragma unroll 1
       for (int c0 = 0; c0 < 256; c0 += 32) {
+        const long long pb = P0 + c0;                     // first pixel of this chunk
+        const bool chunk_ok = pb < p.total_pixels;        // warp-uniform; chunks never straddle total_pixels (multiple of 32)
+        float rv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rv[j] = rnext[j];
+        if (c0 + 32 < 256) load_res(c0 + 32);
+        if (c0 == 0) {
+          mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
+          tc_fence_after();
+        }
         uint32_t r[32];
         tmem_ld32(tmem_acc + (uint32_t)c0, r);
         tmem_ld_wait();
-        const long long pb = P0 + c0;                     // first pixel of this chunk
-        if (pb < p.total_pixels) {                        // warp-uniform; chunks never straddle total_pixels (multiple of 32)
+        if (chunk_ok) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
@@ -1044,12 +1066,8 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]) * 1.4142135623730951f;
           }
           if (p.res_f32) {
-            const float* rp = p.res_f32 + pb * 128 + c;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float rv = rp[j * 128];
-              v[j] += p.res_relu ? fmaxf(rv, 0.f) : rv;
-            }
+            for (int j = 0; j < 32; ++j) v[j] += p.res_relu ? fmaxf(rv[j], 0.f) : rv[j];
           }
           if (p.out_scale != 1.0f) {
 #pragma unroll
@@ -1323,7 +1341,9 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   // also run as CTA pairs, N = 128, weights streamed (measured +1.9 % on the whole SNGAN-32 pass); 0 disables, 2 = experiment:
   // streamed weights for EVERY Cout = 128 3x3 layer instead of the resident-weight kernel
   static const int stream128 = getenv("SDG_PAIR_STREAM128") ? atoi(getenv("SDG_PAIR_STREAM128")) : 1;
-  const int sbn = (!p.sc_sep && Cout % 256 == 0) ? 256 : ((p.sc_sep || (stream128 && Cout == 128)) && Cout % 128 == 0 ? 128 : 0);
+  // the skip-accumulator form is single-buffered at N = 256 (TMEM is full): worth it only when the mainloop is long
+  const bool sep_short = p.sc_sep && k_iters < 40;
+  const int sbn = (Cout % 256 == 0 && !sep_short) ? 256 : ((p.sc_sep || (stream128 && Cout == 128)) && Cout % 128 == 0 ? 128 : 0);
   if (g_pair_mode && sbn && p.m_tiles >= 2 && !p.pool && (!p.img || Cout == 128)) {
     // CTA-pair kernel with streamed weights: M = 256 x N = sbn per MMA
     p.n_tiles = Cout / sbn;
