@@ -149,8 +149,11 @@ SDG_API int sdg_conv2d_sg2_h16(const void* in, const void* wb, const float* bias
  * out extent (H + 2*pad - 4) / stride + 1: stride 2 evaluates only the outputs a following stride-2 1x1 conv reads. */
 SDG_API int sdg_blur_h16(const void* in, void* out, int64_t n, int H, int W, int C, int pad, int stride, int precision,
                  void* stream);
-/* Kernel selection for Cout = 128 3x3 stages: on != 0 (default) uses the CTA-pair kernel (tcgen05.mma.cta_group::2,
- * weights resident in shared memory), 0 forces the single-CTA kernel.  Process-wide; for tests and A/B timing. */
+/* Kernel selection of the tensor-core convolution (process-wide; for tests and A/B timing):
+ *   1 (default) every kernel where it applies: role-swapped (M = 128 channels x N = 256 pixels) for Cout = 128, streamed
+ *               CTA pairs (tcgen05.mma.cta_group::2, N = 256) for Cout % 256 == 0, single-CTA otherwise;
+ *   2           CTA-pair kernels (resident / streamed weights) but no role swap;
+ *   0           the single-CTA pixel-major kernel only. */
 SDG_API int sdg_set_conv_pair(int on);
 /* First conv of the SNGAN discriminators straight from the dataset bytes: out = relu(conv3x3(normalise(x)) + b).
  * Replaces transform.py:3-11 + DBlockOptimized.c1 + ReLU.  x: uint8 [n,S,S,3] or fp32 [n,3,S,S] (layout);

@@ -1143,7 +1143,8 @@ int tc_num_sms() { return g_num_sms; }
 
 constexpr int kPairSmemMax = 227 * 1024 - 3072;       // dynamic shared memory budget of the pair kernel (static: ~2.5 KB)
 constexpr int kStreamSmem = 1024 + 6 * (TC_A_BYTES + 128 * TC_BK * 2);   // 6 x 32 KB (BN 256) = 8 x 24 KB (BN 128) stages
-static int g_pair_mode = 1;                          // 0 = never use the CTA-pair kernels, 1 = use them where they apply
+static int g_pair_mode = 1;                          // 0 = single-CTA pixel-major kernels only, 1 = default selection (role-swapped,
+                                                     // streamed / resident CTA pairs where they apply), 2 = CTA pairs but no role swap
 void conv_tc_set_pair(int on) { g_pair_mode = on; }
 
 int tc_encode_2d(CUtensorMap* map, const void* ptr, int f16, uint64_t inner, uint64_t outer, uint32_t box_inner,
@@ -1302,7 +1303,7 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   const int k_iters = p.taps * p.kchunks + p.sc_chunks;
   // role-swapped kernel (N = 256 pixels per MMA) for Cout = 128 layers with a "linear" epilogue
   static const int swap_mode = getenv("SDG_SWAP") ? atoi(getenv("SDG_SWAP")) : 1;     // SDG_SWAP=0: A/B against the pixel-major kernels
-  if (swap_mode && g_pair_mode && Cout == 128 && !p.pool && !p.box16 && !p.sc_sep && !a.sd && !a.gemm && p.m_tiles >= 2 &&
+  if (swap_mode && g_pair_mode == 1 && Cout == 128 && !p.pool && !p.box16 && !p.sc_sep && !a.sd && !a.gemm && p.m_tiles >= 2 &&
       p.total_pixels % 32 == 0 && (!a.head_out || (256 % (Hc * Wc) == 0 && Hc * Wc >= 32))) {
     const long long tiles = (p.m_tiles + 1) / 2;
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);

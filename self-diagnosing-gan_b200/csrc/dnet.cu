@@ -928,7 +928,7 @@ static int forward_stylegan2_h16(sdg_ctx* c, const void* x, int layout, int64_t 
 }
 
 extern "C" int sdg_set_conv_pair(int on) {
-  conv_tc_set_pair(on ? 1 : 0);
+  conv_tc_set_pair(on < 0 ? 0 : (on > 2 ? 1 : on));
   return 0;
 }
 

@@ -445,11 +445,12 @@ def _check_conv(errs, prec, tag, slack=1.0):
     (37, 8, 128, 128, 3),      # odd number of M tiles (19): the pair kernel's last M=256 tile is half empty
 ])
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
-@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("pair", [0, 1, 2])
 def test_conv2d_h16_tcgen05_vs_torch(n, hw, cin, cout, ks, prec, pair, dev):
     """The tcgen05 implicit-GEMM kernels alone (no fusion) against F.conv2d on the same 16-bit-rounded operands
     (fp32 accumulate both sides; 16-bit outputs within one output ulp of the scale, fp32 output within 2e-5).
-    pair=1: Cout = 128 3x3 cases run on the CTA-pair (cta_group::2, resident weights) kernel; 0: single-CTA kernel."""
+    pair=1: default kernel selection (role-swapped kernel for Cout = 128, streamed CTA pairs for Cout % 256 == 0);
+    2: CTA-pair kernels without the role swap (resident weights for Cout = 128); 0: single-CTA kernel."""
     errs = _conv_fused(dev, n, hw, cin, cout, ks, prec, seed=n * 1000 + hw, pair=pair)
     _check_conv(errs, prec, f"conv {prec} pair={pair} n={n} hw={hw} {cin}->{cout} k{ks}")
 
@@ -467,13 +468,13 @@ def test_conv2d_h16_tcgen05_vs_torch(n, hw, cin, cout, ks, prec, pair, dev):
     ("many tiles, pooled", 200, 32, 128, 128, dict(pool=1, img=True)),
 ])
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
-@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("pair", [0, 1, 2])
 def test_conv2d_fused_block_stage_vs_torch(tag, n, hw, cin, cout, kw, prec, pair, dev):
     """Fused epilogues: pooling by warp shuffles, shortcut conv as extra K columns, image shortcut FMAs, identity
     residual from the fp32 stream, the three output forms -- on both kernel variants."""
     errs = _conv_fused(dev, n, hw, cin, cout, 3, prec, seed=hw * 7 + n, pair=pair, **kw)
     _check_conv(errs, prec, f"{prec} pair={pair} {tag}")
-    if kw.get("pool") and pair == 1:
+    if kw.get("pool") and pair >= 1:
         # the same stage as a 4x4 stride-2 conv (TMA traversal stride 2); weights are re-rounded after summing,
         # so allow two output ulps
         kw4 = dict(kw, pool=2)
