@@ -248,11 +248,11 @@ def run_ours(args, rank, world, local_rank):
             "peak_source": f"{peaks['source']} (sustained: kernel timed inside a long step)",
             "launches_timed": int(pl.value), "ms_per_launch": (pm.value / pl.value) if pl.value else None,
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE 4096-sample launch of this kernel from the committed
-            # `ncu --set full` capture (profiles/r1c_ncu_full_b1c2_pool4_summary.txt): 1.087 GB read + 0.250 GB written;
+            # `ncu --set full` capture (profiles/r1f_ncu_full_swap_summary.txt, launch 0): 1.087 GB read + 0.247 GB written;
             # algorithmic minimum of that launch = 4096 x (256 KiB input + 64 KiB output) + weights = 1.343 GB
-            "traffic": 1.086914e9 + 250.010368e6,
-            "traffic_note": "per 4096-sample launch, ncu --set full (profiles/r1c_ncu_full_b1c2_pool4_summary.txt); "
-                            "algorithmic bytes of the same launch: 1.343e9 (input once, output once)",
+            "traffic": 1.087083e9 + 247.195904e6,
+            "traffic_note": "per 4096-sample launch, ncu --set full (profiles/r1f_ncu_full_swap_summary.txt, launch 0: tensor "
+                            "pipe 67.5 % active); algorithmic bytes of the same launch: 1.343e9 (input once, output once)",
         },
     }
     if world == 1:

@@ -52,17 +52,14 @@ int minibatch_stddev_cat_fp32(const float* in, float* out, float* sd_scratch, in
                               cudaStream_t s);
 // the same statistic without the concat: sd_sample[b] = the stddev-channel value sample b would see
 int minibatch_stddev_fp32(const float* in, float* sd_sample, int64_t n, int batch, int HW, int C, cudaStream_t s);
-// wb[o*K + p*C + c] = h16(W[o][c*HW + p] * mul)      (EqualLinear on the NCHW-flattened map; activations NHWC, K = C*HW)
-int pack_linear_nchw_h16(const float* W, float mul, h16* wb, int O, int C, int HW, int f16, cudaStream_t s);
 // contribution of ONE extra input channel (index c_extra of cin_w) of a 3x3 pad-1 conv on an S x S map whose value is constant
 // over the map: wsum[p*Cout + o] = mul * sum over the taps that stay inside the map at pixel p of W[o][c_extra][tap]
 int pack_const_channel_fp32(const float* W, float mul, float* wsum, int Cout, int cin_w, int c_extra, int S, cudaStream_t s);
-// 16-bit (tensor-core path) pieces: first 1x1 conv + FusedLeakyReLU from the image (w3 [3][C] fp32, scaled), Blur, widening
+// 16-bit (tensor-core path) pieces: first 1x1 conv + FusedLeakyReLU from the image (w3 [3][C] fp32, scaled), Blur
 int sg2_first_conv_h16(const void* x, int layout, const float* w3, const float* bias, h16* out, int64_t n, int S, int C, int f16,
                        cudaStream_t s);
 // blur_h16: out extent = (H + 2*pad - 4) / stride + 1 (stride 2 = only the blur outputs a stride-2 1x1 conv reads)
 int blur_h16(const h16* in, h16* out, int64_t n, int H, int W, int C, int pad, int stride, int f16, cudaStream_t s);
-int widen_h16(const h16* in, float* out, int64_t total, int f16, cudaStream_t s);
 // split-precision tail operands (see sg2_fp32.cu): activations fp32 [rows][C] -> [rows][hi | lo | hi]; weights -> per K group
 // of C channels [Wh | Wh | Wl] (conv: G = 9 taps of W[O][cin_w][3][3]; linear: G = HW pixels of W[O][C*HW], NCHW flatten)
 int split3_rows_h16(const float* in, h16* out, int64_t rows, int C, int f16, cudaStream_t s);
@@ -109,16 +106,6 @@ int bn_fold(const float* gamma, const float* beta, const float* mean, const floa
             float* shift, int C, cudaStream_t s);
 // DCGAN fc weight [C*HW] (NCHW flatten) -> NHWC flatten order
 int permute_fc(const float* w, float* out, int C, int HW, cudaStream_t s);
-
-// ---- elem_h16.cu: streaming helpers of the 16-bit path (NHWC, 16-byte accesses) -------------------
-// patches [n,H,W,64]: 3x3x3 neighbourhood of the normalised input at k = tap*3+c (27 real, rest 0);
-// pooled [n,H/2,W/2,64]: avg_pool2d of the normalised input in channels 0..2 (rest 0)
-int stage_first_conv(const void* x, int layout, h16* patches, h16* pooled, int64_t n, int H, int W, int f16,
-                     cudaStream_t s);
-int combine_h16(const h16* a, int pool_a, const h16* b, int pool_b, h16* out_relu, h16* out_raw, int64_t n, int Ho,
-                int Wo, int C, int f16, cudaStream_t s);
-int head_h16(const h16* hrelu, const float* w, const float* bias, float* logits, int64_t n, int HW, int C, int f16,
-             cudaStream_t s);
 
 // ---- conv_tc.cu / conv_first.cu: tcgen05 implicit-GEMM convolutions (16-bit in, fp32 TMEM accumulate) ----
 // One fused residual-block stage: conv (3x3 pad 1 or 1x1, stride 1) [+ the block's 1x1 shortcut conv as extra K

@@ -5,7 +5,8 @@
 //   ResBlock's (out + skip) / sqrt(2)           :611-614
 //   minibatch-stddev + concat                   :662-670
 //   EqualLinear on the NCHW-flattened map       :672-673 (weight re-ordered once so activations stay NHWC)
-// Correctness-first CUDA-core kernels (activations NHWC fp32); the tensor-core form of this network is future work.
+// fp32 CUDA-core kernels of the exact engine, plus the 16-bit streaming pieces (first conv, blur, split-precision tail
+// operands) of the tensor-core engine whose convolutions live in conv_tc.cu.
 #include "kernels.cuh"
 
 namespace sdg {
@@ -132,26 +133,6 @@ int minibatch_stddev_fp32(const float* in, float* sd_sample, int64_t n, int batc
   return 0;
 }
 
-template <bool F16>
-__global__ void __launch_bounds__(256)
-pack_linear_nchw_h16_kernel(const float* __restrict__ W, float mul, h16* __restrict__ wb, int O, int C, int HW) {
-  const int64_t K = (int64_t)C * HW, total = (int64_t)O * K;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int o = (int)(i / K);
-    const int k = (int)(i - (int64_t)o * K);           // p*C + c
-    const int c = k % C, p = k / C;
-    wb[i] = (h16)(pack_h2<F16>(W[(int64_t)o * K + (int64_t)c * HW + p] * mul, 0.f) & 0xffffu);
-  }
-}
-
-int pack_linear_nchw_h16(const float* W, float mul, h16* wb, int O, int C, int HW, int f16, cudaStream_t s) {
-  const int64_t total = (int64_t)O * C * HW;
-  if (f16) { SDG_LAUNCH(pack_linear_nchw_h16_kernel<true>, stream_grid(total, 256), 256, 0, s, W, mul, wb, O, C, HW); }
-  else { SDG_LAUNCH(pack_linear_nchw_h16_kernel<false>, stream_grid(total, 256), 256, 0, s, W, mul, wb, O, C, HW); }
-  return 0;
-}
-
 __global__ void __launch_bounds__(256)
 pack_const_channel_kernel(const float* __restrict__ W, float mul, float* __restrict__ wsum, int Cout, int cin_w, int c_extra, int S) {
   const int total = S * S * Cout;
@@ -191,7 +172,7 @@ int pack_linear_nchw_fp32(const float* W, float mul, float* wp, int O, int C, in
 }
 
 // ---------------------------------------------------------------------------------------------------
-// 16-bit (tensor-core path) helpers: first 1x1 conv from the image, blur, widening of the last feature map
+// 16-bit (tensor-core path) helpers: first 1x1 conv from the image, blur
 // ---------------------------------------------------------------------------------------------------
 // ConvLayer(3, C, 1): out[pix][o] = flrelu(sum_c w[c][o] * x[pix][c] + b[o]); w3 = [3][C] (pack_conv_fp32 layout), already
 // carrying 1/sqrt(3).  HBM-write-bound (2*C bytes per pixel).  A thread owns ONE group of 8 output channels for the whole
@@ -451,22 +432,6 @@ int pack_split3_h16(const float* W, float mul, h16* wb, int O, int C, int G, int
   const int64_t total = (int64_t)O * C * G;
   if (f16) { SDG_LAUNCH(pack_split3_kernel<true>, stream_grid(total, 256), 256, 0, s, W, mul, wb, O, C, G, cin_w, linear); }
   else { SDG_LAUNCH(pack_split3_kernel<false>, stream_grid(total, 256), 256, 0, s, W, mul, wb, O, C, G, cin_w, linear); }
-  return 0;
-}
-
-template <bool F16>
-__global__ void widen_h16_kernel(const h16* __restrict__ in, float* __restrict__ out, int64_t total2) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += stride) {
-    const float2 t = unpack_h2<F16>(reinterpret_cast<const uint32_t*>(in)[i]);
-    reinterpret_cast<float2*>(out)[i] = t;
-  }
-}
-
-int widen_h16(const h16* in, float* out, int64_t total, int f16, cudaStream_t s) {
-  if (total == 0) return 0;
-  if (f16) { SDG_LAUNCH(widen_h16_kernel<true>, stream_grid(total / 2, 256), 256, 0, s, in, out, total / 2); }
-  else { SDG_LAUNCH(widen_h16_kernel<false>, stream_grid(total / 2, 256), 256, 0, s, in, out, total / 2); }
   return 0;
 }
 
