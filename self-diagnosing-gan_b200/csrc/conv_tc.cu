@@ -1,25 +1,34 @@
-// conv_tc.cu -- tcgen05 implicit-GEMM convolution with fused block epilogues (the throughput path).
+// conv_tc.cu -- tcgen05 implicit-GEMM convolutions with fused block epilogues (the throughput path).
 //
-// Replaces, for one spectral-normalised residual-block stage of the SNGAN discriminators (torch-mimicry
-// DBlock / DBlockOptimized; call site trainer.py:150):
-//     F.conv2d(x, W/sigma, b, stride 1, pad ks/2)                       (3x3 or 1x1)
-//   [ + F.conv2d(s, Wsc/sigma_sc, bsc)   the block's 1x1 shortcut conv, folded in as extra K columns ]
-//   [ + Wsc3 . avg_pool2d(x_img)         DBlockOptimized's 3-channel shortcut, 3 FMAs in the epilogue ]
-//   [ avg_pool2d(., 2) ]  [ + identity shortcut ]  [ ReLU for the next conv ]
+// Replaces, for one residual-block stage of the discriminators on the path
+//   * torch-mimicry DBlock / DBlockOptimized of SNGANDiscriminator32/64 (call site trainer.py:150):
+//       F.conv2d(x, W/sigma, b, stride 1, pad ks/2)                       (3x3 or 1x1)
+//     [ + F.conv2d(s, Wsc/sigma_sc, bsc)   the block's 1x1 shortcut conv, folded in as extra K columns ]
+//     [ + Wsc3 . avg_pool2d(x_img)         DBlockOptimized's 3-channel shortcut, 3 FMAs in the epilogue ]
+//     [ avg_pool2d(., 2) ]  [ + identity shortcut ]  [ ReLU for the next conv ]  [ ReLU -> sum-pool -> SNLinear head ]
+//   * ConvLayer / ResBlock of the StyleGAN2 discriminator (diagan/models/stylegan2.py:553-616):
+//       EqualConv2d (stride 1 pad 1, or stride 2 pad 0 on the blurred tensor) + FusedLeakyReLU
+//     [ + skip 1x1 conv in a second accumulator ]  [ * 1/sqrt(2) ]  [ + the minibatch-stddev channel as a rank-1 term ]
+//     and EqualLinear as a plain GEMM.
 //
-// GEMM view: D[M = pixels, N = Cout] = A[M, K] * B[N, K]^T, 16-bit operands (fp16 or bf16), fp32 accumulate.
+// Four kernels share the TMA traversal and the K schedule; conv_tc() picks by shape:
+//   conv_swap_kernel          Cout = 128: D^T[128 ch, 256 px] = W . A^T, one CTA, M = 128 x N = 256 per tcgen05.mma
+//   conv_pair_stream_kernel   Cout % 256 == 0 (or skip accumulator): CTA pair, cta_group::2, M = 256 px x N = 256 / 128
+//   conv_pair_kernel          Cout = 128, weights resident in shared memory, CTA pair (A/B baseline since the swap kernel)
+//   conv_tc_kernel<BN>        one CTA, M = 128 px x N = 64 / 128 (Cout = 64 layers, legacy pooled epilogue, baseline)
+//
+// Pixel-major GEMM view: D[M = pixels, N = Cout] = A[M, K] * B[N, K]^T, 16-bit operands (fp16 or bf16), fp32 accumulate.
 //   * A is never materialised: NHWC activations are read by 4-D TMA boxes of 64 channels x 128 pixels, one
 //     box set per (tap, 64-channel chunk), shifted by the tap offset; the halo of the 3x3 window is the
 //     TMA out-of-bounds zero fill.  A box lands in shared memory as rows of 128 B, 128B-swizzled = the
-//     canonical K-major UMMA operand layout.
-//     Tile geometry: "linear" = 128 consecutive pixels (full-width rows, W <= 16 or no pooling);
-//     "box16" = 8 rows x 16 columns (pooled layers with W >= 32) so that every epilogue warp owns two
-//     rows x 16 columns = whole 2x2 pooling quads.  Either way one TMA box per operand per stage.
-//   * B (weights [Cout][K] K-major, sigma folded in, shortcut columns appended) by 2-D TMA boxes {64, BN}.
-//   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM accumulator;
-//     smem stages are recycled with tcgen05.commit -> mbarrier.
-//   * epilogue warps: tcgen05.ld, 2x2 average pooling by warp shuffles, + bias, + shortcut, then up to
-//     three stores: ReLU'd 16-bit (operand of the next conv), raw 16-bit, raw fp32 (residual stream / head).
+//     canonical K-major UMMA operand layout.  Stride-2 forms use the tensor map's traversal stride.
+//     Tile geometry: "linear" = 128 consecutive pixels (full-width rows; rows of 256+ pixels split in boxes);
+//     "box16" = 8 rows x 16 columns (legacy pooled epilogue with W >= 32).
+//   * B (weights [Cout][K] K-major, sigma / equalised-lr scale folded in, shortcut columns appended) by 2-D TMA boxes.
+//   * one elected thread issues tcgen05.mma into a double-buffered TMEM accumulator; smem stages are recycled with
+//     tcgen05.commit -> mbarrier.
+//   * epilogue warps: tcgen05.ld, + bias, activation, shortcuts, then up to three stores: ReLU'd 16-bit (operand of the
+//     next conv), raw 16-bit, raw fp32 (residual stream / head).
 // Persistent CTAs (one per SM), static tile schedule, warp-specialised: warp 0 TMA producer, warp 1 MMA
 // issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
 #include <cstdlib>
