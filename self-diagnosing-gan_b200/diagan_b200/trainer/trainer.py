@@ -135,7 +135,7 @@ class LogitRecorder:
                 self.stats = engine.RunningStats(hi - lo, self.device)
             self.stats.update(snap[lo:hi])
 
-    def record_from_host(self, netD, host_u8: torch.Tensor, step=None, chunk: int = 8192) -> torch.Tensor:
+    def record_from_host(self, netD, host_u8: torch.Tensor, step=None, chunk: int = 12544) -> torch.Tensor:
         """Recording pass over a dataset that lives in (pinned) HOST memory: uint8 NHWC chunks are
         copied on a side stream into two staging buffers while the previous chunk is in the engine, so
         the H2D traffic (3 KB/sample for CIFAR shape) overlaps the forward."""
