@@ -135,14 +135,13 @@ class LogitRecorder:
                 self.stats = engine.RunningStats(hi - lo, self.device)
             self.stats.update(snap[lo:hi])
 
-    def record_from_host(self, netD, host_u8: torch.Tensor, step=None, chunk: int = 12544) -> torch.Tensor:
+    def record_from_host(self, netD, host_u8: torch.Tensor, step=None, chunk: int = 12544, first_chunk: int = 2048) -> torch.Tensor:
         """Recording pass over a dataset that lives in (pinned) HOST memory: uint8 NHWC chunks are
         copied on a side stream into two staging buffers while the previous chunk is in the engine, so
-        the H2D traffic (3 KB/sample for CIFAR shape) overlaps the forward."""
-        self.load_weights(netD)
+        the H2D traffic (3 KB/sample for CIFAR shape) overlaps the forward.  The first chunk is small and its copy is
+        issued before the weights are packed, so almost nothing of the transfer is exposed."""
         n = host_u8.shape[0]
         self.n = n
-        snap = torch.zeros(n, dtype=torch.float32, device=self.device)
         main = torch.cuda.current_stream(self.device)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
@@ -154,16 +153,28 @@ class LogitRecorder:
             self._ev_used = [torch.cuda.Event() for _ in range(2)]
             for e in self._ev_used:
                 e.record(main)
-        starts = list(range(0, n, chunk))
-        for i, s0 in enumerate(starts):
-            b = i & 1
-            nb = min(chunk, n - s0)
+        bounds = [0]
+        if 0 < first_chunk < min(chunk, n):
+            bounds.append(first_chunk)
+        while bounds[-1] < n:
+            bounds.append(min(n, bounds[-1] + chunk))
+
+        def issue_copy(i):
+            b, s0, s1 = i & 1, bounds[i], bounds[i + 1]
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(self._ev_used[b])          # staging buffer free again
-                self._stage[b][:nb].copy_(host_u8[s0:s0 + nb], non_blocking=True)
+                self._stage[b][:s1 - s0].copy_(host_u8[s0:s1], non_blocking=True)
                 self._ev_copied[b].record(self._copy_stream)
+
+        issue_copy(0)                                                   # overlaps sigma + weight packing
+        self.load_weights(netD)
+        snap = torch.zeros(n, dtype=torch.float32, device=self.device)
+        for i in range(len(bounds) - 1):
+            b, s0, s1 = i & 1, bounds[i], bounds[i + 1]
+            if i + 1 < len(bounds) - 1:
+                issue_copy(i + 1)                                       # next chunk streams in during this forward
             main.wait_event(self._ev_copied[b])
-            self.engine.forward(self._stage[b][:nb], out=snap[s0:s0 + nb])
+            self.engine.forward(self._stage[b][:s1 - s0], out=snap[s0:s1])
             self._ev_used[b].record(main)
         if step is not None:
             self.observe(step, snap)
