@@ -693,6 +693,29 @@ def test_resize_center_crop_bit_exact_vs_pil_and_oracle(h, w, size, n, dev):
         pass
 
 
+def test_resize_edge_cases(dev):
+    """Empty input, single-channel images (mnist_fmnist transform, transform.py:25-33), and a non-CUDA tensor is refused."""
+    from diagan_b200 import _lib
+    from diagan_b200.datasets.transform import DeviceTransform, get_transform
+    from oracle import resize as resize_oracle
+    tf = get_transform("mnist_fmnist")
+    assert tf.img_size == 32
+    assert tf(torch.empty(0, 28, 28, 1, dtype=torch.uint8, device=dev)).shape == (0, 32, 32, 1)
+    g = np.random.RandomState(3).randint(0, 256, (11, 28, 28, 1)).astype(np.uint8)
+    got = tf(torch.from_numpy(g).to(dev)).cpu().numpy()
+    assert np.array_equal(got, resize_oracle.resize_center_crop_u8(g, 32))
+    try:
+        from PIL import Image
+        want = np.stack([np.asarray(Image.fromarray(im[..., 0], mode="L").resize((32, 32), Image.BILINEAR))[..., None] for im in g])
+        assert np.array_equal(got, want)
+    except ImportError:
+        pass
+    with pytest.raises(_lib.SdgError):
+        DeviceTransform(32)(torch.zeros(2, 28, 28, 3, dtype=torch.uint8))
+    with pytest.raises(_lib.SdgError):
+        DeviceTransform(32)(torch.zeros(2, 28, 28, 3, dtype=torch.float32, device=dev))
+
+
 def test_resident_dataset_from_raw_colour_mnist_shape(dev):
     """Colour-MNIST items are 28x28 uint8 RGB, resized to 32 (color_mnist.py:90-100 + transform.py:23-31): the resident
     dataset built on the GPU equals the per-item PIL path, normalisation included (first-conv LUT == ToTensor + Normalize)."""
@@ -703,6 +726,22 @@ def test_resident_dataset_from_raw_colour_mnist_shape(dev):
     ds = ResidentDataset.from_raw_images(raw, "color_mnist", dev)
     assert ds.data.shape == (64, 32, 32, 3) and ds.data.dtype == torch.uint8
     assert np.array_equal(ds.data.cpu().numpy(), resize_oracle.resize_center_crop_u8(raw, 32))
+
+
+@pytest.mark.parametrize("size,batch,n", [(8, 4, 8), (16, 2, 6), (64, 4, 4)])
+def test_stylegan2_tensorcore_small_sizes_vs_oracle(size, batch, n, dev):
+    """Sizes without a golden fixture (one to four ResBlocks; a single reference batch; batch 2 = stddev group of 2) against
+    the float64 oracle, which the 32 / 128 fixtures pin to the reference module."""
+    from diagan_b200 import engine, synthetic
+    from oracle import stylegan2 as sg2_oracle
+    params = synthetic.stylegan2_state_dict(size, seed=size)
+    x = _u8(n, size, 5)
+    want = sg2_oracle.logits_pass(params, x, size, batch, dtype=torch.float64)
+    got = engine.DiscriminatorEngine(dev).load_stylegan2(params, "fp16", batch=batch).forward(x.to(dev)).cpu().numpy()
+    exact = engine.DiscriminatorEngine(dev).load_stylegan2(params, "fp32", batch=batch).forward(x.to(dev)).cpu().numpy()
+    e16, e32 = _logit_close(got, want)[0], _logit_close(exact, want)[0]
+    print(f"stylegan2 D{size} batch {batch}: fp16 {e16:.2e}, fp32 engine {e32:.2e} (logit mean {want.mean():.3f} std {want.std():.3f})")
+    assert e32 <= 1e-5 and e16 <= 2e-3
 
 
 # ---------------------------------------------------------------------------------------------------
