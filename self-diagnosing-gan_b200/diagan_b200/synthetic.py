@@ -90,6 +90,24 @@ def stylegan2_flops(size: int) -> float:
     return 2.0 * mac
 
 
+def dcgan_state_dict(seed: int = 1) -> dict:
+    """Random-init MNIST_DCGAN_Discriminator state_dict (diagan/models/mnist.py:161-192, key names of its nn.Sequential):
+    PyTorch-default conv init U(+-1/sqrt(fan_in)), BatchNorm affine and running statistics away from the identity."""
+    rng = np.random.RandomState(seed)
+    u = lambda lo, hi, *shape: torch.from_numpy(rng.uniform(lo, hi, shape).astype(np.float32))
+    sd = {}
+    for ci, bi, cin, cout in ((0, None, 3, 16), (3, 4, 16, 32), (7, 8, 32, 64), (11, 12, 64, 128), (15, 16, 128, 256),
+                              (19, 20, 256, 512)):
+        b = 1.0 / math.sqrt(cin * 9)
+        sd[f"conv.{ci}.weight"] = u(-b, b, cout, cin, 3, 3)
+        if bi is not None:
+            sd[f"conv.{bi}.weight"], sd[f"conv.{bi}.bias"] = u(0.8, 1.2, cout), u(-0.1, 0.1, cout)
+            sd[f"conv.{bi}.running_mean"], sd[f"conv.{bi}.running_var"] = u(-0.05, 0.05, cout), u(0.5, 1.5, cout)
+    b = 1.0 / math.sqrt(8192)
+    sd["out_d.weight"], sd["out_d.bias"] = u(-b, b, 1, 8192), u(-b, b, 1)
+    return sd
+
+
 def perturb_(state_dict: dict, step: int, scale: float = 1e-3, device=None) -> dict:
     """W += scale * randn(seed = step): a deterministic stand-in for the training between two recording
     passes, so that per-sample logits move and std > 0."""

@@ -7,8 +7,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "self-diagnosing-gan_b200")):
-    sys.path.insert(0, p)
+sys.path.insert(0, os.path.join(ROOT, "self-diagnosing-gan_b200"))
 import torch  # noqa: E402
 
 from diagan_b200 import engine, synthetic  # noqa: E402
@@ -35,9 +34,8 @@ def main():
         eng.load_sngan(synthetic.sngan_state_dict(size, 1), size, a.precision, True)
         flop = FLOP[a.arch]
     elif a.arch == "dcgan32":
-        from oracle import dcgan          # tool only: random-init parameters with the reference's key names
         size = 32
-        eng.load_dcgan(dcgan.init_params(1))
+        eng.load_dcgan(synthetic.dcgan_state_dict(1))
         flop = FLOP[a.arch]
     else:
         size = a.size
