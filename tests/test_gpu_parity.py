@@ -744,6 +744,26 @@ def test_stylegan2_tensorcore_small_sizes_vs_oracle(size, batch, n, dev):
     assert e32 <= 1e-5 and e16 <= 2e-3
 
 
+@pytest.mark.parametrize("arch", [32, 64])
+def test_sngan_tensorcore_tiny_batches(arch, dev):
+    """1, 2, 3 and 5 samples: fewer pixels than one 256-pixel tile in the late blocks, so the kernel selection falls back
+    from the role-swapped / CTA-pair kernels to the single-CTA one (fused head by atomics); logits must match the oracle and
+    agree with the same samples' logits inside a large pass up to fp32 summation order."""
+    from diagan_b200 import engine, synthetic
+    sd = synthetic.sngan_state_dict(arch, seed=3)
+    x = _u8(261, arch, 9).to(dev)
+    eng = engine.DiscriminatorEngine(dev).load_sngan(sd, arch, "fp16", True)
+    full = eng.forward(x)
+    want = sngan_oracle.logits_pass(sd, x[:5].cpu(), arch, dtype=torch.float64)
+    assert _logit_close(full[:5].cpu().numpy(), want)[0] <= 2e-3
+    for n in (1, 2, 3, 5):
+        got = eng.forward(x[:n].contiguous())
+        err = _logit_close(got.cpu().numpy(), want[:n])[0]
+        assert err <= 2e-3, (n, err)
+        # different kernels may sum in a different order: equal to fp32 rounding, not necessarily bit for bit
+        torch.testing.assert_close(got, full[:n], rtol=2e-4, atol=2e-5)
+
+
 # ---------------------------------------------------------------------------------------------------
 # the recorder end to end: pass -> snapshots -> pickle -> calculate_scores -> weights
 # ---------------------------------------------------------------------------------------------------
