@@ -1031,6 +1031,14 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         named_bar_sync(1, 128);
       }
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
+      if (p.debug_skip_epi) {                             // timing experiment only (SDG_DEBUG_SKIP_EPI=1): drain the protocol
+        mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
+        continue;
+      }
       float head_sum = 0.f;
       // The residual does not depend on the accumulator: the 32 loads of a chunk are issued one chunk AHEAD (chunk 0 before
       // the accumulator wait), so their latency hides behind the previous chunk's arithmetic and stores.  (The epilogue,

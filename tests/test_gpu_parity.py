@@ -805,6 +805,56 @@ def test_recorder_end_to_end(tmp_path, dev):
         assert np.array_equal(sc[k], want[k]), k
 
 
+def test_config0_colour_mnist_dcgan_chain(tmp_path, dev):
+    """BASELINE configs[0] end to end at reduced size: raw 28x28 Colour-MNIST-shaped images (major_ratio 0.99) -> the
+    reference transform (Resize 32 + CenterCrop, bit-exact on the GPU) -> MNIST_DCGAN discriminator in eval mode (exact
+    fp32 engine) over six weight snapshots -> logits_netD_eval.pkl -> calculate_scores -> ldr_conf_1.0_ratio_50 weights
+    (train_mimicry_color_mnist_phase2.py:24-27 passes them to the sampler un-floored) -> top-100 indices."""
+    from diagan_b200 import engine
+    from diagan_b200.trainer.trainer import LogitRecorder, LogTrainer, ResidentDataset
+    from diagan_b200.utils.plot import calculate_scores
+    from oracle import resize as resize_oracle
+
+    class Net:
+        def __init__(self, p): self.p = p
+        def state_dict(self): return self.p
+        def train(self): pass
+
+    n = 600
+    rng = np.random.RandomState(1)
+    mask = (rng.rand(n, 28, 28, 1) < 0.19).astype(np.uint8)
+    colour = np.where((np.arange(n) < int(n * 0.99))[:, None, None, None], np.array([255, 0, 0], np.uint8),
+                      np.array([0, 255, 0], np.uint8))
+    raw = (mask * colour).astype(np.uint8)[rng.permutation(n)]
+    ds = ResidentDataset.from_raw_images(raw, "color_mnist", dev)
+    x32 = resize_oracle.resize_center_crop_u8(raw, 32)
+    assert np.array_equal(ds.data.cpu().numpy(), x32)                       # the loader's images, bit for bit
+
+    base = dcgan_oracle.init_params(seed=4)
+    tr = LogTrainer(tmp_path, Net(base), recorder=LogitRecorder(ds, dev, precision="fp32"), device=dev, logit_save_steps=100,
+                    save_logit_after=0, stop_save_logit_after=500, save_steps=500, save_eval_logits=True)
+    want_logits = {}
+    for step in range(0, 501, 100):
+        gen = torch.Generator().manual_seed(step)
+        tr.netD.p = {k: (v + 2e-2 * torch.randn(v.shape, generator=gen) if k.endswith("weight") and v.dim() == 4 else v)
+                     for k, v in base.items()}
+        tr.on_step(step)
+        want_logits[step] = dcgan_oracle.logits_pass(tr.netD.p, torch.from_numpy(x32))
+    saved = pickle.load(open(tmp_path / "logits_netD_eval.pkl", "rb"))
+    assert list(saved.keys()) == [0, 100, 200, 300, 400, 500]
+    for s_ in saved:
+        assert _logit_close(saved[s_], want_logits[s_])[0] <= 1e-5
+    got = calculate_scores(saved, start_epoch=0, end_epoch=501)
+    assert np.array_equal(got["ldr_conf_1.0_ratio_50"], so.calculate_scores(saved, 0, 501)["ldr_conf_1.0_ratio_50"])
+    # same chain on the oracle's own logits: scores agree to the logit tolerance, and so do the selected samples
+    ref = so.calculate_scores(want_logits, 0, 501)["ldr_conf_1.0_ratio_50"]
+    w = got["ldr_conf_1.0_ratio_50"]
+    assert np.abs(w - ref).max() <= 1e-4 * np.abs(ref).max()
+    top = engine.top_indices(torch.from_numpy(w).to(dev), 100, True).cpu().numpy()
+    assert np.array_equal(top, np.argsort(w, kind="stable")[-100:])
+    assert len(set(top.tolist()) & set(np.argsort(ref, kind="stable")[-100:].tolist())) >= 95
+
+
 def test_get_logit_from_dataloader_contract(dev):
     """The generic path: (data, target, weight, index) batches from a shuffled DataLoader, scattered by index."""
     from diagan_b200.trainer.trainer import LogTrainer
