@@ -889,13 +889,15 @@ conv_pair_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 // Per stage: weights 16 KB + two 128-pixel boxes 32 KB; 4 stages; accumulator 2 x 256 TMEM columns.
 constexpr int SW_STAGE = 3 * TC_A_BYTES;      // 48 KB
 constexpr int SW_STAGES = 4;
+constexpr int SW_EPI_WARPS = 8;
+constexpr int SW_THREADS = 128 + 32 * SW_EPI_WARPS;
 constexpr int kSwapSmem = 1024 + SW_STAGES * SW_STAGE;
 
 template <bool F16>
 __device__ __forceinline__ uint16_t to_h16(float v) { return (uint16_t)(pack_h2<F16>(v, 0.f) & 0xffffu); }
 
 template <bool F16>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(SW_THREADS, 1)
 conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_s, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -924,7 +926,7 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_acc_full[s]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[s]), 4);
+      mbar_init(smem_u32(&bar_acc_empty[s]), SW_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -995,9 +997,12 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp >= 4) {
     // ================= epilogue: thread = output channel, TMEM columns = the tile's 256 pixels =================
-    const int q = warp - 4;
+    // eight epilogue warps: warp w may only read the TMEM lane quadrant w % 4, so two warps share each 32-channel quadrant
+    // and split the tile's 256 pixel columns between them (warps 4..7: columns 0..127, warps 8..11: columns 128..255)
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int c = q * 32 + lane;
-    const int et = threadIdx.x - 128;                     // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 128;                     // 0..255 among the epilogue threads
     const float bias = p.bias ? p.bias[c] : 0.f;
     float w3[3] = {0.f, 0.f, 0.f};
     if (p.img) { w3[0] = p.sc_w3[c * 3]; w3[1] = p.sc_w3[c * 3 + 1]; w3[2] = p.sc_w3[c * 3 + 2]; }
@@ -1009,11 +1014,10 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
       const long long P0 = t * 256;
       if (p.img) {
-        // avg_pool2d of the normalised network input at the tile's (pooled) pixels: two pixels per epilogue thread
-        named_bar_sync(1, 128);                           // previous tile's readers are done with s_px
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const long long pix = P0 + h * 128 + et;
+        // avg_pool2d of the normalised network input at the tile's (pooled) pixels: one pixel per epilogue thread
+        named_bar_sync(1, SW_EPI_WARPS * 32);             // previous tile's readers are done with s_px
+        {
+          const long long pix = P0 + et;
           float px[3] = {0.f, 0.f, 0.f};
           if (pix < p.total_pixels) {
             const long long n = pix / HW;
@@ -1026,9 +1030,9 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               px[ch] = (norm_px(p.img, p.img_layout, n, iy, ix, ch, iH, iW) + norm_px(p.img, p.img_layout, n, iy, ix + 1, ch, iH, iW) +
                         norm_px(p.img, p.img_layout, n, iy + 1, ix, ch, iH, iW) + norm_px(p.img, p.img_layout, n, iy + 1, ix + 1, ch, iH, iW)) * 0.25f;
           }
-          s_px[(h * 128 + et) * 3] = px[0]; s_px[(h * 128 + et) * 3 + 1] = px[1]; s_px[(h * 128 + et) * 3 + 2] = px[2];
+          s_px[et * 3] = px[0]; s_px[et * 3 + 1] = px[1]; s_px[et * 3 + 2] = px[2];
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, SW_EPI_WARPS * 32);
       }
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
       if (p.debug_skip_epi) {                             // timing experiment only (SDG_DEBUG_SKIP_EPI=1): drain the protocol
@@ -1051,16 +1055,17 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int j = 0; j < 32; ++j) rnext[j] = __ldg(rp + j * 128);
         }
       };
-      load_res(0);
+      const int cbeg = half * 128, cend = cbeg + 128;
+      load_res(cbeg);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 256; c0 += 32) {
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
         const long long pb = P0 + c0;                     // first pixel of this chunk
         const bool chunk_ok = pb < p.total_pixels;        // warp-uniform; chunks never straddle total_pixels (multiple of 32)
         float rv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) rv[j] = rnext[j];
-        if (c0 + 32 < 256) load_res(c0 + 32);
-        if (c0 == 0) {
+        if (c0 + 32 < cend) load_res(c0 + 32);
+        if (c0 == cbeg) {
           mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
           tc_fence_after();
         }
@@ -1124,14 +1129,14 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
       if (p.head_out) {
         // deterministic cross-warp reduction: one thread per image adds the four warp partials in a fixed order
-        named_bar_sync(2, 128);
+        named_bar_sync(2, SW_EPI_WARPS * 32);
         const int imgs = 256 / HW;
         if (et < imgs) {
           const long long img = P0 / HW + et;
           if (img < p.n_images)
             p.head_out[img] = p.head_b[0] + ((s_head[et] + s_head[8 + et]) + (s_head[16 + et] + s_head[24 + et]));
         }
-        named_bar_sync(2, 128);
+        named_bar_sync(2, SW_EPI_WARPS * 32);
       }
     }
   }
@@ -1324,8 +1329,8 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
       p.total_pixels % 32 == 0 && (!a.head_out || (256 % (Hc * Wc) == 0 && Hc * Wc >= 32))) {
     const long long tiles = (p.m_tiles + 1) / 2;
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-    if (f16) { SDG_LAUNCH(conv_swap_kernel<true>, grid, TC_THREADS, kSwapSmem, s, map_a, map_b, map_s, p); }
-    else { SDG_LAUNCH(conv_swap_kernel<false>, grid, TC_THREADS, kSwapSmem, s, map_a, map_b, map_s, p); }
+    if (f16) { SDG_LAUNCH(conv_swap_kernel<true>, grid, SW_THREADS, kSwapSmem, s, map_a, map_b, map_s, p); }
+    else { SDG_LAUNCH(conv_swap_kernel<false>, grid, SW_THREADS, kSwapSmem, s, map_a, map_b, map_s, p); }
     return 0;
   }
   static const int stream_all = getenv("SDG_PAIR_STREAM128") ? atoi(getenv("SDG_PAIR_STREAM128")) == 2 : 0;
