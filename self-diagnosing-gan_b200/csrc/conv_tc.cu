@@ -1003,10 +1003,12 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int half = (warp - 4) >> 2;
     const int c = q * 32 + lane;
     const int et = threadIdx.x - 128;                     // 0..255 among the epilogue threads
-    const float bias = p.bias ? p.bias[c] : 0.f;
+    const int CO = p.Cout;                                // 128, or 64: weight rows 64..127 are TMA zero fill (half the MMA idles)
+    const bool c_ok = c < CO;
+    const float bias = (p.bias && c_ok) ? p.bias[c] : 0.f;
     float w3[3] = {0.f, 0.f, 0.f};
-    if (p.img) { w3[0] = p.sc_w3[c * 3]; w3[1] = p.sc_w3[c * 3 + 1]; w3[2] = p.sc_w3[c * 3 + 2]; }
-    const float hw_c = p.head_out ? p.head_w[c] : 0.f;
+    if (p.img && c_ok) { w3[0] = p.sc_w3[c * 3]; w3[1] = p.sc_w3[c * 3 + 1]; w3[2] = p.sc_w3[c * 3 + 2]; }
+    const float hw_c = (p.head_out && c_ok) ? p.head_w[c] : 0.f;
     const int HW = p.H * p.W;
     long long local = 0;
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
@@ -1049,10 +1051,10 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // not the MMA, paced the residual layers: 34 % tensor-pipe activity in profiles/r1f_ncu_full_swap_summary.txt.)
       float rnext[32];
       auto load_res = [&](int c0n) {
-        if (p.res_f32 && P0 + c0n < p.total_pixels) {
-          const float* rp = p.res_f32 + (P0 + c0n) * 128 + c;
+        if (p.res_f32 && c_ok && P0 + c0n < p.total_pixels) {
+          const float* rp = p.res_f32 + (P0 + c0n) * CO + c;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) rnext[j] = __ldg(rp + j * 128);
+          for (int j = 0; j < 32; ++j) rnext[j] = __ldg(rp + j * CO);
         }
       };
       const int cbeg = half * 128, cend = cbeg + 128;
@@ -1061,6 +1063,7 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int c0 = cbeg; c0 < cend; c0 += 32) {
         const long long pb = P0 + c0;                     // first pixel of this chunk
         const bool chunk_ok = pb < p.total_pixels;        // warp-uniform; chunks never straddle total_pixels (multiple of 32)
+        const bool st_ok = chunk_ok && c_ok;
         float rv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) rv[j] = rnext[j];
@@ -1095,20 +1098,20 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
           }
-          if (p.out_f32) {
-            float* op = p.out_f32 + pb * 128 + c;
+          if (p.out_f32 && st_ok) {
+            float* op = p.out_f32 + pb * CO + c;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) op[j * 128] = v[j];
+            for (int j = 0; j < 32; ++j) op[j * CO] = v[j];
           }
-          if (p.out_raw) {
-            uint16_t* op = p.out_raw + pb * 128 + c;
+          if (p.out_raw && st_ok) {
+            uint16_t* op = p.out_raw + pb * CO + c;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) op[j * 128] = to_h16<F16>(v[j]);
+            for (int j = 0; j < 32; ++j) op[j * CO] = to_h16<F16>(v[j]);
           }
-          if (p.out_relu) {
-            uint16_t* op = p.out_relu + pb * 128 + c;
+          if (p.out_relu && st_ok) {
+            uint16_t* op = p.out_relu + pb * CO + c;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) op[j * 128] = to_h16<F16>(fmaxf(v[j], 0.f));
+            for (int j = 0; j < 32; ++j) op[j * CO] = to_h16<F16>(fmaxf(v[j], 0.f));
           }
           if (p.head_out) {
 #pragma unroll
@@ -1325,12 +1328,17 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   const int k_iters = p.taps * p.kchunks + p.sc_chunks;
   // role-swapped kernel (N = 256 pixels per MMA) for Cout = 128 layers with a "linear" epilogue
   static const int swap_mode = getenv("SDG_SWAP") ? atoi(getenv("SDG_SWAP")) : 1;     // SDG_SWAP=0: A/B against the pixel-major kernels
-  if (swap_mode && g_pair_mode == 1 && Cout == 128 && !p.pool && !p.box16 && !p.sc_sep && !a.sd && !a.gemm && p.m_tiles >= 2 &&
-      p.total_pixels % 32 == 0 && (!a.head_out || (256 % (Hc * Wc) == 0 && Hc * Wc >= 32))) {
+  static const int swap64 = getenv("SDG_SWAP64") ? atoi(getenv("SDG_SWAP64")) : 0;
+  if (swap_mode && g_pair_mode == 1 && (Cout == 128 || (swap64 && Cout == 64)) && !p.pool && !p.box16 && !p.sc_sep && !a.sd &&
+      !a.gemm && p.m_tiles >= 2 && p.total_pixels % 32 == 0 && (!a.head_out || (256 % (Hc * Wc) == 0 && Hc * Wc >= 32))) {
+    // Cout = 64 (SDG_SWAP64=1, experiment): the weight box still has 128 rows; rows 64..127 lie outside the tensor and are
+    // zero filled by TMA, so the M = 128 instruction runs half empty and N stays 256
+    CUtensorMap map_w;
+    { int rc = tc_encode_2d(&map_w, a.wb, f16, k_cols, Cout, TC_BK, 128); if (rc) return rc; }
     const long long tiles = (p.m_tiles + 1) / 2;
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-    if (f16) { SDG_LAUNCH(conv_swap_kernel<true>, grid, SW_THREADS, kSwapSmem, s, map_a, map_b, map_s, p); }
-    else { SDG_LAUNCH(conv_swap_kernel<false>, grid, SW_THREADS, kSwapSmem, s, map_a, map_b, map_s, p); }
+    if (f16) { SDG_LAUNCH(conv_swap_kernel<true>, grid, SW_THREADS, kSwapSmem, s, map_a, map_w, map_s, p); }
+    else { SDG_LAUNCH(conv_swap_kernel<false>, grid, SW_THREADS, kSwapSmem, s, map_a, map_w, map_s, p); }
     return 0;
   }
   static const int stream_all = getenv("SDG_PAIR_STREAM128") ? atoi(getenv("SDG_PAIR_STREAM128")) == 2 : 0;
