@@ -49,31 +49,39 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi-equivalent (NVML) samples of SM clock and throttle reasons during the timed region."""
+    """nvidia-smi-equivalent (NVML) samples of SM clock and throttle reasons during the timed region.  NVML is initialised
+    in the constructor (before the timed region starts) so that the thread samples from its first millisecond."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
-
-    def run(self):
+        self.nv = self.handle = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
-                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            self.nv, self.handle = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        except Exception as e:          # NVML missing: report that instead of inventing clocks
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def run(self):
+        nv, h = self.nv, self.handle
+        if nv is None:
+            return
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        try:
             while not self.stop_flag:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
-        except Exception as e:          # NVML missing: report that instead of inventing clocks
-            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+                time.sleep(0.01)
+        except Exception as e:
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
 
     def result(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
@@ -183,6 +191,7 @@ def run_ours(args, rank, world, local_rank):
 
     def timed(step_fn, steps, warmup, profile=False):
         rec.stats = None
+        sampler = ClockSampler(local_rank) if (profile and rank == 0) else None      # NVML init happens here, untimed
         for i in range(warmup):
             step_fn(i)
         barrier()
@@ -190,7 +199,6 @@ def run_ours(args, rank, world, local_rank):
             lib.sdg_ctx_profile(rec.engine._h, 1)
         engine.launch_count(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler = ClockSampler(local_rank) if (profile and rank == 0) else None
         if sampler:
             sampler.start()
         e0.record()
@@ -250,19 +258,21 @@ def run_ours(args, rank, world, local_rank):
                                           "avg_pool2d: 36/16 of the executed MACs); > peak because the fused form skips work",
             "peak_source": f"{peaks['source']} (sustained: kernel timed inside a long step)",
             "launches_timed": int(pl.value), "ms_per_launch": (pm.value / pl.value) if pl.value else None,
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE 4096-sample launch of this kernel from the committed
-            # `ncu --set full` capture (profiles/r1f_ncu_full_swap_summary.txt, launch 0): 1.087 GB read + 0.247 GB written;
-            # algorithmic minimum of that launch = 4096 x (256 KiB input + 64 KiB output) + weights = 1.343 GB
-            "traffic": 1.087083e9 + 247.195904e6,
-            "traffic_note": "per 4096-sample launch, ncu --set full (profiles/r1f_ncu_full_swap_summary.txt, launch 0: tensor "
-                            "pipe 67.5 % active); algorithmic bytes of the same launch: 1.343e9 (input once, output once)",
+            # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed
+            # `ncu --set full` capture (profiles/r1f_ncu_full_swap_summary.txt, launch 0: 4096 samples, 1.087 GB read +
+            # 0.247 GB written = 325.7 KB/sample; algorithmic minimum 256 KiB in + 64 KiB out per sample = 327.7 KB),
+            # scaled to the samples one launch of THIS run processed
+            "traffic": (1.087083e9 + 247.195904e6) / 4096.0 * (n_local * args.steps / max(1, int(pl.value))),
+            "traffic_note": "ncu --set full, 325.7 KB/sample measured on a 4096-sample launch (profiles/"
+                            "r1f_ncu_full_swap_summary.txt, launch 0: tensor pipe 67.5 % active) x samples per launch here; "
+                            "algorithmic bytes: 327.7 KB/sample (input once, output once)",
         },
     }
     if world == 1:
         threads = os.cpu_count() or 1
-        v, detail = cpu_step_rate(4096, threads)
+        v, detail = cpu_step_rate(32768, threads)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "oracle torch fp32 forward on 4096 of 50000 samples (extrapolated linearly) "
+                                "sample": "oracle torch fp32 forward on 32768 of 50000 samples (extrapolated linearly) "
                                           "+ faithful calculate_scores on the full [50,50000] window / 50",
                                 "detail": detail}
     print(json.dumps(line), flush=True)
