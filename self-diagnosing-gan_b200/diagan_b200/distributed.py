@@ -95,10 +95,10 @@ def engine_is_stylegan2(netD) -> bool:
     return "final_conv.0.weight" in sd and "convs.0.0.weight" in sd
 
 
-def get_logit(recorder, netD, step=None) -> torch.Tensor:
-    """Distributed recording pass (train_ffhq.py:128-143 semantics: every rank ends up with the full
-    vector).  ``recorder`` is a :class:`diagan_b200.trainer.trainer.LogitRecorder` whose ``shard`` is this
-    rank's range; returns float32 [N] on the device."""
+def get_logit_resident(recorder, netD, step=None) -> torch.Tensor:
+    """Distributed recording pass over a resident dataset: every rank scores its contiguous index shard and ends up with
+    the full vector (train_ffhq.py:128-143 semantics).  ``recorder`` is a :class:`diagan_b200.trainer.trainer.LogitRecorder`;
+    returns float32 [N] on the device."""
     n = recorder.n
     # StyleGAN2: shard boundaries on whole loader batches (the recorder drops the ragged tail of the LAST shard only)
     mult = recorder.batch if engine_is_stylegan2(netD) else 1
@@ -109,6 +109,80 @@ def get_logit(recorder, netD, step=None) -> torch.Tensor:
     if step is not None:
         recorder.observe(step, full)
     return full
+
+
+def gather_indexed(idx: torch.Tensor, values: torch.Tensor, n: int):
+    """This rank's ``(dataset index, value)`` pairs -> ``np.float64 [n]`` holding every rank's values at their indices
+    (zeros elsewhere, train_ffhq.py:130).  One all-gather per tensor for the whole pass; ranks may hold different counts:
+    shorter ones are padded with index -1, which is dropped after the exchange."""
+    import numpy as np
+    if get_world_size() > 1:
+        cnt = torch.tensor([idx.numel()], dtype=torch.int64, device=idx.device)
+        m = int(concat_all_gather(cnt).max().item())
+        pad = m - idx.numel()
+        if pad:
+            idx = torch.cat([idx, idx.new_full((pad,), -1)])
+            values = torch.cat([values, values.new_zeros(pad)])
+        idx, values = concat_all_gather(idx), concat_all_gather(values)
+        keep = idx >= 0
+        idx, values = idx[keep], values[keep]
+    out = np.zeros(n)
+    out[idx.cpu().numpy()] = values.double().cpu().numpy()
+    return out
+
+
+_loader_recorders = {}
+
+
+def get_logit(dataloader, netD, device=None, step=None):
+    """Same call as ``stylegan2/train_ffhq.py:128-143`` -- ``get_logit(dataloader=loader, netD=discriminator, device=device)``
+    -- returning ``np.float64 [len(dataloader.dataset)]`` indexed by dataset index on every rank, ``netD`` left in train mode.
+
+    Each rank walks ITS loader (the reference's DistributedSampler shard, items ``(img, idx)``), the forward runs in the CUDA
+    engine with every loader batch treated as one minibatch-stddev batch exactly like ``netD(real_data)`` does, and the
+    ``(idx, logit)`` pairs are exchanged with ONE pair of all-gathers at the end of the pass (the reference issues two
+    blocking all-gathers per batch of 4).  A :class:`LogitRecorder` as first argument selects the resident-dataset pass."""
+    if not hasattr(dataloader, "dataset"):
+        return get_logit_resident(dataloader, netD, step)
+    from .trainer.trainer import LogitRecorder
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    rec = _loader_recorders.get(device)
+    if rec is None:
+        rec = _loader_recorders[device] = LogitRecorder(None, device)
+    n = len(dataloader.dataset)
+    idx_parts, logit_parts = [], []
+    sg2 = engine_is_stylegan2(netD)
+    loaded = False
+    pending, pending_b = [], 0                             # loader batches of equal size waiting for one engine call
+
+    def flush():
+        nonlocal pending
+        if not pending:
+            return
+        if sg2:
+            rec.engine.set_batch(pending_b)                # consecutive groups of pending_b samples = the loader's batches
+        logit_parts.append(rec.engine.forward(torch.cat(pending) if len(pending) > 1 else pending[0]))
+        pending = []
+
+    for item in dataloader:
+        data, idx = item[0], item[-1]
+        if not loaded:                                     # weights packed once per pass, after the batch size is known
+            rec.batch = int(data.shape[0]) if sg2 else rec.batch
+            rec.load_weights(netD)
+            loaded = True
+        x = data.to(device=device, dtype=torch.float32).contiguous()
+        if pending and (x.shape[0] != pending_b or len(pending) * pending_b >= 256):
+            flush()                                        # a short last batch is its own stddev batch (drop_last=False)
+        pending.append(x)
+        pending_b = int(x.shape[0])
+        idx_parts.append(idx.to(device))
+    flush()
+    idx_all = torch.cat(idx_parts) if idx_parts else torch.empty(0, dtype=torch.int64, device=device)
+    logit_all = torch.cat(logit_parts) if logit_parts else torch.empty(0, dtype=torch.float32, device=device)
+    out = gather_indexed(idx_all, logit_all, n)
+    if hasattr(netD, "train"):
+        netD.train()                                       # train_ffhq.py:142
+    return out
 
 
 def sharded_score(recorder, conf: float, eps: float = 0.0) -> torch.Tensor:

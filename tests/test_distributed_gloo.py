@@ -59,6 +59,13 @@ def _worker(rank, world, port, n, out_dir):
     assert spans[0][0] == 0 and spans[-1][1] == n and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
     assert np.array_equal(D.all_gather_shards(torch.from_numpy(mean[blo:bhi].copy()), n, multiple=8).numpy(), mean)
 
+    # (2c) get_logit's exchange: ranks hold different numbers of (index, value) pairs in arbitrary order (a shuffled
+    # DistributedSampler shard); one padded all-gather per tensor reassembles the dataset-indexed vector on every rank
+    perm = np.random.RandomState(9).permutation(n)
+    mine = perm[: (2 * n) // 3] if rank == 0 else perm[(2 * n) // 3:]
+    full = D.gather_indexed(torch.from_numpy(mine.copy()), torch.from_numpy(mean[mine].astype(np.float32)), n)
+    assert full.dtype == np.float64 and np.array_equal(full, mean.astype(np.float32).astype(np.float64))
+
     # (3) reference-contract concat_all_gather (train_ffhq.py:150-161)
     idx = torch.arange(rank * 4, rank * 4 + 4)
     assert D.concat_all_gather(idx).tolist() == list(range(world * 4))

@@ -884,6 +884,48 @@ def test_get_logit_from_dataloader_contract(dev):
     assert got.dtype == np.float64 and ok
 
 
+def test_stylegan2_get_logit_reference_signature(golden_dir, dev):
+    """``get_logit(dataloader, netD, device)`` exactly as stylegan2/train_ffhq.py:320 calls it: items ``(img, idx)``, every
+    loader batch is one minibatch-stddev batch, result np.float64 [N] by dataset index, netD back in train mode."""
+    from diagan_b200 import distributed as D
+    from oracle import stylegan2 as sg2_oracle
+    g = _load(golden_dir, "stylegan2_d32")
+    batch = int(g["batch"])
+    params = sg2_oracle.init_params(32, int(g["param_seed"]))
+    x = sngan_oracle.normalise_u8(torch.from_numpy(g["x_u8"]))
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self): return x.shape[0]
+        def __getitem__(self, i): return x[i], i
+
+    class Net:
+        mode = "eval"
+        def state_dict(self): return params
+        def train(self): self.mode = "train"
+
+    net = Net()
+    loader = torch.utils.data.DataLoader(DS(), batch_size=batch, shuffle=False, drop_last=True)
+    got = D.get_logit(dataloader=loader, netD=net, device=dev)
+    n_full = x.shape[0] // batch * batch
+    assert got.dtype == np.float64 and got.shape == (x.shape[0],) and net.mode == "train"
+    assert _logit_close(got[:n_full], g["logits"][:n_full])[0] <= 2e-3 and np.all(got[n_full:] == 0.0)
+    # SNGAN through the same call, shuffled loader with a ragged last batch: per-sample logits land at their index
+    sd = sngan_oracle.init_params(32, seed=1)
+    xs = _u8(75, 32, 4)
+    xn = sngan_oracle.normalise_u8(xs)
+
+    class DS2(torch.utils.data.Dataset):
+        def __len__(self): return 75
+        def __getitem__(self, i): return xn[i], i
+
+    class Net2(Net):
+        def state_dict(self): return sd
+
+    got2 = D.get_logit(torch.utils.data.DataLoader(DS2(), batch_size=16, shuffle=True), Net2(), dev)
+    want2 = sngan_oracle.logits_pass(sd, xs, 32, dtype=torch.float64)
+    assert _logit_close(got2, want2)[0] <= 2e-3
+
+
 def test_recorder_stylegan2_drop_last(golden_dir, dev):
     """StyleGAN2 recording pass through LogitRecorder: whole batches only, the ragged tail keeps 0.0 like the
     reference's drop_last=True loader (stylegan2/train_ffhq.py:596-602)."""
