@@ -142,9 +142,9 @@ def get_logit(dataloader, netD, device=None, step=None):
     engine with every loader batch treated as one minibatch-stddev batch exactly like ``netD(real_data)`` does, and the
     ``(idx, logit)`` pairs are exchanged with ONE pair of all-gathers at the end of the pass (the reference issues two
     blocking all-gathers per batch of 4).  A :class:`LogitRecorder` as first argument selects the resident-dataset pass."""
-    if not hasattr(dataloader, "dataset"):
-        return get_logit_resident(dataloader, netD, step)
     from .trainer.trainer import LogitRecorder
+    if isinstance(dataloader, LogitRecorder):
+        return get_logit_resident(dataloader, netD, step)
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     rec = _loader_recorders.get(device)
     if rec is None:

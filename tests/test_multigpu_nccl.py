@@ -1,0 +1,75 @@
+"""Two-rank NCCL run of the sharded diagnosis path on real GPUs (skipped on boxes with a single GPU; run with
+``gpurun --gpus 2 -- python -m pytest tests/test_multigpu_nccl.py -m gpu``).  The host-side index arithmetic is covered on CPU
+by tests/test_distributed_gloo.py; this file checks that the sharded pass + score exchange over NCCL reproduces the
+single-GPU result bit for bit (samples are independent, so sharding must not change a single logit)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "self-diagnosing-gan_b200")):
+        sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from diagan_b200 import distributed as D
+    from diagan_b200 import engine, synthetic
+    from diagan_b200.trainer.trainer import LogitRecorder, ResidentDataset
+
+    # ---- SNGAN-32: three sharded passes -> running stats -> sharded score == the same on one GPU ----
+    n = 3001                                                        # ragged: shards of 1501 and 1500
+    x = synthetic.uniform_images_u8(n, 32, seed=1).to(dev)
+    base = synthetic.sngan_state_dict(32, seed=1)
+    rec = LogitRecorder(ResidentDataset(x), dev, keep_snapshots=False)
+    solo = LogitRecorder(ResidentDataset(x), dev, keep_snapshots=False)
+    for step in (0, 100, 200):
+        sd = synthetic.perturb_(base, step, 2e-2)
+        full = D.get_logit(rec, sd, step=None)
+        lo, hi = D.shard_range(n)
+        rec.observe(step, full)                                     # stats of this rank's shard only
+        ref = solo.record(sd, step=step)
+        assert torch.equal(full, ref), "sharded logits differ from the single-GPU pass"
+    t = engine.conf_from_key("ldr_conf_0.3_ratio_50")
+    got = D.sharded_score(rec, t, eps=1e-6)
+    want = solo.stats.score(t, eps=1e-6)
+    assert torch.equal(got, want), "sharded score differs"
+    assert torch.equal(engine.top_indices(got, 100, True), engine.top_indices(want, 100, True))
+
+    # ---- StyleGAN2 (size 32, loader batch 4): shards are whole batches, logits identical to one GPU ----
+    n2 = 44
+    x2 = synthetic.uniform_images_u8(n2, 32, seed=2).to(dev)
+    p2 = synthetic.stylegan2_state_dict(32, seed=3)
+    r2 = LogitRecorder(ResidentDataset(x2), dev, batch=4)
+    s2 = LogitRecorder(ResidentDataset(x2), dev, batch=4)
+    lo2, hi2 = D.shard_range(n2, multiple=4)
+    assert lo2 % 4 == 0
+    assert torch.equal(D.get_logit(r2, p2), s2.record(p2))
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_nccl_matches_single_gpu(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
