@@ -89,13 +89,41 @@ class DRS(nn.Module):
         sel = idx[:k].long()
         return fake_samples.to(self.device).index_select(0, sel).float().cpu()
 
+    # batches of candidates scored per host round trip in generate_images (bounds the memory of the pending images)
+    max_batches_in_flight = 32
+
     def generate_images(self, num_images, device=None):
+        """drs.py:59-69 -- ``while num < num_images: imgs, ldr = get_fake...(batch); accepted = sub_rejection_sampler(...)``
+        -- with the accept / compact step batched: as long as ``k = (num_images - num) // batch_size`` is at least 2, not even
+        a 100 % acceptance rate could finish the loop within the next ``k`` batches, so the reference would run all of them;
+        they are generated with ``k`` generator calls (same generator RNG stream), scored by ONE discriminator call,
+        judged by ``k`` acceptance launches that update the running maximum in order on the device (psi = one draw of
+        ``k * batch_size`` from the global NumPy stream == ``k`` draws of ``batch_size``), and read back with ONE host sync.
+        The accepted images, their order and both RNG streams after the call are those of the sequential loop."""
         chunks, num = [], 0
-        while num < num_images:                                      # drs.py:59-69
-            imgs, ldr = self._ldr_device(self.batch_size)
-            _, _, idx, count = self.accept(ldr)
-            k = int(count.item())
-            chunks.append(imgs.index_select(0, idx[:k].long()))
-            num += k
+        B = self.batch_size
+        while num < num_images:
+            k = max(1, min(self.max_batches_in_flight, (num_images - num) // B))
+            with torch.no_grad():
+                imgs = [self.netG.generate_images(B, device=self.device) for _ in range(k)]
+                x = torch.cat(imgs, dim=0) if k > 1 else imgs[0]
+                out = self.netD(x)
+                if type(out) is tuple:
+                    out = out[0]
+                ldr = out.detach().reshape(-1).to(device=self.device, dtype=torch.float32).contiguous()
+            psi = torch.from_numpy(np.random.rand(k * B)).to(self.device, non_blocking=True)     # drs.py:54
+            idx = torch.empty(k, B, dtype=torch.int32, device=self.device)
+            cnt = torch.zeros(k, dtype=torch.int32, device=self.device)
+            g = self.gamma
+            for j in range(k):
+                check(self._lib.sdg_drs_accept(ptr(ldr[j * B:(j + 1) * B]), B, ptr(self._max), 1e-6, float(self.percentile),
+                                               0 if g is None else 1, 0.0 if g is None else float(g), ptr(psi[j * B:(j + 1) * B]),
+                                               None, None, ptr(idx[j]), ptr(cnt[j:j + 1]), stream_ptr(self.device)),
+                      "sdg_drs_accept")
+            counts = cnt.cpu().tolist()                                   # the one host sync of this round
+            for j in range(k):
+                if counts[j]:
+                    chunks.append(imgs[j].index_select(0, idx[j, :counts[j]].long()))
+                num += counts[j]
         out = torch.cat(chunks, dim=0)[:num_images]
         return out.cpu().float() if device is None else out.to(device)

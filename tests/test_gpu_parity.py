@@ -242,6 +242,38 @@ def test_drs_module_contract(dev):
     assert e.generate_images(50).is_cuda and e.batch_size == 128
 
 
+def test_drs_generate_images_batched_equals_sequential(dev):
+    """generate_images scores up to 32 candidate batches per host round trip; the accepted images, their
+    order, the running maximum and BOTH random streams (NumPy psi, generator) must be those of the one-batch-at-a-time loop
+    of drs.py:59-69."""
+    from diagan_b200.models.drs import DRS
+
+    class G:
+        def __init__(self):
+            self.gen = torch.Generator(device="cuda").manual_seed(5)
+            self.calls = 0
+
+        def generate_images(self, n, device=None):
+            self.calls += 1
+            return torch.randn(n, 3, 8, 8, generator=self.gen, device=device)
+
+    class D(torch.nn.Module):
+        def forward(self, x):
+            return x.mean(dim=(1, 2, 3)).view(-1, 1) * 9.0 + 0.25
+
+    outs = []
+    for in_flight in (1, 32):
+        g = G()
+        np.random.seed(7)
+        drs = DRS(g, D(), dev, batch_size=64)
+        drs.max_batches_in_flight = in_flight
+        imgs = drs.generate_images(1000, device=dev)
+        outs.append((imgs, drs.maximum, np.random.rand(), g.calls, torch.randn(4, generator=g.gen, device=dev)))
+    a, b = outs
+    assert a[0].shape == (1000, 3, 8, 8) and torch.equal(a[0], b[0])
+    assert a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and torch.equal(a[4], b[4])
+
+
 def test_drs_with_engine_discriminator_sngan64(dev):
     """BASELINE config 4: DRS acceptance pass with the SNGAN-64 discriminator running in the CUDA engine
     (EngineNetD keeps the netD(x) -> [B,1] contract of drs.py:24-28); logits checked against the oracle."""
