@@ -899,7 +899,7 @@ __device__ __forceinline__ uint16_t to_h16(float v) { return (uint16_t)(pack_h2<
 template <bool F16>
 __global__ void __launch_bounds__(SW_THREADS, 1)
 conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_s, const TcParams p) {
+                 const __grid_constant__ CUtensorMap map_s, const TcParams p, const int n_stages) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
@@ -963,7 +963,7 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tma_load_4d(dst + TC_A_BYTES, am, full, ch * TC_BK, p.cs * x0[0] + dx, p.cs * y0[0] + dy, n0[0]);
           tma_load_4d(dst + 2 * TC_A_BYTES, am, full, ch * TC_BK, p.cs * x0[1] + dx, p.cs * y0[1] + dy, n0[1]);
           if (++kc == p.kchunks) { kc = 0; ++tap; }
-          if (++stage == SW_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -990,7 +990,7 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int k = 0; k < TC_BK / 16; ++k)
             umma_bf16(d_tmem, wdesc + (uint64_t)(2 * k), pdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
           umma_commit(smem_u32(&bar_empty[stage]));
-          if (++stage == SW_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(smem_u32(&bar_acc_full[acc]));
       }
@@ -1337,8 +1337,10 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
     { int rc = tc_encode_2d(&map_w, a.wb, f16, k_cols, Cout, TC_BK, 128); if (rc) return rc; }
     const long long tiles = (p.m_tiles + 1) / 2;
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-    if (f16) { SDG_LAUNCH(conv_swap_kernel<true>, grid, SW_THREADS, kSwapSmem, s, map_a, map_w, map_s, p); }
-    else { SDG_LAUNCH(conv_swap_kernel<false>, grid, SW_THREADS, kSwapSmem, s, map_a, map_w, map_s, p); }
+    static const int sw_stages_env = getenv("SDG_SWAP_STAGES") ? atoi(getenv("SDG_SWAP_STAGES")) : SW_STAGES;   // timing experiment
+    const int sw_stages = sw_stages_env >= 2 && sw_stages_env <= SW_STAGES ? sw_stages_env : SW_STAGES;
+    if (f16) { SDG_LAUNCH(conv_swap_kernel<true>, grid, SW_THREADS, kSwapSmem, s, map_a, map_w, map_s, p, sw_stages); }
+    else { SDG_LAUNCH(conv_swap_kernel<false>, grid, SW_THREADS, kSwapSmem, s, map_a, map_w, map_s, p, sw_stages); }
     return 0;
   }
   static const int stream_all = getenv("SDG_PAIR_STREAM128") ? atoi(getenv("SDG_PAIR_STREAM128")) == 2 : 0;
