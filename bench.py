@@ -38,6 +38,40 @@ SCORE_KEY = "ldr_conf_0.3_ratio_50"
 FLOP_PER_SAMPLE = 2 * 272_072_832        # reference formulation, SURVEY 8(a) appendix
 T_WINDOW = 50
 
+# The headline line is configs[1] (default).  --workload selects the same measurement for the other discriminator
+# configurations of BASELINE.json (parity-test cases by the contract, measured here for completeness).
+WORKLOADS = {
+    "sngan32": dict(arch="sngan", size=32, n=N_PER_GPU, key=SCORE_KEY, flop=FLOP_PER_SAMPLE, metric=METRIC,
+                    desc="configs[1]: SNGAN-32 recording pass (weights re-packed per pass) + Welford stats + "
+                         "ldr_conf_0.3_ratio_50 weights + top-100, 50k x 3x32x32 uint8 per GPU",
+                    kernel="conv_swap_kernel block1.c2 (3x3 128->128 @32x32 + avg-pool + shortcut; 55.5% of the reference FLOPs), "
+                           "run as the algebraically equal 4x4 stride-2 conv with role-swapped operands (M = 128 channels, "
+                           "N = 256 pixels per tcgen05.mma)",
+                    dom_ref_flop=2.0 * 9 * 128 * 128 * 1024, cpu_sample=32768, ref_sample=2048),
+    "sngan64": dict(arch="sngan", size=64, n=25325, key="ldr_conf_5.0_ratio_50", flop=2 * 644_809_728,
+                    metric="per-sample D logits + LDR scores per second (SNGAN-64, CelebA shape, 202 599 / 8 samples per GPU)",
+                    desc="configs[2]: SNGAN-64 recording pass + Welford stats + ldr_conf_5.0_ratio_50 weights + top-100, "
+                         "25 325 x 3x64x64 uint8 per GPU (the 8-way shard of 202 599)",
+                    kernel="conv_tc_kernel<64> block1.c2 (3x3 64->64 @64x64 + avg-pool + shortcut; 23.4% of the reference FLOPs) as "
+                           "the 4x4 stride-2 conv",
+                    dom_ref_flop=2.0 * 9 * 64 * 64 * 4096, cpu_sample=4096, ref_sample=512),
+    "stylegan2": dict(arch="stylegan2", size=256, n=2048, key="ldr_conf_3.0_ratio_50", flop=None,
+                      metric="per-sample D logits + LDR scores per second (StyleGAN2-256 discriminator, FFHQ shape, bounded 2048 "
+                             "samples per GPU)",
+                      desc="configs[4]: StyleGAN2-256 recording pass (loader batch 4) + Welford stats + ldr_conf_3.0_ratio_50 "
+                           "weights + top-100, 2048 x 3x256x256 uint8 per GPU (bounded sample of the 70k pass)",
+                      kernel="conv_swap_kernel ResBlock 1 conv1 (3x3 128->128 @256x256 + FusedLeakyReLU; 20.8% of the FLOPs)",
+                      dom_ref_flop=2.0 * 9 * 128 * 128 * 65536, cpu_sample=16, ref_sample=8),
+}
+
+
+def _workload(name):
+    w = dict(WORKLOADS[name])
+    if w["flop"] is None:
+        from diagan_b200 import synthetic
+        w["flop"] = synthetic.stylegan2_flops(w["size"])
+    return w
+
 
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -91,19 +125,28 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own CPU implementation of the path, restated in oracle/ (kind "port")
 # ---------------------------------------------------------------------------------------------------
-def cpu_step_rate(sample_n: int, threads: int, score_n: int = N_PER_GPU):
-    """Time the CPU path on a bounded sample: the torch fp32 SNGAN-32 oracle forward (batch 64, eval,
-    no_grad, tensor-slice batches) over ``sample_n`` samples, plus the reference-faithful
+def cpu_step_rate(sample_n: int, threads: int, score_n: int = N_PER_GPU, workload: str = "sngan32"):
+    """Time the CPU path on a bounded sample: the torch fp32 oracle forward of the workload's discriminator (batch 64 --
+    StyleGAN2: batch 4 --, eval, no_grad, tensor-slice batches) over ``sample_n`` samples, plus the reference-faithful
     calculate_scores on a full [50, score_n] window (it recomputes mean/std for each of the 99 keys).
-    Returns samples/s of a whole 50k-sample step extrapolated linearly from the sample."""
+    Returns samples/s of a whole ``score_n``-sample step extrapolated linearly from the sample."""
     from oracle import scores as so
-    from oracle import sngan as sngan_oracle
+    w = WORKLOADS[workload]
     torch.set_num_threads(threads)
-    params = sngan_oracle.init_params(32, seed=1)
-    x = torch.from_numpy(np.random.RandomState(1).randint(0, 256, (sample_n, 32, 32, 3)).astype(np.uint8))
-    sngan_oracle.logits_pass(params, x[:64], 32)                    # warm-up
+    size = w["size"]
+    x = torch.from_numpy(np.random.RandomState(1).randint(0, 256, (sample_n, size, size, 3)).astype(np.uint8))
+    if w["arch"] == "sngan":
+        from oracle import sngan as sngan_oracle
+        params = sngan_oracle.init_params(size, seed=1)
+        run = lambda xs: sngan_oracle.logits_pass(params, xs, size)
+        run(x[:64])                                                  # warm-up
+    else:
+        from oracle import stylegan2 as sg2_oracle
+        params = sg2_oracle.init_params(size, seed=1)
+        run = lambda xs: sg2_oracle.logits_pass(params, xs, size, 4)
+        run(x[:4])
     t0 = time.perf_counter()
-    sngan_oracle.logits_pass(params, x, 32)
+    run(x)
     t_fwd = time.perf_counter() - t0
     rng = np.random.RandomState(0)
     logits = {s: rng.normal(1.0, 1.5, score_n).astype(np.float32).astype(np.float64) for s in range(T_WINDOW)}
@@ -118,25 +161,25 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 2048
+    w = WORKLOADS[args.workload]
+    sample = w["ref_sample"]
     vals = []
     for _ in range(args.warmup):
-        cpu_step_rate(256, threads, score_n=2000)
+        cpu_step_rate(max(4, sample // 8), threads, score_n=2000, workload=args.workload)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, detail = cpu_step_rate(sample, threads)
+        v, detail = cpu_step_rate(sample, threads, score_n=w["n"], workload=args.workload)
         vals.append(v)
     elapsed = time.perf_counter() - t0
     value = float(np.mean(vals))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: SNGAN-32 recording pass + ldr_conf_0.3_ratio_50 weights, 50k x 3x32x32",
-                   "l2": "n/a (CPU)"},
+        "config": {"workload": w["desc"], "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"oracle torch fp32 forward on {sample} of 50000 samples per step (extrapolated "
-                                   f"linearly) + faithful calculate_scores on the full [50,50000] window / 50"},
+                         "sample": f"oracle torch fp32 forward on {sample} of {w['n']} samples per step (extrapolated "
+                                   f"linearly) + faithful calculate_scores on the full [50,{w['n']}] window / 50"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -152,14 +195,17 @@ def run_ours(args, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    n_local, n_total = N_PER_GPU, N_PER_GPU * world
+    w = _workload(args.workload)
+    n_local, n_total = w["n"], w["n"] * world
     lo = rank * n_local
-    # synthetic shard: uint8 CIFAR shape, seeded per rank; pinned host copy for the e2e leg
-    host = synthetic.uniform_images_u8(n_local, 32, seed=1 + rank, pin=True)
+    # synthetic shard: uint8 images of the workload's shape, seeded per rank; pinned host copy for the e2e leg
+    host = synthetic.uniform_images_u8(n_local, w["size"], seed=1 + rank, pin=True)
     ds = ResidentDataset(host.to(dev))
-    base = {k: v.to(dev) for k, v in synthetic.sngan_state_dict(32, seed=1).items()}
-    rec = LogitRecorder(ds, dev, precision=args.precision, inplace_relu=True, keep_snapshots=False)
-    t_conf = engine.conf_from_key(SCORE_KEY)
+    sd0 = synthetic.sngan_state_dict(w["size"], seed=1) if w["arch"] == "sngan" else synthetic.stylegan2_state_dict(w["size"], seed=1)
+    base = {k: v.to(dev) for k, v in sd0.items()}
+    rec = LogitRecorder(ds, dev, precision=args.precision, inplace_relu=True, keep_snapshots=False, batch=4)
+    t_conf = engine.conf_from_key(w["key"])
+    host_chunk = 12544 if w["size"] <= 32 else (8192 if w["size"] <= 64 else 256)
     snap = torch.zeros(n_local, dtype=torch.float32, device=dev)
     lib = engine._lib.load()
 
@@ -185,7 +231,7 @@ def run_ours(args, rank, world, local_rank):
         return finish(i)
 
     def step_host(i):
-        rec.record_from_host(weight_sets[i % n_sets], host, step=i)
+        rec.record_from_host(weight_sets[i % n_sets], host, step=i, chunk=host_chunk, first_chunk=min(2048, host_chunk // 4))
         full, top = finish(i)
         return full.cpu(), top.cpu()                       # D2H of the step's result
 
@@ -229,30 +275,27 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = n_total * args.steps / (ms_e2e / 1e3)
     dom_tflops = (pf.value / 1e12) / (pm.value / 1e3) if pm.value > 0 else None          # EXECUTED FLOPs / time
     # the same launches in the reference formulation (conv3x3 at full resolution, then avg-pool): 2*9*Cin*Cout per pixel
-    ref_flops = 2.0 * 9 * 128 * 128 * 1024 * n_local * args.steps        # every sample of every timed step
+    ref_flops = w["dom_ref_flop"] * n_local * args.steps                 # every sample of every timed step
     dom_ref_tflops = (ref_flops / 1e12) / (pm.value / 1e3) if pm.value > 0 else None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": "configs[1]: SNGAN-32 recording pass (weights re-packed per pass) + Welford stats + "
-                               "ldr_conf_0.3_ratio_50 weights + top-100, 50k x 3x32x32 uint8 per GPU",
-                   "samples_per_gpu": n_local, "score_key": SCORE_KEY,
-                   "l2": "inputs larger than L2 (154 MB dataset, >1 GB activations per sweep); no explicit flush",
+        "config": {"workload": w["desc"],
+                   "samples_per_gpu": n_local, "score_key": w["key"],
+                   "l2": f"inputs larger than L2 ({host.numel() / 1e6:.0f} MB dataset, >1 GB activations per sweep); no explicit flush",
                    "parallelism": f"sample-index shards x{world}, MIN all-reduce + one all-gather per step"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel()),
                 "d2h_bytes_per_step": int(n_total * 8 + 100 * 8), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "whole_path_tflops": value / world * FLOP_PER_SAMPLE / 1e12,
+        "whole_path_tflops": value / world * w["flop"] / 1e12,
         "roofline": {
             "bound": "tensor",
-            "kernel": "conv_swap_kernel block1.c2 (3x3 128->128 @32x32 + avg-pool + shortcut; 55.5% of the reference FLOPs), "
-                      "run as the algebraically equal 4x4 stride-2 conv with role-swapped operands (M = 128 channels, "
-                      "N = 256 pixels per tcgen05.mma)",
+            "kernel": w["kernel"],
             "achieved": dom_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
             "frac": (dom_tflops / peaks["bf16_sustained"]) if dom_tflops else None,
-            "flops_counted": "EXECUTED by the tensor pipe (2*M*N*K of the GEMM run: 16 taps per pooled pixel)",
+            "flops_counted": "EXECUTED by the tensor pipe (2*M*N*K of the GEMM run" + (": 16 taps per pooled pixel)" if w["arch"] == "sngan" else ")"),
             "reference_formulation_tflops": dom_ref_tflops,
             "reference_formulation_note": "same launches counted as the reference computes them (conv3x3 at 32x32 then "
                                           "avg_pool2d: 36/16 of the executed MACs); > peak because the fused form skips work",
@@ -262,7 +305,8 @@ def run_ours(args, rank, world, local_rank):
             # `ncu --set full` capture (profiles/r1f_ncu_full_swap_summary.txt, launch 0: 4096 samples, 1.087 GB read +
             # 0.247 GB written = 325.7 KB/sample; algorithmic minimum 256 KiB in + 64 KiB out per sample = 327.7 KB),
             # scaled to the samples one launch of THIS run processed
-            "traffic": (1.087083e9 + 247.195904e6) / 4096.0 * (n_local * args.steps / max(1, int(pl.value))),
+            "traffic": ((1.087083e9 + 247.195904e6) / 4096.0 * (n_local * args.steps / max(1, int(pl.value)))
+                        if args.workload == "sngan32" else None),
             "traffic_note": "ncu --set full, 325.7 KB/sample measured on a 4096-sample launch (profiles/"
                             "r1f_ncu_full_swap_summary.txt, launch 0: tensor pipe 67.5 % active) x samples per launch here; "
                             "algorithmic bytes: 327.7 KB/sample (input once, output once)",
@@ -270,10 +314,10 @@ def run_ours(args, rank, world, local_rank):
     }
     if world == 1:
         threads = os.cpu_count() or 1
-        v, detail = cpu_step_rate(32768, threads)
+        v, detail = cpu_step_rate(w["cpu_sample"], threads, score_n=n_local, workload=args.workload)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "oracle torch fp32 forward on 32768 of 50000 samples (extrapolated linearly) "
-                                          "+ faithful calculate_scores on the full [50,50000] window / 50",
+                                "sample": f"oracle torch fp32 forward on {w['cpu_sample']} of {n_local} samples (extrapolated linearly) "
+                                          f"+ faithful calculate_scores on the full [50,{n_local}] window / 50",
                                 "detail": detail}
     print(json.dumps(line), flush=True)
 
@@ -284,6 +328,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sngan32", choices=sorted(WORKLOADS),
+                    help="sngan32 = the headline (BASELINE configs[1]); sngan64 / stylegan2 = the same measurement for configs[2] / [4]")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="tensor-core operand type (fp32 accumulate either way); fp16 meets the 1e-3 parity bar")
     args = ap.parse_args()
