@@ -179,7 +179,7 @@ int pack_linear_nchw_fp32(const float* W, float mul, float* wp, int O, int C, in
 // kernel (its 24 weights + 8 biases stay in registers) and strides over pixels; consecutive lanes write consecutive 16 B.
 // C and S are powers of two, so all index arithmetic is shifts (64-bit division is what made the first version slow).
 template <bool F16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 sg2_first_conv_kernel(const void* __restrict__ x, int layout, const float* __restrict__ w3, const float* __restrict__ bias,
                       h16* __restrict__ out, int64_t n_pix, int hw_shift, int c8_shift, int C) {
   const int C8 = 1 << c8_shift;
@@ -286,7 +286,7 @@ __device__ __forceinline__ void blur_hrow(const BlurCols& bc, int iy, int H, int
 }
 
 template <bool F16, int ST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)      // <= 64 registers: occupancy, not issue rate, bounds this kernel (ncu: 35 % warps)
 blur_h16_kernel(const h16* __restrict__ in, h16* __restrict__ out, int H, int W, int C, int Ho, int Wo, int pad, int c8_shift,
                 int x_tiles, int y_segs, int rows) {
   const int C8 = 1 << c8_shift;
