@@ -1305,9 +1305,15 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
     p.m_tiles = cdiv(a.n, p.bn) * p.tiles_y;
   }
   p.res_relu = a.res_relu; p.img_layout = a.img_layout;
+  // Timing experiments that produce WRONG results (operand loads or epilogues skipped) exist only in a library built with
+  // `make EXTRA=-DSDG_TIMING_EXPERIMENTS`; the shipped build ignores these environment variables.
+#ifdef SDG_TIMING_EXPERIMENTS
   static const int dbg_skip_a = getenv("SDG_DEBUG_SKIP_A") ? atoi(getenv("SDG_DEBUG_SKIP_A")) : 0;
-  static const int dbg_stages = getenv("SDG_PAIR_STAGES") ? atoi(getenv("SDG_PAIR_STAGES")) : 0;
   static const int dbg_skip_epi = getenv("SDG_DEBUG_SKIP_EPI") ? atoi(getenv("SDG_DEBUG_SKIP_EPI")) : 0;
+#else
+  static const int dbg_skip_a = 0, dbg_skip_epi = 0;
+#endif
+  static const int dbg_stages = getenv("SDG_PAIR_STAGES") ? atoi(getenv("SDG_PAIR_STAGES")) : 0;
   p.debug_skip_a = dbg_skip_a;
   p.debug_skip_epi = dbg_skip_epi;
   p.n_images = a.n;

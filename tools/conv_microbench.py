@@ -1,6 +1,8 @@
 """Kernel-level timing of one fused conv stage through the C ABI (CUDA events on the launching stream).
     python tools/conv_microbench.py [--n 4096] [--hw 32] [--cin 128] [--cout 128] [--pool 0] [--pair 1] [--iters 20]
-Debug environment switches of libsdg (SDG_DEBUG_SKIP_A, SDG_DEBUG_SKIP_EPI, SDG_PAIR_STAGES) apply."""
+Environment switches of libsdg apply: SDG_SWAP, SDG_SWAP_STAGES, SDG_PAIR_STAGES, SDG_PAIR_STREAM128 (kernel selection /
+pipeline depth, results stay correct); SDG_DEBUG_SKIP_A / SDG_DEBUG_SKIP_EPI (loads or epilogues skipped: timing only, wrong
+results) only in a library built with `make -C self-diagnosing-gan_b200/csrc EXTRA=-DSDG_TIMING_EXPERIMENTS`."""
 import argparse
 import os
 import sys
