@@ -51,9 +51,13 @@ struct TcParams {
   int sc_chunks;             // extra shortcut K iterations read through map_s (0 = none) = sc_taps * sc_kchunks
   int sc_kchunks;            // shortcut channels / 64
   int tw;                    // taps per kernel row (3: 3x3, 4: pooled-3x3-as-4x4, 1: 1x1)
-  int cs;                    // input coordinate scale: 2 for the 4x4 stride-2 form, else 1
+  int cs;                    // input coordinate scale (rows; columns too unless csx differs): 2 for the stride-2 forms, else 1
+  int csx;                   // input coordinate scale of the columns (4 in the super-pixel form of a stride-2 conv)
   int img_up;                // epilogue pixels are at pooled resolution of `img` (stride-2 form)
   int toff;                  // offset of tap 0 relative to the output pixel (times cs): -1 for "same" padding, 0 for none
+  int toffx;                 // the same for the columns
+  int superpix;              // GEMM pixel = two horizontally adjacent output pixels of a Cout = 64 layer (channels 64..127 = the
+                             // odd pixel): only the image-shortcut table of the role-swapped epilogue needs to know
   int act;                   // 1: FusedLeakyReLU on (acc + bias) before the residual
   float out_scale;           // final multiplier (StyleGAN2 ResBlock: 1/sqrt(2))
   int wide;                  // W > 128: a tile is 128 consecutive pixels of one row (tiles_x per row)
@@ -109,10 +113,14 @@ __device__ __forceinline__ void tc_k_iter(const TcParams& p, int it, int main_it
   } else if (p.tw == 3) {
     const int ty3 = (tap * 11) >> 5;            // tap / 3 for tap in 0..8
     dy = ty3 + p.toff;
-    dx = tap - 3 * ty3 + p.toff;
+    dx = tap - 3 * ty3 + p.toffx;
   } else if (p.tw == 4) {
     dy = (tap >> 2) + p.toff;
-    dx = (tap & 3) + p.toff;
+    dx = (tap & 3) + p.toffx;
+  } else if (p.tw > 1) {                        // general tap grid (super-pixel forms: 3x4, 4x6)
+    const int ty = tap / p.tw;
+    dy = ty + p.toff;
+    dx = tap - ty * p.tw + p.toffx;
   }
 }
 
@@ -495,7 +503,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_expect_tx(full, STAGE_BYTES);
           const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
           const int cs = (is_sc && p.sc_sep) ? 1 : p.cs;
-          tma_load_4d(a_dst, am, full, ch * TC_BK, cs * x0 + dx, cs * y0 + dy, n0);
+          const int csx = (is_sc && p.sc_sep) ? 1 : p.csx;
+          tma_load_4d(a_dst, am, full, ch * TC_BK, csx * x0 + dx, cs * y0 + dy, n0);
           tma_load_2d(a_dst + TC_A_BYTES, &map_b, full, it * TC_BK, nt * BN);
           if (++kc == p.kchunks) { kc = 0; ++tap; }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
@@ -653,7 +662,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (leader) mbar_arrive(smem_u32(&bar_full[stage]));
           } else {
             if (leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * TC_A_BYTES);     // both CTAs' A tiles
-            tma_load_4d_pair(a_base + stage * TC_A_BYTES, am, full_leader, ch * TC_BK, p.cs * x0 + dx, p.cs * y0 + dy, n0);
+            tma_load_4d_pair(a_base + stage * TC_A_BYTES, am, full_leader, ch * TC_BK, p.csx * x0 + dx, p.cs * y0 + dy, n0);
           }
           if (++kc == p.kchunks) { kc = 0; ++tap; }
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
@@ -809,11 +818,12 @@ conv_pair_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           tc_k_iter(p, it, main_iters, tap, kc, is_sc, ch, dy, dx);
           const CUtensorMap* am = is_sc ? &map_s : &map_a;
           const int cs = (is_sc && p.sc_sep) ? 1 : p.cs;
+          const int csx = (is_sc && p.sc_sep) ? 1 : p.csx;
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[stage]), 0);
           if (leader) mbar_expect_tx(smem_u32(&bar_full[stage]), 2 * STAGE);
           const uint32_t dst = smem_base + stage * STAGE;
-          tma_load_4d_pair(dst, am, full_leader, ch * TC_BK, cs * x0 + dx, cs * y0 + dy, n0);
+          tma_load_4d_pair(dst, am, full_leader, ch * TC_BK, csx * x0 + dx, cs * y0 + dy, n0);
           tma_load_2d_pair(dst + TC_A_BYTES, &map_b, full_leader, it * TC_BK, nt * BN + (int)rank * (BN / 2));
           if (++kc == p.kchunks) { kc = 0; ++tap; }
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
@@ -908,7 +918,8 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __shared__ __align__(8) uint64_t bar_acc_full[2];
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_px[256 * 3];              // pooled normalised image pixels of the current tile (image shortcut)
+  __shared__ float s_px[256 * 2 * 3];          // pooled normalised image pixels of the current tile (image shortcut; two per
+                                               // GEMM pixel in the super-pixel form)
   __shared__ float s_head[4 * 8];              // per-warp partial logits of the (up to 8) images of the current tile
 
   const int warp = threadIdx.x >> 5;
@@ -960,8 +971,8 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_expect_tx(full, SW_STAGE);
           const uint32_t dst = smem_base + stage * SW_STAGE;
           tma_load_2d(dst, &map_b, full, it * TC_BK, 0);
-          tma_load_4d(dst + TC_A_BYTES, am, full, ch * TC_BK, p.cs * x0[0] + dx, p.cs * y0[0] + dy, n0[0]);
-          tma_load_4d(dst + 2 * TC_A_BYTES, am, full, ch * TC_BK, p.cs * x0[1] + dx, p.cs * y0[1] + dy, n0[1]);
+          tma_load_4d(dst + TC_A_BYTES, am, full, ch * TC_BK, p.csx * x0[0] + dx, p.cs * y0[0] + dy, n0[0]);
+          tma_load_4d(dst + 2 * TC_A_BYTES, am, full, ch * TC_BK, p.csx * x0[1] + dx, p.cs * y0[1] + dy, n0[1]);
           if (++kc == p.kchunks) { kc = 0; ++tap; }
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
@@ -1009,6 +1020,7 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float w3[3] = {0.f, 0.f, 0.f};
     if (p.img && c_ok) { w3[0] = p.sc_w3[c * 3]; w3[1] = p.sc_w3[c * 3 + 1]; w3[2] = p.sc_w3[c * 3 + 2]; }
     const float hw_c = (p.head_out && c_ok) ? p.head_w[c] : 0.f;
+    const int spx_n = p.superpix ? 2 : 1, spx_par = p.superpix ? (c >> 6) : 0;    // warp-uniform: a warp owns 32 channels
     const int HW = p.H * p.W;
     long long local = 0;
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
@@ -1018,21 +1030,25 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (p.img) {
         // avg_pool2d of the normalised network input at the tile's (pooled) pixels: one pixel per epilogue thread
         named_bar_sync(1, SW_EPI_WARPS * 32);             // previous tile's readers are done with s_px
-        {
+        const int npar = p.superpix ? 2 : 1;
+        for (int par = 0; par < npar; ++par) {
           const long long pix = P0 + et;
           float px[3] = {0.f, 0.f, 0.f};
           if (pix < p.total_pixels) {
             const long long n = pix / HW;
             const int r = (int)(pix - n * HW);
-            const int y = r / p.W, x = r - y * p.W;
+            const int y = r / p.W, xg = r - y * p.W;
+            const int x = p.superpix ? 2 * xg + par : xg;            // output column of this parity
+            const int Wout = p.superpix ? 2 * p.W : p.W;
             const int iy = p.img_up ? 2 * y : y, ix = p.img_up ? 2 * x : x;
-            const int iH = p.img_up ? 2 * p.H : p.H, iW = p.img_up ? 2 * p.W : p.W;
+            const int iH = p.img_up ? 2 * p.H : p.H, iW = p.img_up ? 2 * Wout : Wout;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch)
               px[ch] = (norm_px(p.img, p.img_layout, n, iy, ix, ch, iH, iW) + norm_px(p.img, p.img_layout, n, iy, ix + 1, ch, iH, iW) +
                         norm_px(p.img, p.img_layout, n, iy + 1, ix, ch, iH, iW) + norm_px(p.img, p.img_layout, n, iy + 1, ix + 1, ch, iH, iW)) * 0.25f;
           }
-          s_px[et * 3] = px[0]; s_px[et * 3 + 1] = px[1]; s_px[et * 3 + 2] = px[2];
+          float* d = s_px + (et * npar + par) * 3;
+          d[0] = px[0]; d[1] = px[1]; d[2] = px[2];
         }
         named_bar_sync(1, SW_EPI_WARPS * 32);
       }
@@ -1082,7 +1098,7 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (p.img) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float* px = s_px + (c0 + j) * 3;      // same address in every lane: broadcast
+              const float* px = s_px + ((c0 + j) * spx_n + spx_par) * 3;      // same address in every lane: broadcast
               v[j] = fmaf(w3[0], px[0], fmaf(w3[1], px[1], fmaf(w3[2], px[2], v[j])));
             }
           }
@@ -1171,6 +1187,12 @@ constexpr int kStreamSmem = 1024 + 6 * (TC_A_BYTES + 128 * TC_BK * 2);   // 6 x 
 static int g_pair_mode = 1;                          // 0 = single-CTA pixel-major kernels only, 1 = default selection (role-swapped,
                                                      // streamed / resident CTA pairs where they apply), 2 = CTA pairs but no role swap
 void conv_tc_set_pair(int on) { g_pair_mode = on; }
+// true when Cout = 128 stages with a linear epilogue run on the role-swapped kernel (the only epilogue that knows the
+// super-pixel form of the image shortcut)
+bool conv_tc_swap_active() {
+  static const int swap_mode = getenv("SDG_SWAP") ? atoi(getenv("SDG_SWAP")) : 1;
+  return swap_mode && g_pair_mode == 1;
+}
 
 int tc_encode_2d(CUtensorMap* map, const void* ptr, int f16, uint64_t inner, uint64_t outer, uint32_t box_inner,
                  uint32_t box_outer) {
@@ -1189,11 +1211,12 @@ int tc_encode_2d(CUtensorMap* map, const void* ptr, int f16, uint64_t inner, uin
 // 4-D map over NHWC activations; box = 64 channels x bw x bh x bn pixels; es = traversal stride over pixels (2 for the
 // stride-2 form: the box then spans es*bw x es*bh input pixels and every es-th one is loaded)
 static int encode_act(CUtensorMap* map, const void* ptr, int f16, int64_t n, int H, int W, int C, int bw, int bh, int bn,
-                      int es) {
+                      int es, int esx = 0) {
+  if (esx <= 0) esx = es;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), (cuuint32_t)bn};
-  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(bw * esx), (cuuint32_t)(bh * es), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)esx, (cuuint32_t)es, 1};
   CUresult r = g_encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1235,7 +1258,10 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   const int H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout, taps = a.taps;
   const bool s2 = a.pool4 != 0;          // conv3x3 + avg_pool2d(2) evaluated as the equivalent 4x4 stride-2 conv
   const bool strided = s2 || a.stride == 2;
-  SDG_REQUIRE(taps == 9 || taps == 1, SDG_E_UNSUPPORTED, "conv_tc: taps=%d", taps);
+  SDG_REQUIRE(a.general || taps == 9 || taps == 1, SDG_E_UNSUPPORTED, "conv_tc: taps=%d", taps);
+  SDG_REQUIRE(!a.general || (a.taps_x >= 1 && a.taps_y >= 1 && a.grid_w >= 4 && (a.grid_w & (a.grid_w - 1)) == 0 && a.in_H > 0 &&
+                             a.in_W > 0 && !a.pool && !a.pool4 && a.stride == 1 && !a.sc_in && !a.gemm && a.sx * a.grid_w <= 256),
+              SDG_E_INVALID, "conv_tc: malformed general tap grid");
   SDG_REQUIRE(!s2 || (taps == 9 && a.pool), SDG_E_INVALID, "conv_tc: pool4 needs a pooled 3x3 stage");
   SDG_REQUIRE(a.stride == 1 || a.stride == 2, SDG_E_UNSUPPORTED, "conv_tc: stride=%d", a.stride);
   SDG_REQUIRE(!(a.stride == 2 && a.pool), SDG_E_UNSUPPORTED, "conv_tc: strided conv with pooling");
@@ -1243,6 +1269,8 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   if (a.gemm) {
     SDG_REQUIRE(taps == 1 && H == 1 && W >= 1 && a.n == 1 && !a.pool && a.stride == 1 && !a.sc_in && !a.img && !a.sd, SDG_E_INVALID,
                 "conv_tc: gemm mode takes a [W rows][Cin] matrix (n = 1, H = 1, taps = 1) and no conv extras");
+  } else if (a.general) {
+    SDG_REQUIRE(H >= 4 && (H & (H - 1)) == 0, SDG_E_UNSUPPORTED, "conv_tc: general grid H=%d", H);
   } else {
     SDG_REQUIRE(W >= 4 && W <= 512 && (W & (W - 1)) == 0 && H == W, SDG_E_UNSUPPORTED, "conv_tc: H=%d W=%d", H, W);
   }
@@ -1251,7 +1279,7 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   SDG_REQUIRE((a.sd == nullptr) == (a.sd_w == nullptr) && (!a.sd || !a.pool), SDG_E_INVALID, "conv_tc: sd / sd_w mismatch");
   SDG_REQUIRE(a.sc_C % TC_BK == 0, SDG_E_UNSUPPORTED, "conv_tc: shortcut channels %d", a.sc_C);
   SDG_REQUIRE((a.sc_C == 0) == (a.sc_in == nullptr), SDG_E_INVALID, "conv_tc: shortcut tensor / channels mismatch");
-  SDG_REQUIRE(!a.img || (a.pool && a.sc_w3), SDG_E_INVALID, "conv_tc: image shortcut needs pooling and weights");
+  SDG_REQUIRE(!a.img || ((a.pool || a.general) && a.sc_w3), SDG_E_INVALID, "conv_tc: image shortcut needs pooling and weights");
   SDG_REQUIRE(a.out_relu || a.out_raw || a.out_f32 || a.head_out, SDG_E_INVALID, "conv_tc: no output");
   SDG_REQUIRE(!a.head_out || (a.head_w && a.head_b && Cout == 128 && !a.pool && !a.img && (H * W == 32 || H * W == 64) && !a.gemm),
               SDG_E_UNSUPPORTED, "conv_tc: fused head needs Cout = 128, an un-pooled stage and 32 or 64 pixels per image");
@@ -1261,7 +1289,7 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   if (a.n == 0) return 0;
   // H, W describe the GEMM's M grid for a stride-1 conv and for pool4 (where the grid is H/2 x W/2); for an explicit
   // stride-2 conv they are the OUTPUT grid and in_H / in_W give the input tensor's extent
-  const int Hc = s2 ? H / 2 : H, Wc = s2 ? W / 2 : W;
+  const int Hc = s2 ? H / 2 : H, Wc = a.general ? a.grid_w : (s2 ? W / 2 : W);
   const int Hin = a.in_H ? a.in_H : H, Win = a.in_W ? a.in_W : W;
   TcParams p;
   p.H = Hc; p.W = Wc; p.Cin = Cin; p.Cout = Cout;
@@ -1269,9 +1297,14 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   p.tw = s2 ? 4 : (taps == 9 ? 3 : 1);
   p.cs = strided ? 2 : 1;
   p.toff = a.no_pad ? 0 : -1;
+  p.csx = p.cs; p.toffx = p.toff; p.superpix = 0;
+  if (a.general) {
+    p.taps = a.taps_x * a.taps_y; p.tw = a.taps_x;
+    p.cs = a.sy; p.csx = a.sx; p.toff = a.offy; p.toffx = a.offx; p.superpix = a.superpix;
+  }
   p.act = a.act;
   p.out_scale = a.out_scale;
-  p.img_up = s2 ? 1 : 0;
+  p.img_up = (s2 || (a.general && a.img_up)) ? 1 : 0;
   p.kchunks = Cin / TC_BK;
   p.sc_kchunks = a.sc_C / TC_BK;
   p.sc_chunks = (s2 ? 4 : 1) * p.sc_kchunks;
@@ -1321,11 +1354,12 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   p.bias = a.bias; p.sd = a.sd; p.sd_w = a.sd_w; p.res_f32 = a.res_f32;
   p.head_w = a.head_w; p.head_b = a.head_b; p.head_out = a.head_out; p.img = a.img; p.sc_w3 = a.sc_w3;
   p.out_relu = a.out_relu; p.out_raw = a.out_raw; p.out_f32 = a.out_f32;
-  const int es = strided ? 2 : 1;               // TMA traversal stride over input pixels
+  const int es = a.general ? a.sy : (strided ? 2 : 1);      // TMA traversal stride over input pixels (rows; columns: esx)
+  const int esx = a.general ? a.sx : es;
 
   CUtensorMap map_a, map_b, map_s;
   const uint64_t k_cols = (uint64_t)p.taps * Cin + (uint64_t)p.sc_chunks * TC_BK;
-  { int rc = encode_act(&map_a, a.in, f16, a.n, Hin, Win, Cin, bw, bh, bn, es); if (rc) return rc; }
+  { int rc = encode_act(&map_a, a.in, f16, a.n, Hin, Win, Cin, bw, bh, bn, es, esx); if (rc) return rc; }
   if (a.sc_in && a.sc_sep) { int rc = encode_act(&map_s, a.sc_in, f16, a.n, Hc, Wc, a.sc_C, bw, bh, bn, 1); if (rc) return rc; }
   else if (a.sc_in) { int rc = encode_act(&map_s, a.sc_in, f16, a.n, Hin, Win, a.sc_C, bw, bh, bn, es); if (rc) return rc; }
   else map_s = map_a;

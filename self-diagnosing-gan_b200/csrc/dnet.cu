@@ -52,6 +52,10 @@ struct ConvLayer {
   DevBuf w3, bias_sum;       // 16-bit path: fp32 [Cout][3] shortcut weights (DBlockOptimized), conv + shortcut bias
   int ktot = 0;              // 16-bit path: K columns of w16 (conv taps + folded shortcut columns)
   int pool4 = 0;             // 16-bit path: packed for the 4x4 stride-2 form of conv3x3 + avg_pool2d
+  // super-pixel form of a Cout = 64 layer (two adjacent output pixels = one 128-channel GEMM pixel):
+  // w16s [128][ty * (tx + shift) * Cin], bias2 / w3s = the 64-channel vectors twice
+  int superpix = 0;
+  DevBuf w16s, bias2, w3s;
   bool has_bias = false;
 };
 
@@ -154,7 +158,8 @@ extern "C" int sdg_ctx_create(int device, sdg_ctx** out) {
 extern "C" int sdg_ctx_destroy(sdg_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); l.w3.release(); l.bias_sum.release(); }
+  for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); l.w3.release(); l.bias_sum.release();
+                            l.w16s.release(); l.bias2.release(); l.w3s.release(); }
   c->head_w.release(); c->head_b.release(); c->sigma.release();
   c->sn_table.release(); c->sn_scratch.release(); c->bn_scratch.release();
   for (auto& b : c->buf) b.release();
@@ -297,6 +302,30 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
         if (rc) return rc;
       } else {
         SDG_CUDA(cudaMemcpyAsync(l2.bias_sum.p, l2.bias.p, sizeof(float) * l2.cout, cudaMemcpyDeviceToDevice, s));
+      }
+      // ---- super-pixel forms of the Cout = 64 layers (SNGAN-64 block1.c2 and block2.c1) ----
+      static const int use_superpix = getenv("SDG_SUPERPIX") ? atoi(getenv("SDG_SUPERPIX")) : 1;
+      auto dup = [&](DevBuf& dst, const float* src, int n_el) -> int {
+        { int rc = dst.ensure(sizeof(float) * 2 * n_el); if (rc) return rc; }
+        SDG_CUDA(cudaMemcpyAsync(dst.p, src, sizeof(float) * n_el, cudaMemcpyDeviceToDevice, s));
+        SDG_CUDA(cudaMemcpyAsync(dst.as<float>() + n_el, src, sizeof(float) * n_el, cudaMemcpyDeviceToDevice, s));
+        return 0;
+      };
+      l1.superpix = l2.superpix = 0;
+      if (use_superpix && c->blocks[bi].kind == 0 && l2.cout == 64 && l2.cin == 64 && l2.pool4) {
+        // block1.c2 in the 4x4 stride-2 form: 4 x 4 taps, x-stride 2 -> 4 x 6 taps, x-stride 4
+        { int rc = l2.w16s.ensure(sizeof(h16) * 128 * 4 * 6 * l2.cin); if (rc) return rc; }
+        { int rc = pack_superpix_h16(l2.w16.as<h16>(), l2.w16s.as<h16>(), 64, l2.cin, 4, 4, 2, s); if (rc) return rc; }
+        { int rc = dup(l2.bias2, l2.bias_sum.as<float>(), 64); if (rc) return rc; }
+        { int rc = dup(c->convs[isc].w3s, c->convs[isc].w3.as<float>(), 64 * 3); if (rc) return rc; }
+        l2.superpix = 1;
+      }
+      if (use_superpix && c->blocks[bi].kind == 1 && l1.cout == 64 && l1.cin == 64) {
+        // a plain 3x3 conv: 3 x 3 taps -> 3 x 4 taps, x-stride 2
+        { int rc = l1.w16s.ensure(sizeof(h16) * 128 * 3 * 4 * l1.cin); if (rc) return rc; }
+        { int rc = pack_superpix_h16(l1.w16.as<h16>(), l1.w16s.as<h16>(), 64, l1.cin, 3, 3, 1, s); if (rc) return rc; }
+        { int rc = dup(l1.bias2, l1.bias.as<float>(), 64); if (rc) return rc; }
+        l1.superpix = 1;
       }
     }
   }
@@ -446,15 +475,29 @@ static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, 
       // DBlockOptimized: c1 straight from the image bytes; shortcut c_sc(avg_pool2d(x)) as 3 FMAs in c2's epilogue
       if ((rc = first_conv(x, layout, c1.w16.as<h16>(), c1.bias.as<float>(), T, nb, S, c1.cout, f16, s))) return rc;
       a2.img = x; a2.img_layout = layout; a2.sc_w3 = c->convs[i1 + 2].w3.as<float>();
+      // executed FLOPs of this launch: the 4x4 stride-2 form does 16 taps per pooled pixel instead of 9 per input pixel
+      double macs_per_out = c2.pool4 ? 16.0 * c2.cin * 0.25 : 9.0 * c2.cin;
+      if (c2.superpix && conv_tc_swap_active()) {
+        // two pooled pixels per GEMM pixel: [n, ho, ho/2] grid, 4 x 6 taps at x-stride 4, 128 "channels"
+        a2.general = 1; a2.pool = 0; a2.pool4 = 0; a2.img_up = 1; a2.superpix = 1;
+        a2.H = ho; a2.W = ho / 2; a2.grid_w = ho / 2; a2.in_H = hw; a2.in_W = hw;
+        a2.taps_y = 4; a2.taps_x = 6; a2.sy = 2; a2.sx = 4; a2.offy = -1; a2.offx = -1;
+        a2.Cout = 128; a2.wb = c2.w16s.as<h16>(); a2.bias = c2.bias2.as<float>(); a2.sc_w3 = c->convs[i1 + 2].w3s.as<float>();
+        macs_per_out = 24.0 * c2.cin * 0.25;            // per original-resolution pixel per output channel, zeros included
+      }
       if ((rc = prof_begin(c, s))) return rc;
       if ((rc = conv_tc(a2, f16, s))) return rc;
-      // executed FLOPs of this launch: the 4x4 stride-2 form does 16 taps per pooled pixel instead of 9 per input pixel
-      const double macs_per_out = c2.pool4 ? 16.0 * c2.cin * 0.25 : 9.0 * c2.cin;
       if ((rc = prof_end(c, s, 2.0 * (double)nb * hw * hw * c2.cout * macs_per_out))) return rc;
     } else {
       TcConv a1;
       a1.n = nb; a1.H = hw; a1.W = hw; a1.Cin = c1.cin; a1.Cout = c1.cout; a1.taps = 9;
       a1.in = hR[cur]; a1.wb = c1.w16.as<h16>(); a1.bias = c1.bias.as<float>(); a1.out_relu = T;
+      if (c1.superpix && conv_tc_swap_active()) {
+        // two adjacent output pixels per GEMM pixel: [n, hw, hw/2] grid, 3 x 4 taps at x-stride 2, 128 "channels"
+        a1.general = 1; a1.H = hw; a1.W = hw / 2; a1.grid_w = hw / 2; a1.in_H = hw; a1.in_W = hw;
+        a1.taps_y = 3; a1.taps_x = 4; a1.sy = 1; a1.sx = 2; a1.offy = -1; a1.offx = -1;
+        a1.Cout = 128; a1.wb = c1.w16s.as<h16>(); a1.bias = c1.bias2.as<float>();
+      }
       if ((rc = conv_tc(a1, f16, s))) return rc;
       if (has_sc) {                      // 1x1 shortcut conv folded into c2's K loop (input: relu(h) or h)
         a2.sc_in = c->inplace_relu ? hR[cur] : hW[cur];

@@ -99,6 +99,10 @@ int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* w
 int pack_pool4_h16(const float* W, const float* sigma, h16* wb, int Cout, int Cin, int f16, int ld, cudaStream_t s);
 int pack_pool4_sc_h16(const float* Wsc, const float* sigma, h16* wb, int Cout, int Csc, int sc_pad, int f16, int ld, int col0,
                       cudaStream_t s);
+// super-pixel expansion of a packed 16-bit weight matrix (Cout = 64 layers): src [Cout][ty * txs * Cin] ->
+// dst [2*Cout][ty * (txs + shift) * Cin]; row par*Cout + c holds src row c shifted right by par*shift taps (zeros elsewhere):
+// output pixels 2x and 2x+1 of a conv with x-stride `shift` share one window of txs + shift input columns
+int pack_superpix_h16(const h16* src, h16* dst, int Cout, int Cin, int ty, int txs, int shift, cudaStream_t s);
 int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);          // out = a + b
 int scale_vec(const float* in, const float* sigma, float* out, int n, cudaStream_t s);   // out = in / sigma
 // BatchNorm(eval) folding: scale[o] = gamma/sqrt(var+eps), shift[o] = beta - mean*scale
@@ -128,6 +132,12 @@ struct TcConv {
   int no_pad = 0;                 // 1: taps start at the output pixel (padding 0) instead of one pixel before ("same")
   int act = 0;                    // 1: FusedLeakyReLU on (acc + bias): leaky_relu(., 0.2) * sqrt(2), before the residual
   float out_scale = 1.0f;         // final multiplier after the residual (StyleGAN2 ResBlock: 1/sqrt(2))
+  // general tap grid (super-pixel forms of Cout = 64 layers): taps_y x taps_x taps starting at (offy, offx) relative to
+  // (sy * y, sx * x) of the GEMM pixel (y, x); the GEMM grid is H rows x grid_w columns, the input in_H x in_W.
+  // wb = [Cout][taps_y * taps_x * Cin] in (ty, tx, c) order.  superpix = 1: a GEMM pixel is two adjacent output pixels
+  // (channel 64 + c = pixel 2x+1): only the image shortcut needs to know.
+  int general = 0, grid_w = 0, taps_x = 0, taps_y = 0, sx = 1, sy = 1, offx = 0, offy = 0, superpix = 0;
+  int img_up = 0;                 // general form: the GEMM rows are at half the resolution of `img` (pooled stage)
   int gemm = 0;                   // 1: plain GEMM rows: in = [W rows][Cin] (H = 1, any W >= 1), taps = 1  (EqualLinear)
   const float* sd = nullptr;      // [n] per-sample scalar of a spatially constant extra input channel (minibatch-stddev) ...
   const float* sd_w = nullptr;    // ... and its summed weights [H*W][Cout]: v += sd[n] * sd_w[pixel][o] before the activation
@@ -148,6 +158,7 @@ struct TcConv {
 };
 int conv_tc_init(int device);
 int conv_tc(const TcConv& args, int f16, cudaStream_t s);
+bool conv_tc_swap_active();
 void conv_tc_set_pair(int on);   // 1 (default): Cout = 128 3x3 layers run on the CTA-pair (cta_group::2) kernel
 // out = relu(conv3x3(normalise(x)) + bias): x uint8 NHWC or fp32 NCHW [n,3,S,S]; wb [Cout][64] (k = tap*3+c, 27 real)
 int first_conv_init();

@@ -247,4 +247,26 @@ int permute_fc(const float* w, float* out, int C, int HW, cudaStream_t s) {
   return 0;
 }
 
+__global__ void __launch_bounds__(256)
+pack_superpix_kernel(const h16* __restrict__ src, h16* __restrict__ dst, int Cout, int Cin, int ty, int txs, int shift) {
+  const int txd = txs + shift;
+  const int64_t Kd = (int64_t)ty * txd * Cin, Ks = (int64_t)ty * txs * Cin, total = 2LL * Cout * Kd;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int row = (int)(i / Kd);
+    const int k = (int)(i - (int64_t)row * Kd);
+    const int par = row / Cout, c = row - par * Cout;
+    const int tap = k / Cin, ci = k - tap * Cin;
+    const int t_y = tap / txd, j = tap - t_y * txd;
+    const int tx = j - par * shift;
+    dst[i] = (tx >= 0 && tx < txs) ? src[(int64_t)c * Ks + ((int64_t)t_y * txs + tx) * Cin + ci] : (h16)0;
+  }
+}
+
+int pack_superpix_h16(const h16* src, h16* dst, int Cout, int Cin, int ty, int txs, int shift, cudaStream_t s) {
+  const int64_t total = 2LL * Cout * ty * (txs + shift) * Cin;
+  SDG_LAUNCH(pack_superpix_kernel, stream_grid(total, 256), 256, 0, s, src, dst, Cout, Cin, ty, txs, shift);
+  return 0;
+}
+
 }  // namespace sdg
