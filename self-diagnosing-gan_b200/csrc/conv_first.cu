@@ -29,7 +29,11 @@ struct FcParams {
   h16* out;
 };
 
-template <int BN, bool F16>
+// SP = super-pixel form for Cout = 64 (BN = 128): a GEMM row is two horizontally adjacent pixels, its 128 columns are
+// 64 channels of the even + 64 of the odd pixel; the window is 3 x 4 taps at x-stride 2 (K = 36 + 2 bias columns, 3 MMAs),
+// the weights hold each 3x3 filter twice, shifted by one column.  Same bytes out per tile as the Cout = 128 case, half the
+// tiles, 36 instead of 54 gathered values per pixel pair (the builders, not HBM, bound the plain Cout = 64 kernel).
+template <int BN, bool F16, bool SP>
 __global__ void __launch_bounds__(FC_THREADS, 2)
 first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const FcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -43,13 +47,14 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
 
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float s_rawf[3][768];      // raw rows: (R+2) x S x 3 bytes (u8) or floats (fp32 NCHW)
+  __shared__ __align__(16) float s_rawf[3][1152];     // raw rows: (R+2) x S x 3 bytes (u8) or floats (fp32 NCHW)
   __shared__ uint16_t s_lut[256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = p.S;
-  const int R = 128 / S;                  // image rows per tile
+  const int SX = SP ? S / 2 : S;          // GEMM pixels per image row
+  const int R = 128 / SX;                 // image rows per tile
   const int tiles_y = S / R;
 
   if (threadIdx.x < 256) {
@@ -89,13 +94,14 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
     // bias as two extra K columns (k = 27: hi, k = 28: lo) of the resident weight tile; A carries 1.0 there.
     // row o of the swizzled tile: 16-byte chunk 3 (k = 24..31) sits at chunk position 3 ^ (o & 7)
     for (int o = lane; o < BN; o += 32) {
-      const float b = p.bias[o];
+      const float b = p.bias[SP ? (o & 63) : o];
       const uint32_t hi = pack_h2<F16>(b, 0.f) & 0xffffu;
       const float bhi = unpack_h2<F16>(hi).x;
       const uint32_t lo = pack_h2<F16>(b - bhi, 0.f) & 0xffffu;
-      uint16_t* chunk = reinterpret_cast<uint16_t*>(smem_gen + 2 * FC_A_BYTES + o * 128 + ((3 ^ (o & 7)) << 4));
-      chunk[3] = (uint16_t)hi;
-      chunk[4] = (uint16_t)lo;
+      // plain: k = 27, 28 (chunk 3, elements 3, 4); super-pixel: k = 36, 37 (chunk 4, elements 4, 5)
+      uint16_t* chunk = reinterpret_cast<uint16_t*>(smem_gen + 2 * FC_A_BYTES + o * 128 + (((SP ? 4 : 3) ^ (o & 7)) << 4));
+      chunk[SP ? 4 : 3] = (uint16_t)hi;
+      chunk[SP ? 5 : 4] = (uint16_t)lo;
     }
     fence_proxy_async_smem();
     __syncwarp();
@@ -113,6 +119,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
         umma_bf16(d_tmem, adesc, bdesc, idesc, 0u);                 // k = 0..15
         umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);         // k = 16..31 (27, 28: the bias columns; 29..31 zero)
+        if (SP) umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u); // k = 32..47 (36, 37: the bias columns)
         umma_commit(smem_u32(&a_empty[buf]));
         umma_commit(smem_u32(&acc_full[buf]));
       }
@@ -120,7 +127,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
   } else if (warp >= 4) {
     // ================= builders: raw rows -> normalised patch -> swizzled im2col tile =================
     const int bt = threadIdx.x - 128;           // 0..127 = pixel of the tile
-    const int ly = bt / S, lx = bt - ly * S;
+    const int ly = bt / SX, lx = bt - ly * SX;      // row of the tile, GEMM pixel within the row
     const bool u8 = p.layout == SDG_LAYOUT_U8_NHWC;
     auto prefetch_raw = [&](long long tile, int rb) {
       if (tile < p.tiles) {
@@ -164,11 +171,15 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
       // the raw buffer of tile local-1 is free now: prefetch two tiles ahead
       prefetch_raw(tile + 2 * (long long)gridDim.x, (int)((local + 2) % 3));
       // ---- gather this pixel's 3x3x3 neighbourhood: k = (ky*3+kx)*3 + c (27 independent byte -> LUT chains) ----
-      uint16_t vals[28];
+      constexpr uint32_t kOne = F16 ? 0x3C00u : 0x3F80u;      // 1.0 in the operand type: the bias columns
+      constexpr int TX = SP ? 4 : 3;                           // window columns
+      constexpr int NV = 3 * TX * 3;                           // 27 or 36 gathered values
+      constexpr int NW = SP ? 24 : 16;                         // packed 32-bit words written per row (K = 48 or 32)
+      uint16_t vals[NW * 2];
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int ky = tap / 3, kx = tap % 3;
-        const int iy = y0 + ly + ky - 1, ix = lx + kx - 1;
+      for (int tap = 0; tap < 3 * TX; ++tap) {
+        const int ky = tap / TX, kx = tap % TX;
+        const int iy = y0 + ly + ky - 1, ix = (SP ? 2 * lx : lx) + kx - 1;
         const bool ok = iy >= 0 && iy < S && ix >= 0 && ix < S;
         const int pr = ly + ky;
 #pragma unroll
@@ -181,16 +192,16 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
           vals[tap * 3 + c] = h;
         }
       }
-      constexpr uint32_t kOne = F16 ? 0x3C00u : 0x3F80u;      // 1.0 in the operand type: the bias columns
-      vals[27] = (uint16_t)kOne;
-      uint32_t packed[16];
+      vals[NV] = (uint16_t)kOne; vals[NV + 1] = (uint16_t)kOne;   // bias hi / lo columns
 #pragma unroll
-      for (int j = 0; j < 14; ++j) packed[j] = (uint32_t)vals[2 * j] | ((uint32_t)vals[2 * j + 1] << 16);
-      packed[14] = kOne; packed[15] = 0u;
+      for (int j = NV + 2; j < NW * 2; ++j) vals[j] = 0;
+      uint32_t packed[NW];
+#pragma unroll
+      for (int j = 0; j < NW; ++j) packed[j] = (uint32_t)vals[2 * j] | ((uint32_t)vals[2 * j + 1] << 16);
       mbar_wait(smem_u32(&a_empty[buf]), ph ^ 1u);          // the MMAs that read this A buffer have retired
       uint8_t* row = smem_gen + buf * FC_A_BYTES + bt * 128;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
+      for (int ch = 0; ch < NW / 4; ++ch)
         *reinterpret_cast<uint4*>(row + ((ch ^ (bt & 7)) << 4)) =
             make_uint4(packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
       fence_proxy_async_smem();                             // generic-proxy writes -> visible to the tensor core
@@ -255,37 +266,47 @@ template <int BN>
 constexpr int fc_smem_bytes() { return 2 * FC_A_BYTES + BN * 128 + FC_OUT_BUFS * (BN / 64) * 128 * 128 + 1024; }
 
 int first_conv_init() {
-  SDG_CUDA(cudaFuncSetAttribute(first_conv_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<128>()));
-  SDG_CUDA(cudaFuncSetAttribute(first_conv_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<128>()));
-  SDG_CUDA(cudaFuncSetAttribute(first_conv_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<64>()));
-  SDG_CUDA(cudaFuncSetAttribute(first_conv_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<64>()));
+  SDG_CUDA(cudaFuncSetAttribute((first_conv_kernel<128, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<128>()));
+  SDG_CUDA(cudaFuncSetAttribute((first_conv_kernel<128, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<128>()));
+  SDG_CUDA(cudaFuncSetAttribute((first_conv_kernel<128, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<128>()));
+  SDG_CUDA(cudaFuncSetAttribute((first_conv_kernel<128, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<128>()));
+  SDG_CUDA(cudaFuncSetAttribute((first_conv_kernel<64, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<64>()));
+  SDG_CUDA(cudaFuncSetAttribute((first_conv_kernel<64, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes<64>()));
   return 0;
 }
 
 int first_conv(const void* x, int layout, const h16* wb, const float* bias, h16* out, int64_t n, int S, int Cout,
-               int f16, cudaStream_t s) {
+               int f16, cudaStream_t s, int superpix) {
   SDG_REQUIRE(S == 32 || S == 64, SDG_E_UNSUPPORTED, "first_conv: image size %d", S);
   SDG_REQUIRE(Cout == 64 || Cout == 128, SDG_E_UNSUPPORTED, "first_conv: Cout=%d", Cout);
+  SDG_REQUIRE(!superpix || Cout == 64, SDG_E_INVALID, "first_conv: the super-pixel form is for Cout = 64");
   SDG_REQUIRE(bias, SDG_E_INVALID, "first_conv: bias required");
   SDG_REQUIRE(((uintptr_t)x % 4) == 0 && ((uintptr_t)out % 16) == 0, SDG_E_INVALID, "first_conv: misaligned pointer");
   if (n == 0) return 0;
+  // super-pixel form: wb is [128][64] (pack_first_superpix_h16), the output [n*S*S/2 rows][128] is the same memory as
+  // [n*S*S rows][64]
+  const int bn = superpix ? 128 : Cout;
+  const uint64_t rows = (uint64_t)n * S * S / (superpix ? 2 : 1);
   CUtensorMap map_b, map_out;
-  { int rc = tc_encode_2d(&map_b, wb, f16, 64, Cout, 64, Cout); if (rc) return rc; }
-  { int rc = tc_encode_2d(&map_out, out, f16, Cout, (uint64_t)n * S * S, 64, 128); if (rc) return rc; }
+  { int rc = tc_encode_2d(&map_b, wb, f16, 64, bn, 64, bn); if (rc) return rc; }
+  { int rc = tc_encode_2d(&map_out, out, f16, bn, rows, 64, 128); if (rc) return rc; }
   FcParams p;
   p.x = x; p.layout = layout; p.S = S; p.Cout = Cout; p.n_images = n;
-  p.tiles = n * (S * S / 128);
+  p.tiles = (long long)(rows / 128);
   p.bias = bias; p.out = out;
   const int sms = tc_num_sms();
   const int grid = (int)(p.tiles < 2 * sms ? p.tiles : 2 * sms);     // two persistent CTAs per SM
-  if (Cout == 128 && f16) {
-    SDG_LAUNCH((first_conv_kernel<128, true>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, map_out, p);
+  if (superpix) {
+    if (f16) { SDG_LAUNCH((first_conv_kernel<128, true, true>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, map_out, p); }
+    else { SDG_LAUNCH((first_conv_kernel<128, false, true>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, map_out, p); }
+  } else if (Cout == 128 && f16) {
+    SDG_LAUNCH((first_conv_kernel<128, true, false>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, map_out, p);
   } else if (Cout == 128) {
-    SDG_LAUNCH((first_conv_kernel<128, false>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, map_out, p);
+    SDG_LAUNCH((first_conv_kernel<128, false, false>), grid, FC_THREADS, fc_smem_bytes<128>(), s, map_b, map_out, p);
   } else if (f16) {
-    SDG_LAUNCH((first_conv_kernel<64, true>), grid, FC_THREADS, fc_smem_bytes<64>(), s, map_b, map_out, p);
+    SDG_LAUNCH((first_conv_kernel<64, true, false>), grid, FC_THREADS, fc_smem_bytes<64>(), s, map_b, map_out, p);
   } else {
-    SDG_LAUNCH((first_conv_kernel<64, false>), grid, FC_THREADS, fc_smem_bytes<64>(), s, map_b, map_out, p);
+    SDG_LAUNCH((first_conv_kernel<64, false, false>), grid, FC_THREADS, fc_smem_bytes<64>(), s, map_b, map_out, p);
   }
   return 0;
 }

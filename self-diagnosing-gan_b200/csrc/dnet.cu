@@ -312,6 +312,12 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
         return 0;
       };
       l1.superpix = l2.superpix = 0;
+      if (use_superpix && c->blocks[bi].kind == 0 && l1.cout == 64 && l1.cin == 3) {
+        // block1.c1 from the image bytes: 3 x 3 taps -> 3 x 4 taps, x-stride 2, [128][64] weight tile
+        { int rc = l1.w16s.ensure(sizeof(h16) * 128 * 64); if (rc) return rc; }
+        { int rc = pack_first_superpix_h16(W[i1], sig + i1, l1.w16s.as<h16>(), 64, f16, s); if (rc) return rc; }
+        l1.superpix = 1;
+      }
       if (use_superpix && c->blocks[bi].kind == 0 && l2.cout == 64 && l2.cin == 64 && l2.pool4) {
         // block1.c2 in the 4x4 stride-2 form: 4 x 4 taps, x-stride 2 -> 4 x 6 taps, x-stride 4
         { int rc = l2.w16s.ensure(sizeof(h16) * 128 * 4 * 6 * l2.cin); if (rc) return rc; }
@@ -473,7 +479,11 @@ static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, 
     }
     if (bl.kind == 0) {
       // DBlockOptimized: c1 straight from the image bytes; shortcut c_sc(avg_pool2d(x)) as 3 FMAs in c2's epilogue
-      if ((rc = first_conv(x, layout, c1.w16.as<h16>(), c1.bias.as<float>(), T, nb, S, c1.cout, f16, s))) return rc;
+      if (c1.superpix) {
+        if ((rc = first_conv(x, layout, c1.w16s.as<h16>(), c1.bias.as<float>(), T, nb, S, c1.cout, f16, s, 1))) return rc;
+      } else {
+        if ((rc = first_conv(x, layout, c1.w16.as<h16>(), c1.bias.as<float>(), T, nb, S, c1.cout, f16, s))) return rc;
+      }
       a2.img = x; a2.img_layout = layout; a2.sc_w3 = c->convs[i1 + 2].w3.as<float>();
       // executed FLOPs of this launch: the 4x4 stride-2 form does 16 taps per pooled pixel instead of 9 per input pixel
       double macs_per_out = c2.pool4 ? 16.0 * c2.cin * 0.25 : 9.0 * c2.cin;

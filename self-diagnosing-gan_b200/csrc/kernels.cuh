@@ -162,7 +162,11 @@ bool conv_tc_swap_active();
 void conv_tc_set_pair(int on);   // 1 (default): Cout = 128 3x3 layers run on the CTA-pair (cta_group::2) kernel
 // out = relu(conv3x3(normalise(x)) + bias): x uint8 NHWC or fp32 NCHW [n,3,S,S]; wb [Cout][64] (k = tap*3+c, 27 real)
 int first_conv_init();
+// superpix = 1 (Cout = 64): wb is the [128][64] super-pixel weight tile of pack_first_superpix_h16
 int first_conv(const void* x, int layout, const h16* wb, const float* bias, h16* out, int64_t n, int S, int Cout,
-               int f16, cudaStream_t s);
+               int f16, cudaStream_t s, int superpix = 0);
+// first-conv weights in super-pixel form: wb[(par*Cout + o)*64 + (ky*4 + j)*3 + c] = W[o][c][ky][j - par] / sigma for
+// 0 <= j - par <= 2, zero elsewhere (columns 36, 37 receive the bias in the kernel)
+int pack_first_superpix_h16(const float* W, const float* sigma, h16* wb, int Cout, int f16, cudaStream_t s);
 
 }  // namespace sdg

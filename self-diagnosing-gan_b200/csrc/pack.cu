@@ -247,6 +247,31 @@ int permute_fc(const float* w, float* out, int C, int HW, cudaStream_t s) {
   return 0;
 }
 
+template <bool F16>
+__global__ void __launch_bounds__(256)
+pack_first_superpix_kernel(const float* __restrict__ W, const float* __restrict__ sigma, h16* __restrict__ wb, int Cout) {
+  const float sg = sigma ? sigma[0] : 1.f;
+  const int total = 2 * Cout * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int row = i >> 6, k = i & 63;
+    const int par = row / Cout, o = row - par * Cout;
+    float w = 0.f;
+    if (k < 36) {
+      const int tap = k / 3, c = k - tap * 3;
+      const int ky = tap >> 2, j = tap & 3;
+      const int kx = j - par;
+      if (kx >= 0 && kx <= 2) w = W[((o * 3 + c) * 3 + ky) * 3 + kx] / sg;
+    }
+    wb[i] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
+  }
+}
+
+int pack_first_superpix_h16(const float* W, const float* sigma, h16* wb, int Cout, int f16, cudaStream_t s) {
+  if (f16) { SDG_LAUNCH(pack_first_superpix_kernel<true>, stream_grid(2 * Cout * 64, 256), 256, 0, s, W, sigma, wb, Cout); }
+  else { SDG_LAUNCH(pack_first_superpix_kernel<false>, stream_grid(2 * Cout * 64, 256), 256, 0, s, W, sigma, wb, Cout); }
+  return 0;
+}
+
 __global__ void __launch_bounds__(256)
 pack_superpix_kernel(const h16* __restrict__ src, h16* __restrict__ dst, int Cout, int Cin, int ty, int txs, int shift) {
   const int txd = txs + shift;
