@@ -226,13 +226,16 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
     int cout = i < n_convs ? ls[i].cout : 1;
     int K = i < n_convs ? ls[i].cin * ls[i].ks * ls[i].ks : ndf;
     tab[i].W = W[i]; tab[i].u = u[i]; tab[i].cout = cout; tab[i].K = K;
-    scratch_floats += (size_t)K + cout;
+    scratch_floats += (size_t)K * (1 + sn_slices()) + cout;
   }
   { int rc = c->sn_scratch.ensure(scratch_floats * sizeof(float)); if (rc) return rc; }
   { int rc = c->sn_table.ensure(sizeof(SnLayer) * n_layers); if (rc) return rc; }
   { int rc = c->sigma.ensure(sizeof(float) * n_layers); if (rc) return rc; }
   float* sp = c->sn_scratch.as<float>();
-  for (int i = 0; i < n_layers; ++i) { tab[i].v = sp; sp += tab[i].K; tab[i].t = sp; sp += tab[i].cout; }
+  for (int i = 0; i < n_layers; ++i) {
+    tab[i].v = sp; sp += tab[i].K; tab[i].t = sp; sp += tab[i].cout;
+    tab[i].vp = sp; sp += (size_t)tab[i].K * sn_slices();
+  }
   SDG_CUDA(cudaMemcpyAsync(c->sn_table.p, tab.data(), sizeof(SnLayer) * n_layers, cudaMemcpyHostToDevice, s));
   { int rc = sn_sigmas(c->sn_table.as<SnLayer>(), tab.data(), n_layers, c->sigma.as<float>(), s); if (rc) return rc; }
 

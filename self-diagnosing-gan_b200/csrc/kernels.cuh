@@ -84,7 +84,9 @@ struct SnLayer {
   int cout, K;
   float* v;           // scratch [K]
   float* t;           // scratch [cout]
+  float* vp;          // scratch [sn_slices()][K]: row-slice partials of u.W
 };
+int sn_slices();
 int sn_sigmas(const SnLayer* layers_dev, const SnLayer* layers_host, int n_layers, float* sigma_dev,
               cudaStream_t s);
 // wp[(tap*Cin + c)*Cout + o] = W[o][c][tap] * scale[o] / sigma   (scale may be null; sigma may be null)

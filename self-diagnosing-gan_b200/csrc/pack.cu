@@ -11,13 +11,18 @@ namespace sdg {
 
 constexpr float kSnEps = 1e-12f;
 
-// v_raw[k] = sum_o u[o] * W[o][k]     (thread per column k: coalesced across k)
+constexpr int kSnSlices = 8;   // row slices of u.W (partials summed in a fixed order: sigma stays deterministic)
+
+// vp[z][k] = sum over the rows o of slice z of u[o] * W[o][k]     (thread per column k: coalesced across k)
 __global__ void __launch_bounds__(256) sn_uW_kernel(const SnLayer* __restrict__ layers) {
   const SnLayer L = layers[blockIdx.y];
+  const int z = blockIdx.z;
+  const int per = (L.cout + kSnSlices - 1) / kSnSlices;
+  const int o0 = z * per, o1 = min(L.cout, o0 + per);
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L.K; k += gridDim.x * blockDim.x) {
     float acc = 0.f;
-    for (int o = 0; o < L.cout; ++o) acc = fmaf(L.u[o], L.W[(int64_t)o * L.K + k], acc);
-    L.v[k] = acc;
+    for (int o = o0; o < o1; ++o) acc = fmaf(L.u[o], L.W[(int64_t)o * L.K + k], acc);
+    L.vp[(int64_t)z * L.K + k] = acc;
   }
 }
 
@@ -36,7 +41,12 @@ __global__ void __launch_bounds__(256) sn_normalize_v_kernel(const SnLayer* __re
   __shared__ float red[8];
   const SnLayer L = layers[blockIdx.x];
   float s = 0.f;
-  for (int k = threadIdx.x; k < L.K; k += blockDim.x) s = fmaf(L.v[k], L.v[k], s);
+  for (int k = threadIdx.x; k < L.K; k += blockDim.x) {
+    float a = 0.f;
+    for (int z = 0; z < kSnSlices; ++z) a += L.vp[(int64_t)z * L.K + k];      // fixed order
+    L.v[k] = a;
+    s = fmaf(a, a, s);
+  }
   float nrm = sqrtf(block_sum(s, red));
   float d = fmaxf(nrm, kSnEps);
   for (int k = threadIdx.x; k < L.K; k += blockDim.x) L.v[k] = L.v[k] / d;
@@ -77,7 +87,7 @@ int sn_sigmas(const SnLayer* layers_dev, const SnLayer* layers_host, int n_layer
     maxK = layers_host[i].K > maxK ? layers_host[i].K : maxK;
     maxC = layers_host[i].cout > maxC ? layers_host[i].cout : maxC;
   }
-  SDG_LAUNCH(sn_uW_kernel, dim3((unsigned)cdiv(maxK, 256), n_layers), 256, 0, s, layers_dev);
+  SDG_LAUNCH(sn_uW_kernel, dim3((unsigned)cdiv(maxK, 256), n_layers, kSnSlices), 256, 0, s, layers_dev);
   SDG_LAUNCH(sn_normalize_v_kernel, n_layers, 256, 0, s, layers_dev);
   SDG_LAUNCH(sn_Wv_kernel, dim3((unsigned)cdiv(maxC, 8), n_layers), 256, 0, s, layers_dev);
   SDG_LAUNCH(sn_sigma_kernel, n_layers, 256, 0, s, layers_dev, sigma_dev);
@@ -293,5 +303,7 @@ int pack_superpix_h16(const h16* src, h16* dst, int Cout, int Cin, int ty, int t
   SDG_LAUNCH(pack_superpix_kernel, stream_grid(total, 256), 256, 0, s, src, dst, Cout, Cin, ty, txs, shift);
   return 0;
 }
+
+int sn_slices() { return kSnSlices; }
 
 }  // namespace sdg
