@@ -3,8 +3,8 @@
 The reference builds every dataset item with ``transforms.Resize(img_size)``, ``CenterCrop(img_size)``, ``ToTensor``,
 ``Normalize(0.5, 0.5)`` (diagan-pkg/diagan/datasets/transform.py:3-41) applied to a PIL image
 (e.g. color_mnist.py:90-100).  The arithmetic lives in two third-party dependencies that are NOT vendored in
-/root/reference: torchvision (requirements: ``torchvision==0.8.1``; geometry of Resize(int) / CenterCrop) and Pillow
-(``Pillow==8.0.1``; ``Image.resize(..., BILINEAR)`` = libImaging/Resample.c, 8-bit fixed-point path).  Restated here from
+/root/reference: torchvision (``environment.yml:44``: ``torchvision=0.8.2``; geometry of Resize(int) / CenterCrop) and Pillow
+(``environment.yml:34``: ``pillow=8.1.0``; ``Image.resize(..., BILINEAR)`` = libImaging/Resample.c, 8-bit fixed-point path).  Restated here from
 their published algorithms:
 
 * Resize(int s) on a (w, h) image: the shorter side becomes s, the longer ``int(s * long / short)``
@@ -16,8 +16,11 @@ their published algorithms:
   22-bit fixed point k = int(0.5 + w * 2**22) (``normalize_coeffs_8bpc``); a pixel is
   clip8((2**21 + sum_x in[x + xmin] * k[x]) >> 22).  Same-size resizes are a copy.
 
-PINNED: ``tests/test_oracle_golden.py`` checks this restatement bit-for-bit against Pillow itself (installed in this image)
-on every shape used by the reference's datasets plus odd shapes, and against ``tests/golden/resize_*.npz``.
+PINNED: ``tests/test_oracle_golden.py`` checks this restatement bit-for-bit against Pillow itself (12.2, the version installed in
+this image) on every shape used by the reference's datasets plus odd shapes, and against ``tests/golden/resize_*.npz`` (outputs
+of the reference's own ``get_transform`` run here).  The reference pins pillow 8.1.0, which cannot be installed here; its 8-bit
+``ImagingResample`` path (PRECISION_BITS = 22, round-half-up, horizontal pass first) is the same algorithm as restated above
+[UNVERIFIED against an 8.1.0 install].
 """
 from __future__ import annotations
 
