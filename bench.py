@@ -52,8 +52,9 @@ WORKLOADS = {
                     metric="per-sample D logits + LDR scores per second (SNGAN-64, CelebA shape, 202 599 / 8 samples per GPU)",
                     desc="configs[2]: SNGAN-64 recording pass + Welford stats + ldr_conf_5.0_ratio_50 weights + top-100, "
                          "25 325 x 3x64x64 uint8 per GPU (the 8-way shard of 202 599)",
-                    kernel="conv_tc_kernel<64> block1.c2 (3x3 64->64 @64x64 + avg-pool + shortcut; 23.4% of the reference FLOPs) as "
-                           "the 4x4 stride-2 conv",
+                    kernel="conv_swap_kernel block1.c2 (3x3 64->64 @64x64 + avg-pool + shortcut; 23.4% of the reference FLOPs) as the "
+                           "4x4 stride-2 conv in super-pixel form (two output pixels = one 128-channel GEMM pixel, 4x6 taps; the "
+                           "executed FLOPs include its structural zeros)",
                     dom_ref_flop=2.0 * 9 * 64 * 64 * 4096, cpu_sample=4096, ref_sample=512),
     "stylegan2": dict(arch="stylegan2", size=256, n=2048, key="ldr_conf_3.0_ratio_50", flop=None,
                       metric="per-sample D logits + LDR scores per second (StyleGAN2-256 discriminator, FFHQ shape, bounded 2048 "
