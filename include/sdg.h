@@ -44,7 +44,15 @@ extern "C" {
 #define SDG_PREC_FP32      0      /* CUDA-core fp32 (IEEE, no TF32): the 1e-5 parity mode */
 #define SDG_PREC_BF16      1      /* tcgen05 kind::f16, bf16 operands, fp32 TMEM accumulators */
 #define SDG_PREC_FP16      2      /* tcgen05 kind::f16, fp16 operands, fp32 TMEM accumulators: same speed as bf16,
-                                     8x smaller rounding error -- the throughput mode that meets the 1e-3 parity bar */
+                                     8x smaller rounding error -- the throughput mode.  Measured against the float64
+                                     oracle: <= 1e-3 of the logit SCALE on every tested network; relative
+                                     to an individual near-zero logit it exceeds 1e-3 (1.26e-2 on a random-init SNGAN-32
+                                     whose logits cancel to ~-0.2, where cuDNN TF32 -- the reference's own GPU arithmetic --
+                                     measures 1.42e-2).  fp16 has a finite RANGE (65504): see sdg_ctx_set_range_flag */
+
+/* fp16 range guard: bits OR-ed into the caller's flag by any kernel that rounds to an fp16 operand */
+#define SDG_RANGE_ACT      1      /* an activation left the fp16 range (|v| > 65504, or inf/NaN) when stored as an operand */
+#define SDG_RANGE_WEIGHT   2      /* a packed weight did */
 
 /* input layouts of sdg_d_forward */
 #define SDG_LAYOUT_U8_NHWC   0    /* uint8 [n,H,W,3]; normalised (x/255-.5)/.5 on load (transform.py:3-11) */
@@ -64,6 +72,13 @@ SDG_API int sdg_abi_version(void);
 /* per-device context: packed weights, TMA descriptors, activation scratch */
 SDG_API int sdg_ctx_create(int device, sdg_ctx** out);
 SDG_API int sdg_ctx_destroy(sdg_ctx* ctx);
+/* fp16 range guard (no reference counterpart: the reference computes in fp32/TF32, whose range cannot be exceeded).
+ * `device_flag` is a caller-owned, caller-zeroed DEVICE int32 (or NULL to detach).  With SDG_PREC_FP16 every kernel behind
+ * sdg_*_load / sdg_d_forward that rounds a value to an fp16 operand ORs SDG_RANGE_* into it when the value is outside the
+ * fp16 range, so that one overflowing pixel can never silently poison a logit and the running statistics after it: the
+ * caller reads the flag after the pass and re-runs it with SDG_PREC_BF16 (fp32 range) -- diagan_b200 does so automatically
+ * (LogitRecorder, range_check).  The flag is sticky; the library never clears it.  bf16 / fp32 modes never set it. */
+SDG_API int sdg_ctx_set_range_flag(sdg_ctx* ctx, int32_t* device_flag);
 /* upper bound on samples processed per internal sweep (bounds scratch memory); 0 = default */
 SDG_API int sdg_ctx_set_chunk(sdg_ctx* ctx, int64_t samples_per_chunk);
 

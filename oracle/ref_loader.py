@@ -153,3 +153,69 @@ def reference_stylegan2_discriminator():
     finally:
         ext.load = real
     return StyleGANDiscriminator
+
+
+class _PermissiveModule(types.ModuleType):
+    """Stand-in for a package that is absent here: any attribute is a fresh empty class (usable as a base class, never
+    called on the diagnosis path), any submodule imports.  Explicit stubs set earlier win."""
+    __path__ = []
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        full = f"{self.__name__}.{name}"
+        if full in sys.modules:
+            return sys.modules[full]
+        obj = type(name, (), {})
+        setattr(self, name, obj)
+        return obj
+
+
+class _PermissiveFinder:
+    def __init__(self, roots):
+        self.roots = tuple(roots)
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery
+        if fullname.split(".")[0] in self.roots:
+            return importlib.machinery.ModuleSpec(fullname, self)
+        return None
+
+    def create_module(self, spec):
+        return _PermissiveModule(spec.name)
+
+    def exec_module(self, module):
+        pass
+
+
+def stub_training_stack():
+    """Make ``diagan.trainer.trainer`` / ``diagan.trainer.evaluate`` importable here: torch_mimicry (incl. ``.training``,
+    ``.metrics``, ``.utils``) and tensorflow are absent, neither is touched by the diagnosis path itself.  Only for the
+    drop-in tests (tests/test_dropin_cpu.py): proves ``diagan_b200.patch.install()`` binds onto the REAL classes."""
+    _ensure_path()
+    _stub_matplotlib()
+    _stub_mimicry()
+    import numpy as np
+    if "numpy.lib.type_check" not in sys.modules:          # removed in NumPy 2 (compute_fid_with_attr.py:9 imports `imag`)
+        try:
+            import numpy.lib.type_check  # noqa: F401
+        except Exception:
+            _stub("numpy.lib.type_check", imag=np.imag, real=np.real)
+    missing = []
+    for root in ("tensorflow", "torch_mimicry", "lmdb", "imageio", "cv2", "tensorboard", "tensorboardX", "seaborn"):
+        mod = sys.modules.get(root)
+        if mod is None or not getattr(mod, "__file__", None):
+            missing.append(root)
+    if missing and not any(isinstance(f, _PermissiveFinder) for f in sys.meta_path):
+        sys.meta_path.append(_PermissiveFinder(missing))
+    if "torch_mimicry" in missing:
+        # packages stubbed as plain modules by _stub_mimicry need a __path__ so that their submodules import
+        for name, mod in list(sys.modules.items()):
+            if name.split(".")[0] == "torch_mimicry" and not hasattr(mod, "__path__"):
+                mod.__path__ = []
+        import importlib
+        tr = importlib.import_module("torch_mimicry.training")
+        tr.Trainer = type("Trainer", (), {})
+        for sub in ("logger", "metric_log"):
+            setattr(tr, sub, importlib.import_module(f"torch_mimicry.training.{sub}"))
+        sys.modules["torch_mimicry"].training = tr

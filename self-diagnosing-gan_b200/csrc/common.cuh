@@ -46,6 +46,15 @@ inline int check(cudaError_t e, const char* what) {
     SDG_CUDA(cudaGetLastError());                                             \
   } while (0)
 
+// fp16 range guard (include/sdg.h, sdg_ctx_set_range_flag): the caller-owned device flag of the ctx an entry point is
+// working for, visible to the kernel launchers of this thread for the duration of the call
+extern thread_local int* t_range_flag;
+struct RangeScope {
+  explicit RangeScope(int* flag) { t_range_flag = flag; }
+  ~RangeScope() { t_range_flag = nullptr; }
+};
+constexpr float kF16Max = 65504.0f;
+
 constexpr int kNumSMs = 148;   // B200
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -27,6 +27,7 @@ struct FcParams {
   long long n_images, tiles;
   const float* bias;
   h16* out;
+  int* ovf;                  // fp16 range guard flag or null
 };
 
 // SP = super-pixel form for Cout = 64 (BN = 128): a GEMM row is two horizontally adjacent pixels, its 128 columns are
@@ -212,6 +213,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
     const int q = warp;
     const int row = q * 32 + lane;
     long long local = 0;
+    uint32_t nonfinite = 0;           // fp16 range guard: OR of the inf / NaN marks of every packed output word
     for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++local) {
       const int buf = (int)(local & 1);
       const uint32_t ph = (uint32_t)((local >> 1) & 1);
@@ -235,6 +237,8 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
           pk.y = pack_relu_h2<F16>(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
           pk.z = pack_relu_h2<F16>(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
           pk.w = pack_relu_h2<F16>(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
+          if (F16) nonfinite |= f16x2_nonfinite_bits(pk.x) | f16x2_nonfinite_bits(pk.y) | f16x2_nonfinite_bits(pk.z) |
+                                f16x2_nonfinite_bits(pk.w);
           const int chunk = ((c0 & 63) >> 3) + g;                 // 16-byte chunk within the 128-byte row
           *reinterpret_cast<uint4*>(srow + ((chunk ^ (row & 7)) << 4)) = pk;
         }
@@ -252,6 +256,7 @@ first_conv_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_consta
       }
     }
     if (threadIdx.x == 0) bulk_wait_all();
+    if (F16 && nonfinite) range_flag_set(p.ovf, SDG_RANGE_ACT);
   }
 
   tc_fence_before();
@@ -293,7 +298,7 @@ int first_conv(const void* x, int layout, const h16* wb, const float* bias, h16*
   FcParams p;
   p.x = x; p.layout = layout; p.S = S; p.Cout = Cout; p.n_images = n;
   p.tiles = (long long)(rows / 128);
-  p.bias = bias; p.out = out;
+  p.bias = bias; p.out = out; p.ovf = t_range_flag;
   const int sms = tc_num_sms();
   const int grid = (int)(p.tiles < 2 * sms ? p.tiles : 2 * sms);     // two persistent CTAs per SM
   if (superpix) {

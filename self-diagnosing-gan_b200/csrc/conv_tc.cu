@@ -87,6 +87,7 @@ struct TcParams {
   h16* out_relu;             // relu(v) 16-bit or null
   h16* out_raw;              // v 16-bit or null
   float* out_f32;            // v fp32 or null
+  int* ovf;                  // fp16 range guard flag (sdg_ctx_set_range_flag) or null
 };
 
 __device__ __forceinline__ float norm_px(const void* img, int layout, long long n, int y, int x, int c, int H, int W) {
@@ -210,7 +211,7 @@ __device__ __forceinline__ void store_rows16_coalesced(h16* base, long long wpix
 template <int BN, bool F16>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float* s_bias, const float* s_w3,
                                                  uint32_t tmem_acc, long long mt, int nt, int q, int lane,
-                                                 uint32_t acc_full_bar, uint32_t acc_phase) {
+                                                 uint32_t acc_full_bar, uint32_t acc_phase, float& vmax) {
   if (p.debug_skip_epi) {
     mbar_wait(acc_full_bar, acc_phase);
     tc_fence_after();
@@ -342,6 +343,11 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const float*
       if (p.out_scale != 1.0f) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+      }
+      if (F16 && active && (p.out_raw || p.out_relu)) {
+        // fp16 range guard: the largest value about to be rounded to a 16-bit operand (negative ones vanish under ReLU)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, p.out_raw ? fabsf(v[j]) : v[j]);
       }
       if (p.head_out && active) {          // s_w3 holds the head weights in this mode
 #pragma unroll
@@ -549,17 +555,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ================= epilogue =================
     const int q = warp - 4;                       // TMEM lane quadrant this warp may access
     long long local = 0;
+    float vmax = 0.f;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int nt = (int)(tile % p.n_tiles);
       const long long mt = tile / p.n_tiles;
       const int acc = (int)(local & 1);
       const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
       tc_epilogue_tile<BN, F16>(p, s_bias, s_w3, tmem_base + (uint32_t)acc * acc_stride, mt, nt, q, lane,
-                                smem_u32(&bar_acc_full[acc]), acc_phase);
+                                smem_u32(&bar_acc_full[acc]), acc_phase, vmax);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
     }
+    if (F16 && vmax > kF16Max) range_flag_set(p.ovf, SDG_RANGE_ACT);
   }
 
   tc_fence_before();
@@ -710,16 +718,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ================= epilogue: this CTA's 128 TMEM lanes =================
     const int q = warp - 4;
     long long local = 0;
+    float vmax = 0.f;
     for (long long ct = cluster_id; ct < pair_tiles; ct += n_clusters, ++local) {
       const long long mt = 2 * ct + rank;
       const int acc = (int)(local & 1);
       const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
       tc_epilogue_tile<128, F16>(p, s_bias, s_w3, tmem_base + (uint32_t)(acc * 128), mt, 0, q, lane,
-                                 smem_u32(&bar_acc_full[acc]), acc_phase);
+                                 smem_u32(&bar_acc_full[acc]), acc_phase, vmax);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_acc_empty[acc]), 0));
     }
+    if (F16 && vmax > kF16Max) range_flag_set(p.ovf, SDG_RANGE_ACT);
   }
 
   tc_fence_before();
@@ -865,17 +875,19 @@ conv_pair_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     // ================= epilogue: this CTA's 128 TMEM lanes x BN columns =================
     const int q = warp - 4;
     long long local = 0;
+    float vmax = 0.f;
     for (long long t = cluster_id; t < total; t += n_clusters, ++local) {
       const int nt = (int)(t % p.n_tiles);
       const long long mt = 2 * (t / p.n_tiles) + rank;
       const int acc = (int)(local % n_acc);
       const uint32_t acc_phase = (uint32_t)((local / n_acc) & 1);
       tc_epilogue_tile<BN, F16>(p, s_bias, s_w3, tmem_base + (uint32_t)acc * acc_stride, mt, nt, q, lane,
-                                smem_u32(&bar_acc_full[acc]), acc_phase);
+                                smem_u32(&bar_acc_full[acc]), acc_phase, vmax);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_acc_empty[acc]), 0));
     }
+    if (F16 && vmax > kF16Max) range_flag_set(p.ovf, SDG_RANGE_ACT);
   }
 
   tc_fence_before();
@@ -1023,6 +1035,7 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int spx_n = p.superpix ? 2 : 1, spx_par = p.superpix ? (c >> 6) : 0;    // warp-uniform: a warp owns 32 channels
     const int HW = p.H * p.W;
     long long local = 0;
+    float vmax = 0.f;                                     // fp16 range guard: largest value rounded to a 16-bit operand
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
       const int acc = (int)(local & 1);
       const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
@@ -1114,6 +1127,10 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
           }
+          if (F16 && st_ok && (p.out_raw || p.out_relu)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, p.out_raw ? fabsf(v[j]) : v[j]);
+          }
           if (p.out_f32 && st_ok) {
             float* op = p.out_f32 + pb * CO + c;
 #pragma unroll
@@ -1158,6 +1175,7 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         named_bar_sync(2, SW_EPI_WARPS * 32);
       }
     }
+    if (F16 && vmax > kF16Max) range_flag_set(p.ovf, SDG_RANGE_ACT);
   }
 
   tc_fence_before();
@@ -1224,8 +1242,12 @@ static int encode_act(CUtensorMap* map, const void* ptr, int f16, int64_t n, int
   return 0;
 }
 
+// Function attributes (opt-in shared memory) are per DEVICE, the driver entry point is per process: one bit per device id
+// records which devices have been initialised, so that a single process may drive several GPUs.
+static std::atomic<unsigned long long> g_dev_init{0};
+
 int conv_tc_init(int device) {
-  if (g_encode) return 0;
+  if (device >= 0 && device < 64 && ((g_dev_init.load(std::memory_order_acquire) >> device) & 1ULL)) return 0;
   cudaDeviceProp prop;
   SDG_CUDA(cudaGetDeviceProperties(&prop, device));
   SDG_REQUIRE(prop.major == 10, SDG_E_DEVICE, "conv_tc: device %d is sm_%d%d, need sm_100 (B200)", device, prop.major,
@@ -1249,7 +1271,8 @@ int conv_tc_init(int device) {
   SDG_CUDA(cudaFuncSetAttribute((conv_pair_stream_kernel<128, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
   g_encode = (EncodeTiledFn)fn;
   int rc = first_conv_init();
-  if (rc) { g_encode = nullptr; return rc; }
+  if (rc) return rc;
+  if (device >= 0 && device < 64) g_dev_init.fetch_or(1ULL << device, std::memory_order_release);
   return 0;
 }
 
@@ -1354,6 +1377,7 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   p.bias = a.bias; p.sd = a.sd; p.sd_w = a.sd_w; p.res_f32 = a.res_f32;
   p.head_w = a.head_w; p.head_b = a.head_b; p.head_out = a.head_out; p.img = a.img; p.sc_w3 = a.sc_w3;
   p.out_relu = a.out_relu; p.out_raw = a.out_raw; p.out_f32 = a.out_f32;
+  p.ovf = t_range_flag;
   const int es = a.general ? a.sy : (strided ? 2 : 1);      // TMA traversal stride over input pixels (rows; columns: esx)
   const int esx = a.general ? a.sx : es;
 

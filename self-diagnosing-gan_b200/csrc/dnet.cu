@@ -17,6 +17,7 @@
 namespace sdg {
 
 static thread_local std::string t_error;
+thread_local int* t_range_flag = nullptr;
 std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
@@ -57,6 +58,10 @@ struct ConvLayer {
   int superpix = 0;
   DevBuf w16s, bias2, w3s;
   bool has_bias = false;
+  void release_all() {
+    w32.release(); w16.release(); bias.release(); w3.release(); bias_sum.release();
+    w16s.release(); bias2.release(); w3s.release();
+  }
 };
 
 struct BlockSpec { int kind, cin, cout, down; };   // kind 0 = DBlockOptimized, 1 = DBlock
@@ -87,6 +92,7 @@ struct sdg_ctx {
   std::vector<std::pair<int, int>> sg2_blocks;
   int sg2_batch = 4;
   DevBuf sg2_sd;
+  int* range_flag = nullptr;             // caller-owned device int32 (sdg_ctx_set_range_flag) or null
   // optional timing of the dominant kernel (block1.c2) with events on the launching stream
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -158,13 +164,19 @@ extern "C" int sdg_ctx_create(int device, sdg_ctx** out) {
 extern "C" int sdg_ctx_destroy(sdg_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); l.w3.release(); l.bias_sum.release();
-                            l.w16s.release(); l.bias2.release(); l.w3s.release(); }
+  for (auto& l : c->convs) l.release_all();
   c->head_w.release(); c->head_b.release(); c->sigma.release();
   c->sn_table.release(); c->sn_scratch.release(); c->bn_scratch.release();
   for (auto& b : c->buf) b.release();
   c->xin.release(); c->xpool.release(); c->sg2_sd.release();
   delete c;
+  return 0;
+}
+
+extern "C" int sdg_ctx_set_range_flag(sdg_ctx* c, int32_t* device_flag) {
+  SDG_REQUIRE(c, SDG_E_INVALID, "sdg_ctx_set_range_flag: null ctx");
+  SDG_REQUIRE(((uintptr_t)device_flag % 4) == 0, SDG_E_INVALID, "sdg_ctx_set_range_flag: misaligned flag");
+  c->range_flag = device_flag;
   return 0;
 }
 
@@ -193,6 +205,7 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
               "sdg_sngan_load: precision=%d", precision);
   cudaStream_t s = (cudaStream_t)stream;
   SDG_CUDA(cudaSetDevice(c->device));
+  RangeScope range_scope(c->range_flag);
   int ndf = 0;
   sngan_spec(arch, c->blocks, c->size, ndf);
 
@@ -241,7 +254,7 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
 
   // ---- pack W / sigma ----
   if ((int)c->convs.size() != n_convs) {
-    for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); }
+    for (auto& l : c->convs) l.release_all();
     c->convs.assign(n_convs, ConvLayer());
   }
   const float* sig = c->sigma.as<float>();
@@ -366,10 +379,11 @@ extern "C" int sdg_dcgan_load(sdg_ctx* c, const float* const* conv_w, const floa
               "sdg_dcgan_load: only SDG_PREC_FP32 is implemented for the DCGAN discriminator");
   cudaStream_t s = (cudaStream_t)stream;
   SDG_CUDA(cudaSetDevice(c->device));
+  RangeScope range_scope(c->range_flag);
   c->loaded = false;
   c->arch = SDG_ARCH_DCGAN32; c->precision = precision; c->size = 32; c->blocks.clear();
   if (c->convs.size() != 6) {
-    for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); }
+    for (auto& l : c->convs) l.release_all();
     c->convs.assign(6, ConvLayer());
   }
   { int rc = c->bn_scratch.ensure(sizeof(float) * 512); if (rc) return rc; }
@@ -548,13 +562,15 @@ static int forward_dcgan_fp32(sdg_ctx* c, const void* x, int layout, int64_t nb,
 }
 
 extern "C" int sdg_d_forward(sdg_ctx* c, const void* x, int layout, int64_t n, float* logits_out, void* stream) {
-  SDG_REQUIRE(c && x && logits_out, SDG_E_INVALID, "sdg_d_forward: null pointer");
+  SDG_REQUIRE(c, SDG_E_INVALID, "sdg_d_forward: null context");
   SDG_REQUIRE(c->loaded, SDG_E_STATE, "sdg_d_forward: no discriminator weights loaded");
   SDG_REQUIRE(layout == SDG_LAYOUT_U8_NHWC || layout == SDG_LAYOUT_F32_NCHW, SDG_E_INVALID, "sdg_d_forward: layout=%d", layout);
   SDG_REQUIRE(n >= 0, SDG_E_INVALID, "sdg_d_forward: n=%lld", (long long)n);
-  if (n == 0) return 0;
+  if (n == 0) return 0;          // an empty shard (world > N, StyleGAN2 drop_last tail): torch hands out null pointers for it
+  SDG_REQUIRE(x && logits_out, SDG_E_INVALID, "sdg_d_forward: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   SDG_CUDA(cudaSetDevice(c->device));
+  RangeScope range_scope(c->range_flag);
   const int S = c->size;
   const bool bf = c->precision != SDG_PREC_FP32;
   if (c->arch == SDG_ARCH_STYLEGAN2) {
@@ -724,6 +740,7 @@ extern "C" int sdg_stylegan2_load(sdg_ctx* c, int size, int n_tensors, const flo
   SDG_REQUIRE(size >= 8 && size <= 1024 && (size & (size - 1)) == 0, SDG_E_INVALID, "sdg_stylegan2_load: size=%d", size);
   cudaStream_t s = (cudaStream_t)stream;
   SDG_CUDA(cudaSetDevice(c->device));
+  RangeScope range_scope(c->range_flag);
   c->loaded = false;
   c->sg2_blocks.clear();
   int cin = sg2_channels(size);
@@ -739,7 +756,7 @@ extern "C" int sdg_stylegan2_load(sdg_ctx* c, int size, int n_tensors, const flo
   c->arch = SDG_ARCH_STYLEGAN2; c->precision = precision; c->size = size; c->blocks.clear();
   const int n_convs = 1 + 3 * nblk + 2;                  // first, (conv1, conv2, skip) per block, final conv, linear 0
   if ((int)c->convs.size() != n_convs) {
-    for (auto& l : c->convs) { l.w32.release(); l.w16.release(); l.bias.release(); l.w3.release(); l.bias_sum.release(); }
+    for (auto& l : c->convs) l.release_all();
     c->convs.assign(n_convs, ConvLayer());
   }
   const bool tc = precision != SDG_PREC_FP32;

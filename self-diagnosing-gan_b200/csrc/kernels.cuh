@@ -31,6 +31,14 @@ __device__ __forceinline__ uint32_t pack_relu_h2(float x, float y) {
   return r;
 }
 
+// fp16 range guard: bit 0 = an ACTIVATION left the fp16 range when it was stored as a 16-bit operand, bit 1 = a packed WEIGHT
+// did.  The flag is sticky device memory owned by the caller (sdg_ctx_set_range_flag); setting it is the rare path.
+__device__ __forceinline__ void range_flag_set(int* flag, int bit) {
+  if (flag) atomicOr(flag, bit);
+}
+// true if either half of a packed fp16x2 word is inf / NaN (exponent all ones): the carry of +1 at the exponent's LSB
+__device__ __forceinline__ uint32_t f16x2_nonfinite_bits(uint32_t pk) { return ((pk & 0x7C007C00u) + 0x04000400u) & 0x80008000u; }
+
 template <bool F16>
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) {
   if (F16) return __half22float2(*reinterpret_cast<__half2*>(&v));

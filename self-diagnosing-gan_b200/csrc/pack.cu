@@ -122,7 +122,8 @@ int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float
 template <bool F16>
 __global__ void __launch_bounds__(256)
 pack_conv_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigma, const float* __restrict__ scale,
-                     h16* __restrict__ wb, int Cout, int Cin, int Kpad, int taps, int ld, int col0, float mul, int cin_w) {
+                     h16* __restrict__ wb, int Cout, int Cin, int Kpad, int taps, int ld, int col0, float mul, int cin_w,
+                     int* ovf) {
   const int total = Cout * Kpad;
   const float sg = sigma ? sigma[0] : 1.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -136,6 +137,7 @@ pack_conv_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigm
       if (scale) w = w * scale[o];
       if (mul != 1.0f) w = w * mul;
     }
+    if (F16 && !(fabsf(w) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_WEIGHT);
     wb[(int64_t)o * ld + col0 + k] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
   }
 }
@@ -146,10 +148,10 @@ int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* w
   if (cin_w <= 0) cin_w = Cin;
   if (f16) {
     SDG_LAUNCH(pack_conv_h16_kernel<true>, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wb, Cout, Cin, Kpad,
-               ks * ks, ld, col0, mul, cin_w);
+               ks * ks, ld, col0, mul, cin_w, t_range_flag);
   } else {
     SDG_LAUNCH(pack_conv_h16_kernel<false>, stream_grid(total, 256), 256, 0, s, W, sigma, scale, wb, Cout, Cin, Kpad,
-               ks * ks, ld, col0, mul, cin_w);
+               ks * ks, ld, col0, mul, cin_w, t_range_flag);
   }
   return 0;
 }
@@ -157,7 +159,7 @@ int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* w
 template <bool F16>
 __global__ void __launch_bounds__(256)
 pack_pool4_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigma, h16* __restrict__ wb, int Cout, int Cin,
-                      int ld) {
+                      int ld, int* ovf) {
   const int total = Cout * 16 * Cin;
   const float sg = sigma[0];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -173,21 +175,22 @@ pack_pool4_h16_kernel(const float* __restrict__ W, const float* __restrict__ sig
         acc += W[((int64_t)o * Cin + c) * 9 + ky * 3 + kx] / sg;       // (W / sigma) as the reference forms it
       }
     }
+    if (F16 && !(fabsf(0.25f * acc) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_WEIGHT);
     wb[(int64_t)o * ld + t * Cin + c] = (h16)(pack_h2<F16>(0.25f * acc, 0.f) & 0xffffu);
   }
 }
 
 int pack_pool4_h16(const float* W, const float* sigma, h16* wb, int Cout, int Cin, int f16, int ld, cudaStream_t s) {
   int total = Cout * 16 * Cin;
-  if (f16) { SDG_LAUNCH(pack_pool4_h16_kernel<true>, stream_grid(total, 256), 256, 0, s, W, sigma, wb, Cout, Cin, ld); }
-  else { SDG_LAUNCH(pack_pool4_h16_kernel<false>, stream_grid(total, 256), 256, 0, s, W, sigma, wb, Cout, Cin, ld); }
+  if (f16) { SDG_LAUNCH(pack_pool4_h16_kernel<true>, stream_grid(total, 256), 256, 0, s, W, sigma, wb, Cout, Cin, ld, t_range_flag); }
+  else { SDG_LAUNCH(pack_pool4_h16_kernel<false>, stream_grid(total, 256), 256, 0, s, W, sigma, wb, Cout, Cin, ld, t_range_flag); }
   return 0;
 }
 
 template <bool F16>
 __global__ void __launch_bounds__(256)
 pack_pool4_sc_h16_kernel(const float* __restrict__ Wsc, const float* __restrict__ sigma, h16* __restrict__ wb, int Cout,
-                         int Csc, int sc_pad, int ld, int col0) {
+                         int Csc, int sc_pad, int ld, int col0, int* ovf) {
   const int total = Cout * 4 * sc_pad;
   const float sg = sigma[0];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -195,6 +198,7 @@ pack_pool4_sc_h16_kernel(const float* __restrict__ Wsc, const float* __restrict_
     const int r = i / sc_pad;
     const int t = r & 3, o = r >> 2;
     const float w = c < Csc ? 0.25f * (Wsc[(int64_t)o * Csc + c] / sg) : 0.f;
+    if (F16 && !(fabsf(w) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_WEIGHT);
     wb[(int64_t)o * ld + col0 + t * sc_pad + c] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
   }
 }
@@ -202,8 +206,8 @@ pack_pool4_sc_h16_kernel(const float* __restrict__ Wsc, const float* __restrict_
 int pack_pool4_sc_h16(const float* Wsc, const float* sigma, h16* wb, int Cout, int Csc, int sc_pad, int f16, int ld, int col0,
                       cudaStream_t s) {
   int total = Cout * 4 * sc_pad;
-  if (f16) { SDG_LAUNCH(pack_pool4_sc_h16_kernel<true>, stream_grid(total, 256), 256, 0, s, Wsc, sigma, wb, Cout, Csc, sc_pad, ld, col0); }
-  else { SDG_LAUNCH(pack_pool4_sc_h16_kernel<false>, stream_grid(total, 256), 256, 0, s, Wsc, sigma, wb, Cout, Csc, sc_pad, ld, col0); }
+  if (f16) { SDG_LAUNCH(pack_pool4_sc_h16_kernel<true>, stream_grid(total, 256), 256, 0, s, Wsc, sigma, wb, Cout, Csc, sc_pad, ld, col0, t_range_flag); }
+  else { SDG_LAUNCH(pack_pool4_sc_h16_kernel<false>, stream_grid(total, 256), 256, 0, s, Wsc, sigma, wb, Cout, Csc, sc_pad, ld, col0, t_range_flag); }
   return 0;
 }
 
@@ -259,7 +263,8 @@ int permute_fc(const float* w, float* out, int C, int HW, cudaStream_t s) {
 
 template <bool F16>
 __global__ void __launch_bounds__(256)
-pack_first_superpix_kernel(const float* __restrict__ W, const float* __restrict__ sigma, h16* __restrict__ wb, int Cout) {
+pack_first_superpix_kernel(const float* __restrict__ W, const float* __restrict__ sigma, h16* __restrict__ wb, int Cout,
+                           int* ovf) {
   const float sg = sigma ? sigma[0] : 1.f;
   const int total = 2 * Cout * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -272,13 +277,14 @@ pack_first_superpix_kernel(const float* __restrict__ W, const float* __restrict_
       const int kx = j - par;
       if (kx >= 0 && kx <= 2) w = W[((o * 3 + c) * 3 + ky) * 3 + kx] / sg;
     }
+    if (F16 && !(fabsf(w) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_WEIGHT);
     wb[i] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
   }
 }
 
 int pack_first_superpix_h16(const float* W, const float* sigma, h16* wb, int Cout, int f16, cudaStream_t s) {
-  if (f16) { SDG_LAUNCH(pack_first_superpix_kernel<true>, stream_grid(2 * Cout * 64, 256), 256, 0, s, W, sigma, wb, Cout); }
-  else { SDG_LAUNCH(pack_first_superpix_kernel<false>, stream_grid(2 * Cout * 64, 256), 256, 0, s, W, sigma, wb, Cout); }
+  if (f16) { SDG_LAUNCH(pack_first_superpix_kernel<true>, stream_grid(2 * Cout * 64, 256), 256, 0, s, W, sigma, wb, Cout, t_range_flag); }
+  else { SDG_LAUNCH(pack_first_superpix_kernel<false>, stream_grid(2 * Cout * 64, 256), 256, 0, s, W, sigma, wb, Cout, t_range_flag); }
   return 0;
 }
 

@@ -137,10 +137,13 @@ extern "C" int sdg_resize_center_crop_u8(const uint8_t* in, int64_t n, int H, in
   int* tab = nullptr;
   SDG_CUDA(cudaMallocAsync(&tab, host.size() * sizeof(int), s));
   SDG_CUDA(cudaMemcpyAsync(tab, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice, s));   // pageable: staged before return
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per device: one bit per device id (a single process may drive several GPUs)
+  static std::atomic<unsigned long long> attr_set{0};
+  int dev = 0;
+  SDG_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !((attr_set.load() >> dev) & 1ULL)) {
     SDG_CUDA(cudaFuncSetAttribute(resize_crop_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    if (dev < 64) attr_set.fetch_or(1ULL << dev);
   }
   SDG_LAUNCH(resize_crop_u8_kernel, (unsigned)n, 256, smem, s, in, out, H, W, C, size, left, top, tab, tab + n_hb, ht.ksize,
              tab + n_hb + n_hk, tab + n_hb + n_hk + n_vb, vt.ksize, y_first, y_count);

@@ -388,12 +388,13 @@ __device__ __forceinline__ void split_hilo(float v, h16& hi, h16& lo) {
 // in fp32 [rows][C] -> out 16-bit [rows][3C] = [hi | lo | hi]
 template <bool F16>
 __global__ void __launch_bounds__(256)
-split3_rows_kernel(const float* __restrict__ in, h16* __restrict__ out, int64_t total, int C) {
+split3_rows_kernel(const float* __restrict__ in, h16* __restrict__ out, int64_t total, int C, int* ovf) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t r = i / C;
     const int c = (int)(i - r * C);
     h16 hi, lo;
+    if (F16 && !(fabsf(in[i]) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_ACT);
     split_hilo<F16>(in[i], hi, lo);
     h16* o = out + r * 3 * C;
     o[c] = hi; o[C + c] = lo; o[2 * C + c] = hi;
@@ -403,8 +404,8 @@ split3_rows_kernel(const float* __restrict__ in, h16* __restrict__ out, int64_t 
 int split3_rows_h16(const float* in, h16* out, int64_t rows, int C, int f16, cudaStream_t s) {
   const int64_t total = rows * C;
   if (total == 0) return 0;
-  if (f16) { SDG_LAUNCH(split3_rows_kernel<true>, stream_grid(total, 256), 256, 0, s, in, out, total, C); }
-  else { SDG_LAUNCH(split3_rows_kernel<false>, stream_grid(total, 256), 256, 0, s, in, out, total, C); }
+  if (f16) { SDG_LAUNCH(split3_rows_kernel<true>, stream_grid(total, 256), 256, 0, s, in, out, total, C, t_range_flag); }
+  else { SDG_LAUNCH(split3_rows_kernel<false>, stream_grid(total, 256), 256, 0, s, in, out, total, C, t_range_flag); }
   return 0;
 }
 
@@ -413,7 +414,8 @@ int split3_rows_h16(const float* in, h16* out, int64_t rows, int C, int f16, cud
 // linear mode: g = pixel p, w = W[o][c*G + p] (EqualLinear on an NCHW-flattened map, activations NHWC)
 template <bool F16>
 __global__ void __launch_bounds__(256)
-pack_split3_kernel(const float* __restrict__ W, float mul, h16* __restrict__ wb, int O, int C, int G, int cin_w, int linear) {
+pack_split3_kernel(const float* __restrict__ W, float mul, h16* __restrict__ wb, int O, int C, int G, int cin_w, int linear,
+                   int* ovf) {
   const int64_t K = (int64_t)G * C, total = (int64_t)O * K;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -421,6 +423,7 @@ pack_split3_kernel(const float* __restrict__ W, float mul, h16* __restrict__ wb,
     const int k = (int)(i - (int64_t)o * K);
     const int g = k / C, c = k - g * C;
     const float w = (linear ? W[(int64_t)o * K + (int64_t)c * G + g] : W[((int64_t)o * cin_w + c) * G + g]) * mul;
+    if (F16 && !(fabsf(w) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_WEIGHT);
     h16 hi, lo;
     split_hilo<F16>(w, hi, lo);
     h16* d = wb + (int64_t)o * 3 * K + (int64_t)g * 3 * C;
@@ -430,8 +433,8 @@ pack_split3_kernel(const float* __restrict__ W, float mul, h16* __restrict__ wb,
 
 int pack_split3_h16(const float* W, float mul, h16* wb, int O, int C, int G, int cin_w, int linear, int f16, cudaStream_t s) {
   const int64_t total = (int64_t)O * C * G;
-  if (f16) { SDG_LAUNCH(pack_split3_kernel<true>, stream_grid(total, 256), 256, 0, s, W, mul, wb, O, C, G, cin_w, linear); }
-  else { SDG_LAUNCH(pack_split3_kernel<false>, stream_grid(total, 256), 256, 0, s, W, mul, wb, O, C, G, cin_w, linear); }
+  if (f16) { SDG_LAUNCH(pack_split3_kernel<true>, stream_grid(total, 256), 256, 0, s, W, mul, wb, O, C, G, cin_w, linear, t_range_flag); }
+  else { SDG_LAUNCH(pack_split3_kernel<false>, stream_grid(total, 256), 256, 0, s, W, mul, wb, O, C, G, cin_w, linear, t_range_flag); }
   return 0;
 }
 

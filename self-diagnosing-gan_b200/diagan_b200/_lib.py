@@ -17,6 +17,7 @@ ABI_VERSION = 1
 ARCH_DCGAN32, ARCH_STYLEGAN2, ARCH_SNGAN32, ARCH_SNGAN64 = 1, 2, 32, 64
 PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 LAYOUT_U8_NHWC, LAYOUT_F32_NCHW = 0, 1
+RANGE_ACT, RANGE_WEIGHT = 1, 2
 
 _vp, _i, _i64, _d, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float, C.c_size_t
 _pp = C.POINTER(C.c_void_p)
@@ -27,6 +28,7 @@ SIGNATURES = {
     "sdg_abi_version": (_i, []),
     "sdg_ctx_create": (_i, [_i, _pp]),
     "sdg_ctx_destroy": (_i, [_vp]),
+    "sdg_ctx_set_range_flag": (_i, [_vp, _vp]),
     "sdg_ctx_set_chunk": (_i, [_vp, _i64]),
     "sdg_sngan_load": (_i, [_vp, _i, _i, _pp, _pp, _pp, _i, _i, _vp]),
     "sdg_sngan_sigmas": (_i, [_vp, _vp, _vp]),

@@ -104,6 +104,7 @@ def get_logit_resident(recorder, netD, step=None) -> torch.Tensor:
     mult = recorder.batch if engine_is_stylegan2(netD) else 1
     lo, hi = shard_range(n, multiple=mult)
     recorder.shard = (lo, hi)
+    recorder.shard_multiple = mult                 # sharded_score must all-gather with the same shard size
     snap = recorder.record(netD)
     full = all_gather_shards(snap[lo:hi], n, multiple=mult)
     if step is not None:
@@ -150,35 +151,40 @@ def get_logit(dataloader, netD, device=None, step=None):
     if rec is None:
         rec = _loader_recorders[device] = LogitRecorder(None, device)
     n = len(dataloader.dataset)
-    idx_parts, logit_parts = [], []
     sg2 = engine_is_stylegan2(netD)
-    loaded = False
-    pending, pending_b = [], 0                             # loader batches of equal size waiting for one engine call
 
-    def flush():
-        nonlocal pending
-        if not pending:
-            return
-        if sg2:
-            rec.engine.set_batch(pending_b)                # consecutive groups of pending_b samples = the loader's batches
-        logit_parts.append(rec.engine.forward(torch.cat(pending) if len(pending) > 1 else pending[0]))
-        pending = []
+    def run(precision):
+        idx_parts, logit_parts = [], []
+        loaded = False
+        pending, pending_b = [], 0                         # loader batches of equal size waiting for one engine call
 
-    for item in dataloader:
-        data, idx = item[0], item[-1]
-        if not loaded:                                     # weights packed once per pass, after the batch size is known
-            rec.batch = int(data.shape[0]) if sg2 else rec.batch
-            rec.load_weights(netD)
-            loaded = True
-        x = data.to(device=device, dtype=torch.float32).contiguous()
-        if pending and (x.shape[0] != pending_b or len(pending) * pending_b >= 256):
-            flush()                                        # a short last batch is its own stddev batch (drop_last=False)
-        pending.append(x)
-        pending_b = int(x.shape[0])
-        idx_parts.append(idx.to(device))
-    flush()
-    idx_all = torch.cat(idx_parts) if idx_parts else torch.empty(0, dtype=torch.int64, device=device)
-    logit_all = torch.cat(logit_parts) if logit_parts else torch.empty(0, dtype=torch.float32, device=device)
+        def flush():
+            nonlocal pending
+            if not pending:
+                return
+            if sg2:
+                rec.engine.set_batch(pending_b)            # consecutive groups of pending_b samples = the loader's batches
+            logit_parts.append(rec.engine.forward(torch.cat(pending) if len(pending) > 1 else pending[0]))
+            pending = []
+
+        for item in dataloader:
+            data, idx = item[0], item[-1]
+            if not loaded:                                 # weights packed once per pass, after the batch size is known
+                rec.batch = int(data.shape[0]) if sg2 else rec.batch
+                rec.load_weights(netD, precision)
+                loaded = True
+            x = data.to(device=device, dtype=torch.float32).contiguous()
+            if pending and (x.shape[0] != pending_b or len(pending) * pending_b >= 256):
+                flush()                                    # a short last batch is its own stddev batch (drop_last=False)
+            pending.append(x)
+            pending_b = int(x.shape[0])
+            idx_parts.append(idx.to(device))
+        flush()
+        idx_all = torch.cat(idx_parts) if idx_parts else torch.empty(0, dtype=torch.int64, device=device)
+        logit_all = torch.cat(logit_parts) if logit_parts else torch.empty(0, dtype=torch.float32, device=device)
+        return idx_all, logit_all
+
+    idx_all, logit_all = rec._guarded(netD, run, "sync")   # fp16 range guard: an overflowing pass is re-run in bf16
     out = gather_indexed(idx_all, logit_all, n)
     if hasattr(netD, "train"):
         netD.train()                                       # train_ffhq.py:142
@@ -189,7 +195,7 @@ def sharded_score(recorder, conf: float, eps: float = 0.0) -> torch.Tensor:
     """ldr_conf score of the whole dataset from per-rank running statistics: local floor+min, MIN
     all-reduce of the bound, local clip, one all-gather of the float64 shard -> float64 [N]."""
     local = recorder.stats.score(conf, eps=eps, min_reduce=all_reduce_min_)
-    return all_gather_shards(local, recorder.n)
+    return all_gather_shards(local, recorder.n, multiple=getattr(recorder, "shard_multiple", 1))
 
 
 def save_logit(logits_dict, output_path):

@@ -38,6 +38,14 @@ def conf_from_key(key: str) -> float:
     raise KeyError(f"{key!r} is not one of the reference's score keys")
 
 
+def _resolve_device(device=None) -> torch.device:
+    """A CUDA device WITH an index (``cuda`` alone means the current device, not device 0)."""
+    d = torch.device("cuda") if device is None else torch.device(device)
+    if d.type != "cuda":
+        raise _lib.SdgError(f"device {d}: diagan_b200 is sm_100a only and has no CPU path")
+    return torch.device("cuda", torch.cuda.current_device()) if d.index is None else d
+
+
 def _require_cuda(t: torch.Tensor, name: str):
     if not t.is_cuda:
         raise _lib.SdgError(f"{name} must be a CUDA tensor (diagan_b200 has no CPU path)")
@@ -98,10 +106,13 @@ class DiscriminatorEngine:
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.SdgError("no CUDA device: diagan_b200 is sm_100a only and has no CPU fallback")
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = _resolve_device(device)
         h = C.c_void_p()
-        check(self.lib.sdg_ctx_create(self.device.index or 0, C.byref(h)), "sdg_ctx_create")
+        check(self.lib.sdg_ctx_create(self.device.index, C.byref(h)), "sdg_ctx_create")
         self._h = h
+        # fp16 range guard (include/sdg.h, sdg_ctx_set_range_flag): a sticky device flag the fp16 kernels OR into
+        self._range = torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(self.lib.sdg_ctx_set_range_flag(self._h, ptr(self._range)), "sdg_ctx_set_range_flag")
         self.arch = None
         self.size = None
         self.n_layers = 0
@@ -110,6 +121,7 @@ class DiscriminatorEngine:
 
     def close(self):
         if getattr(self, "_h", None):
+            self.lib.sdg_ctx_set_range_flag(self._h, None)
             self.lib.sdg_ctx_destroy(self._h)
             self._h = None
 
@@ -118,6 +130,14 @@ class DiscriminatorEngine:
             self.close()
         except Exception:
             pass
+
+    def range_status(self, reset: bool = True) -> int:
+        """Host read (one 4-byte D2H, synchronises the stream) of the fp16 range flag: 0, or a mask of
+        ``_lib.RANGE_ACT`` / ``_lib.RANGE_WEIGHT`` if a value left the fp16 range since the last reset."""
+        v = int(self._range.item())
+        if v and reset:
+            self._range.zero_()
+        return v
 
     def set_chunk(self, samples: int):
         check(self.lib.sdg_ctx_set_chunk(self._h, int(samples)), "sdg_ctx_set_chunk")
@@ -144,7 +164,8 @@ class DiscriminatorEngine:
         bn_idx = [4, 8, 12, 16, 20]
         W = [self._dev(state_dict[f"conv.{i}.weight"]) for i in conv_idx]
         if W[0].shape[1] != 3:
-            raise _lib.SdgError("DCGAN discriminator with num_pack != 1 is not supported")
+            raise _lib.SdgError(f"DCGAN discriminator with nc * num_pack = {W[0].shape[1]} input channels: only nc = 3, "
+                                "num_pack = 1 is implemented")
         g = [self._dev(state_dict[f"conv.{i}.weight"]) for i in bn_idx]
         be = [self._dev(state_dict[f"conv.{i}.bias"]) for i in bn_idx]
         mu = [self._dev(state_dict[f"conv.{i}.running_mean"]) for i in bn_idx]
@@ -221,15 +242,16 @@ class RunningStats:
 
     def __init__(self, n: int, device):
         self.lib = _lib.load()
-        self.n, self.device, self.count = int(n), torch.device(device), 0
+        self.n, self.device, self.count = int(n), _resolve_device(device), 0
         self.state = torch.zeros(4, self.n, dtype=torch.float64, device=self.device)   # mean, m2, last, sad
 
     def update(self, snapshot: torch.Tensor):
         _require_cuda(snapshot, "snapshot")
         assert snapshot.dtype == torch.float32 and snapshot.numel() == self.n
         m, q, la, sa = self.state[0], self.state[1], self.state[2], self.state[3]
-        check(self.lib.sdg_stats_update(ptr(snapshot), ptr(m), ptr(q), ptr(la), ptr(sa), self.n, self.count,
-                                        stream_ptr(self.device)), "sdg_stats_update")
+        with torch.cuda.device(self.device):
+            check(self.lib.sdg_stats_update(ptr(snapshot), ptr(m), ptr(q), ptr(la), ptr(sa), self.n, self.count,
+                                            stream_ptr(self.device)), "sdg_stats_update")
         self.count += 1
 
     @property
@@ -261,8 +283,9 @@ def window_moments(snaps: torch.Tensor, want=("mean", "var", "ldrd", "ldr")):
     T, n = snaps.shape
     out = {k: torch.empty(n, dtype=torch.float64, device=snaps.device) for k in want}
     fn = {torch.float32: lib.sdg_window_moments_f32, torch.float64: lib.sdg_window_moments_f64}[snaps.dtype]
-    check(fn(ptr(snaps), T, n, snaps.stride(0), ptr(out.get("mean")), ptr(out.get("var")), ptr(out.get("ldrd")),
-             ptr(out.get("ldr")), stream_ptr(snaps.device)), "sdg_window_moments")
+    with torch.cuda.device(snaps.device):
+        check(fn(ptr(snaps), T, n, snaps.stride(0), ptr(out.get("mean")), ptr(out.get("var")), ptr(out.get("ldrd")),
+                 ptr(out.get("ldr")), stream_ptr(snaps.device)), "sdg_window_moments")
     return out
 
 
@@ -279,11 +302,12 @@ def scores_from_moments(mean, var, confs, floor=FLOOR, ratio=RATIO, eps=0.0, m2_
         sc = score[s:s + kk]
         mins = torch.empty(kk, dtype=torch.float64, device=mean.device)
         st = stream_ptr(mean.device)
-        check(lib.sdg_score_floor_min(ptr(mean), ptr(var), n, cs.ctypes.data_as(C.POINTER(C.c_double)), kk, floor,
-                                      float(m2_over), ptr(sc), ptr(mins), st), "sdg_score_floor_min")
-        if min_reduce is not None:
-            min_reduce(mins)
-        check(lib.sdg_score_clip(ptr(sc), n, kk, ptr(mins), ratio, eps, st), "sdg_score_clip")
+        with torch.cuda.device(mean.device):
+            check(lib.sdg_score_floor_min(ptr(mean), ptr(var), n, cs.ctypes.data_as(C.POINTER(C.c_double)), kk, floor,
+                                          float(m2_over), ptr(sc), ptr(mins), st), "sdg_score_floor_min")
+            if min_reduce is not None:
+                min_reduce(mins)
+            check(lib.sdg_score_clip(ptr(sc), n, kk, ptr(mins), ratio, eps, st), "sdg_score_clip")
         out_chunks.append(mins)
     return score
 
@@ -303,8 +327,9 @@ def top_indices(score: torch.Tensor, k: int, largest: bool = True) -> torch.Tens
         ws = torch.empty(need, dtype=torch.uint8, device=score.device)
         _topk_ws[score.device] = ws
     out = torch.empty(k, dtype=torch.int64, device=score.device)
-    check(lib.sdg_topk_indices(ptr(score), n, k, 1 if largest else 0, ptr(out), ptr(ws), ws.numel(),
-                               stream_ptr(score.device)), "sdg_topk_indices")
+    with torch.cuda.device(score.device):
+        check(lib.sdg_topk_indices(ptr(score), n, k, 1 if largest else 0, ptr(out), ptr(ws), ws.numel(),
+                                   stream_ptr(score.device)), "sdg_topk_indices")
     return out
 
 

@@ -23,9 +23,10 @@ class DRS(nn.Module):
         super().__init__()
         self.netG = netG
         self.netD = netD
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
+        if torch.device(device).type != "cuda":
             raise _lib.SdgError("diagan_b200 DRS needs a CUDA device (no CPU fallback)")
+        from ..engine import _resolve_device
+        self.device = _resolve_device(device)
         self.batch_size = batch_size
         self.percentile = percentile
         self.gamma = gamma
@@ -60,8 +61,9 @@ class DRS(nn.Module):
     def init_drs(self):
         for _ in range(50):                                         # drs.py:31-36
             _, ldr = self._ldr_device(self.batch_size)
-            check(self._lib.sdg_drs_update_max(ptr(ldr), ldr.numel(), ptr(self._max), stream_ptr(self.device)),
-                  "sdg_drs_update_max")
+            with torch.cuda.device(self.device):
+                check(self._lib.sdg_drs_update_max(ptr(ldr), ldr.numel(), ptr(self._max), stream_ptr(self.device)),
+                      "sdg_drs_update_max")
 
     def accept(self, ldr, psi=None, eps=1e-6, gamma=None):
         """Device acceptance pass -> (p float32 [n], accept uint8 [n], idx int32 [n], count int32 [1])."""
@@ -76,10 +78,11 @@ class DRS(nn.Module):
         acc = torch.empty(n, dtype=torch.uint8, device=self.device)
         idx = torch.empty(n, dtype=torch.int32, device=self.device)
         g = self.gamma if gamma is None else gamma
-        check(self._lib.sdg_drs_accept(ptr(ldr), n, ptr(self._max), float(eps), float(self.percentile),
-                                       0 if g is None else 1, 0.0 if g is None else float(g), ptr(psi_d), ptr(p),
-                                       ptr(acc), ptr(idx), ptr(self._count), stream_ptr(self.device)),
-              "sdg_drs_accept")
+        with torch.cuda.device(self.device):
+            check(self._lib.sdg_drs_accept(ptr(ldr), n, ptr(self._max), float(eps), float(self.percentile),
+                                           0 if g is None else 1, 0.0 if g is None else float(g), ptr(psi_d), ptr(p),
+                                           ptr(acc), ptr(idx), ptr(self._count), stream_ptr(self.device)),
+                  "sdg_drs_accept")
         return p, acc, idx, self._count
 
     def sub_rejection_sampler(self, fake_samples, ldr, eps=1e-6, gamma=None):
@@ -115,11 +118,12 @@ class DRS(nn.Module):
             idx = torch.empty(k, B, dtype=torch.int32, device=self.device)
             cnt = torch.zeros(k, dtype=torch.int32, device=self.device)
             g = self.gamma
-            for j in range(k):
-                check(self._lib.sdg_drs_accept(ptr(ldr[j * B:(j + 1) * B]), B, ptr(self._max), 1e-6, float(self.percentile),
-                                               0 if g is None else 1, 0.0 if g is None else float(g), ptr(psi[j * B:(j + 1) * B]),
-                                               None, None, ptr(idx[j]), ptr(cnt[j:j + 1]), stream_ptr(self.device)),
-                      "sdg_drs_accept")
+            with torch.cuda.device(self.device):
+                for j in range(k):
+                    check(self._lib.sdg_drs_accept(ptr(ldr[j * B:(j + 1) * B]), B, ptr(self._max), 1e-6, float(self.percentile),
+                                                   0 if g is None else 1, 0.0 if g is None else float(g),
+                                                   ptr(psi[j * B:(j + 1) * B]), None, None, ptr(idx[j]), ptr(cnt[j:j + 1]),
+                                                   stream_ptr(self.device)), "sdg_drs_accept")
             counts = cnt.cpu().tolist()                                   # the one host sync of this round
             for j in range(k):
                 if counts[j]:

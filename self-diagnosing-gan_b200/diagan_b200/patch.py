@@ -16,6 +16,28 @@ from __future__ import annotations
 
 import importlib
 
+_originals = {}      # (module name, attribute path) -> the reference's own object, for uninstall()
+
+
+def _swap(mod, owner, attr, new):
+    key = (mod.__name__, owner.__name__ if owner is not mod else "", attr)
+    if key not in _originals:
+        _originals[key] = (owner, attr, getattr(owner, attr, None), hasattr(owner, attr))
+    setattr(owner, attr, new)
+
+
+def uninstall() -> int:
+    """Put the reference's own objects back (tests; A/B runs of the same script).  Returns how many were restored."""
+    n = 0
+    for owner, attr, old, existed in _originals.values():
+        if existed:
+            setattr(owner, attr, old)
+        elif hasattr(owner, attr):
+            delattr(owner, attr)
+        n += 1
+    _originals.clear()
+    return n
+
 
 def install(verbose: bool = True) -> dict:
     from .models import drs as b_drs
@@ -34,15 +56,20 @@ def install(verbose: bool = True) -> dict:
         fn(mod)
         done[modname] = "patched"
 
-    _try("diagan.utils.plot", lambda m: setattr(m, "calculate_scores", b_plot.calculate_scores))
+    _try("diagan.utils.plot", lambda m: _swap(m, m, "calculate_scores", b_plot.calculate_scores))
 
     def _trainer(m):
-        m.LogTrainer._get_logit = b_trainer._get_logit
-        m.LogTrainer._save_logit = b_trainer._save_logit
-        m.LogTrainer._restore_logits = b_trainer._restore_logits      # opt-in resume (call after construction)
+        # the reference's own pass stays reachable: _get_logit delegates to it (with a warning) for discriminators or
+        # modes the engine does not reproduce (train-mode DCGAN of train_mimicry_color_mnist_phase1.py, nc = 1 of the
+        # MNIST/FMNIST scripts, architectures detect_arch rejects), so those scripts keep running unchanged
+        if not hasattr(m.LogTrainer, "_get_logit_ref"):
+            _swap(m, m.LogTrainer, "_get_logit_ref", m.LogTrainer._get_logit)
+        _swap(m, m.LogTrainer, "_get_logit", b_trainer._get_logit)
+        _swap(m, m.LogTrainer, "_save_logit", b_trainer._save_logit)
+        _swap(m, m.LogTrainer, "_restore_logits", b_trainer._restore_logits)   # opt-in resume (call after construction)
     _try("diagan.trainer.trainer", _trainer)
-    _try("diagan.models.drs", lambda m: setattr(m, "DRS", b_drs.DRS))
-    _try("diagan.trainer.evaluate", lambda m: setattr(m, "DRS", b_eval.DRS))
+    _try("diagan.models.drs", lambda m: _swap(m, m, "DRS", b_drs.DRS))
+    _try("diagan.trainer.evaluate", lambda m: _swap(m, m, "DRS", b_eval.DRS))
     if verbose:
         for k, v in done.items():
             print(f"diagan_b200.patch: {k}: {v}")

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import os
 import pickle
+import warnings
 from collections import defaultdict
 from pathlib import Path
 
@@ -83,8 +84,8 @@ class LogitRecorder:
     """
 
     def __init__(self, dataset: ResidentDataset = None, device=None, precision="fp16", inplace_relu=True,
-                 shard=None, keep_snapshots=True, stats_window=None, batch=4):
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+                 shard=None, keep_snapshots=True, stats_window=None, batch=4, range_fallback="bf16"):
+        self.device = engine._resolve_device(device)
         self.dataset = dataset
         self.precision = precision
         self.inplace_relu = inplace_relu
@@ -98,28 +99,67 @@ class LogitRecorder:
         # StyleGAN2 only: the loader batch size of the reference pass (stylegan2/train_ffhq.py:596-602); minibatch-stddev
         # groups live inside consecutive batches of this size and the ragged tail is dropped (drop_last=True)
         self.batch = batch
+        self.dcgan_precision = "fp32"             # the DCGAN discriminator's own default (exact CUDA-core engine)
+        self.shard_multiple = 1                   # set by distributed.get_logit_resident (StyleGAN2: whole loader batches)
+        # fp16 range guard: a pass during which a value left the fp16 range is re-run with this precision ("bf16" has the
+        # fp32 range at 8x the rounding error; "fp32" is the exact CUDA-core engine, ~50x slower)
+        self.range_fallback = range_fallback
+        self.range_events = 0                     # passes that had to be re-run
+
+    def _guarded(self, netD, run, range_check):
+        """Run one pass (``run(precision)`` loads the weights and launches the forward).  ``range_check``:
+        "sync"     -- read the fp16 range flag after the pass (one 4-byte D2H) and, if a value left the fp16 range,
+                      warn and re-run the pass with ``range_fallback``;
+        "deferred" -- do not touch the host; the flag stays set until :meth:`check_range` is called;
+        "off"      -- ignore the flag."""
+        out = run(self.precision)
+        if range_check != "sync" or self.precision != "fp16":
+            return out
+        flag = self.engine.range_status(reset=True)
+        if flag:
+            self.range_events += 1
+            what = " and ".join(n for b, n in ((_lib.RANGE_ACT, "an activation"), (_lib.RANGE_WEIGHT, "a packed weight")) if flag & b)
+            warnings.warn(f"diagan_b200: {what} left the fp16 range (|v| > 65504) during this recording pass; re-running "
+                          f"it with precision={self.range_fallback!r}", RuntimeWarning, stacklevel=3)
+            out = run(self.range_fallback)
+        return out
+
+    def check_range(self):
+        """Deferred form of the range guard: raises if any fp16 pass since the last check left the fp16 range."""
+        if self.precision == "fp16" and self.engine.range_status(reset=True):
+            raise _lib.SdgError("a value left the fp16 range (|v| > 65504) during a recording pass since the last check: "
+                                "its logits and the statistics folded from them are invalid; re-run with "
+                                "range_check='sync' or precision='bf16'")
 
     def _range(self):
         return (0, self.n) if self.shard is None else self.shard
 
-    def load_weights(self, netD):
+    def load_weights(self, netD, precision=None):
         sd = netD.state_dict() if hasattr(netD, "state_dict") else netD
         kind = engine.detect_arch(sd)
+        precision = precision or self.precision
         if kind == "stylegan2":
-            self.engine.load_stylegan2(sd, self.precision, batch=self.batch)
+            self.engine.load_stylegan2(sd, precision, batch=self.batch)
         else:
-            self.engine.load(sd, self.precision if kind != "dcgan32" else "fp32", self.inplace_relu)
+            self.engine.load(sd, precision if kind != "dcgan32" else self.dcgan_precision, self.inplace_relu)
 
-    def record(self, netD, step=None, out: torch.Tensor = None) -> torch.Tensor:
-        """One recording pass over the resident dataset (this rank's shard) -> float32 [N] on the device."""
+    def record(self, netD, step=None, out: torch.Tensor = None, range_check="sync") -> torch.Tensor:
+        """One recording pass over the resident dataset (this rank's shard) -> float32 [N] on the device.
+        ``range_check``: see :meth:`_guarded` ("sync" costs one 4-byte device->host read per pass)."""
         if self.dataset is None:
             raise _lib.SdgError("LogitRecorder.record needs a ResidentDataset")
-        self.load_weights(netD)
-        lo, hi = self._range()
         snap = torch.zeros(self.n, dtype=torch.float32, device=self.device) if out is None else out
-        if self.engine.arch == "stylegan2":
-            hi = lo + (hi - lo) // self.batch * self.batch      # drop_last: the tail keeps its 0.0 like the reference
-        self.engine.forward(self.dataset.data[lo:hi], out=snap[lo:hi])
+
+        def run(precision):
+            self.load_weights(netD, precision)
+            lo, hi = self._range()
+            if self.engine.arch == "stylegan2":
+                hi = lo + (hi - lo) // self.batch * self.batch      # drop_last: the tail keeps its 0.0 like the reference
+            if hi > lo:
+                self.engine.forward(self.dataset.data[lo:hi], out=snap[lo:hi])
+            return snap
+
+        self._guarded(netD, run, range_check)
         if step is not None:
             self.observe(step, snap)
         return snap
@@ -135,7 +175,8 @@ class LogitRecorder:
                 self.stats = engine.RunningStats(hi - lo, self.device)
             self.stats.update(snap[lo:hi])
 
-    def record_from_host(self, netD, host_u8: torch.Tensor, step=None, chunk: int = 12544, first_chunk: int = 2048) -> torch.Tensor:
+    def record_from_host(self, netD, host_u8: torch.Tensor, step=None, chunk: int = 12544, first_chunk: int = 2048,
+                         range_check="sync") -> torch.Tensor:
         """Recording pass over a dataset that lives in (pinned) HOST memory: uint8 NHWC chunks are
         copied on a side stream into two staging buffers while the previous chunk is in the engine, so
         the H2D traffic (3 KB/sample for CIFAR shape) overlaps the forward.  The first chunk is small and its copy is
@@ -166,53 +207,111 @@ class LogitRecorder:
                 self._stage[b][:s1 - s0].copy_(host_u8[s0:s1], non_blocking=True)
                 self._ev_copied[b].record(self._copy_stream)
 
-        issue_copy(0)                                                   # overlaps sigma + weight packing
-        self.load_weights(netD)
         snap = torch.zeros(n, dtype=torch.float32, device=self.device)
-        for i in range(len(bounds) - 1):
-            b, s0, s1 = i & 1, bounds[i], bounds[i + 1]
-            if i + 1 < len(bounds) - 1:
-                issue_copy(i + 1)                                       # next chunk streams in during this forward
-            main.wait_event(self._ev_copied[b])
-            self.engine.forward(self._stage[b][:s1 - s0], out=snap[s0:s1])
-            self._ev_used[b].record(main)
+
+        def run(precision):
+            issue_copy(0)                                                   # overlaps sigma + weight packing
+            self.load_weights(netD, precision)
+            for i in range(len(bounds) - 1):
+                b, s0, s1 = i & 1, bounds[i], bounds[i + 1]
+                if i + 1 < len(bounds) - 1:
+                    issue_copy(i + 1)                                       # next chunk streams in during this forward
+                main.wait_event(self._ev_copied[b])
+                self.engine.forward(self._stage[b][:s1 - s0], out=snap[s0:s1])
+                self._ev_used[b].record(main)
+            return snap
+
+        self._guarded(netD, run, range_check)
         if step is not None:
             self.observe(step, snap)
         return snap
 
-    def record_from_loader(self, netD, dataloader, n=None) -> torch.Tensor:
+    def record_from_loader(self, netD, dataloader, n=None, range_check="sync", group: int = 16) -> torch.Tensor:
         """Generic feeding path with the reference's item contract: batches ``(data, target, weight,
         index)`` (predefined.py:22-24) or ``(img, idx)`` come from a DataLoader, the forward still runs in
-        the CUDA engine, logits are scattered by dataset index (trainer.py:148-154)."""
-        self.load_weights(netD)
+        the CUDA engine, logits are scattered by dataset index (trainer.py:148-154).  Up to ``group`` loader batches are
+        concatenated per engine call (samples are independent in every discriminator this path serves except StyleGAN2,
+        which goes through ``diagan_b200.distributed.get_logit``), so a batch-64 loader costs one launch sequence per 1024
+        samples instead of per 64."""
         n = len(dataloader.dataset) if n is None else n
         snap = torch.zeros(n, dtype=torch.float32, device=self.device)
-        for item in dataloader:
-            data, idx = item[0], item[-1]
-            x = data.to(device=self.device, dtype=torch.float32).contiguous()
-            snap[idx.to(self.device)] = self.engine.forward(x)
-        return snap
+
+        def run(precision):
+            self.load_weights(netD, precision)
+            per_call = 1 if self.engine.arch == "stylegan2" else max(1, int(group))
+            xs, ids = [], []
+
+            def flush():
+                if xs:
+                    x = torch.cat(xs) if len(xs) > 1 else xs[0]
+                    i = torch.cat(ids) if len(ids) > 1 else ids[0]
+                    snap[i] = self.engine.forward(x)
+                    xs.clear(); ids.clear()
+
+            for item in dataloader:
+                data, idx = item[0], item[-1]
+                xs.append(data.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous())
+                ids.append(idx.to(self.device, non_blocking=True))
+                if len(xs) >= per_call:
+                    flush()
+            flush()
+            return snap
+
+        return self._guarded(netD, run, range_check)
 
 
 # ---- reference-named methods (usable standalone or grafted onto the reference class) -------------
+
+def _unsupported_reason(sd, eval_mode):
+    """None if the CUDA engine reproduces ``netD(x)`` for this state_dict / mode, else why it does not."""
+    try:
+        kind = engine.detect_arch(sd)
+    except _lib.SdgError as e:
+        return str(e)
+    if kind == "dcgan32":
+        nc = int(sd["conv.0.weight"].shape[1])
+        if nc != 3:
+            return (f"the DCGAN discriminator was built with nc * num_pack = {nc} input channels (mnist.py:156-163); the "
+                    "engine implements nc = 3, num_pack = 1")
+        if not eval_mode:
+            return ("train-mode logits of the DCGAN discriminator (Dropout + batch-statistics BatchNorm, "
+                    "save_eval_logits=False) are stochastic and batch dependent; only eval_mode=True has a per-sample "
+                    "definition")
+    elif kind != "stylegan2" and not eval_mode:
+        return ("train-mode logits of a spectral-norm discriminator advance sn_u / sn_sigma once per batch "
+                "(trainer.py:145-146 leaves netD in train mode); the engine computes sigma once per pass with eval "
+                "semantics")
+    return None
+
 
 def _get_logit(self, netD, eval_mode=False):
     """``LogTrainer._get_logit`` (trainer.py:142-156): float64 [N] by dataset index.
 
     Uses ``self.recorder`` (a :class:`LogitRecorder` with a resident dataset) when present, otherwise
-    feeds the CUDA engine from ``self.dataloader``.  Only eval-mode logits have a per-sample definition
-    for discriminators with BatchNorm/Dropout; SNGAN is mode-independent apart from
-    the spectral-norm buffers, which this pass never updates."""
+    feeds the CUDA engine from ``self.dataloader``.
+
+    Discriminators / modes the engine does not reproduce (``_unsupported_reason``: train-mode DCGAN, nc != 3, an
+    architecture ``detect_arch`` rejects, train-mode spectral norm) are handed to the reference's own method when
+    ``diagan_b200.patch.install()`` kept it as ``_get_logit_ref`` -- with a warning, never silently; without it they
+    raise, except train-mode SNGAN, which warns and returns eval-semantics logits (identical up to the sn_u drift).
+    A missing ``libsdg.so`` or a non-B200 device always raises: the fallback is for unsupported MODELS only."""
+    sd = netD.state_dict()
+    why = _unsupported_reason(sd, eval_mode)
+    if why is not None:
+        ref = getattr(type(self), "_get_logit_ref", None)
+        if ref is not None:
+            warnings.warn(f"diagan_b200: {why}; this pass runs through the reference's own LogTrainer._get_logit",
+                          RuntimeWarning, stacklevel=2)
+            return ref(self, netD=netD, eval_mode=eval_mode)
+        if "spectral-norm" not in why:
+            raise _lib.SdgError(why)
+        warnings.warn(f"diagan_b200: {why}; returning eval-semantics logits", RuntimeWarning, stacklevel=2)
     rec = getattr(self, "recorder", None)
     if rec is None:
         rec = LogitRecorder(None, getattr(self, "device", None))
         self.recorder = rec
-    sd = netD.state_dict()
-    if not eval_mode and engine.detect_arch(sd) == "dcgan32":
-        raise _lib.SdgError("train-mode logits of the DCGAN discriminator (Dropout + batch-stat BatchNorm) are "
-                            "stochastic and batch dependent; only eval_mode=True is reproducible")
     if rec.dataset is not None:
-        snap = rec.record(netD)
+        snap = rec.record(netD, range_check="sync")
     else:
         snap = rec.record_from_loader(netD, self.dataloader)
     if hasattr(netD, "train"):
