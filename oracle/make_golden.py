@@ -187,6 +187,31 @@ def make_stylegan2():
         print(f"stylegan2_d{size} logits[:4]", y[:4])
 
 
+def make_stylegan2_256():
+    """BASELINE configs[4] at its own size: StyleGANDiscriminator(256), two reference batches of 4 (train_ffhq.py:318).  The
+    input bytes are regenerated by the tests from ``x_seed`` (RandomState(seed).randint, stable across NumPy versions), so the
+    fixture holds only the eight logits."""
+    D = ref_loader.reference_stylegan2_discriminator()
+    size, n, batch, x_seed = 256, 8, 4, 7
+    net = D(size=size)
+    params = sg2_oracle.init_params(size, seed=1)
+    sd = net.state_dict()
+    for k, v in params.items():
+        assert sd[k].shape == v.shape, (k, sd[k].shape, v.shape)
+        sd[k] = v.clone()
+    net.load_state_dict(sd)
+    net.eval()
+    x_u8 = np.random.RandomState(x_seed).randint(0, 256, (n, size, size, 3)).astype(np.uint8)
+    x = ((torch.from_numpy(x_u8).permute(0, 3, 1, 2).float() / 255.0 - 0.5) / 0.5).contiguous()
+    with torch.no_grad():
+        y = torch.cat([net(x[s:s + batch]) for s in range(0, n, batch)]).view(-1).numpy()
+    chk = np.float64(sum(float(np.sum(v.numpy().astype(np.float64))) for v in params.values()))
+    np.savez_compressed(os.path.join(OUT, "stylegan2_d256.npz"), size=np.int64(size), batch=np.int64(batch),
+                        param_seed=np.int64(1), param_checksum=chk, x_seed=np.int64(x_seed), n=np.int64(n),
+                        x_checksum=np.int64(int(x_u8.astype(np.int64).sum())), logits=y.astype(np.float32))
+    print("stylegan2_d256 logits", y)
+
+
 def make_resize():
     """The reference's own transform (datasets/transform.py: Resize, CenterCrop, ToTensor, Normalize) applied to PIL images
     built like color_mnist.py:92 does; the uint8 image is recovered exactly from the normalised tensor."""
@@ -212,8 +237,13 @@ def make_resize():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)      # single-thread convs: deterministic accumulation order
+    if len(sys.argv) > 1:         # python oracle/make_golden.py make_stylegan2_256  -> only that fixture
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     make_scores()
     make_drs()
     make_dcgan()
     make_stylegan2()
+    make_stylegan2_256()
     make_resize()

@@ -101,12 +101,23 @@ def sn_weight(params: dict, key: str) -> torch.Tensor:
     return w / sigma_eval(w, params[f"{key}.sn_u"])
 
 
+def normalised_weights(params: dict, arch: int) -> dict:
+    """{layer key: W / sigma} for every layer: what eval-mode mimicry recomputes (to the same value) in every forward."""
+    return {key: sn_weight(params, key) for key, _, _, _ in layer_list(arch)}
+
+
 def _conv(params, key, x, pad):
-    return F.conv2d(x, sn_weight(params, key), params[f"{key}.bias"], stride=1, padding=pad)
+    w = params["__wn__"][key] if "__wn__" in params else sn_weight(params, key)
+    return F.conv2d(x, w, params[f"{key}.bias"], stride=1, padding=pad)
 
 
-def forward(params: dict, x: torch.Tensor, arch: int = 32, inplace_relu: bool = True) -> torch.Tensor:
-    """x float32 NCHW in [-1,1] -> logits [B,1].
+def forward(params: dict, x: torch.Tensor, arch: int = 32, inplace_relu: bool = True, with_head_l1: bool = False):
+    """x float32 NCHW in [-1,1] -> logits [B,1]  (``with_head_l1``: also the L1 mass of the head's dot product,
+    sum_c |w_c * pooled_c| + |b|, [B] -- the magnitude of the terms a logit sums, i.e. the scale against which the rounding
+    error of that sum is meaningful when the terms cancel to a near-zero logit).
+
+    ``params["__wn__"]`` (optional, from :func:`normalised_weights`) supplies W / sigma computed once instead of per forward:
+    only bench.py's best-case eager baseline uses it (eval-mode sigma is the same in every forward).
 
     ``inplace_relu=True`` reproduces mimicry's ``nn.ReLU(True)`` aliasing in ``DBlock``: the
     residual branch runs first and rectifies ``x`` in place, so the shortcut branch (the 1x1 conv,
@@ -137,7 +148,11 @@ def forward(params: dict, x: torch.Tensor, arch: int = 32, inplace_relu: bool = 
     h = F.relu(h)
     h = torch.sum(h, dim=(2, 3))
     head = ARCH[arch]["head"]
-    return F.linear(h, sn_weight(params, head), params[f"{head}.bias"])
+    w, b = (params["__wn__"][head] if "__wn__" in params else sn_weight(params, head)), params[f"{head}.bias"]
+    out = F.linear(h, w, b)
+    if with_head_l1:
+        return out, (h.abs() * w.abs().view(1, -1)).sum(1) + b.abs().view(-1)
+    return out
 
 
 def normalise_u8(x_u8_nhwc: torch.Tensor) -> torch.Tensor:
@@ -147,17 +162,23 @@ def normalise_u8(x_u8_nhwc: torch.Tensor) -> torch.Tensor:
 
 
 def logits_pass(params, data_u8_nhwc: torch.Tensor, arch=32, batch=64, inplace_relu=True,
-                dtype=torch.float32) -> np.ndarray:
+                dtype=torch.float32, device=None, with_head_l1=False):
     """The recording pass of trainer.py:142-156 on an in-memory dataset, sequential batches of 64:
     float64 [N] with fp32 values widened, indexed by dataset index.  ``dtype=torch.float64`` evaluates
     the same network in double precision (the exact-arithmetic yardstick the parity tests use to
-    separate the GPU's rounding error from the fp32 CPU path's own)."""
+    separate the GPU's rounding error from the fp32 CPU path's own).  ``device``: where the checker's own arithmetic
+    runs (the float64 evaluation of thousands of samples is run on the GPU by the BASELINE-size tests; still torch, still
+    the restatement above, never the product's kernels).  ``with_head_l1``: -> (logits, head L1 mass), see forward()."""
     n = data_u8_nhwc.shape[0]
-    out = np.zeros(n)
-    if dtype != torch.float32:
-        params = {k: v.to(dtype) for k, v in params.items()}
+    out, l1 = np.zeros(n), np.zeros(n)
+    if dtype != torch.float32 or device is not None:
+        params = {k: v.to(device=device, dtype=dtype) for k, v in params.items()}
     with torch.no_grad():
         for s in range(0, n, batch):
-            x = normalise_u8(data_u8_nhwc[s:s + batch]).to(dtype)
-            out[s:s + batch] = forward(params, x, arch, inplace_relu).view(-1).numpy()
-    return out
+            x = normalise_u8(data_u8_nhwc[s:s + batch].to(device) if device is not None else data_u8_nhwc[s:s + batch]).to(dtype)
+            y = forward(params, x, arch, inplace_relu, with_head_l1=with_head_l1)
+            if with_head_l1:
+                out[s:s + batch], l1[s:s + batch] = y[0].view(-1).cpu().numpy(), y[1].view(-1).cpu().numpy()
+            else:
+                out[s:s + batch] = y.view(-1).cpu().numpy()
+    return (out, l1) if with_head_l1 else out

@@ -81,8 +81,9 @@ def eq_conv(x, w, stride=1, padding=0, bias=None):
     return F.conv2d(x, w * scale, bias=bias, stride=stride, padding=padding)
 
 
-def forward(params: dict, x: torch.Tensor, size: int) -> torch.Tensor:
-    """x: one reference batch, float NCHW [B,3,size,size] in [-1,1] -> logits [B,1]."""
+def forward(params: dict, x: torch.Tensor, size: int, with_head_l1: bool = False):
+    """x: one reference batch, float NCHW [B,3,size,size] in [-1,1] -> logits [B,1]  (``with_head_l1``: also
+    sum_j |w_j * h_j| + |b| of the last EqualLinear, [B]: the magnitude of the terms the logit sums)."""
     p = params
     h = flrelu(eq_conv(x, p["convs.0.0.weight"]), p["convs.0.1.bias"])
     for i, _ in enumerate(block_channels(size), start=1):
@@ -102,19 +103,28 @@ def forward(params: dict, x: torch.Tensor, size: int) -> torch.Tensor:
     w0 = p["final_linear.0.weight"]
     h = flrelu(F.linear(h, w0 * (1 / math.sqrt(w0.shape[1]))), p["final_linear.0.bias"])
     w1 = p["final_linear.1.weight"]
-    return F.linear(h, w1 * (1 / math.sqrt(w1.shape[1])), bias=p["final_linear.1.bias"])
+    out = F.linear(h, w1 * (1 / math.sqrt(w1.shape[1])), bias=p["final_linear.1.bias"])
+    if with_head_l1:
+        return out, (h.abs() * (w1.abs() * (1 / math.sqrt(w1.shape[1]))).view(1, -1)).sum(1) + p["final_linear.1.bias"].abs().view(-1)
+    return out
 
 
-def logits_pass(params, data_u8_nhwc: torch.Tensor, size: int, batch: int, dtype=torch.float32) -> np.ndarray:
+def logits_pass(params, data_u8_nhwc: torch.Tensor, size: int, batch: int, dtype=torch.float32, device=None,
+                with_head_l1=False):
     """Recording pass over an in-memory dataset in consecutive batches of ``batch`` (stylegan2/train_ffhq.py:128-143
     with a sequential, un-flipped loader; the tail that does not fill a batch is dropped like drop_last=True)."""
     from .sngan import normalise_u8
     n = data_u8_nhwc.shape[0] // batch * batch
-    out = np.zeros(data_u8_nhwc.shape[0])
-    if dtype != torch.float32:
-        params = {k: v.to(dtype) for k, v in params.items()}
+    out, l1 = np.zeros(data_u8_nhwc.shape[0]), np.zeros(data_u8_nhwc.shape[0])
+    if dtype != torch.float32 or device is not None:
+        params = {k: v.to(device=device, dtype=dtype) for k, v in params.items()}
     with torch.no_grad():
         for s in range(0, n, batch):
-            x = normalise_u8(data_u8_nhwc[s:s + batch]).to(dtype)
-            out[s:s + batch] = forward(params, x, size).view(-1).numpy()
-    return out
+            xb = data_u8_nhwc[s:s + batch]
+            x = normalise_u8(xb.to(device) if device is not None else xb).to(dtype)
+            y = forward(params, x, size, with_head_l1=with_head_l1)
+            if with_head_l1:
+                out[s:s + batch], l1[s:s + batch] = y[0].view(-1).cpu().numpy(), y[1].view(-1).cpu().numpy()
+            else:
+                out[s:s + batch] = y.view(-1).cpu().numpy()
+    return (out, l1) if with_head_l1 else out

@@ -121,6 +121,23 @@ def test_stylegan2_oracle_matches_reference(golden_dir, size):
     assert sg2_oracle.block_channels(256) == [(128, 256), (256, 512), (512, 512), (512, 512), (512, 512), (512, 512)]
 
 
+def sg2_256_inputs(g):
+    """The d256 fixture stores a seed instead of 1.5 MB of random bytes (oracle/make_golden.py:make_stylegan2_256)."""
+    x = np.random.RandomState(int(g["x_seed"])).randint(0, 256, (int(g["n"]), 256, 256, 3)).astype(np.uint8)
+    assert int(x.astype(np.int64).sum()) == int(g["x_checksum"])
+    return x
+
+
+def test_stylegan2_256_oracle_matches_reference(golden_dir):
+    """BASELINE configs[4] at its own size: the restatement against logits of the reference StyleGANDiscriminator(256)."""
+    g = _load(golden_dir, "stylegan2_d256")
+    params = sg2_oracle.init_params(256, int(g["param_seed"]))
+    assert sum(float(np.sum(v.numpy().astype(np.float64))) for v in params.values()) == float(g["param_checksum"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    y = sg2_oracle.logits_pass(params, torch.from_numpy(sg2_256_inputs(g)), 256, int(g["batch"]))
+    np.testing.assert_allclose(y, g["logits"], rtol=2e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("h,w,size", [(28, 28, 32), (218, 178, 64), (45, 37, 32), (37, 45, 32), (100, 300, 64), (32, 32, 32),
                                       (64, 48, 64), (20, 20, 64)])
 def test_resize_oracle_bit_exact_vs_pillow(h, w, size):
