@@ -210,6 +210,13 @@ SDG_API int sdg_score_floor_min(const double* mean, const double* var, int64_t n
  * Between the phases a sharded caller all-reduces `mins` with MIN. */
 SDG_API int sdg_score_clip(double* score, int64_t n, int n_conf, const double* mins, double ratio, double eps,
                    void* stream);
+/* One-collective form for sample-index shards (the reference's precedent, stylegan2/train_ffhq.py:128-143,
+ * issues two all-gathers per batch of 4): every rank runs phase 1 on its shard with score = payload, mins = payload +
+ * shard_size, all-gathers the [shard_size + 1] doubles, and this call clips the gathered [world][shard_size + 1] buffer
+ * against the GLOBAL minimum (min over the world trailing slots) into the dense vector out [n]:
+ * out[i] = max(min(v_i, gmin * ratio), eps).  A rank with an empty shard contributes +inf as its minimum. */
+SDG_API int sdg_score_clip_gathered(const double* gathered, int world, int64_t shard_size, int64_t n, double ratio,
+                            double eps, double* out, void* stream);
 
 /* ---- top-index selection ---------------------------------------------------------------------
  * Replaces np.argsort(w)[-k:] / [:k] (eval_gan_drs_with_index.py:97-99, plot.py:100-101) with the

@@ -176,15 +176,41 @@ score_clip_kernel(double* __restrict__ score, int64_t n, const double* __restric
   }
 }
 
+// one-collective form of the sharded score: gathered = [world][shard + 1] doubles, slot r = rank r's floor-clipped shard
+// (padded to `shard`) followed by its local minimum; out[i] = max(min(v, gmin * ratio), eps) with gmin = min over the slots
+__global__ void __launch_bounds__(256)
+score_clip_gathered_kernel(const double* __restrict__ gathered, int world, int64_t shard, int64_t n, double ratio, double eps,
+                           double* __restrict__ out) {
+  __shared__ double s_min;
+  if (threadIdx.x == 0) {
+    double m = gathered[shard];
+    for (int r = 1; r < world; ++r) {
+      const double v = gathered[(int64_t)r * (shard + 1) + shard];
+      m = v < m ? v : m;
+    }
+    s_min = m;
+  }
+  __syncthreads();
+  const double upper = s_min * ratio;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / shard;
+    double v = gathered[r * (shard + 1) + (i - r * shard)];
+    v = v > upper ? upper : v;
+    if (eps > 0.0) v = v < eps ? eps : v;
+    out[i] = v;
+  }
+}
+
 }  // namespace sdg
 
 using namespace sdg;
 
 extern "C" int sdg_stats_update(const float* snapshot, double* mean, double* m2, double* last, double* sad,
                                 int64_t n, int64_t t, void* stream) {
-  SDG_REQUIRE(snapshot && mean && m2 && last && sad, SDG_E_INVALID, "sdg_stats_update: null pointer");
   SDG_REQUIRE(n >= 0 && t >= 0, SDG_E_INVALID, "sdg_stats_update: n=%lld t=%lld", (long long)n, (long long)t);
-  if (n == 0) return 0;
+  if (n == 0) return 0;          // an empty shard: torch hands out null pointers for empty tensors
+  SDG_REQUIRE(snapshot && mean && m2 && last && sad, SDG_E_INVALID, "sdg_stats_update: null pointer");
   auto al = [](const void* p, size_t a) { return ((uintptr_t)p % a) == 0; };
   int vec_ok = al(snapshot, 8) && al(mean, 16) && al(m2, 16) && al(last, 16) && al(sad, 16);
   int grid = stream_grid(cdiv(n, 2), 256);
@@ -217,7 +243,7 @@ extern "C" int sdg_window_moments_f64(const double* snaps, int64_t T, int64_t n,
 extern "C" int sdg_score_floor_min(const double* mean, const double* var, int64_t n, const double* conf_host,
                                    int n_conf, double floor, double var_is_m2_over, double* score, double* mins,
                                    void* stream) {
-  SDG_REQUIRE(mean && var && conf_host && score && mins, SDG_E_INVALID, "sdg_score_floor_min: null pointer");
+  SDG_REQUIRE(conf_host && mins && (n == 0 || (mean && var && score)), SDG_E_INVALID, "sdg_score_floor_min: null pointer");
   SDG_REQUIRE(n_conf >= 1 && n_conf <= 128, SDG_E_INVALID, "sdg_score_floor_min: n_conf=%d (1..128)", n_conf);
   SDG_REQUIRE(n >= 0, SDG_E_INVALID, "sdg_score_floor_min: n=%lld", (long long)n);
   ConfTable tab;
@@ -232,10 +258,20 @@ extern "C" int sdg_score_floor_min(const double* mean, const double* var, int64_
 
 extern "C" int sdg_score_clip(double* score, int64_t n, int n_conf, const double* mins, double ratio, double eps,
                               void* stream) {
-  SDG_REQUIRE(score && mins, SDG_E_INVALID, "sdg_score_clip: null pointer");
   SDG_REQUIRE(n_conf >= 1 && n >= 0, SDG_E_INVALID, "sdg_score_clip: n_conf=%d n=%lld", n_conf, (long long)n);
   if (n == 0) return 0;
+  SDG_REQUIRE(score && mins, SDG_E_INVALID, "sdg_score_clip: null pointer");
   int gx = stream_grid(n, 256, n_conf >= 8 ? 1 : 8);
   SDG_LAUNCH(score_clip_kernel, dim3(gx, n_conf), 256, 0, stream, score, n, mins, ratio, eps);
+  return 0;
+}
+
+extern "C" int sdg_score_clip_gathered(const double* gathered, int world, int64_t shard_size, int64_t n, double ratio,
+                                       double eps, double* out, void* stream) {
+  SDG_REQUIRE(gathered && out, SDG_E_INVALID, "sdg_score_clip_gathered: null pointer");
+  SDG_REQUIRE(world >= 1 && shard_size >= 1 && n >= 0 && n <= (int64_t)world * shard_size, SDG_E_INVALID,
+              "sdg_score_clip_gathered: world=%d shard=%lld n=%lld", world, (long long)shard_size, (long long)n);
+  if (n == 0) return 0;
+  SDG_LAUNCH(score_clip_gathered_kernel, stream_grid(n, 256, 8), 256, 0, stream, gathered, world, shard_size, n, ratio, eps, out);
   return 0;
 }

@@ -49,6 +49,7 @@ SIGNATURES = {
     "sdg_window_moments_f64": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "sdg_score_floor_min": (_i, [_vp, _vp, _i64, C.POINTER(_d), _i, _d, _d, _vp, _vp, _vp]),
     "sdg_score_clip": (_i, [_vp, _i64, _i, _vp, _d, _d, _vp]),
+    "sdg_score_clip_gathered": (_i, [_vp, _i, _i64, _i64, _d, _d, _vp, _vp]),
     "sdg_topk_workspace_bytes": (_sz, [_i64]),
     "sdg_topk_indices": (_i, [_vp, _i64, _i, _i, _vp, _vp, _sz, _vp]),
     "sdg_drs_update_max": (_i, [_vp, _i, _vp, _vp]),

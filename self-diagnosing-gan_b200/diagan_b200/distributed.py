@@ -198,6 +198,38 @@ def sharded_score(recorder, conf: float, eps: float = 0.0) -> torch.Tensor:
     return all_gather_shards(local, recorder.n, multiple=getattr(recorder, "shard_multiple", 1))
 
 
+def sharded_score_fused(stats, conf: float, n: int, eps: float = 0.0, multiple: int = 1, floor=None, ratio=None) -> torch.Tensor:
+    """The same vector as :func:`sharded_score` with ONE collective per call: each rank all-gathers its floor-clipped shard
+    with its local minimum appended, and the clip against the global minimum runs on the gathered buffer
+    (``sdg_score_clip_gathered``).  ``stats`` is this rank's :class:`diagan_b200.engine.RunningStats`."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import _lib, engine
+    lib = _lib.load()
+    floor = engine.FLOOR if floor is None else floor
+    ratio = engine.RATIO if ratio is None else ratio
+    world = get_world_size()
+    s = shard_size(n, world, multiple)
+    dev = stats.state.device
+    payload = torch.zeros(s + 1, dtype=torch.float64, device=dev)
+    cs = np.asarray([conf], dtype=np.float64)
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        _lib.check(lib.sdg_score_floor_min(_lib.ptr(stats.mean), _lib.ptr(stats.m2), stats.n,
+                                           cs.ctypes.data_as(C.POINTER(C.c_double)), 1, floor, float(stats.count - 1),
+                                           _lib.ptr(payload), _lib.ptr(payload[s:]), st), "sdg_score_floor_min")
+        gathered = payload
+        if world > 1:
+            gathered = torch.empty(world * (s + 1), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(gathered, payload)
+        out = torch.empty(n, dtype=torch.float64, device=dev)
+        _lib.check(lib.sdg_score_clip_gathered(_lib.ptr(gathered), world, s, n, ratio, eps, _lib.ptr(out), st),
+                   "sdg_score_clip_gathered")
+    return out
+
+
 def save_logit(logits_dict, output_path):
     """train_ffhq.py:145-147 (rank 0 calls it, :321-323)."""
     for name, logits in logits_dict.items():

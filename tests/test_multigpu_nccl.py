@@ -54,16 +54,30 @@ def _worker(rank, world, port, out_dir):
     want = solo.stats.score(t, eps=1e-6)
     assert torch.equal(got, want), "sharded score differs"
     assert torch.equal(engine.top_indices(got, 100, True), engine.top_indices(want, 100, True))
+    # one-collective form (local minimum rides in the all-gather payload): the same bits
+    assert torch.equal(D.sharded_score_fused(rec.stats, t, n, eps=1e-6), want)
+
+    # ---- an EMPTY shard (world > N): rank 1 owns nothing, must neither raise nor hang the collective ----
+    x1 = x[:1].contiguous()
+    r1 = LogitRecorder(ResidentDataset(x1), dev, keep_snapshots=False)
+    full1 = D.get_logit(r1, base)
+    assert full1.shape == (1,) and torch.equal(full1, LogitRecorder(ResidentDataset(x1), dev).record(base))
 
     # ---- StyleGAN2 (size 32, loader batch 4): shards are whole batches, logits identical to one GPU ----
-    n2 = 44
+    # n2 / world is NOT a multiple of the batch: shards of 24 and 22, the ragged tail (2) is dropped by rank 1
+    n2 = 46
     x2 = synthetic.uniform_images_u8(n2, 32, seed=2).to(dev)
     p2 = synthetic.stylegan2_state_dict(32, seed=3)
-    r2 = LogitRecorder(ResidentDataset(x2), dev, batch=4)
-    s2 = LogitRecorder(ResidentDataset(x2), dev, batch=4)
+    r2 = LogitRecorder(ResidentDataset(x2), dev, batch=4, keep_snapshots=False)
+    s2 = LogitRecorder(ResidentDataset(x2), dev, batch=4, keep_snapshots=False)
     lo2, hi2 = D.shard_range(n2, multiple=4)
-    assert lo2 % 4 == 0
-    assert torch.equal(D.get_logit(r2, p2), s2.record(p2))
+    assert lo2 % 4 == 0 and (lo2, hi2) == ((0, 24) if rank == 0 else (24, 46))
+    for step in (0, 100, 200):
+        pp = synthetic.perturb_(p2, step, 2e-2)
+        assert torch.equal(D.get_logit(r2, pp, step=step), s2.record(pp, step=step))
+    assert r2.shard_multiple == 4
+    t3 = engine.conf_from_key("ldr_conf_3.0_ratio_50")
+    assert torch.equal(D.sharded_score(r2, t3, eps=1e-6), s2.stats.score(t3, eps=1e-6))
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 
