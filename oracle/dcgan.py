@@ -49,8 +49,9 @@ def init_params(seed: int = 1, nc: int = 3) -> dict:
     return p
 
 
-def forward(params: dict, x: torch.Tensor) -> torch.Tensor:
-    """x float32 NCHW [B,3,32,32] (28x28 also accepted by the reference) -> logits [B,1]."""
+def forward(params: dict, x: torch.Tensor, with_head_l1: bool = False):
+    """x float32 NCHW [B,3,32,32] (28x28 also accepted by the reference) -> logits [B,1]  (``with_head_l1``: also
+    sum_j |w_j * h_j| + |b| of the Linear(8192, 1) head, [B]: the magnitude of the terms the logit sums)."""
     h = x
     for ci, bi, _, _, stride in LAYERS:
         h = F.conv2d(h, params[f"conv.{ci}.weight"], None, stride=stride, padding=1)
@@ -59,15 +60,26 @@ def forward(params: dict, x: torch.Tensor) -> torch.Tensor:
                              params[f"conv.{bi}.weight"], params[f"conv.{bi}.bias"], False, 0.1, BN_EPS)
         h = F.leaky_relu(h, SLOPE)
     h = h.reshape(-1, 4 * 4 * 512)
-    return F.linear(h, params["out_d.weight"], params["out_d.bias"])
+    out = F.linear(h, params["out_d.weight"], params["out_d.bias"])
+    if with_head_l1:
+        return out, (h.abs() * params["out_d.weight"].abs().view(1, -1)).sum(1) + params["out_d.bias"].abs().view(-1)
+    return out
 
 
-def logits_pass(params, data_u8_nhwc: torch.Tensor, batch=64) -> np.ndarray:
-    """trainer.py:142-156 over an in-memory uint8 NHWC 32x32 dataset (already resized)."""
+def logits_pass(params, data_u8_nhwc: torch.Tensor, batch=64, dtype=torch.float32, device=None, with_head_l1=False):
+    """trainer.py:142-156 over an in-memory uint8 NHWC 32x32 dataset (already resized).  ``dtype`` / ``device`` /
+    ``with_head_l1``: as in oracle/sngan.py:logits_pass (float64 yardstick, evaluated where the test wants)."""
     from .sngan import normalise_u8
     n = data_u8_nhwc.shape[0]
-    out = np.zeros(n)
+    out, l1 = np.zeros(n), np.zeros(n)
+    if dtype != torch.float32 or device is not None:
+        params = {k: v.to(device=device, dtype=dtype) for k, v in params.items()}
     with torch.no_grad():
         for s in range(0, n, batch):
-            out[s:s + batch] = forward(params, normalise_u8(data_u8_nhwc[s:s + batch])).view(-1).numpy()
-    return out
+            xb = data_u8_nhwc[s:s + batch]
+            y = forward(params, normalise_u8(xb.to(device) if device is not None else xb).to(dtype), with_head_l1=with_head_l1)
+            if with_head_l1:
+                out[s:s + batch], l1[s:s + batch] = y[0].view(-1).cpu().numpy(), y[1].view(-1).cpu().numpy()
+            else:
+                out[s:s + batch] = y.view(-1).cpu().numpy()
+    return (out, l1) if with_head_l1 else out

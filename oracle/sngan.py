@@ -182,3 +182,57 @@ def logits_pass(params, data_u8_nhwc: torch.Tensor, arch=32, batch=64, inplace_r
             else:
                 out[s:s + batch] = y.view(-1).cpu().numpy()
     return (out, l1) if with_head_l1 else out
+
+
+# ---------------------------------------------------------------------------------------------------
+# InfoMax-GAN / SSGAN discriminators (predefined_models.py:36-52,74-90 model='infomax_gan' | 'ssgan')
+# PARITY UNPINNED like the rest of this file: torch-mimicry 0.1.16 nets/infomax_gan/infomax_gan_{32,64}.py and
+# nets/ssgan/ssgan_{32,64}.py as recalled.  Both are the SNGAN residual stack; what differs is the attribute names of the
+# state_dict (InfoMax) and the extra outputs of forward(), of which the diagnosis path keeps [0] (trainer.py:151-152).
+# ---------------------------------------------------------------------------------------------------
+def infomax_key_map(arch: int) -> dict:
+    n_blocks = len(ARCH[arch]["blocks"])
+    m = {f"local_feat_blocks.{i}": f"block{i + 1}" for i in range(n_blocks - 1)}
+    m["global_feat_blocks.0"] = f"block{n_blocks}"
+    m["linear"] = ARCH[arch]["head"]
+    return m
+
+
+def as_variant_state_dict(params: dict, arch: int, variant: str, seed: int = 7) -> dict:
+    """SNGAN-named parameters -> a state_dict with the key names (and extra heads) of the mimicry ``variant``:
+    'ssgan' adds the 4-way rotation head l_y; 'infomax' renames the blocks and adds the nrkhs critic layers."""
+    rng = np.random.RandomState(seed)
+    ndf = ARCH[arch]["ndf"]
+    r = lambda *shape: torch.from_numpy((0.05 * rng.standard_normal(shape)).astype(np.float32))
+    if variant == "ssgan":
+        out = dict(params)
+        out.update({"l_y.weight": r(4, ndf), "l_y.bias": r(4), "l_y.sn_u": r(1, 4), "l_y.sn_sigma": torch.ones(1)})
+        return out
+    assert variant == "infomax"
+    inv = {v: k for k, v in infomax_key_map(arch).items()}
+    out = {}
+    for k, v in params.items():
+        prefix = k.split(".")[0]
+        out[inv[prefix] + k[len(prefix):]] = v
+    nrkhs = 1024
+    for name, shape in (("local_nrkhs_a", (ndf, ndf, 1, 1)), ("local_nrkhs_b", (nrkhs, ndf, 1, 1)),
+                        ("local_nrkhs_sc", (nrkhs, ndf, 1, 1)), ("global_nrkhs_a", (ndf, ndf)),
+                        ("global_nrkhs_b", (nrkhs, ndf)), ("global_nrkhs_sc", (nrkhs, ndf))):
+        out[f"{name}.weight"], out[f"{name}.bias"] = r(*shape), r(shape[0])
+        out[f"{name}.sn_u"], out[f"{name}.sn_sigma"] = r(1, shape[0]), torch.ones(1)
+    return out
+
+
+def forward_variant(state_dict: dict, x: torch.Tensor, arch: int, variant: str, inplace_relu: bool = True):
+    """forward() of the mimicry InfoMax-GAN / SSGAN discriminator on its own state_dict: a TUPLE whose [0] is the [B,1]
+    logit -- (output, output_classes) for SSGAN, (output, local_feat, global_feat) for InfoMax-GAN."""
+    if variant == "ssgan":
+        out = forward(state_dict, x, arch, inplace_relu)
+        return out, None                       # the rotation logits are not on the diagnosis path
+    km = infomax_key_map(arch)
+    canon = {}
+    for k, v in state_dict.items():
+        prefix = ".".join(k.split(".")[:2]) if k.startswith(("local_feat_blocks", "global_feat_blocks")) else k.split(".")[0]
+        if prefix in km:
+            canon[km[prefix] + k[len(prefix):]] = v
+    return forward(canon, x, arch, inplace_relu), None, None

@@ -129,7 +129,7 @@ static int prof_end(sdg_ctx* c, cudaStream_t s, double flops) {
 static int64_t max_act_elems(const sdg_ctx* c) {
   // largest per-sample activation tensor (elements)
   int64_t m = 0;
-  if (c->arch == SDG_ARCH_DCGAN32) return 16 * 16 * 32;
+  if (c->arch == SDG_ARCH_DCGAN32) return c->precision == SDG_PREC_FP32 ? 16 * 16 * 32 : 16 * 16 * 64;
   int hw = c->size;
   for (auto& b : c->blocks) {
     int hidden = b.kind == 0 ? b.cout : b.cin;
@@ -375,13 +375,15 @@ extern "C" int sdg_dcgan_load(sdg_ctx* c, const float* const* conv_w, const floa
                               const float* fc_w, const float* fc_b, int precision, void* stream) {
   SDG_REQUIRE(c && conv_w && bn_gamma && bn_beta && bn_mean && bn_var && fc_w && fc_b, SDG_E_INVALID,
               "sdg_dcgan_load: null pointer");
-  SDG_REQUIRE(precision == SDG_PREC_FP32, SDG_E_UNSUPPORTED,
-              "sdg_dcgan_load: only SDG_PREC_FP32 is implemented for the DCGAN discriminator");
+  SDG_REQUIRE(precision == SDG_PREC_FP32 || precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID,
+              "sdg_dcgan_load: precision=%d", precision);
   cudaStream_t s = (cudaStream_t)stream;
   SDG_CUDA(cudaSetDevice(c->device));
   RangeScope range_scope(c->range_flag);
   c->loaded = false;
   c->arch = SDG_ARCH_DCGAN32; c->precision = precision; c->size = 32; c->blocks.clear();
+  const bool tc = precision != SDG_PREC_FP32;
+  if (tc) { int rc = conv_tc_init(c->device); if (rc) return rc; }
   if (c->convs.size() != 6) {
     for (auto& l : c->convs) l.release_all();
     c->convs.assign(6, ConvLayer());
@@ -391,20 +393,37 @@ extern "C" int sdg_dcgan_load(sdg_ctx* c, const float* const* conv_w, const floa
     ConvLayer& l = c->convs[i];
     l.cin = kDcganSpec[i][0]; l.cout = kDcganSpec[i][1]; l.stride = kDcganSpec[i][2]; l.ks = 3;
     SDG_REQUIRE(conv_w[i], SDG_E_INVALID, "sdg_dcgan_load: conv %d null", i);
-    { int rc = l.w32.ensure(sizeof(float) * 9 * l.cin * l.cout); if (rc) return rc; }
     const float* scale = nullptr;
     l.has_bias = i > 0;
+    // tensor-core path: conv 1 stays an fp32 CUDA-core kernel (K = 27); convs 2..6 run on tcgen05 with their channels padded
+    // to whole 64-channel TMA chunks (zero weights, zero bias: leaky_relu(0) = 0 keeps the padding channels at zero), the
+    // eval-mode BatchNorm folded into weights and bias, and 1/sqrt(2) folded into both so that the FusedLeakyReLU epilogue
+    // (leaky_relu(., 0.2) * sqrt(2), positively homogeneous) evaluates the plain LeakyReLU(0.2) of mnist.py:164
+    const bool h = tc && i > 0;
+    const float mul = h ? 0.70710678118654752f : 1.0f;
+    const int cout_p = h ? (l.cout + 63) / 64 * 64 : l.cout, cin_p = h ? (l.cin + 63) / 64 * 64 : l.cin;
     if (i > 0) {
       SDG_REQUIRE(bn_gamma[i - 1] && bn_beta[i - 1] && bn_mean[i - 1] && bn_var[i - 1], SDG_E_INVALID,
                   "sdg_dcgan_load: bn %d null", i);
-      { int rc = l.bias.ensure(sizeof(float) * l.cout); if (rc) return rc; }
+      { int rc = l.bias.ensure(sizeof(float) * cout_p); if (rc) return rc; }
+      if (cout_p != l.cout) SDG_CUDA(cudaMemsetAsync(l.bias.p, 0, sizeof(float) * cout_p, s));
       int rc = bn_fold(bn_gamma[i - 1], bn_beta[i - 1], bn_mean[i - 1], bn_var[i - 1], 1e-5f,
-                       c->bn_scratch.as<float>(), l.bias.as<float>(), l.cout, s);
+                       c->bn_scratch.as<float>(), l.bias.as<float>(), l.cout, s, mul);
       if (rc) return rc;
       scale = c->bn_scratch.as<float>();
     }
-    int rc = pack_conv_fp32(conv_w[i], nullptr, scale, l.w32.as<float>(), l.cout, l.cin, 3, s);
-    if (rc) return rc;
+    if (h) {
+      l.kpad = l.ktot = 9 * cin_p;
+      { int rc = l.w16.ensure(sizeof(h16) * (size_t)l.ktot * cout_p); if (rc) return rc; }
+      if (cout_p != l.cout) SDG_CUDA(cudaMemsetAsync(l.w16.p, 0, sizeof(h16) * (size_t)l.ktot * cout_p, s));
+      int rc = pack_conv_h16(conv_w[i], nullptr, scale, l.w16.as<h16>(), l.cout, cin_p, l.kpad, 3, precision == SDG_PREC_FP16,
+                             l.ktot, 0, s, 1.0f, l.cin);
+      if (rc) return rc;
+    } else {
+      { int rc = l.w32.ensure(sizeof(float) * 9 * l.cin * l.cout); if (rc) return rc; }
+      int rc = pack_conv_fp32(conv_w[i], nullptr, scale, l.w32.as<float>(), l.cout, l.cin, 3, s);
+      if (rc) return rc;
+    }
   }
   c->head_len = 8192;
   { int rc = c->head_w.ensure(sizeof(float) * 8192); if (rc) return rc; }
@@ -561,6 +580,35 @@ static int forward_dcgan_fp32(sdg_ctx* c, const void* x, int layout, int64_t nb,
   return head_dot_fp32(in, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, c->head_len, s);
 }
 
+// DCGAN discriminator on the tensor cores (mnist.py:161-192, eval mode): conv 1 from the image bytes on CUDA cores, convs 2..6
+// as tcgen05 implicit GEMMs (stride-2 layers through the TMA traversal stride, BatchNorm + LeakyReLU in the epilogue), the
+// 8192 -> 1 Linear head as an fp32 dot product over the fp32 output of conv 6.
+static int forward_dcgan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, float* logits, cudaStream_t s) {
+  const int f16 = c->precision == SDG_PREC_FP16;
+  h16* a = c->buf[0].as<h16>();
+  h16* b = c->buf[1].as<h16>();
+  float* f = c->buf[2].as<float>();
+  int rc;
+  if ((rc = dcgan_first_conv_h16(x, layout, c->convs[0].w32.as<float>(), a, nb, 32, f16, s))) return rc;
+  int hw = 16;
+  for (int i = 1; i < 6; ++i) {
+    const ConvLayer& l = c->convs[i];
+    const int cin_p = (l.cin + 63) / 64 * 64, cout_p = (l.cout + 63) / 64 * 64;
+    const int ho = l.stride == 2 ? hw / 2 : hw;
+    TcConv t;
+    t.n = nb; t.H = ho; t.W = ho; t.Cin = cin_p; t.Cout = cout_p; t.taps = 9;
+    t.in = a; t.wb = l.w16.as<h16>(); t.bias = l.bias.as<float>(); t.act = 1;
+    if (l.stride == 2) { t.stride = 2; t.in_H = hw; t.in_W = hw; }
+    if (i == 5) t.out_f32 = f; else t.out_raw = b;
+    if (i == 5 && (rc = prof_begin(c, s))) return rc;
+    if ((rc = conv_tc(t, f16, s))) return rc;
+    if (i == 5 && (rc = prof_end(c, s, 2.0 * (double)nb * ho * ho * l.cout * 9.0 * l.cin))) return rc;
+    hw = ho;
+    h16* tmp = a; a = b; b = tmp;
+  }
+  return head_dot_fp32(f, c->head_w.as<float>(), c->head_b.as<float>(), logits, nb, c->head_len, s);
+}
+
 extern "C" int sdg_d_forward(sdg_ctx* c, const void* x, int layout, int64_t n, float* logits_out, void* stream) {
   SDG_REQUIRE(c, SDG_E_INVALID, "sdg_d_forward: null context");
   SDG_REQUIRE(c->loaded, SDG_E_STATE, "sdg_d_forward: no discriminator weights loaded");
@@ -615,7 +663,11 @@ extern "C" int sdg_d_forward(sdg_ctx* c, const void* x, int layout, int64_t n, f
     }
   }
   if (chunk > n) chunk = n;
-  if (bf) {
+  if (bf && c->arch == SDG_ARCH_DCGAN32) {
+    // two 16-bit ping-pong buffers of [16,16,64] per sample, one fp32 [4,4,512]
+    for (int i = 0; i < 2; ++i) { int rc = c->buf[i].ensure((size_t)chunk * 16 * 16 * 64 * 2); if (rc) return rc; }
+    { int rc = c->buf[2].ensure((size_t)chunk * 16 * 512 * 4); if (rc) return rc; }
+  } else if (bf) {
     // T: full-resolution relu(c1) of any block; hR/hW: block outputs 16-bit; hF: block outputs fp32
     int64_t t_el = 0, h_el = 0;
     int hw = S;
@@ -641,7 +693,8 @@ extern "C" int sdg_d_forward(sdg_ctx* c, const void* x, int layout, int64_t n, f
     const int64_t nb = (n - s0) < chunk ? (n - s0) : chunk;
     const void* xs = (const char*)x + (size_t)s0 * in_stride;
     int rc;
-    if (c->arch == SDG_ARCH_DCGAN32) rc = forward_dcgan_fp32(c, xs, layout, nb, logits_out + s0, s);
+    if (c->arch == SDG_ARCH_DCGAN32) rc = bf ? forward_dcgan_h16(c, xs, layout, nb, logits_out + s0, s)
+                                             : forward_dcgan_fp32(c, xs, layout, nb, logits_out + s0, s);
     else if (bf) rc = forward_sngan_h16(c, xs, layout, nb, logits_out + s0, s);
     else rc = forward_sngan_fp32(c, xs, layout, nb, logits_out + s0, s);
     if (rc) return rc;

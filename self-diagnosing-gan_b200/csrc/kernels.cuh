@@ -101,7 +101,8 @@ int sn_sigmas(const SnLayer* layers_dev, const SnLayer* layers_host, int n_layer
 int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float* wp, int Cout, int Cin, int ks,
                    cudaStream_t s, float mul = 1.0f);
 // wb[o*ld + col0 + k] = h16(W[o][c][tap] * scale[o] / sigma) at k = tap*Cin + c, zero padded up to Kpad columns
-// cin_w > 0: the weight tensor has cin_w >= Cin input channels and only the first Cin are packed
+// cin_w > 0: the weight tensor has cin_w input channels: cin_w >= Cin packs only the first Cin, cin_w < Cin pads the packed
+// layout's channels cin_w..Cin-1 with zeros (DCGAN: 16 / 32 real channels inside a 64-channel TMA chunk)
 int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* wb, int Cout, int Cin, int Kpad,
                   int ks, int f16, int ld, int col0, cudaStream_t s, float mul = 1.0f, int cin_w = 0);
 // pooled-3x3 weights for the 4x4 stride-2 form: wb[o*ld + (a*4+b)*Cin + c] = 0.25 * sum of W[o][c][ky][kx] / sigma over
@@ -116,8 +117,12 @@ int pack_superpix_h16(const h16* src, h16* dst, int Cout, int Cin, int ty, int t
 int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);          // out = a + b
 int scale_vec(const float* in, const float* sigma, float* out, int n, cudaStream_t s);   // out = in / sigma
 // BatchNorm(eval) folding: scale[o] = gamma/sqrt(var+eps), shift[o] = beta - mean*scale
+// mul scales both outputs (DCGAN tensor-core path: 1/sqrt(2) cancels the gain of the FusedLeakyReLU epilogue)
 int bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
-            float* shift, int C, cudaStream_t s);
+            float* shift, int C, cudaStream_t s, float mul = 1.0f);
+// DCGAN conv1 on the tensor-core path: out[n,S/2,S/2,64] 16-bit = leaky_relu(conv3x3 stride 2 pad 1 (normalise(x)), 0.2) in
+// channels 0..15, zeros in 16..63 (one 64-channel TMA chunk for the next layer); wp = pack_conv_fp32 layout [27][16]
+int dcgan_first_conv_h16(const void* x, int layout, const float* wp, h16* out, int64_t n, int S, int f16, cudaStream_t s);
 // DCGAN fc weight [C*HW] (NCHW flatten) -> NHWC flatten order
 int permute_fc(const float* w, float* out, int C, int HW, cudaStream_t s);
 

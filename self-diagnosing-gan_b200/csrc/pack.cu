@@ -132,10 +132,12 @@ pack_conv_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigm
     float w = 0.f;
     if (k < taps * Cin) {
       int tap = k / Cin, c = k - tap * Cin;
-      w = W[((int64_t)o * cin_w + c) * taps + tap];
-      if (sigma) w = w / sg;
-      if (scale) w = w * scale[o];
-      if (mul != 1.0f) w = w * mul;
+      if (c < cin_w) {                           // cin_w < Cin: the packed layout pads the input channels with zeros
+        w = W[((int64_t)o * cin_w + c) * taps + tap];
+        if (sigma) w = w / sg;
+        if (scale) w = w * scale[o];
+        if (mul != 1.0f) w = w * mul;
+      }
     }
     if (F16 && !(fabsf(w) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_WEIGHT);
     wb[(int64_t)o * ld + col0 + k] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
@@ -233,18 +235,20 @@ int scale_vec(const float* in, const float* sigma, float* out, int n, cudaStream
 }
 
 __global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
-                               float* scale, float* shift, int C) {
+                               float* scale, float* shift, int C, float mul) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < C) {
     float sc = gamma[i] / sqrtf(var[i] + eps);
+    float sh = beta[i] - mean[i] * sc;
+    if (mul != 1.0f) { sc *= mul; sh *= mul; }
     scale[i] = sc;
-    shift[i] = beta[i] - mean[i] * sc;
+    shift[i] = sh;
   }
 }
 
 int bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
-            float* shift, int C, cudaStream_t s) {
-  SDG_LAUNCH(bn_fold_kernel, (unsigned)cdiv(C, 256), 256, 0, s, gamma, beta, mean, var, eps, scale, shift, C);
+            float* shift, int C, cudaStream_t s, float mul) {
+  SDG_LAUNCH(bn_fold_kernel, (unsigned)cdiv(C, 256), 256, 0, s, gamma, beta, mean, var, eps, scale, shift, C, mul);
   return 0;
 }
 

@@ -69,9 +69,40 @@ def sngan_layer_keys(arch: int):
     return keys + [head]
 
 
+# torch-mimicry InfoMaxGANDiscriminator32/64 (predefined_models.py:36-52,74-90: model='infomax_gan') hold the SAME residual
+# stack as SNGANDiscriminator32/64 under other attribute names: local_feat_blocks = Sequential(block1 .. block(n-1)),
+# global_feat_blocks = Sequential(last block), linear = the SNLinear head; forward returns (output, local_feat, global_feat)
+# and the diagnosis path keeps [0] (trainer.py:151-152).  SSGANDiscriminator32/64 ARE the SNGAN stacks plus a rotation head
+# l_y whose output is dropped the same way.  [torch-mimicry 0.1.16 sources as recalled: parity unpinned like SNGAN itself.]
+def _infomax_key_map(arch: int) -> dict:
+    n_blocks = 4 if arch == 32 else 5
+    m = {f"local_feat_blocks.{i}": f"block{i + 1}" for i in range(n_blocks - 1)}
+    m["global_feat_blocks.0"] = f"block{n_blocks}"
+    m["linear"] = "l5" if arch == 32 else "l6"
+    return m
+
+
+def canonical_sngan_state_dict(state_dict, kind: str) -> dict:
+    """state_dict of an InfoMax-GAN / SSGAN discriminator -> the SNGAN key names the engine loads (tensors shared, extra
+    heads -- l_y, the nrkhs critics -- dropped)."""
+    if kind.startswith("infomax"):
+        out = {}
+        for old, new in _infomax_key_map(int(kind[7:])).items():
+            for k, v in state_dict.items():
+                if k.startswith(old + "."):
+                    out[new + k[len(old):]] = v
+        return out
+    return state_dict
+
+
 def detect_arch(state_dict) -> str:
-    """'sngan32' | 'sngan64' | 'dcgan32' from parameter names (mimicry / reference state_dict layouts)."""
+    """'sngan32' | 'sngan64' | 'ssgan32' | 'ssgan64' | 'infomax32' | 'infomax64' | 'dcgan32' | 'stylegan2' from parameter
+    names (mimicry / reference state_dict layouts)."""
     keys = set(state_dict.keys())
+    if "local_feat_blocks.0.c1.weight" in keys and "global_feat_blocks.0.c1.weight" in keys and "linear.weight" in keys:
+        return "infomax64" if "local_feat_blocks.3.c1.weight" in keys else "infomax32"
+    if "l_y.weight" in keys and "block1.c_sc.weight" in keys:
+        return "ssgan64" if "l6.weight" in keys else "ssgan32"
     if "conv.0.weight" in keys and "out_d.weight" in keys:
         return "dcgan32"
     if "final_conv.0.weight" in keys and "convs.0.0.weight" in keys:
@@ -80,8 +111,8 @@ def detect_arch(state_dict) -> str:
         return "sngan64"
     if "l5.weight" in keys and "block4.c1.weight" in keys and "block1.c_sc.weight" in keys:
         return "sngan32"
-    raise _lib.SdgError("unsupported discriminator: expected torch-mimicry SNGANDiscriminator32/64, the reference's "
-                        "MNIST_DCGAN_Discriminator or its StyleGANDiscriminator state_dict")
+    raise _lib.SdgError("unsupported discriminator: expected torch-mimicry SNGAN / SSGAN / InfoMax-GAN Discriminator32/64, the "
+                        "reference's MNIST_DCGAN_Discriminator or its StyleGANDiscriminator state_dict")
 
 
 def stylegan2_tensor_keys(state_dict):
@@ -159,7 +190,9 @@ class DiscriminatorEngine:
         self.arch, self.size, self.n_layers = f"sngan{arch}", arch, len(keys)
         return self
 
-    def load_dcgan(self, state_dict, precision: str = "fp32"):
+    def load_dcgan(self, state_dict, precision: str = "fp16"):
+        """MNIST_DCGAN_Discriminator, eval mode.  fp16 / bf16: convs 2..6 on tcgen05 (BatchNorm folded, LeakyReLU in the
+        epilogue); fp32: the exact CUDA-core engine (the 1e-5 parity mode)."""
         conv_idx = [0, 3, 7, 11, 15, 19]
         bn_idx = [4, 8, 12, 16, 20]
         W = [self._dev(state_dict[f"conv.{i}.weight"]) for i in conv_idx]
@@ -200,10 +233,11 @@ class DiscriminatorEngine:
     def load(self, state_dict, precision: str = None, inplace_relu: bool = True):
         kind = detect_arch(state_dict)
         if kind == "dcgan32":
-            return self.load_dcgan(state_dict, precision or "fp32")
+            return self.load_dcgan(state_dict, precision or "fp16")
         if kind == "stylegan2":
             return self.load_stylegan2(state_dict, precision or "fp16")
-        return self.load_sngan(state_dict, int(kind[5:]), precision or "fp16", inplace_relu)
+        arch = int(kind[-2:])                       # sngan / ssgan / infomax + 32 | 64: one residual stack, one engine
+        return self.load_sngan(canonical_sngan_state_dict(state_dict, kind), arch, precision or "fp16", inplace_relu)
 
     def sigmas(self) -> torch.Tensor:
         out = torch.empty(self.n_layers, dtype=torch.float32, device=self.device)

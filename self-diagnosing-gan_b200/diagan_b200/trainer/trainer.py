@@ -99,7 +99,6 @@ class LogitRecorder:
         # StyleGAN2 only: the loader batch size of the reference pass (stylegan2/train_ffhq.py:596-602); minibatch-stddev
         # groups live inside consecutive batches of this size and the ragged tail is dropped (drop_last=True)
         self.batch = batch
-        self.dcgan_precision = "fp32"             # the DCGAN discriminator's own default (exact CUDA-core engine)
         self.shard_multiple = 1                   # set by distributed.get_logit_resident (StyleGAN2: whole loader batches)
         # fp16 range guard: a pass during which a value left the fp16 range is re-run with this precision ("bf16" has the
         # fp32 range at 8x the rounding error; "fp32" is the exact CUDA-core engine, ~50x slower)
@@ -141,7 +140,7 @@ class LogitRecorder:
         if kind == "stylegan2":
             self.engine.load_stylegan2(sd, precision, batch=self.batch)
         else:
-            self.engine.load(sd, precision if kind != "dcgan32" else self.dcgan_precision, self.inplace_relu)
+            self.engine.load(sd, precision, self.inplace_relu)
 
     def record(self, netD, step=None, out: torch.Tensor = None, range_check="sync") -> torch.Tensor:
         """One recording pass over the resident dataset (this rank's shard) -> float32 [N] on the device.

@@ -67,6 +67,16 @@ def test_key_grammar_and_arch_detection():
     assert engine.detect_arch(sngan.init_params(32)) == "sngan32"
     assert engine.detect_arch(sngan.init_params(64)) == "sngan64"
     assert engine.detect_arch(dcgan.init_params()) == "dcgan32"
+    # InfoMax-GAN / SSGAN discriminators (predefined_models.py:36-52): the SNGAN stack under other names / with extra heads
+    for arch in (32, 64):
+        p = sngan.init_params(arch)
+        for variant in ("ssgan", "infomax"):
+            sd = sngan.as_variant_state_dict(p, arch, variant)
+            kind = engine.detect_arch(sd)
+            assert kind == f"{variant}{arch}"
+            canon = engine.canonical_sngan_state_dict(sd, kind)
+            for k in engine.sngan_layer_keys(arch):
+                assert canon[f"{k}.weight"] is p[f"{k}.weight"] and canon[f"{k}.sn_u"] is p[f"{k}.sn_u"]
     assert [k + ".weight" in sngan.init_params(32) for k in engine.sngan_layer_keys(32)] == [True] * 11
     assert len(engine.sngan_layer_keys(64)) == 16
     # layer order of the ABI == forward order of the oracle

@@ -121,6 +121,88 @@ def test_sngan_tensorcore_thousands_of_samples_vs_oracle(arch, n, seed, dev):
 
 
 # ---------------------------------------------------------------------------------------------------
+# InfoMax-GAN / SSGAN discriminators (tuple outputs) through the same engine
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("arch", [32, 64])
+@pytest.mark.parametrize("variant", ["ssgan", "infomax"])
+def test_infomax_and_ssgan_discriminators(arch, variant, dev):
+    """predefined_models.py:36-52,74-90 build InfoMaxGANDiscriminator / SSGANDiscriminator for model='infomax_gan' | 'ssgan';
+    their forward returns a tuple and trainer.py:151-152 keeps [0].  The engine must take their state_dicts as they are and
+    return exactly that element."""
+    from diagan_b200 import engine, synthetic
+    from diagan_b200.trainer.trainer import LogitRecorder, ResidentDataset, _unsupported_reason
+    n = 130
+    x = synthetic.uniform_images_u8(n, arch, seed=5)
+    p = sngan_oracle.init_params(arch, seed=5)
+    sd = sngan_oracle.as_variant_state_dict(p, arch, variant)
+    assert _unsupported_reason(sd, eval_mode=True) is None
+    xf = sngan_oracle.normalise_u8(x)
+    with torch.no_grad():
+        out = sngan_oracle.forward_variant({k: v.double() for k, v in sd.items()}, xf.double(), arch, variant)
+    assert isinstance(out, tuple) and out[0].shape == (n, 1)
+    want = out[0].view(-1).numpy()
+    eng = engine.DiscriminatorEngine(dev)
+    got32 = eng.load(sd, "fp32").forward(x.to(dev)).cpu().numpy()
+    assert eng.arch == f"sngan{arch}"
+    err = np.abs(got32 - want) / np.maximum(np.abs(want), np.abs(want).mean())
+    assert err.max() <= 2e-5, err.max()
+    got16 = LogitRecorder(ResidentDataset(x.to(dev)), dev).record(sd)
+    plain = LogitRecorder(ResidentDataset(x.to(dev)), dev).record(p)
+    assert torch.equal(got16, plain)                         # the same packed weights, the same kernels, the same bits
+
+
+# ---------------------------------------------------------------------------------------------------
+# configs[0]: MNIST-DCGAN discriminator on the tensor cores
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec,tolB", [("fp16", 2e-4), ("bf16", 3e-3)])
+def test_dcgan_tensorcore_vs_reference_golden(golden_dir, prec, tolB, dev):
+    """MNIST_DCGAN_Discriminator (eval) with convs 2..6 on tcgen05 against the logits of the reference module itself (golden)
+    and the float64 oracle; both input layouts; sweep-size invariance."""
+    from diagan_b200 import engine
+    from oracle import dcgan as dcgan_oracle
+    g = np.load(os.path.join(golden_dir, "dcgan_eval.npz"))
+    params = dcgan_oracle.init_params(int(g["param_seed"]))
+    x = torch.from_numpy(g["x_u8"])
+    eng = engine.DiscriminatorEngine(dev).load_dcgan(params, prec)
+    got = eng.forward(x.to(dev)).cpu().numpy().astype(np.float64)
+    assert eng.range_status() == 0
+    want, l1 = dcgan_oracle.logits_pass(params, x, dtype=torch.float64, with_head_l1=True)
+    m = _measures(got, want, l1)
+    mg = _measures(got, g["logits"], l1)
+    torch.backends.cudnn.allow_tf32 = True
+    mtf = _measures(dcgan_oracle.logits_pass(params, x, device=dev), want, l1)
+    print(f"dcgan {prec} vs float64 oracle: {_fmt(m)}; vs reference-module golden A {mg['A']:.2e} B {mg['B']:.2e} | torch-eager "
+          f"TF32: A {mtf['A']:.2e} B {mtf['B']:.2e}")
+    assert m["B"] <= tolB and mg["B"] <= tolB
+    if prec == "fp16":
+        assert m["A"] <= 1e-3 or m["B"] <= 1.25 * mtf["B"]
+    xf = sngan_oracle.normalise_u8(x).contiguous().to(dev)
+    assert np.array_equal(eng.forward(xf).cpu().numpy().astype(np.float64), got)
+    eng.set_chunk(7)
+    assert np.array_equal(eng.forward(x.to(dev)).cpu().numpy().astype(np.float64), got)
+
+
+def test_dcgan_tensorcore_full_config0_size(dev):
+    """configs[0] at its own size: 10 000 Colour-MNIST-shaped samples, one recording pass, fp16 tensor-core engine vs the
+    float64 oracle (evaluated on the GPU) and vs the exact fp32 engine; odd tail sizes."""
+    from diagan_b200 import engine, synthetic
+    from oracle import dcgan as dcgan_oracle
+    n = 10_000
+    x = synthetic.uniform_images_u8(n, 32, seed=3)
+    params = dcgan_oracle.init_params(seed=6)
+    eng = engine.DiscriminatorEngine(dev).load_dcgan(params, "fp16")
+    got = eng.forward(x.to(dev))
+    want, l1 = dcgan_oracle.logits_pass(params, x, batch=1000, dtype=torch.float64, device=dev, with_head_l1=True)
+    m = _measures(got.cpu().numpy(), want, l1)
+    print(f"dcgan fp16 n={n} vs float64 oracle: {_fmt(m)}")
+    assert m["B"] <= 2e-4
+    exact = engine.DiscriminatorEngine(dev).load_dcgan(params, "fp32").forward(x.to(dev))
+    assert _measures(exact.cpu().numpy(), want, l1)["A"] <= 1e-5
+    for k in (1, 3, 9, 130):                                   # ragged sizes: per-sample logits do not depend on the batch
+        assert torch.equal(eng.forward(x[:k].contiguous().to(dev)), got[:k])
+
+
+# ---------------------------------------------------------------------------------------------------
 # configs[1]: score stage at [50, 50 000], bit for bit
 # ---------------------------------------------------------------------------------------------------
 def test_score_stage_50x50000_bit_exact_vs_oracle(dev):

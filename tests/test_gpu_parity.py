@@ -316,7 +316,7 @@ def test_dcgan_fp32_vs_reference_golden(golden_dir, dev):
     from diagan_b200 import engine
     g = _load(golden_dir, "dcgan_eval")
     params = dcgan_oracle.init_params(int(g["param_seed"]))
-    eng = engine.DiscriminatorEngine(dev).load(params)
+    eng = engine.DiscriminatorEngine(dev).load(params, "fp32")
     assert eng.arch == "dcgan32"
     x = torch.from_numpy(g["x_u8"]).to(dev)
     y = eng.forward(x).cpu().numpy()

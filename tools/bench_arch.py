@@ -35,7 +35,7 @@ def main():
         flop = FLOP[a.arch]
     elif a.arch == "dcgan32":
         size = 32
-        eng.load_dcgan(synthetic.dcgan_state_dict(1))
+        eng.load_dcgan(synthetic.dcgan_state_dict(1), a.precision)
         flop = FLOP[a.arch]
     else:
         size = a.size
@@ -57,7 +57,7 @@ def main():
     ms = e0.elapsed_time(e1) / a.iters
     rate = a.n / ms * 1e3
     extra = f", {rate * flop / 1e12:.1f} TFLOP/s (reference-formulation FLOPs)" if flop else ""
-    print(f"{a.arch} size={size} n={a.n} {a.precision if a.arch != 'dcgan32' else 'fp32'}: {ms:.2f} ms/pass, "
+    print(f"{a.arch} size={size} n={a.n} {a.precision}: {ms:.2f} ms/pass, "
           f"{rate:,.0f} samples/s{extra}")
 
 
