@@ -641,6 +641,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_slot), TC_TMEM_COLS);
   tc_fence_before();
+  __syncthreads();                                      // CTA-level ordering of tcgen05.alloc's write of tmem_base_slot (what
+                                                        // compute-sanitizer racecheck models; the cluster barrier alone is
+                                                        // sufficient on hardware, see profiles/r2_racecheck_triage.md)
   cluster_sync_all();                                   // barriers of both CTAs initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
@@ -802,6 +805,7 @@ conv_pair_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_slot), tmem_cols);
   tc_fence_before();
+  __syncthreads();                                      // see conv_pair_kernel: CTA-level ordering for racecheck's model
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
