@@ -82,6 +82,7 @@ struct TcParams {
   const float* head_b;
   float* head_out;           // [n_images] zero-initialised by the caller; at most two warps contribute per image
   const float* res_f32;      // identity shortcut, fp32 [out pixels][Cout] or null
+  const h16* res_h16;        // identity shortcut as a 16-bit tensor (role-swapped kernel only) or null
   const void* img;           // network input for the 3-FMA shortcut (DBlockOptimized) or null
   const float* sc_w3;        // [Cout][3] fp32, W_sc / sigma
   h16* out_relu;             // relu(v) 16-bit or null
@@ -641,9 +642,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_slot), TC_TMEM_COLS);
   tc_fence_before();
-  __syncthreads();                                      // CTA-level ordering of tcgen05.alloc's write of tmem_base_slot (what
-                                                        // compute-sanitizer racecheck models; the cluster barrier alone is
-                                                        // sufficient on hardware, see profiles/r2_racecheck_triage.md)
   cluster_sync_all();                                   // barriers of both CTAs initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
@@ -805,7 +803,6 @@ conv_pair_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_slot), tmem_cols);
   tc_fence_before();
-  __syncthreads();                                      // see conv_pair_kernel: CTA-level ordering for racecheck's model
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
@@ -1088,6 +1085,12 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const float* rp = p.res_f32 + (P0 + c0n) * CO + c;
 #pragma unroll
           for (int j = 0; j < 32; ++j) rnext[j] = __ldg(rp + j * CO);
+        } else if (p.res_h16 && c_ok && P0 + c0n < p.total_pixels) {
+          // 16-bit residual (mimicry's in-place ReLU makes the identity shortcut relu(h), which IS the stored conv operand):
+          // half the bytes of the fp32 stream, and no fp32 copy of the block output has to be written at all
+          const uint16_t* rp = p.res_h16 + (P0 + c0n) * CO + c;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rnext[j] = __uint_as_float((uint32_t)__ldg(rp + j * CO));      // raw bits, converted at use
         }
       };
       const int cbeg = half * 128, cend = cbeg + 128;
@@ -1126,6 +1129,12 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (p.res_f32) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += p.res_relu ? fmaxf(rv[j], 0.f) : rv[j];
+          } else if (p.res_h16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float r16 = unpack_h2<F16>(__float_as_uint(rv[j]) & 0xffffu).x;
+              v[j] += p.res_relu ? fmaxf(r16, 0.f) : r16;
+            }
           }
           if (p.out_scale != 1.0f) {
 #pragma unroll
@@ -1311,8 +1320,9 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   SDG_REQUIRE(!a.head_out || (a.head_w && a.head_b && Cout == 128 && !a.pool && !a.img && (H * W == 32 || H * W == 64) && !a.gemm),
               SDG_E_UNSUPPORTED, "conv_tc: fused head needs Cout = 128, an un-pooled stage and 32 or 64 pixels per image");
   auto al16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
-  SDG_REQUIRE(al16(a.in) && al16(a.wb) && al16(a.sc_in) && al16(a.res_f32) && al16(a.out_relu) && al16(a.out_raw) &&
-                  al16(a.out_f32), SDG_E_INVALID, "conv_tc: pointers must be 16-byte aligned");
+  SDG_REQUIRE(al16(a.in) && al16(a.wb) && al16(a.sc_in) && al16(a.res_f32) && al16(a.res_h16) && al16(a.out_relu) &&
+                  al16(a.out_raw) && al16(a.out_f32), SDG_E_INVALID, "conv_tc: pointers must be 16-byte aligned");
+  SDG_REQUIRE(!(a.res_f32 && a.res_h16), SDG_E_INVALID, "conv_tc: one residual tensor at most");
   if (a.n == 0) return 0;
   // H, W describe the GEMM's M grid for a stride-1 conv and for pool4 (where the grid is H/2 x W/2); for an explicit
   // stride-2 conv they are the OUTPUT grid and in_H / in_W give the input tensor's extent
@@ -1378,7 +1388,7 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   p.debug_skip_epi = dbg_skip_epi;
   p.n_images = a.n;
   p.total_pixels = a.n * Hc * Wc;
-  p.bias = a.bias; p.sd = a.sd; p.sd_w = a.sd_w; p.res_f32 = a.res_f32;
+  p.bias = a.bias; p.sd = a.sd; p.sd_w = a.sd_w; p.res_f32 = a.res_f32; p.res_h16 = a.res_h16;
   p.head_w = a.head_w; p.head_b = a.head_b; p.head_out = a.head_out; p.img = a.img; p.sc_w3 = a.sc_w3;
   p.out_relu = a.out_relu; p.out_raw = a.out_raw; p.out_f32 = a.out_f32;
   p.ovf = t_range_flag;
@@ -1397,8 +1407,11 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   // role-swapped kernel (N = 256 pixels per MMA) for Cout = 128 layers with a "linear" epilogue
   static const int swap_mode = getenv("SDG_SWAP") ? atoi(getenv("SDG_SWAP")) : 1;     // SDG_SWAP=0: A/B against the pixel-major kernels
   static const int swap64 = getenv("SDG_SWAP64") ? atoi(getenv("SDG_SWAP64")) : 0;
+  // (a single 128-pixel box is allowed when the 16-bit residual is used, which only this kernel implements: the second box
+  // of the tile then lies beyond the tensor and is zero filled)
   if (swap_mode && g_pair_mode == 1 && (Cout == 128 || (swap64 && Cout == 64)) && !p.pool && !p.box16 && !p.sc_sep && !a.sd &&
-      !a.gemm && p.m_tiles >= 2 && p.total_pixels % 32 == 0 && (!a.head_out || (256 % (Hc * Wc) == 0 && Hc * Wc >= 32))) {
+      !a.gemm && (p.m_tiles >= 2 || a.res_h16) && p.total_pixels % 32 == 0 &&
+      (!a.head_out || (256 % (Hc * Wc) == 0 && Hc * Wc >= 32))) {
     // Cout = 64 (SDG_SWAP64=1, experiment): the weight box still has 128 rows; rows 64..127 lie outside the tensor and are
     // zero filled by TMA, so the M = 128 instruction runs half empty and N stays 256
     CUtensorMap map_w;
@@ -1411,6 +1424,8 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
     else { SDG_LAUNCH(conv_swap_kernel<false>, grid, SW_THREADS, kSwapSmem, s, map_a, map_w, map_s, p, sw_stages); }
     return 0;
   }
+  SDG_REQUIRE(!a.res_h16, SDG_E_UNSUPPORTED, "conv_tc: the 16-bit residual needs the role-swapped kernel (Cout = 128, linear "
+              "epilogue, pixel count a multiple of 32)");
   static const int stream_all = getenv("SDG_PAIR_STREAM128") ? atoi(getenv("SDG_PAIR_STREAM128")) == 2 : 0;
   if (g_pair_mode && Cout == 128 && taps == 9 && k_iters <= PAIR_MAX_KI && p.m_tiles >= 2 && !p.sc_sep && !stream_all) {
     // CTA-pair kernel: weights resident (64 rows per CTA), A streamed through as many 16 KB stages as fit

@@ -501,9 +501,16 @@ static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, 
     a2.in = T; a2.wb = c2.w16.as<h16>(); a2.bias = c2.bias_sum.as<float>();
     a2.pool = bl.down;
     a2.pool4 = c2.pool4;
+    // mimicry's in-place ReLU (the default) makes an identity shortcut add relu(h), which is exactly the 16-bit tensor the
+    // next conv reads anyway: blocks with an identity shortcut then take their residual from it and NO fp32 copy of a block
+    // output is needed (half the epilogue bytes of those layers).  Only the role-swapped kernel implements it.
+    static const int res16_env = getenv("SDG_RES16") ? atoi(getenv("SDG_RES16")) : 1;
+    const bool res16 = res16_env && c->inplace_relu && conv_tc_swap_active();
+    const bool next_identity_res16 = !last && !next_sc && res16 && c->blocks[bi + 1].cout == 128 &&
+                                     ((int64_t)nb * ho * ho) % 32 == 0;
     a2.out_relu = last ? nullptr : hR[o];
     a2.out_raw = (next_sc && !c->inplace_relu) ? hW[o] : nullptr;
-    a2.out_f32 = (last || !next_sc) ? hF[o] : nullptr;
+    a2.out_f32 = (last || (!next_sc && !next_identity_res16)) ? hF[o] : nullptr;
     // last block of SNGAN-32 (8x8, 128 channels, identity shortcut): ReLU -> sum-pool -> SNLinear fused into the epilogue
     static const int fuse_head_env = getenv("SDG_FUSE_HEAD") ? atoi(getenv("SDG_FUSE_HEAD")) : 1;
     const bool fuse_head = fuse_head_env && last && !bl.down && c2.cout == 128 && (ho * ho == 64 || ho * ho == 32) && bl.kind == 1;
@@ -548,6 +555,9 @@ static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, 
       if (has_sc) {                      // 1x1 shortcut conv folded into c2's K loop (input: relu(h) or h)
         a2.sc_in = c->inplace_relu ? hR[cur] : hW[cur];
         a2.sc_C = c->convs[i1 + 2].kpad;
+      } else if (res16 && c2.cout == 128 && ((int64_t)nb * hw * hw) % 32 == 0) {
+        a2.res_h16 = hR[cur];            // identity shortcut = relu(h), already stored as the 16-bit conv operand
+        a2.res_relu = 0;
       } else {                           // identity shortcut from the fp32 residual stream
         a2.res_f32 = hF[cur];
         a2.res_relu = c->inplace_relu;

@@ -163,6 +163,7 @@ struct TcConv {
   const float* head_b = nullptr;
   float* head_out = nullptr;
   const float* res_f32 = nullptr; // identity shortcut [n,Ho,Wo,Cout] fp32
+  const h16* res_h16 = nullptr;   // ... or as a 16-bit tensor (role-swapped kernel only; conv_tc rejects it elsewhere)
   int res_relu = 0;               // rectify the identity shortcut (mimicry's in-place ReLU aliasing)
   const void* img = nullptr;      // network input (DBlockOptimized: shortcut = Wsc3 . avg_pool2d(img) at pooled res)
   int img_layout = 0;
