@@ -32,6 +32,7 @@
 // Persistent CTAs (one per SM), static tile schedule, warp-specialised: warp 0 TMA producer, warp 1 MMA
 // issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
 #include <cstdlib>
+#include <cstring>
 
 #include "tc_ptx.cuh"
 
@@ -45,7 +46,20 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;     // 16 KB
 constexpr int TC_TMEM_COLS = 256;                 // 2 accumulator stages x up to 128 fp32 columns
 constexpr int TC_MAX_COUT = 1024;
 
+// Tap-shared operand schedule of conv_swap_shared_kernel: the pixel operand is loaded once per (64-channel chunk, column
+// variant) as a "copy" of rows+halo image rows, and the taps that differ only by a ROW shift read it through a shifted
+// descriptor start address (whole 1024-byte swizzle atoms, so no re-layout).
+struct ShSched {
+  int n_copy;                 // copies per 64-channel chunk (3: 3x3 stride 1; 8: the 4x4 stride-2 form)
+  int tpc;                    // taps per copy (3 / 2)
+  int copy_bytes;             // rows x tile width x 128 B actually loaded
+  int row_bytes;              // tile width x 128 B: one row shift of the descriptor start
+  signed char col0[8], row0[8];          // box origin of copy k in input pixel coordinates
+  signed char wtap[8][3], roff[8][3];    // tap j of copy k: index into the weight K layout, row shift inside the copy
+};
+
 struct TcParams {
+  ShSched sh;
   int H, W, Cin, Cout, taps;
   int kchunks;               // Cin / 64
   int sc_chunks;             // extra shortcut K iterations read through map_s (0 = none) = sc_taps * sc_kchunks
@@ -899,17 +913,6 @@ conv_pair_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Role-swapped kernel for Cout = 128 layers (every 3x3 conv of SNGAN-32, StyleGAN2's 256x256 conv1):
-//     D^T[128 channels, 256 pixels] = W[128, K] * A[256 pixels, K]^T
-// i.e. the WEIGHTS are the UMMA "A" operand (M = 128) and the pixel tile is the "B" operand with N = 256, so that one
-// tcgen05.mma covers 128 x 256 x 16 -- twice the work per instruction of the pixel-major kernels, whose N is capped at
-// Cout = 128.  Measured (profiles/r1e_ncu_full_pair_stream_summary.txt): N = 128 instructions keep the tensor pipe 55-58 %
-// busy, N = 256 instructions 95 %; the instruction, not shared-memory bandwidth, is the unit that has to be large.
-// The accumulator comes out transposed: TMEM lane = output channel, column = pixel.  That suits NHWC: for a fixed pixel the
-// 32 lanes of an epilogue warp hold 32 consecutive channels, so every global access of the epilogue (16-bit / fp32 stores,
-// fp32 residual loads) is a contiguous 64 / 128-byte segment with no shuffle transposes at all.
-// Per stage: weights 16 KB + two 128-pixel boxes 32 KB; 4 stages; accumulator 2 x 256 TMEM columns.
 constexpr int SW_STAGE = 3 * TC_A_BYTES;      // 48 KB
 constexpr int SW_STAGES = 4;
 constexpr int SW_EPI_WARPS = 8;
@@ -919,108 +922,13 @@ constexpr int kSwapSmem = 1024 + SW_STAGES * SW_STAGE;
 template <bool F16>
 __device__ __forceinline__ uint16_t to_h16(float v) { return (uint16_t)(pack_h2<F16>(v, 0.f) & 0xffffu); }
 
+// ---------------------------------------------------------------------------------------------------
+// epilogue of the role-swapped kernels (shared by conv_swap_kernel and conv_swap_shared_kernel): thread = output channel,
+// TMEM columns = the tile's 256 pixels
 template <bool F16>
-__global__ void __launch_bounds__(SW_THREADS, 1)
-conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_s, const TcParams p, const int n_stages) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-
-  __shared__ __align__(8) uint64_t bar_full[SW_STAGES];
-  __shared__ __align__(8) uint64_t bar_empty[SW_STAGES];
-  __shared__ __align__(8) uint64_t bar_acc_full[2];
-  __shared__ __align__(8) uint64_t bar_acc_empty[2];
-  __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_px[256 * 2 * 3];          // pooled normalised image pixels of the current tile (image shortcut; two per
-                                               // GEMM pixel in the super-pixel form)
-  __shared__ float s_head[4 * 8];              // per-warp partial logits of the (up to 8) images of the current tile
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
-    if (p.sc_chunks) tma_prefetch_desc(&map_s);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < SW_STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bar_acc_full[s]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[s]), SW_EPI_WARPS);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(smem_u32(&tmem_base_slot), 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
-
-  const long long tiles = (p.m_tiles + 1) >> 1;          // 256-pixel tiles = pairs of 128-pixel boxes
-  const int main_iters = p.taps * p.kchunks;
-  const int k_iters = main_iters + p.sc_chunks;
-
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        int n0[2], y0[2], x0[2];
-        tc_tile_origin(p, 2 * t, n0[0], y0[0], x0[0]);
-        tc_tile_origin(p, 2 * t + 1, n0[1], y0[1], x0[1]);      // beyond the last box: image index >= n, zero filled
-        int tap = 0, kc = 0;
-        for (int it = 0; it < k_iters; ++it) {
-          bool is_sc;
-          int dy, dx, ch;
-          tc_k_iter(p, it, main_iters, tap, kc, is_sc, ch, dy, dx);
-          const CUtensorMap* am = is_sc ? &map_s : &map_a;
-          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-          const uint32_t full = smem_u32(&bar_full[stage]);
-          mbar_expect_tx(full, SW_STAGE);
-          const uint32_t dst = smem_base + stage * SW_STAGE;
-          tma_load_2d(dst, &map_b, full, it * TC_BK, 0);
-          tma_load_4d(dst + TC_A_BYTES, am, full, ch * TC_BK, p.csx * x0[0] + dx, p.cs * y0[0] + dy, n0[0]);
-          tma_load_4d(dst + 2 * TC_A_BYTES, am, full, ch * TC_BK, p.csx * x0[1] + dx, p.cs * y0[1] + dy, n0[1]);
-          if (++kc == p.kchunks) { kc = 0; ++tap; }
-          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer: M = 128 channels, N = 256 pixels =================
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(128, 256, F16);
-      int stage = 0;
-      uint32_t phase = 0;
-      long long local = 0;
-      for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
-        const int acc = (int)(local & 1);
-        const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
-        mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-        for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
-          tc_fence_after();
-          const uint32_t w_addr = smem_base + stage * SW_STAGE;
-          const uint64_t wdesc = make_sw128_desc(w_addr);
-          const uint64_t pdesc = make_sw128_desc(w_addr + TC_A_BYTES);
-#pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            umma_bf16(d_tmem, wdesc + (uint64_t)(2 * k), pdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
-          umma_commit(smem_u32(&bar_empty[stage]));
-          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
-        }
-        umma_commit(smem_u32(&bar_acc_full[acc]));
-      }
-    }
-  } else if (warp >= 4) {
-    // ================= epilogue: thread = output channel, TMEM columns = the tile's 256 pixels =================
+__device__ __forceinline__ void swap_epilogue_loop(const TcParams& p, const uint32_t tmem_base, uint64_t* bar_acc_full,
+                                                   uint64_t* bar_acc_empty, float* s_px, float* s_head, const long long tiles,
+                                                   const int warp, const int lane) {
     // eight epilogue warps: warp w may only read the TMEM lane quadrant w % 4, so two warps share each 32-channel quadrant
     // and split the tile's 256 pixel columns between them (warps 4..7: columns 0..127, warps 8..11: columns 128..255)
     const int q = warp & 3;
@@ -1189,6 +1097,282 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
     if (F16 && vmax > kF16Max) range_flag_set(p.ovf, SDG_RANGE_ACT);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Role-swapped kernel for Cout = 128 layers (every 3x3 conv of SNGAN-32, StyleGAN2's 256x256 conv1):
+//     D^T[128 channels, 256 pixels] = W[128, K] * A[256 pixels, K]^T
+// i.e. the WEIGHTS are the UMMA "A" operand (M = 128) and the pixel tile is the "B" operand with N = 256, so that one
+// tcgen05.mma covers 128 x 256 x 16 -- twice the work per instruction of the pixel-major kernels, whose N is capped at
+// Cout = 128.  Measured (profiles/r1e_ncu_full_pair_stream_summary.txt): N = 128 instructions keep the tensor pipe 55-58 %
+// busy, N = 256 instructions 95 %; the instruction, not shared-memory bandwidth, is the unit that has to be large.
+// The accumulator comes out transposed: TMEM lane = output channel, column = pixel.  That suits NHWC: for a fixed pixel the
+// 32 lanes of an epilogue warp hold 32 consecutive channels, so every global access of the epilogue (16-bit / fp32 stores,
+// fp32 residual loads) is a contiguous 64 / 128-byte segment with no shuffle transposes at all.
+// Per stage: weights 16 KB + two 128-pixel boxes 32 KB; 4 stages; accumulator 2 x 256 TMEM columns.
+
+template <bool F16>
+__global__ void __launch_bounds__(SW_THREADS, 1)
+conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_s, const TcParams p, const int n_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  __shared__ __align__(8) uint64_t bar_full[SW_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[SW_STAGES];
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_px[256 * 2 * 3];          // pooled normalised image pixels of the current tile (image shortcut; two per
+                                               // GEMM pixel in the super-pixel form)
+  __shared__ float s_head[4 * 8];              // per-warp partial logits of the (up to 8) images of the current tile
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (p.sc_chunks) tma_prefetch_desc(&map_s);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SW_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_acc_full[s]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[s]), SW_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const long long tiles = (p.m_tiles + 1) >> 1;          // 256-pixel tiles = pairs of 128-pixel boxes
+  const int main_iters = p.taps * p.kchunks;
+  const int k_iters = main_iters + p.sc_chunks;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        int n0[2], y0[2], x0[2];
+        tc_tile_origin(p, 2 * t, n0[0], y0[0], x0[0]);
+        tc_tile_origin(p, 2 * t + 1, n0[1], y0[1], x0[1]);      // beyond the last box: image index >= n, zero filled
+        int tap = 0, kc = 0;
+        for (int it = 0; it < k_iters; ++it) {
+          bool is_sc;
+          int dy, dx, ch;
+          tc_k_iter(p, it, main_iters, tap, kc, is_sc, ch, dy, dx);
+          const CUtensorMap* am = is_sc ? &map_s : &map_a;
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          const uint32_t dst = smem_base + stage * SW_STAGE;
+          // timing experiment (SDG_TIMING_EXPERIMENTS builds only, WRONG results): debug_skip_a = m reloads the pixel operand
+          // only on every m-th K iteration (stale shared memory otherwise): how much of the time is operand ingest?
+          if (p.debug_skip_a > 1 && (it % p.debug_skip_a) != 0) {
+            mbar_expect_tx(full, TC_A_BYTES);
+            tma_load_2d(dst, &map_b, full, it * TC_BK, 0);
+          } else {
+          mbar_expect_tx(full, SW_STAGE);
+          tma_load_2d(dst, &map_b, full, it * TC_BK, 0);
+          tma_load_4d(dst + TC_A_BYTES, am, full, ch * TC_BK, p.csx * x0[0] + dx, p.cs * y0[0] + dy, n0[0]);
+          tma_load_4d(dst + 2 * TC_A_BYTES, am, full, ch * TC_BK, p.csx * x0[1] + dx, p.cs * y0[1] + dy, n0[1]);
+          }
+          if (++kc == p.kchunks) { kc = 0; ++tap; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: M = 128 channels, N = 256 pixels =================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(128, 256, F16);
+      int stage = 0;
+      uint32_t phase = 0;
+      long long local = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
+        const int acc = (int)(local & 1);
+        const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
+        mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          const uint32_t w_addr = smem_base + stage * SW_STAGE;
+          const uint64_t wdesc = make_sw128_desc(w_addr);
+          const uint64_t pdesc = make_sw128_desc(w_addr + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(d_tmem, wdesc + (uint64_t)(2 * k), pdesc + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&bar_empty[stage]));
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&bar_acc_full[acc]));
+      }
+    }
+  } else if (warp >= 4) {
+    swap_epilogue_loop<F16>(p, tmem_base, bar_acc_full, bar_acc_empty, s_px, s_head, tiles, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Role-swapped kernel with TAP-SHARED operand staging, for layers whose 256-pixel tile is one whole 16 x 16 output grid
+// (SNGAN-32 block1.c2 in the 4x4 stride-2 form, block2.c1).
+// What bounds conv_swap_kernel is not the tensor pipe but operand INGEST: every K step (64 channels of one tap) pulls
+// 16 KB of weights + 32 KB of pixels from L2 into shared memory for 4 x 128 cycles of MMA, 96 B per cycle against the
+// ~64 B per cycle an SM takes in (ncu, profiles/r2b_*: l1tex__m_xbar2l1tex_read_bytes at its ceiling while the tensor pipe is
+// 67-72 % busy; with the pixel loads skipped -- a timing experiment that produces wrong results -- the pass drops from
+// 17.3 to 14.4 ms).  The pixel operand is the redundant part: the taps of a 3x3 (4x4) window re-read the same activations
+// 9 (16) times.  Here a tile's activations are staged ONCE per (64-channel chunk, column variant) as a "copy" of 18 (17)
+// image rows x 16 pixels, and the taps that differ by a row shift only move the UMMA descriptor's start address by whole
+// rows (2 KB = two 1024-byte swizzle atoms, so TMA's 128B swizzle and the descriptor still agree).  A column shift would
+// break the 8-row swizzle atom, hence one copy per column variant: 6 copies x 36 KB instead of 18 loads x 32 KB for a 3x3
+// layer, 16 x 34 KB instead of 32 x 32 KB for the 4x4 stride-2 form (parity planes through the TMA traversal stride).
+// Two producers (pixel copies: warp 0, weights: warp 3) feed independent rings; the epilogue is conv_swap_kernel's.
+constexpr int SH_W_STAGES = 4;
+constexpr int SH_COPY_PITCH = 36 * 1024;
+constexpr int SH_COPIES = 4;
+constexpr int kSwapSharedSmem = 1024 + SH_W_STAGES * TC_A_BYTES + SH_COPIES * SH_COPY_PITCH;      // 209 KB
+
+template <bool F16>
+__global__ void __launch_bounds__(SW_THREADS, 1)
+conv_swap_shared_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t copy_base = smem_base + SH_W_STAGES * TC_A_BYTES;
+
+  __shared__ __align__(8) uint64_t bar_wfull[SH_W_STAGES];
+  __shared__ __align__(8) uint64_t bar_wempty[SH_W_STAGES];
+  __shared__ __align__(8) uint64_t bar_pfull[SH_COPIES];
+  __shared__ __align__(8) uint64_t bar_pempty[SH_COPIES];
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_px[256 * 2 * 3];
+  __shared__ float s_head[4 * 8];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_c);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SH_W_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_wfull[s]), 1);
+      mbar_init(smem_u32(&bar_wempty[s]), 1);
+    }
+    for (int s = 0; s < SH_COPIES; ++s) {
+      mbar_init(smem_u32(&bar_pfull[s]), 1);
+      mbar_init(smem_u32(&bar_pempty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_acc_full[s]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[s]), SW_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const long long tiles = p.n_images;                     // one image (16 x 16 output pixels) per tile
+  const ShSched& sh = p.sh;
+
+  if (warp == 0) {
+    // ================= pixel-copy producer =================
+    if (elect_one()) {
+      int pb = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        for (int c = 0; c < p.kchunks; ++c) {
+          for (int k = 0; k < sh.n_copy; ++k) {
+            mbar_wait(smem_u32(&bar_pempty[pb]), phase ^ 1u);
+            const uint32_t full = smem_u32(&bar_pfull[pb]);
+            mbar_expect_tx(full, (uint32_t)sh.copy_bytes);
+            tma_load_4d(copy_base + pb * SH_COPY_PITCH, &map_c, full, c * TC_BK, sh.col0[k], sh.row0[k], (int)t);
+            if (++pb == SH_COPIES) { pb = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ================= weight producer: one [128 x 64] K chunk per tap, in the order the copies are consumed =================
+    if (elect_one()) {
+      int ws = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        for (int c = 0; c < p.kchunks; ++c) {
+          for (int k = 0; k < sh.n_copy; ++k) {
+            for (int j = 0; j < sh.tpc; ++j) {
+              mbar_wait(smem_u32(&bar_wempty[ws]), phase ^ 1u);
+              const uint32_t full = smem_u32(&bar_wfull[ws]);
+              mbar_expect_tx(full, TC_A_BYTES);
+              tma_load_2d(smem_base + ws * TC_A_BYTES, &map_b, full, ((int)sh.wtap[k][j] * p.kchunks + c) * TC_BK, 0);
+              if (++ws == SH_W_STAGES) { ws = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: M = 128 channels, N = 256 pixels =================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(128, 256, F16);
+      int ws = 0, pb = 0;
+      uint32_t wphase = 0, pphase = 0;
+      long long local = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
+        const int acc = (int)(local & 1);
+        const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
+        mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        uint32_t accumulate = 0;
+        for (int c = 0; c < p.kchunks; ++c) {
+          for (int k = 0; k < sh.n_copy; ++k) {
+            mbar_wait(smem_u32(&bar_pfull[pb]), pphase);
+            const uint32_t c_addr = copy_base + pb * SH_COPY_PITCH;
+            for (int j = 0; j < sh.tpc; ++j) {
+              mbar_wait(smem_u32(&bar_wfull[ws]), wphase);
+              tc_fence_after();
+              const uint64_t wdesc = make_sw128_desc(smem_base + ws * TC_A_BYTES);
+              const uint64_t pdesc = make_sw128_desc(c_addr + (uint32_t)((int)sh.roff[k][j] * sh.row_bytes));
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 16; ++kk) {
+                umma_bf16(d_tmem, wdesc + (uint64_t)(2 * kk), pdesc + (uint64_t)(2 * kk), idesc, accumulate);
+                accumulate = 1u;
+              }
+              umma_commit(smem_u32(&bar_wempty[ws]));
+              if (++ws == SH_W_STAGES) { ws = 0; wphase ^= 1u; }
+            }
+            umma_commit(smem_u32(&bar_pempty[pb]));        // every tap of this copy has been issued: free it when they retire
+            if (++pb == SH_COPIES) { pb = 0; pphase ^= 1u; }
+          }
+        }
+        umma_commit(smem_u32(&bar_acc_full[acc]));
+      }
+    }
+  } else if (warp >= 4) {
+    swap_epilogue_loop<F16>(p, tmem_base, bar_acc_full, bar_acc_empty, s_px, s_head, tiles, warp, lane);
   }
 
   tc_fence_before();
@@ -1278,6 +1462,8 @@ int conv_tc_init(int device) {
   SDG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemMax));
   SDG_CUDA(cudaFuncSetAttribute(conv_swap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwapSmem));
   SDG_CUDA(cudaFuncSetAttribute(conv_swap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwapSmem));
+  SDG_CUDA(cudaFuncSetAttribute(conv_swap_shared_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwapSharedSmem));
+  SDG_CUDA(cudaFuncSetAttribute(conv_swap_shared_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwapSharedSmem));
   SDG_CUDA(cudaFuncSetAttribute((conv_pair_stream_kernel<256, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
   SDG_CUDA(cudaFuncSetAttribute((conv_pair_stream_kernel<256, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
   SDG_CUDA(cudaFuncSetAttribute((conv_pair_stream_kernel<128, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
@@ -1416,6 +1602,41 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
     // zero filled by TMA, so the M = 128 instruction runs half empty and N stays 256
     CUtensorMap map_w;
     { int rc = tc_encode_2d(&map_w, a.wb, f16, k_cols, Cout, TC_BK, 128); if (rc) return rc; }
+    // tap-shared operand staging (conv_swap_shared_kernel) when a tile is one whole 16 x 16 output grid
+    static const int shared_taps = getenv("SDG_SHARED_TAPS") ? atoi(getenv("SDG_SHARED_TAPS")) : 1;
+    if (shared_taps && Cout == 128 && Hc == 16 && Wc == 16 && !a.general && p.sc_chunks == 0 && (s2 || (taps == 9 && !strided)) &&
+        p.toff == -1) {
+      ShSched& sh = p.sh;
+      memset(&sh, 0, sizeof(sh));
+      int rows;
+      if (s2) {                                   // 4x4 stride-2 form: copy k = rowclass * 4 + b, taps a = rowclass (roff 0), + 2 (roff 1)
+        sh.n_copy = 8; sh.tpc = 2; rows = 17;
+        for (int rc = 0; rc < 2; ++rc)
+          for (int b = 0; b < 4; ++b) {
+            const int k = rc * 4 + b;
+            sh.col0[k] = (signed char)(b - 1);
+            sh.row0[k] = (signed char)(rc == 0 ? -1 : 0);           // input rows -1, 1, 3, ... (a = 0, 2) or 0, 2, 4, ... (a = 1, 3)
+            const int a0 = rc == 0 ? 0 : 1;
+            sh.wtap[k][0] = (signed char)(a0 * 4 + b); sh.roff[k][0] = 0;
+            sh.wtap[k][1] = (signed char)((a0 + 2) * 4 + b); sh.roff[k][1] = 1;
+          }
+      } else {                                    // 3x3 stride 1: copy k = dx + 1, taps dy = -1, 0, 1
+        sh.n_copy = 3; sh.tpc = 3; rows = 18;
+        for (int k = 0; k < 3; ++k) {
+          sh.col0[k] = (signed char)(k - 1);
+          sh.row0[k] = -1;
+          for (int j = 0; j < 3; ++j) { sh.wtap[k][j] = (signed char)(j * 3 + k); sh.roff[k][j] = (signed char)j; }
+        }
+      }
+      sh.row_bytes = Wc * 128;
+      sh.copy_bytes = rows * sh.row_bytes;
+      CUtensorMap map_c;
+      { int rc = encode_act(&map_c, a.in, f16, a.n, Hin, Win, Cin, Wc, rows, 1, es, esx); if (rc) return rc; }
+      const int grid = (int)(a.n < g_num_sms ? a.n : g_num_sms);
+      if (f16) { SDG_LAUNCH(conv_swap_shared_kernel<true>, grid, SW_THREADS, kSwapSharedSmem, s, map_c, map_w, p); }
+      else { SDG_LAUNCH(conv_swap_shared_kernel<false>, grid, SW_THREADS, kSwapSharedSmem, s, map_c, map_w, p); }
+      return 0;
+    }
     const long long tiles = (p.m_tiles + 1) / 2;
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
     static const int sw_stages_env = getenv("SDG_SWAP_STAGES") ? atoi(getenv("SDG_SWAP_STAGES")) : SW_STAGES;   // timing experiment
