@@ -1307,8 +1307,11 @@ conv_swap_shared_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_
           for (int k = 0; k < sh.n_copy; ++k) {
             mbar_wait(smem_u32(&bar_pempty[pb]), phase ^ 1u);
             const uint32_t full = smem_u32(&bar_pfull[pb]);
+            if (p.debug_skip_a & 4) { mbar_arrive(full); }        // timing experiment (wrong results): no pixel loads at all
+            else {
             mbar_expect_tx(full, (uint32_t)sh.copy_bytes);
             tma_load_4d(copy_base + pb * SH_COPY_PITCH, &map_c, full, c * TC_BK, sh.col0[k], sh.row0[k], (int)t);
+            }
             if (++pb == SH_COPIES) { pb = 0; phase ^= 1u; }
           }
         }
@@ -1325,8 +1328,11 @@ conv_swap_shared_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_
             for (int j = 0; j < sh.tpc; ++j) {
               mbar_wait(smem_u32(&bar_wempty[ws]), phase ^ 1u);
               const uint32_t full = smem_u32(&bar_wfull[ws]);
+              if (p.debug_skip_a & 8) { mbar_arrive(full); }      // timing experiment (wrong results): no weight loads at all
+              else {
               mbar_expect_tx(full, TC_A_BYTES);
               tma_load_2d(smem_base + ws * TC_A_BYTES, &map_b, full, ((int)sh.wtap[k][j] * p.kchunks + c) * TC_BK, 0);
+              }
               if (++ws == SH_W_STAGES) { ws = 0; phase ^= 1u; }
             }
           }
