@@ -66,7 +66,8 @@ WORKLOADS = {
                            "4x4 stride-2 conv in super-pixel form (two output pixels = one 128-channel GEMM pixel, 4x6 taps of which "
                            "4x4 per output pixel are real: a third of the executed MACs are structural zeros and are NOT counted)",
                     dom_ref_flop=2.0 * 9 * 64 * 64 * 4096, dom_exec_useful=16.0 / 24.0, cpu_sample=2048,
-                    traffic=None,
+                    traffic=((4.399691e9 + 1.052111e9) / 8192.0, "profiles/r1h_ncu_full_sngan64_superpix_summary.txt third launch "
+                             "(8192 samples: 4.400 GB read + 1.052 GB written; algorithmic 512 KiB in + 128 KiB out per sample = 655.4 KB)"),
                     eager=dict(ref_batch=64, ref_n=16_384, best_batch=1024, best_n=16_384)),
     "stylegan2": dict(arch="stylegan2", size=256, n_total=2048, n_weak=2048, key="ldr_conf_3.0_ratio_50", flop=None,
                       metric="per-sample D logits + LDR scores per second (StyleGAN2-256 discriminator, FFHQ shape, bounded 2048 "
@@ -75,7 +76,8 @@ WORKLOADS = {
                            "weights + top-100 over 2048 x 3x256x256 uint8 (bounded sample of the 70k pass)",
                       kernel="conv_swap_kernel ResBlock 1 conv1 (3x3 128->128 @256x256 + FusedLeakyReLU; 20.8% of the FLOPs)",
                       dom_ref_flop=2.0 * 9 * 128 * 128 * 65536, dom_exec_useful=1.0, cpu_sample=8,
-                      traffic=None,
+                      traffic=((1.900776e9 + 1.841034e9) / 112.0, "profiles/r2c_ncu_full_sg2_conv1_summary.txt (112 samples: 1.901 GB read + "
+                               "1.841 GB written; algorithmic 16 MiB in + 16 MiB out per sample = 33.55 MB)"),
                       eager=dict(ref_batch=4, ref_n=64, best_batch=16, best_n=64)),
 }
 
@@ -261,23 +263,31 @@ def gpu_eager_baseline(w, dev, host_u8):
     xd = host_u8[:n2].to(dev)
     logits = torch.empty(n2, device=dev)
 
-    def best_pass():
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+    import contextlib
+
+    def best_pass(autocast):
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if autocast else contextlib.nullcontext()
+        with torch.no_grad(), ctx:
             for s in range(0, n2, B2):
                 x = normalise_u8(xd[s:s + B2]).contiguous(memory_format=torch.channels_last)
                 logits[s:s + B2] = fwd(pre, x).view(-1).float()
-    best_pass()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        best_pass()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / 3
-    out["best_case"] = {"value": n2 / (ms / 1e3), "unit": UNIT, "samples": n2, "batch": B2,
-                        "how": "resident uint8 dataset, channels-last, bf16 autocast (cuDNN / cuBLAS), W/sigma once per pass, no "
-                               "host syncs"}
+
+    best = None
+    for autocast, label in ((True, "bf16 autocast"), (False, "fp32 storage, cuDNN TF32")):
+        best_pass(autocast)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            best_pass(autocast)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 3
+        if best is None or ms < best[0]:
+            best = (ms, label)
+    out["best_case"] = {"value": n2 / (best[0] / 1e3), "unit": UNIT, "samples": n2, "batch": B2,
+                        "how": f"resident uint8 dataset, channels-last, {best[1]} (the faster of bf16 autocast and TF32), "
+                               "W/sigma once per pass, no host syncs"}
     return out
 
 
