@@ -16,7 +16,8 @@ all-gathered.  ``value`` = 50 000 x K / max-over-ranks time.  For N > 1 the line
 
 Prints ONE JSON line (rank 0).  ``value`` is timed with the dataset shard resident in HBM; ``e2e`` is the same metric
 through ``LogitRecorder.record_from_host`` with the uint8 shard in pinned host memory (H2D inside the timed region) and
-the score vector + top indices read back to the host every step.  At N = 1 the line also carries ``cpu_baseline`` (the
+the score vector + top indices read back to pinned host memory every step (asynchronous copy, the host waits for it one step
+later: the consumer of step i's scores runs beside step i + 1).  At N = 1 the line also carries ``cpu_baseline`` (the
 oracle port on the host cores) and ``gpu_eager_baseline`` (the oracle network in PyTorch eager on the same B200: the
 reference's pass as users run it today, and a best-case library run).
 """
@@ -342,11 +343,22 @@ def run_ours(args, rank, world, local_rank):
             rec.record(weight_sets[i % n_sets], step=i, out=snap, range_check="deferred")
             return finish()
 
+        # end-to-end leg: the step's result (score vector + top indices) is read back into pinned host buffers every step; the
+        # copy is asynchronous and the host waits for it ONE STEP LATER (double-buffered), so the consumer of step i's scores
+        # runs beside step i + 1 instead of stalling the GPU behind the host's launch work
+        host_out = [(torch.empty(n_total, dtype=torch.float64).pin_memory(), torch.empty(100, dtype=torch.int64).pin_memory(),
+                     torch.cuda.Event()) for _ in range(2)]
+
         def step_host(i):
             rec.record_from_host(weight_sets[i % n_sets], host, step=i, chunk=host_chunk, first_chunk=min(2048, host_chunk // 4),
                                  range_check="deferred")
             full, top = finish()
-            return full.cpu(), top.cpu()                       # D2H of the step's result
+            hf, ht, ev = host_out[i & 1]
+            hf.copy_(full, non_blocking=True)                  # D2H of the step's result
+            ht.copy_(top, non_blocking=True)
+            ev.record()
+            host_out[(i + 1) & 1][2].synchronize()             # the previous step's result is on the host now
+            return hf, ht
 
         def timed(step_fn, steps, warmup, prof=False):
             rec.stats = None
