@@ -87,3 +87,33 @@ def test_two_rank_nccl_matches_single_gpu(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_one_process_drives_two_devices():
+    """one-time initialisation (opt-in shared memory sizes, driver entry point) is tracked per device and every
+    wrapper guards the current device, so a single process can run engines on cuda:0 and cuda:1 -- without touching
+    torch.cuda.set_device -- and gets the same bits on both."""
+    for p in (ROOT, os.path.join(ROOT, "self-diagnosing-gan_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from diagan_b200 import engine, synthetic
+    from diagan_b200.trainer.trainer import LogitRecorder, ResidentDataset
+    n = 515
+    x = synthetic.uniform_images_u8(n, 32, seed=8)
+    sd = synthetic.sngan_state_dict(32, seed=8)
+    outs = []
+    for d in (1, 0, 1):                                       # device 1 first: nothing may silently default to device 0
+        dev = torch.device("cuda", d)
+        rec = LogitRecorder(ResidentDataset(x.to(dev)), dev, keep_snapshots=False)
+        for step in (0, 100, 200):
+            snap = rec.record(synthetic.perturb_(sd, step, 2e-2), step=step)
+        assert snap.device == dev and rec.stats.state.device == dev
+        w = rec.stats.score(engine.conf_from_key("ldr_conf_0.3_ratio_50"), eps=1e-6)
+        top = engine.top_indices(w, 50, True)
+        assert w.device == dev and top.device == dev
+        outs.append((snap.cpu(), w.cpu(), top.cpu()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs[0], outs[2]):
+        assert torch.equal(a, b)
