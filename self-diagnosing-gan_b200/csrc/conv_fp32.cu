@@ -250,68 +250,73 @@ int head_dot_fp32(const float* h, const float* w, const float* bias, float* logi
 // straight from the image, fp32 accumulation (0.36 % of the network's MACs: CUDA cores), stored as ONE 128-byte row per
 // output pixel = 16 real + 48 zero 16-bit channels, i.e. the 64-channel K chunk the tcgen05 kernels stream by TMA.
 template <bool F16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 dcgan_first_conv_kernel(const void* __restrict__ x, int layout, const float* __restrict__ wp, h16* __restrict__ out,
                         int64_t total, int S, int* ovf) {
+  // thread = (output pixel, half): 8 of the 16 real channels + half of the pixel row's zero padding (<= 64 registers, four
+  // CTAs per SM: the kernel is latency-bound, the first version with 16 accumulators per thread ran at one CTA per SM)
   __shared__ float sw[27 * 16];
   for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i] = wp[i];
   __syncthreads();
   const int So = S / 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * total; t += stride) {
+    const int64_t i = t >> 1;
+    const int half = (int)(t & 1);
     const int ox = (int)(i % So);
     const int64_t r = i / So;
     const int oy = (int)(r % So);
     const int64_t n = r / So;
-    float acc[16];
+    float acc[8];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) acc[o] = 0.f;
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = 2 * oy - 1 + ky;
-      if (iy < 0 || iy >= S) continue;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = 2 * ox - 1 + kx;
-        if (ix < 0 || ix >= S) continue;
+        const bool ok = iy >= 0 && iy < S && ix >= 0 && ix < S;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          float v;
-          if (layout == SDG_LAYOUT_U8_NHWC) {
-            v = __fdiv_rn((float)reinterpret_cast<const uint8_t*>(x)[((n * S + iy) * S + ix) * 3 + c], 255.0f);
-            v = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
-          } else {
-            v = reinterpret_cast<const float*>(x)[((n * 3 + c) * S + iy) * (int64_t)S + ix];
+          float v = 0.f;
+          if (ok) {
+            if (layout == SDG_LAYOUT_U8_NHWC) {
+              v = __fdiv_rn((float)reinterpret_cast<const uint8_t*>(x)[((n * S + iy) * S + ix) * 3 + c], 255.0f);
+              v = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
+            } else {
+              v = reinterpret_cast<const float*>(x)[((n * 3 + c) * S + iy) * (int64_t)S + ix];
+            }
           }
-          const float* w = sw + ((ky * 3 + kx) * 3 + c) * 16;
-#pragma unroll
-          for (int o = 0; o < 16; ++o) acc[o] = fmaf(v, w[o], acc[o]);
+          const float4* w = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 3 + c) * 16 + half * 8);
+          const float4 w0 = w[0], w1 = w[1];
+          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
         }
       }
     }
-    uint32_t pk[8];
+    uint32_t pk[4];
     uint32_t bad = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
       const float a = acc[2 * j], b = acc[2 * j + 1];
       pk[j] = pack_h2<F16>(a > 0.f ? a : 0.2f * a, b > 0.f ? b : 0.2f * b);
       if (F16) bad |= f16x2_nonfinite_bits(pk[j]);
     }
     if (F16 && bad) range_flag_set(ovf, SDG_RANGE_ACT);
     uint4* o4 = reinterpret_cast<uint4*>(out + i * 64);
-    o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    o4[half] = make_uint4(pk[0], pk[1], pk[2], pk[3]);          // channels 8*half .. 8*half+7
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int j = 2; j < 8; ++j) o4[j] = z;
+    for (int j = 0; j < 3; ++j) o4[2 + 3 * half + j] = z;      // this half's share of the 48 zero channels
   }
 }
 
 int dcgan_first_conv_h16(const void* x, int layout, const float* wp, h16* out, int64_t n, int S, int f16, cudaStream_t s) {
   const int64_t total = n * (S / 2) * (S / 2);
   if (total == 0) return 0;
-  if (f16) { SDG_LAUNCH(dcgan_first_conv_kernel<true>, stream_grid(total, 256), 256, 0, s, x, layout, wp, out, total, S, t_range_flag); }
-  else { SDG_LAUNCH(dcgan_first_conv_kernel<false>, stream_grid(total, 256), 256, 0, s, x, layout, wp, out, total, S, t_range_flag); }
+  if (f16) { SDG_LAUNCH(dcgan_first_conv_kernel<true>, stream_grid(2 * total, 256, 16), 256, 0, s, x, layout, wp, out, total, S, t_range_flag); }
+  else { SDG_LAUNCH(dcgan_first_conv_kernel<false>, stream_grid(2 * total, 256, 16), 256, 0, s, x, layout, wp, out, total, S, t_range_flag); }
   return 0;
 }
 
