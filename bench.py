@@ -52,12 +52,13 @@ WORKLOADS = {
                     metric="per-sample D logits + LDR scores per second (SNGAN-32, 50k CIFAR-10-shape samples)",
                     desc="configs[1]: SNGAN-32 recording pass (weights re-packed per pass) + Welford stats + "
                          "ldr_conf_0.3_ratio_50 weights + top-100 over ONE 50k x 3x32x32 uint8 dataset",
-                    kernel="conv_swap_kernel block1.c2 (3x3 128->128 @32x32 + avg-pool + shortcut; 55.5% of the reference FLOPs), "
+                    kernel="conv_swap_shared_kernel block1.c2 (3x3 128->128 @32x32 + avg-pool + shortcut; 55.5% of the reference FLOPs), "
                            "run as the algebraically equal 4x4 stride-2 conv with role-swapped operands (M = 128 channels, "
-                           "N = 256 pixels per tcgen05.mma)",
+                           "N = 256 pixels per tcgen05.mma) and tap-shared operand staging",
                     dom_ref_flop=2.0 * 9 * 128 * 128 * 1024, dom_exec_useful=1.0, cpu_sample=16384,
-                    traffic=((1.087083e9 + 247.195904e6) / 4096.0, "profiles/r1f_ncu_full_swap_summary.txt launch 0 (4096 samples: "
-                             "1.087 GB read + 0.247 GB written; algorithmic 256 KiB in + 64 KiB out per sample = 327.7 KB)"),
+                    traffic=((3.316908e9 + 0.799314e9) / 12504.0, "profiles/r2g_ncu_full_sngan32_sweep_summary.txt launch 1 "
+                             "(12 504 samples: 3.317 GB read + 0.799 GB written = 329.2 KB/sample; algorithmic 256 KiB in + 64 KiB "
+                             "out per sample = 327.7 KB)"),
                     eager=dict(ref_batch=64, ref_n=50_000, best_batch=4096, best_n=50_000)),
     "sngan64": dict(arch="sngan", size=64, n_total=202_599, n_weak=25_325, key="ldr_conf_5.0_ratio_50", flop=2 * 644_809_728,
                     metric="per-sample D logits + LDR scores per second (SNGAN-64, CelebA shape, 202 599 samples)",
