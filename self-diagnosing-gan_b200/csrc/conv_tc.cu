@@ -49,13 +49,22 @@ constexpr int TC_MAX_COUT = 1024;
 // Tap-shared operand schedule of conv_swap_shared_kernel: the pixel operand is loaded once per (64-channel chunk, column
 // variant) as a "copy" of rows+halo image rows, and the taps that differ only by a ROW shift read it through a shifted
 // descriptor start address (whole 1024-byte swizzle atoms, so no re-layout).
+struct ShCopy {
+  signed char src;            // 0: the conv operand (map_c), 1: the folded shortcut's tensor (map_s)
+  signed char chunk;          // 64-channel chunk of that tensor
+  signed char col0, row0;     // box origin in input pixel coordinates
+  signed char rows;           // box rows (output rows + halo)
+  signed char ntaps;          // taps served by this copy (1..3)
+  short wk[3];                // tap j: 64-column chunk of the weight matrix
+  signed char roff[3];        // tap j: row shift inside the copy
+};
 struct ShSched {
-  int n_copy;                 // copies per 64-channel chunk (3: 3x3 stride 1; 8: the 4x4 stride-2 form)
-  int tpc;                    // taps per copy (3 / 2)
-  int copy_bytes;             // rows x tile width x 128 B actually loaded
-  int row_bytes;              // tile width x 128 B: one row shift of the descriptor start
-  signed char col0[8], row0[8];          // box origin of copy k in input pixel coordinates
-  signed char wtap[8][3], roff[8][3];    // tap j of copy k: index into the weight K layout, row shift inside the copy
+  int n_copies;               // copies per tile, in consumption order
+  int row_bytes;              // bytes of one copy row (= one row shift of the descriptor start): tile row pixels x 128
+  int perm;                   // 0: the tile is one 16 x 16 grid in natural order; 4: four 8 x 8 grids, pixel order (row, image, column)
+  int pitch;                  // bytes between the copy buffers (largest copy, a multiple of 1024)
+  int w_stages;               // weight ring depth (4, or 3 when the copies need the room)
+  ShCopy cp[24];
 };
 
 struct TcParams {
@@ -1100,6 +1109,142 @@ __device__ __forceinline__ void swap_epilogue_loop(const TcParams& p, const uint
 }
 
 // ---------------------------------------------------------------------------------------------------
+// The same epilogue for tiles of FOUR 8 x 8 images whose 256 TMEM columns are in (row, image, column) order -- the order in
+// which conv_swap_shared_kernel stages such tiles so that a row shift of the operand is a whole number of swizzle atoms:
+// column J <-> image 4t + ((J >> 3) & 3), pixel (J >> 5, J & 7).  Identity residual (fp32 or 16-bit), up to three outputs,
+// fused SNGAN head; no image shortcut / super pixels (those layers do not have 8 x 8 outputs).
+template <bool F16>
+__device__ __forceinline__ void swap_epilogue_loop_perm(const TcParams& p, const uint32_t tmem_base, uint64_t* bar_acc_full,
+                                                        uint64_t* bar_acc_empty, float* s_head, const long long tiles,
+                                                        const int warp, const int lane) {
+  const int q = warp & 3;
+  const int half = (warp - 4) >> 2;
+  const int c = q * 32 + lane;
+  const int et = threadIdx.x - 128;
+  constexpr int CO = 128;
+  const float bias = p.bias ? p.bias[c] : 0.f;
+  const float hw_c = p.head_out ? p.head_w[c] : 0.f;
+  long long local = 0;
+  float vmax = 0.f;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
+    const int acc = (int)(local & 1);
+    const uint32_t acc_phase = (uint32_t)((local >> 1) & 1);
+    const long long P0 = t * 256;                         // first pixel of image 4t
+    const long long img0 = t * 4;
+    bool vi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vi[i] = img0 + i < p.n_images;
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
+    if (p.debug_skip_epi) {
+      mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
+      tc_fence_after();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
+      continue;
+    }
+    float hsum[4] = {0.f, 0.f, 0.f, 0.f};
+    float rnext[32];
+    // element (pixel, channel c) of column j of the chunk that holds image row y: ((P0 + (j >> 3) * 64 + y * 8 + (j & 7)) * CO + c
+    auto load_res = [&](int y) {
+      const long long base = (P0 + y * 8) * CO + c;
+      if (p.res_f32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (vi[j >> 3]) rnext[j] = __ldg(p.res_f32 + base + ((j >> 3) * 64 + (j & 7)) * CO);
+      } else if (p.res_h16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (vi[j >> 3]) rnext[j] = __uint_as_float((uint32_t)__ldg(p.res_h16 + base + ((j >> 3) * 64 + (j & 7)) * CO));
+      }
+    };
+    const int ybeg = half * 4;
+    load_res(ybeg);
+#pragma unroll 1
+    for (int y = ybeg; y < ybeg + 4; ++y) {
+      float rv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rv[j] = rnext[j];
+      if (y + 1 < ybeg + 4) load_res(y + 1);
+      if (y == ybeg) {
+        mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
+        tc_fence_after();
+      }
+      uint32_t r[32];
+      tmem_ld32(tmem_acc + (uint32_t)(y * 32), r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
+      if (p.act) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]) * 1.4142135623730951f;
+      }
+      if (p.res_f32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += p.res_relu ? fmaxf(rv[j], 0.f) : rv[j];
+      } else if (p.res_h16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float r16 = unpack_h2<F16>(__float_as_uint(rv[j]) & 0xffffu).x;
+          v[j] += p.res_relu ? fmaxf(r16, 0.f) : r16;
+        }
+      }
+      if (p.out_scale != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+      }
+      const long long base = (P0 + y * 8) * CO + c;
+      if (F16 && (p.out_raw || p.out_relu)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (vi[j >> 3]) vmax = fmaxf(vmax, p.out_raw ? fabsf(v[j]) : v[j]);
+      }
+      if (p.out_f32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (vi[j >> 3]) p.out_f32[base + ((j >> 3) * 64 + (j & 7)) * CO] = v[j];
+      }
+      if (p.out_raw) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (vi[j >> 3]) p.out_raw[base + ((j >> 3) * 64 + (j & 7)) * CO] = to_h16<F16>(v[j]);
+      }
+      if (p.out_relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (vi[j >> 3]) p.out_relu[base + ((j >> 3) * 64 + (j & 7)) * CO] = to_h16<F16>(fmaxf(v[j], 0.f));
+      }
+      if (p.head_out) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) hsum[j >> 3] += fmaxf(v[j], 0.f);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
+    if (p.head_out) {
+      // every warp holds, for each of the four images, the sum over its 32 channels and its four image rows: fixed shuffle
+      // tree per warp, then one thread per image adds the eight warp partials in a fixed order (deterministic logits)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float part = hsum[i] * hw_c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) s_head[(half * 4 + q) * 4 + i] = part;
+      }
+      named_bar_sync(2, SW_EPI_WARPS * 32);
+      if (et < 4 && img0 + et < p.n_images) {
+        const float* h = s_head + et;
+        p.head_out[img0 + et] = p.head_b[0] + (((h[0] + h[4]) + (h[8] + h[12])) + ((h[16] + h[20]) + (h[24] + h[28])));
+      }
+      named_bar_sync(2, SW_EPI_WARPS * 32);
+    }
+  }
+  if (F16 && vmax > kF16Max) range_flag_set(p.ovf, SDG_RANGE_ACT);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Role-swapped kernel for Cout = 128 layers (every 3x3 conv of SNGAN-32, StyleGAN2's 256x256 conv1):
 //     D^T[128 channels, 256 pixels] = W[128, K] * A[256 pixels, K]^T
 // i.e. the WEIGHTS are the UMMA "A" operand (M = 128) and the pixel tile is the "B" operand with N = 256, so that one
@@ -1244,17 +1389,19 @@ conv_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // break the 8-row swizzle atom, hence one copy per column variant: 6 copies x 36 KB instead of 18 loads x 32 KB for a 3x3
 // layer, 16 x 34 KB instead of 32 x 32 KB for the 4x4 stride-2 form (parity planes through the TMA traversal stride).
 // Two producers (pixel copies: warp 0, weights: warp 3) feed independent rings; the epilogue is conv_swap_kernel's.
-constexpr int SH_W_STAGES = 4;
-constexpr int SH_COPY_PITCH = 36 * 1024;
+constexpr int SH_W_STAGES = 4;                // upper bound of the weight ring (sh.w_stages are used)
 constexpr int SH_COPIES = 4;
-constexpr int kSwapSharedSmem = 1024 + SH_W_STAGES * TC_A_BYTES + SH_COPIES * SH_COPY_PITCH;      // 209 KB
+constexpr int kSwapSharedSmem = 1024 + 208 * 1024;      // 4 x 16 KB weights + 4 x 36 KB copies, or 3 x 16 KB + 4 x 40 KB
 
 template <bool F16>
 __global__ void __launch_bounds__(SW_THREADS, 1)
-conv_swap_shared_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+conv_swap_shared_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_s,
+                        const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t copy_base = smem_base + SH_W_STAGES * TC_A_BYTES;
+  const uint32_t copy_base = smem_base + (uint32_t)p.sh.w_stages * TC_A_BYTES;
+  const uint32_t SH_COPY_PITCH = (uint32_t)p.sh.pitch;
+  const int w_stages = p.sh.w_stages;
 
   __shared__ __align__(8) uint64_t bar_wfull[SH_W_STAGES];
   __shared__ __align__(8) uint64_t bar_wempty[SH_W_STAGES];
@@ -1271,6 +1418,7 @@ conv_swap_shared_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_c);
+    tma_prefetch_desc(&map_s);
     tma_prefetch_desc(&map_b);
   }
   if (warp == 1 && lane == 0) {
@@ -1294,8 +1442,9 @@ conv_swap_shared_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  const long long tiles = p.n_images;                     // one image (16 x 16 output pixels) per tile
   const ShSched& sh = p.sh;
+  // natural order: one image (16 x 16 outputs) per tile; permuted order: four images (8 x 8 outputs each) per tile
+  const long long tiles = sh.perm ? (p.n_images + 3) >> 2 : p.n_images;
 
   if (warp == 0) {
     // ================= pixel-copy producer =================
@@ -1303,17 +1452,19 @@ conv_swap_shared_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_
       int pb = 0;
       uint32_t phase = 0;
       for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        for (int c = 0; c < p.kchunks; ++c) {
-          for (int k = 0; k < sh.n_copy; ++k) {
-            mbar_wait(smem_u32(&bar_pempty[pb]), phase ^ 1u);
-            const uint32_t full = smem_u32(&bar_pfull[pb]);
-            if (p.debug_skip_a & 4) { mbar_arrive(full); }        // timing experiment (wrong results): no pixel loads at all
-            else {
-            mbar_expect_tx(full, (uint32_t)sh.copy_bytes);
-            tma_load_4d(copy_base + pb * SH_COPY_PITCH, &map_c, full, c * TC_BK, sh.col0[k], sh.row0[k], (int)t);
-            }
-            if (++pb == SH_COPIES) { pb = 0; phase ^= 1u; }
+        for (int k = 0; k < sh.n_copies; ++k) {
+          const ShCopy& cp = sh.cp[k];
+          mbar_wait(smem_u32(&bar_pempty[pb]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_pfull[pb]);
+          if (p.debug_skip_a & 4) { mbar_arrive(full); }        // timing experiment (wrong results): no pixel loads at all
+          else {
+            mbar_expect_tx(full, (uint32_t)((int)cp.rows * sh.row_bytes));
+            const CUtensorMap* m = cp.src ? &map_s : &map_c;
+            // permuted maps are {channel, column, image, row}: a copy lands as [row][image][8 pixels], images beyond n zero filled
+            if (sh.perm) tma_load_4d(copy_base + pb * SH_COPY_PITCH, m, full, (int)cp.chunk * TC_BK, cp.col0, (int)(t * 4), cp.row0);
+            else tma_load_4d(copy_base + pb * SH_COPY_PITCH, m, full, (int)cp.chunk * TC_BK, cp.col0, cp.row0, (int)t);
           }
+          if (++pb == SH_COPIES) { pb = 0; phase ^= 1u; }
         }
       }
     }
@@ -1323,18 +1474,17 @@ conv_swap_shared_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_
       int ws = 0;
       uint32_t phase = 0;
       for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        for (int c = 0; c < p.kchunks; ++c) {
-          for (int k = 0; k < sh.n_copy; ++k) {
-            for (int j = 0; j < sh.tpc; ++j) {
-              mbar_wait(smem_u32(&bar_wempty[ws]), phase ^ 1u);
-              const uint32_t full = smem_u32(&bar_wfull[ws]);
-              if (p.debug_skip_a & 8) { mbar_arrive(full); }      // timing experiment (wrong results): no weight loads at all
-              else {
+        for (int k = 0; k < sh.n_copies; ++k) {
+          const ShCopy& cp = sh.cp[k];
+          for (int j = 0; j < cp.ntaps; ++j) {
+            mbar_wait(smem_u32(&bar_wempty[ws]), phase ^ 1u);
+            const uint32_t full = smem_u32(&bar_wfull[ws]);
+            if (p.debug_skip_a & 8) { mbar_arrive(full); }      // timing experiment (wrong results): no weight loads at all
+            else {
               mbar_expect_tx(full, TC_A_BYTES);
-              tma_load_2d(smem_base + ws * TC_A_BYTES, &map_b, full, ((int)sh.wtap[k][j] * p.kchunks + c) * TC_BK, 0);
-              }
-              if (++ws == SH_W_STAGES) { ws = 0; phase ^= 1u; }
+              tma_load_2d(smem_base + ws * TC_A_BYTES, &map_b, full, (int)cp.wk[j] * TC_BK, 0);
             }
+            if (++ws == w_stages) { ws = 0; phase ^= 1u; }
           }
         }
       }
@@ -1353,32 +1503,32 @@ conv_swap_shared_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
         uint32_t accumulate = 0;
-        for (int c = 0; c < p.kchunks; ++c) {
-          for (int k = 0; k < sh.n_copy; ++k) {
-            mbar_wait(smem_u32(&bar_pfull[pb]), pphase);
-            const uint32_t c_addr = copy_base + pb * SH_COPY_PITCH;
-            for (int j = 0; j < sh.tpc; ++j) {
-              mbar_wait(smem_u32(&bar_wfull[ws]), wphase);
-              tc_fence_after();
-              const uint64_t wdesc = make_sw128_desc(smem_base + ws * TC_A_BYTES);
-              const uint64_t pdesc = make_sw128_desc(c_addr + (uint32_t)((int)sh.roff[k][j] * sh.row_bytes));
+        for (int k = 0; k < sh.n_copies; ++k) {
+          const ShCopy& cp = sh.cp[k];
+          mbar_wait(smem_u32(&bar_pfull[pb]), pphase);
+          const uint32_t c_addr = copy_base + pb * SH_COPY_PITCH;
+          for (int j = 0; j < cp.ntaps; ++j) {
+            mbar_wait(smem_u32(&bar_wfull[ws]), wphase);
+            tc_fence_after();
+            const uint64_t wdesc = make_sw128_desc(smem_base + ws * TC_A_BYTES);
+            const uint64_t pdesc = make_sw128_desc(c_addr + (uint32_t)((int)cp.roff[j] * sh.row_bytes));
 #pragma unroll
-              for (int kk = 0; kk < TC_BK / 16; ++kk) {
-                umma_bf16(d_tmem, wdesc + (uint64_t)(2 * kk), pdesc + (uint64_t)(2 * kk), idesc, accumulate);
-                accumulate = 1u;
-              }
-              umma_commit(smem_u32(&bar_wempty[ws]));
-              if (++ws == SH_W_STAGES) { ws = 0; wphase ^= 1u; }
+            for (int kk = 0; kk < TC_BK / 16; ++kk) {
+              umma_bf16(d_tmem, wdesc + (uint64_t)(2 * kk), pdesc + (uint64_t)(2 * kk), idesc, accumulate);
+              accumulate = 1u;
             }
-            umma_commit(smem_u32(&bar_pempty[pb]));        // every tap of this copy has been issued: free it when they retire
-            if (++pb == SH_COPIES) { pb = 0; pphase ^= 1u; }
+            umma_commit(smem_u32(&bar_wempty[ws]));
+            if (++ws == w_stages) { ws = 0; wphase ^= 1u; }
           }
+          umma_commit(smem_u32(&bar_pempty[pb]));          // every tap of this copy has been issued: free it when they retire
+          if (++pb == SH_COPIES) { pb = 0; pphase ^= 1u; }
         }
         umma_commit(smem_u32(&bar_acc_full[acc]));
       }
     }
   } else if (warp >= 4) {
-    swap_epilogue_loop<F16>(p, tmem_base, bar_acc_full, bar_acc_empty, s_px, s_head, tiles, warp, lane);
+    if (sh.perm) swap_epilogue_loop_perm<F16>(p, tmem_base, bar_acc_full, bar_acc_empty, s_head, tiles, warp, lane);
+    else swap_epilogue_loop<F16>(p, tmem_base, bar_acc_full, bar_acc_empty, s_px, s_head, tiles, warp, lane);
   }
 
   tc_fence_before();
@@ -1448,6 +1598,21 @@ static int encode_act(CUtensorMap* map, const void* ptr, int f16, int64_t n, int
 // Function attributes (opt-in shared memory) are per DEVICE, the driver entry point is per process: one bit per device id
 // records which devices have been initialised, so that a single process may drive several GPUs.
 static std::atomic<unsigned long long> g_dev_init{0};
+
+// the same tensor viewed as {channel, column, IMAGE, row} (strides are free in a tiled map): a box {64, bw, bn, bh} then lands in
+// shared memory as [row][image][column], the layout conv_swap_shared_kernel needs for tiles of several small images
+static int encode_act_perm(CUtensorMap* map, const void* ptr, int f16, int64_t n, int H, int W, int C, int bw, int bh, int bn,
+                           int es) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)n, (cuuint64_t)H};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(bw * es), (cuuint32_t)bn, (cuuint32_t)(bh * es)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, 1, (cuuint32_t)es};
+  CUresult r = g_encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SDG_REQUIRE(r == CUDA_SUCCESS, SDG_E_INVALID, "conv_tc: cuTensorMapEncodeTiled(act, permuted) failed: %d", (int)r);
+  return 0;
+}
 
 int conv_tc_init(int device) {
   if (device >= 0 && device < 64 && ((g_dev_init.load(std::memory_order_acquire) >> device) & 1ULL)) return 0;
@@ -1601,46 +1766,76 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   static const int swap64 = getenv("SDG_SWAP64") ? atoi(getenv("SDG_SWAP64")) : 0;
   // (a single 128-pixel box is allowed when the 16-bit residual is used, which only this kernel implements: the second box
   // of the tile then lies beyond the tensor and is zero filled)
+  // tap-shared operand staging (conv_swap_shared_kernel) applies when a tile is one whole 16 x 16 output grid, or four 8 x 8
+  // grids in (row, image, column) order; 3x3 stride 1 or the 4x4 stride-2 form, optionally with the folded 1x1 shortcut.
+  // It is chosen by SHAPE only (any n >= 1), so that a sample's logit never depends on the batch it is evaluated in.
+  static const int shared_taps = getenv("SDG_SHARED_TAPS") ? atoi(getenv("SDG_SHARED_TAPS")) : 1;   // 2: 16 x 16 grids only
+  const bool grid16 = Hc == 16 && Wc == 16, grid8 = Hc == 8 && Wc == 8 && shared_taps == 1;
+  const bool sh_ok = shared_taps && Cout == 128 && (grid16 || grid8) && !a.general && (p.sc_chunks == 0 || (s2 && grid8)) &&
+                     (s2 || (taps == 9 && !strided)) && p.toff == -1 && (grid16 || !a.img);
   if (swap_mode && g_pair_mode == 1 && (Cout == 128 || (swap64 && Cout == 64)) && !p.pool && !p.box16 && !p.sc_sep && !a.sd &&
-      !a.gemm && (p.m_tiles >= 2 || a.res_h16) && p.total_pixels % 32 == 0 &&
+      !a.gemm && (p.m_tiles >= 2 || a.res_h16 || sh_ok) && p.total_pixels % 32 == 0 &&
       (!a.head_out || (256 % (Hc * Wc) == 0 && Hc * Wc >= 32))) {
     // Cout = 64 (SDG_SWAP64=1, experiment): the weight box still has 128 rows; rows 64..127 lie outside the tensor and are
     // zero filled by TMA, so the M = 128 instruction runs half empty and N stays 256
     CUtensorMap map_w;
     { int rc = tc_encode_2d(&map_w, a.wb, f16, k_cols, Cout, TC_BK, 128); if (rc) return rc; }
-    // tap-shared operand staging (conv_swap_shared_kernel) when a tile is one whole 16 x 16 output grid
-    static const int shared_taps = getenv("SDG_SHARED_TAPS") ? atoi(getenv("SDG_SHARED_TAPS")) : 1;
-    if (shared_taps && Cout == 128 && Hc == 16 && Wc == 16 && !a.general && p.sc_chunks == 0 && (s2 || (taps == 9 && !strided)) &&
-        p.toff == -1) {
+    if (sh_ok) {
       ShSched& sh = p.sh;
       memset(&sh, 0, sizeof(sh));
-      int rows;
-      if (s2) {                                   // 4x4 stride-2 form: copy k = rowclass * 4 + b, taps a = rowclass (roff 0), + 2 (roff 1)
-        sh.n_copy = 8; sh.tpc = 2; rows = 17;
-        for (int rc = 0; rc < 2; ++rc)
-          for (int b = 0; b < 4; ++b) {
-            const int k = rc * 4 + b;
-            sh.col0[k] = (signed char)(b - 1);
-            sh.row0[k] = (signed char)(rc == 0 ? -1 : 0);           // input rows -1, 1, 3, ... (a = 0, 2) or 0, 2, 4, ... (a = 1, 3)
-            const int a0 = rc == 0 ? 0 : 1;
-            sh.wtap[k][0] = (signed char)(a0 * 4 + b); sh.roff[k][0] = 0;
-            sh.wtap[k][1] = (signed char)((a0 + 2) * 4 + b); sh.roff[k][1] = 1;
+      sh.perm = grid8 ? 4 : 0;
+      sh.row_bytes = (grid8 ? 4 * 8 : 16) * 128;
+      int nc = 0;
+      for (int c = 0; c < p.kchunks; ++c) {
+        if (s2) {                                 // 4x4 stride-2 form: copy = (row class, column tap b); taps a = class, class + 2
+          for (int rcl = 0; rcl < 2; ++rcl)
+            for (int b = 0; b < 4; ++b) {
+              ShCopy& cp = sh.cp[nc++];
+              cp.src = 0; cp.chunk = (signed char)c; cp.col0 = (signed char)(b - 1);
+              cp.row0 = (signed char)(rcl == 0 ? -1 : 0);           // input rows -1, 1, 3, ... (a = 0, 2) or 0, 2, 4, ... (a = 1, 3)
+              cp.rows = (signed char)(Hc + 1); cp.ntaps = 2;
+              const int a0 = rcl == 0 ? 0 : 1;
+              cp.wk[0] = (short)((a0 * 4 + b) * p.kchunks + c); cp.roff[0] = 0;
+              cp.wk[1] = (short)(((a0 + 2) * 4 + b) * p.kchunks + c); cp.roff[1] = 1;
+            }
+        } else {                                  // 3x3 stride 1: copy = column tap, taps dy = -1, 0, 1
+          for (int kx = 0; kx < 3; ++kx) {
+            ShCopy& cp = sh.cp[nc++];
+            cp.src = 0; cp.chunk = (signed char)c; cp.col0 = (signed char)(kx - 1); cp.row0 = -1;
+            cp.rows = (signed char)(Hc + 2); cp.ntaps = 3;
+            for (int j = 0; j < 3; ++j) { cp.wk[j] = (short)((j * 3 + kx) * p.kchunks + c); cp.roff[j] = (signed char)j; }
           }
-      } else {                                    // 3x3 stride 1: copy k = dx + 1, taps dy = -1, 0, 1
-        sh.n_copy = 3; sh.tpc = 3; rows = 18;
-        for (int k = 0; k < 3; ++k) {
-          sh.col0[k] = (signed char)(k - 1);
-          sh.row0[k] = -1;
-          for (int j = 0; j < 3; ++j) { sh.wtap[k][j] = (signed char)(j * 3 + k); sh.roff[k][j] = (signed char)j; }
         }
       }
-      sh.row_bytes = Wc * 128;
-      sh.copy_bytes = rows * sh.row_bytes;
-      CUtensorMap map_c;
-      { int rc = encode_act(&map_c, a.in, f16, a.n, Hin, Win, Cin, Wc, rows, 1, es, esx); if (rc) return rc; }
-      const int grid = (int)(a.n < g_num_sms ? a.n : g_num_sms);
-      if (f16) { SDG_LAUNCH(conv_swap_shared_kernel<true>, grid, SW_THREADS, kSwapSharedSmem, s, map_c, map_w, p); }
-      else { SDG_LAUNCH(conv_swap_shared_kernel<false>, grid, SW_THREADS, kSwapSharedSmem, s, map_c, map_w, p); }
+      // folded 1x1 shortcut of a pooled block: the four taps of the 2x2 stride-2 average, each its own parity plane
+      const int main_chunks = p.taps * p.kchunks;
+      for (int st = 0; st < (p.sc_chunks ? 4 : 0); ++st)
+        for (int ch = 0; ch < p.sc_kchunks; ++ch) {
+          ShCopy& cp = sh.cp[nc++];
+          cp.src = 1; cp.chunk = (signed char)ch; cp.col0 = (signed char)(st & 1); cp.row0 = (signed char)(st >> 1);
+          cp.rows = (signed char)Hc; cp.ntaps = 1;
+          cp.wk[0] = (short)(main_chunks + st * p.sc_kchunks + ch); cp.roff[0] = 0;
+        }
+      sh.n_copies = nc;
+      SDG_REQUIRE(nc <= 24, SDG_E_UNSUPPORTED, "conv_tc: tap-shared schedule with %d copies", nc);
+      const int rows_main = s2 ? Hc + 1 : Hc + 2;
+      sh.pitch = (rows_main * sh.row_bytes + 1023) / 1024 * 1024;
+      sh.w_stages = (SH_W_STAGES * TC_A_BYTES + SH_COPIES * sh.pitch <= kSwapSharedSmem - 1024) ? SH_W_STAGES : SH_W_STAGES - 1;
+      SDG_REQUIRE(sh.w_stages * TC_A_BYTES + SH_COPIES * sh.pitch <= kSwapSharedSmem - 1024, SDG_E_UNSUPPORTED,
+                  "conv_tc: tap-shared copies of %d bytes do not fit", sh.pitch);
+      CUtensorMap map_c, map_s2;
+      if (grid8) {
+        { int rc = encode_act_perm(&map_c, a.in, f16, a.n, Hin, Win, Cin, 8, rows_main, 4, es); if (rc) return rc; }
+        if (a.sc_in) { int rc = encode_act_perm(&map_s2, a.sc_in, f16, a.n, Hin, Win, a.sc_C, 8, Hc, 4, es); if (rc) return rc; }
+        else map_s2 = map_c;
+      } else {
+        { int rc = encode_act(&map_c, a.in, f16, a.n, Hin, Win, Cin, Wc, rows_main, 1, es, esx); if (rc) return rc; }
+        map_s2 = map_c;
+      }
+      const long long tiles_sh = grid8 ? (a.n + 3) / 4 : a.n;
+      const int grid = (int)(tiles_sh < g_num_sms ? tiles_sh : g_num_sms);
+      if (f16) { SDG_LAUNCH(conv_swap_shared_kernel<true>, grid, SW_THREADS, kSwapSharedSmem, s, map_c, map_s2, map_w, p); }
+      else { SDG_LAUNCH(conv_swap_shared_kernel<false>, grid, SW_THREADS, kSwapSharedSmem, s, map_c, map_s2, map_w, p); }
       return 0;
     }
     const long long tiles = (p.m_tiles + 1) / 2;
