@@ -176,6 +176,15 @@ SDG_API int sdg_set_conv_pair(int on);
 SDG_API int sdg_first_conv_h16(const void* x, int layout, const void* wb, const float* bias, void* out, int64_t n, int S,
                        int Cout, int precision, void* stream);
 
+/* SNGAN-32 block 1 (torch-mimicry DBlockOptimized(3, 128): c1 -> ReLU -> c2 -> avg_pool2d, + c_sc(avg_pool2d(x)); call site
+ * diagan/trainer/trainer.py:150 through SNGANDiscriminator32.forward) as ONE launch: relu(c1(x)) is built and consumed in shared
+ * memory (conv_b1fused.cu).  out_relu[n,16,16,128] = relu(block1(x)) 16-bit, what sdg_first_conv_h16 followed by
+ * sdg_conv2d_h16(pool = 2, img) writes.  x: uint8 [n,32,32,3]; w1 [128][64] as for sdg_first_conv_h16; w2 [128][2048] in the
+ * 4x4 stride-2 form (K index (a*4+b)*128 + c); bias2 [128] = c2 + shortcut bias; sc_w3 [128][3] fp32;
+ * dbg_t: optional [n,32,32,128] copy of the intermediate tensor (tests), or null. */
+SDG_API int sdg_sngan32_block1_fused_h16(const void* x, const void* w1, const float* b1, const void* w2, const float* bias2,
+                                 const float* sc_w3, void* out_relu, void* dbg_t, int64_t n, int precision, void* stream);
+
 /* ---- dataset transform (the input pipeline of the pass) ----------------------
  * Replaces transforms.Resize(size) + transforms.CenterCrop(size) of datasets/transform.py:3-41 as applied to every item of
  * every recording pass by the reference's DataLoader workers: one pass over the raw uint8 dataset in [n,H,W,C] (C = 3 or 1)

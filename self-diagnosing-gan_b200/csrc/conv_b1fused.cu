@@ -1,0 +1,563 @@
+// conv_b1fused.cu -- SNGAN-32 block 1 (DBlockOptimized) as ONE kernel: the 256 KB / sample tensor relu(c1(x)) never leaves the SM.
+//
+// Replaces, for torch-mimicry's DBlockOptimized(3, 128) of SNGANDiscriminator32 (call site trainer.py:150):
+//     T   = relu(conv3x3(normalise(x)) + b1)                        (first_conv_kernel: 3 KB in, 256 KB out per sample)
+//     out = relu(avg_pool2d(conv3x3(T) + b2) + Wsc . avg_pool2d(x) + bsc)   (conv_swap_shared_kernel, 4x4 stride-2 form:
+//                                                                            256 KB in, 64 KB out per sample)
+// Unfused, T is the largest stream of the whole pass (HBM write-bound first conv: 17 % of the SNGAN-32 forward) and its re-read
+// is what makes block1.c2 operand-ingest bound.  Here a CTA PAIR owns one image (CTA rank s = the left / right strip of 8 output
+// columns), builds its strip of T in shared memory with the first conv's own arithmetic (same LUT-normalised 16-bit operand,
+// same K = 32 tcgen05.mma with the bias in columns 27 / 28, same cvt.rn.relu rounding: T is bit-identical to first_conv's),
+// and runs the 4x4 stride-2 form of c2 as tcgen05.mma.cta_group::2 with M = 256 pixels (128 per CTA) x N = 128 channels
+// straight from that tile.  Only the weights stream (8 KB per CTA per 256 MMA cycles = 32 B per cycle).
+//
+// T in shared memory uses the NO-SWIZZLE K-major UMMA layout: 16-byte cells (8 channels of one pixel); 8 consecutive M rows
+// 16 bytes apart, groups of 8 rows SBO apart, the two K halves of an instruction LBO apart.  With SBO = one plane row the 8-row
+// groups are the tile's 16 output rows, so a tap's ROW shift and its COLUMN shift are both just a different descriptor start
+// address (the 128B-swizzled layout cannot express a one-pixel column shift; that is why the unfused kernel needs one staged
+// copy per column variant, and why a resident T did not fit before: profiles/r2b_swap_kernel_limiters.md section 4).
+//   T cell (ty, tx, k8):  ty = 2R + pr in 0..33 (image row + 1), tx = 2C + pc in 0..17 (image column - 16 s + 1)
+//       byte offset ((pr*2 + pc)*16 + k8) * 2448 + R * 144 + C * 16            4 parity planes x 16 x (17 rows x 9 cells) = 153 KB
+//   tap (ky, kx) of output pixel (r, c): plane (ky & 1, kx & 1), R = r + (ky >> 1), C = c + (kx >> 1).
+// The halo cells (ty = 0, 33; tx = 0 for s = 0, tx = 17 for s = 1) are zeroed once and never written.
+//
+// Pipeline (per CTA; all barriers as in conv_pair_stream_kernel: "full"-type barriers live in the leader and are signalled by
+// both CTAs, "empty"-type ones are multicast by the leader's tcgen05.commit):
+//   unit = one ROW-PARITY half of T (272 pixels): c2's taps ky in {1, 3} read only odd ty, ky in {0, 2} only even ty, so while
+//   the tensor pipe runs the 64 MMAs of one half, the T warps rebuild the other half for the next image: no second T buffer.
+//   T warps (4..7 and 12..15): gather 128 pixels x 27 bytes -> A1 (no-swizzle im2col tile, double-buffered) -> [c1 MMA, K = 32]
+//   -> TMEM -> relu/convert -> T cells; three batches per unit (128 + 128 + 16 pixels); the two sets split the K columns of the
+//   gather and the channels of the drain.  Epilogue warps (8..11): TMEM -> + bias + 3-FMA image shortcut -> relu -> 16-bit NHWC.
+//   Warp 0: weight TMA, warp 1: c2 MMA issuer, warp 3: c1 MMA issuer (leader CTA), warp 2: TMEM.
+#include <cstdlib>
+
+#include "tc_ptx.cuh"
+
+namespace sdg {
+
+constexpr int BF_THREADS = 512;
+constexpr int BF_T_THREADS = 256;                       // two sets of four T warps (4..7 and 12..15)
+constexpr int BF_W_STAGES = 5;
+constexpr int BF_W_MAX = 20;                            // barrier slots (timing experiments run deeper rings over T's memory)
+constexpr int BF_W_BYTES = 64 * 64 * 2;                 // 8 KB: this CTA's 64 output channels x 64 k
+constexpr int BF_ROW = 9 * 16;                          // 144: one plane row = 9 cells
+constexpr int BF_K8 = 17 * BF_ROW;                      // 2448: 17 plane rows per 8-channel group
+constexpr int BF_PLANE = 16 * BF_K8;                    // 39168 per (row parity, column parity)
+constexpr int BF_T_BYTES = 4 * BF_PLANE;                // 156672
+constexpr int BF_A1_BYTES = 4 * 128 * 16;               // 8192: [k8 0..3][128 pixels] x 16 B
+constexpr int BF_W1_BYTES = 4 * 64 * 16;                // 4096: [k8 0..3][64 channels] x 16 B
+constexpr int BF_X_ROWB = 64;                           // raw image rows: 56 bytes of the strip's 18 columns at offset 4
+constexpr int BF_X_BYTES = 32 * BF_X_ROWB;              // the image rows of the NEXT tile, as they land (cp.async)
+constexpr int BF_P_ROWB = 160;                          // normalised 16-bit patch: 19 pixels x (c0, c1, c2, pad) per row
+constexpr int BF_P_BYTES = 34 * BF_P_ROWB;              // rows -1..32, columns 15 s - 1 .. 15 s + 17; out-of-image pixels stay zero
+constexpr int BF_OFF_T = BF_W_STAGES * BF_W_BYTES;
+constexpr int BF_OFF_A1 = BF_OFF_T + BF_T_BYTES;
+constexpr int BF_OFF_W1 = BF_OFF_A1 + 2 * BF_A1_BYTES;  // A1 is double-buffered
+constexpr int BF_OFF_X = BF_OFF_W1 + BF_W1_BYTES;
+constexpr int BF_OFF_P = BF_OFF_X + BF_X_BYTES;
+constexpr int kB1FusedSmem = 1024 + BF_OFF_P + BF_P_BYTES;
+static_assert(kB1FusedSmem <= 227 * 1024 - 4096, "b1_fused_kernel: shared memory budget");
+
+struct BfParams {
+  const uint8_t* x;          // [n][32][32][3]
+  const h16* w1;             // [128][64] K-major, k = (ky*3+kx)*3 + c (27 real columns)
+  const float* b1;           // [128]
+  const float* bias2;        // [128] c2 bias + shortcut bias
+  const float* sc_w3;        // [128][3] fp32, W_sc / sigma
+  h16* out_relu;             // [n][16][16][128]
+  h16* dbg_t;                // [n][32][32][128] copy of T (tests only) or null
+  int* ovf;                  // fp16 range guard flag or null
+  long long n_images;
+  int w_stages;              // weight ring depth in use (2..BF_W_STAGES).  tcgen05.mma executes in issue order, so the ring depth also
+                             // bounds how many c2 chunks (256 MMA cycles each) can be queued ahead of a c1 batch.
+                             // (SDG_TIMING_EXPERIMENTS builds accept deeper rings that overwrite T: wrong results)
+  int dbg;                   // SDG_TIMING_EXPERIMENTS builds only (WRONG results): 1 no gather, 2 no T drain, 4 no c2 epilogue, 8 no c1 MMAs,
+                             // 16 no c2 MMAs
+};
+
+// K-major operand without swizzle: rows of a group 16 B apart, 8-row groups `sbo` bytes apart, K halves `lbo` bytes apart
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;                                             // layout type 0 = SWIZZLE_NONE
+}
+
+// weight chunk `idx` (0..15) of phase `ph`: ph 0 = taps ky in {1, 3} (odd T rows), ph 1 = ky in {0, 2}; kx 0..3; h = 64-channel half
+__device__ __forceinline__ void bf_chunk(int ph, int idx, int& ky, int& kx, int& h) {
+  ky = (ph == 0 ? 1 : 0) + 2 * (idx >> 3);
+  kx = (idx >> 1) & 3;
+  h = idx & 1;
+}
+
+// pixel `m` of batch `b` of the unit with row parity `pr`, strip `s`: cell (R, C) of column-parity plane pc
+__device__ __forceinline__ bool bf_pixel(int s, int pr, int b, int m, int& R, int& C, int& pc) {
+  int rr;
+  bool valid = true;
+  if (b == 0) {                                         // the 8-column parity plane: 16 rows x 8 cells
+    rr = m >> 3; C = (m & 7) + (1 - s); pc = s;
+  } else {                                              // the 9-column one: 144 cells in address order
+    const int idx = (b - 1) * 128 + m;
+    valid = idx < 144;
+    rr = idx / 9; C = idx - rr * 9; pc = 1 - s;
+  }
+  R = rr + (pr ? 0 : 1);
+  return valid;
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(BF_THREADS, 1)
+b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  __shared__ __align__(8) uint64_t bar_wfull[BF_W_MAX];
+  __shared__ __align__(8) uint64_t bar_wempty[BF_W_MAX];
+  __shared__ __align__(8) uint64_t bar_a1_full[2];
+  __shared__ __align__(8) uint64_t bar_c1_full[2];
+  __shared__ __align__(8) uint64_t bar_c1_empty[2];
+  __shared__ __align__(8) uint64_t bar_t_ready[2];
+  __shared__ __align__(8) uint64_t bar_t_free[2];
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ uint16_t s_lut[256];
+  __shared__ __align__(16) float s_bias[128];
+  __shared__ __align__(16) float s_w3[128 * 3];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int s = (int)rank;                              // strip: output columns 8s .. 8s+7
+  const bool leader = rank == 0;
+#ifdef SDG_TIMING_EXPERIMENTS
+  const int dbg = p.dbg;
+#else
+  constexpr int dbg = 0;
+#endif
+  const int w_stages = p.w_stages;
+
+  // ---- one-time setup ----
+  if (threadIdx.x < 256) {
+    float v = __fdiv_rn((float)threadIdx.x, 255.0f);
+    v = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
+    s_lut[threadIdx.x] = (uint16_t)(pack_h2<F16>(v, 0.f) & 0xffffu);
+  }
+  for (int i = threadIdx.x; i < 128; i += BF_THREADS) s_bias[i] = p.bias2[i];
+  for (int i = threadIdx.x; i < 128 * 3; i += BF_THREADS) s_w3[i] = p.sc_w3[i];
+  for (int i = threadIdx.x; i < BF_T_BYTES / 16; i += BF_THREADS)
+    reinterpret_cast<uint4*>(smem_gen + BF_OFF_T)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < BF_P_BYTES / 16; i += BF_THREADS)
+    reinterpret_cast<uint4*>(smem_gen + BF_OFF_P)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // c1 weights of this CTA's 64 channels, no-swizzle [k8][row]; the bias rides in K columns 27 (hi) and 28 (lo)
+  for (int i = threadIdx.x; i < 64 * 4; i += BF_THREADS) {
+    const int r = i >> 2, j = i & 3;
+    const int o = s * 64 + r;
+    uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.w1) + o * 128 + j * 16);
+    if (j == 3) {
+      const float b = p.b1[o];
+      const uint32_t hi = pack_h2<F16>(b, 0.f) & 0xffffu;
+      const float bhi = unpack_h2<F16>(hi).x;
+      const uint32_t lo = pack_h2<F16>(b - bhi, 0.f) & 0xffffu;
+      w.y = (w.y & 0x0000ffffu) | (hi << 16);           // k = 27
+      w.z = (w.z & 0xffff0000u) | lo;                   // k = 28
+    }
+    *reinterpret_cast<uint4*>(smem_gen + BF_OFF_W1 + j * 1024 + r * 16) = w;
+  }
+  fence_proxy_async_smem();
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&map_w2);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < BF_W_MAX; ++i) {
+      mbar_init(smem_u32(&bar_wfull[i]), 1);
+      mbar_init(smem_u32(&bar_wempty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_a1_full[i]), 16);         // 8 T warps x 2 CTAs
+      mbar_init(smem_u32(&bar_c1_full[i]), 1);
+      mbar_init(smem_u32(&bar_c1_empty[i]), 16);
+      mbar_init(smem_u32(&bar_t_ready[i]), 16);
+      mbar_init(smem_u32(&bar_t_free[i]), 1);
+      mbar_init(smem_u32(&bar_acc_full[i]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[i]), 8);        // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const long long cluster_id = blockIdx.x >> 1;
+  const long long n_clusters = gridDim.x >> 1;
+  const long long my_tiles = cluster_id < p.n_images ? (p.n_images - cluster_id + n_clusters - 1) / n_clusters : 0;
+  const uint32_t t_base = smem_base + BF_OFF_T;
+  const bool t_warp = (warp >= 4 && warp < 8) || warp >= 12;
+
+  if (warp == 0) {
+    // ================= weight producer: this CTA's 64 rows of every [128 x 64] K chunk, in consumption order =================
+    if (elect_one()) {
+      int ws = 0;
+      uint32_t phase = 0;
+      for (long long l = 0; l < my_tiles; ++l) {
+        for (int ph = 0; ph < 2; ++ph) {
+          for (int idx = 0; idx < 16; ++idx) {
+            int ky, kx, h;
+            bf_chunk(ph, idx, ky, kx, h);
+            const int it = (ky * 4 + kx) * 2 + h;
+            mbar_wait(smem_u32(&bar_wempty[ws]), phase ^ 1u);
+            if (leader) mbar_expect_tx(smem_u32(&bar_wfull[ws]), 2 * BF_W_BYTES);
+            tma_load_2d_pair(smem_base + ws * BF_W_BYTES, &map_w2, mapa_u32(smem_u32(&bar_wfull[ws]), 0), it * 64, (int)rank * 64);
+            if (++ws == w_stages) { ws = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= c2 MMA issuer (leader CTA only): 16 K chunks x 4 MMAs per unit =================
+    // One thread's barrier instructions cost ~100 cycles each even when the phase is already complete, and a chunk is only 256
+    // MMA cycles: the loop below touches ONE barrier per chunk and tests the next stage's barrier before issuing this stage's
+    // MMAs so that the test's latency hides behind them; c1's batches have their own issuer (warp 3).
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc(256, 128, F16);
+      // every address below is loop invariant; a single thread pays ~10 cycles per dependent instruction, so nothing is
+      // recomputed per chunk: barrier addresses advance by 8, the weight descriptor by 8 KB >> 4, and T's descriptors are
+      // compile-time offsets from t_base (the 16 chunks of a phase are unrolled)
+      const uint32_t wfull0 = smem_u32(&bar_wfull[0]), wempty0 = smem_u32(&bar_wempty[0]);
+      const uint32_t w_wrap = (uint32_t)w_stages * 8u;
+      const uint64_t t_desc0 = make_nosw_desc(t_base, BF_K8, BF_ROW);
+      const uint64_t w_desc0 = make_sw128_desc(smem_base);
+      uint32_t wo = 0;                                  // 8 * stage
+      uint32_t wphase = 0;
+      bool ready = false;                               // stage wo / 8 is known to be full
+      for (long long l = 0; l < my_tiles; ++l) {
+        const int acc = (int)(l & 1);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          mbar_wait(smem_u32(&bar_t_ready[ph]), (uint32_t)(l & 1));
+          if (ph == 0) mbar_wait(smem_u32(&bar_acc_empty[acc]), (uint32_t)(((l >> 1) & 1) ^ 1));
+          tc_fence_after();
+#pragma unroll
+          for (int idx = 0; idx < 16; ++idx) {
+            const int ky = (ph == 0 ? 1 : 0) + 2 * (idx >> 3), kx = (idx >> 1) & 3, h = idx & 1;      // = bf_chunk(ph, idx)
+            constexpr int kStep = (2 * BF_K8) >> 4;
+            const int a_off = ((((ky & 1) * 2 + (kx & 1)) * 16 + h * 8) * BF_K8 + (ky >> 1) * BF_ROW + (kx >> 1) * 16) >> 4;
+            if (!ready) mbar_wait(wfull0 + wo, wphase);
+            tc_fence_after();
+            const uint32_t cur = wo;
+            wo += 8u;
+            if (wo == w_wrap) { wo = 0; wphase ^= 1u; }
+            ready = mbar_try_wait(wfull0 + wo, wphase);                     // next stage: consumed after the MMAs below
+            const uint64_t adesc = t_desc0 + (uint64_t)a_off;
+            const uint64_t bdesc = w_desc0 + (uint64_t)(cur * (BF_W_BYTES / 16 / 8));
+            if (!(dbg & 16)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_pair(d_tmem, adesc + (uint64_t)(j * kStep), bdesc + (uint64_t)(2 * j), idesc, (ph | idx | j) != 0 ? 1u : 0u);
+            }
+            umma_commit_pair(wempty0 + cur, 3);
+          }
+          umma_commit_pair(smem_u32(&bar_t_free[ph]), 3);            // this half of T may be rebuilt once these MMAs retire
+          if (ph == 1) umma_commit_pair(smem_u32(&bar_acc_full[acc]), 3);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ================= c1 MMA issuer (leader CTA only): one K = 32 batch of 256 pixels whenever both CTAs have built it =================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc(256, 128, F16);
+      const uint64_t a1desc = make_nosw_desc(smem_base + BF_OFF_A1, 2048, 128);
+      const uint64_t w1desc = make_nosw_desc(smem_base + BF_OFF_W1, 1024, 128);
+      const long long g_total = 6 * my_tiles;
+      for (long long g = 0; g < g_total; ++g) {
+        const int cb = (int)(g & 1);
+        const uint32_t par = (uint32_t)((g >> 1) & 1);
+        mbar_wait(smem_u32(&bar_a1_full[cb]), par);
+        mbar_wait(smem_u32(&bar_c1_empty[cb]), par ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + 256u + (uint32_t)(cb * 128);
+        const uint64_t ad = a1desc + (uint64_t)(cb * (BF_A1_BYTES >> 4));
+        if (!(dbg & 8)) {
+          umma_pair(d, ad, w1desc, idesc, 0u);                              // k = 0..15
+          umma_pair(d, ad + 256u, w1desc + 128u, idesc, 1u);                // k = 16..31 (27, 28: bias; 29..31 zero)
+        }
+        umma_commit_pair(smem_u32(&bar_c1_full[cb]), 3);
+      }
+    }
+  } else if (t_warp) {
+    // ================= T warps: raw rows -> im2col batch -> [c1 MMA] -> relu / convert -> T cells =================
+    // two sets of four warps (TMEM lane quadrant = warp & 3 in both): set 0 gathers K columns 0..15 and drains channels
+    // 0..63 of every batch, set 1 the other halves
+    const int set = warp >= 12 ? 1 : 0;
+    const int q = warp & 3;
+    const int tt = q * 32 + lane;                       // batch pixel = TMEM lane
+    const int t256 = set * 128 + tt;
+    const int goff = s ? 40 : 0;                        // first byte of an image row held in the landing buffer
+    constexpr uint32_t kOne = F16 ? 0x3C00u : 0x3F80u;
+    // raw rows of tile l -> the (single) landing buffer; the strip needs image columns 15 s - 1 .. 15 s + 17 = bytes goff .. goff + 55
+    auto prefetch_x = [&](long long l) {
+      if (l < my_tiles) {
+        const long long n = cluster_id + l * n_clusters;
+        const uint8_t* src = p.x + n * 3072 + goff;
+        const uint32_t dst = smem_base + BF_OFF_X + 4;
+        for (int w = t256; w < 32 * 14; w += BF_T_THREADS) {
+          const int row = w / 14, wi = w - row * 14;
+          cp_async_4(dst + row * BF_X_ROWB + wi * 4, src + row * 96 + wi * 4);
+        }
+      }
+      cp_async_commit();
+    };
+    // landed bytes -> normalised 16-bit patch (the first conv's lookup table, applied ONCE per byte instead of once per tap):
+    // patch pixel (ry, cx) = image pixel (ry - 1, 15 s - 1 + cx) as (c0, c1, c2, 0); 18 in-image columns per row
+    auto convert_x = [&]() {
+      const uint8_t* raw = smem_gen + BF_OFF_X + 4;
+      for (int i = t256; i < 32 * 18; i += BF_T_THREADS) {
+        const int row = i / 18, j = i - row * 18;       // j-th in-image pixel of the row: image column (s ? 14 : 0) + j
+        const uint8_t* b = raw + row * BF_X_ROWB + 3 * ((s ? 14 : 0) + j) - goff;
+        const uint32_t lo = (uint32_t)s_lut[b[0]] | ((uint32_t)s_lut[b[1]] << 16), hi = (uint32_t)s_lut[b[2]];
+        *reinterpret_cast<uint2*>(smem_gen + BF_OFF_P + (row + 1) * BF_P_ROWB + (j + (s ? 0 : 1)) * 8) = make_uint2(lo, hi);
+      }
+    };
+    // gather this set's 16 K columns of batch pixel tt of (unit uu, batch b) of the tile in the patch into A1[gb]:
+    // K column k = (ky*3 + kx)*3 + c for k < 27; 27, 28 = 1.0 (bias hi / lo); 29..31 = 0
+    auto build_a1 = [&](int uu, int b, int gb) {
+      const int pr = 1 - uu;
+      int R, C, pc;
+      const bool valid = bf_pixel(s, pr, b, tt, R, C, pc);
+      if (valid && !(dbg & 1)) {
+        const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;
+        // pixel (y + ky - 1, x - 1) of tap row ky: patch row y + ky, patch column x - 1 - (15 s - 1) = x - 15 s
+        const uint2* row0 = reinterpret_cast<const uint2*>(smem_gen + BF_OFF_P + y * BF_P_ROWB + (x - 15 * s) * 8);
+        const uint2* row1 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(row0) + BF_P_ROWB);
+        const uint2* row2 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(row0) + 2 * BF_P_ROWB);
+        uint32_t w[8];
+        if (set == 0) {
+          const uint2 a0 = row0[0], a1 = row0[1], a2 = row0[2], b0 = row1[0], b1 = row1[1], b2 = row1[2];
+          w[0] = a0.x;
+          w[1] = __byte_perm(a0.y, a1.x, 0x5410);       // lo16(a0.y) | lo16(a1.x) << 16
+          w[2] = __byte_perm(a1.x, a1.y, 0x5432);       // hi16(a1.x) | lo16(a1.y) << 16
+          w[3] = a2.x;
+          w[4] = __byte_perm(a2.y, b0.x, 0x5410);
+          w[5] = __byte_perm(b0.x, b0.y, 0x5432);
+          w[6] = b1.x;
+          w[7] = __byte_perm(b1.y, b2.x, 0x5410);
+        } else {
+          const uint2 b2 = row1[2], c0 = row2[0], c1 = row2[1], c2 = row2[2];
+          w[0] = __byte_perm(b2.x, b2.y, 0x5432);
+          w[1] = c0.x;
+          w[2] = __byte_perm(c0.y, c1.x, 0x5410);
+          w[3] = __byte_perm(c1.x, c1.y, 0x5432);
+          w[4] = c2.x;
+          w[5] = (c2.y & 0xffffu) | (kOne << 16);
+          w[6] = kOne;
+          w[7] = 0u;
+        }
+        uint8_t* row = smem_gen + BF_OFF_A1 + gb * BF_A1_BYTES + (2 * set) * 2048 + tt * 16;
+        *reinterpret_cast<uint4*>(row) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(row + 2048) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_a1_full[gb]), 0));
+    };
+    if (my_tiles > 0) {
+      prefetch_x(0);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      named_bar_sync(1, BF_T_THREADS);
+      convert_x();
+      named_bar_sync(1, BF_T_THREADS);
+      prefetch_x(1);
+      build_a1(0, 0, 0);
+    }
+    long long g = 0;
+    uint32_t vmaxw = 0;                                 // fp16 range guard: running maximum of the (non-negative) packed halves
+    for (long long l = 0; l < my_tiles; ++l) {
+      const long long n = cluster_id + l * n_clusters;
+      for (int uu = 0; uu < 2; ++uu) {
+        const int pr = 1 - uu;
+        for (int b = 0; b < 3; ++b, ++g) {
+          const int cb = (int)(g & 1);
+          // the next batch's operand first (its buffer was read by batch g - 1, whose completion this thread has seen), so
+          // that its MMA overlaps this batch's drain
+          if (b < 2) build_a1(uu, b + 1, cb ^ 1);
+          else if (uu == 0) build_a1(1, 0, cb ^ 1);
+          else if (l + 1 < my_tiles) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");                // the next image's rows have landed
+            named_bar_sync(1, BF_T_THREADS);                                    // ... for every T thread, and nobody reads this image's patch any more
+            convert_x();
+            named_bar_sync(1, BF_T_THREADS);                                    // patch complete, landing buffer idle
+            prefetch_x(l + 2);
+            build_a1(0, 0, cb ^ 1);
+          }
+          mbar_wait(smem_u32(&bar_c1_full[cb]), (uint32_t)((g >> 1) & 1));      // batch g is in TMEM
+          tc_fence_after();
+          if (b == 0) mbar_wait(smem_u32(&bar_t_free[uu]), (uint32_t)((l & 1) ^ 1));   // c2 is done with this half of T
+          int R, C, pc;
+          const bool valid = bf_pixel(s, pr, b, tt, R, C, pc);
+          if ((b < 2 || q == 0) && !(dbg & 2)) {
+            uint8_t* cell = smem_gen + BF_OFF_T + ((pr * 2 + pc) * 16 + set * 8) * BF_K8 + R * BF_ROW + C * 16;
+            const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;
+            const uint32_t taddr = tmem_base + 256u + (uint32_t)(cb * 128 + set * 64) + ((uint32_t)(q * 32) << 16);
+            uint32_t r[64];
+            tmem_ld32(taddr, r);
+            tmem_ld32(taddr + 32u, r + 32);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int gq = 0; gq < 8; ++gq) {
+                uint4 pk;
+                pk.x = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]));
+                pk.y = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
+                pk.z = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+                pk.w = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
+                if (F16) vmaxw = __vmaxu2(__vmaxu2(vmaxw, pk.x), __vmaxu2(__vmaxu2(pk.y, pk.z), pk.w));
+                *reinterpret_cast<uint4*>(cell + gq * BF_K8) = pk;
+                if (p.dbg_t)
+                  *reinterpret_cast<uint4*>(p.dbg_t + (((n * 32 + y) * 32 + x) * 128 + set * 64 + gq * 8)) = pk;
+              }
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async_smem();                     // T cells -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_c1_empty[cb]), 0));
+        }
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_t_ready[uu]), 0));
+      }
+    }
+    // post-ReLU halves are non-negative: inf / NaN <=> a half >= 0x7C00
+    if (F16 && ((vmaxw & 0xffffu) >= 0x7C00u || (vmaxw >> 16) >= 0x7C00u)) range_flag_set(p.ovf, SDG_RANGE_ACT);
+  } else if (warp >= 8 && warp < 12) {
+    // ================= c2 epilogue: this CTA's 128 output pixels x 128 channels =================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int oy = m >> 3, ox = 8 * s + (m & 7);
+    const int g4 = lane >> 2, i4 = lane & 3;
+    uint32_t vmaxw = 0;
+    for (long long l = 0; l < my_tiles; ++l) {
+      const long long n = cluster_id + l * n_clusters;
+      const int acc = (int)(l & 1);
+      // avg_pool2d of the normalised network input at this output pixel (DBlockOptimized shortcut input)
+      float px[3];
+      {
+        const uint8_t* ip = p.x + ((n * 32 + 2 * oy) * 32 + 2 * ox) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          auto nv = [&](int off) {
+            const float v = __fdiv_rn((float)ip[off + c], 255.0f);
+            return __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
+          };
+          px[c] = (nv(0) + nv(3) + nv(96) + nv(99)) * 0.25f;
+        }
+      }
+      mbar_wait(smem_u32(&bar_acc_full[acc]), (uint32_t)((l >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
+      if (!(dbg & 4)) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * g);
+          v[4 * g] = __uint_as_float(r[4 * g]) + b4.x; v[4 * g + 1] = __uint_as_float(r[4 * g + 1]) + b4.y;
+          v[4 * g + 2] = __uint_as_float(r[4 * g + 2]) + b4.z; v[4 * g + 3] = __uint_as_float(r[4 * g + 3]) + b4.w;
+        }
+        {
+          float w3[96];
+#pragma unroll
+          for (int g = 0; g < 24; ++g) {
+            const float4 t = *reinterpret_cast<const float4*>(s_w3 + c0 * 3 + 4 * g);
+            w3[4 * g] = t.x; w3[4 * g + 1] = t.y; w3[4 * g + 2] = t.z; w3[4 * g + 3] = t.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = fmaf(w3[3 * j], px[0], fmaf(w3[3 * j + 1], px[1], fmaf(w3[3 * j + 2], px[2], v[j])));
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          pk[j] = pack_relu_h2<F16>(v[2 * j], v[2 * j + 1]);
+          if (F16) vmaxw = __vmaxu2(vmaxw, pk[j]);
+        }
+        // 4 x 4 transpose inside each group of 4 lanes: 4 lanes then write the 64 contiguous bytes of ONE pixel
+        warp_transpose4_u4(pk, lane);
+#pragma unroll
+        for (int mm = 0; mm < 4; ++mm) {
+          const int m2 = q * 32 + g4 * 4 + mm;
+          const long long opix = (n * 16 + (m2 >> 3)) * 16 + 8 * s + (m2 & 7);
+          *reinterpret_cast<uint4*>(p.out_relu + opix * 128 + c0 + i4 * 8) = make_uint4(pk[4 * mm], pk[4 * mm + 1], pk[4 * mm + 2], pk[4 * mm + 3]);
+        }
+      }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_acc_empty[acc]), 0));
+    }
+    if (F16 && ((vmaxw & 0xffffu) >= 0x7C00u || (vmaxw >> 16) >= 0x7C00u)) range_flag_set(p.ovf, SDG_RANGE_ACT);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+int b1_fused_init() {
+  SDG_CUDA(cudaFuncSetAttribute(b1_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1FusedSmem));
+  SDG_CUDA(cudaFuncSetAttribute(b1_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1FusedSmem));
+  return 0;
+}
+
+int b1_fused(const void* x, const h16* w1, const float* b1, const h16* w2, const float* bias2, const float* sc_w3, h16* out_relu,
+             h16* dbg_t, int64_t n, int f16, cudaStream_t s) {
+  SDG_REQUIRE(x && w1 && b1 && w2 && bias2 && sc_w3 && out_relu, SDG_E_INVALID, "b1_fused: null pointer");
+  auto al16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
+  SDG_REQUIRE(((uintptr_t)x % 4) == 0 && al16(w1) && al16(w2) && al16(out_relu) && al16(dbg_t), SDG_E_INVALID,
+              "b1_fused: misaligned pointer");
+  if (n == 0) return 0;
+  CUtensorMap map_w2;
+  { int rc = tc_encode_2d(&map_w2, w2, f16, 16 * 128, 128, 64, 64); if (rc) return rc; }
+  BfParams p;
+  p.x = (const uint8_t*)x; p.w1 = w1; p.b1 = b1; p.bias2 = bias2; p.sc_w3 = sc_w3; p.out_relu = out_relu; p.dbg_t = dbg_t;
+  p.ovf = t_range_flag; p.n_images = n;
+  static const int ws_env = getenv("SDG_B1_WSTAGES") ? atoi(getenv("SDG_B1_WSTAGES")) : BF_W_STAGES;
+  p.w_stages = ws_env >= 2 && ws_env <= BF_W_STAGES ? ws_env : BF_W_STAGES;
+  p.dbg = 0;
+#ifdef SDG_TIMING_EXPERIMENTS
+  static const int dbg_env = getenv("SDG_B1_DEBUG") ? atoi(getenv("SDG_B1_DEBUG")) : 0;
+  p.dbg = dbg_env;
+  if (ws_env > BF_W_STAGES && ws_env <= 19) p.w_stages = ws_env;
+#endif
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(tc_num_sms() / 2 * 2));
+  cfg.blockDim = dim3(BF_THREADS);
+  cfg.dynamicSmemBytes = kB1FusedSmem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  // the tile schedule is static (tile = cluster + l * clusters): every cluster of the grid must be resident at once, and a GPC
+  // with an odd number of free SMs cannot host a CTA pair on its last one -- ask the driver how many pairs fit
+  long long clusters = tc_max_active_clusters(f16 ? (const void*)b1_fused_kernel<true> : (const void*)b1_fused_kernel<false>, &cfg);
+  if (clusters < 1) clusters = 1;
+  if (n < clusters) clusters = n;
+  cfg.gridDim = dim3((unsigned)(2 * clusters));
+  if (f16) { SDG_CUDA(cudaLaunchKernelEx(&cfg, b1_fused_kernel<true>, map_w2, p)); }
+  else { SDG_CUDA(cudaLaunchKernelEx(&cfg, b1_fused_kernel<false>, map_w2, p)); }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+}  // namespace sdg

@@ -195,26 +195,7 @@ __device__ __forceinline__ void warp_transpose8_f4(float (&t)[32], int lane) {
   }
 }
 
-// Same idea for the 16-bit outputs: a row's 32 columns are 4 x 16 B; a 4 x 4 transpose inside each group of 4 lanes
-// lets 4 lanes write the 64 contiguous bytes of ONE row (8 rows per instruction) instead of 32 lanes x 16 B on 32 rows.
-__device__ __forceinline__ void warp_transpose4_u4(uint32_t (&t)[16], int lane) {
-#pragma unroll
-  for (int s = 2; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if ((j & s) == 0) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t a = t[4 * j + e], b = t[4 * (j + s) + e];
-          const uint32_t recv = __shfl_xor_sync(0xffffffffu, up ? a : b, s);
-          t[4 * j + e] = up ? recv : a;
-          t[4 * (j + s) + e] = up ? b : recv;
-        }
-      }
-    }
-  }
-}
+// (warp_transpose4_u4, the 4 x 4 variant for the 16-bit outputs, lives in tc_ptx.cuh: conv_b1fused.cu uses it too)
 
 // store this warp's 32 rows x 32 columns of 16-bit values (pk = the lane's own row, 16 packed words) coalesced
 __device__ __forceinline__ void store_rows16_coalesced(h16* base, long long wpix, long long total_pixels, int Cout, int col0,
@@ -1553,6 +1534,25 @@ constexpr int tc_smem_bytes() { return TC_STAGES * (TC_A_BYTES + BN * TC_BK * 2)
 
 int tc_num_sms() { return g_num_sms; }
 
+int tc_max_active_clusters(const void* kernel, const cudaLaunchConfig_t* cfg) {
+  struct Entry { const void* k; int dev; size_t smem; int n; };
+  static Entry cache[32];
+  static std::atomic<int> n_cached{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int nc = n_cached.load(std::memory_order_acquire);
+  for (int i = 0; i < nc; ++i)
+    if (cache[i].k == kernel && cache[i].dev == dev && cache[i].smem == cfg->dynamicSmemBytes) return cache[i].n;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  static const int verbose = getenv("SDG_VERBOSE") ? atoi(getenv("SDG_VERBOSE")) : 0;
+  if (verbose) fprintf(stderr, "sdg: %d clusters of %u CTAs x %u threads, %zu B dynamic smem resident at once\n", n,
+                       cfg->numAttrs ? cfg->attrs[0].val.clusterDim.x : 1, cfg->blockDim.x, cfg->dynamicSmemBytes);
+  const int slot = n_cached.load(std::memory_order_relaxed);
+  if (slot < 32) { cache[slot] = {kernel, dev, cfg->dynamicSmemBytes, n}; n_cached.store(slot + 1, std::memory_order_release); }
+  return n;
+}
+
 constexpr int kPairSmemMax = 227 * 1024 - 3072;       // dynamic shared memory budget of the pair kernel (static: ~2.5 KB)
 constexpr int kStreamSmem = 1024 + 6 * (TC_A_BYTES + 128 * TC_BK * 2);   // 6 x 32 KB (BN 256) = 8 x 24 KB (BN 128) stages
 static int g_pair_mode = 1;                          // 0 = single-CTA pixel-major kernels only, 1 = default selection (role-swapped,
@@ -1641,6 +1641,8 @@ int conv_tc_init(int device) {
   SDG_CUDA(cudaFuncSetAttribute((conv_pair_stream_kernel<128, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
   g_encode = (EncodeTiledFn)fn;
   int rc = first_conv_init();
+  if (rc) return rc;
+  rc = b1_fused_init();
   if (rc) return rc;
   if (device >= 0 && device < 64) g_dev_init.fetch_or(1ULL << device, std::memory_order_release);
   return 0;
@@ -1870,6 +1872,12 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    {
+      cfg.gridDim = dim3((unsigned)(g_num_sms / 2 * 2));
+      const long long fit = tc_max_active_clusters(f16 ? (const void*)conv_pair_kernel<true> : (const void*)conv_pair_kernel<false>, &cfg);
+      if (fit >= 1 && fit < clusters) clusters = fit;
+      cfg.gridDim = dim3((unsigned)(2 * clusters));
+    }
     if (f16) { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<true>, map_a, map_bh, map_s, p, n_stages)); }
     else { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<false>, map_a, map_bh, map_s, p, n_stages)); }
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1900,6 +1908,15 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    {
+      // static tile schedule: all clusters must be resident at once (a GPC with an odd number of free SMs strands one)
+      const void* kfn = sbn == 256 ? (f16 ? (const void*)conv_pair_stream_kernel<256, true> : (const void*)conv_pair_stream_kernel<256, false>)
+                                   : (f16 ? (const void*)conv_pair_stream_kernel<128, true> : (const void*)conv_pair_stream_kernel<128, false>);
+      cfg.gridDim = dim3((unsigned)(g_num_sms / 2 * 2));
+      const long long fit = tc_max_active_clusters(kfn, &cfg);
+      if (fit >= 1 && fit < clusters) clusters = fit;
+      cfg.gridDim = dim3((unsigned)(2 * clusters));
+    }
     if (sbn == 256 && f16) { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_stream_kernel<256, true>, map_a, map_bh, map_s, p, n_stages)); }
     else if (sbn == 256) { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_stream_kernel<256, false>, map_a, map_bh, map_s, p, n_stages)); }
     else if (f16) { SDG_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_stream_kernel<128, true>, map_a, map_bh, map_s, p, n_stages)); }

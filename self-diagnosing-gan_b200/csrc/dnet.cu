@@ -520,7 +520,17 @@ static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, 
       a2.head_w = c->head_w.as<float>(); a2.head_b = c->head_b.as<float>(); a2.head_out = logits;
       fused_head_done = true;
     }
-    if (bl.kind == 0) {
+    // SNGAN-32 block 1 as ONE kernel (conv_b1fused.cu): relu(c1(x)) stays in shared memory.  Needs the byte dataset, the 4x4
+    // stride-2 form of c2 and a consumer that only reads relu(h) (mimicry's in-place ReLU; the next block has a shortcut conv).
+    static const int fuse_b1_env = getenv("SDG_FUSE_B1") ? atoi(getenv("SDG_FUSE_B1")) : 1;
+    if (bl.kind == 0 && fuse_b1_env && S == 32 && c1.cout == 128 && c2.cout == 128 && c2.pool4 && !c2.superpix &&
+        layout == SDG_LAYOUT_U8_NHWC && a2.out_relu && !a2.out_raw && !a2.out_f32 && !a2.head_out && conv_tc_swap_active()) {
+      if ((rc = prof_begin(c, s))) return rc;
+      if ((rc = b1_fused(x, c1.w16.as<h16>(), c1.bias.as<float>(), c2.w16.as<h16>(), c2.bias_sum.as<float>(),
+                         c->convs[i1 + 2].w3.as<float>(), a2.out_relu, nullptr, nb, f16, s))) return rc;
+      // useful FLOPs of the launch: c2 in the 4x4 stride-2 form (16 taps per pooled pixel) + c1 (27 MACs per pixel and channel)
+      if ((rc = prof_end(c, s, 2.0 * (double)nb * hw * hw * c2.cout * (16.0 * c2.cin * 0.25 + 27.0)))) return rc;
+    } else if (bl.kind == 0) {
       // DBlockOptimized: c1 straight from the image bytes; shortcut c_sc(avg_pool2d(x)) as 3 FMAs in c2's epilogue
       if (c1.superpix) {
         if ((rc = first_conv(x, layout, c1.w16s.as<h16>(), c1.bias.as<float>(), T, nb, S, c1.cout, f16, s, 1))) return rc;
@@ -749,6 +759,19 @@ extern "C" int sdg_conv2d_sg2_h16(const void* in, const void* wb, const float* b
   a.sc_in = (const h16*)skip_in; a.sc_C = skip_C; a.sc_sep = skip_in ? 1 : 0;
   a.res_f32 = res_f32; a.out_scale = out_scale; a.out_raw = (h16*)out_raw; a.out_f32 = out_f32;
   return conv_tc(a, precision == SDG_PREC_FP16, (cudaStream_t)stream);
+}
+
+extern "C" int sdg_sngan32_block1_fused_h16(const void* x, const void* w1, const float* b1, const void* w2, const float* bias2,
+                                            const float* sc_w3, void* out_relu, void* dbg_t, int64_t n, int precision,
+                                            void* stream) {
+  SDG_REQUIRE(precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID, "sdg_sngan32_block1_fused_h16: precision=%d",
+              precision);
+  SDG_REQUIRE(n >= 0, SDG_E_INVALID, "sdg_sngan32_block1_fused_h16: n=%lld", (long long)n);
+  int dev = 0;
+  SDG_CUDA(cudaGetDevice(&dev));
+  { int rc = conv_tc_init(dev); if (rc) return rc; }
+  return b1_fused(x, (const h16*)w1, b1, (const h16*)w2, bias2, sc_w3, (h16*)out_relu, (h16*)dbg_t, n,
+                  precision == SDG_PREC_FP16, (cudaStream_t)stream);
 }
 
 extern "C" int sdg_blur_h16(const void* in, void* out, int64_t n, int H, int W, int C, int pad, int stride, int precision,

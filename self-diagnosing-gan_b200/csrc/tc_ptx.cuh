@@ -156,8 +156,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of a CTA of this cluster (address from mapa).  Default semantics (release at CTA scope), as CUTLASS's
+// ClusterBarrier::arrive(cta_id) does: a .release.cluster here compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR, i.e. the
+// arriving thread first waits for every global store it has in flight (microseconds after an epilogue).  What the arrivals of
+// these kernels publish is ordered by other means: TMEM reads by tcgen05.fence::before_thread_sync, shared-memory operands
+// written for the tensor core by fence.proxy.async (each CTA's tensor core reads only its own CTA's shared memory).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
 // TMA loads whose completion is signalled on an mbarrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1,
@@ -199,6 +204,8 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
 int tc_encode_2d(CUtensorMap* map, const void* ptr, int f16, uint64_t inner, uint64_t outer, uint32_t box_inner,
                  uint32_t box_outer);
 int tc_num_sms();
+// clusters of cfg's shape that can be resident at once on the current device (cached per kernel and device; <= 0 on error)
+int tc_max_active_clusters(const void* kernel, const cudaLaunchConfig_t* cfg);
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_4(uint32_t dst_smem, const void* src) {
@@ -208,6 +215,28 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+
+// Same idea for the 16-bit outputs: a row's 32 columns are 4 x 16 B; a 4 x 4 transpose inside each group of 4 lanes
+// lets 4 lanes write the 64 contiguous bytes of ONE row (8 rows per instruction) instead of 32 lanes x 16 B on 32 rows.
+__device__ __forceinline__ void warp_transpose4_u4(uint32_t (&t)[16], int lane) {
+#pragma unroll
+  for (int s = 2; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if ((j & s) == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t a = t[4 * j + e], b = t[4 * (j + s) + e];
+          const uint32_t recv = __shfl_xor_sync(0xffffffffu, up ? a : b, s);
+          t[4 * j + e] = up ? recv : a;
+          t[4 * (j + s) + e] = up ? b : recv;
+        }
+      }
+    }
+  }
 }
 
 }  // namespace sdg
