@@ -38,7 +38,7 @@ namespace sdg {
 constexpr int BF_THREADS = 512;
 constexpr int BF_T_THREADS = 256;                       // two sets of four T warps (4..7 and 12..15)
 constexpr int BF_W_STAGES = 5;
-constexpr int BF_W_MAX = 20;                            // barrier slots (timing experiments run deeper rings over T's memory)
+constexpr int BF_W_MAX = 8;                             // barrier slots
 constexpr int BF_W_BYTES = 64 * 64 * 2;                 // 8 KB: this CTA's 64 output channels x 64 k
 constexpr int BF_ROW = 9 * 16;                          // 144: one plane row = 9 cells
 constexpr int BF_K8 = 17 * BF_ROW;                      // 2448: 17 plane rows per 8-channel group
@@ -55,15 +55,17 @@ constexpr int BF_OFF_A1 = BF_OFF_T + BF_T_BYTES;
 constexpr int BF_OFF_W1 = BF_OFF_A1 + 2 * BF_A1_BYTES;  // A1 is double-buffered
 constexpr int BF_OFF_X = BF_OFF_W1 + BF_W1_BYTES;
 constexpr int BF_OFF_P = BF_OFF_X + BF_X_BYTES;
-constexpr int kB1FusedSmem = 1024 + BF_OFF_P + BF_P_BYTES;
-static_assert(kB1FusedSmem <= 227 * 1024 - 4096, "b1_fused_kernel: shared memory budget");
+constexpr int BF_SC_BYTES = 2 * 128 * 16;               // shortcut operand: [k8 0..1][128 output pixels] x 16 B
+constexpr int BF_OFF_SC = BF_OFF_P + BF_P_BYTES;
+constexpr int kB1FusedSmem = 1024 + BF_OFF_SC + BF_SC_BYTES;
+constexpr int BF_W2_LD = 16 * 128 + 64;                 // packed c2 weights: 16 taps x 128 channels + one 64-column chunk for the shortcut
+constexpr int BF_SC_CHUNK = 32;                         // ... which is K chunk 32
+static_assert(kB1FusedSmem <= 227 * 1024 - 1024, "b1_fused_kernel: shared memory budget (static: < 1 KB of barriers)");
 
 struct BfParams {
   const uint8_t* x;          // [n][32][32][3]
   const h16* w1;             // [128][64] K-major, k = (ky*3+kx)*3 + c (27 real columns)
   const float* b1;           // [128]
-  const float* bias2;        // [128] c2 bias + shortcut bias
-  const float* sc_w3;        // [128][3] fp32, W_sc / sigma
   h16* out_relu;             // [n][16][16][128]
   h16* dbg_t;                // [n][32][32][128] copy of T (tests only) or null
   int* ovf;                  // fp16 range guard flag or null
@@ -123,10 +125,9 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
   __shared__ __align__(8) uint64_t bar_t_free[2];
   __shared__ __align__(8) uint64_t bar_acc_full[2];
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ __align__(8) uint64_t bar_sc_full;         // shortcut operand of the next tile built (both CTAs) -> issuer
+  __shared__ __align__(8) uint64_t bar_sc_free;         // its MMA has retired -> the T warps may overwrite it
   __shared__ uint32_t tmem_base_slot;
-  __shared__ uint16_t s_lut[256];
-  __shared__ __align__(16) float s_bias[128];
-  __shared__ __align__(16) float s_w3[128 * 3];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,13 +142,6 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
   const int w_stages = p.w_stages;
 
   // ---- one-time setup ----
-  if (threadIdx.x < 256) {
-    float v = __fdiv_rn((float)threadIdx.x, 255.0f);
-    v = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
-    s_lut[threadIdx.x] = (uint16_t)(pack_h2<F16>(v, 0.f) & 0xffffu);
-  }
-  for (int i = threadIdx.x; i < 128; i += BF_THREADS) s_bias[i] = p.bias2[i];
-  for (int i = threadIdx.x; i < 128 * 3; i += BF_THREADS) s_w3[i] = p.sc_w3[i];
   for (int i = threadIdx.x; i < BF_T_BYTES / 16; i += BF_THREADS)
     reinterpret_cast<uint4*>(smem_gen + BF_OFF_T)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = threadIdx.x; i < BF_P_BYTES / 16; i += BF_THREADS)
@@ -184,6 +178,8 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       mbar_init(smem_u32(&bar_acc_full[i]), 1);
       mbar_init(smem_u32(&bar_acc_empty[i]), 8);        // 4 epilogue warps x 2 CTAs
     }
+    mbar_init(smem_u32(&bar_sc_full), 16);
+    mbar_init(smem_u32(&bar_sc_free), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_slot), 512);
@@ -204,11 +200,14 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       int ws = 0;
       uint32_t phase = 0;
       for (long long l = 0; l < my_tiles; ++l) {
-        for (int ph = 0; ph < 2; ++ph) {
-          for (int idx = 0; idx < 16; ++idx) {
-            int ky, kx, h;
-            bf_chunk(ph, idx, ky, kx, h);
-            const int it = (ky * 4 + kx) * 2 + h;
+        for (int ci = -1; ci < 32; ++ci) {              // the shortcut chunk, then phase 0's and phase 1's sixteen
+          {
+            int it = BF_SC_CHUNK;
+            if (ci >= 0) {
+              int ky, kx, h;
+              bf_chunk(ci >> 4, ci & 15, ky, kx, h);
+              it = (ky * 4 + kx) * 2 + h;
+            }
             mbar_wait(smem_u32(&bar_wempty[ws]), phase ^ 1u);
             if (leader) mbar_expect_tx(smem_u32(&bar_wfull[ws]), 2 * BF_W_BYTES);
             tma_load_2d_pair(smem_base + ws * BF_W_BYTES, &map_w2, mapa_u32(smem_u32(&bar_wfull[ws]), 0), it * 64, (int)rank * 64);
@@ -234,13 +233,28 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       uint32_t wo = 0;                                  // 8 * stage
       uint32_t wphase = 0;
       bool ready = false;                               // stage wo / 8 is known to be full
+      const uint64_t sc_desc = make_nosw_desc(smem_base + BF_OFF_SC, 2048, 128);
       for (long long l = 0; l < my_tiles; ++l) {
         const int acc = (int)(l & 1);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+        {
+          // the tile's first MMA initialises the accumulator with bias + W_sc . avg_pool2d(x): one K = 16 step whose operands
+          // carry the fp32 terms as 16-bit hi / lo pairs (columns: ph.wh, pl.wh, ph.wl, 1.bias_hi, 1.bias_lo, 1.bias_lo2)
+          mbar_wait(smem_u32(&bar_sc_full), (uint32_t)(l & 1));
+          mbar_wait(smem_u32(&bar_acc_empty[acc]), (uint32_t)(((l >> 1) & 1) ^ 1));
+          if (!ready) mbar_wait(wfull0 + wo, wphase);
+          tc_fence_after();
+          const uint32_t cur = wo;
+          wo += 8u;
+          if (wo == w_wrap) { wo = 0; wphase ^= 1u; }
+          ready = mbar_try_wait(wfull0 + wo, wphase);
+          umma_pair(d_tmem, sc_desc, w_desc0 + (uint64_t)(cur * (BF_W_BYTES / 16 / 8)), idesc, 0u);
+          umma_commit_pair(wempty0 + cur, 3);
+          umma_commit_pair(smem_u32(&bar_sc_free), 3);
+        }
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
           mbar_wait(smem_u32(&bar_t_ready[ph]), (uint32_t)(l & 1));
-          if (ph == 0) mbar_wait(smem_u32(&bar_acc_empty[acc]), (uint32_t)(((l >> 1) & 1) ^ 1));
           tc_fence_after();
 #pragma unroll
           for (int idx = 0; idx < 16; ++idx) {
@@ -258,7 +272,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
             if (!(dbg & 16)) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                umma_pair(d_tmem, adesc + (uint64_t)(j * kStep), bdesc + (uint64_t)(2 * j), idesc, (ph | idx | j) != 0 ? 1u : 0u);
+                umma_pair(d_tmem, adesc + (uint64_t)(j * kStep), bdesc + (uint64_t)(2 * j), idesc, 1u);
             }
             umma_commit_pair(wempty0 + cur, 3);
           }
@@ -312,16 +326,46 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       }
       cp_async_commit();
     };
-    // landed bytes -> normalised 16-bit patch (the first conv's lookup table, applied ONCE per byte instead of once per tap):
-    // patch pixel (ry, cx) = image pixel (ry - 1, 15 s - 1 + cx) as (c0, c1, c2, 0); 18 in-image columns per row
-    auto convert_x = [&]() {
+    // normalise as transform.py:3-11 does in fp32, (u / 255 - 0.5) / 0.5, without the two IEEE divisions: u * (1/255) with one
+    // Newton correction is the correctly rounded quotient for every u in 0..255 (checked exhaustively; the bit-identity test of
+    // relu(c1(x)) against first_conv_kernel, which divides, covers it on the GPU), and dividing by 0.5 is an exact doubling
+    auto nrm = [](uint8_t u) {
+      const float f = (float)u, r = 1.0f / 255.0f;
+      float q = __fmul_rn(f, r);
+      q = __fmaf_rn(__fmaf_rn(-q, 255.0f, f), r, q);
+      return __fmul_rn(__fsub_rn(q, 0.5f), 2.0f);
+    };
+    // landed bytes -> (a) normalised 16-bit patch, the first conv's operand values, converted ONCE per byte instead of once per
+    // tap: patch pixel (ry, cx) = image pixel (ry - 1, 15 s - 1 + cx) as (c0, c1, c2, 0); 18 in-image columns per row;
+    // (b) the shortcut operand of tile L: row m = avg_pool2d(normalised x) at output pixel (m >> 3, 8 s + (m & 7)) as hi / lo pairs
+    auto convert_x = [&](long long L) {
       const uint8_t* raw = smem_gen + BF_OFF_X + 4;
       for (int i = t256; i < 32 * 18; i += BF_T_THREADS) {
         const int row = i / 18, j = i - row * 18;       // j-th in-image pixel of the row: image column (s ? 14 : 0) + j
         const uint8_t* b = raw + row * BF_X_ROWB + 3 * ((s ? 14 : 0) + j) - goff;
-        const uint32_t lo = (uint32_t)s_lut[b[0]] | ((uint32_t)s_lut[b[1]] << 16), hi = (uint32_t)s_lut[b[2]];
+        const uint32_t lo = pack_h2<F16>(nrm(b[0]), nrm(b[1])), hi = pack_h2<F16>(nrm(b[2]), 0.f);
         *reinterpret_cast<uint2*>(smem_gen + BF_OFF_P + (row + 1) * BF_P_ROWB + (j + (s ? 0 : 1)) * 8) = make_uint2(lo, hi);
       }
+      mbar_wait(smem_u32(&bar_sc_free), (uint32_t)((L & 1) ^ 1));     // the previous tile's shortcut MMA has read the buffer
+      {
+        const uint8_t* b = raw + (2 * (tt >> 3)) * BF_X_ROWB + 3 * (2 * (8 * s + (tt & 7))) - goff;
+        float px[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) px[c] = (nrm(b[c]) + nrm(b[3 + c]) + nrm(b[BF_X_ROWB + c]) + nrm(b[BF_X_ROWB + 3 + c])) * 0.25f;
+        uint32_t ph[3], pl[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          ph[c] = pack_h2<F16>(px[c], 0.f) & 0xffffu;
+          pl[c] = pack_h2<F16>(px[c] - unpack_h2<F16>(ph[c]).x, 0.f) & 0xffffu;
+        }
+        uint4 v;
+        if (set == 0) v = make_uint4(ph[0] | (ph[1] << 16), ph[2] | (pl[0] << 16), pl[1] | (pl[2] << 16), ph[0] | (ph[1] << 16));
+        else v = make_uint4(ph[2] | (kOne << 16), kOne | (kOne << 16), 0u, 0u);
+        *reinterpret_cast<uint4*>(smem_gen + BF_OFF_SC + set * 2048 + tt * 16) = v;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_sc_full), 0));
     };
     // gather this set's 16 K columns of batch pixel tt of (unit uu, batch b) of the tile in the patch into A1[gb]:
     // K column k = (ky*3 + kx)*3 + c for k < 27; 27, 28 = 1.0 (bias hi / lo); 29..31 = 0
@@ -369,7 +413,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       prefetch_x(0);
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       named_bar_sync(1, BF_T_THREADS);
-      convert_x();
+      convert_x(0);
       named_bar_sync(1, BF_T_THREADS);
       prefetch_x(1);
       build_a1(0, 0, 0);
@@ -389,7 +433,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
           else if (l + 1 < my_tiles) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");                // the next image's rows have landed
             named_bar_sync(1, BF_T_THREADS);                                    // ... for every T thread, and nobody reads this image's patch any more
-            convert_x();
+            convert_x(l + 1);
             named_bar_sync(1, BF_T_THREADS);                                    // patch complete, landing buffer idle
             prefetch_x(l + 2);
             build_a1(0, 0, cb ^ 1);
@@ -435,26 +479,11 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
   } else if (warp >= 8 && warp < 12) {
     // ================= c2 epilogue: this CTA's 128 output pixels x 128 channels =================
     const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const int oy = m >> 3, ox = 8 * s + (m & 7);
     const int g4 = lane >> 2, i4 = lane & 3;
     uint32_t vmaxw = 0;
     for (long long l = 0; l < my_tiles; ++l) {
       const long long n = cluster_id + l * n_clusters;
       const int acc = (int)(l & 1);
-      // avg_pool2d of the normalised network input at this output pixel (DBlockOptimized shortcut input)
-      float px[3];
-      {
-        const uint8_t* ip = p.x + ((n * 32 + 2 * oy) * 32 + 2 * ox) * 3;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          auto nv = [&](int off) {
-            const float v = __fdiv_rn((float)ip[off + c], 255.0f);
-            return __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
-          };
-          px[c] = (nv(0) + nv(3) + nv(96) + nv(99)) * 0.25f;
-        }
-      }
       mbar_wait(smem_u32(&bar_acc_full[acc]), (uint32_t)((l >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
@@ -464,28 +493,11 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * g);
-          v[4 * g] = __uint_as_float(r[4 * g]) + b4.x; v[4 * g + 1] = __uint_as_float(r[4 * g + 1]) + b4.y;
-          v[4 * g + 2] = __uint_as_float(r[4 * g + 2]) + b4.z; v[4 * g + 3] = __uint_as_float(r[4 * g + 3]) + b4.w;
-        }
-        {
-          float w3[96];
-#pragma unroll
-          for (int g = 0; g < 24; ++g) {
-            const float4 t = *reinterpret_cast<const float4*>(s_w3 + c0 * 3 + 4 * g);
-            w3[4 * g] = t.x; w3[4 * g + 1] = t.y; w3[4 * g + 2] = t.z; w3[4 * g + 3] = t.w;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = fmaf(w3[3 * j], px[0], fmaf(w3[3 * j + 1], px[1], fmaf(w3[3 * j + 2], px[2], v[j])));
-        }
+        // bias and shortcut are already in the accumulator (the tile's first MMA): ReLU + convert only
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          pk[j] = pack_relu_h2<F16>(v[2 * j], v[2 * j + 1]);
+          pk[j] = pack_relu_h2<F16>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
           if (F16) vmaxw = __vmaxu2(vmaxw, pk[j]);
         }
         // 4 x 4 transpose inside each group of 4 lanes: 4 lanes then write the 64 contiguous bytes of ONE pixel
@@ -519,17 +531,57 @@ int b1_fused_init() {
   return 0;
 }
 
-int b1_fused(const void* x, const h16* w1, const float* b1, const h16* w2, const float* bias2, const float* sc_w3, h16* out_relu,
-             h16* dbg_t, int64_t n, int f16, cudaStream_t s) {
-  SDG_REQUIRE(x && w1 && b1 && w2 && bias2 && sc_w3 && out_relu, SDG_E_INVALID, "b1_fused: null pointer");
+// w2f[o][0..2047] = w2[o][.] (when w2 is given; else the caller packed them in place), then the shortcut chunk:
+// columns 2048.. = wh0 wh1 wh2 | wh0 wh1 wh2 | wl0 wl1 wl2 | bias_hi bias_lo bias_lo2 | zeros, w = wh + wl the fp32 W_sc / sigma
+template <bool F16>
+__global__ void __launch_bounds__(256)
+b1_fused_pack_kernel(const h16* __restrict__ w2, const float* __restrict__ sc_w3, const float* __restrict__ bias2,
+                     h16* __restrict__ w2f) {
+  const int o = blockIdx.x;
+  if (w2)
+    for (int i = threadIdx.x; i < 2048 / 8; i += blockDim.x)
+      reinterpret_cast<uint4*>(w2f + (size_t)o * BF_W2_LD)[i] = reinterpret_cast<const uint4*>(w2 + (size_t)o * 2048)[i];
+  if (threadIdx.x < 64) {
+    const int k = threadIdx.x;
+    auto hi16 = [](float v) { return (uint16_t)(pack_h2<F16>(v, 0.f) & 0xffffu); };
+    auto back = [](uint16_t h) { return unpack_h2<F16>((uint32_t)h).x; };
+    uint16_t v = 0;
+    if (k < 9) {
+      const float w = sc_w3[o * 3 + k % 3];
+      const uint16_t wh = hi16(w);
+      v = k < 6 ? wh : hi16(w - back(wh));
+    } else if (k < 12) {
+      const float b = bias2[o];
+      const uint16_t b0 = hi16(b);
+      const uint16_t b1 = hi16(b - back(b0));
+      v = k == 9 ? b0 : (k == 10 ? b1 : hi16(b - back(b0) - back(b1)));
+    }
+    w2f[(size_t)o * BF_W2_LD + 2048 + k] = v;
+  }
+}
+
+int b1_fused_pack(const h16* w2, const float* sc_w3, const float* bias2, h16* w2f, int f16, cudaStream_t s) {
+  SDG_REQUIRE(sc_w3 && bias2 && w2f, SDG_E_INVALID, "b1_fused_pack: null pointer");
+  SDG_REQUIRE(((uintptr_t)w2 % 16) == 0 && ((uintptr_t)w2f % 16) == 0, SDG_E_INVALID, "b1_fused_pack: misaligned pointer");
+  if (f16) { SDG_LAUNCH(b1_fused_pack_kernel<true>, 128, 256, 0, s, w2, sc_w3, bias2, w2f); }
+  else { SDG_LAUNCH(b1_fused_pack_kernel<false>, 128, 256, 0, s, w2, sc_w3, bias2, w2f); }
+  return 0;
+}
+
+int b1_fused_w2_elems() { return 128 * BF_W2_LD; }
+int b1_fused_w2_ld() { return BF_W2_LD; }
+
+int b1_fused(const void* x, const h16* w1, const float* b1, const h16* w2f, h16* out_relu, h16* dbg_t, int64_t n, int f16,
+             cudaStream_t s) {
+  SDG_REQUIRE(x && w1 && b1 && w2f && out_relu, SDG_E_INVALID, "b1_fused: null pointer");
   auto al16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
-  SDG_REQUIRE(((uintptr_t)x % 4) == 0 && al16(w1) && al16(w2) && al16(out_relu) && al16(dbg_t), SDG_E_INVALID,
+  SDG_REQUIRE(((uintptr_t)x % 4) == 0 && al16(w1) && al16(w2f) && al16(out_relu) && al16(dbg_t), SDG_E_INVALID,
               "b1_fused: misaligned pointer");
   if (n == 0) return 0;
   CUtensorMap map_w2;
-  { int rc = tc_encode_2d(&map_w2, w2, f16, 16 * 128, 128, 64, 64); if (rc) return rc; }
+  { int rc = tc_encode_2d(&map_w2, w2f, f16, BF_W2_LD, 128, 64, 64); if (rc) return rc; }
   BfParams p;
-  p.x = (const uint8_t*)x; p.w1 = w1; p.b1 = b1; p.bias2 = bias2; p.sc_w3 = sc_w3; p.out_relu = out_relu; p.dbg_t = dbg_t;
+  p.x = (const uint8_t*)x; p.w1 = w1; p.b1 = b1; p.out_relu = out_relu; p.dbg_t = dbg_t;
   p.ovf = t_range_flag; p.n_images = n;
   static const int ws_env = getenv("SDG_B1_WSTAGES") ? atoi(getenv("SDG_B1_WSTAGES")) : BF_W_STAGES;
   p.w_stages = ws_env >= 2 && ws_env <= BF_W_STAGES ? ws_env : BF_W_STAGES;
@@ -537,7 +589,6 @@ int b1_fused(const void* x, const h16* w1, const float* b1, const h16* w2, const
 #ifdef SDG_TIMING_EXPERIMENTS
   static const int dbg_env = getenv("SDG_B1_DEBUG") ? atoi(getenv("SDG_B1_DEBUG")) : 0;
   p.dbg = dbg_env;
-  if (ws_env > BF_W_STAGES && ws_env <= 19) p.w_stages = ws_env;
 #endif
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(tc_num_sms() / 2 * 2));

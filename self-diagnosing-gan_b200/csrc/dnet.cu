@@ -57,10 +57,11 @@ struct ConvLayer {
   // w16s [128][ty * (tx + shift) * Cin], bias2 / w3s = the 64-channel vectors twice
   int superpix = 0;
   DevBuf w16s, bias2, w3s;
+  DevBuf w16f;               // SNGAN-32 block1.c2 for the one-kernel block 1 (conv_b1fused.cu): w16's 2048 columns + the shortcut chunk
   bool has_bias = false;
   void release_all() {
     w32.release(); w16.release(); bias.release(); w3.release(); bias_sum.release();
-    w16s.release(); bias2.release(); w3s.release();
+    w16s.release(); bias2.release(); w3s.release(); w16f.release();
   }
 };
 
@@ -319,6 +320,13 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
       } else {
         SDG_CUDA(cudaMemcpyAsync(l2.bias_sum.p, l2.bias.p, sizeof(float) * l2.cout, cudaMemcpyDeviceToDevice, s));
       }
+      // ---- one-kernel block 1 of SNGAN-32: the same c2 weights with the shortcut / bias chunk appended ----
+      if (c->blocks[bi].kind == 0 && arch == SDG_ARCH_SNGAN32 && l2.pool4 && l2.cout == 128 && l2.cin == 128) {
+        { int rc = l2.w16f.ensure(sizeof(h16) * (size_t)b1_fused_w2_elems()); if (rc) return rc; }
+        { int rc = pack_pool4_h16(W[i2], sig + i2, l2.w16f.as<h16>(), l2.cout, l2.cin, f16, b1_fused_w2_ld(), s); if (rc) return rc; }
+        { int rc = b1_fused_pack(nullptr, c->convs[isc].w3.as<float>(), l2.bias_sum.as<float>(), l2.w16f.as<h16>(), f16, s);
+          if (rc) return rc; }
+      }
       // ---- super-pixel forms of the Cout = 64 layers (SNGAN-64 block1.c2 and block2.c1) ----
       static const int use_superpix = getenv("SDG_SUPERPIX") ? atoi(getenv("SDG_SUPERPIX")) : 1;
       auto dup = [&](DevBuf& dst, const float* src, int n_el) -> int {
@@ -524,10 +532,10 @@ static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, 
     // stride-2 form of c2 and a consumer that only reads relu(h) (mimicry's in-place ReLU; the next block has a shortcut conv).
     static const int fuse_b1_env = getenv("SDG_FUSE_B1") ? atoi(getenv("SDG_FUSE_B1")) : 1;
     if (bl.kind == 0 && fuse_b1_env && S == 32 && c1.cout == 128 && c2.cout == 128 && c2.pool4 && !c2.superpix &&
-        layout == SDG_LAYOUT_U8_NHWC && a2.out_relu && !a2.out_raw && !a2.out_f32 && !a2.head_out && conv_tc_swap_active()) {
+        c2.w16f.p && layout == SDG_LAYOUT_U8_NHWC && a2.out_relu && !a2.out_raw && !a2.out_f32 && !a2.head_out &&
+        conv_tc_swap_active()) {
       if ((rc = prof_begin(c, s))) return rc;
-      if ((rc = b1_fused(x, c1.w16.as<h16>(), c1.bias.as<float>(), c2.w16.as<h16>(), c2.bias_sum.as<float>(),
-                         c->convs[i1 + 2].w3.as<float>(), a2.out_relu, nullptr, nb, f16, s))) return rc;
+      if ((rc = b1_fused(x, c1.w16.as<h16>(), c1.bias.as<float>(), c2.w16f.as<h16>(), a2.out_relu, nullptr, nb, f16, s))) return rc;
       // useful FLOPs of the launch: c2 in the 4x4 stride-2 form (16 taps per pooled pixel) + c1 (27 MACs per pixel and channel)
       if ((rc = prof_end(c, s, 2.0 * (double)nb * hw * hw * c2.cout * (16.0 * c2.cin * 0.25 + 27.0)))) return rc;
     } else if (bl.kind == 0) {
@@ -770,8 +778,16 @@ extern "C" int sdg_sngan32_block1_fused_h16(const void* x, const void* w1, const
   int dev = 0;
   SDG_CUDA(cudaGetDevice(&dev));
   { int rc = conv_tc_init(dev); if (rc) return rc; }
-  return b1_fused(x, (const h16*)w1, b1, (const h16*)w2, bias2, sc_w3, (h16*)out_relu, (h16*)dbg_t, n,
-                  precision == SDG_PREC_FP16, (cudaStream_t)stream);
+  SDG_REQUIRE(w2 && bias2 && sc_w3, SDG_E_INVALID, "sdg_sngan32_block1_fused_h16: null pointer");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int f16 = precision == SDG_PREC_FP16;
+  h16* w2f = nullptr;
+  SDG_CUDA(cudaMallocAsync((void**)&w2f, sizeof(h16) * (size_t)b1_fused_w2_elems(), st));
+  int rc = b1_fused_pack((const h16*)w2, sc_w3, bias2, w2f, f16, st);
+  if (!rc) rc = b1_fused(x, (const h16*)w1, b1, w2f, (h16*)out_relu, (h16*)dbg_t, n, f16, st);
+  cudaFreeAsync(w2f, st);
+  return rc;
 }
 
 extern "C" int sdg_blur_h16(const void* in, void* out, int64_t n, int H, int W, int C, int pad, int stride, int precision,

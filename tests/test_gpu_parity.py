@@ -580,7 +580,7 @@ def test_sngan_tensorcore_vs_oracle(arch, n, seed, inplace, prec, tol, dev):
     xf = sngan_oracle.normalise_u8(x).contiguous().to(dev)
     gf = eng.forward(xf).cpu().numpy()
     if arch == 32 and os.environ.get("SDG_FUSE_B1", "1") != "0":
-        assert np.abs(gf - got).max() <= 0.05 * max(float(np.std(want)), 1e-3)
+        assert np.abs(gf - got).max() <= (0.05 if prec == "fp16" else 0.4) * max(float(np.std(want)), 1e-3)   # bf16: 8x the ulp
     else:
         assert np.array_equal(gf, got)
 
