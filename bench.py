@@ -52,13 +52,15 @@ WORKLOADS = {
                     metric="per-sample D logits + LDR scores per second (SNGAN-32, 50k CIFAR-10-shape samples)",
                     desc="configs[1]: SNGAN-32 recording pass (weights re-packed per pass) + Welford stats + "
                          "ldr_conf_0.3_ratio_50 weights + top-100 over ONE 50k x 3x32x32 uint8 dataset",
-                    kernel="conv_swap_shared_kernel block1.c2 (3x3 128->128 @32x32 + avg-pool + shortcut; 55.5% of the reference FLOPs), "
-                           "run as the algebraically equal 4x4 stride-2 conv with role-swapped operands (M = 128 channels, "
-                           "N = 256 pixels per tcgen05.mma) and tap-shared operand staging",
-                    dom_ref_flop=2.0 * 9 * 128 * 128 * 1024, dom_exec_useful=1.0, cpu_sample=16384,
-                    traffic=((3.316908e9 + 0.799314e9) / 12504.0, "profiles/r2g_ncu_full_sngan32_sweep_summary.txt launch 1 "
-                             "(12 504 samples: 3.317 GB read + 0.799 GB written = 329.2 KB/sample; algorithmic 256 KiB in + 64 KiB "
-                             "out per sample = 327.7 KB)"),
+                    kernel="b1_fused_kernel: the whole of block 1 in one launch -- c1 (3x3 3->128 from the bytes) -> ReLU -> c2 (3x3 128->128 "
+                           "@32x32 + avg-pool, run as the algebraically equal 4x4 stride-2 conv) + image shortcut -> ReLU; 56.0% of the "
+                           "reference FLOPs; CTA pairs (tcgen05.mma.cta_group::2, M = 256 pixels x N = 128 channels), relu(c1(x)) built "
+                           "and consumed in shared memory as a no-swizzle UMMA operand, only the weights stream",
+                    dom_ref_flop=2.0 * 9 * 128 * 128 * 1024 + 2.0 * 27 * 128 * 1024, dom_exec_useful=1.0, cpu_sample=16384,
+                    traffic=((39.038208e6 + 765.836544e6) / 12504.0, "profiles/r2i_ncu_full_b1fused_summary.txt (12 504 samples: 39.0 MB "
+                             "read + 765.8 MB written to DRAM during the launch = 64.4 KB/sample; algorithmic 3 KiB in + 64 KiB out per "
+                             "sample = 68.6 KB -- the tail of the output is still dirty in L2 when the launch ends; the two kernels this "
+                             "one replaces moved 585 KB/sample)"),
                     eager=dict(ref_batch=64, ref_n=50_000, best_batch=4096, best_n=50_000)),
     "sngan64": dict(arch="sngan", size=64, n_total=202_599, n_weak=25_325, key="ldr_conf_5.0_ratio_50", flop=2 * 644_809_728,
                     metric="per-sample D logits + LDR scores per second (SNGAN-64, CelebA shape, 202 599 samples)",
@@ -443,7 +445,8 @@ def run_ours(args, rank, world, local_rank):
             "achieved": dom_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
             "frac": (dom_tflops / peaks["bf16_sustained"]) if dom_tflops else None,
             "flops_counted": "USEFUL FLOPs executed by the tensor pipe: 2*M*N*K of the GEMM run (16 taps per pooled pixel in the "
-                             "4x4 stride-2 form), structural zeros of the super-pixel packing excluded",
+                             "4x4 stride-2 form; SNGAN-32: plus the 27 real MACs per pixel and channel of c1, which the same launch "
+                             "computes), structural zeros of the super-pixel packing and K padding excluded",
             "executed_tflops_incl_structural_zeros": dom_exec,
             "reference_formulation_tflops": dom_ref_tflops,
             "reference_formulation_note": "same launches counted as the reference computes them (conv3x3 at full resolution then "

@@ -74,7 +74,7 @@ struct BfParams {
                              // bounds how many c2 chunks (256 MMA cycles each) can be queued ahead of a c1 batch.
                              // (SDG_TIMING_EXPERIMENTS builds accept deeper rings that overwrite T: wrong results)
   int dbg;                   // SDG_TIMING_EXPERIMENTS builds only (WRONG results): 1 no gather, 2 no T drain, 4 no c2 epilogue, 8 no c1 MMAs,
-                             // 16 no c2 MMAs
+                             // 16 no c2 MMAs, 32 no weight loads
 };
 
 // K-major operand without swizzle: rows of a group 16 B apart, 8-row groups `sbo` bytes apart, K halves `lbo` bytes apart
@@ -209,8 +209,12 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
               it = (ky * 4 + kx) * 2 + h;
             }
             mbar_wait(smem_u32(&bar_wempty[ws]), phase ^ 1u);
-            if (leader) mbar_expect_tx(smem_u32(&bar_wfull[ws]), 2 * BF_W_BYTES);
-            tma_load_2d_pair(smem_base + ws * BF_W_BYTES, &map_w2, mapa_u32(smem_u32(&bar_wfull[ws]), 0), it * 64, (int)rank * 64);
+            if (dbg & 32) {                             // timing experiment (wrong results): no weight loads at all
+              if (leader) mbar_arrive(smem_u32(&bar_wfull[ws]));
+            } else {
+              if (leader) mbar_expect_tx(smem_u32(&bar_wfull[ws]), 2 * BF_W_BYTES);
+              tma_load_2d_pair(smem_base + ws * BF_W_BYTES, &map_w2, mapa_u32(smem_u32(&bar_wfull[ws]), 0), it * 64, (int)rank * 64);
+            }
             if (++ws == w_stages) { ws = 0; phase ^= 1u; }
           }
         }

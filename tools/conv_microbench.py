@@ -54,14 +54,16 @@ def main():
             for _ in range(3):
                 run()
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(a.iters):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.iters + 1)]
+            ev[0].record()
+            for i in range(a.iters):
                 run()
-            e1.record()
+                ev[i + 1].record()
             torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / a.iters
-            print(f"block1 n={a.n} {name}: {ms * 1e3:.1f} us  {flops / ms / 1e9:.1f} TFLOP/s (useful, 4x4 stride-2 form)")
+            t = sorted(ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(a.iters))
+            ms = sum(t) / len(t) / 1e3
+            print(f"block1 n={a.n} {name}: mean {ms * 1e3:.1f} us (min {t[0]:.1f} median {t[len(t) // 2]:.1f} max {t[-1]:.1f})  "
+                  f"{flops / ms / 1e9:.1f} TFLOP/s (useful, 4x4 stride-2 form)")
         return
     if a.first:
         img = torch.randint(0, 256, (a.n, a.hw, a.hw, 3), dtype=torch.uint8, device=dev)
