@@ -1595,6 +1595,22 @@ static int encode_act(CUtensorMap* map, const void* ptr, int f16, int64_t n, int
   return 0;
 }
 
+// plain (un-swizzled) box of bc channels x bw columns x bh rows of one image over NHWC activations: the streaming kernels
+// (blur_tma.cu) read such a box with ordinary shared-memory loads; out-of-bounds elements arrive as zeros
+int tc_encode_act_box(CUtensorMap* map, const void* ptr, int f16, int64_t n, int H, int W, int C, int bc, int bw, int bh) {
+  SDG_REQUIRE(g_encode, SDG_E_STATE, "conv_tc: conv_tc_init not called");
+  SDG_REQUIRE(bc <= 256 && bw <= 256 && bh <= 256 && (bc * 2) % 16 == 0, SDG_E_INVALID, "tc_encode_act_box: box %d x %d x %d", bc, bw, bh);
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SDG_REQUIRE(r == CUDA_SUCCESS, SDG_E_INVALID, "conv_tc: cuTensorMapEncodeTiled(act box) failed: %d", (int)r);
+  return 0;
+}
+
 // Function attributes (opt-in shared memory) are per DEVICE, the driver entry point is per process: one bit per device id
 // records which devices have been initialised, so that a single process may drive several GPUs.
 static std::atomic<unsigned long long> g_dev_init{0};

@@ -796,6 +796,9 @@ extern "C" int sdg_blur_h16(const void* in, void* out, int64_t n, int H, int W, 
   SDG_REQUIRE(precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID, "sdg_blur_h16: precision=%d", precision);
   SDG_REQUIRE(C % 8 == 0 && (stride == 1 || stride == 2) && pad >= 0 && pad <= 3 && H + 2 * pad >= 4 && W + 2 * pad >= 4,
               SDG_E_INVALID, "sdg_blur_h16: C=%d pad=%d stride=%d H=%d W=%d", C, pad, stride, H, W);
+  int dev = 0;
+  SDG_CUDA(cudaGetDevice(&dev));
+  { int rc = conv_tc_init(dev); if (rc) return rc; }      // the TMA-fed blur needs the tensor-map encoder
   return blur_h16((const h16*)in, (h16*)out, n, H, W, C, pad, stride, precision == SDG_PREC_FP16, (cudaStream_t)stream);
 }
 

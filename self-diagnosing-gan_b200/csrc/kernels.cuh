@@ -68,6 +68,10 @@ int sg2_first_conv_h16(const void* x, int layout, const float* w3, const float* 
                        cudaStream_t s);
 // blur_h16: out extent = (H + 2*pad - 4) / stride + 1 (stride 2 = only the blur outputs a stride-2 1x1 conv reads)
 int blur_h16(const h16* in, h16* out, int64_t n, int H, int W, int C, int pad, int stride, int f16, cudaStream_t s);
+// blur_tma.cu: the same operation, bit for bit, as a TMA-fed streaming kernel (C % 64 == 0, images of >= 32 output rows);
+// blur_h16 dispatches to it (SDG_BLUR_TMA=0: never, 1..3: variant)
+bool blur_tma_applies(int H, int W, int C, int stride);
+int blur_tma(const h16* in, h16* out, int64_t n, int H, int W, int C, int pad, int stride, int f16, int variant, cudaStream_t s);
 // split-precision tail operands (see sg2_fp32.cu): activations fp32 [rows][C] -> [rows][hi | lo | hi]; weights -> per K group
 // of C channels [Wh | Wh | Wl] (conv: G = 9 taps of W[O][cin_w][3][3]; linear: G = HW pixels of W[O][C*HW], NCHW flatten)
 int split3_rows_h16(const float* in, h16* out, int64_t rows, int C, int f16, cudaStream_t s);

@@ -155,6 +155,7 @@ select_sort_kernel(const unsigned long long* __restrict__ sel_key, const unsigne
 // ---------------------------------------------------------------------------------------------------
 constexpr int kSelPasses = 9;
 constexpr int kSelMaxBins = 2048;
+constexpr int kSelUnroll = 8;
 
 struct FusedState {
   unsigned int hist[kSelPasses][kSelMaxBins];
@@ -185,7 +186,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 select_fused_kernel(const double* __restrict__ score, int64_t n, int largest, int k, int kpow2, FusedState* st,
                     unsigned long long* __restrict__ sel_key, unsigned int* __restrict__ sel_idx,
                     int64_t* __restrict__ idx_out) {
@@ -196,7 +197,7 @@ select_fused_kernel(const double* __restrict__ score, int64_t n, int largest, in
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + tid;
+  const int64_t w0 = (int64_t)blockIdx.x * blockDim.x + (tid & ~31);     // first sample of this warp's 32-wide slice
   unsigned long long pk = 0;
   unsigned int pi = 0, k_rem = (unsigned int)k, target = 0;
   bool done = false;
@@ -206,22 +207,43 @@ select_fused_kernel(const double* __restrict__ score, int64_t n, int largest, in
     sel_digit(pass, shift, bits, on_idx);
     const int nb = 1 << bits;
     const unsigned int mask = (unsigned int)nb - 1u;
+    const int hs = shift + bits;                             // first bit above this digit (of the key, or of the index)
+    const unsigned long long himask = on_idx ? (hs >= 32 ? 0ULL : (unsigned long long)(~0u << hs))
+                                             : (hs >= 64 ? 0ULL : (~0ULL << hs));
     for (int b = tid; b < nb; b += 256) sh[b] = 0;
     __syncthreads();
-    for (int64_t i = i0; i < n; i += stride) {
-      unsigned long long key; unsigned int id;
-      composite(score[i], (unsigned int)i, largest, key, id);
-      bool match; unsigned int digit;
-      if (!on_idx) {
-        const int hs = shift + bits;                       // bits above this digit are already fixed
-        match = hs >= 64 || (key >> hs) == (pk >> hs);
-        digit = (unsigned int)(key >> shift) & mask;
-      } else {
-        const int hs = shift + bits;
-        match = key == pk && (hs >= 32 || (id >> hs) == (pi >> hs));
-        digit = (id >> shift) & mask;
+    // warp-uniform sweep, kSelUnroll independent 8-byte loads in flight per thread; lanes of a warp that hit the same bin
+    // (nearly all of them in the first pass: the top 11 bits of a double are its sign and exponent) are combined with
+    // match.any so the shared-memory atomic sees one add per distinct bin instead of up to 32 serialised ones
+    // (n < 2^32 is an entry-point requirement: sample indices are 32-bit, a wrapped sum is caught by the 64-bit bound test)
+    for (int64_t b0 = w0; b0 < n; b0 += (int64_t)kSelUnroll * stride) {
+      double v[kSelUnroll];
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const int64_t i = b0 + (int64_t)u * stride + lane;
+        v[u] = i < n ? __ldg(score + i) : 0.0;
       }
-      if (match) atomicAdd(&sh[digit], 1u);
+#pragma unroll
+      for (int u = 0; u < kSelUnroll; ++u) {
+        const int64_t wb = b0 + (int64_t)u * stride;
+        if (wb >= n) break;                                   // warp-uniform
+        const int64_t i = wb + lane;
+        unsigned long long key; unsigned int id;
+        composite(v[u], (unsigned int)i, largest, key, id);
+        bool match; unsigned int digit;
+        if (!on_idx) {                                        // (pass-uniform branch)
+          match = ((key ^ pk) & himask) == 0ULL;             // bits above this digit are already fixed
+          digit = (unsigned int)(key >> shift) & mask;
+        } else {
+          match = key == pk && ((id ^ pi) & (unsigned int)himask) == 0u;
+          digit = (id >> shift) & mask;
+        }
+        match = match && i < n;
+        // after the first pass nearly every warp has no candidate left: one vote skips the match / atomic sequence
+        if (!__any_sync(0xffffffffu, match)) continue;
+        const unsigned int peers = __match_any_sync(0xffffffffu, match ? digit : 0xffffffffu);
+        if (match && lane == __ffs(peers) - 1) atomicAdd(&sh[digit], (unsigned int)__popc(peers));
+      }
     }
     __syncthreads();
     for (int b = tid; b < nb; b += 256)
@@ -261,12 +283,23 @@ select_fused_kernel(const double* __restrict__ score, int64_t n, int largest, in
     __syncthreads();
   }
   // compaction: every candidate at or above the threshold composite (pk, pi) -- exactly k of them
-  for (int64_t i = i0; i < n; i += stride) {
-    unsigned long long key; unsigned int id;
-    composite(score[i], (unsigned int)i, largest, key, id);
-    if (key > pk || (key == pk && id >= pi)) {
-      const unsigned int slot = atomicAdd(&st->out_count, 1u);
-      if (slot < (unsigned int)k) { sel_key[slot] = ordered_key(score[i]); sel_idx[slot] = (unsigned int)i; }
+  for (int64_t b0 = w0; b0 < n; b0 += (int64_t)kSelUnroll * stride) {
+    double v[kSelUnroll];
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      const int64_t i = b0 + (int64_t)u * stride + lane;
+      v[u] = i < n ? __ldg(score + i) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < kSelUnroll; ++u) {
+      const int64_t i = b0 + (int64_t)u * stride + lane;
+      if (i >= n) continue;
+      unsigned long long key; unsigned int id;
+      composite(v[u], (unsigned int)i, largest, key, id);
+      if (key > pk || (key == pk && id >= pi)) {
+        const unsigned int slot = atomicAdd(&st->out_count, 1u);
+        if (slot < (unsigned int)k) { sel_key[slot] = ordered_key(v[u]); sel_idx[slot] = (unsigned int)i; }
+      }
     }
   }
   __threadfence();
@@ -339,10 +372,15 @@ extern "C" int sdg_topk_indices(const double* score, int64_t n, int k, int large
       SDG_CUDA(cudaFuncSetAttribute(select_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       if (dev < 64) attr_set.fetch_or(1ULL << dev);
     }
-    // at most 2 resident CTAs per SM (<= 56 KB of shared memory each): the cooperative launch guarantees co-residency,
-    // which the in-kernel grid barrier relies on
-    int64_t grid = cdiv(n, 256 * 8);
-    if (grid > 2LL * sms) grid = 2LL * sms;
+    // at most 4 resident CTAs per SM (<= 64 registers, <= 56 KB of shared memory each; 2 when k needs the big sort
+    // buffer): the cooperative launch guarantees co-residency, which the in-kernel grid barrier relies on.  The sweeps
+    // are latency / issue bound per warp (ncu: 16 warps per SM issue 45 % of the cycles), so residency pays at large n.
+    int64_t grid = cdiv(n, 256 * kSelUnroll);
+    int per_sm = smem <= 24 * 1024 ? 4 : 2, fit = 0;
+    SDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, select_fused_kernel, 256, smem));
+    SDG_REQUIRE(fit >= 1, SDG_E_DEVICE, "sdg_topk_indices: the selection kernel does not fit an SM");
+    if (per_sm > fit) per_sm = fit;
+    if (grid > (int64_t)per_sm * sms) grid = (int64_t)per_sm * sms;
     if (grid < 1) grid = 1;
     int largest_i = largest, k_i = k, kp_i = kp;
     void* args[] = {(void*)&score, (void*)&n, (void*)&largest_i, (void*)&k_i, (void*)&kp_i, (void*)&fs, (void*)&sel_key,

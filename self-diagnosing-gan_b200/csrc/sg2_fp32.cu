@@ -318,8 +318,9 @@ blur_h16_kernel(const h16* __restrict__ in, h16* __restrict__ out, int H, int W,
     uint32_t* hp = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float e = 0.125f * (a[2 * j] + d[2 * j]) + 0.375f * (b2[2 * j] + c[2 * j]);
-      const float f = 0.125f * (a[2 * j + 1] + d[2 * j + 1]) + 0.375f * (b2[2 * j + 1] + c[2 * j + 1]);
+      // written out as the compiler contracts it, so that blur_tma.cu can match it bit for bit
+      const float e = fmaf(0.125f, a[2 * j] + d[2 * j], 0.375f * (b2[2 * j] + c[2 * j]));
+      const float f = fmaf(0.125f, a[2 * j + 1] + d[2 * j + 1], 0.375f * (b2[2 * j + 1] + c[2 * j + 1]));
       hp[j] = pack_h2<F16>(e, f);
     }
     *reinterpret_cast<uint4*>(dst) = pk;
@@ -354,6 +355,11 @@ int blur_h16(const h16* in, h16* out, int64_t n, int H, int W, int C, int pad, i
   if (n == 0 || Ho <= 0 || Wo <= 0) return 0;
   SDG_REQUIRE((C & (C - 1)) == 0 && C >= 8 && C <= 2048, SDG_E_UNSUPPORTED, "blur_h16: C=%d must be a power of two in 8..2048", C);
   SDG_REQUIRE(stride == 1 || stride == 2, SDG_E_UNSUPPORTED, "blur_h16: stride=%d", stride);
+  {
+    const char* e = getenv("SDG_BLUR_TMA");            // read per call: the tests switch it inside one process
+    const int variant = e ? atoi(e) : 1;
+    if (variant > 0 && blur_tma_applies(H, W, C, stride)) return blur_tma(in, out, n, H, W, C, pad, stride, f16, variant, s);
+  }
   const int c8s = ilog2(C / 8);
   const int xpb = 256 >> c8s;
   const int x_tiles = (int)cdiv(Wo, xpb);

@@ -203,6 +203,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
 // host helpers shared by the tensor-core kernels (conv_tc.cu)
 int tc_encode_2d(CUtensorMap* map, const void* ptr, int f16, uint64_t inner, uint64_t outer, uint32_t box_inner,
                  uint32_t box_outer);
+int tc_encode_act_box(CUtensorMap* map, const void* ptr, int f16, int64_t n, int H, int W, int C, int bc, int bw, int bh);
 int tc_num_sms();
 // clusters of cfg's shape that can be resident at once on the current device (cached per kernel and device; <= 0 on error)
 int tc_max_active_clusters(const void* kernel, const cudaLaunchConfig_t* cfg);

@@ -143,6 +143,60 @@ def test_odd_sizes_and_unaligned_shards(dev):
     assert np.array_equal(mom["mean"].cpu().numpy(), so.moments(full[:, 3:].cpu().numpy().astype(np.float64))[0])
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("T", [2, 33, 50, 51, 64, 160, 161, 200])
+def test_window_moments_every_dispatch_branch(dev, T, dtype):
+    """the shared-memory-staged kernel (aligned 16-byte copies, element copies for ragged N) and the generic two-pass kernel
+    (windows too long for the tile) give NumPy's bits:
+    mean / var as plot.py:243-246 (np.mean / np.var(ddof=1) along axis 0), ldr = last row, ldrd = mean |row diff|."""
+    from diagan_b200 import engine
+    rng = np.random.RandomState(T)
+    for n in (1, 129, 5000, 40000):
+        arr = rng.normal(1.0, 1.5, (T, n)).astype(dtype)
+        mom = engine.window_moments(torch.from_numpy(arr).to(dev))
+        a64 = arr.astype(np.float64)
+        mean, var = so.moments(a64)
+        assert np.array_equal(mom["mean"].cpu().numpy(), mean)
+        assert np.array_equal(mom["var"].cpu().numpy(), var)
+        assert np.array_equal(mom["ldr"].cpu().numpy(), a64[-1])
+        sad = np.zeros(n)
+        for t in range(1, T):                       # row order, like the kernels and oracle.scores.welford
+            sad = sad + np.abs(a64[t] - a64[t - 1])
+        assert np.array_equal(mom["ldrd"].cpu().numpy(), sad / (T - 1))
+
+
+@pytest.mark.parametrize("n_conf", [1, 3])
+def test_score_vectorised_and_scalar_paths(dev, n_conf):
+    """odd / even N, aligned and unaligned bases: the 16-byte path and the scalar path of the score kernels agree with NumPy"""
+    from diagan_b200 import engine
+    rng = np.random.RandomState(3)
+    confs = [0.3, 1.0, 5.0][:n_conf]
+    for n in (1, 2, 7, 1024, 4097, 100_001):
+        big_m = torch.from_numpy(rng.normal(1.0, 1.5, n + 1)).to(dev)
+        big_v = torch.from_numpy(rng.gamma(2.0, 1.0, n + 1)).to(dev)
+        for off in (0, 1):                          # off = 1: 8-byte aligned only
+            m, v = big_m[off:off + n], big_v[off:off + n]
+            got = engine.scores_from_moments(m, v, confs, eps=1e-6).cpu().numpy()
+            mh, vh = m.cpu().numpy(), v.cpu().numpy()
+            for j, c in enumerate(confs):
+                sc = np.clip(mh + c * np.sqrt(vh), 1e-2, None)
+                want = np.maximum(np.minimum(sc, sc.min() * 50), 1e-6)
+                assert np.array_equal(got[j], want), (n, off, c)
+
+
+def test_top_indices_sizes_around_the_sweep_unroll(dev):
+    from diagan_b200 import engine
+    rng = np.random.RandomState(5)
+    for n in (1, 31, 33, 2047, 2049, 70_001, 700_001):
+        w = rng.normal(0.0, 2.0, n)
+        w[rng.randint(0, n, max(1, n // 50))] = w[0]          # some exact ties
+        wd = torch.from_numpy(w).to(dev)
+        order = np.argsort(w, kind="stable")
+        for k in sorted({1, min(n, 100), min(n, 4096)}):
+            assert np.array_equal(engine.top_indices(wd, k, True).cpu().numpy(), order[-k:])
+            assert np.array_equal(engine.top_indices(wd, k, False).cpu().numpy(), order[:k])
+
+
 @pytest.mark.parametrize("name", SCORE_CASES)
 def test_top_indices_match_stable_argsort(golden_dir, name, dev):
     from diagan_b200 import engine
@@ -676,6 +730,34 @@ def test_blur_h16_vs_upfirdn2d_oracle(H, C, pad, stride, n, prec, dev):
                            stream_ptr(dev)), "sdg_blur_h16")
     err = (out.float().cpu() - want).abs().max().item()
     assert err <= want.abs().max().item() * (2.0 ** -10 if prec == "fp16" else 2.0 ** -7)
+
+
+@pytest.mark.parametrize("H,W,C,n", [(32, 32, 64, 3), (64, 64, 128, 2), (100, 36, 64, 2), (256, 256, 128, 1), (33, 70, 256, 2)])
+@pytest.mark.parametrize("pad,stride", [(2, 1), (1, 2), (1, 1), (0, 1), (3, 2)])
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_blur_tma_bit_equal_to_register_kernel(H, W, C, n, pad, stride, prec, dev):
+    """every variant of the TMA-fed blur (csrc/blur_tma.cu) == the register-sliding kernel it replaces, bit for bit, incl.
+    ragged strips / segments, non-square images and every padding; the latter is pinned to upfirdn2d above"""
+    import os
+    from diagan_b200 import _lib
+    from diagan_b200._lib import check, ptr, stream_ptr
+    lib = _lib.load()
+    dt = _tdt(prec)
+    pc = {"fp16": _lib.PREC_FP16, "bf16": _lib.PREC_BF16}[prec]
+    x = torch.randn(n, H, W, C, generator=torch.Generator().manual_seed(H * W + C)).to(dt).to(dev)
+    ho, wo = (H + 2 * pad - 4) // stride + 1, (W + 2 * pad - 4) // stride + 1
+    outs = []
+    try:
+        for v in (0, 1, 2, 3):
+            os.environ["SDG_BLUR_TMA"] = str(v)
+            out = torch.full((n, ho, wo, C), float("nan"), dtype=dt, device=dev)
+            check(lib.sdg_blur_h16(ptr(x), ptr(out), n, H, W, C, pad, stride, pc, stream_ptr(dev)), "sdg_blur_h16")
+            outs.append(out.view(torch.int16).cpu())
+    finally:
+        os.environ.pop("SDG_BLUR_TMA", None)
+    assert not torch.isnan(outs[0].view(dt).float()).any()
+    for v in (1, 2, 3):
+        assert torch.equal(outs[0], outs[v]), f"variant {v} differs from the register kernel"
 
 
 @pytest.mark.parametrize("size", [32, 128])
