@@ -66,12 +66,15 @@ WORKLOADS = {
                     metric="per-sample D logits + LDR scores per second (SNGAN-64, CelebA shape, 202 599 samples)",
                     desc="configs[2]: SNGAN-64 recording pass + Welford stats + ldr_conf_5.0_ratio_50 weights + top-100 over ONE "
                          "202 599 x 3x64x64 uint8 dataset",
-                    kernel="conv_swap_kernel block1.c2 (3x3 64->64 @64x64 + avg-pool + shortcut; 23.4% of the reference FLOPs) as the "
-                           "4x4 stride-2 conv in super-pixel form (two output pixels = one 128-channel GEMM pixel, 4x6 taps of which "
-                           "4x4 per output pixel are real: a third of the executed MACs are structural zeros and are NOT counted)",
-                    dom_ref_flop=2.0 * 9 * 64 * 64 * 4096, dom_exec_useful=16.0 / 24.0, cpu_sample=2048,
-                    traffic=((4.399691e9 + 1.052111e9) / 8192.0, "profiles/r1h_ncu_full_sngan64_superpix_summary.txt third launch "
-                             "(8192 samples: 4.400 GB read + 1.052 GB written; algorithmic 512 KiB in + 128 KiB out per sample = 655.4 KB)"),
+                    kernel="b1_fused_kernel<64>: the whole of block 1 in one launch per 32 x 32 image quadrant -- c1 (3x3 3->64 from "
+                           "the bytes, halo recomputed) -> ReLU -> c2 (3x3 64->64 @64x64 + avg-pool, run as the algebraically equal 4x4 "
+                           "stride-2 conv) + image shortcut -> ReLU; 24.5% of the reference FLOPs; CTA pairs (tcgen05.mma.cta_group::2, "
+                           "M = 256 pixels x N = 64 channels, no structural zeros), relu(c1(x)) built and consumed in shared memory; "
+                           "paced by the CUDA-core warps that build that tile, not by the tensor pipe (profiles/r3_b1fused64.md)",
+                    dom_ref_flop=2.0 * 9 * 64 * 64 * 4096 + 2.0 * 27 * 64 * 4096, dom_exec_useful=1.0, cpu_sample=2048,
+                    traffic=((100.9e6 + 1016.5e6) / 8192.0, "profiles/r3_launches_sngan64_fused.md (8192 samples: 100.9 MB read + "
+                             "1016.5 MB written to DRAM during the launch = 136 KB/sample; algorithmic 12 KiB in + 128 KiB out per "
+                             "sample = 143 KB; the two kernels this one replaces moved 1.19 MB/sample)"),
                     eager=dict(ref_batch=64, ref_n=16_384, best_batch=1024, best_n=16_384)),
     "stylegan2": dict(arch="stylegan2", size=256, n_total=2048, n_weak=2048, key="ldr_conf_3.0_ratio_50", flop=None,
                       metric="per-sample D logits + LDR scores per second (StyleGAN2-256 discriminator, FFHQ shape, bounded 2048 "

@@ -185,6 +185,13 @@ SDG_API int sdg_first_conv_h16(const void* x, int layout, const void* wb, const 
 SDG_API int sdg_sngan32_block1_fused_h16(const void* x, const void* w1, const float* b1, const void* w2, const float* bias2,
                                  const float* sc_w3, void* out_relu, void* dbg_t, int64_t n, int precision, void* stream);
 
+/* SNGAN-64 block 1 (torch-mimicry DBlockOptimized(3, 64) of SNGANDiscriminator64; call sites predefined_models.py:76,88) as ONE
+ * launch, per 32 x 32 quadrant of the image (halo recomputed from the neighbouring quadrants' pixels).  x: uint8 [n,64,64,3];
+ * w1 [64][64]; w2 [64][1024] in the 4x4 stride-2 form (K index (a*4+b)*64 + c); bias2 [64]; sc_w3 [64][3];
+ * out_relu [n,32,32,64]; dbg_t: optional [n,64,64,64] copy of relu(c1(x)) (tests), or null. */
+SDG_API int sdg_sngan64_block1_fused_h16(const void* x, const void* w1, const float* b1, const void* w2, const float* bias2,
+                                 const float* sc_w3, void* out_relu, void* dbg_t, int64_t n, int precision, void* stream);
+
 /* ---- dataset transform (the input pipeline of the pass) ----------------------
  * Replaces transforms.Resize(size) + transforms.CenterCrop(size) of datasets/transform.py:3-41 as applied to every item of
  * every recording pass by the reference's DataLoader workers: one pass over the raw uint8 dataset in [n,H,W,C] (C = 3 or 1)

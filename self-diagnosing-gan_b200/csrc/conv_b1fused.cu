@@ -29,6 +29,14 @@
 //   -> TMEM -> relu/convert -> T cells; three batches per unit (128 + 128 + 16 pixels); the two sets split the K columns of the
 //   gather and the channels of the drain.  Epilogue warps (8..11): TMEM -> + bias + 3-FMA image shortcut -> relu -> 16-bit NHWC.
 //   Warp 0: weight TMA, warp 1: c2 MMA issuer, warp 3: c1 MMA issuer (leader CTA), warp 2: TMEM.
+//
+// CH = 64 (SNGANDiscriminator64's DBlockOptimized(3, 64), 64 x 64 images): the same machine per QUADRANT of an image.  A tile
+// is the 32 x 32 pixel quadrant (qy, qx) = 16 x 16 pooled pixels; its T strip (34 x 18 cells per CTA) now carries real halo
+// values -- relu(c1(x)) of the neighbouring quadrants' border pixels, recomputed here (c1 is 2 % of the MACs), zeros only
+// outside the image -- so every cell of a unit is rebuilt for every tile and the patch spans image rows / columns -2 .. 33 of
+// the quadrant.  N = 64: tcgen05.mma.cta_group::2 of M = 256 pixels x N = 64 channels, no structural zeros (the unfused
+// path packs two pooled pixels into one 128-channel GEMM pixel and spends a third of its MACs on zeros); a 64-channel tap is
+// one K chunk, and a weight stage holds TWO taps (the same 8 KB per CTA and 256 MMA cycles per barrier as CH = 128).
 #include <cstdlib>
 
 #include "tc_ptx.cuh"
@@ -37,45 +45,71 @@ namespace sdg {
 
 constexpr int BF_THREADS = 512;
 constexpr int BF_T_THREADS = 256;                       // two sets of four T warps (4..7 and 12..15)
-constexpr int BF_W_STAGES = 5;
-constexpr int BF_W_MAX = 8;                             // barrier slots
-constexpr int BF_W_BYTES = 64 * 64 * 2;                 // 8 KB: this CTA's 64 output channels x 64 k
+constexpr int BF_W_MAX = 8;                             // barrier slots = deepest weight ring
+constexpr int BF_W_BYTES = 64 * 64 * 2;                 // 8 KB per stage: CH = 128: this CTA's 64 output channels x 64 k (half a tap);
+                                                        // CH = 64: its 32 channels x 64 k of two taps (2 x 4 KB)
 constexpr int BF_ROW = 9 * 16;                          // 144: one plane row = 9 cells
 constexpr int BF_K8 = 17 * BF_ROW;                      // 2448: 17 plane rows per 8-channel group
-constexpr int BF_PLANE = 16 * BF_K8;                    // 39168 per (row parity, column parity)
-constexpr int BF_T_BYTES = 4 * BF_PLANE;                // 156672
 constexpr int BF_A1_BYTES = 4 * 128 * 16;               // 8192: [k8 0..3][128 pixels] x 16 B
-constexpr int BF_W1_BYTES = 4 * 64 * 16;                // 4096: [k8 0..3][64 channels] x 16 B
-constexpr int BF_X_ROWB = 64;                           // raw image rows: 56 bytes of the strip's 18 columns at offset 4
-constexpr int BF_X_BYTES = 32 * BF_X_ROWB;              // the image rows of the NEXT tile, as they land (cp.async)
-constexpr int BF_P_ROWB = 160;                          // normalised 16-bit patch: 19 pixels x (c0, c1, c2, pad) per row
-constexpr int BF_P_BYTES = 34 * BF_P_ROWB;              // rows -1..32, columns 15 s - 1 .. 15 s + 17; out-of-image pixels stay zero
-constexpr int BF_OFF_T = BF_W_STAGES * BF_W_BYTES;
-constexpr int BF_OFF_A1 = BF_OFF_T + BF_T_BYTES;
-constexpr int BF_OFF_W1 = BF_OFF_A1 + 2 * BF_A1_BYTES;  // A1 is double-buffered
-constexpr int BF_OFF_X = BF_OFF_W1 + BF_W1_BYTES;
-constexpr int BF_OFF_P = BF_OFF_X + BF_X_BYTES;
+constexpr int BF_X_ROWB = 64;                           // raw image rows: the bytes of the strip's columns (CH = 128: 56 at offset 4)
+constexpr int BF_P_ROWB = 160;                          // normalised 16-bit patch: up to 20 pixels x (c0, c1, c2, pad) per row
 constexpr int BF_SC_BYTES = 2 * 128 * 16;               // shortcut operand: [k8 0..1][128 output pixels] x 16 B
-constexpr int BF_OFF_SC = BF_OFF_P + BF_P_BYTES;
-constexpr int kB1FusedSmem = 1024 + BF_OFF_SC + BF_SC_BYTES;
-constexpr int BF_W2_LD = 16 * 128 + 64;                 // packed c2 weights: 16 taps x 128 channels + one 64-column chunk for the shortcut
-constexpr int BF_SC_CHUNK = 32;                         // ... which is K chunk 32
-static_assert(kB1FusedSmem <= 227 * 1024 - 1024, "b1_fused_kernel: shared memory budget (static: < 1 KB of barriers)");
+
+template <int CH>
+struct Bf {
+  static constexpr bool QUAD = CH == 64;                // tile = quadrant of a 64 x 64 image (else: the 32 x 32 image)
+  static constexpr int IMG = QUAD ? 64 : 32;            // image side
+  static constexpr int NH = CH / 2;                     // output channels (B rows) per CTA
+  static constexpr int G = CH / 8;                      // 8-channel groups per pixel
+  static constexpr int PLANE = G * BF_K8;               // bytes per (row parity, column parity) plane: 39168 | 19584
+  static constexpr int T_BYTES = 4 * PLANE;             // 156672 | 78336
+  static constexpr int W1_BYTES = 4 * NH * 16;          // [k8 0..3][NH channels] x 16 B
+  static constexpr int W_STAGES = QUAD ? 8 : 5;         // weight ring depth (T leaves room for 8 when CH = 64)
+  static constexpr int CHUNKS = QUAD ? 4 : 16;          // weight stages per phase (8 taps: half a tap | two taps per stage)
+  static constexpr int X_ROWS = QUAD ? 36 : 32;         // landing buffer: image rows -2 .. 33 of the quadrant | the image's 32 rows
+  static constexpr int X_BYTES = X_ROWS * BF_X_ROWB;
+  static constexpr int P_ROWS = QUAD ? 36 : 34;         // patch rows -2 .. 33 | -1 .. 32
+  static constexpr int P_BYTES = P_ROWS * BF_P_ROWB;
+  static constexpr int OFF_T = W_STAGES * BF_W_BYTES;
+  static constexpr int OFF_A1 = OFF_T + T_BYTES;
+  static constexpr bool ALT = QUAD;                     // the two T-warp sets take alternate batches (below) instead of halves of each
+  static constexpr int NA1 = ALT ? 4 : 2;               // im2col buffers = c1 accumulators: two per set | double-buffered
+  static constexpr int OFF_W1 = OFF_A1 + NA1 * BF_A1_BYTES;
+  static constexpr int OFF_X = OFF_W1 + W1_BYTES;
+  static constexpr int OFF_P = OFF_X + X_BYTES;
+  static constexpr int OFF_SC = OFF_P + P_BYTES;
+  static constexpr int OFF_LUT = OFF_SC + BF_SC_BYTES;  // CH = 64: normalised value of every byte, fp32 [256] then 16-bit [256]
+  static constexpr int SMEM = 1024 + OFF_LUT + (QUAD ? 1536 : 0);
+  static constexpr int W2_LD = 16 * CH + 64;            // packed c2 weights: 16 taps x CH channels + one 64-column chunk for the shortcut
+  static constexpr int SC_COL = 16 * CH;                // ... which starts at this column
+  static constexpr int UNIT_CELLS = QUAD ? 306 : 272;   // T cells one unit (row-parity half) computes: 2 x 17 x 9 | 16 x 8 + 16 x 9
+  static_assert(SMEM <= 227 * 1024 - 1024, "b1_fused_kernel: shared memory budget (static: < 1 KB of barriers)");
+};
 
 struct BfParams {
-  const uint8_t* x;          // [n][32][32][3]
-  const h16* w1;             // [128][64] K-major, k = (ky*3+kx)*3 + c (27 real columns)
-  const float* b1;           // [128]
-  h16* out_relu;             // [n][16][16][128]
-  h16* dbg_t;                // [n][32][32][128] copy of T (tests only) or null
+  const uint8_t* x;          // [n][IMG][IMG][3]
+  const h16* w1;             // [CH][64] K-major, k = (ky*3+kx)*3 + c (27 real columns)
+  const float* b1;           // [CH]
+  h16* out_relu;             // [n][IMG/2][IMG/2][CH]
+  h16* dbg_t;                // [n][IMG][IMG][CH] copy of T (tests only) or null
   int* ovf;                  // fp16 range guard flag or null
-  long long n_images;
-  int w_stages;              // weight ring depth in use (2..BF_W_STAGES).  tcgen05.mma executes in issue order, so the ring depth also
+  long long n_tiles;         // images (CH = 128) or image quadrants (CH = 64: tile = 4 * image + 2 * qy + qx)
+  int w_stages;              // weight ring depth in use (2..Bf<CH>::W_STAGES).  tcgen05.mma executes in issue order, so the ring depth also
                              // bounds how many c2 chunks (256 MMA cycles each) can be queued ahead of a c1 batch.
                              // (SDG_TIMING_EXPERIMENTS builds accept deeper rings that overwrite T: wrong results)
   int dbg;                   // SDG_TIMING_EXPERIMENTS builds only (WRONG results): 1 no gather, 2 no T drain, 4 no c2 epilogue, 8 no c1 MMAs,
                              // 16 no c2 MMAs, 32 no weight loads
 };
+
+// normalise as transform.py:3-11 does in fp32, (u / 255 - 0.5) / 0.5, without the two IEEE divisions: u * (1/255) with one
+// Newton correction is the correctly rounded quotient for every u in 0..255 (checked exhaustively; the bit-identity test of
+// relu(c1(x)) against first_conv_kernel, which divides, covers it on the GPU), and dividing by 0.5 is an exact doubling
+__device__ __forceinline__ float bf_nrm(uint8_t u) {
+  const float f = (float)u, r = 1.0f / 255.0f;
+  float q = __fmul_rn(f, r);
+  q = __fmaf_rn(__fmaf_rn(-q, 255.0f, f), r, q);
+  return __fmul_rn(__fsub_rn(q, 0.5f), 2.0f);
+}
 
 // K-major operand without swizzle: rows of a group 16 B apart, 8-row groups `sbo` bytes apart, K halves `lbo` bytes apart
 __device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
@@ -95,7 +129,15 @@ __device__ __forceinline__ void bf_chunk(int ph, int idx, int& ky, int& kx, int&
 }
 
 // pixel `m` of batch `b` of the unit with row parity `pr`, strip `s`: cell (R, C) of column-parity plane pc
+template <bool QUAD>
 __device__ __forceinline__ bool bf_pixel(int s, int pr, int b, int m, int& R, int& C, int& pc) {
+  if (QUAD) {                                           // every cell of both column-parity planes: 2 x (17 rows x 9 cells)
+    const int idx = b * 128 + m;
+    pc = idx >= 153 ? 1 : 0;
+    const int rem = idx - 153 * pc;
+    R = rem / 9; C = rem - R * 9;
+    return idx < 306;
+  }
   int rr;
   bool valid = true;
   if (b == 0) {                                         // the 8-column parity plane: 16 rows x 8 cells
@@ -109,18 +151,23 @@ __device__ __forceinline__ bool bf_pixel(int s, int pr, int b, int m, int& R, in
   return valid;
 }
 
-template <bool F16>
+template <bool F16, int CH>
 __global__ void __launch_bounds__(BF_THREADS, 1)
 b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
+  using B = Bf<CH>;
+  constexpr bool QUAD = B::QUAD, ALT = B::ALT;
+  constexpr int NH = B::NH, G = B::G, IMG = B::IMG;
+  constexpr int BF_OFF_T = B::OFF_T, BF_OFF_A1 = B::OFF_A1, BF_OFF_W1 = B::OFF_W1, BF_OFF_X = B::OFF_X, BF_OFF_P = B::OFF_P,
+                BF_OFF_SC = B::OFF_SC, BF_T_BYTES = B::T_BYTES, BF_P_BYTES = B::P_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   __shared__ __align__(8) uint64_t bar_wfull[BF_W_MAX];
   __shared__ __align__(8) uint64_t bar_wempty[BF_W_MAX];
-  __shared__ __align__(8) uint64_t bar_a1_full[2];
-  __shared__ __align__(8) uint64_t bar_c1_full[2];
-  __shared__ __align__(8) uint64_t bar_c1_empty[2];
+  __shared__ __align__(8) uint64_t bar_a1_full[4];
+  __shared__ __align__(8) uint64_t bar_c1_full[4];
+  __shared__ __align__(8) uint64_t bar_c1_empty[4];
   __shared__ __align__(8) uint64_t bar_t_ready[2];
   __shared__ __align__(8) uint64_t bar_t_free[2];
   __shared__ __align__(8) uint64_t bar_acc_full[2];
@@ -147,9 +194,9 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
   for (int i = threadIdx.x; i < BF_P_BYTES / 16; i += BF_THREADS)
     reinterpret_cast<uint4*>(smem_gen + BF_OFF_P)[i] = make_uint4(0u, 0u, 0u, 0u);
   // c1 weights of this CTA's 64 channels, no-swizzle [k8][row]; the bias rides in K columns 27 (hi) and 28 (lo)
-  for (int i = threadIdx.x; i < 64 * 4; i += BF_THREADS) {
+  for (int i = threadIdx.x; i < NH * 4; i += BF_THREADS) {
     const int r = i >> 2, j = i & 3;
-    const int o = s * 64 + r;
+    const int o = s * NH + r;
     uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.w1) + o * 128 + j * 16);
     if (j == 3) {
       const float b = p.b1[o];
@@ -159,7 +206,12 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       w.y = (w.y & 0x0000ffffu) | (hi << 16);           // k = 27
       w.z = (w.z & 0xffff0000u) | lo;                   // k = 28
     }
-    *reinterpret_cast<uint4*>(smem_gen + BF_OFF_W1 + j * 1024 + r * 16) = w;
+    *reinterpret_cast<uint4*>(smem_gen + BF_OFF_W1 + j * (NH * 16) + r * 16) = w;
+  }
+  if (QUAD && threadIdx.x < 256) {
+    const float v = bf_nrm((uint8_t)threadIdx.x);
+    reinterpret_cast<float*>(smem_gen + B::OFF_LUT)[threadIdx.x] = v;
+    reinterpret_cast<uint16_t*>(smem_gen + B::OFF_LUT + 1024)[threadIdx.x] = (uint16_t)(pack_h2<F16>(v, 0.f) & 0xffffu);
   }
   fence_proxy_async_smem();
 
@@ -169,10 +221,12 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       mbar_init(smem_u32(&bar_wfull[i]), 1);
       mbar_init(smem_u32(&bar_wempty[i]), 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bar_a1_full[i]), 16);         // 8 T warps x 2 CTAs
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(smem_u32(&bar_a1_full[i]), ALT ? 8 : 16);      // the T warps that build a batch (one set | both) x 2 CTAs
       mbar_init(smem_u32(&bar_c1_full[i]), 1);
-      mbar_init(smem_u32(&bar_c1_empty[i]), 16);
+      mbar_init(smem_u32(&bar_c1_empty[i]), ALT ? 8 : 16);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar_t_ready[i]), 16);
       mbar_init(smem_u32(&bar_t_free[i]), 1);
       mbar_init(smem_u32(&bar_acc_full[i]), 1);
@@ -190,7 +244,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
 
   const long long cluster_id = blockIdx.x >> 1;
   const long long n_clusters = gridDim.x >> 1;
-  const long long my_tiles = cluster_id < p.n_images ? (p.n_images - cluster_id + n_clusters - 1) / n_clusters : 0;
+  const long long my_tiles = cluster_id < p.n_tiles ? (p.n_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
   const uint32_t t_base = smem_base + BF_OFF_T;
   const bool t_warp = (warp >= 4 && warp < 8) || warp >= 12;
 
@@ -200,20 +254,29 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       int ws = 0;
       uint32_t phase = 0;
       for (long long l = 0; l < my_tiles; ++l) {
-        for (int ci = -1; ci < 32; ++ci) {              // the shortcut chunk, then phase 0's and phase 1's sixteen
+        for (int ci = -1; ci < 2 * B::CHUNKS; ++ci) {   // the shortcut chunk, then phase 0's and phase 1's stages
           {
-            int it = BF_SC_CHUNK;
+            int col = B::SC_COL;                        // first K column of the stage in the packed weights
             if (ci >= 0) {
-              int ky, kx, h;
-              bf_chunk(ci >> 4, ci & 15, ky, kx, h);
-              it = (ky * 4 + kx) * 2 + h;
+              if (QUAD) {                               // taps (ky, kx0) and (ky, kx0 + 1): 128 consecutive columns
+                const int ph = ci / B::CHUNKS, idx = ci % B::CHUNKS;
+                col = (((ph == 0 ? 1 : 0) + 2 * (idx >> 1)) * 4 + 2 * (idx & 1)) * 64;
+              } else {
+                int ky, kx, h;
+                bf_chunk(ci >> 4, ci & 15, ky, kx, h);
+                col = ((ky * 4 + kx) * 2 + h) * 64;
+              }
             }
-            mbar_wait(smem_u32(&bar_wempty[ws]), phase ^ 1u);
+            const bool two = QUAD && ci >= 0;           // two [NH x 64] boxes per stage; the shortcut chunk of CH = 64 is one
+            const uint32_t bytes = (QUAD && ci < 0) ? BF_W_BYTES / 2 : BF_W_BYTES;
+            mbar_wait_relaxed(smem_u32(&bar_wempty[ws]), phase ^ 1u);
             if (dbg & 32) {                             // timing experiment (wrong results): no weight loads at all
               if (leader) mbar_arrive(smem_u32(&bar_wfull[ws]));
             } else {
-              if (leader) mbar_expect_tx(smem_u32(&bar_wfull[ws]), 2 * BF_W_BYTES);
-              tma_load_2d_pair(smem_base + ws * BF_W_BYTES, &map_w2, mapa_u32(smem_u32(&bar_wfull[ws]), 0), it * 64, (int)rank * 64);
+              const uint32_t wfull = mapa_u32(smem_u32(&bar_wfull[ws]), 0);
+              if (leader) mbar_expect_tx(smem_u32(&bar_wfull[ws]), 2 * bytes);
+              tma_load_2d_pair(smem_base + ws * BF_W_BYTES, &map_w2, wfull, col, (int)rank * NH);
+              if (two) tma_load_2d_pair(smem_base + ws * BF_W_BYTES + BF_W_BYTES / 2, &map_w2, wfull, col + 64, (int)rank * NH);
             }
             if (++ws == w_stages) { ws = 0; phase ^= 1u; }
           }
@@ -226,7 +289,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
     // MMA cycles: the loop below touches ONE barrier per chunk and tests the next stage's barrier before issuing this stage's
     // MMAs so that the test's latency hides behind them; c1's batches have their own issuer (warp 3).
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = make_idesc(256, 128, F16);
+      constexpr uint32_t idesc = make_idesc(256, CH, F16);
       // every address below is loop invariant; a single thread pays ~10 cycles per dependent instruction, so nothing is
       // recomputed per chunk: barrier addresses advance by 8, the weight descriptor by 8 KB >> 4, and T's descriptors are
       // compile-time offsets from t_base (the 16 chunks of a phase are unrolled)
@@ -240,7 +303,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       const uint64_t sc_desc = make_nosw_desc(smem_base + BF_OFF_SC, 2048, 128);
       for (long long l = 0; l < my_tiles; ++l) {
         const int acc = (int)(l & 1);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * CH);
         {
           // the tile's first MMA initialises the accumulator with bias + W_sc . avg_pool2d(x): one K = 16 step whose operands
           // carry the fp32 terms as 16-bit hi / lo pairs (columns: ph.wh, pl.wh, ph.wl, 1.bias_hi, 1.bias_lo, 1.bias_lo2)
@@ -261,22 +324,37 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
           mbar_wait(smem_u32(&bar_t_ready[ph]), (uint32_t)(l & 1));
           tc_fence_after();
 #pragma unroll
-          for (int idx = 0; idx < 16; ++idx) {
-            const int ky = (ph == 0 ? 1 : 0) + 2 * (idx >> 3), kx = (idx >> 1) & 3, h = idx & 1;      // = bf_chunk(ph, idx)
+          for (int idx = 0; idx < B::CHUNKS; ++idx) {
             constexpr int kStep = (2 * BF_K8) >> 4;
-            const int a_off = ((((ky & 1) * 2 + (kx & 1)) * 16 + h * 8) * BF_K8 + (ky >> 1) * BF_ROW + (kx >> 1) * 16) >> 4;
             if (!ready) mbar_wait(wfull0 + wo, wphase);
             tc_fence_after();
             const uint32_t cur = wo;
             wo += 8u;
             if (wo == w_wrap) { wo = 0; wphase ^= 1u; }
             ready = mbar_try_wait(wfull0 + wo, wphase);                     // next stage: consumed after the MMAs below
-            const uint64_t adesc = t_desc0 + (uint64_t)a_off;
             const uint64_t bdesc = w_desc0 + (uint64_t)(cur * (BF_W_BYTES / 16 / 8));
-            if (!(dbg & 16)) {
+            if (QUAD) {
+              // stage idx = taps (ky, kx0) and (ky, kx0 + 1), 64 channels each: 2 x 4 MMAs of K = 16
+              const int ky = (ph == 0 ? 1 : 0) + 2 * (idx >> 1), kx0 = 2 * (idx & 1);
+              if (!(dbg & 16)) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                umma_pair(d_tmem, adesc + (uint64_t)(j * kStep), bdesc + (uint64_t)(2 * j), idesc, 1u);
+                for (int e = 0; e < 2; ++e) {
+                  const int kx = kx0 + e;
+                  const int a_off = ((((ky & 1) * 2 + (kx & 1)) * G) * BF_K8 + (ky >> 1) * BF_ROW + (kx >> 1) * 16) >> 4;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    umma_pair(d_tmem, t_desc0 + (uint64_t)(a_off + j * kStep), bdesc + (uint64_t)(e * (BF_W_BYTES / 2 / 16) + 2 * j), idesc, 1u);
+                }
+              }
+            } else {
+              const int ky = (ph == 0 ? 1 : 0) + 2 * (idx >> 3), kx = (idx >> 1) & 3, h = idx & 1;      // = bf_chunk(ph, idx)
+              const int a_off = ((((ky & 1) * 2 + (kx & 1)) * 16 + h * 8) * BF_K8 + (ky >> 1) * BF_ROW + (kx >> 1) * 16) >> 4;
+              const uint64_t adesc = t_desc0 + (uint64_t)a_off;
+              if (!(dbg & 16)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  umma_pair(d_tmem, adesc + (uint64_t)(j * kStep), bdesc + (uint64_t)(2 * j), idesc, 1u);
+              }
             }
             umma_commit_pair(wempty0 + cur, 3);
           }
@@ -288,21 +366,22 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
   } else if (warp == 3) {
     // ================= c1 MMA issuer (leader CTA only): one K = 32 batch of 256 pixels whenever both CTAs have built it =================
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = make_idesc(256, 128, F16);
+      constexpr uint32_t idesc = make_idesc(256, CH, F16);
       const uint64_t a1desc = make_nosw_desc(smem_base + BF_OFF_A1, 2048, 128);
-      const uint64_t w1desc = make_nosw_desc(smem_base + BF_OFF_W1, 1024, 128);
+      const uint64_t w1desc = make_nosw_desc(smem_base + BF_OFF_W1, NH * 16, 128);
       const long long g_total = 6 * my_tiles;
       for (long long g = 0; g < g_total; ++g) {
-        const int cb = (int)(g & 1);
-        const uint32_t par = (uint32_t)((g >> 1) & 1);
+        // buffer / accumulator of batch g and the parity of its use: double-buffered, or (ALT) two per T-warp set
+        const int cb = ALT ? (int)((g & 1) * 2 + ((g >> 1) & 1)) : (int)(g & 1);
+        const uint32_t par = ALT ? (uint32_t)((g >> 2) & 1) : (uint32_t)((g >> 1) & 1);
         mbar_wait(smem_u32(&bar_a1_full[cb]), par);
         mbar_wait(smem_u32(&bar_c1_empty[cb]), par ^ 1u);
         tc_fence_after();
-        const uint32_t d = tmem_base + 256u + (uint32_t)(cb * 128);
+        const uint32_t d = tmem_base + 256u + (uint32_t)(cb * CH);
         const uint64_t ad = a1desc + (uint64_t)(cb * (BF_A1_BYTES >> 4));
         if (!(dbg & 8)) {
           umma_pair(d, ad, w1desc, idesc, 0u);                              // k = 0..15
-          umma_pair(d, ad + 256u, w1desc + 128u, idesc, 1u);                // k = 16..31 (27, 28: bias; 29..31 zero)
+          umma_pair(d, ad + 256u, w1desc + (uint64_t)(2 * NH), idesc, 1u);  // k = 16..31 (27, 28: bias; 29..31 zero)
         }
         umma_commit_pair(smem_u32(&bar_c1_full[cb]), 3);
       }
@@ -315,47 +394,87 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
     const int q = warp & 3;
     const int tt = q * 32 + lane;                       // batch pixel = TMEM lane
     const int t256 = set * 128 + tt;
-    const int goff = s ? 40 : 0;                        // first byte of an image row held in the landing buffer
     constexpr uint32_t kOne = F16 ? 0x3C00u : 0x3F80u;
-    // raw rows of tile l -> the (single) landing buffer; the strip needs image columns 15 s - 1 .. 15 s + 17 = bytes goff .. goff + 55
+    constexpr int XO = QUAD ? 0 : 4;                    // offset of the landed bytes inside a landing-buffer row
+    // tile l of this cluster: image n and (CH = 64) quadrant (qy, qx); goff = first byte of an image row held in the landing
+    // buffer (4-byte aligned; CH = 128: image columns 15 s - 1 .. 15 s + 17 = bytes goff .. goff + 55; CH = 64: image columns
+    // 32 qx + 16 s - 2 .. + 17, the 64 bytes from goff, clipped at the row end)
+    auto tile_of = [&](long long l, long long& n, int& qy, int& qx, int& goff) {
+      const long long t = cluster_id + l * n_clusters;
+      if (QUAD) {
+        n = t >> 2; qy = (int)(t & 3) >> 1; qx = (int)(t & 1);
+        const int b0 = (32 * qx + 16 * s - 2) * 3;
+        goff = b0 < 0 ? 0 : (b0 & ~3);
+      } else {
+        n = t; qy = 0; qx = 0; goff = s ? 40 : 0;
+      }
+    };
+    // raw rows of tile l -> the (single) landing buffer
     auto prefetch_x = [&](long long l) {
       if (l < my_tiles) {
-        const long long n = cluster_id + l * n_clusters;
-        const uint8_t* src = p.x + n * 3072 + goff;
-        const uint32_t dst = smem_base + BF_OFF_X + 4;
-        for (int w = t256; w < 32 * 14; w += BF_T_THREADS) {
-          const int row = w / 14, wi = w - row * 14;
-          cp_async_4(dst + row * BF_X_ROWB + wi * 4, src + row * 96 + wi * 4);
+        long long n; int qy, qx, goff;
+        tile_of(l, n, qy, qx, goff);
+        const uint32_t dst = smem_base + BF_OFF_X + XO;
+        if (QUAD) {
+          const uint8_t* src = p.x + n * (64 * 64 * 3) + goff;
+          for (int w = t256; w < 36 * 16; w += BF_T_THREADS) {
+            const int row = w >> 4, wi = w & 15;
+            const int Y = 32 * qy - 2 + row;
+            if (Y >= 0 && Y < 64 && goff + wi * 4 < 192) cp_async_4(dst + row * BF_X_ROWB + wi * 4, src + Y * 192 + wi * 4);
+          }
+        } else {
+          const uint8_t* src = p.x + n * 3072 + goff;
+          for (int w = t256; w < 32 * 14; w += BF_T_THREADS) {
+            const int row = w / 14, wi = w - row * 14;
+            cp_async_4(dst + row * BF_X_ROWB + wi * 4, src + row * 96 + wi * 4);
+          }
         }
       }
       cp_async_commit();
     };
-    // normalise as transform.py:3-11 does in fp32, (u / 255 - 0.5) / 0.5, without the two IEEE divisions: u * (1/255) with one
-    // Newton correction is the correctly rounded quotient for every u in 0..255 (checked exhaustively; the bit-identity test of
-    // relu(c1(x)) against first_conv_kernel, which divides, covers it on the GPU), and dividing by 0.5 is an exact doubling
-    auto nrm = [](uint8_t u) {
-      const float f = (float)u, r = 1.0f / 255.0f;
-      float q = __fmul_rn(f, r);
-      q = __fmaf_rn(__fmaf_rn(-q, 255.0f, f), r, q);
-      return __fmul_rn(__fsub_rn(q, 0.5f), 2.0f);
-    };
+    auto nrm = [](uint8_t u) { return bf_nrm(u); };
+    // CH = 64 converts 2 160 bytes per tile on warps whose instruction stream paces the kernel: a table lookup per byte instead
+    // (the entries are nrm()'s values and their 16-bit roundings, so the operands are bit-identical)
+    const float* lut32 = reinterpret_cast<const float*>(smem_gen + B::OFF_LUT);
+    const uint16_t* lut16 = reinterpret_cast<const uint16_t*>(smem_gen + B::OFF_LUT + 1024);
     // landed bytes -> (a) normalised 16-bit patch, the first conv's operand values, converted ONCE per byte instead of once per
     // tap: patch pixel (ry, cx) = image pixel (ry - 1, 15 s - 1 + cx) as (c0, c1, c2, 0); 18 in-image columns per row;
     // (b) the shortcut operand of tile L: row m = avg_pool2d(normalised x) at output pixel (m >> 3, 8 s + (m & 7)) as hi / lo pairs
+    // CH = 64: patch pixel (ry, cx) = quadrant pixel (ry - 2, 16 s - 2 + cx), 20 columns; pixels outside the IMAGE are written as
+    // zeros for every tile (which ones they are changes with the quadrant)
     auto convert_x = [&](long long L) {
-      const uint8_t* raw = smem_gen + BF_OFF_X + 4;
-      for (int i = t256; i < 32 * 18; i += BF_T_THREADS) {
-        const int row = i / 18, j = i - row * 18;       // j-th in-image pixel of the row: image column (s ? 14 : 0) + j
-        const uint8_t* b = raw + row * BF_X_ROWB + 3 * ((s ? 14 : 0) + j) - goff;
-        const uint32_t lo = pack_h2<F16>(nrm(b[0]), nrm(b[1])), hi = pack_h2<F16>(nrm(b[2]), 0.f);
-        *reinterpret_cast<uint2*>(smem_gen + BF_OFF_P + (row + 1) * BF_P_ROWB + (j + (s ? 0 : 1)) * 8) = make_uint2(lo, hi);
+      const uint8_t* raw = smem_gen + BF_OFF_X + XO;
+      long long n_; int qy, qx, goff;
+      tile_of(L, n_, qy, qx, goff);
+      if (QUAD) {
+        for (int i = t256; i < 36 * 20; i += BF_T_THREADS) {
+          const int ry = i / 20, cx = i - ry * 20;
+          const int Y = 32 * qy - 2 + ry, X = 32 * qx + 16 * s - 2 + cx;
+          uint2 v = make_uint2(0u, 0u);
+          if (Y >= 0 && Y < 64 && X >= 0 && X < 64) {
+            const uint8_t* b = raw + ry * BF_X_ROWB + 3 * X - goff;
+            v = make_uint2((uint32_t)lut16[b[0]] | ((uint32_t)lut16[b[1]] << 16), (uint32_t)lut16[b[2]]);
+          }
+          *reinterpret_cast<uint2*>(smem_gen + BF_OFF_P + ry * BF_P_ROWB + cx * 8) = v;
+        }
+      } else {
+        for (int i = t256; i < 32 * 18; i += BF_T_THREADS) {
+          const int row = i / 18, j = i - row * 18;     // j-th in-image pixel of the row: image column (s ? 14 : 0) + j
+          const uint8_t* b = raw + row * BF_X_ROWB + 3 * ((s ? 14 : 0) + j) - goff;
+          const uint32_t lo = pack_h2<F16>(nrm(b[0]), nrm(b[1])), hi = pack_h2<F16>(nrm(b[2]), 0.f);
+          *reinterpret_cast<uint2*>(smem_gen + BF_OFF_P + (row + 1) * BF_P_ROWB + (j + (s ? 0 : 1)) * 8) = make_uint2(lo, hi);
+        }
       }
       mbar_wait(smem_u32(&bar_sc_free), (uint32_t)((L & 1) ^ 1));     // the previous tile's shortcut MMA has read the buffer
       {
-        const uint8_t* b = raw + (2 * (tt >> 3)) * BF_X_ROWB + 3 * (2 * (8 * s + (tt & 7))) - goff;
+        // the 2 x 2 input pixels under pooled output pixel (tt >> 3, 8 s + (tt & 7)) of the tile
+        const uint8_t* b = QUAD ? raw + (2 + 2 * (tt >> 3)) * BF_X_ROWB + 3 * (32 * qx + 2 * (8 * s + (tt & 7))) - goff
+                                : raw + (2 * (tt >> 3)) * BF_X_ROWB + 3 * (2 * (8 * s + (tt & 7))) - goff;
         float px[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) px[c] = (nrm(b[c]) + nrm(b[3 + c]) + nrm(b[BF_X_ROWB + c]) + nrm(b[BF_X_ROWB + 3 + c])) * 0.25f;
+        for (int c = 0; c < 3; ++c)
+          px[c] = QUAD ? (lut32[b[c]] + lut32[b[3 + c]] + lut32[b[BF_X_ROWB + c]] + lut32[b[BF_X_ROWB + 3 + c]]) * 0.25f
+                       : (nrm(b[c]) + nrm(b[3 + c]) + nrm(b[BF_X_ROWB + c]) + nrm(b[BF_X_ROWB + 3 + c])) * 0.25f;
         uint32_t ph[3], pl[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -371,21 +490,24 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_sc_full), 0));
     };
-    // gather this set's 16 K columns of batch pixel tt of (unit uu, batch b) of the tile in the patch into A1[gb]:
-    // K column k = (ky*3 + kx)*3 + c for k < 27; 27, 28 = 1.0 (bias hi / lo); 29..31 = 0
+    // gather the K columns of batch pixel tt of (unit uu, batch b) of the tile in the patch into A1[gb] -- this set's 16 columns,
+    // or (ALT) all 32: K column k = (ky*3 + kx)*3 + c for k < 27; 27, 28 = 1.0 (bias hi / lo); 29..31 = 0
     auto build_a1 = [&](int uu, int b, int gb) {
       const int pr = 1 - uu;
       int R, C, pc;
-      const bool valid = bf_pixel(s, pr, b, tt, R, C, pc);
+      const bool valid = bf_pixel<QUAD>(s, pr, b, tt, R, C, pc);
       if (valid && !(dbg & 1)) {
-        const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;
-        // pixel (y + ky - 1, x - 1) of tap row ky: patch row y + ky, patch column x - 1 - (15 s - 1) = x - 15 s
-        const uint2* row0 = reinterpret_cast<const uint2*>(smem_gen + BF_OFF_P + y * BF_P_ROWB + (x - 15 * s) * 8);
+        const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;       // pixel of the tile: rows -1 .. 32, columns 16 s - 1 .. 16 s + 16
+        // pixel (y + ky - 1, x - 1) of tap row ky: CH = 128: patch row y + ky, patch column x - 1 - (15 s - 1) = x - 15 s;
+        // CH = 64: patch row y + ky + 1, patch column x - 1 - (16 s - 2) = x - 16 s + 1
+        const uint2* row0 = QUAD ? reinterpret_cast<const uint2*>(smem_gen + BF_OFF_P + (y + 1) * BF_P_ROWB + (x - 16 * s + 1) * 8)
+                                 : reinterpret_cast<const uint2*>(smem_gen + BF_OFF_P + y * BF_P_ROWB + (x - 15 * s) * 8);
         const uint2* row1 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(row0) + BF_P_ROWB);
         const uint2* row2 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(row0) + 2 * BF_P_ROWB);
-        uint32_t w[8];
-        if (set == 0) {
+        uint8_t* row = smem_gen + BF_OFF_A1 + gb * BF_A1_BYTES + tt * 16;
+        if (ALT || set == 0) {
           const uint2 a0 = row0[0], a1 = row0[1], a2 = row0[2], b0 = row1[0], b1 = row1[1], b2 = row1[2];
+          uint32_t w[8];
           w[0] = a0.x;
           w[1] = __byte_perm(a0.y, a1.x, 0x5410);       // lo16(a0.y) | lo16(a1.x) << 16
           w[2] = __byte_perm(a1.x, a1.y, 0x5432);       // hi16(a1.x) | lo16(a1.y) << 16
@@ -394,8 +516,12 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
           w[5] = __byte_perm(b0.x, b0.y, 0x5432);
           w[6] = b1.x;
           w[7] = __byte_perm(b1.y, b2.x, 0x5410);
-        } else {
+          *reinterpret_cast<uint4*>(row) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(row + 2048) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        if (ALT || set == 1) {
           const uint2 b2 = row1[2], c0 = row2[0], c1 = row2[1], c2 = row2[2];
+          uint32_t w[8];
           w[0] = __byte_perm(b2.x, b2.y, 0x5432);
           w[1] = c0.x;
           w[2] = __byte_perm(c0.y, c1.x, 0x5410);
@@ -404,78 +530,121 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
           w[5] = (c2.y & 0xffffu) | (kOne << 16);
           w[6] = kOne;
           w[7] = 0u;
+          *reinterpret_cast<uint4*>(row + 2 * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(row + 3 * 2048) = make_uint4(w[4], w[5], w[6], w[7]);
         }
-        uint8_t* row = smem_gen + BF_OFF_A1 + gb * BF_A1_BYTES + (2 * set) * 2048 + tt * 16;
-        *reinterpret_cast<uint4*>(row) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(row + 2048) = make_uint4(w[4], w[5], w[6], w[7]);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_a1_full[gb]), 0));
     };
-    if (my_tiles > 0) {
-      prefetch_x(0);
+    uint32_t vmaxw = 0;                                 // fp16 range guard: running maximum of the (non-negative) packed halves
+    // batch (uu, b) of tile (n, qy, qx) is in TMEM accumulator cb: relu / convert -> T cells.  Channels [ch0, ch0 + NCH).
+    auto drain = [&](long long n, int qy, int qx, int uu, int b, int cb) {
+      constexpr int NCH = ALT ? CH : CH / 2;
+      const int ch0 = ALT ? 0 : set * (CH / 2);
+      const int pr = 1 - uu;
+      int R, C, pc;
+      const bool valid = bf_pixel<QUAD>(s, pr, b, tt, R, C, pc);
+      if ((b < 2 || q < (QUAD ? 2 : 1)) && !(dbg & 2)) {
+        uint8_t* cell = smem_gen + BF_OFF_T + ((pr * 2 + pc) * G + (ch0 >> 3)) * BF_K8 + R * BF_ROW + C * 16;
+        // pixel of the tile (rows -1 .. 32), then of the image; CH = 64: a cell outside the image is conv padding = zero
+        const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;
+        const int Y = 32 * qy + y, X = 32 * qx + x;
+        const bool in_img = !QUAD || (Y >= 0 && Y < 64 && X >= 0 && X < 64);
+        const uint32_t taddr = tmem_base + 256u + (uint32_t)(cb * CH + ch0) + ((uint32_t)(q * 32) << 16);
+        uint32_t r[NCH];
+        tmem_ld32(taddr, r);
+        if (NCH == 64) tmem_ld32(taddr + 32u, r + (NCH == 64 ? 32 : 0));
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int gq = 0; gq < NCH / 8; ++gq) {
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (in_img) {
+              pk.x = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]));
+              pk.y = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
+              pk.z = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+              pk.w = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
+            }
+            if (F16) vmaxw = __vmaxu2(__vmaxu2(vmaxw, pk.x), __vmaxu2(__vmaxu2(pk.y, pk.z), pk.w));
+            *reinterpret_cast<uint4*>(cell + gq * BF_K8) = pk;
+            if (p.dbg_t && in_img)
+              *reinterpret_cast<uint4*>(p.dbg_t + ((((long long)n * IMG + Y) * IMG + X) * CH + ch0 + gq * 8)) = pk;
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();                         // T cells -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_c1_empty[cb]), 0));
+    };
+    // the patch of tile l replaces the previous one: every T thread has landed its rows and nobody reads the old patch any more
+    auto switch_patch = [&](long long l) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       named_bar_sync(1, BF_T_THREADS);
-      convert_x(0);
-      named_bar_sync(1, BF_T_THREADS);
-      prefetch_x(1);
-      build_a1(0, 0, 0);
+      convert_x(l);
+      named_bar_sync(1, BF_T_THREADS);                  // patch complete, landing buffer idle
+      prefetch_x(l + 1);
+    };
+    if (my_tiles > 0) {
+      prefetch_x(0);
+      switch_patch(0);
     }
-    long long g = 0;
-    uint32_t vmaxw = 0;                                 // fp16 range guard: running maximum of the (non-negative) packed halves
-    for (long long l = 0; l < my_tiles; ++l) {
-      const long long n = cluster_id + l * n_clusters;
-      for (int uu = 0; uu < 2; ++uu) {
-        const int pr = 1 - uu;
-        for (int b = 0; b < 3; ++b, ++g) {
-          const int cb = (int)(g & 1);
-          // the next batch's operand first (its buffer was read by batch g - 1, whose completion this thread has seen), so
-          // that its MMA overlaps this batch's drain
-          if (b < 2) build_a1(uu, b + 1, cb ^ 1);
-          else if (uu == 0) build_a1(1, 0, cb ^ 1);
-          else if (l + 1 < my_tiles) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");                // the next image's rows have landed
-            named_bar_sync(1, BF_T_THREADS);                                    // ... for every T thread, and nobody reads this image's patch any more
-            convert_x(l + 1);
-            named_bar_sync(1, BF_T_THREADS);                                    // patch complete, landing buffer idle
-            prefetch_x(l + 2);
-            build_a1(0, 0, cb ^ 1);
-          }
-          mbar_wait(smem_u32(&bar_c1_full[cb]), (uint32_t)((g >> 1) & 1));      // batch g is in TMEM
-          tc_fence_after();
-          if (b == 0) mbar_wait(smem_u32(&bar_t_free[uu]), (uint32_t)((l & 1) ^ 1));   // c2 is done with this half of T
-          int R, C, pc;
-          const bool valid = bf_pixel(s, pr, b, tt, R, C, pc);
-          if ((b < 2 || q == 0) && !(dbg & 2)) {
-            uint8_t* cell = smem_gen + BF_OFF_T + ((pr * 2 + pc) * 16 + set * 8) * BF_K8 + R * BF_ROW + C * 16;
-            const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;
-            const uint32_t taddr = tmem_base + 256u + (uint32_t)(cb * 128 + set * 64) + ((uint32_t)(q * 32) << 16);
-            uint32_t r[64];
-            tmem_ld32(taddr, r);
-            tmem_ld32(taddr + 32u, r + 32);
-            tmem_ld_wait();
-            if (valid) {
-#pragma unroll
-              for (int gq = 0; gq < 8; ++gq) {
-                uint4 pk;
-                pk.x = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]));
-                pk.y = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
-                pk.z = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
-                pk.w = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
-                if (F16) vmaxw = __vmaxu2(__vmaxu2(vmaxw, pk.x), __vmaxu2(__vmaxu2(pk.y, pk.z), pk.w));
-                *reinterpret_cast<uint4*>(cell + gq * BF_K8) = pk;
-                if (p.dbg_t)
-                  *reinterpret_cast<uint4*>(p.dbg_t + (((n * 32 + y) * 32 + x) * 128 + set * 64 + gq * 8)) = pk;
-              }
+    if (ALT) {
+      // The two sets take ALTERNATE batches (set = g & 1), each with two im2col buffers / c1 accumulators of its own: with a
+      // 64-channel c2 the tensor pipe needs a tile's T in ~2 000 cycles, and what paces a batch is the fixed latency of its
+      // barrier round trips and TMEM loads, not instruction issue -- two independent streams per scheduler hide twice as much.
+      // batch g = 6 l + 3 uu + b; buffer (g & 1) * 2 + ((g >> 1) & 1), used every fourth batch.
+      // (32-bit counters: this loop's own arithmetic is part of what paces the kernel; a cluster sees < 2^28 tiles)
+      const int g_total = (int)(6 * my_tiles);
+      auto build = [&](int g) {
+        const int l = g / 6;
+        const int r = g - 6 * l;
+        if (r == set && l > 0) switch_patch(l);         // this set's first batch of tile l (both sets meet here)
+        build_a1(r / 3, r % 3, (g & 1) * 2 + ((g >> 1) & 1));
+      };
+      if (set < g_total) build(set);
+      long long n = 0;
+      int qy = 0, qx = 0, goff_ = 0;
+      for (int g = set; g < g_total; g += 2) {
+        if (g + 2 < g_total) build(g + 2);              // its buffer was read by batch g - 2, whose completion this thread has seen
+        const int l = g / 6;
+        const int r = g - 6 * l, uu = r / 3, b = r - 3 * uu;
+        const int cb = (g & 1) * 2 + ((g >> 1) & 1);
+        if (r == set) tile_of(l, n, qy, qx, goff_);     // this set's first batch of the tile
+        mbar_wait(smem_u32(&bar_c1_full[cb]), (uint32_t)((g >> 2) & 1));       // batch g is in TMEM
+        tc_fence_after();
+        // this set's first batch of the unit (r = 0, 4 | 1, 3): c2 is done with this half of T
+        if (r == set || r == 4 - set) mbar_wait(smem_u32(&bar_t_free[uu]), (uint32_t)((l & 1) ^ 1));
+        drain(n, qy, qx, uu, b, cb);
+        // ... and its last one (r = 2, 4 | 1, 5): the unit is complete once every T warp of both CTAs has said so
+        if ((r == 2 + 3 * set || r == 4 - 3 * set) && lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_t_ready[uu]), 0));
+      }
+    } else {
+      if (my_tiles > 0) build_a1(0, 0, 0);
+      long long g = 0;
+      for (long long l = 0; l < my_tiles; ++l) {
+        long long n; int qy, qx, goff_;
+        tile_of(l, n, qy, qx, goff_);
+        for (int uu = 0; uu < 2; ++uu) {
+          for (int b = 0; b < 3; ++b, ++g) {
+            const int cb = (int)(g & 1);
+            // the next batch's operand first (its buffer was read by batch g - 1, whose completion this thread has seen), so
+            // that its MMA overlaps this batch's drain
+            if (b < 2) build_a1(uu, b + 1, cb ^ 1);
+            else if (uu == 0) build_a1(1, 0, cb ^ 1);
+            else if (l + 1 < my_tiles) {
+              switch_patch(l + 1);
+              build_a1(0, 0, cb ^ 1);
             }
+            mbar_wait(smem_u32(&bar_c1_full[cb]), (uint32_t)((g >> 1) & 1));      // batch g is in TMEM
+            tc_fence_after();
+            if (b == 0) mbar_wait(smem_u32(&bar_t_free[uu]), (uint32_t)((l & 1) ^ 1));   // c2 is done with this half of T
+            drain(n, qy, qx, uu, b, cb);
           }
-          tc_fence_before();
-          fence_proxy_async_smem();                     // T cells -> visible to the tensor core
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_c1_empty[cb]), 0));
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_t_ready[uu]), 0));
         }
-        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_t_ready[uu]), 0));
       }
     }
     // post-ReLU halves are non-negative: inf / NaN <=> a half >= 0x7C00
@@ -486,14 +655,16 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
     const int g4 = lane >> 2, i4 = lane & 3;
     uint32_t vmaxw = 0;
     for (long long l = 0; l < my_tiles; ++l) {
-      const long long n = cluster_id + l * n_clusters;
+      const long long t = cluster_id + l * n_clusters;
+      const long long n = QUAD ? t >> 2 : t;
+      const int qy = QUAD ? (int)(t & 3) >> 1 : 0, qx = QUAD ? (int)(t & 1) : 0;
       const int acc = (int)(l & 1);
-      mbar_wait(smem_u32(&bar_acc_full[acc]), (uint32_t)((l >> 1) & 1));
+      mbar_wait_relaxed(smem_u32(&bar_acc_full[acc]), (uint32_t)((l >> 1) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * CH) + ((uint32_t)(q * 32) << 16);
       if (!(dbg & 4)) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < CH; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
@@ -509,8 +680,8 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
 #pragma unroll
         for (int mm = 0; mm < 4; ++mm) {
           const int m2 = q * 32 + g4 * 4 + mm;
-          const long long opix = (n * 16 + (m2 >> 3)) * 16 + 8 * s + (m2 & 7);
-          *reinterpret_cast<uint4*>(p.out_relu + opix * 128 + c0 + i4 * 8) = make_uint4(pk[4 * mm], pk[4 * mm + 1], pk[4 * mm + 2], pk[4 * mm + 3]);
+          const long long opix = (n * (IMG / 2) + 16 * qy + (m2 >> 3)) * (IMG / 2) + 16 * qx + 8 * s + (m2 & 7);
+          *reinterpret_cast<uint4*>(p.out_relu + opix * CH + c0 + i4 * 8) = make_uint4(pk[4 * mm], pk[4 * mm + 1], pk[4 * mm + 2], pk[4 * mm + 3]);
         }
       }
       }
@@ -530,21 +701,24 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
 }
 
 int b1_fused_init() {
-  SDG_CUDA(cudaFuncSetAttribute(b1_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1FusedSmem));
-  SDG_CUDA(cudaFuncSetAttribute(b1_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB1FusedSmem));
+  SDG_CUDA(cudaFuncSetAttribute((b1_fused_kernel<true, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, Bf<128>::SMEM));
+  SDG_CUDA(cudaFuncSetAttribute((b1_fused_kernel<false, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, Bf<128>::SMEM));
+  SDG_CUDA(cudaFuncSetAttribute((b1_fused_kernel<true, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, Bf<64>::SMEM));
+  SDG_CUDA(cudaFuncSetAttribute((b1_fused_kernel<false, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, Bf<64>::SMEM));
   return 0;
 }
 
-// w2f[o][0..2047] = w2[o][.] (when w2 is given; else the caller packed them in place), then the shortcut chunk:
-// columns 2048.. = wh0 wh1 wh2 | wh0 wh1 wh2 | wl0 wl1 wl2 | bias_hi bias_lo bias_lo2 | zeros, w = wh + wl the fp32 W_sc / sigma
+// w2f[o][0 .. 16 CH) = w2[o][.] (when w2 is given; else the caller packed them in place), then the shortcut chunk:
+// columns 16 CH .. = wh0 wh1 wh2 | wh0 wh1 wh2 | wl0 wl1 wl2 | bias_hi bias_lo bias_lo2 | zeros, w = wh + wl the fp32 W_sc / sigma
 template <bool F16>
 __global__ void __launch_bounds__(256)
 b1_fused_pack_kernel(const h16* __restrict__ w2, const float* __restrict__ sc_w3, const float* __restrict__ bias2,
-                     h16* __restrict__ w2f) {
+                     h16* __restrict__ w2f, int ch) {
   const int o = blockIdx.x;
+  const int kmain = 16 * ch, ld = kmain + 64;
   if (w2)
-    for (int i = threadIdx.x; i < 2048 / 8; i += blockDim.x)
-      reinterpret_cast<uint4*>(w2f + (size_t)o * BF_W2_LD)[i] = reinterpret_cast<const uint4*>(w2 + (size_t)o * 2048)[i];
+    for (int i = threadIdx.x; i < kmain / 8; i += blockDim.x)
+      reinterpret_cast<uint4*>(w2f + (size_t)o * ld)[i] = reinterpret_cast<const uint4*>(w2 + (size_t)o * kmain)[i];
   if (threadIdx.x < 64) {
     const int k = threadIdx.x;
     auto hi16 = [](float v) { return (uint16_t)(pack_h2<F16>(v, 0.f) & 0xffffu); };
@@ -560,44 +734,32 @@ b1_fused_pack_kernel(const h16* __restrict__ w2, const float* __restrict__ sc_w3
       const uint16_t b1 = hi16(b - back(b0));
       v = k == 9 ? b0 : (k == 10 ? b1 : hi16(b - back(b0) - back(b1)));
     }
-    w2f[(size_t)o * BF_W2_LD + 2048 + k] = v;
+    w2f[(size_t)o * ld + kmain + k] = v;
   }
 }
 
-int b1_fused_pack(const h16* w2, const float* sc_w3, const float* bias2, h16* w2f, int f16, cudaStream_t s) {
+// ch = 128 (SNGAN-32) or 64 (SNGAN-64)
+int b1_fused_pack(const h16* w2, const float* sc_w3, const float* bias2, h16* w2f, int ch, int f16, cudaStream_t s) {
   SDG_REQUIRE(sc_w3 && bias2 && w2f, SDG_E_INVALID, "b1_fused_pack: null pointer");
+  SDG_REQUIRE(ch == 128 || ch == 64, SDG_E_UNSUPPORTED, "b1_fused_pack: ch=%d", ch);
   SDG_REQUIRE(((uintptr_t)w2 % 16) == 0 && ((uintptr_t)w2f % 16) == 0, SDG_E_INVALID, "b1_fused_pack: misaligned pointer");
-  if (f16) { SDG_LAUNCH(b1_fused_pack_kernel<true>, 128, 256, 0, s, w2, sc_w3, bias2, w2f); }
-  else { SDG_LAUNCH(b1_fused_pack_kernel<false>, 128, 256, 0, s, w2, sc_w3, bias2, w2f); }
+  if (f16) { SDG_LAUNCH(b1_fused_pack_kernel<true>, ch, 256, 0, s, w2, sc_w3, bias2, w2f, ch); }
+  else { SDG_LAUNCH(b1_fused_pack_kernel<false>, ch, 256, 0, s, w2, sc_w3, bias2, w2f, ch); }
   return 0;
 }
 
-int b1_fused_w2_elems() { return 128 * BF_W2_LD; }
-int b1_fused_w2_ld() { return BF_W2_LD; }
+int b1_fused_w2_ld(int ch) { return 16 * ch + 64; }
+int b1_fused_w2_elems(int ch) { return ch * b1_fused_w2_ld(ch); }
 
-int b1_fused(const void* x, const h16* w1, const float* b1, const h16* w2f, h16* out_relu, h16* dbg_t, int64_t n, int f16,
-             cudaStream_t s) {
-  SDG_REQUIRE(x && w1 && b1 && w2f && out_relu, SDG_E_INVALID, "b1_fused: null pointer");
-  auto al16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
-  SDG_REQUIRE(((uintptr_t)x % 4) == 0 && al16(w1) && al16(w2f) && al16(out_relu) && al16(dbg_t), SDG_E_INVALID,
-              "b1_fused: misaligned pointer");
-  if (n == 0) return 0;
-  CUtensorMap map_w2;
-  { int rc = tc_encode_2d(&map_w2, w2f, f16, BF_W2_LD, 128, 64, 64); if (rc) return rc; }
-  BfParams p;
-  p.x = (const uint8_t*)x; p.w1 = w1; p.b1 = b1; p.out_relu = out_relu; p.dbg_t = dbg_t;
-  p.ovf = t_range_flag; p.n_images = n;
-  static const int ws_env = getenv("SDG_B1_WSTAGES") ? atoi(getenv("SDG_B1_WSTAGES")) : BF_W_STAGES;
-  p.w_stages = ws_env >= 2 && ws_env <= BF_W_STAGES ? ws_env : BF_W_STAGES;
-  p.dbg = 0;
-#ifdef SDG_TIMING_EXPERIMENTS
-  static const int dbg_env = getenv("SDG_B1_DEBUG") ? atoi(getenv("SDG_B1_DEBUG")) : 0;
-  p.dbg = dbg_env;
-#endif
+template <bool F16, int CH>
+static int b1_fused_launch(const CUtensorMap& map_w2, BfParams& p, cudaStream_t s) {
+  using B = Bf<CH>;
+  static const int ws_env = getenv("SDG_B1_WSTAGES") ? atoi(getenv("SDG_B1_WSTAGES")) : B::W_STAGES;
+  p.w_stages = ws_env >= 2 && ws_env <= B::W_STAGES ? ws_env : B::W_STAGES;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(tc_num_sms() / 2 * 2));
   cfg.blockDim = dim3(BF_THREADS);
-  cfg.dynamicSmemBytes = kB1FusedSmem;
+  cfg.dynamicSmemBytes = B::SMEM;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -605,14 +767,36 @@ int b1_fused(const void* x, const h16* w1, const float* b1, const h16* w2f, h16*
   cfg.attrs = attr; cfg.numAttrs = 1;
   // the tile schedule is static (tile = cluster + l * clusters): every cluster of the grid must be resident at once, and a GPC
   // with an odd number of free SMs cannot host a CTA pair on its last one -- ask the driver how many pairs fit
-  long long clusters = tc_max_active_clusters(f16 ? (const void*)b1_fused_kernel<true> : (const void*)b1_fused_kernel<false>, &cfg);
+  long long clusters = tc_max_active_clusters((const void*)b1_fused_kernel<F16, CH>, &cfg);
   if (clusters < 1) clusters = 1;
-  if (n < clusters) clusters = n;
+  if (p.n_tiles < clusters) clusters = p.n_tiles;
   cfg.gridDim = dim3((unsigned)(2 * clusters));
-  if (f16) { SDG_CUDA(cudaLaunchKernelEx(&cfg, b1_fused_kernel<true>, map_w2, p)); }
-  else { SDG_CUDA(cudaLaunchKernelEx(&cfg, b1_fused_kernel<false>, map_w2, p)); }
+  SDG_CUDA(cudaLaunchKernelEx(&cfg, b1_fused_kernel<F16, CH>, map_w2, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
+}
+
+// ch = 128: x [n][32][32][3] -> out_relu [n][16][16][128]; ch = 64: x [n][64][64][3] -> out_relu [n][32][32][64]
+int b1_fused(const void* x, const h16* w1, const float* b1, const h16* w2f, h16* out_relu, h16* dbg_t, int64_t n, int ch, int f16,
+             cudaStream_t s) {
+  SDG_REQUIRE(x && w1 && b1 && w2f && out_relu, SDG_E_INVALID, "b1_fused: null pointer");
+  SDG_REQUIRE(ch == 128 || ch == 64, SDG_E_UNSUPPORTED, "b1_fused: ch=%d", ch);
+  auto al16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
+  SDG_REQUIRE(((uintptr_t)x % 4) == 0 && al16(w1) && al16(w2f) && al16(out_relu) && al16(dbg_t), SDG_E_INVALID,
+              "b1_fused: misaligned pointer");
+  if (n == 0) return 0;
+  CUtensorMap map_w2;
+  { int rc = tc_encode_2d(&map_w2, w2f, f16, b1_fused_w2_ld(ch), ch, 64, ch / 2); if (rc) return rc; }
+  BfParams p;
+  p.x = (const uint8_t*)x; p.w1 = w1; p.b1 = b1; p.out_relu = out_relu; p.dbg_t = dbg_t;
+  p.ovf = t_range_flag; p.n_tiles = ch == 64 ? 4 * n : n;
+  p.dbg = 0;
+#ifdef SDG_TIMING_EXPERIMENTS
+  static const int dbg_env = getenv("SDG_B1_DEBUG") ? atoi(getenv("SDG_B1_DEBUG")) : 0;
+  p.dbg = dbg_env;
+#endif
+  if (ch == 128) return f16 ? b1_fused_launch<true, 128>(map_w2, p, s) : b1_fused_launch<false, 128>(map_w2, p, s);
+  return f16 ? b1_fused_launch<true, 64>(map_w2, p, s) : b1_fused_launch<false, 64>(map_w2, p, s);
 }
 
 }  // namespace sdg

@@ -320,11 +320,13 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
       } else {
         SDG_CUDA(cudaMemcpyAsync(l2.bias_sum.p, l2.bias.p, sizeof(float) * l2.cout, cudaMemcpyDeviceToDevice, s));
       }
-      // ---- one-kernel block 1 of SNGAN-32: the same c2 weights with the shortcut / bias chunk appended ----
-      if (c->blocks[bi].kind == 0 && arch == SDG_ARCH_SNGAN32 && l2.pool4 && l2.cout == 128 && l2.cin == 128) {
-        { int rc = l2.w16f.ensure(sizeof(h16) * (size_t)b1_fused_w2_elems()); if (rc) return rc; }
-        { int rc = pack_pool4_h16(W[i2], sig + i2, l2.w16f.as<h16>(), l2.cout, l2.cin, f16, b1_fused_w2_ld(), s); if (rc) return rc; }
-        { int rc = b1_fused_pack(nullptr, c->convs[isc].w3.as<float>(), l2.bias_sum.as<float>(), l2.w16f.as<h16>(), f16, s);
+      // ---- one-kernel block 1 of SNGAN-32 / SNGAN-64: the same c2 weights with the shortcut / bias chunk appended ----
+      if (c->blocks[bi].kind == 0 && l2.pool4 && l2.cout == l2.cin && l1.cin == 3 &&
+          ((arch == SDG_ARCH_SNGAN32 && l2.cout == 128) || (arch == SDG_ARCH_SNGAN64 && l2.cout == 64))) {
+        const int ch = l2.cout;
+        { int rc = l2.w16f.ensure(sizeof(h16) * (size_t)b1_fused_w2_elems(ch)); if (rc) return rc; }
+        { int rc = pack_pool4_h16(W[i2], sig + i2, l2.w16f.as<h16>(), l2.cout, l2.cin, f16, b1_fused_w2_ld(ch), s); if (rc) return rc; }
+        { int rc = b1_fused_pack(nullptr, c->convs[isc].w3.as<float>(), l2.bias_sum.as<float>(), l2.w16f.as<h16>(), ch, f16, s);
           if (rc) return rc; }
       }
       // ---- super-pixel forms of the Cout = 64 layers (SNGAN-64 block1.c2 and block2.c1) ----
@@ -528,14 +530,17 @@ static int forward_sngan_h16(sdg_ctx* c, const void* x, int layout, int64_t nb, 
       a2.head_w = c->head_w.as<float>(); a2.head_b = c->head_b.as<float>(); a2.head_out = logits;
       fused_head_done = true;
     }
-    // SNGAN-32 block 1 as ONE kernel (conv_b1fused.cu): relu(c1(x)) stays in shared memory.  Needs the byte dataset, the 4x4
-    // stride-2 form of c2 and a consumer that only reads relu(h) (mimicry's in-place ReLU; the next block has a shortcut conv).
+    // Block 1 of SNGAN-32 / SNGAN-64 as ONE kernel (conv_b1fused.cu): relu(c1(x)) stays in shared memory.  Needs the byte
+    // dataset, the 4x4 stride-2 form of c2 and a consumer that only reads relu(h) (mimicry's in-place ReLU; the next block has
+    // a shortcut conv).  (SDG_FUSE_B1: 0 = never, 1 = both, 32 / 64 = that architecture only.)
     static const int fuse_b1_env = getenv("SDG_FUSE_B1") ? atoi(getenv("SDG_FUSE_B1")) : 1;
-    if (bl.kind == 0 && fuse_b1_env && S == 32 && c1.cout == 128 && c2.cout == 128 && c2.pool4 && !c2.superpix &&
-        c2.w16f.p && layout == SDG_LAYOUT_U8_NHWC && a2.out_relu && !a2.out_raw && !a2.out_f32 && !a2.head_out &&
+    const bool fuse_b1_on = fuse_b1_env == 1 || fuse_b1_env == S;
+    if (bl.kind == 0 && fuse_b1_on && ((S == 32 && c2.cout == 128) || (S == 64 && c2.cout == 64)) && c1.cout == c2.cout &&
+        c2.pool4 && c2.w16f.p && layout == SDG_LAYOUT_U8_NHWC && a2.out_relu && !a2.out_raw && !a2.out_f32 && !a2.head_out &&
         conv_tc_swap_active()) {
       if ((rc = prof_begin(c, s))) return rc;
-      if ((rc = b1_fused(x, c1.w16.as<h16>(), c1.bias.as<float>(), c2.w16f.as<h16>(), a2.out_relu, nullptr, nb, f16, s))) return rc;
+      if ((rc = b1_fused(x, c1.w16.as<h16>(), c1.bias.as<float>(), c2.w16f.as<h16>(), a2.out_relu, nullptr, nb, c2.cout, f16, s)))
+        return rc;
       // useful FLOPs of the launch: c2 in the 4x4 stride-2 form (16 taps per pooled pixel) + c1 (27 MACs per pixel and channel)
       if ((rc = prof_end(c, s, 2.0 * (double)nb * hw * hw * c2.cout * (16.0 * c2.cin * 0.25 + 27.0)))) return rc;
     } else if (bl.kind == 0) {
@@ -769,25 +774,36 @@ extern "C" int sdg_conv2d_sg2_h16(const void* in, const void* wb, const float* b
   return conv_tc(a, precision == SDG_PREC_FP16, (cudaStream_t)stream);
 }
 
-extern "C" int sdg_sngan32_block1_fused_h16(const void* x, const void* w1, const float* b1, const void* w2, const float* bias2,
-                                            const float* sc_w3, void* out_relu, void* dbg_t, int64_t n, int precision,
-                                            void* stream) {
-  SDG_REQUIRE(precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID, "sdg_sngan32_block1_fused_h16: precision=%d",
-              precision);
-  SDG_REQUIRE(n >= 0, SDG_E_INVALID, "sdg_sngan32_block1_fused_h16: n=%lld", (long long)n);
+static int block1_fused_entry(const char* who, int ch, const void* x, const void* w1, const float* b1, const void* w2,
+                              const float* bias2, const float* sc_w3, void* out_relu, void* dbg_t, int64_t n, int precision,
+                              void* stream) {
+  SDG_REQUIRE(precision == SDG_PREC_BF16 || precision == SDG_PREC_FP16, SDG_E_INVALID, "%s: precision=%d", who, precision);
+  SDG_REQUIRE(n >= 0, SDG_E_INVALID, "%s: n=%lld", who, (long long)n);
   int dev = 0;
   SDG_CUDA(cudaGetDevice(&dev));
   { int rc = conv_tc_init(dev); if (rc) return rc; }
-  SDG_REQUIRE(w2 && bias2 && sc_w3, SDG_E_INVALID, "sdg_sngan32_block1_fused_h16: null pointer");
+  SDG_REQUIRE(w2 && bias2 && sc_w3, SDG_E_INVALID, "%s: null pointer", who);
   if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int f16 = precision == SDG_PREC_FP16;
   h16* w2f = nullptr;
-  SDG_CUDA(cudaMallocAsync((void**)&w2f, sizeof(h16) * (size_t)b1_fused_w2_elems(), st));
-  int rc = b1_fused_pack((const h16*)w2, sc_w3, bias2, w2f, f16, st);
-  if (!rc) rc = b1_fused(x, (const h16*)w1, b1, w2f, (h16*)out_relu, (h16*)dbg_t, n, f16, st);
+  SDG_CUDA(cudaMallocAsync((void**)&w2f, sizeof(h16) * (size_t)b1_fused_w2_elems(ch), st));
+  int rc = b1_fused_pack((const h16*)w2, sc_w3, bias2, w2f, ch, f16, st);
+  if (!rc) rc = b1_fused(x, (const h16*)w1, b1, w2f, (h16*)out_relu, (h16*)dbg_t, n, ch, f16, st);
   cudaFreeAsync(w2f, st);
   return rc;
+}
+
+extern "C" int sdg_sngan32_block1_fused_h16(const void* x, const void* w1, const float* b1, const void* w2, const float* bias2,
+                                            const float* sc_w3, void* out_relu, void* dbg_t, int64_t n, int precision,
+                                            void* stream) {
+  return block1_fused_entry("sdg_sngan32_block1_fused_h16", 128, x, w1, b1, w2, bias2, sc_w3, out_relu, dbg_t, n, precision, stream);
+}
+
+extern "C" int sdg_sngan64_block1_fused_h16(const void* x, const void* w1, const float* b1, const void* w2, const float* bias2,
+                                            const float* sc_w3, void* out_relu, void* dbg_t, int64_t n, int precision,
+                                            void* stream) {
+  return block1_fused_entry("sdg_sngan64_block1_fused_h16", 64, x, w1, b1, w2, bias2, sc_w3, out_relu, dbg_t, n, precision, stream);
 }
 
 extern "C" int sdg_blur_h16(const void* in, void* out, int64_t n, int H, int W, int C, int pad, int stride, int precision,

@@ -185,16 +185,16 @@ int first_conv_init();
 // superpix = 1 (Cout = 64): wb is the [128][64] super-pixel weight tile of pack_first_superpix_h16
 int first_conv(const void* x, int layout, const h16* wb, const float* bias, h16* out, int64_t n, int S, int Cout,
                int f16, cudaStream_t s, int superpix = 0);
-// conv_b1fused.cu: SNGAN-32 block 1 (c1 -> relu -> c2 in the 4x4 stride-2 form + image shortcut -> relu) in ONE kernel,
-// relu(c1(x)) kept in shared memory.  x uint8 [n,32,32,3]; w1 [128][64] (first_conv's operand); w2f [128][b1_fused_w2_ld()]:
-// pack_pool4_h16's 2048 columns followed by the shortcut chunk b1_fused_pack writes (fp32 W_sc / sigma [128][3] and
-// bias2 = c2 + shortcut bias as 16-bit hi / lo columns; w2 = null when the main columns were packed in place);
-// out_relu [n,16,16,128]; dbg_t [n,32,32,128] or null
+// conv_b1fused.cu: block 1 of SNGAN-32 (ch = 128) / SNGAN-64 (ch = 64) -- c1 -> relu -> c2 in the 4x4 stride-2 form + image
+// shortcut -> relu -- in ONE kernel, relu(c1(x)) kept in shared memory.  x uint8 [n,S,S,3], S = 32 | 64; w1 [ch][64]
+// (first_conv's operand); w2f [ch][b1_fused_w2_ld(ch)]: pack_pool4_h16's 16 ch columns followed by the shortcut chunk
+// b1_fused_pack writes (fp32 W_sc / sigma [ch][3] and bias2 = c2 + shortcut bias as 16-bit hi / lo columns; w2 = null when
+// the main columns were packed in place); out_relu [n,S/2,S/2,ch]; dbg_t [n,S,S,ch] or null
 int b1_fused_init();
-int b1_fused_w2_elems();
-int b1_fused_w2_ld();
-int b1_fused_pack(const h16* w2, const float* sc_w3, const float* bias2, h16* w2f, int f16, cudaStream_t s);
-int b1_fused(const void* x, const h16* w1, const float* b1, const h16* w2f, h16* out_relu, h16* dbg_t, int64_t n, int f16,
+int b1_fused_w2_elems(int ch);
+int b1_fused_w2_ld(int ch);
+int b1_fused_pack(const h16* w2, const float* sc_w3, const float* bias2, h16* w2f, int ch, int f16, cudaStream_t s);
+int b1_fused(const void* x, const h16* w1, const float* b1, const h16* w2f, h16* out_relu, h16* dbg_t, int64_t n, int ch, int f16,
              cudaStream_t s);
 // first-conv weights in super-pixel form: wb[(par*Cout + o)*64 + (ky*4 + j)*3 + c] = W[o][c][ky][j - par] / sigma for
 // 0 <= j - par <= 2, zero elsewhere (columns 36, 37 receive the bias in the kernel)

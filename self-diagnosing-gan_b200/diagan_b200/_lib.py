@@ -44,6 +44,7 @@ SIGNATURES = {
     "sdg_set_conv_pair": (_i, [_i]),
     "sdg_first_conv_h16": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
     "sdg_sngan32_block1_fused_h16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "sdg_sngan64_block1_fused_h16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "sdg_resize_center_crop_u8": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp]),
     "sdg_stats_update": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "sdg_window_moments_f32": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
