@@ -27,30 +27,33 @@ def main():
     ap.add_argument("--first", type=int, default=0, help="time the first conv (from uint8 bytes) instead")
     ap.add_argument("--b1fused", type=int, default=0, help="time SNGAN-32 block 1 as one launch (conv_b1fused.cu) and as the two "
                     "launches it replaces")
+    ap.add_argument("--fused-only", type=int, default=0)
     a = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda", 0)
     if a.b1fused:
-        img = torch.randint(0, 256, (a.n, 32, 32, 3), dtype=torch.uint8, device=dev)
-        w1 = torch.zeros(128, 64, device=dev).half()
-        w1[:, :27] = (torch.randn(128, 27, device=dev) / 5).half()
-        w2 = (torch.randn(128, 2048, device=dev) / 2048 ** 0.5).half()
-        b1, b2 = torch.zeros(128, device=dev), torch.zeros(128, device=dev)
-        w3 = torch.randn(128, 3, device=dev)
-        T = torch.empty(a.n, 32, 32, 128, device=dev, dtype=torch.float16)
-        out = torch.empty(a.n, 16, 16, 128, device=dev, dtype=torch.float16)
+        S, ch = (64, 64) if a.b1fused == 64 else (32, 128)      # --b1fused 64: SNGAN-64 (per image quadrant); else SNGAN-32
+        img = torch.randint(0, 256, (a.n, S, S, 3), dtype=torch.uint8, device=dev)
+        w1 = torch.zeros(ch, 64, device=dev).half()
+        w1[:, :27] = (torch.randn(ch, 27, device=dev) / 5).half()
+        w2 = (torch.randn(ch, 16 * ch, device=dev) / (16 * ch) ** 0.5).half()
+        b1, b2 = torch.zeros(ch, device=dev), torch.zeros(ch, device=dev)
+        w3 = torch.randn(ch, 3, device=dev)
+        T = torch.empty(a.n, S, S, ch, device=dev, dtype=torch.float16)
+        out = torch.empty(a.n, S // 2, S // 2, ch, device=dev, dtype=torch.float16)
         st = stream_ptr(dev)
+        fn = lib.sdg_sngan64_block1_fused_h16 if ch == 64 else lib.sdg_sngan32_block1_fused_h16
 
         def fused():
-            check(lib.sdg_sngan32_block1_fused_h16(ptr(img), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(out), None, a.n,
-                                                   _lib.PREC_FP16, st), "fused")
+            check(fn(ptr(img), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(out), None, a.n, _lib.PREC_FP16, st), "fused")
 
         def two():
-            check(lib.sdg_first_conv_h16(ptr(img), _lib.LAYOUT_U8_NHWC, ptr(w1), ptr(b1), ptr(T), a.n, 32, 128, _lib.PREC_FP16, st), "c1")
-            check(lib.sdg_conv2d_h16(ptr(T), ptr(w2), ptr(b2), a.n, 32, 32, 128, 128, 3, None, 0, 2, None, 0, ptr(img),
+            check(lib.sdg_first_conv_h16(ptr(img), _lib.LAYOUT_U8_NHWC, ptr(w1), ptr(b1), ptr(T), a.n, S, ch, _lib.PREC_FP16, st), "c1")
+            check(lib.sdg_conv2d_h16(ptr(T), ptr(w2), ptr(b2), a.n, S, S, ch, ch, 3, None, 0, 2, None, 0, ptr(img),
                                      _lib.LAYOUT_U8_NHWC, ptr(w3), ptr(out), None, None, _lib.PREC_FP16, st), "c2")
-        flops = 2.0 * a.n * 1024 * 128 * (16 * 128 * 0.25 + 27)
-        for name, run in (("two launches", two), ("fused", fused), ("two launches", two), ("fused", fused)):
+        flops = 2.0 * a.n * S * S * ch * (16 * ch * 0.25 + 27)
+        runs = (("fused", fused), ("fused", fused)) if a.fused_only else (("two launches", two), ("fused", fused), ("two launches", two), ("fused", fused))
+        for name, run in runs:
             for _ in range(3):
                 run()
             torch.cuda.synchronize()
