@@ -75,10 +75,13 @@ struct Bf {
   static constexpr bool ALT = QUAD;                     // the two T-warp sets take alternate batches (below) instead of halves of each
   static constexpr int NA1 = ALT ? 4 : 2;               // im2col buffers = c1 accumulators: two per set | double-buffered
   static constexpr int OFF_W1 = OFF_A1 + NA1 * BF_A1_BYTES;
+  static constexpr bool EPI_PATCH = QUAD;               // the patch / shortcut operand of a tile is built by the EPILOGUE warps, two
+                                                        // tiles ahead, instead of by the T warps (which pace the CH = 64 kernel)
+  static constexpr int NB = EPI_PATCH ? 2 : 1;          // ... into double-buffered landing rows, patch and shortcut operand
   static constexpr int OFF_X = OFF_W1 + W1_BYTES;
-  static constexpr int OFF_P = OFF_X + X_BYTES;
-  static constexpr int OFF_SC = OFF_P + P_BYTES;
-  static constexpr int OFF_LUT = OFF_SC + BF_SC_BYTES;  // CH = 64: normalised value of every byte, fp32 [256] then 16-bit [256]
+  static constexpr int OFF_P = OFF_X + NB * X_BYTES;
+  static constexpr int OFF_SC = OFF_P + NB * P_BYTES;
+  static constexpr int OFF_LUT = OFF_SC + NB * BF_SC_BYTES;  // CH = 64: normalised value of every byte, fp32 [256] then 16-bit [256]
   static constexpr int SMEM = 1024 + OFF_LUT + (QUAD ? 1536 : 0);
   static constexpr int W2_LD = 16 * CH + 64;            // packed c2 weights: 16 taps x CH channels + one 64-column chunk for the shortcut
   static constexpr int SC_COL = 16 * CH;                // ... which starts at this column
@@ -155,7 +158,8 @@ template <bool F16, int CH>
 __global__ void __launch_bounds__(BF_THREADS, 1)
 b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
   using B = Bf<CH>;
-  constexpr bool QUAD = B::QUAD, ALT = B::ALT;
+  constexpr bool QUAD = B::QUAD, ALT = B::ALT, EPI_PATCH = B::EPI_PATCH;
+  static_assert(!EPI_PATCH || (QUAD && ALT), "the epilogue-built patch is written for the CH = 64 schedule");
   constexpr int NH = B::NH, G = B::G, IMG = B::IMG;
   constexpr int BF_OFF_T = B::OFF_T, BF_OFF_A1 = B::OFF_A1, BF_OFF_W1 = B::OFF_W1, BF_OFF_X = B::OFF_X, BF_OFF_P = B::OFF_P,
                 BF_OFF_SC = B::OFF_SC, BF_T_BYTES = B::T_BYTES, BF_P_BYTES = B::P_BYTES;
@@ -172,8 +176,10 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
   __shared__ __align__(8) uint64_t bar_t_free[2];
   __shared__ __align__(8) uint64_t bar_acc_full[2];
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
-  __shared__ __align__(8) uint64_t bar_sc_full;         // shortcut operand of the next tile built (both CTAs) -> issuer
-  __shared__ __align__(8) uint64_t bar_sc_free;         // its MMA has retired -> the T warps may overwrite it
+  __shared__ __align__(8) uint64_t bar_sc_full[2];      // shortcut operand of a tile built (both CTAs) -> issuer   ([1]: EPI_PATCH only)
+  __shared__ __align__(8) uint64_t bar_sc_free[2];      // its MMA has retired -> the buffer may be overwritten
+  __shared__ __align__(8) uint64_t bar_patch_ready[2];  // EPI_PATCH: patch buffer (tile & 1) written (this CTA's epilogue warps) -> T warps
+  __shared__ __align__(8) uint64_t bar_patch_free[2];   // ... and every T warp of this CTA has gathered its last batch of that tile from it
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -191,7 +197,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
   // ---- one-time setup ----
   for (int i = threadIdx.x; i < BF_T_BYTES / 16; i += BF_THREADS)
     reinterpret_cast<uint4*>(smem_gen + BF_OFF_T)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = threadIdx.x; i < BF_P_BYTES / 16; i += BF_THREADS)
+  for (int i = threadIdx.x; i < B::NB * BF_P_BYTES / 16; i += BF_THREADS)
     reinterpret_cast<uint4*>(smem_gen + BF_OFF_P)[i] = make_uint4(0u, 0u, 0u, 0u);
   // c1 weights of this CTA's 64 channels, no-swizzle [k8][row]; the bias rides in K columns 27 (hi) and 28 (lo)
   for (int i = threadIdx.x; i < NH * 4; i += BF_THREADS) {
@@ -232,8 +238,12 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       mbar_init(smem_u32(&bar_acc_full[i]), 1);
       mbar_init(smem_u32(&bar_acc_empty[i]), 8);        // 4 epilogue warps x 2 CTAs
     }
-    mbar_init(smem_u32(&bar_sc_full), 16);
-    mbar_init(smem_u32(&bar_sc_free), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_sc_full[i]), EPI_PATCH ? 8 : 16);   // the warps that build it (4 epilogue | 8 T) x 2 CTAs
+      mbar_init(smem_u32(&bar_sc_free[i]), 1);
+      mbar_init(smem_u32(&bar_patch_ready[i]), 4);
+      mbar_init(smem_u32(&bar_patch_free[i]), 8);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_slot), 512);
@@ -307,7 +317,9 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
         {
           // the tile's first MMA initialises the accumulator with bias + W_sc . avg_pool2d(x): one K = 16 step whose operands
           // carry the fp32 terms as 16-bit hi / lo pairs (columns: ph.wh, pl.wh, ph.wl, 1.bias_hi, 1.bias_lo, 1.bias_lo2)
-          mbar_wait(smem_u32(&bar_sc_full), (uint32_t)(l & 1));
+          const int sb = EPI_PATCH ? (int)(l & 1) : 0;                      // shortcut buffer of the tile and the parity of its use
+          const uint32_t sc_par = EPI_PATCH ? (uint32_t)((l >> 1) & 1) : (uint32_t)(l & 1);
+          mbar_wait(smem_u32(&bar_sc_full[sb]), sc_par);
           mbar_wait(smem_u32(&bar_acc_empty[acc]), (uint32_t)(((l >> 1) & 1) ^ 1));
           if (!ready) mbar_wait(wfull0 + wo, wphase);
           tc_fence_after();
@@ -315,9 +327,9 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
           wo += 8u;
           if (wo == w_wrap) { wo = 0; wphase ^= 1u; }
           ready = mbar_try_wait(wfull0 + wo, wphase);
-          umma_pair(d_tmem, sc_desc, w_desc0 + (uint64_t)(cur * (BF_W_BYTES / 16 / 8)), idesc, 0u);
+          umma_pair(d_tmem, sc_desc + (uint64_t)(sb * (BF_SC_BYTES >> 4)), w_desc0 + (uint64_t)(cur * (BF_W_BYTES / 16 / 8)), idesc, 0u);
           umma_commit_pair(wempty0 + cur, 3);
-          umma_commit_pair(smem_u32(&bar_sc_free), 3);
+          umma_commit_pair(smem_u32(&bar_sc_free[sb]), 3);
         }
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
@@ -465,7 +477,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
           *reinterpret_cast<uint2*>(smem_gen + BF_OFF_P + (row + 1) * BF_P_ROWB + (j + (s ? 0 : 1)) * 8) = make_uint2(lo, hi);
         }
       }
-      mbar_wait(smem_u32(&bar_sc_free), (uint32_t)((L & 1) ^ 1));     // the previous tile's shortcut MMA has read the buffer
+      mbar_wait(smem_u32(&bar_sc_free[0]), (uint32_t)((L & 1) ^ 1));  // the previous tile's shortcut MMA has read the buffer
       {
         // the 2 x 2 input pixels under pooled output pixel (tt >> 3, 8 s + (tt & 7)) of the tile
         const uint8_t* b = QUAD ? raw + (2 + 2 * (tt >> 3)) * BF_X_ROWB + 3 * (32 * qx + 2 * (8 * s + (tt & 7))) - goff
@@ -488,11 +500,11 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_sc_full), 0));
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_sc_full[0]), 0));
     };
     // gather the K columns of batch pixel tt of (unit uu, batch b) of the tile in the patch into A1[gb] -- this set's 16 columns,
     // or (ALT) all 32: K column k = (ky*3 + kx)*3 + c for k < 27; 27, 28 = 1.0 (bias hi / lo); 29..31 = 0
-    auto build_a1 = [&](int uu, int b, int gb) {
+    auto build_a1 = [&](int uu, int b, int gb, int pb = 0) {
       const int pr = 1 - uu;
       int R, C, pc;
       const bool valid = bf_pixel<QUAD>(s, pr, b, tt, R, C, pc);
@@ -500,7 +512,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
         const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;       // pixel of the tile: rows -1 .. 32, columns 16 s - 1 .. 16 s + 16
         // pixel (y + ky - 1, x - 1) of tap row ky: CH = 128: patch row y + ky, patch column x - 1 - (15 s - 1) = x - 15 s;
         // CH = 64: patch row y + ky + 1, patch column x - 1 - (16 s - 2) = x - 16 s + 1
-        const uint2* row0 = QUAD ? reinterpret_cast<const uint2*>(smem_gen + BF_OFF_P + (y + 1) * BF_P_ROWB + (x - 16 * s + 1) * 8)
+        const uint2* row0 = QUAD ? reinterpret_cast<const uint2*>(smem_gen + BF_OFF_P + pb * BF_P_BYTES + (y + 1) * BF_P_ROWB + (x - 16 * s + 1) * 8)
                                  : reinterpret_cast<const uint2*>(smem_gen + BF_OFF_P + y * BF_P_ROWB + (x - 15 * s) * 8);
         const uint2* row1 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(row0) + BF_P_ROWB);
         const uint2* row2 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(row0) + 2 * BF_P_ROWB);
@@ -587,7 +599,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       named_bar_sync(1, BF_T_THREADS);                  // patch complete, landing buffer idle
       prefetch_x(l + 1);
     };
-    if (my_tiles > 0) {
+    if (my_tiles > 0 && !EPI_PATCH) {
       prefetch_x(0);
       switch_patch(0);
     }
@@ -601,8 +613,16 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       auto build = [&](int g) {
         const int l = g / 6;
         const int r = g - 6 * l;
-        if (r == set && l > 0) switch_patch(l);         // this set's first batch of tile l (both sets meet here)
-        build_a1(r / 3, r % 3, (g & 1) * 2 + ((g >> 1) & 1));
+        if (EPI_PATCH) {
+          // this set's first batch of tile l: its patch (built by the epilogue warps, two tiles ahead) is complete; after its last
+          // one (r = 4 + set) this warp is done with the buffer
+          if (r == set) mbar_wait(smem_u32(&bar_patch_ready[l & 1]), (uint32_t)((l >> 1) & 1));
+          build_a1(r / 3, r % 3, (g & 1) * 2 + ((g >> 1) & 1), l & 1);
+          if (r == 4 + set && lane == 0) mbar_arrive(smem_u32(&bar_patch_free[l & 1]));
+        } else {
+          if (r == set && l > 0) switch_patch(l);       // this set's first batch of tile l (both sets meet here)
+          build_a1(r / 3, r % 3, (g & 1) * 2 + ((g >> 1) & 1));
+        }
       };
       if (set < g_total) build(set);
       long long n = 0;
@@ -654,7 +674,88 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
     const int q = warp & 3;
     const int g4 = lane >> 2, i4 = lane & 3;
     uint32_t vmaxw = 0;
-    for (long long l = 0; l < my_tiles; ++l) {
+    // ---- EPI_PATCH (CH = 64): these warps also stage the inputs of the T path, two tiles ahead of their own epilogue ----
+    // raw rows of tile L -> landing buffer L & 1 (cp.async); then, one iteration later, -> (a) the normalised 16-bit patch L & 1:
+    // patch pixel (ry, cx) = quadrant pixel (ry - 2, 16 s - 2 + cx) as (c0, c1, c2, 0), zeros outside the IMAGE; (b) the shortcut
+    // operand L & 1: row m = avg_pool2d(normalised x) at output pixel (m >> 3, 8 s + (m & 7)) as hi / lo 16-bit pairs (K = 16: pooled
+    // pixel hi x 3, lo x 3, hi x 3 again, 1, 1, 1 against W_sc hi, hi, lo and the bias in three pieces; see b1_fused_pack_kernel)
+    const int e128 = q * 32 + lane;
+    auto e_tile_of = [&](long long L, long long& n, int& qy, int& qx, int& goff) {
+      const long long t = cluster_id + L * n_clusters;
+      n = t >> 2; qy = (int)(t & 3) >> 1; qx = (int)(t & 1);
+      const int b0 = (32 * qx + 16 * s - 2) * 3;
+      goff = b0 < 0 ? 0 : (b0 & ~3);
+    };
+    auto e_prefetch = [&](long long L) {
+      if (L < my_tiles) {
+        long long n; int qy, qx, goff;
+        e_tile_of(L, n, qy, qx, goff);
+        const uint32_t dst = smem_base + BF_OFF_X + (uint32_t)(L & 1) * B::X_BYTES;
+        const uint8_t* src = p.x + n * (64 * 64 * 3) + goff;
+        for (int w = e128; w < 36 * 16; w += 128) {
+          const int row = w >> 4, wi = w & 15;
+          const int Y = 32 * qy - 2 + row;
+          if (Y >= 0 && Y < 64 && goff + wi * 4 < 192) cp_async_4(dst + row * BF_X_ROWB + wi * 4, src + Y * 192 + wi * 4);
+        }
+      }
+      cp_async_commit();
+    };
+    auto e_produce = [&](long long L) {
+      if (L >= my_tiles) return;
+      const int pb = (int)(L & 1);
+      const uint32_t par = (uint32_t)(((L >> 1) & 1) ^ 1);
+      const float* lut32 = reinterpret_cast<const float*>(smem_gen + B::OFF_LUT);
+      const uint16_t* lut16 = reinterpret_cast<const uint16_t*>(smem_gen + B::OFF_LUT + 1024);
+      const uint8_t* raw = smem_gen + BF_OFF_X + pb * B::X_BYTES;
+      uint8_t* patch = smem_gen + BF_OFF_P + pb * BF_P_BYTES;
+      long long n_; int qy, qx, goff;
+      e_tile_of(L, n_, qy, qx, goff);
+      mbar_wait(smem_u32(&bar_patch_free[pb]), par);    // the T warps have gathered tile L - 2 from this buffer
+#pragma unroll 2
+      for (int i = e128; i < 36 * 20; i += 128) {
+        const int ry = i / 20, cx = i - ry * 20;
+        const int Y = 32 * qy - 2 + ry, X = 32 * qx + 16 * s - 2 + cx;
+        uint2 v = make_uint2(0u, 0u);
+        if (Y >= 0 && Y < 64 && X >= 0 && X < 64) {
+          const uint8_t* b = raw + ry * BF_X_ROWB + 3 * X - goff;
+          v = make_uint2((uint32_t)lut16[b[0]] | ((uint32_t)lut16[b[1]] << 16), (uint32_t)lut16[b[2]]);
+        }
+        *reinterpret_cast<uint2*>(patch + ry * BF_P_ROWB + cx * 8) = v;
+      }
+      mbar_wait(smem_u32(&bar_sc_free[pb]), par);       // the shortcut MMA of tile L - 2 has read this buffer
+      {
+        // the 2 x 2 input pixels under pooled output pixel (e128 >> 3, 8 s + (e128 & 7)) of the tile
+        constexpr uint32_t kOne = F16 ? 0x3C00u : 0x3F80u;
+        const uint8_t* b = raw + (2 + 2 * (e128 >> 3)) * BF_X_ROWB + 3 * (32 * qx + 2 * (8 * s + (e128 & 7))) - goff;
+        uint32_t ph[3], pl[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float px = (lut32[b[c]] + lut32[b[3 + c]] + lut32[b[BF_X_ROWB + c]] + lut32[b[BF_X_ROWB + 3 + c]]) * 0.25f;
+          ph[c] = pack_h2<F16>(px, 0.f) & 0xffffu;
+          pl[c] = pack_h2<F16>(px - unpack_h2<F16>(ph[c]).x, 0.f) & 0xffffu;
+        }
+        uint8_t* sc = smem_gen + BF_OFF_SC + pb * BF_SC_BYTES + e128 * 16;
+        *reinterpret_cast<uint4*>(sc) = make_uint4(ph[0] | (ph[1] << 16), ph[2] | (pl[0] << 16), pl[1] | (pl[2] << 16), ph[0] | (ph[1] << 16));
+        *reinterpret_cast<uint4*>(sc + 2048) = make_uint4(ph[2] | (kOne << 16), kOne | (kOne << 16), 0u, 0u);
+      }
+      fence_proxy_async_smem();                         // the shortcut operand is read by the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&bar_patch_ready[pb]));
+        mbar_arrive_cluster(mapa_u32(smem_u32(&bar_sc_full[pb]), 0));
+      }
+    };
+    if (EPI_PATCH) e_prefetch(0);
+    for (long long l = EPI_PATCH ? -2 : 0; l < my_tiles; ++l) {
+      if (EPI_PATCH) {
+        // rows of tile l + 2 have landed (every thread's, after the barrier); the barrier also says that everybody is done reading
+        // the other landing buffer (tile l + 1, converted in the previous iteration), which the next prefetch overwrites
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        named_bar_sync(2, 128);
+        e_prefetch(l + 3);
+        e_produce(l + 2);
+        if (l < 0) continue;
+      }
       const long long t = cluster_id + l * n_clusters;
       const long long n = QUAD ? t >> 2 : t;
       const int qy = QUAD ? (int)(t & 3) >> 1 : 0, qx = QUAD ? (int)(t & 1) : 0;
