@@ -38,6 +38,7 @@
 // path packs two pooled pixels into one 128-channel GEMM pixel and spends a third of its MACs on zeros); a 64-channel tap is
 // one K chunk, and a weight stage holds TWO taps (the same 8 KB per CTA and 256 MMA cycles per barrier as CH = 128).
 #include <cstdlib>
+#include <type_traits>
 
 #include "tc_ptx.cuh"
 
@@ -603,43 +604,155 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       prefetch_x(0);
       switch_patch(0);
     }
-    if (ALT) {
-      // The two sets take ALTERNATE batches (set = g & 1), each with two im2col buffers / c1 accumulators of its own: with a
-      // 64-channel c2 the tensor pipe needs a tile's T in ~2 000 cycles, and what paces a batch is the fixed latency of its
-      // barrier round trips and TMEM loads, not instruction issue -- two independent streams per scheduler hide twice as much.
-      // batch g = 6 l + 3 uu + b; buffer (g & 1) * 2 + ((g >> 1) & 1), used every fourth batch.
-      // (32-bit counters: this loop's own arithmetic is part of what paces the kernel; a cluster sees < 2^28 tiles)
-      const int g_total = (int)(6 * my_tiles);
-      auto build = [&](int g) {
-        const int l = g / 6;
-        const int r = g - 6 * l;
-        if (EPI_PATCH) {
-          // this set's first batch of tile l: its patch (built by the epilogue warps, two tiles ahead) is complete; after its last
-          // one (r = 4 + set) this warp is done with the buffer
-          if (r == set) mbar_wait(smem_u32(&bar_patch_ready[l & 1]), (uint32_t)((l >> 1) & 1));
-          build_a1(r / 3, r % 3, (g & 1) * 2 + ((g >> 1) & 1), l & 1);
-          if (r == 4 + set && lane == 0) mbar_arrive(smem_u32(&bar_patch_free[l & 1]));
-        } else {
-          if (r == set && l > 0) switch_patch(l);       // this set's first batch of tile l (both sets meet here)
-          build_a1(r / 3, r % 3, (g & 1) * 2 + ((g >> 1) & 1));
+    if constexpr (ALT) {
+      // CH = 64.  The two sets take ALTERNATE batches (set = g & 1), each with two im2col buffers / c1 accumulators of its own.
+      // With a 64-channel c2 the tensor pipe needs a tile's T in ~2 400 cycles and these eight warps pace the kernel: two in-order
+      // warps per scheduler issue one dependent instruction every ~5 cycles, so what counts is the NUMBER of instructions per
+      // batch -- and the SIZE of the loop: a version specialised per set and batch at compile time was 40 % slower (32 KB of
+      // T-warp code against a 6 KB L0 / 32 KB L1.5 instruction cache shared with the other roles).  So: ONE copy of the loop body,
+      // and everything that does not depend on the data hoisted out of it.  A thread's three pixels of a tile (batch
+      // r = set + 2 k: unit uu = r / 3, batch b = r % 3 of the unit) are described by one packed word each, computed once per
+      // launch: patch offset, T cell, "outside the image" bit per quadrant, and the roles of the batch in the barrier protocol;
+      // barrier addresses (incl. the leader's, mapa) are computed once, buffers and parities follow one counter
+      // (kc = 3 l + k = g >> 1).
+      constexpr uint32_t W_INVALID = 1u << 27, W_SKIP = 1u << 28, W_FIRST = 1u << 29, W_LAST = 1u << 30, W_UNIT1 = 1u << 31;
+      uint32_t pw[3];     // bits 0-9: patch offset / 8, 10-22: T cell offset / 16, 23-26: outside-the-image bit of quadrant 0..3
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int r = set + 2 * k, uu = r / 3, b = r - 3 * uu, pr = 1 - uu;
+        int R, C, pc;
+        const bool valid = bf_pixel<true>(s, pr, b, tt, R, C, pc);
+        const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;        // pixel of the quadrant: rows -1 .. 32, columns 16 s - 1 .. 16 s + 16
+        const int g_off = (y + 1) * BF_P_ROWB + (x - 16 * s + 1) * 8;     // tap row 0 / column 0 of the pixel in the patch
+        const int c_off = ((pr * 2 + pc) * G) * BF_K8 + R * BF_ROW + C * 16;     // its T cell (channel group 0)
+        uint32_t w = valid ? ((uint32_t)(g_off >> 3) | ((uint32_t)(c_off >> 4) << 10)) : W_INVALID;
+#pragma unroll
+        for (int quad = 0; quad < 4; ++quad) {
+          const int Y = 32 * (quad >> 1) + y, X = 32 * (quad & 1) + x;
+          if (Y < 0 || Y >= 64 || X < 0 || X >= 64) w |= 1u << (23 + quad);
         }
-      };
-      if (set < g_total) build(set);
-      long long n = 0;
-      int qy = 0, qx = 0, goff_ = 0;
-      for (int g = set; g < g_total; g += 2) {
-        if (g + 2 < g_total) build(g + 2);              // its buffer was read by batch g - 2, whose completion this thread has seen
-        const int l = g / 6;
-        const int r = g - 6 * l, uu = r / 3, b = r - 3 * uu;
-        const int cb = (g & 1) * 2 + ((g >> 1) & 1);
-        if (r == set) tile_of(l, n, qy, qx, goff_);     // this set's first batch of the tile
-        mbar_wait(smem_u32(&bar_c1_full[cb]), (uint32_t)((g >> 2) & 1));       // batch g is in TMEM
-        tc_fence_after();
-        // this set's first batch of the unit (r = 0, 4 | 1, 3): c2 is done with this half of T
-        if (r == set || r == 4 - set) mbar_wait(smem_u32(&bar_t_free[uu]), (uint32_t)((l & 1) ^ 1));
-        drain(n, qy, qx, uu, b, cb);
-        // ... and its last one (r = 2, 4 | 1, 5): the unit is complete once every T warp of both CTAs has said so
-        if ((r == 2 + 3 * set || r == 4 - 3 * set) && lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_t_ready[uu]), 0));
+        if (b == 2 && q >= 2) w |= W_SKIP;              // the third batch of a unit holds 50 pixels: lane quadrants 0, 1
+        if (r == set || r == 4 - set) w |= W_FIRST;     // this set's first batch of the unit (r = 0, 4 | 1, 3)
+        if (r == 2 + 3 * set || r == 4 - 3 * set) w |= W_LAST;   // ... and its last one (r = 2, 4 | 1, 5)
+        if (uu) w |= W_UNIT1;
+        pw[k] = w;
+      }
+      const uint32_t b_c1full = smem_u32(&bar_c1_full[0]), b_tfree = smem_u32(&bar_t_free[0]);
+      const uint32_t b_pready = smem_u32(&bar_patch_ready[0]), b_pfree = smem_u32(&bar_patch_free[0]);
+      const uint32_t r_a1full = mapa_u32(smem_u32(&bar_a1_full[0]), 0), r_c1empty = mapa_u32(smem_u32(&bar_c1_empty[0]), 0);
+      const uint32_t r_tready = mapa_u32(smem_u32(&bar_t_ready[0]), 0);
+      uint8_t* const a1_row = smem_gen + BF_OFF_A1 + tt * 16;
+      const uint32_t t_lane = tmem_base + 256u + ((uint32_t)(q * 32) << 16);
+
+      const int n_my = (int)my_tiles;                   // (a cluster sees < 2^28 tiles)
+      uint32_t kc = 0;                                  // this set's batch counter: buffer set * 2 + (kc & 1), parity (kc >> 1) & 1
+      long long t = cluster_id;
+      // (l, k) = (-1, 2) is the prologue: only the gather of tile 0's first batch
+      for (int l = -1; l < n_my; ++l) {
+        const int pb = l & 1;
+        const uint32_t tf_par = (uint32_t)((l & 1) ^ 1);
+#pragma unroll 1
+        for (int k = l < 0 ? 2 : 0; k < 3; ++k) {
+          // ---- the NEXT batch's operand first (its buffer was read by the batch before this one, whose completion this thread
+          // has seen), so that its MMA overlaps this batch's drain: gather the 32 K columns of the pixel from the patch ----
+          {
+            uint32_t wn = k == 0 ? pw[1] : (k == 1 ? pw[2] : pw[0]);
+            int pbn = pb;
+            if (k == 2) {                               // first batch of the next tile: its patch (epilogue warps, two tiles ahead)
+              pbn = pb ^ 1;
+              if (l + 1 < n_my) mbar_wait(b_pready + 8u * (uint32_t)pbn, (uint32_t)(((l + 1) >> 1) & 1));
+              else wn = 0xffffffffu;                    // no next tile: no gather, no arrive
+            }
+            if (wn != 0xffffffffu) {
+              if (!(wn & W_INVALID) && !(dbg & 1)) {
+                const uint8_t* base = smem_gen + BF_OFF_P + pbn * BF_P_BYTES + ((wn & 0x3ffu) << 3);
+                const uint2* row0 = reinterpret_cast<const uint2*>(base);
+                const uint2* row1 = reinterpret_cast<const uint2*>(base + BF_P_ROWB);
+                const uint2* row2 = reinterpret_cast<const uint2*>(base + 2 * BF_P_ROWB);
+                uint8_t* row = a1_row + (set * 2 + (int)((kc + (l < 0 ? 0u : 1u)) & 1u)) * BF_A1_BYTES;
+                const uint2 a0 = row0[0], a1 = row0[1], a2 = row0[2], b0 = row1[0], b1 = row1[1], b2 = row1[2];
+                const uint2 c0 = row2[0], c1 = row2[1], c2 = row2[2];
+                uint4 w;
+                w.x = a0.x;
+                w.y = __byte_perm(a0.y, a1.x, 0x5410);  // lo16(a0.y) | lo16(a1.x) << 16
+                w.z = __byte_perm(a1.x, a1.y, 0x5432);  // hi16(a1.x) | lo16(a1.y) << 16
+                w.w = a2.x;
+                *reinterpret_cast<uint4*>(row) = w;
+                w.x = __byte_perm(a2.y, b0.x, 0x5410);
+                w.y = __byte_perm(b0.x, b0.y, 0x5432);
+                w.z = b1.x;
+                w.w = __byte_perm(b1.y, b2.x, 0x5410);
+                *reinterpret_cast<uint4*>(row + 2048) = w;
+                w.x = __byte_perm(b2.x, b2.y, 0x5432);
+                w.y = c0.x;
+                w.z = __byte_perm(c0.y, c1.x, 0x5410);
+                w.w = __byte_perm(c1.x, c1.y, 0x5432);
+                *reinterpret_cast<uint4*>(row + 2 * 2048) = w;
+                w.x = c2.x;
+                w.y = (c2.y & 0xffffu) | (kOne << 16);   // k = 27, 28: 1.0 (bias hi / lo)
+                w.z = kOne;
+                w.w = 0u;
+                *reinterpret_cast<uint4*>(row + 3 * 2048) = w;
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive_cluster(r_a1full + 8u * (uint32_t)(set * 2 + (int)((kc + (l < 0 ? 0u : 1u)) & 1u)));
+                // after its last gather of a tile this warp is done with the patch buffer
+                if (k == 1) mbar_arrive(b_pfree + 8u * (uint32_t)pb);
+              }
+            }
+          }
+          if (l < 0) break;
+          // ---- this batch: TMEM accumulator cb -> relu / convert -> T cells (all 64 channels) ----
+          const uint32_t w = k == 0 ? pw[0] : (k == 1 ? pw[1] : pw[2]);
+          const int cb = set * 2 + (int)(kc & 1u);
+          mbar_wait(b_c1full + 8u * (uint32_t)cb, (kc >> 1) & 1u);          // the batch is in TMEM
+          tc_fence_after();
+          if (w & W_FIRST) mbar_wait(b_tfree + ((w & W_UNIT1) ? 8u : 0u), tf_par);   // c2 is done with this half of T
+          if (!(w & W_SKIP) && !(dbg & 2)) {
+            uint32_t r[64];
+            tmem_ld32(t_lane + (uint32_t)(cb * CH), r);
+            tmem_ld32(t_lane + (uint32_t)(cb * CH) + 32u, r + 32);
+            tmem_ld_wait();
+            if (!(w & W_INVALID)) {
+              const bool in_img = !((w >> (23 + (int)(t & 3))) & 1u);       // a cell outside the image is conv padding = zero
+              uint8_t* cell = smem_gen + BF_OFF_T + (((w >> 10) & 0x1fffu) << 4);
+#pragma unroll
+              for (int gq = 0; gq < 8; ++gq) {
+                uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                if (in_img) {
+                  pk.x = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]));
+                  pk.y = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
+                  pk.z = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+                  pk.w = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
+                }
+                if (F16) vmaxw = __vmaxu2(__vmaxu2(vmaxw, pk.x), __vmaxu2(__vmaxu2(pk.y, pk.z), pk.w));
+                *reinterpret_cast<uint4*>(cell + gq * BF_K8) = pk;
+              }
+              if (p.dbg_t && in_img) {                  // tests only: the same 16-bit values to global memory
+                const int rr = set + 2 * k, uu = rr / 3;
+                int R, C, pc;
+                bf_pixel<true>(s, 1 - uu, rr - 3 * uu, tt, R, C, pc);
+                const int Y = 32 * ((int)(t & 3) >> 1) + 2 * R - uu, X = 32 * (int)(t & 1) + 16 * s - 1 + 2 * C + pc;
+#pragma unroll 1
+                for (int gq = 0; gq < 8; ++gq)
+                  *reinterpret_cast<uint4*>(p.dbg_t + ((((t >> 2) * IMG + Y) * IMG + X) * CH + gq * 8)) =
+                      *reinterpret_cast<const uint4*>(cell + gq * BF_K8);
+              }
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async_smem();                     // T cells -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cluster(r_c1empty + 8u * (uint32_t)cb);
+            // the unit is complete once every T warp of both CTAs has said so
+            if (w & W_LAST) mbar_arrive_cluster(r_tready + ((w & W_UNIT1) ? 8u : 0u));
+          }
+          ++kc;
+        }
+        if (l >= 0) t += n_clusters;
       }
     } else {
       if (my_tiles > 0) build_a1(0, 0, 0);
