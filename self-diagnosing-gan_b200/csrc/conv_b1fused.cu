@@ -55,6 +55,11 @@ constexpr int BF_A1_BYTES = 4 * 128 * 16;               // 8192: [k8 0..3][128 p
 constexpr int BF_X_ROWB = 64;                           // raw image rows: the bytes of the strip's columns (CH = 128: 56 at offset 4)
 constexpr int BF_P_ROWB = 160;                          // normalised 16-bit patch: up to 20 pixels x (c0, c1, c2, pad) per row
 constexpr int BF_SC_BYTES = 2 * 128 * 16;               // shortcut operand: [k8 0..1][128 output pixels] x 16 B
+// CH = 64: the patch is split into its even and odd COLUMNS (two planes of 36 rows x 10 pixels): the three taps of a row are then
+// at (plane pc, C), (plane 1 - pc, C + pc), (plane pc, C + 1) with consecutive lanes (C) 8 bytes apart, and with 96-byte rows
+// two rows of 8 pixels fill the 32 banks exactly
+constexpr int BF_PQ_ROWB = 96;
+constexpr int BF_PQ_PLANE = 36 * BF_PQ_ROWB;
 
 template <int CH>
 struct Bf {
@@ -70,7 +75,7 @@ struct Bf {
   static constexpr int X_ROWS = QUAD ? 36 : 32;         // landing buffer: image rows -2 .. 33 of the quadrant | the image's 32 rows
   static constexpr int X_BYTES = X_ROWS * BF_X_ROWB;
   static constexpr int P_ROWS = QUAD ? 36 : 34;         // patch rows -2 .. 33 | -1 .. 32
-  static constexpr int P_BYTES = P_ROWS * BF_P_ROWB;
+  static constexpr int P_BYTES = QUAD ? 2 * BF_PQ_PLANE : P_ROWS * BF_P_ROWB;
   static constexpr int OFF_T = W_STAGES * BF_W_BYTES;
   static constexpr int OFF_A1 = OFF_T + T_BYTES;
   static constexpr bool ALT = QUAD;                     // the two T-warp sets take alternate batches (below) instead of halves of each
@@ -135,11 +140,18 @@ __device__ __forceinline__ void bf_chunk(int ph, int idx, int& ky, int& kx, int&
 // pixel `m` of batch `b` of the unit with row parity `pr`, strip `s`: cell (R, C) of column-parity plane pc
 template <bool QUAD>
 __device__ __forceinline__ bool bf_pixel(int s, int pr, int b, int m, int& R, int& C, int& pc) {
-  if (QUAD) {                                           // every cell of both column-parity planes: 2 x (17 rows x 9 cells)
+  if (QUAD) {
+    // every cell of both column-parity planes, 2 x (17 rows x 9 cells): first cells 0..7 of every row (a warp = 4 rows x 8 cells:
+    // its LDS.64 gathers from the patch and its STS.128 to T are bank-conflict free), then the ninth cell of the 2 x 17 rows
     const int idx = b * 128 + m;
-    pc = idx >= 153 ? 1 : 0;
-    const int rem = idx - 153 * pc;
-    R = rem / 9; C = rem - R * 9;
+    if (idx < 272) {
+      pc = idx >= 136 ? 1 : 0;
+      const int rem = idx - 136 * pc;
+      R = rem >> 3; C = rem & 7;
+    } else {
+      pc = idx >= 289 ? 1 : 0;
+      R = idx - 272 - 17 * pc; C = 8;
+    }
     return idx < 306;
   }
   int rr;
@@ -615,7 +627,8 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       // launch: patch offset, T cell, "outside the image" bit per quadrant, and the roles of the batch in the barrier protocol;
       // barrier addresses (incl. the leader's, mapa) are computed once, buffers and parities follow one counter
       // (kc = 3 l + k = g >> 1).
-      constexpr uint32_t W_INVALID = 1u << 27, W_SKIP = 1u << 28, W_FIRST = 1u << 29, W_LAST = 1u << 30, W_UNIT1 = 1u << 31;
+      constexpr uint32_t W_PC = 1u << 27, W_SKIP = 1u << 28, W_FIRST = 1u << 29, W_LAST = 1u << 30, W_UNIT1 = 1u << 31;
+      constexpr uint32_t W_INVALID = 0x3ffu;            // bits 0-9 all ones: no pixel
       uint32_t pw[3];     // bits 0-9: patch offset / 8, 10-22: T cell offset / 16, 23-26: outside-the-image bit of quadrant 0..3
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -623,9 +636,10 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
         int R, C, pc;
         const bool valid = bf_pixel<true>(s, pr, b, tt, R, C, pc);
         const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;        // pixel of the quadrant: rows -1 .. 32, columns 16 s - 1 .. 16 s + 16
-        const int g_off = (y + 1) * BF_P_ROWB + (x - 16 * s + 1) * 8;     // tap row 0 / column 0 of the pixel in the patch
+        // tap (0, 0) of the pixel in the patch: patch row y + 1, patch column x - 1 - (16 s - 2) = 2 C + pc -> plane pc, entry C
+        const int g_off = pc * BF_PQ_PLANE + (y + 1) * BF_PQ_ROWB + C * 8;
         const int c_off = ((pr * 2 + pc) * G) * BF_K8 + R * BF_ROW + C * 16;     // its T cell (channel group 0)
-        uint32_t w = valid ? ((uint32_t)(g_off >> 3) | ((uint32_t)(c_off >> 4) << 10)) : W_INVALID;
+        uint32_t w = valid ? ((uint32_t)(g_off >> 3) | ((uint32_t)(c_off >> 4) << 10) | (pc ? W_PC : 0u)) : W_INVALID;
 #pragma unroll
         for (int quad = 0; quad < 4; ++quad) {
           const int Y = 32 * (quad >> 1) + y, X = 32 * (quad & 1) + x;
@@ -664,14 +678,15 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
               else wn = 0xffffffffu;                    // no next tile: no gather, no arrive
             }
             if (wn != 0xffffffffu) {
-              if (!(wn & W_INVALID) && !(dbg & 1)) {
+              if ((wn & 0x3ffu) != W_INVALID && !(dbg & 1)) {
+                // columns x - 1 and x + 1 in the pixel's own column-parity plane, column x in the other one
                 const uint8_t* base = smem_gen + BF_OFF_P + pbn * BF_P_BYTES + ((wn & 0x3ffu) << 3);
-                const uint2* row0 = reinterpret_cast<const uint2*>(base);
-                const uint2* row1 = reinterpret_cast<const uint2*>(base + BF_P_ROWB);
-                const uint2* row2 = reinterpret_cast<const uint2*>(base + 2 * BF_P_ROWB);
+                const uint8_t* mid = base + ((wn & W_PC) ? 8 - BF_PQ_PLANE : BF_PQ_PLANE);
                 uint8_t* row = a1_row + (set * 2 + (int)((kc + (l < 0 ? 0u : 1u)) & 1u)) * BF_A1_BYTES;
-                const uint2 a0 = row0[0], a1 = row0[1], a2 = row0[2], b0 = row1[0], b1 = row1[1], b2 = row1[2];
-                const uint2 c0 = row2[0], c1 = row2[1], c2 = row2[2];
+                auto ld = [](const uint8_t* q) { return *reinterpret_cast<const uint2*>(q); };
+                const uint2 a0 = ld(base), a1 = ld(mid), a2 = ld(base + 8);
+                const uint2 b0 = ld(base + BF_PQ_ROWB), b1 = ld(mid + BF_PQ_ROWB), b2 = ld(base + BF_PQ_ROWB + 8);
+                const uint2 c0 = ld(base + 2 * BF_PQ_ROWB), c1 = ld(mid + 2 * BF_PQ_ROWB), c2 = ld(base + 2 * BF_PQ_ROWB + 8);
                 uint4 w;
                 w.x = a0.x;
                 w.y = __byte_perm(a0.y, a1.x, 0x5410);  // lo16(a0.y) | lo16(a1.x) << 16
@@ -715,7 +730,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
             tmem_ld32(t_lane + (uint32_t)(cb * CH), r);
             tmem_ld32(t_lane + (uint32_t)(cb * CH) + 32u, r + 32);
             tmem_ld_wait();
-            if (!(w & W_INVALID)) {
+            if ((w & 0x3ffu) != W_INVALID) {
               const bool in_img = !((w >> (23 + (int)(t & 3))) & 1u);       // a cell outside the image is conv padding = zero
               uint8_t* cell = smem_gen + BF_OFF_T + (((w >> 10) & 0x1fffu) << 4);
 #pragma unroll
@@ -817,33 +832,61 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       if (L >= my_tiles) return;
       const int pb = (int)(L & 1);
       const uint32_t par = (uint32_t)(((L >> 1) & 1) ^ 1);
-      const float* lut32 = reinterpret_cast<const float*>(smem_gen + B::OFF_LUT);
-      const uint16_t* lut16 = reinterpret_cast<const uint16_t*>(smem_gen + B::OFF_LUT + 1024);
       const uint8_t* raw = smem_gen + BF_OFF_X + pb * B::X_BYTES;
       uint8_t* patch = smem_gen + BF_OFF_P + pb * BF_P_BYTES;
       long long n_; int qy, qx, goff;
       e_tile_of(L, n_, qy, qx, goff);
+      // Pixel X of an image row sits at byte 3 X - goff of its landing row.  The patch starts at image column X0 = 32 qx + 16 s - 2
+      // and 3 X0 = 2 (mod 4): patch column cx is at byte 3 cx + 2 (goff = 3 X0 - 2), or at 3 cx - 6 for the first strip of the image
+      // (X0 = -2, goff = 0).  Either way four pixels are the 12 bytes from byte 2 of an aligned word: four LDS.32 per four pixels
+      // instead of a byte load and a table lookup per value; the conversion is bf_nrm()'s arithmetic (these warps have the time,
+      // the shared-memory pipe has not: profiles/r4_b1fused64.md).
+      const int first = (qx | s) == 0 ? 8 : 0;
       mbar_wait(smem_u32(&bar_patch_free[pb]), par);    // the T warps have gathered tile L - 2 from this buffer
-#pragma unroll 2
-      for (int i = e128; i < 36 * 20; i += 128) {
-        const int ry = i / 20, cx = i - ry * 20;
-        const int Y = 32 * qy - 2 + ry, X = 32 * qx + 16 * s - 2 + cx;
-        uint2 v = make_uint2(0u, 0u);
-        if (Y >= 0 && Y < 64 && X >= 0 && X < 64) {
-          const uint8_t* b = raw + ry * BF_X_ROWB + 3 * X - goff;
-          v = make_uint2((uint32_t)lut16[b[0]] | ((uint32_t)lut16[b[1]] << 16), (uint32_t)lut16[b[2]]);
+#pragma unroll 1
+      for (int i = e128; i < 36 * 5; i += 128) {
+        const int ry = i / 5, g = i - ry * 5;           // patch row, group of four patch columns 4 g .. 4 g + 3
+        const int Y = 32 * qy - 2 + ry, X0 = 32 * qx + 16 * s - 2 + 4 * g;
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0u;
+        if (Y >= 0 && Y < 64) {
+          const int boff = 12 * g - first;              // byte offset of the first of the four words (< 0: pixels left of the image)
+          const uint32_t* wr = reinterpret_cast<const uint32_t*>(raw + ry * BF_X_ROWB + (boff < 0 ? 0 : boff));
+          uint32_t w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+          if (boff < 0) { w2 = w0; w3 = w1; }           // boff = -8: words 2, 3 are the row's first two
+          const uint32_t by[12] = {(w0 >> 16) & 255u, w0 >> 24, w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
+                                   w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24, w3 & 255u, (w3 >> 8) & 255u};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (X0 + j >= 0 && X0 + j < 64) {
+              v[2 * j] = pack_h2<F16>(bf_nrm((uint8_t)by[3 * j]), bf_nrm((uint8_t)by[3 * j + 1]));
+              v[2 * j + 1] = pack_h2<F16>(bf_nrm((uint8_t)by[3 * j + 2]), 0.f);
+            }
+          }
         }
-        *reinterpret_cast<uint2*>(patch + ry * BF_P_ROWB + cx * 8) = v;
+        // patch columns 4 g, 4 g + 2 -> entries 2 g, 2 g + 1 of the even plane; 4 g + 1, 4 g + 3 -> the same entries of the odd one
+        *reinterpret_cast<uint4*>(patch + ry * BF_PQ_ROWB + g * 16) = make_uint4(v[0], v[1], v[4], v[5]);
+        *reinterpret_cast<uint4*>(patch + BF_PQ_PLANE + ry * BF_PQ_ROWB + g * 16) = make_uint4(v[2], v[3], v[6], v[7]);
       }
       mbar_wait(smem_u32(&bar_sc_free[pb]), par);       // the shortcut MMA of tile L - 2 has read this buffer
       {
-        // the 2 x 2 input pixels under pooled output pixel (e128 >> 3, 8 s + (e128 & 7)) of the tile
+        // the 2 x 2 input pixels under pooled output pixel (e128 >> 3, 8 s + (e128 & 7)) of the tile: image column
+        // 32 qx + 2 (8 s + j) = X0 + 2 + 2 j, i.e. six bytes from byte 8 + 6 j (6 j for the first strip) of landing rows 2 + 2 oy, + 1
         constexpr uint32_t kOne = F16 ? 0x3C00u : 0x3F80u;
-        const uint8_t* b = raw + (2 + 2 * (e128 >> 3)) * BF_X_ROWB + 3 * (32 * qx + 2 * (8 * s + (e128 & 7))) - goff;
+        const int off = 6 * (e128 & 7) + 8 - first;
+        const uint32_t sh = (uint32_t)(off & 3) * 8u;
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(raw + (2 + 2 * (e128 >> 3)) * BF_X_ROWB + (off & ~3));
+        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(r0) + BF_X_ROWB);
+        const uint32_t a0 = r0[0], a1 = r0[1], c0 = r1[0], c1 = r1[1];
+        const uint32_t lo0 = __funnelshift_r(a0, a1, sh), hi0 = a1 >> sh, lo1 = __funnelshift_r(c0, c1, sh), hi1 = c1 >> sh;
+        // bytes 0..2 = left pixel, 3..5 = right pixel of the row
+        const uint32_t l0[3] = {lo0 & 255u, (lo0 >> 8) & 255u, (lo0 >> 16) & 255u}, q0[3] = {lo0 >> 24, hi0 & 255u, (hi0 >> 8) & 255u};
+        const uint32_t l1[3] = {lo1 & 255u, (lo1 >> 8) & 255u, (lo1 >> 16) & 255u}, q1[3] = {lo1 >> 24, hi1 & 255u, (hi1 >> 8) & 255u};
         uint32_t ph[3], pl[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float px = (lut32[b[c]] + lut32[b[3 + c]] + lut32[b[BF_X_ROWB + c]] + lut32[b[BF_X_ROWB + 3 + c]]) * 0.25f;
+          const float px = (bf_nrm((uint8_t)l0[c]) + bf_nrm((uint8_t)q0[c]) + bf_nrm((uint8_t)l1[c]) + bf_nrm((uint8_t)q1[c])) * 0.25f;
           ph[c] = pack_h2<F16>(px, 0.f) & 0xffffu;
           pl[c] = pack_h2<F16>(px - unpack_h2<F16>(ph[c]).x, 0.f) & 0xffffu;
         }
