@@ -53,13 +53,13 @@ constexpr int BF_ROW = 9 * 16;                          // 144: one plane row = 
 constexpr int BF_K8 = 17 * BF_ROW;                      // 2448: 17 plane rows per 8-channel group
 constexpr int BF_A1_BYTES = 4 * 128 * 16;               // 8192: [k8 0..3][128 pixels] x 16 B
 constexpr int BF_X_ROWB = 64;                           // raw image rows: the bytes of the strip's columns (CH = 128: 56 at offset 4)
-constexpr int BF_P_ROWB = 160;                          // normalised 16-bit patch: up to 20 pixels x (c0, c1, c2, pad) per row
 constexpr int BF_SC_BYTES = 2 * 128 * 16;               // shortcut operand: [k8 0..1][128 output pixels] x 16 B
 // CH = 64: the patch is split into its even and odd COLUMNS (two planes of 36 rows x 10 pixels): the three taps of a row are then
 // at (plane pc, C), (plane 1 - pc, C + pc), (plane pc, C + 1) with consecutive lanes (C) 8 bytes apart, and with 96-byte rows
 // two rows of 8 pixels fill the 32 banks exactly
 constexpr int BF_PQ_ROWB = 96;
 constexpr int BF_PQ_PLANE = 36 * BF_PQ_ROWB;
+constexpr int BF_P128_PLANE = 34 * BF_PQ_ROWB;          // CH = 128: the same split of its 34 x 20 patch
 
 template <int CH>
 struct Bf {
@@ -75,7 +75,7 @@ struct Bf {
   static constexpr int X_ROWS = QUAD ? 36 : 32;         // landing buffer: image rows -2 .. 33 of the quadrant | the image's 32 rows
   static constexpr int X_BYTES = X_ROWS * BF_X_ROWB;
   static constexpr int P_ROWS = QUAD ? 36 : 34;         // patch rows -2 .. 33 | -1 .. 32
-  static constexpr int P_BYTES = QUAD ? 2 * BF_PQ_PLANE : P_ROWS * BF_P_ROWB;
+  static constexpr int P_BYTES = 2 * P_ROWS * BF_PQ_ROWB;   // two column-parity planes
   static constexpr int OFF_T = W_STAGES * BF_W_BYTES;
   static constexpr int OFF_A1 = OFF_T + T_BYTES;
   static constexpr bool ALT = QUAD;                     // the two T-warp sets take alternate batches (below) instead of halves of each
@@ -87,12 +87,12 @@ struct Bf {
   static constexpr int OFF_X = OFF_W1 + W1_BYTES;
   static constexpr int OFF_P = OFF_X + NB * X_BYTES;
   static constexpr int OFF_SC = OFF_P + NB * P_BYTES;
-  static constexpr int OFF_LUT = OFF_SC + NB * BF_SC_BYTES;  // CH = 64: normalised value of every byte, fp32 [256] then 16-bit [256]
-  static constexpr int SMEM = 1024 + OFF_LUT + (QUAD ? 1536 : 0);
+  static constexpr int OFF_END = OFF_SC + NB * BF_SC_BYTES;
+  static constexpr int SMEM = 1024 + OFF_END;
   static constexpr int W2_LD = 16 * CH + 64;            // packed c2 weights: 16 taps x CH channels + one 64-column chunk for the shortcut
   static constexpr int SC_COL = 16 * CH;                // ... which starts at this column
   static constexpr int UNIT_CELLS = QUAD ? 306 : 272;   // T cells one unit (row-parity half) computes: 2 x 17 x 9 | 16 x 8 + 16 x 9
-  static_assert(SMEM <= 227 * 1024 - 1024, "b1_fused_kernel: shared memory budget (static: < 1 KB of barriers)");
+  static_assert(SMEM + 512 <= 227 * 1024, "b1_fused_kernel: shared memory budget (static: < 512 B of barriers)");
 };
 
 struct BfParams {
@@ -158,10 +158,12 @@ __device__ __forceinline__ bool bf_pixel(int s, int pr, int b, int m, int& R, in
   bool valid = true;
   if (b == 0) {                                         // the 8-column parity plane: 16 rows x 8 cells
     rr = m >> 3; C = (m & 7) + (1 - s); pc = s;
-  } else {                                              // the 9-column one: 144 cells in address order
-    const int idx = (b - 1) * 128 + m;
+  } else {                                              // the 9-column one: cells 0..7 of its 16 rows, then the ninth cell of each
+    const int idx = (b - 1) * 128 + m;                  // (8-cell lane rows: conflict-free gathers from the 96-byte patch rows)
     valid = idx < 144;
-    rr = idx / 9; C = idx - rr * 9; pc = 1 - s;
+    if (idx < 128) { rr = idx >> 3; C = idx & 7; }
+    else { rr = idx - 128; C = 8; }
+    pc = 1 - s;
   }
   R = rr + (pr ? 0 : 1);
   return valid;
@@ -226,11 +228,6 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       w.z = (w.z & 0xffff0000u) | lo;                   // k = 28
     }
     *reinterpret_cast<uint4*>(smem_gen + BF_OFF_W1 + j * (NH * 16) + r * 16) = w;
-  }
-  if (QUAD && threadIdx.x < 256) {
-    const float v = bf_nrm((uint8_t)threadIdx.x);
-    reinterpret_cast<float*>(smem_gen + B::OFF_LUT)[threadIdx.x] = v;
-    reinterpret_cast<uint16_t*>(smem_gen + B::OFF_LUT + 1024)[threadIdx.x] = (uint16_t)(pack_h2<F16>(v, 0.f) & 0xffffu);
   }
   fence_proxy_async_smem();
 
@@ -420,202 +417,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
     const int tt = q * 32 + lane;                       // batch pixel = TMEM lane
     const int t256 = set * 128 + tt;
     constexpr uint32_t kOne = F16 ? 0x3C00u : 0x3F80u;
-    constexpr int XO = QUAD ? 0 : 4;                    // offset of the landed bytes inside a landing-buffer row
-    // tile l of this cluster: image n and (CH = 64) quadrant (qy, qx); goff = first byte of an image row held in the landing
-    // buffer (4-byte aligned; CH = 128: image columns 15 s - 1 .. 15 s + 17 = bytes goff .. goff + 55; CH = 64: image columns
-    // 32 qx + 16 s - 2 .. + 17, the 64 bytes from goff, clipped at the row end)
-    auto tile_of = [&](long long l, long long& n, int& qy, int& qx, int& goff) {
-      const long long t = cluster_id + l * n_clusters;
-      if (QUAD) {
-        n = t >> 2; qy = (int)(t & 3) >> 1; qx = (int)(t & 1);
-        const int b0 = (32 * qx + 16 * s - 2) * 3;
-        goff = b0 < 0 ? 0 : (b0 & ~3);
-      } else {
-        n = t; qy = 0; qx = 0; goff = s ? 40 : 0;
-      }
-    };
-    // raw rows of tile l -> the (single) landing buffer
-    auto prefetch_x = [&](long long l) {
-      if (l < my_tiles) {
-        long long n; int qy, qx, goff;
-        tile_of(l, n, qy, qx, goff);
-        const uint32_t dst = smem_base + BF_OFF_X + XO;
-        if (QUAD) {
-          const uint8_t* src = p.x + n * (64 * 64 * 3) + goff;
-          for (int w = t256; w < 36 * 16; w += BF_T_THREADS) {
-            const int row = w >> 4, wi = w & 15;
-            const int Y = 32 * qy - 2 + row;
-            if (Y >= 0 && Y < 64 && goff + wi * 4 < 192) cp_async_4(dst + row * BF_X_ROWB + wi * 4, src + Y * 192 + wi * 4);
-          }
-        } else {
-          const uint8_t* src = p.x + n * 3072 + goff;
-          for (int w = t256; w < 32 * 14; w += BF_T_THREADS) {
-            const int row = w / 14, wi = w - row * 14;
-            cp_async_4(dst + row * BF_X_ROWB + wi * 4, src + row * 96 + wi * 4);
-          }
-        }
-      }
-      cp_async_commit();
-    };
-    auto nrm = [](uint8_t u) { return bf_nrm(u); };
-    // CH = 64 converts 2 160 bytes per tile on warps whose instruction stream paces the kernel: a table lookup per byte instead
-    // (the entries are nrm()'s values and their 16-bit roundings, so the operands are bit-identical)
-    const float* lut32 = reinterpret_cast<const float*>(smem_gen + B::OFF_LUT);
-    const uint16_t* lut16 = reinterpret_cast<const uint16_t*>(smem_gen + B::OFF_LUT + 1024);
-    // landed bytes -> (a) normalised 16-bit patch, the first conv's operand values, converted ONCE per byte instead of once per
-    // tap: patch pixel (ry, cx) = image pixel (ry - 1, 15 s - 1 + cx) as (c0, c1, c2, 0); 18 in-image columns per row;
-    // (b) the shortcut operand of tile L: row m = avg_pool2d(normalised x) at output pixel (m >> 3, 8 s + (m & 7)) as hi / lo pairs
-    // CH = 64: patch pixel (ry, cx) = quadrant pixel (ry - 2, 16 s - 2 + cx), 20 columns; pixels outside the IMAGE are written as
-    // zeros for every tile (which ones they are changes with the quadrant)
-    auto convert_x = [&](long long L) {
-      const uint8_t* raw = smem_gen + BF_OFF_X + XO;
-      long long n_; int qy, qx, goff;
-      tile_of(L, n_, qy, qx, goff);
-      if (QUAD) {
-        for (int i = t256; i < 36 * 20; i += BF_T_THREADS) {
-          const int ry = i / 20, cx = i - ry * 20;
-          const int Y = 32 * qy - 2 + ry, X = 32 * qx + 16 * s - 2 + cx;
-          uint2 v = make_uint2(0u, 0u);
-          if (Y >= 0 && Y < 64 && X >= 0 && X < 64) {
-            const uint8_t* b = raw + ry * BF_X_ROWB + 3 * X - goff;
-            v = make_uint2((uint32_t)lut16[b[0]] | ((uint32_t)lut16[b[1]] << 16), (uint32_t)lut16[b[2]]);
-          }
-          *reinterpret_cast<uint2*>(smem_gen + BF_OFF_P + ry * BF_P_ROWB + cx * 8) = v;
-        }
-      } else {
-        for (int i = t256; i < 32 * 18; i += BF_T_THREADS) {
-          const int row = i / 18, j = i - row * 18;     // j-th in-image pixel of the row: image column (s ? 14 : 0) + j
-          const uint8_t* b = raw + row * BF_X_ROWB + 3 * ((s ? 14 : 0) + j) - goff;
-          const uint32_t lo = pack_h2<F16>(nrm(b[0]), nrm(b[1])), hi = pack_h2<F16>(nrm(b[2]), 0.f);
-          *reinterpret_cast<uint2*>(smem_gen + BF_OFF_P + (row + 1) * BF_P_ROWB + (j + (s ? 0 : 1)) * 8) = make_uint2(lo, hi);
-        }
-      }
-      mbar_wait(smem_u32(&bar_sc_free[0]), (uint32_t)((L & 1) ^ 1));  // the previous tile's shortcut MMA has read the buffer
-      {
-        // the 2 x 2 input pixels under pooled output pixel (tt >> 3, 8 s + (tt & 7)) of the tile
-        const uint8_t* b = QUAD ? raw + (2 + 2 * (tt >> 3)) * BF_X_ROWB + 3 * (32 * qx + 2 * (8 * s + (tt & 7))) - goff
-                                : raw + (2 * (tt >> 3)) * BF_X_ROWB + 3 * (2 * (8 * s + (tt & 7))) - goff;
-        float px[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          px[c] = QUAD ? (lut32[b[c]] + lut32[b[3 + c]] + lut32[b[BF_X_ROWB + c]] + lut32[b[BF_X_ROWB + 3 + c]]) * 0.25f
-                       : (nrm(b[c]) + nrm(b[3 + c]) + nrm(b[BF_X_ROWB + c]) + nrm(b[BF_X_ROWB + 3 + c])) * 0.25f;
-        uint32_t ph[3], pl[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          ph[c] = pack_h2<F16>(px[c], 0.f) & 0xffffu;
-          pl[c] = pack_h2<F16>(px[c] - unpack_h2<F16>(ph[c]).x, 0.f) & 0xffffu;
-        }
-        uint4 v;
-        if (set == 0) v = make_uint4(ph[0] | (ph[1] << 16), ph[2] | (pl[0] << 16), pl[1] | (pl[2] << 16), ph[0] | (ph[1] << 16));
-        else v = make_uint4(ph[2] | (kOne << 16), kOne | (kOne << 16), 0u, 0u);
-        *reinterpret_cast<uint4*>(smem_gen + BF_OFF_SC + set * 2048 + tt * 16) = v;
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_sc_full[0]), 0));
-    };
-    // gather the K columns of batch pixel tt of (unit uu, batch b) of the tile in the patch into A1[gb] -- this set's 16 columns,
-    // or (ALT) all 32: K column k = (ky*3 + kx)*3 + c for k < 27; 27, 28 = 1.0 (bias hi / lo); 29..31 = 0
-    auto build_a1 = [&](int uu, int b, int gb, int pb = 0) {
-      const int pr = 1 - uu;
-      int R, C, pc;
-      const bool valid = bf_pixel<QUAD>(s, pr, b, tt, R, C, pc);
-      if (valid && !(dbg & 1)) {
-        const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;       // pixel of the tile: rows -1 .. 32, columns 16 s - 1 .. 16 s + 16
-        // pixel (y + ky - 1, x - 1) of tap row ky: CH = 128: patch row y + ky, patch column x - 1 - (15 s - 1) = x - 15 s;
-        // CH = 64: patch row y + ky + 1, patch column x - 1 - (16 s - 2) = x - 16 s + 1
-        const uint2* row0 = QUAD ? reinterpret_cast<const uint2*>(smem_gen + BF_OFF_P + pb * BF_P_BYTES + (y + 1) * BF_P_ROWB + (x - 16 * s + 1) * 8)
-                                 : reinterpret_cast<const uint2*>(smem_gen + BF_OFF_P + y * BF_P_ROWB + (x - 15 * s) * 8);
-        const uint2* row1 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(row0) + BF_P_ROWB);
-        const uint2* row2 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(row0) + 2 * BF_P_ROWB);
-        uint8_t* row = smem_gen + BF_OFF_A1 + gb * BF_A1_BYTES + tt * 16;
-        if (ALT || set == 0) {
-          const uint2 a0 = row0[0], a1 = row0[1], a2 = row0[2], b0 = row1[0], b1 = row1[1], b2 = row1[2];
-          uint32_t w[8];
-          w[0] = a0.x;
-          w[1] = __byte_perm(a0.y, a1.x, 0x5410);       // lo16(a0.y) | lo16(a1.x) << 16
-          w[2] = __byte_perm(a1.x, a1.y, 0x5432);       // hi16(a1.x) | lo16(a1.y) << 16
-          w[3] = a2.x;
-          w[4] = __byte_perm(a2.y, b0.x, 0x5410);
-          w[5] = __byte_perm(b0.x, b0.y, 0x5432);
-          w[6] = b1.x;
-          w[7] = __byte_perm(b1.y, b2.x, 0x5410);
-          *reinterpret_cast<uint4*>(row) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(row + 2048) = make_uint4(w[4], w[5], w[6], w[7]);
-        }
-        if (ALT || set == 1) {
-          const uint2 b2 = row1[2], c0 = row2[0], c1 = row2[1], c2 = row2[2];
-          uint32_t w[8];
-          w[0] = __byte_perm(b2.x, b2.y, 0x5432);
-          w[1] = c0.x;
-          w[2] = __byte_perm(c0.y, c1.x, 0x5410);
-          w[3] = __byte_perm(c1.x, c1.y, 0x5432);
-          w[4] = c2.x;
-          w[5] = (c2.y & 0xffffu) | (kOne << 16);
-          w[6] = kOne;
-          w[7] = 0u;
-          *reinterpret_cast<uint4*>(row + 2 * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(row + 3 * 2048) = make_uint4(w[4], w[5], w[6], w[7]);
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_a1_full[gb]), 0));
-    };
     uint32_t vmaxw = 0;                                 // fp16 range guard: running maximum of the (non-negative) packed halves
-    // batch (uu, b) of tile (n, qy, qx) is in TMEM accumulator cb: relu / convert -> T cells.  Channels [ch0, ch0 + NCH).
-    auto drain = [&](long long n, int qy, int qx, int uu, int b, int cb) {
-      constexpr int NCH = ALT ? CH : CH / 2;
-      const int ch0 = ALT ? 0 : set * (CH / 2);
-      const int pr = 1 - uu;
-      int R, C, pc;
-      const bool valid = bf_pixel<QUAD>(s, pr, b, tt, R, C, pc);
-      if ((b < 2 || q < (QUAD ? 2 : 1)) && !(dbg & 2)) {
-        uint8_t* cell = smem_gen + BF_OFF_T + ((pr * 2 + pc) * G + (ch0 >> 3)) * BF_K8 + R * BF_ROW + C * 16;
-        // pixel of the tile (rows -1 .. 32), then of the image; CH = 64: a cell outside the image is conv padding = zero
-        const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;
-        const int Y = 32 * qy + y, X = 32 * qx + x;
-        const bool in_img = !QUAD || (Y >= 0 && Y < 64 && X >= 0 && X < 64);
-        const uint32_t taddr = tmem_base + 256u + (uint32_t)(cb * CH + ch0) + ((uint32_t)(q * 32) << 16);
-        uint32_t r[NCH];
-        tmem_ld32(taddr, r);
-        if (NCH == 64) tmem_ld32(taddr + 32u, r + (NCH == 64 ? 32 : 0));
-        tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int gq = 0; gq < NCH / 8; ++gq) {
-            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-            if (in_img) {
-              pk.x = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]));
-              pk.y = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
-              pk.z = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
-              pk.w = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
-            }
-            if (F16) vmaxw = __vmaxu2(__vmaxu2(vmaxw, pk.x), __vmaxu2(__vmaxu2(pk.y, pk.z), pk.w));
-            *reinterpret_cast<uint4*>(cell + gq * BF_K8) = pk;
-            if (p.dbg_t && in_img)
-              *reinterpret_cast<uint4*>(p.dbg_t + ((((long long)n * IMG + Y) * IMG + X) * CH + ch0 + gq * 8)) = pk;
-          }
-        }
-      }
-      tc_fence_before();
-      fence_proxy_async_smem();                         // T cells -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_c1_empty[cb]), 0));
-    };
-    // the patch of tile l replaces the previous one: every T thread has landed its rows and nobody reads the old patch any more
-    auto switch_patch = [&](long long l) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      named_bar_sync(1, BF_T_THREADS);
-      convert_x(l);
-      named_bar_sync(1, BF_T_THREADS);                  // patch complete, landing buffer idle
-      prefetch_x(l + 1);
-    };
-    if (my_tiles > 0 && !EPI_PATCH) {
-      prefetch_x(0);
-      switch_patch(0);
-    }
     if constexpr (ALT) {
       // CH = 64.  The two sets take ALTERNATE batches (set = g & 1), each with two im2col buffers / c1 accumulators of its own.
       // With a 64-channel c2 the tensor pipe needs a tile's T in ~2 400 cycles and these eight warps pace the kernel: two in-order
@@ -770,11 +572,159 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
         if (l >= 0) t += n_clusters;
       }
     } else {
-      if (my_tiles > 0) build_a1(0, 0, 0);
+      // CH = 128: tile l of this cluster = image n; the landing buffer holds, per image row, the 56 bytes of image columns
+      // 15 s - 1 .. 15 s + 17 from byte goff of the row (4-byte aligned), at offset 4 of a 64-byte landing row
+      constexpr int XO = 4;
+      const int goff = s ? 40 : 0;
+      auto prefetch_x = [&](long long l) {              // raw rows of tile l -> the (single) landing buffer
+        if (l < my_tiles) {
+          const uint8_t* src = p.x + (cluster_id + l * n_clusters) * 3072 + goff;
+          const uint32_t dst = smem_base + BF_OFF_X + XO;
+          for (int w = t256; w < 32 * 14; w += BF_T_THREADS) {
+            const int row = w / 14, wi = w - row * 14;
+            cp_async_4(dst + row * BF_X_ROWB + wi * 4, src + row * 96 + wi * 4);
+          }
+        }
+        cp_async_commit();
+      };
+      auto nrm = [](uint8_t u) { return bf_nrm(u); };
+      // landed bytes -> (a) normalised 16-bit patch, the first conv's operand values, converted ONCE per byte instead of once per
+      // tap: patch pixel (ry, cx) = image pixel (ry - 1, 15 s - 1 + cx) as (c0, c1, c2, 0), 18 in-image columns per row, stored as
+      // two column-parity planes (entry cx >> 1 of plane cx & 1, 96-byte rows) so that the gathers below, whose lanes step two
+      // columns, read consecutive 8-byte entries; (b) the shortcut operand of tile L: row m = avg_pool2d(normalised x) at output
+      // pixel (m >> 3, 8 s + (m & 7)) as hi / lo pairs
+      auto convert_x = [&](long long L) {
+        const uint8_t* raw = smem_gen + BF_OFF_X + XO;
+        for (int i = t256; i < 32 * 18; i += BF_T_THREADS) {
+          const int row = i / 18, j = i - row * 18;     // j-th in-image pixel of the row: image column (s ? 14 : 0) + j
+          const uint8_t* b = raw + row * BF_X_ROWB + 3 * ((s ? 14 : 0) + j) - goff;
+          const uint32_t lo = pack_h2<F16>(nrm(b[0]), nrm(b[1])), hi = pack_h2<F16>(nrm(b[2]), 0.f);
+          const int cx = j + (s ? 0 : 1);
+          *reinterpret_cast<uint2*>(smem_gen + BF_OFF_P + (cx & 1) * BF_P128_PLANE + (row + 1) * BF_PQ_ROWB + (cx >> 1) * 8) = make_uint2(lo, hi);
+        }
+        mbar_wait(smem_u32(&bar_sc_free[0]), (uint32_t)((L & 1) ^ 1));  // the previous tile's shortcut MMA has read the buffer
+        {
+          // the 2 x 2 input pixels under pooled output pixel (tt >> 3, 8 s + (tt & 7)) of the tile
+          const uint8_t* b = raw + (2 * (tt >> 3)) * BF_X_ROWB + 3 * (2 * (8 * s + (tt & 7))) - goff;
+          float px[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            px[c] = (nrm(b[c]) + nrm(b[3 + c]) + nrm(b[BF_X_ROWB + c]) + nrm(b[BF_X_ROWB + 3 + c])) * 0.25f;
+          uint32_t ph[3], pl[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            ph[c] = pack_h2<F16>(px[c], 0.f) & 0xffffu;
+            pl[c] = pack_h2<F16>(px[c] - unpack_h2<F16>(ph[c]).x, 0.f) & 0xffffu;
+          }
+          uint4 v;
+          if (set == 0) v = make_uint4(ph[0] | (ph[1] << 16), ph[2] | (pl[0] << 16), pl[1] | (pl[2] << 16), ph[0] | (ph[1] << 16));
+          else v = make_uint4(ph[2] | (kOne << 16), kOne | (kOne << 16), 0u, 0u);
+          *reinterpret_cast<uint4*>(smem_gen + BF_OFF_SC + set * 2048 + tt * 16) = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_sc_full[0]), 0));
+      };
+      // gather this set's 16 K columns of batch pixel tt of (unit uu, batch b) of the tile from the patch into A1[gb]:
+      // K column k = (ky*3 + kx)*3 + c for k < 27; 27, 28 = 1.0 (bias hi / lo); 29..31 = 0
+      auto build_a1 = [&](int uu, int b, int gb) {
+        const int pr = 1 - uu;
+        int R, C, pc;
+        const bool valid = bf_pixel<false>(s, pr, b, tt, R, C, pc);
+        if (valid && !(dbg & 1)) {
+          const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;     // pixel of the tile: rows -1 .. 32, columns 16 s - 1 .. 16 s + 16
+          // tap (ky, kx) reads image pixel (y + ky - 1, x + kx - 1) = patch row y + ky, patch column x - 15 s + kx: columns
+          // kx = 0, 2 are entries e0, e0 + 1 of one plane, kx = 1 is entry (cx0 + 1) >> 1 of the other
+          const int cx0 = x - 15 * s;
+          const uint8_t* base = smem_gen + BF_OFF_P + (cx0 & 1) * BF_P128_PLANE + y * BF_PQ_ROWB + (cx0 >> 1) * 8;
+          const uint8_t* mid = smem_gen + BF_OFF_P + ((cx0 + 1) & 1) * BF_P128_PLANE + y * BF_PQ_ROWB + ((cx0 + 1) >> 1) * 8;
+          auto ld = [](const uint8_t* q_) { return *reinterpret_cast<const uint2*>(q_); };
+          uint8_t* row = smem_gen + BF_OFF_A1 + gb * BF_A1_BYTES + tt * 16;
+          if (set == 0) {
+            const uint2 a0 = ld(base), a1 = ld(mid), a2 = ld(base + 8);
+            const uint2 b0 = ld(base + BF_PQ_ROWB), b1 = ld(mid + BF_PQ_ROWB), b2 = ld(base + BF_PQ_ROWB + 8);
+            uint32_t w[8];
+            w[0] = a0.x;
+            w[1] = __byte_perm(a0.y, a1.x, 0x5410);     // lo16(a0.y) | lo16(a1.x) << 16
+            w[2] = __byte_perm(a1.x, a1.y, 0x5432);     // hi16(a1.x) | lo16(a1.y) << 16
+            w[3] = a2.x;
+            w[4] = __byte_perm(a2.y, b0.x, 0x5410);
+            w[5] = __byte_perm(b0.x, b0.y, 0x5432);
+            w[6] = b1.x;
+            w[7] = __byte_perm(b1.y, b2.x, 0x5410);
+            *reinterpret_cast<uint4*>(row) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(row + 2048) = make_uint4(w[4], w[5], w[6], w[7]);
+          } else {
+            const uint2 b2 = ld(base + BF_PQ_ROWB + 8);
+            const uint2 c0 = ld(base + 2 * BF_PQ_ROWB), c1 = ld(mid + 2 * BF_PQ_ROWB), c2 = ld(base + 2 * BF_PQ_ROWB + 8);
+            uint32_t w[8];
+            w[0] = __byte_perm(b2.x, b2.y, 0x5432);
+            w[1] = c0.x;
+            w[2] = __byte_perm(c0.y, c1.x, 0x5410);
+            w[3] = __byte_perm(c1.x, c1.y, 0x5432);
+            w[4] = c2.x;
+            w[5] = (c2.y & 0xffffu) | (kOne << 16);
+            w[6] = kOne;
+            w[7] = 0u;
+            *reinterpret_cast<uint4*>(row + 2 * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(row + 3 * 2048) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_a1_full[gb]), 0));
+      };
+      // batch (uu, b) of image n is in TMEM accumulator cb: relu / convert -> T cells, this set's 64 channels
+      auto drain = [&](long long n, int uu, int b, int cb) {
+        constexpr int NCH = CH / 2;
+        const int ch0 = set * (CH / 2);
+        const int pr = 1 - uu;
+        int R, C, pc;
+        const bool valid = bf_pixel<false>(s, pr, b, tt, R, C, pc);
+        if ((b < 2 || q < 1) && !(dbg & 2)) {            // the third batch of a unit holds 16 pixels: lane quadrant 0
+          uint8_t* cell = smem_gen + BF_OFF_T + ((pr * 2 + pc) * G + (ch0 >> 3)) * BF_K8 + R * BF_ROW + C * 16;
+          const int Y = 2 * R + pr - 1, X = 16 * s - 1 + 2 * C + pc;     // pixel of the image (the halo cells are never computed)
+          const uint32_t taddr = tmem_base + 256u + (uint32_t)(cb * CH + ch0) + ((uint32_t)(q * 32) << 16);
+          uint32_t r[NCH];
+          tmem_ld32(taddr, r);
+          tmem_ld32(taddr + 32u, r + 32);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int gq = 0; gq < NCH / 8; ++gq) {
+              uint4 pk;
+              pk.x = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]));
+              pk.y = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
+              pk.z = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+              pk.w = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
+              if (F16) vmaxw = __vmaxu2(__vmaxu2(vmaxw, pk.x), __vmaxu2(__vmaxu2(pk.y, pk.z), pk.w));
+              *reinterpret_cast<uint4*>(cell + gq * BF_K8) = pk;
+              if (p.dbg_t)
+                *reinterpret_cast<uint4*>(p.dbg_t + ((((long long)n * IMG + Y) * IMG + X) * CH + ch0 + gq * 8)) = pk;
+            }
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();                       // T cells -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_c1_empty[cb]), 0));
+      };
+      // the patch of tile l replaces the previous one: every T thread has landed its rows and nobody reads the old patch any more
+      auto switch_patch = [&](long long l) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        named_bar_sync(1, BF_T_THREADS);
+        convert_x(l);
+        named_bar_sync(1, BF_T_THREADS);                // patch complete, landing buffer idle
+        prefetch_x(l + 1);
+      };
+      if (my_tiles > 0) {
+        prefetch_x(0);
+        switch_patch(0);
+        build_a1(0, 0, 0);
+      }
       long long g = 0;
       for (long long l = 0; l < my_tiles; ++l) {
-        long long n; int qy, qx, goff_;
-        tile_of(l, n, qy, qx, goff_);
+        const long long n = cluster_id + l * n_clusters;
         for (int uu = 0; uu < 2; ++uu) {
           for (int b = 0; b < 3; ++b, ++g) {
             const int cb = (int)(g & 1);
@@ -789,7 +739,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
             mbar_wait(smem_u32(&bar_c1_full[cb]), (uint32_t)((g >> 1) & 1));      // batch g is in TMEM
             tc_fence_after();
             if (b == 0) mbar_wait(smem_u32(&bar_t_free[uu]), (uint32_t)((l & 1) ^ 1));   // c2 is done with this half of T
-            drain(n, qy, qx, uu, b, cb);
+            drain(n, uu, b, cb);
           }
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_t_ready[uu]), 0));
         }
