@@ -37,6 +37,14 @@
 // the quadrant.  N = 64: tcgen05.mma.cta_group::2 of M = 256 pixels x N = 64 channels, no structural zeros (the unfused
 // path packs two pooled pixels into one 128-channel GEMM pixel and spends a third of its MACs on zeros); a 64-channel tap is
 // one K chunk, and a weight stage holds TWO taps (the same 8 KB per CTA and 256 MMA cycles per barrier as CH = 128).
+// A 64-channel c2 needs a tile's T four times sooner than the 128-channel one, so here the T warps -- not the tensor pipe --
+// pace the kernel, and behind them the shared-memory data pipe (N = 64 MMAs fetch 5 KB of operands per 32 tensor cycles).
+// Hence for CH = 64: (1) the T warps only gather and drain; the landing rows, the normalised patch and the shortcut operand of
+// a tile are produced by the EPILOGUE warps, two tiles ahead, into double buffers (mbarrier hand-off, no block-wide barrier);
+// (2) the two T-warp sets take alternate batches with two im2col buffers / accumulators each; (3) one small copy of the T loop
+// with all data-independent arithmetic hoisted (instruction-cache footprint matters: a 32 KB specialised loop ran 40 % slower);
+// (4) bank-conflict-free shared-memory traffic: the patch as two column-parity planes with 96-byte rows, lanes mapped to
+// 8-cell rows, word loads + arithmetic instead of byte loads + table lookups.  profiles/r4_b1fused64.md has the measurements.
 #include <cstdlib>
 #include <type_traits>
 
@@ -79,7 +87,7 @@ struct Bf {
   static constexpr int OFF_T = W_STAGES * BF_W_BYTES;
   static constexpr int OFF_A1 = OFF_T + T_BYTES;
   static constexpr bool ALT = QUAD;                     // the two T-warp sets take alternate batches (below) instead of halves of each
-  static constexpr int NA1 = ALT ? 4 : 2;               // im2col buffers = c1 accumulators: two per set | double-buffered
+  static constexpr int NA1 = ALT ? 6 : 2;               // im2col buffers = c1 accumulators: three per set | double-buffered
   static constexpr int OFF_W1 = OFF_A1 + NA1 * BF_A1_BYTES;
   static constexpr bool EPI_PATCH = QUAD;               // the patch / shortcut operand of a tile is built by the EPILOGUE warps, two
                                                         // tiles ahead, instead of by the T warps (which pace the CH = 64 kernel)
@@ -184,9 +192,9 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
 
   __shared__ __align__(8) uint64_t bar_wfull[BF_W_MAX];
   __shared__ __align__(8) uint64_t bar_wempty[BF_W_MAX];
-  __shared__ __align__(8) uint64_t bar_a1_full[4];
-  __shared__ __align__(8) uint64_t bar_c1_full[4];
-  __shared__ __align__(8) uint64_t bar_c1_empty[4];
+  __shared__ __align__(8) uint64_t bar_a1_full[6];
+  __shared__ __align__(8) uint64_t bar_c1_full[6];
+  __shared__ __align__(8) uint64_t bar_c1_empty[6];
   __shared__ __align__(8) uint64_t bar_t_ready[2];
   __shared__ __align__(8) uint64_t bar_t_free[2];
   __shared__ __align__(8) uint64_t bar_acc_full[2];
@@ -237,7 +245,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       mbar_init(smem_u32(&bar_wfull[i]), 1);
       mbar_init(smem_u32(&bar_wempty[i]), 1);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 6; ++i) {
       mbar_init(smem_u32(&bar_a1_full[i]), ALT ? 8 : 16);      // the T warps that build a batch (one set | both) x 2 CTAs
       mbar_init(smem_u32(&bar_c1_full[i]), 1);
       mbar_init(smem_u32(&bar_c1_empty[i]), ALT ? 8 : 16);
@@ -392,14 +400,17 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       const uint64_t a1desc = make_nosw_desc(smem_base + BF_OFF_A1, 2048, 128);
       const uint64_t w1desc = make_nosw_desc(smem_base + BF_OFF_W1, NH * 16, 128);
       const long long g_total = 6 * my_tiles;
+      int ring = 0;                                     // ALT: position (g >> 1) % 3 in a set's ring of three buffers, and the
+      uint32_t rpar = 0;                                // parity of its use, ((g >> 1) / 3) & 1
       for (long long g = 0; g < g_total; ++g) {
-        // buffer / accumulator of batch g and the parity of its use: double-buffered, or (ALT) two per T-warp set
-        const int cb = ALT ? (int)((g & 1) * 2 + ((g >> 1) & 1)) : (int)(g & 1);
-        const uint32_t par = ALT ? (uint32_t)((g >> 2) & 1) : (uint32_t)((g >> 1) & 1);
+        // buffer / accumulator of batch g and the parity of its use: double-buffered, or (ALT) three per T-warp set (set = g & 1)
+        const int cb = ALT ? (int)(g & 1) * 3 + ring : (int)(g & 1);
+        const uint32_t par = ALT ? rpar : (uint32_t)((g >> 1) & 1);
+        if (ALT && (g & 1)) { if (++ring == 3) { ring = 0; rpar ^= 1u; } }
         mbar_wait(smem_u32(&bar_a1_full[cb]), par);
         mbar_wait(smem_u32(&bar_c1_empty[cb]), par ^ 1u);
         tc_fence_after();
-        const uint32_t d = tmem_base + 256u + (uint32_t)(cb * CH);
+        const uint32_t d = tmem_base + (uint32_t)(2 * CH) + (uint32_t)(cb * CH);      // after c2's two accumulators
         const uint64_t ad = a1desc + (uint64_t)(cb * (BF_A1_BYTES >> 4));
         if (!(dbg & 8)) {
           umma_pair(d, ad, w1desc, idesc, 0u);                              // k = 0..15
@@ -458,116 +469,121 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       const uint32_t r_a1full = mapa_u32(smem_u32(&bar_a1_full[0]), 0), r_c1empty = mapa_u32(smem_u32(&bar_c1_empty[0]), 0);
       const uint32_t r_tready = mapa_u32(smem_u32(&bar_t_ready[0]), 0);
       uint8_t* const a1_row = smem_gen + BF_OFF_A1 + tt * 16;
-      const uint32_t t_lane = tmem_base + 256u + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_lane = tmem_base + (uint32_t)(2 * CH) + ((uint32_t)(q * 32) << 16);
 
       const int n_my = (int)my_tiles;                   // (a cluster sees < 2^28 tiles)
-      uint32_t kc = 0;                                  // this set's batch counter: buffer set * 2 + (kc & 1), parity (kc >> 1) & 1
+      // A set's batches use a ring of THREE im2col buffers / c1 accumulators (set * 3 + 0..2).  While batch j = (l, k) is drained,
+      // the operand of batch j + 2 is gathered: the round trip gather -> both CTAs' arrives -> c1 issuer -> MMA -> commit has
+      // two iterations to complete (with two buffers and one iteration of slack the wait for it was 15 % of these warps' time),
+      // and that slack also pays for signalling "operand built" together with "accumulator drained" after ONE proxy fence per
+      // iteration instead of two.
+      int db = 0;                                       // ring position of the batch being drained,
+      uint32_t dpar = 0;                                // the parity of that use,
+      int bb = 0;                                       // ring position the next gather writes
       long long t = cluster_id;
-      // (l, k) = (-1, 2) is the prologue: only the gather of tile 0's first batch
+      // (l, k) = (-1, 1), (-1, 2): the prologue, only the gathers of tile 0's first two batches
       for (int l = -1; l < n_my; ++l) {
-        const int pb = l & 1;
         const uint32_t tf_par = (uint32_t)((l & 1) ^ 1);
 #pragma unroll 1
-        for (int k = l < 0 ? 2 : 0; k < 3; ++k) {
-          // ---- the NEXT batch's operand first (its buffer was read by the batch before this one, whose completion this thread
-          // has seen), so that its MMA overlaps this batch's drain: gather the 32 K columns of the pixel from the patch ----
-          {
-            uint32_t wn = k == 0 ? pw[1] : (k == 1 ? pw[2] : pw[0]);
-            int pbn = pb;
-            if (k == 2) {                               // first batch of the next tile: its patch (epilogue warps, two tiles ahead)
-              pbn = pb ^ 1;
-              if (l + 1 < n_my) mbar_wait(b_pready + 8u * (uint32_t)pbn, (uint32_t)(((l + 1) >> 1) & 1));
-              else wn = 0xffffffffu;                    // no next tile: no gather, no arrive
+        for (int k = l < 0 ? 1 : 0; k < 3; ++k) {
+          // ---- the operand of the batch after next: (l, 2) when k = 0, else (l + 1, k - 1); gather the 32 K columns of this
+          // thread's pixel from the patch (its buffer was read by the batch before this one, whose completion this thread has seen)
+          uint32_t wn = k == 0 ? pw[2] : (k == 1 ? pw[0] : pw[1]);
+          const int ln = k == 0 ? l : l + 1;            // tile of that batch, patch buffer ln & 1
+          if (ln >= n_my) wn = 0xffffffffu;             // no such tile: no gather, no arrive
+          else if (k == 1) mbar_wait(b_pready + 8u * (uint32_t)(ln & 1), (uint32_t)((ln >> 1) & 1));    // its patch (epilogue warps)
+          const int cbn = set * 3 + bb;
+          if (wn != 0xffffffffu) {
+            if ((wn & 0x3ffu) != W_INVALID && !(dbg & 1)) {
+              // columns x - 1 and x + 1 in the pixel's own column-parity plane, column x in the other one
+              const uint8_t* base = smem_gen + BF_OFF_P + (ln & 1) * BF_P_BYTES + ((wn & 0x3ffu) << 3);
+              const uint8_t* mid = base + ((wn & W_PC) ? 8 - BF_PQ_PLANE : BF_PQ_PLANE);
+              uint8_t* row = a1_row + cbn * BF_A1_BYTES;
+              auto ld = [](const uint8_t* q_) { return *reinterpret_cast<const uint2*>(q_); };
+              const uint2 a0 = ld(base), a1 = ld(mid), a2 = ld(base + 8);
+              const uint2 b0 = ld(base + BF_PQ_ROWB), b1 = ld(mid + BF_PQ_ROWB), b2 = ld(base + BF_PQ_ROWB + 8);
+              const uint2 c0 = ld(base + 2 * BF_PQ_ROWB), c1 = ld(mid + 2 * BF_PQ_ROWB), c2 = ld(base + 2 * BF_PQ_ROWB + 8);
+              uint4 w;
+              w.x = a0.x;
+              w.y = __byte_perm(a0.y, a1.x, 0x5410);    // lo16(a0.y) | lo16(a1.x) << 16
+              w.z = __byte_perm(a1.x, a1.y, 0x5432);    // hi16(a1.x) | lo16(a1.y) << 16
+              w.w = a2.x;
+              *reinterpret_cast<uint4*>(row) = w;
+              w.x = __byte_perm(a2.y, b0.x, 0x5410);
+              w.y = __byte_perm(b0.x, b0.y, 0x5432);
+              w.z = b1.x;
+              w.w = __byte_perm(b1.y, b2.x, 0x5410);
+              *reinterpret_cast<uint4*>(row + 2048) = w;
+              w.x = __byte_perm(b2.x, b2.y, 0x5432);
+              w.y = c0.x;
+              w.z = __byte_perm(c0.y, c1.x, 0x5410);
+              w.w = __byte_perm(c1.x, c1.y, 0x5432);
+              *reinterpret_cast<uint4*>(row + 2 * 2048) = w;
+              w.x = c2.x;
+              w.y = (c2.y & 0xffffu) | (kOne << 16);     // k = 27, 28: 1.0 (bias hi / lo)
+              w.z = kOne;
+              w.w = 0u;
+              *reinterpret_cast<uint4*>(row + 3 * 2048) = w;
             }
-            if (wn != 0xffffffffu) {
-              if ((wn & 0x3ffu) != W_INVALID && !(dbg & 1)) {
-                // columns x - 1 and x + 1 in the pixel's own column-parity plane, column x in the other one
-                const uint8_t* base = smem_gen + BF_OFF_P + pbn * BF_P_BYTES + ((wn & 0x3ffu) << 3);
-                const uint8_t* mid = base + ((wn & W_PC) ? 8 - BF_PQ_PLANE : BF_PQ_PLANE);
-                uint8_t* row = a1_row + (set * 2 + (int)((kc + (l < 0 ? 0u : 1u)) & 1u)) * BF_A1_BYTES;
-                auto ld = [](const uint8_t* q) { return *reinterpret_cast<const uint2*>(q); };
-                const uint2 a0 = ld(base), a1 = ld(mid), a2 = ld(base + 8);
-                const uint2 b0 = ld(base + BF_PQ_ROWB), b1 = ld(mid + BF_PQ_ROWB), b2 = ld(base + BF_PQ_ROWB + 8);
-                const uint2 c0 = ld(base + 2 * BF_PQ_ROWB), c1 = ld(mid + 2 * BF_PQ_ROWB), c2 = ld(base + 2 * BF_PQ_ROWB + 8);
-                uint4 w;
-                w.x = a0.x;
-                w.y = __byte_perm(a0.y, a1.x, 0x5410);  // lo16(a0.y) | lo16(a1.x) << 16
-                w.z = __byte_perm(a1.x, a1.y, 0x5432);  // hi16(a1.x) | lo16(a1.y) << 16
-                w.w = a2.x;
-                *reinterpret_cast<uint4*>(row) = w;
-                w.x = __byte_perm(a2.y, b0.x, 0x5410);
-                w.y = __byte_perm(b0.x, b0.y, 0x5432);
-                w.z = b1.x;
-                w.w = __byte_perm(b1.y, b2.x, 0x5410);
-                *reinterpret_cast<uint4*>(row + 2048) = w;
-                w.x = __byte_perm(b2.x, b2.y, 0x5432);
-                w.y = c0.x;
-                w.z = __byte_perm(c0.y, c1.x, 0x5410);
-                w.w = __byte_perm(c1.x, c1.y, 0x5432);
-                *reinterpret_cast<uint4*>(row + 2 * 2048) = w;
-                w.x = c2.x;
-                w.y = (c2.y & 0xffffu) | (kOne << 16);   // k = 27, 28: 1.0 (bias hi / lo)
-                w.z = kOne;
-                w.w = 0u;
-                *reinterpret_cast<uint4*>(row + 3 * 2048) = w;
-              }
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                mbar_arrive_cluster(r_a1full + 8u * (uint32_t)(set * 2 + (int)((kc + (l < 0 ? 0u : 1u)) & 1u)));
-                // after its last gather of a tile this warp is done with the patch buffer
-                if (k == 1) mbar_arrive(b_pfree + 8u * (uint32_t)pb);
-              }
-            }
+            if (++bb == 3) bb = 0;
           }
-          if (l < 0) break;
           // ---- this batch: TMEM accumulator cb -> relu / convert -> T cells (all 64 channels) ----
           const uint32_t w = k == 0 ? pw[0] : (k == 1 ? pw[1] : pw[2]);
-          const int cb = set * 2 + (int)(kc & 1u);
-          mbar_wait(b_c1full + 8u * (uint32_t)cb, (kc >> 1) & 1u);          // the batch is in TMEM
-          tc_fence_after();
-          if (w & W_FIRST) mbar_wait(b_tfree + ((w & W_UNIT1) ? 8u : 0u), tf_par);   // c2 is done with this half of T
-          if (!(w & W_SKIP) && !(dbg & 2)) {
-            uint32_t r[64];
-            tmem_ld32(t_lane + (uint32_t)(cb * CH), r);
-            tmem_ld32(t_lane + (uint32_t)(cb * CH) + 32u, r + 32);
-            tmem_ld_wait();
-            if ((w & 0x3ffu) != W_INVALID) {
-              const bool in_img = !((w >> (23 + (int)(t & 3))) & 1u);       // a cell outside the image is conv padding = zero
-              uint8_t* cell = smem_gen + BF_OFF_T + (((w >> 10) & 0x1fffu) << 4);
+          const int cb = set * 3 + db;
+          if (l >= 0) {
+            mbar_wait(b_c1full + 8u * (uint32_t)cb, dpar);                  // the batch is in TMEM
+            tc_fence_after();
+            if (w & W_FIRST) mbar_wait(b_tfree + ((w & W_UNIT1) ? 8u : 0u), tf_par);   // c2 is done with this half of T
+            if (!(w & W_SKIP) && !(dbg & 2)) {
+              uint32_t r[64];
+              tmem_ld32(t_lane + (uint32_t)(cb * CH), r);
+              tmem_ld32(t_lane + (uint32_t)(cb * CH) + 32u, r + 32);
+              tmem_ld_wait();
+              if ((w & 0x3ffu) != W_INVALID) {
+                const bool in_img = !((w >> (23 + (int)(t & 3))) & 1u);     // a cell outside the image is conv padding = zero
+                uint8_t* cell = smem_gen + BF_OFF_T + (((w >> 10) & 0x1fffu) << 4);
 #pragma unroll
-              for (int gq = 0; gq < 8; ++gq) {
-                uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-                if (in_img) {
-                  pk.x = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]));
-                  pk.y = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
-                  pk.z = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
-                  pk.w = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
+                for (int gq = 0; gq < 8; ++gq) {
+                  uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                  if (in_img) {
+                    pk.x = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]));
+                    pk.y = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
+                    pk.z = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+                    pk.w = pack_relu_h2<F16>(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
+                  }
+                  if (F16) vmaxw = __vmaxu2(__vmaxu2(vmaxw, pk.x), __vmaxu2(__vmaxu2(pk.y, pk.z), pk.w));
+                  *reinterpret_cast<uint4*>(cell + gq * BF_K8) = pk;
                 }
-                if (F16) vmaxw = __vmaxu2(__vmaxu2(vmaxw, pk.x), __vmaxu2(__vmaxu2(pk.y, pk.z), pk.w));
-                *reinterpret_cast<uint4*>(cell + gq * BF_K8) = pk;
-              }
-              if (p.dbg_t && in_img) {                  // tests only: the same 16-bit values to global memory
-                const int rr = set + 2 * k, uu = rr / 3;
-                int R, C, pc;
-                bf_pixel<true>(s, 1 - uu, rr - 3 * uu, tt, R, C, pc);
-                const int Y = 32 * ((int)(t & 3) >> 1) + 2 * R - uu, X = 32 * (int)(t & 1) + 16 * s - 1 + 2 * C + pc;
+                if (p.dbg_t && in_img) {                // tests only: the same 16-bit values to global memory
+                  const int rr = set + 2 * k, uu = rr / 3;
+                  int R, C, pc;
+                  bf_pixel<true>(s, 1 - uu, rr - 3 * uu, tt, R, C, pc);
+                  const int Y = 32 * ((int)(t & 3) >> 1) + 2 * R - uu, X = 32 * (int)(t & 1) + 16 * s - 1 + 2 * C + pc;
 #pragma unroll 1
-                for (int gq = 0; gq < 8; ++gq)
-                  *reinterpret_cast<uint4*>(p.dbg_t + ((((t >> 2) * IMG + Y) * IMG + X) * CH + gq * 8)) =
-                      *reinterpret_cast<const uint4*>(cell + gq * BF_K8);
+                  for (int gq = 0; gq < 8; ++gq)
+                    *reinterpret_cast<uint4*>(p.dbg_t + ((((t >> 2) * IMG + Y) * IMG + X) * CH + gq * 8)) =
+                        *reinterpret_cast<const uint4*>(cell + gq * BF_K8);
+                }
               }
             }
+            tc_fence_before();
           }
-          tc_fence_before();
-          fence_proxy_async_smem();                     // T cells -> visible to the tensor core
+          // ---- one fence for the im2col rows and the T cells (both are read by the tensor core), then every signal ----
+          fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive_cluster(r_c1empty + 8u * (uint32_t)cb);
-            // the unit is complete once every T warp of both CTAs has said so
-            if (w & W_LAST) mbar_arrive_cluster(r_tready + ((w & W_UNIT1) ? 8u : 0u));
+            if (wn != 0xffffffffu) {
+              mbar_arrive_cluster(r_a1full + 8u * (uint32_t)cbn);
+              // after its last gather of a tile (batch (l, 2), gathered at k = 0) this warp is done with the patch buffer
+              if (k == 0) mbar_arrive(b_pfree + 8u * (uint32_t)(l & 1));
+            }
+            if (l >= 0) {
+              mbar_arrive_cluster(r_c1empty + 8u * (uint32_t)cb);
+              // the unit is complete once every T warp of both CTAs has said so
+              if (w & W_LAST) mbar_arrive_cluster(r_tready + ((w & W_UNIT1) ? 8u : 0u));
+            }
           }
-          ++kc;
+          if (l >= 0 && ++db == 3) { db = 0; dpar ^= 1u; }
         }
         if (l >= 0) t += n_clusters;
       }
@@ -684,7 +700,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
         if ((b < 2 || q < 1) && !(dbg & 2)) {            // the third batch of a unit holds 16 pixels: lane quadrant 0
           uint8_t* cell = smem_gen + BF_OFF_T + ((pr * 2 + pc) * G + (ch0 >> 3)) * BF_K8 + R * BF_ROW + C * 16;
           const int Y = 2 * R + pr - 1, X = 16 * s - 1 + 2 * C + pc;     // pixel of the image (the halo cells are never computed)
-          const uint32_t taddr = tmem_base + 256u + (uint32_t)(cb * CH + ch0) + ((uint32_t)(q * 32) << 16);
+          const uint32_t taddr = tmem_base + (uint32_t)(2 * CH) + (uint32_t)(cb * CH + ch0) + ((uint32_t)(q * 32) << 16);
           uint32_t r[NCH];
           tmem_ld32(taddr, r);
           tmem_ld32(taddr + 32u, r + 32);

@@ -259,22 +259,51 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
     c->convs.assign(n_convs, ConvLayer());
   }
   const float* sig = c->sigma.as<float>();
+  // bias copies, bias sums, fp32 W / sigma vectors: collected here and run as ONE launch (vec_jobs) ahead of the weight packs
+  std::vector<VecJob> vj;
+  auto vjob = [&](void* out, const float* a, const float* b2, const float* sg, int n) {
+    vj.push_back(VecJob{(float*)out, a, b2, sg, n, 0});
+  };
   for (int i = 0; i < n_convs; ++i) {
     ConvLayer& l = c->convs[i];
     l.cout = ls[i].cout; l.cin = ls[i].cin; l.ks = ls[i].ks; l.stride = 1; l.has_bias = true;
     int K = l.cin * l.ks * l.ks;
     l.kpad = (K + 63) / 64 * 64;
     { int rc = l.bias.ensure(sizeof(float) * l.cout); if (rc) return rc; }
-    SDG_CUDA(cudaMemcpyAsync(l.bias.p, b[i], sizeof(float) * l.cout, cudaMemcpyDeviceToDevice, s));
+    vjob(l.bias.p, b[i], nullptr, nullptr, l.cout);
     if (precision == SDG_PREC_FP32) {
       { int rc = l.w32.ensure(sizeof(float) * K * l.cout); if (rc) return rc; }
       int rc = pack_conv_fp32(W[i], sig + i, nullptr, l.w32.as<float>(), l.cout, l.cin, l.ks, s);
       if (rc) return rc;
     }
   }
+  c->head_len = ndf;
+  { int rc = c->head_w.ensure(sizeof(float) * ndf); if (rc) return rc; }
+  { int rc = c->head_b.ensure(sizeof(float)); if (rc) return rc; }
+  vjob(c->head_w.p, W[n_convs], nullptr, sig + n_convs, ndf);
+  vjob(c->head_b.p, b[n_convs], nullptr, nullptr, 1);
+  if (precision != SDG_PREC_FP32) {
+    // biases of c2 and c_sc summed; the 1x1 shortcut of DBlockOptimized kept as fp32 [Cout][3] / sigma
+    for (size_t bi = 0; bi < c->blocks.size(); ++bi) {
+      const int i2 = c->block_first_conv[bi] + 1, isc = i2 + 1;
+      ConvLayer& l2 = c->convs[i2];
+      { int rc = l2.bias_sum.ensure(sizeof(float) * l2.cout); if (rc) return rc; }
+      if (c->block_has_sc[bi]) {
+        ConvLayer& lsc = c->convs[isc];
+        if (c->blocks[bi].kind != 1) {
+          { int rc = lsc.w3.ensure(sizeof(float) * 3 * lsc.cout); if (rc) return rc; }
+          vjob(lsc.w3.p, W[isc], nullptr, sig + isc, 3 * lsc.cout);
+        }
+        vjob(l2.bias_sum.p, b[i2], b[isc], nullptr, l2.cout);
+      } else {
+        vjob(l2.bias_sum.p, b[i2], nullptr, nullptr, l2.cout);
+      }
+    }
+  }
+  { int rc = vec_jobs(vj.data(), (int)vj.size(), s); if (rc) return rc; }
   if (precision != SDG_PREC_FP32) {
     // 16-bit path: c1 as is; c2 with the block's 1x1 shortcut conv folded in as extra K columns (res blocks) or
-    // kept as fp32 [Cout][3] for the 3-FMA epilogue (DBlockOptimized); biases of c2 and c_sc summed.
+    // kept as fp32 [Cout][3] for the 3-FMA epilogue (DBlockOptimized).
     const int f16 = precision == SDG_PREC_FP16;
     for (size_t bi = 0; bi < c->blocks.size(); ++bi) {
       const int i1 = c->block_first_conv[bi], i2 = i1 + 1, isc = i1 + 2;
@@ -300,7 +329,6 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
         int rc = pack_conv_h16(W[i2], sig + i2, nullptr, l2.w16.as<h16>(), l2.cout, l2.cin, l2.kpad, l2.ks, f16, l2.ktot, 0, s);
         if (rc) return rc;
       }
-      { int rc = l2.bias_sum.ensure(sizeof(float) * l2.cout); if (rc) return rc; }
       if (has_sc) {
         ConvLayer& lsc = c->convs[isc];
         if (fold && l2.pool4) {
@@ -310,15 +338,7 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
           int rc = pack_conv_h16(W[isc], sig + isc, nullptr, l2.w16.as<h16>(), lsc.cout, lsc.cin, lsc.kpad, 1, f16, l2.ktot,
                                  l2.kpad, s);
           if (rc) return rc;
-        } else {
-          { int rc = lsc.w3.ensure(sizeof(float) * 3 * lsc.cout); if (rc) return rc; }
-          int rc = scale_vec(W[isc], sig + isc, lsc.w3.as<float>(), 3 * lsc.cout, s);
-          if (rc) return rc;
         }
-        int rc = add_vec(l2.bias.as<float>(), lsc.bias.as<float>(), l2.bias_sum.as<float>(), l2.cout, s);
-        if (rc) return rc;
-      } else {
-        SDG_CUDA(cudaMemcpyAsync(l2.bias_sum.p, l2.bias.p, sizeof(float) * l2.cout, cudaMemcpyDeviceToDevice, s));
       }
       // ---- one-kernel block 1 of SNGAN-32 / SNGAN-64: the same c2 weights with the shortcut / bias chunk appended ----
       if (c->blocks[bi].kind == 0 && l2.pool4 && l2.cout == l2.cin && l1.cin == 3 &&
@@ -361,11 +381,6 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
       }
     }
   }
-  c->head_len = ndf;
-  { int rc = c->head_w.ensure(sizeof(float) * ndf); if (rc) return rc; }
-  { int rc = c->head_b.ensure(sizeof(float)); if (rc) return rc; }
-  { int rc = scale_vec(W[n_convs], sig + n_convs, c->head_w.as<float>(), ndf, s); if (rc) return rc; }
-  SDG_CUDA(cudaMemcpyAsync(c->head_b.p, b[n_convs], sizeof(float), cudaMemcpyDeviceToDevice, s));
   c->loaded = true;
   return 0;
 }

@@ -119,6 +119,11 @@ int pack_pool4_sc_h16(const float* Wsc, const float* sigma, h16* wb, int Cout, i
 // output pixels 2x and 2x+1 of a conv with x-stride `shift` share one window of txs + shift input columns
 int pack_superpix_h16(const h16* src, h16* dst, int Cout, int Cin, int ty, int txs, int shift, cudaStream_t s);
 int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);          // out = a + b
+// several small vector operations in one launch: out = (a [+ b]) [/ sigma[0]]; b and sigma may be null.  Jobs must not read
+// each other's outputs.
+struct VecJob { float* out; const float* a; const float* b; const float* sigma; int n; int pad; };
+constexpr int kMaxVecJobs = 40;
+int vec_jobs(const VecJob* jobs, int n, cudaStream_t s);
 int scale_vec(const float* in, const float* sigma, float* out, int n, cudaStream_t s);   // out = in / sigma
 // BatchNorm(eval) folding: scale[o] = gamma/sqrt(var+eps), shift[o] = beta - mean*scale
 // mul scales both outputs (DCGAN tensor-core path: 1/sqrt(2) cancels the gain of the FusedLeakyReLU epilogue)
