@@ -305,6 +305,16 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
     // 16-bit path: c1 as is; c2 with the block's 1x1 shortcut conv folded in as extra K columns (res blocks) or
     // kept as fp32 [Cout][3] for the 3-FMA epilogue (DBlockOptimized).
     const int f16 = precision == SDG_PREC_FP16;
+    // the W / sigma packs are collected and run as ONE launch (pack_jobs); a consumer of packed weights flushes the list first
+    std::vector<PackJob> pj;
+    auto pjob = [&](int type, const float* Wp, const float* sg, h16* wb, int Cin_, int Kpad_, int taps, int ld, int col0, int total) {
+      pj.push_back(PackJob{Wp, sg, wb, type, Cin_, Kpad_, taps, ld, col0, total, 0});
+    };
+    auto pflush = [&]() -> int {
+      int rc = pj.empty() ? 0 : pack_jobs(pj.data(), (int)pj.size(), f16, s);
+      pj.clear();
+      return rc;
+    };
     for (size_t bi = 0; bi < c->blocks.size(); ++bi) {
       const int i1 = c->block_first_conv[bi], i2 = i1 + 1, isc = i1 + 2;
       const bool has_sc = c->block_has_sc[bi] != 0;
@@ -312,8 +322,7 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
       ConvLayer& l2 = c->convs[i2];
       l1.ktot = l1.kpad;
       { int rc = l1.w16.ensure(sizeof(h16) * (size_t)l1.ktot * l1.cout); if (rc) return rc; }
-      { int rc = pack_conv_h16(W[i1], sig + i1, nullptr, l1.w16.as<h16>(), l1.cout, l1.cin, l1.kpad, l1.ks, f16, l1.ktot, 0, s);
-        if (rc) return rc; }
+      pjob(PACK_CONV, W[i1], sig + i1, l1.w16.as<h16>(), l1.cin, l1.kpad, l1.ks * l1.ks, l1.ktot, 0, l1.cout * l1.kpad);
       const bool fold = has_sc && c->blocks[bi].kind == 1;
       // pooled blocks: conv3x3 + avg_pool2d(2) == a 4x4 stride-2 conv with summed weights (16/36 of the MACs)
       static const int use_pool4 = getenv("SDG_POOL4") ? atoi(getenv("SDG_POOL4")) : 1;
@@ -322,30 +331,21 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
       const int main_cols = l2.pool4 ? 16 * l2.cin : l2.kpad;
       l2.ktot = main_cols + sc_cols;
       { int rc = l2.w16.ensure(sizeof(h16) * (size_t)l2.ktot * l2.cout); if (rc) return rc; }
-      if (l2.pool4) {
-        int rc = pack_pool4_h16(W[i2], sig + i2, l2.w16.as<h16>(), l2.cout, l2.cin, f16, l2.ktot, s);
-        if (rc) return rc;
-      } else {
-        int rc = pack_conv_h16(W[i2], sig + i2, nullptr, l2.w16.as<h16>(), l2.cout, l2.cin, l2.kpad, l2.ks, f16, l2.ktot, 0, s);
-        if (rc) return rc;
-      }
+      if (l2.pool4) pjob(PACK_POOL4, W[i2], sig + i2, l2.w16.as<h16>(), l2.cin, 0, 9, l2.ktot, 0, l2.cout * 16 * l2.cin);
+      else pjob(PACK_CONV, W[i2], sig + i2, l2.w16.as<h16>(), l2.cin, l2.kpad, l2.ks * l2.ks, l2.ktot, 0, l2.cout * l2.kpad);
       if (has_sc) {
         ConvLayer& lsc = c->convs[isc];
-        if (fold && l2.pool4) {
-          int rc = pack_pool4_sc_h16(W[isc], sig + isc, l2.w16.as<h16>(), lsc.cout, lsc.cin, lsc.kpad, f16, l2.ktot, main_cols, s);
-          if (rc) return rc;
-        } else if (fold) {
-          int rc = pack_conv_h16(W[isc], sig + isc, nullptr, l2.w16.as<h16>(), lsc.cout, lsc.cin, lsc.kpad, 1, f16, l2.ktot,
-                                 l2.kpad, s);
-          if (rc) return rc;
-        }
+        if (fold && l2.pool4)
+          pjob(PACK_POOL4_SC, W[isc], sig + isc, l2.w16.as<h16>(), lsc.cin, lsc.kpad, 1, l2.ktot, main_cols, lsc.cout * 4 * lsc.kpad);
+        else if (fold)
+          pjob(PACK_CONV, W[isc], sig + isc, l2.w16.as<h16>(), lsc.cin, lsc.kpad, 1, l2.ktot, l2.kpad, lsc.cout * lsc.kpad);
       }
       // ---- one-kernel block 1 of SNGAN-32 / SNGAN-64: the same c2 weights with the shortcut / bias chunk appended ----
       if (c->blocks[bi].kind == 0 && l2.pool4 && l2.cout == l2.cin && l1.cin == 3 &&
           ((arch == SDG_ARCH_SNGAN32 && l2.cout == 128) || (arch == SDG_ARCH_SNGAN64 && l2.cout == 64))) {
         const int ch = l2.cout;
         { int rc = l2.w16f.ensure(sizeof(h16) * (size_t)b1_fused_w2_elems(ch)); if (rc) return rc; }
-        { int rc = pack_pool4_h16(W[i2], sig + i2, l2.w16f.as<h16>(), l2.cout, l2.cin, f16, b1_fused_w2_ld(ch), s); if (rc) return rc; }
+        pjob(PACK_POOL4, W[i2], sig + i2, l2.w16f.as<h16>(), l2.cin, 0, 9, b1_fused_w2_ld(ch), 0, l2.cout * 16 * l2.cin);
         { int rc = b1_fused_pack(nullptr, c->convs[isc].w3.as<float>(), l2.bias_sum.as<float>(), l2.w16f.as<h16>(), ch, f16, s);
           if (rc) return rc; }
       }
@@ -367,6 +367,7 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
       if (use_superpix && c->blocks[bi].kind == 0 && l2.cout == 64 && l2.cin == 64 && l2.pool4) {
         // block1.c2 in the 4x4 stride-2 form: 4 x 4 taps, x-stride 2 -> 4 x 6 taps, x-stride 4
         { int rc = l2.w16s.ensure(sizeof(h16) * 128 * 4 * 6 * l2.cin); if (rc) return rc; }
+        { int rc = pflush(); if (rc) return rc; }        // reads the packed l2.w16
         { int rc = pack_superpix_h16(l2.w16.as<h16>(), l2.w16s.as<h16>(), 64, l2.cin, 4, 4, 2, s); if (rc) return rc; }
         { int rc = dup(l2.bias2, l2.bias_sum.as<float>(), 64); if (rc) return rc; }
         { int rc = dup(c->convs[isc].w3s, c->convs[isc].w3.as<float>(), 64 * 3); if (rc) return rc; }
@@ -375,11 +376,13 @@ extern "C" int sdg_sngan_load(sdg_ctx* c, int arch, int n_layers, const float* c
       if (use_superpix && c->blocks[bi].kind == 1 && l1.cout == 64 && l1.cin == 64) {
         // a plain 3x3 conv: 3 x 3 taps -> 3 x 4 taps, x-stride 2
         { int rc = l1.w16s.ensure(sizeof(h16) * 128 * 3 * 4 * l1.cin); if (rc) return rc; }
+        { int rc = pflush(); if (rc) return rc; }        // reads the packed l1.w16
         { int rc = pack_superpix_h16(l1.w16.as<h16>(), l1.w16s.as<h16>(), 64, l1.cin, 3, 3, 1, s); if (rc) return rc; }
         { int rc = dup(l1.bias2, l1.bias.as<float>(), 64); if (rc) return rc; }
         l1.superpix = 1;
       }
     }
+    { int rc = pflush(); if (rc) return rc; }
   }
   c->loaded = true;
   return 0;

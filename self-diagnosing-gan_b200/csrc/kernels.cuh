@@ -124,6 +124,12 @@ int add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s); 
 struct VecJob { float* out; const float* a; const float* b; const float* sigma; int n; int pad; };
 constexpr int kMaxVecJobs = 40;
 int vec_jobs(const VecJob* jobs, int n, cudaStream_t s);
+// several 16-bit weight packs (W / sigma) in one launch: PACK_CONV = pack_conv_h16 (scale = null, mul = 1, cin_w = Cin; Kpad, taps,
+// col0 as there), PACK_POOL4 = pack_pool4_h16, PACK_POOL4_SC = pack_pool4_sc_h16 (Cin = Csc, Kpad = sc_pad).  total = elements.
+enum { PACK_CONV = 0, PACK_POOL4 = 1, PACK_POOL4_SC = 2 };
+struct PackJob { const float* W; const float* sigma; h16* wb; int type, Cin, Kpad, taps, ld, col0, total, pad; };
+constexpr int kMaxPackJobs = 16;
+int pack_jobs(const PackJob* jobs, int n, int f16, cudaStream_t s);
 int scale_vec(const float* in, const float* sigma, float* out, int n, cudaStream_t s);   // out = in / sigma
 // BatchNorm(eval) folding: scale[o] = gamma/sqrt(var+eps), shift[o] = beta - mean*scale
 // mul scales both outputs (DCGAN tensor-core path: 1/sqrt(2) cancels the gain of the FusedLeakyReLU epilogue)

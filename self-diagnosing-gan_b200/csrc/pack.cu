@@ -119,6 +119,27 @@ int pack_conv_fp32(const float* W, const float* sigma, const float* scale, float
   return 0;
 }
 
+// element i of a packed [Cout][Kpad] conv weight (the body of pack_conv_h16_kernel and of job type 0 of pack_jobs_kernel)
+template <bool F16>
+__device__ __forceinline__ void pack_conv_h16_elem(const float* __restrict__ W, bool has_sigma, float sg, const float* __restrict__ scale,
+                                                   h16* __restrict__ wb, int Cin, int Kpad, int taps, int ld, int col0, float mul,
+                                                   int cin_w, int* ovf, int i) {
+  int k = i % Kpad;
+  int o = i / Kpad;
+  float w = 0.f;
+  if (k < taps * Cin) {
+    int tap = k / Cin, c = k - tap * Cin;
+    if (c < cin_w) {                             // cin_w < Cin: the packed layout pads the input channels with zeros
+      w = W[((int64_t)o * cin_w + c) * taps + tap];
+      if (has_sigma) w = w / sg;
+      if (scale) w = w * scale[o];
+      if (mul != 1.0f) w = w * mul;
+    }
+  }
+  if (F16 && !(fabsf(w) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_WEIGHT);
+  wb[(int64_t)o * ld + col0 + k] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
+}
+
 template <bool F16>
 __global__ void __launch_bounds__(256)
 pack_conv_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigma, const float* __restrict__ scale,
@@ -126,22 +147,8 @@ pack_conv_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigm
                      int* ovf) {
   const int total = Cout * Kpad;
   const float sg = sigma ? sigma[0] : 1.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int k = i % Kpad;
-    int o = i / Kpad;
-    float w = 0.f;
-    if (k < taps * Cin) {
-      int tap = k / Cin, c = k - tap * Cin;
-      if (c < cin_w) {                           // cin_w < Cin: the packed layout pads the input channels with zeros
-        w = W[((int64_t)o * cin_w + c) * taps + tap];
-        if (sigma) w = w / sg;
-        if (scale) w = w * scale[o];
-        if (mul != 1.0f) w = w * mul;
-      }
-    }
-    if (F16 && !(fabsf(w) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_WEIGHT);
-    wb[(int64_t)o * ld + col0 + k] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
-  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    pack_conv_h16_elem<F16>(W, sigma != nullptr, sg, scale, wb, Cin, Kpad, taps, ld, col0, mul, cin_w, ovf, i);
 }
 
 int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* wb, int Cout, int Cin, int Kpad,
@@ -159,27 +166,32 @@ int pack_conv_h16(const float* W, const float* sigma, const float* scale, h16* w
 }
 
 template <bool F16>
+__device__ __forceinline__ void pack_pool4_h16_elem(const float* __restrict__ W, float sg, h16* __restrict__ wb, int Cin, int ld,
+                                                    int* ovf, int i) {
+  const int c = i % Cin;
+  const int r = i / Cin;
+  const int t = r & 15, o = r >> 4;
+  const int a = t >> 2, b = t & 3;
+  float acc = 0.f;
+  for (int ky = a - 1; ky <= a; ++ky) {
+    if (ky < 0 || ky > 2) continue;
+    for (int kx = b - 1; kx <= b; ++kx) {
+      if (kx < 0 || kx > 2) continue;
+      acc += W[((int64_t)o * Cin + c) * 9 + ky * 3 + kx] / sg;         // (W / sigma) as the reference forms it
+    }
+  }
+  if (F16 && !(fabsf(0.25f * acc) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_WEIGHT);
+  wb[(int64_t)o * ld + t * Cin + c] = (h16)(pack_h2<F16>(0.25f * acc, 0.f) & 0xffffu);
+}
+
+template <bool F16>
 __global__ void __launch_bounds__(256)
 pack_pool4_h16_kernel(const float* __restrict__ W, const float* __restrict__ sigma, h16* __restrict__ wb, int Cout, int Cin,
                       int ld, int* ovf) {
   const int total = Cout * 16 * Cin;
   const float sg = sigma[0];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i % Cin;
-    const int r = i / Cin;
-    const int t = r & 15, o = r >> 4;
-    const int a = t >> 2, b = t & 3;
-    float acc = 0.f;
-    for (int ky = a - 1; ky <= a; ++ky) {
-      if (ky < 0 || ky > 2) continue;
-      for (int kx = b - 1; kx <= b; ++kx) {
-        if (kx < 0 || kx > 2) continue;
-        acc += W[((int64_t)o * Cin + c) * 9 + ky * 3 + kx] / sg;       // (W / sigma) as the reference forms it
-      }
-    }
-    if (F16 && !(fabsf(0.25f * acc) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_WEIGHT);
-    wb[(int64_t)o * ld + t * Cin + c] = (h16)(pack_h2<F16>(0.25f * acc, 0.f) & 0xffffu);
-  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    pack_pool4_h16_elem<F16>(W, sg, wb, Cin, ld, ovf, i);
 }
 
 int pack_pool4_h16(const float* W, const float* sigma, h16* wb, int Cout, int Cin, int f16, int ld, cudaStream_t s) {
@@ -190,19 +202,24 @@ int pack_pool4_h16(const float* W, const float* sigma, h16* wb, int Cout, int Ci
 }
 
 template <bool F16>
+__device__ __forceinline__ void pack_pool4_sc_h16_elem(const float* __restrict__ Wsc, float sg, h16* __restrict__ wb, int Csc,
+                                                       int sc_pad, int ld, int col0, int* ovf, int i) {
+  const int c = i % sc_pad;
+  const int r = i / sc_pad;
+  const int t = r & 3, o = r >> 2;
+  const float w = c < Csc ? 0.25f * (Wsc[(int64_t)o * Csc + c] / sg) : 0.f;
+  if (F16 && !(fabsf(w) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_WEIGHT);
+  wb[(int64_t)o * ld + col0 + t * sc_pad + c] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
+}
+
+template <bool F16>
 __global__ void __launch_bounds__(256)
 pack_pool4_sc_h16_kernel(const float* __restrict__ Wsc, const float* __restrict__ sigma, h16* __restrict__ wb, int Cout,
                          int Csc, int sc_pad, int ld, int col0, int* ovf) {
   const int total = Cout * 4 * sc_pad;
   const float sg = sigma[0];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i % sc_pad;
-    const int r = i / sc_pad;
-    const int t = r & 3, o = r >> 2;
-    const float w = c < Csc ? 0.25f * (Wsc[(int64_t)o * Csc + c] / sg) : 0.f;
-    if (F16 && !(fabsf(w) <= kF16Max)) range_flag_set(ovf, SDG_RANGE_WEIGHT);
-    wb[(int64_t)o * ld + col0 + t * sc_pad + c] = (h16)(pack_h2<F16>(w, 0.f) & 0xffffu);
-  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    pack_pool4_sc_h16_elem<F16>(Wsc, sg, wb, Csc, sc_pad, ld, col0, ovf, i);
 }
 
 int pack_pool4_sc_h16(const float* Wsc, const float* sigma, h16* wb, int Cout, int Csc, int sc_pad, int f16, int ld, int col0,
@@ -222,6 +239,38 @@ __global__ void scale_vec_kernel(const float* __restrict__ in, const float* __re
 __global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + b[i];
+}
+
+// The 16-bit weight packs of one SNGAN load (W / sigma of every conv, 11 launches for SNGAN-32 before) as ONE launch:
+// blockIdx.y = job, grid-stride over its elements in x; the element bodies are the standalone kernels' own.
+struct PackJobTable { int n; int pad; PackJob j[kMaxPackJobs]; };
+template <bool F16>
+__global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ PackJobTable tab, int* ovf) {
+  const PackJob& J = tab.j[blockIdx.y];
+  const float sg = J.sigma[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < J.total; i += gridDim.x * blockDim.x) {
+    if (J.type == PACK_CONV) pack_conv_h16_elem<F16>(J.W, true, sg, nullptr, J.wb, J.Cin, J.Kpad, J.taps, J.ld, J.col0, 1.0f, J.Cin, ovf, i);
+    else if (J.type == PACK_POOL4) pack_pool4_h16_elem<F16>(J.W, sg, J.wb, J.Cin, J.ld, ovf, i);
+    else pack_pool4_sc_h16_elem<F16>(J.W, sg, J.wb, J.Cin, J.Kpad, J.ld, J.col0, ovf, i);
+  }
+}
+
+int pack_jobs(const PackJob* jobs, int n, int f16, cudaStream_t s) {
+  for (int o = 0; o < n; o += kMaxPackJobs) {
+    PackJobTable tab;
+    tab.n = n - o < kMaxPackJobs ? n - o : kMaxPackJobs; tab.pad = 0;
+    int most = 1;
+    for (int i = 0; i < tab.n; ++i) {
+      tab.j[i] = jobs[o + i];
+      SDG_REQUIRE(tab.j[i].W && tab.j[i].sigma && tab.j[i].wb && tab.j[i].total >= 0, SDG_E_INVALID, "pack_jobs: job %d has a null pointer", o + i);
+      if (tab.j[i].total > most) most = tab.j[i].total;
+    }
+    dim3 grid(stream_grid(most, 256), (unsigned)tab.n);
+    if (grid.x > 64) grid.x = 64;                       // x blocks per job: the largest (262 144 elements) takes 16 elements per thread
+    if (f16) { SDG_LAUNCH(pack_jobs_kernel<true>, grid, 256, 0, s, tab, t_range_flag); }
+    else { SDG_LAUNCH(pack_jobs_kernel<false>, grid, 256, 0, s, tab, t_range_flag); }
+  }
+  return 0;
 }
 
 // out = (a [+ b]) [/ sigma[0]] for up to kMaxVecJobs small vectors in ONE launch (block = job): the bias copies, bias sums and
