@@ -70,10 +70,10 @@ WORKLOADS = {
                            "the bytes, halo recomputed) -> ReLU -> c2 (3x3 64->64 @64x64 + avg-pool, run as the algebraically equal 4x4 "
                            "stride-2 conv) + image shortcut -> ReLU; 24.5% of the reference FLOPs; CTA pairs (tcgen05.mma.cta_group::2, "
                            "M = 256 pixels x N = 64 channels, no structural zeros), relu(c1(x)) built and consumed in shared memory; "
-                           "paced by the CUDA-core warps that build that tile, not by the tensor pipe (profiles/r3_b1fused64.md)",
+                           "paced by the CUDA-core warps that build that tile and the shared-memory operand fetch of N = 64 MMAs, not by the tensor pipe (profiles/r3_b1fused64.md, r4_b1fused64.md)",
                     dom_ref_flop=2.0 * 9 * 64 * 64 * 4096 + 2.0 * 27 * 64 * 4096, dom_exec_useful=1.0, cpu_sample=2048,
-                    traffic=((100.9e6 + 1016.5e6) / 8192.0, "profiles/r3_launches_sngan64_fused.md (8192 samples: 100.9 MB read + "
-                             "1016.5 MB written to DRAM during the launch = 136 KB/sample; algorithmic 12 KiB in + 128 KiB out per "
+                    traffic=((101.1e6 + 1020.7e6) / 8192.0, "profiles/r4_ncu_full_b1fused64_summary.txt (8192 samples: 101.1 MB read + "
+                             "1020.7 MB written to DRAM during the launch = 137 KB/sample; algorithmic 12 KiB in + 128 KiB out per "
                              "sample = 143 KB; the two kernels this one replaces moved 1.19 MB/sample)"),
                     eager=dict(ref_batch=64, ref_n=16_384, best_batch=1024, best_n=16_384)),
     "stylegan2": dict(arch="stylegan2", size=256, n_total=2048, n_weak=2048, key="ldr_conf_3.0_ratio_50", flop=None,
