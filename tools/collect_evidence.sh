@@ -14,7 +14,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > $O/r4_bench_reference.lo
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r4_launches_bench_step.csv python bench.py --steps 2 --warmup 1 --no-eager > $O/r4_bench_under_ncu.log 2>&1
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active
 ncu --metrics $M --clock-control none -c 200 --csv --log-file $O/r4_launches_sngan64.csv python tools/bench_arch.py --arch sngan64 --n 8192 --iters 1 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"b1_fused" -s 2 -c 1 -o $O/r4_b1fused64 python tools/bench_arch.py --arch sngan64 --n 8192 --iters 1 > $O/r4_b1fused64_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"b1_fused" -s 2 -c 1 -f -o $O/r4_b1fused64 python tools/bench_arch.py --arch sngan64 --n 8192 --iters 1 > $O/r4_b1fused64_ncu.log 2>&1
 # D: breakdowns
 python tools/step_breakdown.py > $O/r4_breakdown.log 2>&1
 for a in sngan32 sngan64 dcgan32; do python tools/bench_arch.py --arch $a --n $([ $a = sngan64 ] && echo 8192 || echo 50000) >> $O/r4_arch.log 2>&1; done
