@@ -1789,7 +1789,7 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
   // It is chosen by SHAPE only (any n >= 1), so that a sample's logit never depends on the batch it is evaluated in.
   static const int shared_taps = getenv("SDG_SHARED_TAPS") ? atoi(getenv("SDG_SHARED_TAPS")) : 1;   // 2: 16 x 16 grids only
   const bool grid16 = Hc == 16 && Wc == 16, grid8 = Hc == 8 && Wc == 8 && shared_taps == 1;
-  const bool sh_ok = shared_taps && Cout == 128 && (grid16 || grid8) && !a.general && (p.sc_chunks == 0 || (s2 && grid8)) &&
+  const bool sh_ok = shared_taps && Cout == 128 && (grid16 || grid8) && !a.general && (p.sc_chunks == 0 || s2) &&
                      (s2 || (taps == 9 && !strided)) && p.toff == -1 && (grid16 || !a.img);
   if (swap_mode && g_pair_mode == 1 && (Cout == 128 || (swap64 && Cout == 64)) && !p.pool && !p.box16 && !p.sc_sep && !a.sd &&
       !a.gemm && (p.m_tiles >= 2 || a.res_h16 || sh_ok) && p.total_pixels % 32 == 0 &&
@@ -1848,7 +1848,9 @@ int conv_tc(const TcConv& a, int f16, cudaStream_t s) {
         else map_s2 = map_c;
       } else {
         { int rc = encode_act(&map_c, a.in, f16, a.n, Hin, Win, Cin, Wc, rows_main, 1, es, esx); if (rc) return rc; }
-        map_s2 = map_c;
+        // folded shortcut of a pooled block whose output is one 16 x 16 grid (SNGAN-64 block2.c2): Hc rows per parity plane
+        if (a.sc_in && p.sc_chunks) { int rc = encode_act(&map_s2, a.sc_in, f16, a.n, Hin, Win, a.sc_C, Wc, Hc, 1, es, esx); if (rc) return rc; }
+        else map_s2 = map_c;
       }
       const long long tiles_sh = grid8 ? (a.n + 3) / 4 : a.n;
       const int grid = (int)(tiles_sh < g_num_sms ? tiles_sh : g_num_sms);
