@@ -67,7 +67,9 @@ constexpr int BF_SC_BYTES = 2 * 128 * 16;               // shortcut operand: [k8
 // two rows of 8 pixels fill the 32 banks exactly
 constexpr int BF_PQ_ROWB = 96;
 constexpr int BF_PQ_PLANE = 36 * BF_PQ_ROWB;
-constexpr int BF_P128_PLANE = 34 * BF_PQ_ROWB;          // CH = 128: the same split of its 34 x 20 patch
+constexpr int BF_P_ROWB = 160;                          // CH = 128: one interleaved plane, 34 rows x 20 pixels x (c0, c1, c2, pad): the column-parity
+                                                        // split was measured there too -- 4.8 % MORE cycles per image under ncu (store replays
+                                                        // +200 per image) and 2 % on a 6 250-sample pass, no change on the power-capped 50 k pass
 
 template <int CH>
 struct Bf {
@@ -83,7 +85,7 @@ struct Bf {
   static constexpr int X_ROWS = QUAD ? 36 : 32;         // landing buffer: image rows -2 .. 33 of the quadrant | the image's 32 rows
   static constexpr int X_BYTES = X_ROWS * BF_X_ROWB;
   static constexpr int P_ROWS = QUAD ? 36 : 34;         // patch rows -2 .. 33 | -1 .. 32
-  static constexpr int P_BYTES = 2 * P_ROWS * BF_PQ_ROWB;   // two column-parity planes
+  static constexpr int P_BYTES = QUAD ? 2 * BF_PQ_PLANE : P_ROWS * BF_P_ROWB;
   static constexpr int OFF_T = W_STAGES * BF_W_BYTES;
   static constexpr int OFF_A1 = OFF_T + T_BYTES;
   static constexpr bool ALT = QUAD;                     // the two T-warp sets take alternate batches (below) instead of halves of each
@@ -166,12 +168,10 @@ __device__ __forceinline__ bool bf_pixel(int s, int pr, int b, int m, int& R, in
   bool valid = true;
   if (b == 0) {                                         // the 8-column parity plane: 16 rows x 8 cells
     rr = m >> 3; C = (m & 7) + (1 - s); pc = s;
-  } else {                                              // the 9-column one: cells 0..7 of its 16 rows, then the ninth cell of each
-    const int idx = (b - 1) * 128 + m;                  // (8-cell lane rows: conflict-free gathers from the 96-byte patch rows)
+  } else {                                              // the 9-column one: 144 cells in address order
+    const int idx = (b - 1) * 128 + m;
     valid = idx < 144;
-    if (idx < 128) { rr = idx >> 3; C = idx & 7; }
-    else { rr = idx - 128; C = 8; }
-    pc = 1 - s;
+    rr = idx / 9; C = idx - rr * 9; pc = 1 - s;
   }
   R = rr + (pr ? 0 : 1);
   return valid;
@@ -605,18 +605,15 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
       };
       auto nrm = [](uint8_t u) { return bf_nrm(u); };
       // landed bytes -> (a) normalised 16-bit patch, the first conv's operand values, converted ONCE per byte instead of once per
-      // tap: patch pixel (ry, cx) = image pixel (ry - 1, 15 s - 1 + cx) as (c0, c1, c2, 0), 18 in-image columns per row, stored as
-      // two column-parity planes (entry cx >> 1 of plane cx & 1, 96-byte rows) so that the gathers below, whose lanes step two
-      // columns, read consecutive 8-byte entries; (b) the shortcut operand of tile L: row m = avg_pool2d(normalised x) at output
-      // pixel (m >> 3, 8 s + (m & 7)) as hi / lo pairs
+      // tap: patch pixel (ry, cx) = image pixel (ry - 1, 15 s - 1 + cx) as (c0, c1, c2, 0), 18 in-image columns per row;
+      // (b) the shortcut operand of tile L: row m = avg_pool2d(normalised x) at output pixel (m >> 3, 8 s + (m & 7)) as hi / lo pairs
       auto convert_x = [&](long long L) {
         const uint8_t* raw = smem_gen + BF_OFF_X + XO;
         for (int i = t256; i < 32 * 18; i += BF_T_THREADS) {
           const int row = i / 18, j = i - row * 18;     // j-th in-image pixel of the row: image column (s ? 14 : 0) + j
           const uint8_t* b = raw + row * BF_X_ROWB + 3 * ((s ? 14 : 0) + j) - goff;
           const uint32_t lo = pack_h2<F16>(nrm(b[0]), nrm(b[1])), hi = pack_h2<F16>(nrm(b[2]), 0.f);
-          const int cx = j + (s ? 0 : 1);
-          *reinterpret_cast<uint2*>(smem_gen + BF_OFF_P + (cx & 1) * BF_P128_PLANE + (row + 1) * BF_PQ_ROWB + (cx >> 1) * 8) = make_uint2(lo, hi);
+          *reinterpret_cast<uint2*>(smem_gen + BF_OFF_P + (row + 1) * BF_P_ROWB + (j + (s ? 0 : 1)) * 8) = make_uint2(lo, hi);
         }
         mbar_wait(smem_u32(&bar_sc_free[0]), (uint32_t)((L & 1) ^ 1));  // the previous tile's shortcut MMA has read the buffer
         {
@@ -649,16 +646,13 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
         const bool valid = bf_pixel<false>(s, pr, b, tt, R, C, pc);
         if (valid && !(dbg & 1)) {
           const int y = 2 * R + pr - 1, x = 16 * s - 1 + 2 * C + pc;     // pixel of the tile: rows -1 .. 32, columns 16 s - 1 .. 16 s + 16
-          // tap (ky, kx) reads image pixel (y + ky - 1, x + kx - 1) = patch row y + ky, patch column x - 15 s + kx: columns
-          // kx = 0, 2 are entries e0, e0 + 1 of one plane, kx = 1 is entry (cx0 + 1) >> 1 of the other
-          const int cx0 = x - 15 * s;
-          const uint8_t* base = smem_gen + BF_OFF_P + (cx0 & 1) * BF_P128_PLANE + y * BF_PQ_ROWB + (cx0 >> 1) * 8;
-          const uint8_t* mid = smem_gen + BF_OFF_P + ((cx0 + 1) & 1) * BF_P128_PLANE + y * BF_PQ_ROWB + ((cx0 + 1) >> 1) * 8;
-          auto ld = [](const uint8_t* q_) { return *reinterpret_cast<const uint2*>(q_); };
+          // tap (ky, kx) reads image pixel (y + ky - 1, x + kx - 1) = patch row y + ky, patch column x - 15 s + kx
+          const uint2* row0 = reinterpret_cast<const uint2*>(smem_gen + BF_OFF_P + y * BF_P_ROWB + (x - 15 * s) * 8);
+          const uint2* row1 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(row0) + BF_P_ROWB);
+          const uint2* row2 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(row0) + 2 * BF_P_ROWB);
           uint8_t* row = smem_gen + BF_OFF_A1 + gb * BF_A1_BYTES + tt * 16;
           if (set == 0) {
-            const uint2 a0 = ld(base), a1 = ld(mid), a2 = ld(base + 8);
-            const uint2 b0 = ld(base + BF_PQ_ROWB), b1 = ld(mid + BF_PQ_ROWB), b2 = ld(base + BF_PQ_ROWB + 8);
+            const uint2 a0 = row0[0], a1 = row0[1], a2 = row0[2], b0 = row1[0], b1 = row1[1], b2 = row1[2];
             uint32_t w[8];
             w[0] = a0.x;
             w[1] = __byte_perm(a0.y, a1.x, 0x5410);     // lo16(a0.y) | lo16(a1.x) << 16
@@ -671,8 +665,7 @@ b1_fused_kernel(const __grid_constant__ CUtensorMap map_w2, const BfParams p) {
             *reinterpret_cast<uint4*>(row) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(row + 2048) = make_uint4(w[4], w[5], w[6], w[7]);
           } else {
-            const uint2 b2 = ld(base + BF_PQ_ROWB + 8);
-            const uint2 c0 = ld(base + 2 * BF_PQ_ROWB), c1 = ld(mid + 2 * BF_PQ_ROWB), c2 = ld(base + 2 * BF_PQ_ROWB + 8);
+            const uint2 b2 = row1[2], c0 = row2[0], c1 = row2[1], c2 = row2[2];
             uint32_t w[8];
             w[0] = __byte_perm(b2.x, b2.y, 0x5432);
             w[1] = c0.x;
